@@ -1,0 +1,585 @@
+// comm.cu -- PartitionedDNAMap on one 8xB200 box: one hash shard per GPU (one rank = one process = one GPU),
+// k-mers routed to their owner shard by an NCCL all-to-all over NVLink.
+// Replaces S/ds/PartitionedDNAMap.scala:15-63 (paths relative to /root/reference).
+//
+// Insert pipeline per batch of reads (all ranks in lock step, same number of batches):
+//   route_count  : extract canonical k-mers, histogram by owner                      (stream `route`)
+//   route_scatter: re-extract, write every k-mer into its owner's segment of `send`  (stream `route`)
+//   all-to-all   : counts (P x u64), then grouped ncclSend/ncclRecv of the segments  (stream `route`)
+//   insert       : update(key, 1, _ + 1) for every received key                      (the map's stream)
+// Two buffer sets: batch b+1 is routed and exchanged while batch b is inserted.
+#include <nccl.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "extract.cuh"
+
+namespace gb {
+
+constexpr int MAX_RANKS = 64;
+
+struct Comm {
+    int rank = 0, n_ranks = 1, device = 0;
+    ncclComm_t nccl = nullptr;
+    cudaStream_t stream = nullptr; // routing + collectives
+};
+
+static int nccl_fail(ncclResult_t r, const char *what, const char *file, int line)
+{
+    set_error("NCCL error %d (%s) at %s:%d: %s", (int)r, ncclGetErrorString(r), file, line, what);
+    return GB_E_NCCL;
+}
+#define GB_NCCL(expr)                                                              \
+    do {                                                                           \
+        ncclResult_t _r = (expr);                                                  \
+        if (_r != ncclSuccess) return gb::nccl_fail(_r, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// ---------------------------------------------------------------- routing kernels
+// pass 1: per-owner histogram of the batch (shared-memory histogram, one global atomic per owner per CTA)
+template <bool FIXED, bool V210>
+__global__ void __launch_bounds__(INSERT_THREADS)
+route_count_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes, const unsigned long long *__restrict__ offsets,
+                   unsigned int rec_bytes, long long read0, long long n_reads, int k, unsigned int parts,
+                   unsigned long long *owner_count)
+{
+    __shared__ ReadTile tile;
+    __shared__ unsigned int s_hist[MAX_RANKS];
+    const int tid = threadIdx.x;
+    const int nr = stage_tile<FIXED>(tile, bin, n_bytes, offsets, rec_bytes, read0, n_reads, k);
+    if (nr <= 0) return;
+    if (tid < MAX_RANKS) s_hist[tid] = 0;
+    __syncthreads();
+    const unsigned int total_items = tile.prefix[TILE_READS];
+    for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
+        unsigned long long key[SEG];
+        const int cnt = item_keys<V210>(tile, item, k, key);
+#pragma unroll
+        for (int j = 0; j < SEG; j++)
+            if (j < cnt) atomicAdd(&s_hist[owner_of(mix64(key[j]), parts)], 1u);
+    }
+    __syncthreads();
+    if (tid < (int)parts && s_hist[tid]) atomicAdd(&owner_count[tid], (unsigned long long)s_hist[tid]);
+}
+
+// pass 2: each CTA reserves its share of every owner's segment, then writes the keys
+template <bool FIXED, bool V210>
+__global__ void __launch_bounds__(INSERT_THREADS)
+route_scatter_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes, const unsigned long long *__restrict__ offsets,
+                     unsigned int rec_bytes, long long read0, long long n_reads, int k, unsigned int parts,
+                     const unsigned long long *seg_base, unsigned long long *seg_cursor, unsigned long long *send)
+{
+    __shared__ ReadTile tile;
+    __shared__ unsigned int s_hist[MAX_RANKS];
+    __shared__ unsigned long long s_base[MAX_RANKS];
+    const int tid = threadIdx.x;
+    const int nr = stage_tile<FIXED>(tile, bin, n_bytes, offsets, rec_bytes, read0, n_reads, k);
+    if (nr <= 0) return;
+    if (tid < MAX_RANKS) s_hist[tid] = 0;
+    __syncthreads();
+    const unsigned int total_items = tile.prefix[TILE_READS];
+    for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
+        unsigned long long key[SEG];
+        const int cnt = item_keys<V210>(tile, item, k, key);
+#pragma unroll
+        for (int j = 0; j < SEG; j++)
+            if (j < cnt) atomicAdd(&s_hist[owner_of(mix64(key[j]), parts)], 1u);
+    }
+    __syncthreads();
+    if (tid < (int)parts) {
+        s_base[tid] = seg_base[tid] + (s_hist[tid] ? atomicAdd(&seg_cursor[tid], (unsigned long long)s_hist[tid]) : 0);
+        s_hist[tid] = 0;
+    }
+    __syncthreads();
+    for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
+        unsigned long long key[SEG];
+        const int cnt = item_keys<V210>(tile, item, k, key);
+#pragma unroll
+        for (int j = 0; j < SEG; j++)
+            if (j < cnt) {
+                unsigned int o = owner_of(mix64(key[j]), parts);
+                send[s_base[o] + atomicAdd(&s_hist[o], 1u)] = key[j];
+            }
+    }
+}
+
+__global__ void owner_kernel(const unsigned long long *keys, long long n, unsigned int parts, int *owner)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) owner[i] = (int)owner_of(mix64(keys[i]), parts);
+}
+
+// ---------------------------------------------------------------- host helpers
+
+// variable all-to-all of u64 elements: send segment p (send_off[p], send_cnt[p]) goes to rank p
+static int all_to_all_v(Comm *c, const unsigned long long *send, const unsigned long long *send_off, const unsigned long long *send_cnt,
+                        unsigned long long *recv, const unsigned long long *recv_off, const unsigned long long *recv_cnt,
+                        ncclDataType_t type)
+{
+    GB_NCCL(ncclGroupStart());
+    for (int p = 0; p < c->n_ranks; p++) {
+        if (send_cnt[p]) GB_NCCL(ncclSend(send + send_off[p], send_cnt[p], type, p, c->nccl, c->stream));
+        if (recv_cnt[p]) GB_NCCL(ncclRecv(recv + recv_off[p], recv_cnt[p], type, p, c->nccl, c->stream));
+    }
+    GB_NCCL(ncclGroupEnd());
+    return GB_OK;
+}
+
+// every rank contributes P counts; afterwards recv_cnt[p] = what rank p sends to me
+static int exchange_counts(Comm *c, unsigned long long *d_send_cnt, unsigned long long *d_recv_cnt,
+                           unsigned long long *h_send_cnt, unsigned long long *h_recv_cnt)
+{
+    const int P = c->n_ranks;
+    GB_NCCL(ncclGroupStart());
+    for (int p = 0; p < P; p++) {
+        GB_NCCL(ncclSend(d_send_cnt + p, 1, ncclUint64, p, c->nccl, c->stream));
+        GB_NCCL(ncclRecv(d_recv_cnt + p, 1, ncclUint64, p, c->nccl, c->stream));
+    }
+    GB_NCCL(ncclGroupEnd());
+    GB_CUDA(cudaMemcpyAsync(h_send_cnt, d_send_cnt, P * 8, cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(cudaMemcpyAsync(h_recv_cnt, d_recv_cnt, P * 8, cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    return GB_OK;
+}
+
+static int all_reduce_i64(Comm *c, int64_t *v, ncclRedOp_t op)
+{
+    DeviceBuf d;
+    GB_TRY(d.alloc(8));
+    GB_CUDA(cudaMemcpyAsync(d.p, v, 8, cudaMemcpyHostToDevice, c->stream));
+    GB_NCCL(ncclAllReduce(d.p, d.p, 1, ncclInt64, op, c->nccl, c->stream));
+    GB_CUDA(cudaMemcpyAsync(v, d.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    return GB_OK;
+}
+
+struct BatchBufs {
+    unsigned long long *send = nullptr, *recv = nullptr;
+    size_t send_cap = 0, recv_cap = 0;
+    unsigned long long *d_cnt = nullptr; // [0..P) owner counts, [P..2P) seg base, [2P..3P) cursors, [3P..4P) recv counts
+    cudaEvent_t exchanged = nullptr, inserted = nullptr;
+    bool in_flight = false;
+    int64_t recv_total = 0;
+    ~BatchBufs()
+    {
+        if (send) cudaFree(send);
+        if (recv) cudaFree(recv);
+        if (d_cnt) cudaFree(d_cnt);
+        if (exchanged) cudaEventDestroy(exchanged);
+        if (inserted) cudaEventDestroy(inserted);
+    }
+    int ensure(size_t ns, size_t nr)
+    {
+        if (ns > send_cap) {
+            if (send) GB_CUDA(cudaFree(send));
+            send = nullptr;
+            send_cap = ns + ns / 8 + 1024;
+            GB_CUDA(cudaMalloc((void **)&send, send_cap * 8));
+        }
+        if (nr > recv_cap) {
+            if (recv) GB_CUDA(cudaFree(recv));
+            recv = nullptr;
+            recv_cap = nr + nr / 8 + 1024;
+            GB_CUDA(cudaMalloc((void **)&recv, recv_cap * 8));
+        }
+        return GB_OK;
+    }
+};
+
+// wait for every in-flight insert, fold the new-key counter into m->size
+static int drain(Map *m, BatchBufs bufs[2])
+{
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    unsigned long long c[4];
+    GB_TRY(map_read_counters(m, c));
+    m->size += (int64_t)c[0];
+    GB_TRY(map_zero_counters(m));
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    bufs[0].in_flight = bufs[1].in_flight = false;
+    return GB_OK;
+}
+
+template <bool FIXED, bool V210>
+static int pmap_insert_t(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off, unsigned int rec,
+                         unsigned int len0, int64_t n_reads, const int64_t *h_win_prefix, int64_t *n_windows)
+{
+    Comm *c = m->comm;
+    const int P = c->n_ranks;
+    const int k = m->k;
+    // batches of reads: bounded staging memory, and enough of them to overlap exchange with insert
+    const int64_t win_max = FIXED ? std::max<int64_t>(0, (int64_t)len0 - k + 1) : (255 - k + 1);
+    const int64_t batch_reads = std::max<int64_t>(TILE_READS, ((int64_t)(48ll << 20) / std::max<int64_t>(win_max, 1)) / TILE_READS * TILE_READS);
+    int64_t my_batches = (n_reads + batch_reads - 1) / batch_reads, batches = my_batches;
+    GB_TRY(all_reduce_i64(c, &batches, ncclMax));
+
+    BatchBufs bufs[2];
+    for (int i = 0; i < 2; i++) {
+        GB_CUDA(cudaMalloc((void **)&bufs[i].d_cnt, 4 * MAX_RANKS * 8));
+        GB_CUDA(cudaEventCreateWithFlags(&bufs[i].exchanged, cudaEventDisableTiming));
+        GB_CUDA(cudaEventCreateWithFlags(&bufs[i].inserted, cudaEventDisableTiming));
+    }
+    GB_TRY(map_zero_counters(m));
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    GB_CUDA(cudaEventRecord(m->ev0, m->stream));
+
+    int64_t windows = 0, pending_upper = 0; // pending_upper: keys handed to inserts not yet folded into m->size
+    std::vector<unsigned long long> h_cnt(4 * MAX_RANKS);
+    for (int64_t b = 0; b < batches; b++) {
+        BatchBufs &B = bufs[b & 1];
+        const int64_t r0 = std::min(n_reads, b * batch_reads), r1 = std::min(n_reads, r0 + batch_reads), nr = r1 - r0;
+        const int64_t w_upper = FIXED ? nr * win_max : (h_win_prefix ? h_win_prefix[r1] - h_win_prefix[r0] : nr * win_max);
+        windows += FIXED || h_win_prefix ? w_upper : 0;
+        if (B.in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, B.inserted, 0)); // its buffers are being read
+        GB_TRY(B.ensure((size_t)w_upper, 0));
+        unsigned long long *cnt = B.d_cnt, *seg = B.d_cnt + MAX_RANKS, *cur = B.d_cnt + 2 * MAX_RANKS, *rcnt = B.d_cnt + 3 * MAX_RANKS;
+        GB_CUDA(cudaMemsetAsync(B.d_cnt, 0, 4 * MAX_RANKS * 8, c->stream));
+        const unsigned int grid = (unsigned int)((nr + TILE_READS - 1) / TILE_READS);
+        if (nr > 0) {
+            route_count_kernel<FIXED, V210><<<grid, INSERT_THREADS, 0, c->stream>>>(d_bin, n_bytes, d_off, rec, r0, nr, k, (unsigned int)P, cnt);
+            GB_LAUNCHED();
+        }
+        GB_TRY(exchange_counts(c, cnt, rcnt, h_cnt.data(), h_cnt.data() + MAX_RANKS));
+        unsigned long long *h_send = h_cnt.data(), *h_recv = h_cnt.data() + MAX_RANKS;
+        unsigned long long *h_soff = h_cnt.data() + 2 * MAX_RANKS, *h_roff = h_cnt.data() + 3 * MAX_RANKS;
+        unsigned long long st = 0, rt = 0;
+        for (int p = 0; p < P; p++) { h_soff[p] = st; st += h_send[p]; h_roff[p] = rt; rt += h_recv[p]; }
+        GB_TRY(B.ensure(0, (size_t)rt));
+        GB_CUDA(cudaMemcpyAsync(seg, h_soff, P * 8, cudaMemcpyHostToDevice, c->stream));
+        if (nr > 0) {
+            route_scatter_kernel<FIXED, V210><<<grid, INSERT_THREADS, 0, c->stream>>>(d_bin, n_bytes, d_off, rec, r0, nr, k, (unsigned int)P, seg, cur, B.send);
+            GB_LAUNCHED();
+        }
+        GB_TRY(all_to_all_v(c, B.send, h_soff, h_send, B.recv, h_roff, h_recv, ncclUint64));
+        GB_CUDA(cudaEventRecord(B.exchanged, c->stream));
+
+        // room for the received keys (every one may be new); grow only with the pipeline drained
+        int64_t cap = (int64_t)1 << m->bits;
+        if ((int64_t)(cap * 0.9) - m->size - pending_upper < (int64_t)rt || (m->size + pending_upper) * 10 > cap * 7) {
+            GB_TRY(drain(m, bufs));
+            pending_upper = 0;
+            int64_t budget = 0;
+            GB_TRY(map_budget(m, (int64_t)rt, &budget));
+            while (budget < (int64_t)rt) { // map_budget guarantees only a minimum batch: force the size we need
+                GB_TRY(map_rebuild(m, m->bits + 1, false, 0));
+                budget = (int64_t)(((int64_t)1 << m->bits) * 0.9) - m->size;
+            }
+        }
+        GB_CUDA(cudaStreamWaitEvent(m->stream, B.exchanged, 0));
+        GB_TRY(map_launch_update_counts(m, B.recv, (int64_t)rt, m->stream));
+        GB_CUDA(cudaEventRecord(B.inserted, m->stream));
+        B.in_flight = true;
+        B.recv_total = (int64_t)rt;
+        pending_upper += (int64_t)rt;
+    }
+    GB_CUDA(cudaEventRecord(m->ev1, m->stream));
+    GB_TRY(drain(m, bufs));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    GB_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+    m->last_insert_ns = (int64_t)(ms * 1e6);
+    m->windows += windows;
+    if (n_windows) *n_windows = windows;
+    return GB_OK;
+}
+
+static int check_pmap(gb_map *h, Map **m)
+{
+    GB_TRY(check_map(h, m));
+    if (!(*m)->comm) { set_error("map is not bound to a communicator (use gb_pmap_create)"); return GB_E_STATE; }
+    return GB_OK;
+}
+
+__global__ void count_windows_kernel(const uint8_t *bin, const unsigned long long *offsets, long long n_reads, int k,
+                                     unsigned long long *total)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long w = 0;
+    if (i < n_reads) {
+        int len = bin[offsets[i]];
+        w = len >= k ? len - k + 1 : 0;
+    }
+    w = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)w);
+    if ((threadIdx.x & 31) == 0 && w) atomicAdd(total, w);
+}
+
+} // namespace gb
+
+using namespace gb;
+
+extern "C" {
+
+int gb_comm_unique_id(uint8_t id[GB_UNIQUE_ID_BYTES])
+{
+    if (!id) { set_error("null argument"); return GB_E_ARG; }
+    static_assert(sizeof(ncclUniqueId) <= GB_UNIQUE_ID_BYTES, "unique id does not fit");
+    ncclUniqueId u;
+    GB_NCCL(ncclGetUniqueId(&u));
+    memset(id, 0, GB_UNIQUE_ID_BYTES);
+    memcpy(id, &u, sizeof u);
+    return GB_OK;
+}
+
+int gb_comm_create(const uint8_t id[GB_UNIQUE_ID_BYTES], int rank, int n_ranks, int device, gb_comm **out)
+{
+    if (!id || !out) { set_error("null argument"); return GB_E_ARG; }
+    *out = nullptr;
+    if (n_ranks < 1 || n_ranks > MAX_RANKS || rank < 0 || rank >= n_ranks) { set_error("bad rank %d of %d", rank, n_ranks); return GB_E_ARG; }
+    int ndev = 0;
+    GB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("device %d not present (%d devices)", device, ndev); return GB_E_CUDA; }
+    GB_CUDA(cudaSetDevice(device));
+    Comm *c = new Comm();
+    c->rank = rank; c->n_ranks = n_ranks; c->device = device;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    ncclResult_t r = ncclCommInitRank(&c->nccl, n_ranks, u, rank);
+    if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank", __FILE__, __LINE__); }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        ncclCommDestroy(c->nccl);
+        delete c;
+        set_error("stream creation failed");
+        return GB_E_CUDA;
+    }
+    *out = reinterpret_cast<gb_comm *>(c);
+    return GB_OK;
+}
+
+int gb_comm_destroy(gb_comm *h)
+{
+    if (!h) return GB_OK;
+    Comm *c = reinterpret_cast<Comm *>(h);
+    cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->nccl) ncclCommDestroy(c->nccl);
+    delete c;
+    return GB_OK;
+}
+
+int gb_pmap_create(gb_comm *ch, int k, int64_t min_capacity_per_shard, uint32_t flags, gb_map **out)
+{
+    if (!ch) { set_error("null communicator"); return GB_E_ARG; }
+    Comm *c = reinterpret_cast<Comm *>(ch);
+    GB_TRY(gb_map_create(k, min_capacity_per_shard, c->device, flags, out));
+    reinterpret_cast<Map *>(*out)->comm = c;
+    return GB_OK;
+}
+
+int gb_pmap_insert_reads_device(gb_map *h, const uint8_t *d_bin, size_t n_bytes, const uint64_t *d_offsets, int64_t n_reads,
+                                int64_t *n_windows)
+{
+    Map *m;
+    GB_TRY(check_pmap(h, &m));
+    if (n_windows) *n_windows = 0;
+    if (n_reads < 0 || (!d_bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
+    // NOTE: collective -- a rank with no reads still takes part in every exchange
+    if (d_offsets || n_reads == 0) {
+        int64_t w = 0;
+        if (n_reads) {
+            DeviceBuf tot;
+            GB_TRY(tot.alloc(8));
+            GB_CUDA(cudaMemsetAsync(tot.p, 0, 8, m->stream));
+            count_windows_kernel<<<(unsigned int)((n_reads + 255) / 256), 256, 0, m->stream>>>(d_bin, (const unsigned long long *)d_offsets, n_reads, m->k, (unsigned long long *)tot.p);
+            GB_LAUNCHED();
+            GB_CUDA(cudaMemcpyAsync(&w, tot.p, 8, cudaMemcpyDeviceToHost, m->stream));
+            GB_CUDA(cudaStreamSynchronize(m->stream));
+        }
+        int r = m->v210 ? pmap_insert_t<false, true>(m, d_bin, n_bytes, (const unsigned long long *)d_offsets, 0, 0, n_reads, nullptr, nullptr)
+                        : pmap_insert_t<false, false>(m, d_bin, n_bytes, (const unsigned long long *)d_offsets, 0, 0, n_reads, nullptr, nullptr);
+        if (r == GB_OK) { m->windows += w; if (n_windows) *n_windows = w; }
+        return r;
+    }
+    uint8_t len0 = 0;
+    GB_CUDA(cudaMemcpyAsync(&len0, d_bin, 1, cudaMemcpyDeviceToHost, m->stream));
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    unsigned int rec = 1 + (len0 + 3) / 4;
+    if ((unsigned long long)n_reads * rec > n_bytes) { set_error("truncated .bin stream"); return GB_E_ARG; }
+    m->fixed_stride = 1;
+    return m->v210 ? pmap_insert_t<true, true>(m, d_bin, n_bytes, nullptr, rec, len0, n_reads, nullptr, n_windows)
+                   : pmap_insert_t<true, false>(m, d_bin, n_bytes, nullptr, rec, len0, n_reads, nullptr, n_windows);
+}
+
+int gb_pmap_insert_reads(gb_map *h, const uint8_t *bin, size_t n_bytes, int64_t n_reads, int64_t *n_windows)
+{
+    Map *m;
+    GB_TRY(check_pmap(h, &m));
+    if (n_windows) *n_windows = 0;
+    if (n_reads < 0 || (!bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
+    std::vector<unsigned long long> off;
+    std::vector<int64_t> winp;
+    GB_TRY(scan_records(bin, n_bytes, n_reads, m->k, off, winp));
+    const size_t used = (size_t)off[(size_t)n_reads];
+    // fixed stride iff every record has the first record's length
+    bool fixed = n_reads > 0;
+    const unsigned int len0 = n_reads ? bin[0] : 0, rec = 1 + (len0 + 3) / 4;
+    for (int64_t r = 0; fixed && r < n_reads; r++) fixed = bin[off[(size_t)r]] == len0;
+    DeviceBuf d_bin, d_off;
+    GB_TRY(d_bin.alloc(used + 16));
+    if (used) GB_CUDA(cudaMemcpyAsync(d_bin.p, bin, used, cudaMemcpyHostToDevice, m->stream));
+    GB_TRY(d_off.alloc(off.size() * 8));
+    GB_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, m->stream));
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    m->fixed_stride = fixed;
+    if (fixed)
+        return m->v210 ? pmap_insert_t<true, true>(m, (const uint8_t *)d_bin.p, used, nullptr, rec, len0, n_reads, nullptr, n_windows)
+                       : pmap_insert_t<true, false>(m, (const uint8_t *)d_bin.p, used, nullptr, rec, len0, n_reads, nullptr, n_windows);
+    return m->v210 ? pmap_insert_t<false, true>(m, (const uint8_t *)d_bin.p, used, (const unsigned long long *)d_off.p, 0, 0, n_reads, winp.data(), n_windows)
+                   : pmap_insert_t<false, false>(m, (const uint8_t *)d_bin.p, used, (const unsigned long long *)d_off.p, 0, 0, n_reads, winp.data(), n_windows);
+}
+
+int gb_pmap_size(gb_map *h, int64_t *size)
+{
+    Map *m;
+    GB_TRY(check_pmap(h, &m));
+    if (!size) { set_error("null argument"); return GB_E_ARG; }
+    int64_t s = m->size;
+    GB_TRY(all_reduce_i64(m->comm, &s, ncclSum));
+    *size = s;
+    return GB_OK;
+}
+
+int gb_pmap_delete_below(gb_map *h, int32_t min_count)
+{
+    Map *m;
+    GB_TRY(check_pmap(h, &m));
+    return gb_map_delete_below(h, min_count);
+}
+
+int gb_pmap_owner(gb_map *h, const uint64_t *keys, int64_t n, int32_t *owner)
+{
+    Map *m;
+    GB_TRY(check_pmap(h, &m));
+    if (n < 0 || (n > 0 && (!keys || !owner))) { set_error("bad arguments"); return GB_E_ARG; }
+    return gb_owner_of(keys, n, m->comm->n_ranks, owner);
+}
+
+// partition(key) (PartitionedDNAMap.scala:60-63); pure host arithmetic, usable without a GPU
+int gb_owner_of(const uint64_t *keys, int64_t n, int n_parts, int32_t *owner)
+{
+    if (n < 0 || n_parts < 1 || (n > 0 && (!keys || !owner))) { set_error("bad arguments"); return GB_E_ARG; }
+    for (int64_t i = 0; i < n; i++) owner[i] = (int32_t)owner_of(mix64(keys[i]), (unsigned int)n_parts);
+    return GB_OK;
+}
+
+int gb_pmap_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, uint8_t *found)
+{
+    Map *m;
+    GB_TRY(check_pmap(h, &m));
+    if (n < 0 || (n > 0 && !keys)) { set_error("bad arguments"); return GB_E_ARG; }
+    Comm *c = m->comm;
+    const int P = c->n_ranks;
+    // bucket the queries by owner on the host (they come from the host), remember where each one came from
+    std::vector<unsigned long long> h_send((size_t)n), scnt(P, 0), soff(P, 0), rcnt(P, 0), roff(P, 0), fill(P, 0);
+    std::vector<int64_t> origin((size_t)n);
+    std::vector<int32_t> own((size_t)n);
+    for (int64_t i = 0; i < n; i++) { own[(size_t)i] = (int32_t)owner_of(mix64(keys[i]), (unsigned int)P); scnt[own[(size_t)i]]++; }
+    unsigned long long st = 0;
+    for (int p = 0; p < P; p++) { soff[p] = st; st += scnt[p]; }
+    for (int64_t i = 0; i < n; i++) {
+        size_t pos = (size_t)(soff[own[(size_t)i]] + fill[own[(size_t)i]]++);
+        h_send[pos] = keys[i];
+        origin[pos] = i;
+    }
+    DeviceBuf d_cnt, d_send, d_recv, d_ans, d_back;
+    GB_TRY(d_cnt.alloc(2 * MAX_RANKS * 8));
+    GB_CUDA(cudaMemcpyAsync(d_cnt.p, scnt.data(), P * 8, cudaMemcpyHostToDevice, c->stream));
+    std::vector<unsigned long long> tmp(P);
+    GB_TRY(exchange_counts(c, (unsigned long long *)d_cnt.p, (unsigned long long *)d_cnt.p + MAX_RANKS, tmp.data(), rcnt.data()));
+    unsigned long long rt = 0;
+    for (int p = 0; p < P; p++) { roff[p] = rt; rt += rcnt[p]; }
+    GB_TRY(d_send.alloc((size_t)n * 8));
+    GB_TRY(d_recv.alloc((size_t)rt * 8));
+    GB_TRY(d_ans.alloc((size_t)rt * 8));
+    GB_TRY(d_back.alloc((size_t)n * 8));
+    if (n) GB_CUDA(cudaMemcpyAsync(d_send.p, h_send.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    GB_TRY(all_to_all_v(c, (unsigned long long *)d_send.p, soff.data(), scnt.data(), (unsigned long long *)d_recv.p, roff.data(), rcnt.data(), ncclUint64));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    // local probe: answers packed as found << 32 | count
+    std::vector<unsigned long long> h_q((size_t)rt), h_a((size_t)rt);
+    if (rt) {
+        GB_CUDA(cudaMemcpy(h_q.data(), d_recv.p, (size_t)rt * 8, cudaMemcpyDeviceToHost));
+        std::vector<int32_t> cnts((size_t)rt);
+        std::vector<uint8_t> fnd((size_t)rt);
+        GB_TRY(gb_map_lookup(h, (const uint64_t *)h_q.data(), (int64_t)rt, cnts.data(), fnd.data()));
+        for (size_t i = 0; i < (size_t)rt; i++) h_a[i] = ((unsigned long long)fnd[i] << 32) | (uint32_t)cnts[i];
+        GB_CUDA(cudaMemcpyAsync(d_ans.p, h_a.data(), (size_t)rt * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    GB_TRY(all_to_all_v(c, (unsigned long long *)d_ans.p, roff.data(), rcnt.data(), (unsigned long long *)d_back.p, soff.data(), scnt.data(), ncclUint64));
+    std::vector<unsigned long long> h_back((size_t)n);
+    if (n) GB_CUDA(cudaMemcpyAsync(h_back.data(), d_back.p, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t pos = 0; pos < n; pos++) {
+        int64_t i = origin[(size_t)pos];
+        if (counts) counts[i] = (int32_t)(uint32_t)h_back[(size_t)pos];
+        if (found) found[i] = (uint8_t)(h_back[(size_t)pos] >> 32);
+    }
+    return GB_OK;
+}
+
+// Graph.buildGraph over all shards: every shard's (key, count) pairs are all-gathered into a replica of the whole
+// filtered table on every rank, and the single-GPU build runs on the replica (identical result on every rank).
+int gb_pmap_graph_build(gb_map *h, gb_graph **out)
+{
+    Map *m;
+    GB_TRY(check_pmap(h, &m));
+    if (!out) { set_error("null out pointer"); return GB_E_ARG; }
+    *out = nullptr;
+    Comm *c = m->comm;
+    const int P = c->n_ranks;
+    int64_t total = m->size, dual = m->noncanonical;
+    GB_TRY(all_reduce_i64(c, &total, ncclSum));
+    GB_TRY(all_reduce_i64(c, &dual, ncclMax));
+    // per-rank sizes
+    DeviceBuf d_sizes;
+    GB_TRY(d_sizes.alloc(MAX_RANKS * 8 * 2));
+    unsigned long long mine = (unsigned long long)m->size;
+    GB_CUDA(cudaMemcpyAsync(d_sizes.p, &mine, 8, cudaMemcpyHostToDevice, c->stream));
+    GB_NCCL(ncclAllGather(d_sizes.p, (unsigned long long *)d_sizes.p + MAX_RANKS, 1, ncclUint64, c->nccl, c->stream));
+    std::vector<unsigned long long> sizes(P), offs(P);
+    GB_CUDA(cudaMemcpyAsync(sizes.data(), (unsigned long long *)d_sizes.p + MAX_RANKS, P * 8, cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned long long t = 0;
+    for (int p = 0; p < P; p++) { offs[p] = t; t += sizes[p]; }
+
+    // local export to device arrays (through the host-free path: export kernel writes device buffers)
+    DeviceBuf all_keys, all_vals;
+    GB_TRY(all_keys.alloc((size_t)t * 8));
+    GB_TRY(all_vals.alloc((size_t)t * 4));
+    {
+        std::vector<uint64_t> hk((size_t)m->size);
+        std::vector<int32_t> hv((size_t)m->size);
+        int64_t nn = 0;
+        GB_TRY(gb_map_export(h, hk.data(), hv.data(), m->size, &nn));
+        if (nn) {
+            GB_CUDA(cudaMemcpyAsync((unsigned long long *)all_keys.p + offs[c->rank], hk.data(), (size_t)nn * 8, cudaMemcpyHostToDevice, c->stream));
+            GB_CUDA(cudaMemcpyAsync((int *)all_vals.p + offs[c->rank], hv.data(), (size_t)nn * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    GB_NCCL(ncclGroupStart());
+    for (int p = 0; p < P; p++) {
+        if (!sizes[p]) continue;
+        GB_NCCL(ncclBroadcast((unsigned long long *)all_keys.p + offs[p], (unsigned long long *)all_keys.p + offs[p], sizes[p], ncclUint64, p, c->nccl, c->stream));
+        GB_NCCL(ncclBroadcast((int *)all_vals.p + offs[p], (int *)all_vals.p + offs[p], sizes[p], ncclInt32, p, c->nccl, c->stream));
+    }
+    GB_NCCL(ncclGroupEnd());
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+
+    gb_map *rh = nullptr;
+    GB_TRY(gb_map_create(m->k, (int64_t)t, m->device, m->v210 ? GB_FLAG_HASH_SCALA_210 : 0, &rh));
+    Map *r = reinterpret_cast<Map *>(rh);
+    r->noncanonical = dual != 0;
+    int rc = map_zero_counters(r);
+    if (rc == GB_OK) rc = map_launch_update_set(r, (const unsigned long long *)all_keys.p, (const int *)all_vals.p, (int64_t)t, r->stream);
+    unsigned long long cn[4];
+    if (rc == GB_OK) rc = map_read_counters(r, cn);
+    if (rc == GB_OK) {
+        r->size = (int64_t)cn[0];
+        rc = gb_graph_build(rh, out);
+    }
+    gb_map_destroy(rh);
+    return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,255 @@
+// common.cuh -- shared device/host helpers of libgenome_b200 (sm_100a only).
+// Citations: paths relative to /root/reference, S/ = src/main/scala/ru/ifmo/genome/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/genome_b200.h"
+
+namespace gb {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define GB_CUDA(expr)                                                         \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return gb::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+// every kernel launch of the library goes through this: counts it (gb_launch_count) and checks the launch
+void note_launch();
+#define GB_LAUNCHED()                      \
+    do {                                   \
+        gb::note_launch();                 \
+        GB_CUDA(cudaGetLastError());       \
+    } while (0)
+
+#define GB_TRY(expr)                \
+    do {                            \
+        int _r = (expr);            \
+        if (_r != GB_OK) return _r; \
+    } while (0)
+
+// ---------------------------------------------------------------- table layout
+// One 16-byte slot per key: a 32-byte DRAM sector holds two slots, so the key compare, the count
+// update and the graph-phase vertex id of one k-mer touch exactly one sector.
+struct __align__(16) Slot {
+    unsigned long long key; // EMPTY_KEY when free; k <= 31 keys use at most 62 bits
+    int count;              // DNAMap[Int] value
+    unsigned int vid;       // dense vertex id, assigned by gb_graph_build
+};
+static_assert(sizeof(Slot) == 16, "slot must be 16 bytes");
+
+constexpr unsigned long long EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned int NONE32 = 0xFFFFFFFFu;
+
+constexpr int SM_COUNT = 148; // B200
+
+// ---------------------------------------------------------------- k-mer arithmetic (device + host)
+#define GB_HD __host__ __device__ __forceinline__
+
+// Long1DNASeq.hashCode = long.## (S/dna/DNASeq.scala:103), scala-library 2.9.1: iv = (int)v;
+// if (iv == v) iv else (int)(v ^ (v >>> 32)).  For 0 <= v < 2^62 both branches equal (int)(v ^ (v >>> 32)).
+// V210 = scala >= 2.10: low ^ (high + (low >>> 31)).
+template <bool V210>
+GB_HD int scala_hash(unsigned long long v)
+{
+    unsigned int low = (unsigned int)v, high = (unsigned int)(v >> 32);
+    if (V210) return (int)(low ^ (high + (low >> 31)));
+    return (int)(low ^ high);
+}
+
+// Long1DNASeq.complement (165-168) then .reverse (155-163): 2-bit groups reversed, then aligned down.
+GB_HD unsigned long long revcomp(unsigned long long x, int k)
+{
+    unsigned long long v = ~x; // complement = x ^ mask; the bits above 2k are shifted out below
+#ifdef __CUDA_ARCH__
+    v = __brevll(v);
+#else
+    v = ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
+    v = ((v >> 2) & 0x3333333333333333ull) | ((v & 0x3333333333333333ull) << 2);
+    v = ((v >> 4) & 0x0f0f0f0f0f0f0f0full) | ((v & 0x0f0f0f0f0f0f0f0full) << 4);
+    v = ((v >> 8) & 0x00ff00ff00ff00ffull) | ((v & 0x00ff00ff00ff00ffull) << 8);
+    v = ((v >> 16) & 0x0000ffff0000ffffull) | ((v & 0x0000ffff0000ffffull) << 16);
+    v = (v >> 32) | (v << 32);
+#endif
+    // full bit reversal also swapped the two bits of every base: swap them back
+    v = ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
+    return v >> (64 - 2 * k);
+}
+
+// FreqFilter.add (S/data/FreqFilter.scala:31-32): signed 32-bit compare, tie => reverse complement
+template <bool V210>
+GB_HD unsigned long long canonical(unsigned long long x, unsigned long long rc)
+{
+    return scala_hash<V210>(x) < scala_hash<V210>(rc) ? x : rc;
+}
+
+// x.drop(1) :+ base (Graph.scala:279) and base +: x.take(k-1) (Graph.scala:273)
+GB_HD unsigned long long kmer_append(unsigned long long x, int k, unsigned int b)
+{
+    return (x >> 2) | ((unsigned long long)b << (2 * (k - 1)));
+}
+GB_HD unsigned long long kmer_prepend(unsigned long long x, int k, unsigned int b)
+{
+    return ((x << 2) & ((1ull << (2 * k)) - 1)) | b;
+}
+
+// slot / owner hash: free choice, unobservable through DNAMap
+GB_HD unsigned long long mix64(unsigned long long x)
+{
+    x *= 0x9E3779B97F4A7C15ull;
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 29;
+    return x;
+}
+GB_HD unsigned long long slot_of(unsigned long long h, int bits) { return h >> (64 - bits); }
+GB_HD unsigned int owner_of(unsigned long long h, unsigned int parts)
+{
+    return (unsigned int)(((h & 0xFFFFFFFFull) * parts) >> 32);
+}
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------- device memory access helpers
+// table slots are read with L1 bypass (random access, no reuse inside an SM; L1 is not coherent)
+__device__ __forceinline__ Slot load_slot(const Slot *p)
+{
+    Slot s;
+    unsigned int lo, hi, c, v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(c), "=r"(v) : "l"(p));
+    s.key = ((unsigned long long)hi << 32) | lo;
+    s.count = (int)c;
+    s.vid = v;
+    return s;
+}
+
+__device__ __forceinline__ void red_add_s32(int *p, int v)
+{
+    asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// probe for `key`; returns slot index or -1
+__device__ __forceinline__ long long probe_find(const Slot *table, int bits, unsigned long long key, Slot *out)
+{
+    unsigned long long mask = (1ull << bits) - 1;
+    unsigned long long i = slot_of(mix64(key), bits);
+    for (;;) { // the table is never full (map_budget), so an EMPTY slot always ends the probe
+        Slot s = load_slot(table + i);
+        if (s.key == key) { *out = s; return (long long)i; }
+        if (s.key == EMPTY_KEY) return -1;
+        i = (i + 1) & mask;
+    }
+}
+
+// Graph.buildGraph.contains (S/data/graph/Graph.scala:270): q is present if q or rc(q) is a stored key.
+// Keys inserted by FreqFilter.add are stored in canonical orientation, so one probe of canonical(q)
+// decides; both orientations are probed only when the two hashes tie (FreqFilter's rule then stores
+// either orientation) or when keys were inserted as-is through update (dual).  If both
+// orientations are stored, the numerically smaller key is the PRIMARY one: it alone carries a vertex id.
+// On success *slot is the primary stored slot and *strand = 1 when that stored key is rc(q) != q.
+template <bool V210>
+__device__ __forceinline__ bool find_oriented(const Slot *table, int bits, int k, bool dual,
+                                              unsigned long long q, Slot *slot, unsigned int *strand)
+{
+    unsigned long long r = revcomp(q, k);
+    int hq = scala_hash<V210>(q), hr = scala_hash<V210>(r);
+    if (!dual && hq != hr) {
+        unsigned long long c = hq < hr ? q : r;
+        if (probe_find(table, bits, c, slot) < 0) return false;
+        *strand = c != q;
+        return true;
+    }
+    Slot sq, sr;
+    bool fq = probe_find(table, bits, q, &sq) >= 0;
+    bool fr = r != q && probe_find(table, bits, r, &sr) >= 0;
+    if (!fq && !fr) return false;
+    bool use_r = fr && (!fq || r < q);
+    *slot = use_r ? sr : sq;
+    *strand = use_r;
+    return true;
+}
+
+// a stored key is SECONDARY (no vertex of its own) when rc(key) is stored too and is numerically smaller
+template <bool V210>
+__device__ __forceinline__ bool is_secondary(const Slot *table, int bits, int k, bool dual, unsigned long long key)
+{
+    unsigned long long r = revcomp(key, k);
+    if (r >= key) return false;
+    if (!dual && scala_hash<V210>(key) != scala_hash<V210>(r)) return false;
+    Slot s;
+    return probe_find(table, bits, r, &s) >= 0;
+}
+#endif
+
+// ---------------------------------------------------------------- host-side handle state
+struct Comm;
+
+struct Map {
+    int k = 0;
+    int device = 0;
+    bool v210 = false;
+    bool noncanonical = false; // keys were inserted through update/update_counts as-is
+    int bits = 0;              // capacity = 1 << bits
+    Slot *table = nullptr;
+    int64_t size = 0;          // live keys (host mirror, exact after every call)
+    int64_t grows = 0, windows = 0, last_insert_ns = 0, fixed_stride = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, t0 = nullptr, t1 = nullptr;
+    // scratch
+    unsigned long long *d_counters = nullptr; // [0] new keys [1] overflow count [2] flags [3] windows
+    unsigned long long *d_overflow = nullptr; // overflow keys (cap overflow_cap)
+    int64_t overflow_cap = 0;
+    Comm *comm = nullptr;
+};
+
+int map_reserve(Map *m, int64_t want_keys);
+int check_map(gb_map *h, Map **m);
+
+struct DeviceBuf {
+    void *p = nullptr;
+    DeviceBuf() = default;
+    DeviceBuf(const DeviceBuf &) = delete;
+    DeviceBuf &operator=(const DeviceBuf &) = delete;
+    cudaStream_t s = nullptr;
+    bool pooled = false;
+    ~DeviceBuf() { release(); }
+    void release()
+    {
+        if (p) { if (pooled) cudaFreeAsync(p, s); else cudaFree(p); }
+        p = nullptr;
+    }
+    int alloc(size_t n) { release(); pooled = false; GB_CUDA(cudaMalloc(&p, n ? n : 16)); return GB_OK; }
+    // stream-ordered, from the device pool (no device-wide synchronisation)
+    int alloc(size_t n, cudaStream_t stream)
+    {
+        release();
+        pooled = true;
+        s = stream;
+        GB_CUDA(cudaMallocAsync(&p, n ? n : 16, stream));
+        return GB_OK;
+    }
+};
+
+inline unsigned int grid_for(unsigned long long n, int threads, int per_sm = 16)
+{
+    unsigned long long g = (n + threads - 1) / threads;
+    unsigned long long cap = (unsigned long long)SM_COUNT * per_sm;
+    if (g > cap) g = cap;
+    return (unsigned int)(g ? g : 1);
+}
+int map_alloc_table(Slot **t, int bits, cudaStream_t s);
+int pool_setup(int device);
+inline int bits_for(int64_t keys)
+{
+    // smallest power of two with load <= 0.5, at least 2^10 slots
+    int b = 10;
+    while (((int64_t)1 << b) < keys * 2) b++;
+    return b;
+}
+
+} // namespace gb

@@ -1,0 +1,799 @@
+// map.cu -- DNAMap[Int] on one B200: open-addressing HBM hash table, bulk FreqFilter.add, filter, export.
+// Replaces S/ds/ArrayDNAMap.scala:62-243 and the insert loop of S/data/FreqFilter.scala:25-58
+// (paths relative to /root/reference, S/ = src/main/scala/ru/ifmo/genome/).
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <vector>
+
+#include "common.cuh"
+#include "extract.cuh"
+
+namespace gb {
+
+// ================================================================ errors
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return e == cudaErrorMemoryAllocation ? GB_E_OOM : GB_E_CUDA;
+}
+
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// Device allocations are stream-ordered and come from the device's default memory pool, which is told to keep
+// freed memory: tables are re-created every FreqFilter pass (clear, rescale, filter) and must not pay cudaMalloc.
+int pool_setup(int device)
+{
+    cudaMemPool_t pool;
+    GB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    GB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    return GB_OK;
+}
+
+// ================================================================ kernels
+
+__global__ void init_table_kernel(Slot *t, unsigned long long n)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, NONE32);
+    for (; i < n; i += stride) reinterpret_cast<uint4 *>(t)[i] = e;
+}
+
+// ---------------------------------------------------------------- bulk FreqFilter.add
+// Tile staging and window extraction live in extract.cuh; here all SEG table probes of a work item are issued
+// before the first one is consumed (memory-level parallelism for the random 32-byte sector reads).
+template <bool FIXED, bool V210>
+__global__ void __launch_bounds__(INSERT_THREADS)
+insert_reads_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes,
+                    const unsigned long long *__restrict__ offsets, unsigned int rec_bytes,
+                    long long read0, long long n_reads, int k, Slot *table, int bits,
+                    unsigned long long *counters)
+{
+    __shared__ ReadTile tile;
+    __shared__ unsigned int s_newkeys;
+    const int tid = threadIdx.x;
+    const int nr = stage_tile<FIXED>(tile, bin, n_bytes, offsets, rec_bytes, read0, n_reads, k);
+    if (nr <= 0) return;
+    if (tid == 0) s_newkeys = 0;
+
+    const unsigned int total_items = tile.prefix[TILE_READS];
+    const unsigned long long tmask = (1ull << bits) - 1;
+    int newkeys = 0;
+
+    for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
+        unsigned long long key[SEG], idx[SEG], cur[SEG];
+        const int cnt = item_keys<V210>(tile, item, k, key);
+#pragma unroll
+        for (int j = 0; j < SEG; j++) idx[j] = slot_of(mix64(key[j]), bits);
+#pragma unroll
+        for (int j = 0; j < SEG; j++)
+            if (j < cnt) cur[j] = load_key(table + idx[j]);
+#pragma unroll
+        for (int j = 0; j < SEG; j++)
+            if (j < cnt) newkeys += upsert_add(table, tmask, idx[j], cur[j], key[j], 1);
+    }
+
+    // one global atomic per CTA for the size counter
+    newkeys = __reduce_add_sync(0xFFFFFFFFu, newkeys);
+    __syncthreads();
+    if ((tid & 31) == 0 && newkeys) atomicAdd(&s_newkeys, (unsigned int)newkeys);
+    __syncthreads();
+    if (tid == 0) {
+        if (s_newkeys) atomicAdd(&counters[0], (unsigned long long)s_newkeys);
+        unsigned long long w = 0;
+        for (int i = 0; i < nr; i++) w += tile.nwin[i];
+        atomicAdd(&counters[3], w);
+    }
+}
+
+// empirical random-access ceiling (R_gups): what the insert kernel does to the table with hashing,
+// probing and extraction stripped away -- one 8-byte key read and one 4-byte red.add per update, 8 updates per
+// thread in flight, addresses uniform over the table.
+__global__ void __launch_bounds__(256)
+random_atomics_kernel(Slot *table, unsigned long long mask, long long n, unsigned long long seed)
+{
+    long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    unsigned long long idx[8], cur[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) idx[j] = mix64((unsigned long long)(i0 + j) * 0x9E3779B97F4A7C15ull + seed) & mask;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (i0 + j < n) cur[j] = load_key(table + idx[j]);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        if (i0 + j < n) red_add_s32(&table[idx[j]].count, (int)(cur[j] & 1) + 1);
+}
+
+// every record of a fixed-stride stream must carry the same length byte; counters[2] != 0 otherwise
+__global__ void verify_fixed_kernel(const uint8_t *__restrict__ bin, unsigned int rec_bytes, unsigned int len0,
+                                    long long n_reads, unsigned long long *counters)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (; i < n_reads; i += stride) bad |= bin[(unsigned long long)i * rec_bytes] != len0;
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicOr(&counters[2], 1ull);
+}
+
+// update(key, 1, _ + 1) / update(key, v) for explicit keys
+template <bool SET>
+__global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ vals,
+                                   long long n, Slot *table, int bits, unsigned long long *counters)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long mask = (1ull << bits) - 1;
+    int nk = 0;
+    if (i < n) {
+        unsigned long long key = keys[i];
+        unsigned long long idx = slot_of(mix64(key), bits);
+        if (!SET) {
+            nk = upsert_add(table, mask, idx, load_key(table + idx), key, 1);
+        } else {
+            for (;;) {
+                unsigned long long cur = load_key(table + idx);
+                if (cur == EMPTY_KEY) {
+                    cur = atomicCAS(&table[idx].key, EMPTY_KEY, key);
+                    if (cur == EMPTY_KEY) { nk = 1; cur = key; }
+                }
+                if (cur == key) { atomicExch(&table[idx].count, vals[i]); break; }
+                idx = (idx + 1) & mask;
+            }
+        }
+    }
+    nk = __reduce_add_sync(0xFFFFFFFFu, nk);
+    if ((threadIdx.x & 31) == 0 && nk) atomicAdd(&counters[0], (unsigned long long)nk);
+}
+
+__global__ void lookup_kernel(const unsigned long long *__restrict__ keys, long long n, const Slot *table, int bits,
+                              int *counts, uint8_t *found)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Slot s;
+    bool f = probe_find(table, bits, keys[i], &s) >= 0;
+    if (counts) counts[i] = f ? s.count : 0;
+    if (found) found[i] = f;
+}
+
+// deleteAll(v < min_count): survivors are counted, then re-inserted into a table sized for them (the
+// reference tombstones and then rescales when load drops below 0.3, ArrayDNAMap.scala:164-173,217-230)
+__global__ void count_survivors_kernel(const Slot *table, unsigned long long n, int min_count,
+                                       unsigned long long *counters)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned int c = 0;
+    for (; i < n; i += stride) {
+        Slot s = load_slot(table + i);
+        c += (s.key != EMPTY_KEY && s.count >= min_count);
+    }
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    __shared__ unsigned int s_c;
+    if (threadIdx.x == 0) s_c = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_c, c);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_c) atomicAdd(&counters[1], (unsigned long long)s_c);
+}
+
+__global__ void rehash_kernel(const Slot *old_table, unsigned long long n, int min_count, bool filter,
+                              Slot *new_table, int new_bits)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long mask = (1ull << new_bits) - 1;
+    for (; i < n; i += stride) {
+        Slot s = load_slot(old_table + i);
+        if (s.key == EMPTY_KEY || (filter && s.count < min_count)) continue;
+        unsigned long long idx = slot_of(mix64(s.key), new_bits);
+        for (;;) {
+            unsigned long long cur = load_key(new_table + idx);
+            if (cur == EMPTY_KEY && atomicCAS(&new_table[idx].key, EMPTY_KEY, s.key) == EMPTY_KEY) {
+                new_table[idx].count = s.count;
+                break;
+            }
+            idx = (idx + 1) & mask;
+        }
+    }
+}
+
+// mapReduce/foreach export: compaction with one global atomic per CTA
+__global__ void export_kernel(const Slot *table, unsigned long long n, unsigned long long *keys, int *vals,
+                              unsigned long long cap, unsigned long long *counters)
+{
+    __shared__ unsigned int s_n;
+    __shared__ unsigned long long s_base;
+    unsigned long long tiles = (n + blockDim.x - 1) / blockDim.x;
+    for (unsigned long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        unsigned long long i = t * blockDim.x + threadIdx.x;
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        Slot s;
+        s.key = EMPTY_KEY;
+        if (i < n) s = load_slot(table + i);
+        bool live = s.key != EMPTY_KEY;
+        unsigned int ballot = __ballot_sync(0xFFFFFFFFu, live);
+        unsigned int lane = threadIdx.x & 31, wbase = 0;
+        if (lane == 0 && ballot) wbase = atomicAdd(&s_n, __popc(ballot));
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = s_n ? atomicAdd(&counters[1], (unsigned long long)s_n) : 0;
+        __syncthreads();
+        if (live) {
+            unsigned long long o = s_base + wbase + __popc(ballot & ((1u << lane) - 1));
+            if (o < cap) {
+                if (keys) keys[o] = s.key;
+                if (vals) vals[o] = s.count;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+} // namespace gb
+
+using namespace gb;
+
+// ================================================================ host side
+
+namespace gb {
+
+int map_alloc_table(Slot **t, int bits, cudaStream_t s)
+{
+    unsigned long long n = 1ull << bits;
+    GB_CUDA(cudaMallocAsync((void **)t, n * sizeof(Slot), s));
+    init_table_kernel<<<grid_for(n, 256, 32), 256, 0, s>>>(*t, n);
+    GB_LAUNCHED();
+    return GB_OK;
+}
+
+// rehash into a table of new_bits (optionally dropping counts below min_count)
+int map_rebuild(Map *m, int new_bits, bool filter, int min_count)
+{
+    Slot *nt = nullptr;
+    GB_TRY(map_alloc_table(&nt, new_bits, m->stream));
+    unsigned long long n = 1ull << m->bits;
+    rehash_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(m->table, n, min_count, filter, nt, new_bits);
+    GB_LAUNCHED();
+    GB_CUDA(cudaFreeAsync(m->table, m->stream));
+    m->table = nt;
+    m->bits = new_bits;
+    m->grows++;
+    return GB_OK;
+}
+
+// make room so that `incoming` further updates can never fill the table (load stays <= 0.9 even if every
+// update is a new key), growing by rehash like ArrayDNAMap.rescale (217-230).  Returns how many updates may
+// be issued before the next reserve through *budget.
+int map_budget(Map *m, int64_t incoming, int64_t *budget)
+{
+    int64_t cap = (int64_t)1 << m->bits;
+    int64_t room = (int64_t)(cap * 0.9) - m->size;
+    int64_t min_batch = std::min<int64_t>(incoming, (int64_t)TILE_READS * 256);
+    if (m->size * 10 > cap * 7 || room < min_batch) {
+        int nb = bits_for(std::max<int64_t>(m->size, 1) * 2);
+        while ((int64_t)(((int64_t)1 << nb) * 0.9) - m->size < min_batch) nb++;
+        if (nb > m->bits) GB_TRY(map_rebuild(m, nb, false, 0));
+        cap = (int64_t)1 << m->bits;
+        room = (int64_t)(cap * 0.9) - m->size;
+    }
+    *budget = room;
+    return GB_OK;
+}
+
+int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return GB_OK;
+    update_keys_kernel<false><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, nullptr, n, m->table, m->bits, m->d_counters);
+    GB_LAUNCHED();
+    return GB_OK;
+}
+
+int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d_vals, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return GB_OK;
+    update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->bits, m->d_counters);
+    GB_LAUNCHED();
+    return GB_OK;
+}
+
+int map_reserve(Map *m, int64_t want_keys)
+{
+    int nb = bits_for(want_keys);
+    if (nb > m->bits) return map_rebuild(m, nb, false, 0);
+    return GB_OK;
+}
+
+int map_read_counters(Map *m, unsigned long long out[4])
+{
+    GB_CUDA(cudaMemcpyAsync(out, m->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    return GB_OK;
+}
+
+int map_zero_counters(Map *m)
+{
+    GB_CUDA(cudaMemsetAsync(m->d_counters, 0, 4 * sizeof(unsigned long long), m->stream));
+    return GB_OK;
+}
+
+template <bool FIXED>
+static int launch_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off,
+                         unsigned int rec, int64_t read0, int64_t n_reads)
+{
+    if (n_reads <= 0) return GB_OK;
+    unsigned int grid = (unsigned int)((n_reads + TILE_READS - 1) / TILE_READS);
+    if (m->v210)
+        insert_reads_kernel<FIXED, true><<<grid, INSERT_THREADS, 0, m->stream>>>(
+            d_bin, n_bytes, d_off, rec, read0, n_reads, m->k, m->table, m->bits, m->d_counters);
+    else
+        insert_reads_kernel<FIXED, false><<<grid, INSERT_THREADS, 0, m->stream>>>(
+            d_bin, n_bytes, d_off, rec, read0, n_reads, m->k, m->table, m->bits, m->d_counters);
+    GB_LAUNCHED();
+    return GB_OK;
+}
+
+// Core of gb_map_insert_reads*: the stream is on the device.  h_windows_prefix (optional, n_reads+1) gives
+// exact per-read window prefix sums for batching in the ragged case.
+static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off,
+                         bool fixed, unsigned int rec, unsigned int len0, int64_t n_reads,
+                         const int64_t *h_win_prefix, int64_t *n_windows)
+{
+    GB_TRY(map_zero_counters(m));
+    int64_t done = 0;
+    int64_t total_ns = 0;
+    while (done < n_reads) {
+        // how many reads fit the budget (whole tiles)
+        int64_t left = n_reads - done;
+        int64_t win_per_read_max = fixed ? std::max<int64_t>(0, (int64_t)len0 - m->k + 1) : (255 - m->k + 1);
+        int64_t want = fixed ? left * win_per_read_max
+                             : (h_win_prefix ? h_win_prefix[n_reads] - h_win_prefix[done] : left * win_per_read_max);
+        int64_t budget = 0;
+        GB_TRY(map_budget(m, want, &budget));
+        int64_t take = left;
+        if (want > budget) {
+            if (fixed) {
+                take = win_per_read_max ? budget / win_per_read_max : left;
+            } else if (h_win_prefix) {
+                const int64_t *b = h_win_prefix + done, *e = h_win_prefix + n_reads + 1;
+                take = (std::upper_bound(b, e, h_win_prefix[done] + budget) - b) - 1;
+            } else {
+                take = budget / win_per_read_max;
+            }
+            take = std::max<int64_t>(TILE_READS, take / TILE_READS * TILE_READS);
+            take = std::min(take, left);
+        }
+        unsigned long long before[4], after[4];
+        GB_TRY(map_read_counters(m, before));
+        GB_CUDA(cudaEventRecord(m->ev0, m->stream));
+        if (fixed) GB_TRY(launch_insert<true>(m, d_bin, n_bytes, nullptr, rec, done, take));
+        else GB_TRY(launch_insert<false>(m, d_bin, n_bytes, d_off, 0, done, take));
+        GB_CUDA(cudaEventRecord(m->ev1, m->stream));
+        GB_TRY(map_read_counters(m, after));
+        float ms = 0;
+        GB_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        total_ns += (int64_t)(ms * 1e6);
+        m->size += (int64_t)(after[0] - before[0]);
+        done += take;
+    }
+    unsigned long long c[4];
+    GB_TRY(map_read_counters(m, c));
+    m->windows += (int64_t)c[3];
+    m->last_insert_ns = total_ns;
+    if (n_windows) *n_windows = (int64_t)c[3];
+    return GB_OK;
+}
+
+// host scan of the record chain (PairedEndData.getPairs.read, PairedEndData.scala:24-32)
+int scan_records(const uint8_t *bin, size_t n_bytes, int64_t n_reads, int k,
+                        std::vector<unsigned long long> &off, std::vector<int64_t> &winp)
+{
+    off.resize((size_t)n_reads + 1);
+    winp.resize((size_t)n_reads + 1);
+    size_t pos = 0;
+    int64_t w = 0;
+    for (int64_t r = 0; r < n_reads; r++) {
+        if (pos >= n_bytes) { set_error("truncated .bin stream at read %lld", (long long)r); return GB_E_ARG; }
+        unsigned int len = bin[pos];
+        size_t nxt = pos + 1 + (len + 3) / 4;
+        if (nxt > n_bytes) { set_error("truncated .bin stream at read %lld", (long long)r); return GB_E_ARG; }
+        off[(size_t)r] = pos;
+        winp[(size_t)r] = w;
+        if ((int)len >= k) w += len - k + 1;
+        pos = nxt;
+    }
+    off[(size_t)n_reads] = pos;
+    winp[(size_t)n_reads] = w;
+    return GB_OK;
+}
+
+int check_map(gb_map *h, Map **m)
+{
+    if (!h) { set_error("null map handle"); return GB_E_ARG; }
+    *m = reinterpret_cast<Map *>(h);
+    GB_CUDA(cudaSetDevice((*m)->device));
+    return GB_OK;
+}
+
+} // namespace gb
+
+// ================================================================ C ABI
+
+extern "C" {
+
+const char *gb_last_error(void) { return g_err; }
+int gb_version(void) { return 100; }
+
+int gb_device_count(int *n)
+{
+    if (!n) { set_error("null argument"); return GB_E_ARG; }
+    GB_CUDA(cudaGetDeviceCount(n));
+    return GB_OK;
+}
+
+int gb_host_alloc(size_t n_bytes, void **ptr)
+{
+    if (!ptr) { set_error("null argument"); return GB_E_ARG; }
+    GB_CUDA(cudaHostAlloc(ptr, n_bytes ? n_bytes : 16, cudaHostAllocDefault));
+    return GB_OK;
+}
+
+int gb_host_free(void *ptr)
+{
+    if (ptr) GB_CUDA(cudaFreeHost(ptr));
+    return GB_OK;
+}
+
+int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_map **out)
+{
+    if (!out) { set_error("null out pointer"); return GB_E_ARG; }
+    *out = nullptr;
+    if (k < 1 || k > 31) { set_error("k = %d outside 1..31", k); return GB_E_K_RANGE; }
+    if (min_capacity < 0) { set_error("negative capacity"); return GB_E_ARG; }
+    int ndev = 0;
+    GB_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_error("device %d not present (%d devices)", device, ndev); return GB_E_CUDA; }
+    GB_CUDA(cudaSetDevice(device));
+    GB_TRY(pool_setup(device));
+    Map *m = new Map();
+    m->k = k;
+    m->device = device;
+    m->v210 = (flags & GB_FLAG_HASH_SCALA_210) != 0;
+    m->bits = bits_for(min_capacity);
+    int r = GB_OK;
+    do {
+        if ((r = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
+        if ((r = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
+        if ((r = cudaEventCreate(&m->ev0) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
+        if ((r = cudaEventCreate(&m->ev1) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
+        if ((r = cudaEventCreate(&m->t0) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
+        if ((r = cudaEventCreate(&m->t1) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
+        if ((r = cudaMalloc((void **)&m->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess ? GB_OK : GB_E_OOM)) break;
+        if ((r = map_alloc_table(&m->table, m->bits, m->stream))) break;
+        if ((r = cudaStreamSynchronize(m->stream) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
+    } while (0);
+    if (r != GB_OK) {
+        if (!g_err[0]) set_error("map creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        gb_map_destroy(reinterpret_cast<gb_map *>(m));
+        return r;
+    }
+    *out = reinterpret_cast<gb_map *>(m);
+    return GB_OK;
+}
+
+int gb_map_destroy(gb_map *h)
+{
+    if (!h) return GB_OK;
+    Map *m = reinterpret_cast<Map *>(h);
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->table) cudaFreeAsync(m->table, m->stream);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    if (m->d_counters) cudaFree(m->d_counters);
+    if (m->d_overflow) cudaFree(m->d_overflow);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->t0) cudaEventDestroy(m->t0);
+    if (m->t1) cudaEventDestroy(m->t1);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    delete m;
+    return GB_OK;
+}
+
+int gb_map_insert_reads_device(gb_map *h, const uint8_t *d_bin, size_t n_bytes, const uint64_t *d_offsets,
+                               int64_t n_reads, int64_t *n_windows)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    if (n_windows) *n_windows = 0;
+    if (n_reads < 0 || (!d_bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
+    if (n_reads == 0) return GB_OK;
+    if (d_offsets)
+        return insert_device(m, d_bin, n_bytes, (const unsigned long long *)d_offsets, false, 0, 0, n_reads, nullptr, n_windows);
+    // fixed-stride stream: take the length from the first record, verify all of them on the device
+    uint8_t len0 = 0;
+    GB_CUDA(cudaMemcpyAsync(&len0, d_bin, 1, cudaMemcpyDeviceToHost, m->stream));
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    unsigned int rec = 1 + (len0 + 3) / 4;
+    if ((unsigned long long)n_reads * rec > n_bytes) { set_error("truncated .bin stream"); return GB_E_ARG; }
+    GB_TRY(map_zero_counters(m));
+    verify_fixed_kernel<<<grid_for((unsigned long long)n_reads, 256), 256, 0, m->stream>>>(d_bin, rec, len0, n_reads, m->d_counters);
+    GB_LAUNCHED();
+    unsigned long long c[4];
+    GB_TRY(map_read_counters(m, c));
+    if (c[2]) { set_error("records are not fixed-length: pass d_offsets"); return GB_E_ARG; }
+    m->fixed_stride = 1;
+    return insert_device(m, d_bin, n_bytes, nullptr, true, rec, len0, n_reads, nullptr, n_windows);
+}
+
+int gb_map_insert_reads(gb_map *h, const uint8_t *bin, size_t n_bytes, int64_t n_reads, int64_t *n_windows)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    if (n_windows) *n_windows = 0;
+    if (n_reads < 0 || (!bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
+    if (n_reads == 0) return GB_OK;
+    if (n_bytes == 0) { set_error("truncated .bin stream at read 0"); return GB_E_ARG; }
+
+    // fixed-stride fast path: if the stream is long enough for n_reads records of the first record's size,
+    // copy exactly those bytes and let the device check every length byte (sound: equal length bytes at
+    // i*rec imply the record chain is i*rec).  Otherwise scan the chain on the host.
+    unsigned int len0 = bin[0], rec = 1 + (len0 + 3) / 4;
+    bool try_fixed = (unsigned long long)n_reads * rec <= n_bytes;
+    DeviceBuf d_bin, d_off;
+    if (try_fixed) {
+        size_t used = (size_t)n_reads * rec;
+        GB_TRY(d_bin.alloc(used + 16, m->stream));
+        GB_CUDA(cudaMemcpyAsync(d_bin.p, bin, used, cudaMemcpyHostToDevice, m->stream));
+        GB_TRY(map_zero_counters(m));
+        verify_fixed_kernel<<<grid_for((unsigned long long)n_reads, 256), 256, 0, m->stream>>>(
+            (const uint8_t *)d_bin.p, rec, len0, n_reads, m->d_counters);
+        GB_LAUNCHED();
+        unsigned long long c[4];
+        GB_TRY(map_read_counters(m, c));
+        if (!c[2]) {
+            m->fixed_stride = 1;
+            return insert_device(m, (const uint8_t *)d_bin.p, used, nullptr, true, rec, len0, n_reads, nullptr, n_windows);
+        }
+    }
+    m->fixed_stride = 0;
+    std::vector<unsigned long long> off;
+    std::vector<int64_t> winp;
+    GB_TRY(scan_records(bin, n_bytes, n_reads, m->k, off, winp));
+    size_t used = (size_t)off[(size_t)n_reads];
+    if (!d_bin.p || !try_fixed || used > (size_t)n_reads * rec) {
+        d_bin.release();
+        GB_TRY(d_bin.alloc(used + 16, m->stream));
+        GB_CUDA(cudaMemcpyAsync(d_bin.p, bin, used, cudaMemcpyHostToDevice, m->stream));
+    }
+    GB_TRY(d_off.alloc(off.size() * 8, m->stream));
+    GB_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, m->stream));
+    return insert_device(m, (const uint8_t *)d_bin.p, used, (const unsigned long long *)d_off.p, false, 0, 0, n_reads,
+                         winp.data(), n_windows);
+}
+
+static int update_common(gb_map *h, const uint64_t *keys, const int32_t *vals, int64_t n, bool set)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    if (n < 0 || (n > 0 && (!keys || (set && !vals)))) { set_error("bad arguments"); return GB_E_ARG; }
+    if (n == 0) return GB_OK;
+    unsigned long long kmask = (1ull << (2 * m->k)) - 1;
+    for (int64_t i = 0; i < n; i++)
+        if (keys[i] & ~kmask) { set_error("key %lld is longer than k = %d", (long long)i, m->k); return GB_E_K_RANGE; }
+    m->noncanonical = true;
+    DeviceBuf dk, dv;
+    GB_TRY(dk.alloc((size_t)n * 8, m->stream));
+    GB_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, m->stream));
+    if (set) {
+        GB_TRY(dv.alloc((size_t)n * 4, m->stream));
+        GB_CUDA(cudaMemcpyAsync(dv.p, vals, (size_t)n * 4, cudaMemcpyHostToDevice, m->stream));
+    }
+    int64_t done = 0;
+    while (done < n) {
+        int64_t budget = 0;
+        GB_TRY(map_budget(m, n - done, &budget));
+        int64_t take = std::min(n - done, std::max<int64_t>(budget, 1));
+        GB_TRY(map_zero_counters(m));
+        if (set) GB_TRY(map_launch_update_set(m, (const unsigned long long *)dk.p + done, (const int *)dv.p + done, take, m->stream));
+        else GB_TRY(map_launch_update_counts(m, (const unsigned long long *)dk.p + done, take, m->stream));
+        unsigned long long c[4];
+        GB_TRY(map_read_counters(m, c));
+        m->size += (int64_t)c[0];
+        done += take;
+    }
+    return GB_OK;
+}
+
+int gb_map_update_counts(gb_map *h, const uint64_t *keys, int64_t n) { return update_common(h, keys, nullptr, n, false); }
+int gb_map_update(gb_map *h, const uint64_t *keys, const int32_t *vals, int64_t n) { return update_common(h, keys, vals, n, true); }
+
+int gb_map_size(gb_map *h, int64_t *size)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    if (!size) { set_error("null argument"); return GB_E_ARG; }
+    *size = m->size;
+    return GB_OK;
+}
+
+int gb_map_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, uint8_t *found)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    if (n < 0 || (n > 0 && !keys)) { set_error("bad arguments"); return GB_E_ARG; }
+    if (n == 0) return GB_OK;
+    DeviceBuf dk, dc, df;
+    GB_TRY(dk.alloc((size_t)n * 8, m->stream));
+    GB_TRY(dc.alloc((size_t)n * 4, m->stream));
+    GB_TRY(df.alloc((size_t)n, m->stream));
+    GB_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, m->stream));
+    lookup_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, m->stream>>>((const unsigned long long *)dk.p, n, m->table, m->bits,
+                                                                          (int *)dc.p, (uint8_t *)df.p);
+    GB_LAUNCHED();
+    if (counts) GB_CUDA(cudaMemcpyAsync(counts, dc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
+    if (found) GB_CUDA(cudaMemcpyAsync(found, df.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    return GB_OK;
+}
+
+int gb_map_delete_below(gb_map *h, int32_t min_count)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    unsigned long long n = 1ull << m->bits;
+    GB_TRY(map_zero_counters(m));
+    count_survivors_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(m->table, n, min_count, m->d_counters);
+    GB_LAUNCHED();
+    unsigned long long c[4];
+    GB_TRY(map_read_counters(m, c));
+    int64_t keep = (int64_t)c[1];
+    if (keep == m->size) return GB_OK;
+    int nb = bits_for(keep);
+    GB_TRY(map_rebuild(m, nb, true, min_count));
+    m->size = keep;
+    return GB_OK;
+}
+
+int gb_map_export(gb_map *h, uint64_t *keys, int32_t *vals, int64_t cap, int64_t *n_out)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    if (n_out) *n_out = m->size;
+    if (!keys && !vals) return GB_OK;
+    if (cap < m->size) { set_error("export buffer too small: %lld < %lld", (long long)cap, (long long)m->size); return GB_E_CAPACITY; }
+    if (m->size == 0) return GB_OK;
+    DeviceBuf dk, dv;
+    GB_TRY(dk.alloc((size_t)m->size * 8, m->stream));
+    GB_TRY(dv.alloc((size_t)m->size * 4, m->stream));
+    unsigned long long n = 1ull << m->bits;
+    GB_TRY(map_zero_counters(m));
+    export_kernel<<<grid_for(n, 256, 16), 256, 0, m->stream>>>(m->table, n, (unsigned long long *)dk.p, (int *)dv.p,
+                                                             (unsigned long long)m->size, m->d_counters);
+    GB_LAUNCHED();
+    if (keys) GB_CUDA(cudaMemcpyAsync(keys, dk.p, (size_t)m->size * 8, cudaMemcpyDeviceToHost, m->stream));
+    if (vals) GB_CUDA(cudaMemcpyAsync(vals, dv.p, (size_t)m->size * 4, cudaMemcpyDeviceToHost, m->stream));
+    unsigned long long c[4];
+    GB_TRY(map_read_counters(m, c));
+    if ((int64_t)c[1] != m->size) { set_error("internal: exported %llu keys, size is %lld", c[1], (long long)m->size); return GB_E_INVARIANT; }
+    return GB_OK;
+}
+
+int gb_map_clear(gb_map *h, int64_t min_capacity)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    if (min_capacity < 0) { set_error("negative capacity"); return GB_E_ARG; }
+    int nb = bits_for(min_capacity);
+    if (nb != m->bits) {
+        Slot *nt = nullptr;
+        GB_CUDA(cudaFreeAsync(m->table, m->stream));
+        m->table = nullptr;
+        GB_TRY(map_alloc_table(&nt, nb, m->stream));
+        m->table = nt;
+        m->bits = nb;
+    } else {
+        unsigned long long n = 1ull << m->bits;
+        init_table_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(m->table, n);
+        GB_LAUNCHED();
+    }
+    m->size = 0;
+    m->noncanonical = false;
+    m->windows = 0;
+    return GB_OK;
+}
+
+long long gb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gb_timer_start(gb_map *h)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    GB_CUDA(cudaEventRecord(m->t0, m->stream));
+    return GB_OK;
+}
+
+int gb_timer_stop(gb_map *h, int64_t *ns)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    if (!ns) { set_error("null argument"); return GB_E_ARG; }
+    GB_CUDA(cudaEventRecord(m->t1, m->stream));
+    GB_CUDA(cudaEventSynchronize(m->t1));
+    float ms = 0;
+    GB_CUDA(cudaEventElapsedTime(&ms, m->t0, m->t1));
+    *ns = (int64_t)((double)ms * 1e6);
+    return GB_OK;
+}
+
+int gb_sync(gb_map *h)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    return GB_OK;
+}
+
+int gb_bench_random_atomics(int device, size_t table_bytes, int64_t n_updates, int iters, int64_t *ns_per_iter)
+{
+    if (!ns_per_iter || table_bytes < 1024 || n_updates <= 0 || iters <= 0) { set_error("bad arguments"); return GB_E_ARG; }
+    GB_CUDA(cudaSetDevice(device));
+    unsigned long long slots = 1;
+    while (slots * 2 * sizeof(Slot) <= table_bytes) slots *= 2;
+    Slot *t = nullptr;
+    GB_CUDA(cudaMalloc((void **)&t, slots * sizeof(Slot)));
+    GB_CUDA(cudaMemset(t, 0, slots * sizeof(Slot)));
+    cudaEvent_t e0, e1;
+    GB_CUDA(cudaEventCreate(&e0));
+    GB_CUDA(cudaEventCreate(&e1));
+    unsigned int grid = (unsigned int)((n_updates + 256 * 8 - 1) / (256 * 8));
+    random_atomics_kernel<<<grid, 256>>>(t, slots - 1, n_updates, 1);
+    GB_LAUNCHED();
+    GB_CUDA(cudaEventRecord(e0));
+    for (int i = 0; i < iters; i++) {
+        random_atomics_kernel<<<grid, 256>>>(t, slots - 1, n_updates, 2 + i);
+        GB_LAUNCHED();
+    }
+    GB_CUDA(cudaEventRecord(e1));
+    GB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    GB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ns_per_iter = (int64_t)(ms * 1e6 / iters);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    GB_CUDA(cudaFree(t));
+    return GB_OK;
+}
+
+int gb_map_stats(gb_map *h, int64_t stats[8])
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    if (!stats) { set_error("null argument"); return GB_E_ARG; }
+    memset(stats, 0, 8 * sizeof(int64_t));
+    stats[0] = (int64_t)1 << m->bits;
+    stats[1] = stats[0] * (int64_t)sizeof(Slot);
+    stats[2] = m->grows;
+    stats[3] = m->windows;
+    stats[4] = m->last_insert_ns;
+    stats[5] = m->fixed_stride;
+    return GB_OK;
+}
+
+} // extern "C"

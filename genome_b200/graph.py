@@ -1,0 +1,107 @@
+"""Host-side mirror of trait Graph / MapGraph / object Graph (S/data/graph/Graph.scala, paths relative to
+/root/reference) over the C ABI.  Nodes and edges are addressed by their index in the current export: the
+reference's ids are not reproducible even reference-vs-reference."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .dnamap import PartitionedDNAMap
+
+
+class MapGraph:
+    """class MapGraph (Graph.scala:152-262) held in device memory."""
+
+    def __init__(self, handle, k):
+        self.h = handle
+        self.k = k
+
+    def close(self):
+        if getattr(self, "h", None):
+            capi.lib().gb_graph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def counts(self):
+        """(getNodes.size, getEdges.size, getEdges.map(_.seq.length).sum)"""
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        capi.check(capi.lib().gb_graph_counts(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def export(self):
+        """node_kmer u64[N], edge_start u32[E], edge_end u32[E], edge_off u64[E+1] (bases), bases u8[n_bases] (codes)."""
+        nn, ne, nb = self.counts()
+        node_kmer = np.empty(nn, np.uint64)
+        es = np.empty(ne, np.uint32)
+        ee = np.empty(ne, np.uint32)
+        off = np.empty(ne + 1, np.uint64)
+        packed = np.zeros((nb + 3) // 4, np.uint8)
+        capi.check(capi.lib().gb_graph_export(self.h, capi.ptr(node_kmer), capi.ptr(es), capi.ptr(ee), capi.ptr(off), capi.ptr(packed)))
+        bases = np.empty(packed.size * 4, np.uint8)
+        for j in range(4):
+            bases[j::4] = (packed >> (2 * j)) & 3
+        return node_kmer, es, ee, off, bases[:nb]
+
+    # ---- trait Graph
+    def getNodes(self):
+        return self.export()[0]
+
+    def getEdges(self):
+        """list of (start index, end index, seq codes)"""
+        _, es, ee, off, bases = self.export()
+        return [(int(es[i]), int(ee[i]), bases[int(off[i]):int(off[i + 1])]) for i in range(es.size)]
+
+    def components(self):
+        """Graph.components (54-72): (number of components, label per node)."""
+        nn = self.counts()[0]
+        label = np.zeros(nn, np.uint32)
+        nc = C.c_int64()
+        capi.check(capi.lib().gb_graph_components(self.h, capi.ptr(label), C.byref(nc)))
+        return nc.value, label
+
+    def retain_largest(self):
+        """graph.retain(components.maxBy(_.size)) (GraphBuilder.scala:52-54)."""
+        capi.check(capi.lib().gb_graph_retain_largest(self.h))
+
+    def simplifyGraph(self):
+        capi.check(capi.lib().gb_graph_simplify(self.h))
+
+    def removeBubbles(self):
+        capi.check(capi.lib().gb_graph_remove_bubbles(self.h))
+
+    def removeEdges(self, edge_idx):
+        idx = np.ascontiguousarray(edge_idx, dtype=np.uint32)
+        capi.check(capi.lib().gb_graph_remove_edges(self.h, capi.ptr(idx), idx.size))
+
+    def clipTips(self, max_len):
+        """EXTENSION (no reference counterpart)."""
+        n = C.c_int64()
+        capi.check(capi.lib().gb_graph_clip_tips(self.h, int(max_len), C.byref(n)))
+        return n.value
+
+    def check(self):
+        capi.check(capi.lib().gb_graph_check(self.h))
+
+    def stats(self):
+        s = (C.c_int64 * 8)()
+        capi.check(capi.lib().gb_graph_stats(self.h, s))
+        return dict(kept_kmers=s[0], jump_launches=s[1], cycle_vertices=s[2], build_ns=s[3])
+
+
+class Graph:
+    """object Graph (Graph.scala:264-392)."""
+
+    @staticmethod
+    def buildGraph(k, kmersFreq):
+        """Graph.buildGraph(k, kmersFreq) (269-382) on the map's current contents."""
+        if k != kmersFreq.k:
+            raise ValueError("k differs from the map's k")
+        h = C.c_void_p()
+        fn = capi.lib().gb_pmap_graph_build if isinstance(kmersFreq, PartitionedDNAMap) else capi.lib().gb_graph_build
+        capi.check(fn(kmersFreq.h, C.byref(h)))
+        return MapGraph(h, k)

@@ -1,0 +1,172 @@
+/*
+ * genome_b200.h -- C ABI of libgenome_b200.so: the B200 (sm_100a) replacement for winger/genome's
+ * k-mer -> de Bruijn graph hot path.  Plain pointers and sizes only; every entry point names the
+ * reference interface it replaces (paths relative to /root/reference, S/ = src/main/scala/ru/ifmo/genome/).
+ *
+ * Conventions
+ *   - every function returns 0 (GB_OK) or a negative GB_E_* code; gb_last_error() gives the thread-local text.
+ *   - handles own all device memory; host buffers are caller-allocated; exports use size-then-fill.
+ *   - calls on one handle must be serialised by the caller; different handles are independent.
+ *   - a k-mer is one uint64: base i at bits 2i..2i+1, code A0 G1 C2 T3 (S/dna/DNASeq.scala:80-85,
+ *     S/dna/Base.scala:13-16).  Supported k: 1..31 (k = 32 is broken in the reference itself).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with GB_E_CUDA.
+ */
+#ifndef GENOME_B200_H
+#define GENOME_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GB_OK            0
+#define GB_E_ARG        -1   /* null pointer, negative size, truncated .bin stream */
+#define GB_E_K_RANGE    -2   /* k outside 1..31 (assert key.length == k, S/ds/ArrayDNAMap.scala:182-206) */
+#define GB_E_OOM        -3
+#define GB_E_CUDA       -4
+#define GB_E_NCCL       -5
+#define GB_E_CAPACITY   -6   /* more than 2^31-1 kept k-mers on one GPU, or a caller buffer too small */
+#define GB_E_INVARIANT  -7   /* a graph invariant failed (assert at S/data/graph/Graph.scala:357) */
+#define GB_E_STATE      -8   /* call not valid in the handle's current state */
+
+/* gb_map_create flags */
+#define GB_FLAG_HASH_SCALA_210  1u  /* Long.## of scala >= 2.10 instead of the pinned 2.9.1 */
+
+typedef struct gb_map gb_map;     /* DNAMap[Int]: one shard (one GPU) of the k-mer count table */
+typedef struct gb_graph gb_graph; /* Graph / MapGraph */
+typedef struct gb_comm gb_comm;   /* the set of shards of a PartitionedDNAMap: one rank per GPU */
+
+const char *gb_last_error(void);
+/* diagnostics: kernels launched by this library in this process so far */
+long long gb_launch_count(void);
+/* diagnostics: empirical random-access ceiling of a table of table_bytes (one 8-byte key read + one 4-byte
+ * red.add per update, no hashing or probing): ns per pass of n_updates, averaged over iters passes */
+int gb_bench_random_atomics(int device, size_t table_bytes, int64_t n_updates, int iters, int64_t *ns_per_iter);
+int gb_version(void);
+int gb_device_count(int *n);
+
+/* pinned host staging memory for the .bin stream (optional; any host pointer is accepted by the calls below) */
+int gb_host_alloc(size_t n_bytes, void **ptr);
+int gb_host_free(void *ptr);
+
+/* ------------------------------------------------------------------------------------------------
+ * DNAMap[Int]  (trait DNAMap, S/ds/ArrayDNAMap.scala:49-60; ArrayDNAMap 62-243)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* new ArrayDNAMap[Int](k) (ArrayDNAMap.scala:62-72).  min_capacity = expected number of distinct keys
+ * (0 = unknown: the table starts small and grows by rehashing, like rescale() 217-230). */
+int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_map **out);
+int gb_map_destroy(gb_map *m);
+
+/* FreqFilter.add over a `.bin` stream (S/data/FreqFilter.scala:28-36,44-49 + PairedEndData.getPairs,
+ * S/data/PairedEndData.scala:20-36): for each of the first n_reads reads with len >= k, every k-window x is
+ * canonicalised (y = x if x.hashCode < rc(x).hashCode else rc(x)) and update(y, 1, _ + 1) is applied.
+ * `bin` is a HOST buffer; *n_windows (optional) receives the number of updates. */
+int gb_map_insert_reads(gb_map *m, const uint8_t *bin, size_t n_bytes, int64_t n_reads, int64_t *n_windows);
+
+/* same, with the stream already resident in device memory (d_bin: cudaMalloc'ed on the map's device).
+ * d_offsets: n_reads+1 record offsets on the device, or NULL when every record has the same length. */
+int gb_map_insert_reads_device(gb_map *m, const uint8_t *d_bin, size_t n_bytes, const uint64_t *d_offsets,
+                               int64_t n_reads, int64_t *n_windows);
+
+/* update(key, 1, _ + 1) for n keys taken as they are (DNAMap.update(key, v0, f), ArrayDNAMap.scala:198-203
+ * with the closure of FreqFilter.scala:33).  Keys need not be canonical. */
+int gb_map_update_counts(gb_map *m, const uint64_t *keys, int64_t n);
+/* update(key, v) (ArrayDNAMap.scala:191-196) for n (key, value) pairs; later pairs win on duplicate keys
+ * only if the caller orders the calls (within one call duplicates are a caller error). */
+int gb_map_update(gb_map *m, const uint64_t *keys, const int32_t *vals, int64_t n);
+
+/* size (ArrayDNAMap.scala:71) */
+int gb_map_size(gb_map *m, int64_t *size);
+/* apply / contains (ArrayDNAMap.scala:181-184,232): counts[i] = value or 0, found[i] = 0/1; either may be NULL */
+int gb_map_lookup(gb_map *m, const uint64_t *keys, int64_t n, int32_t *counts, uint8_t *found);
+/* deleteAll((k, v) => v < min_count) (ArrayDNAMap.scala:212-215 with the predicate of FreqFilter.scala:55) */
+int gb_map_delete_below(gb_map *m, int32_t min_count);
+/* mapReduce / foreach (ArrayDNAMap.scala:234-241): the host closure runs over the exported arrays.
+ * Call with keys == NULL to get *n only.  Order is unspecified (hash order in the reference too). */
+int gb_map_export(gb_map *m, uint64_t *keys, int32_t *vals, int64_t cap, int64_t *n);
+/* incoming / outcoming (S/data/graph/Graph.scala:270-282) for n query k-mers against the current contents:
+ * masks[i] bit b (0..3) = outcoming has base b, bit 4+b = incoming has base b (Base.fromInt order). */
+int gb_map_neighbour_masks(gb_map *m, const uint64_t *keys, int64_t n, uint8_t *masks);
+
+/* empty the map and size it for min_capacity distinct keys (a fresh `new ArrayDNAMap[Int](k)` that reuses the
+ * handle, its streams and the pooled device memory) */
+int gb_map_clear(gb_map *m, int64_t min_capacity);
+/* device-side stopwatch on the handle's stream (CUDA events): start, issue calls, stop (synchronises) */
+int gb_timer_start(gb_map *m);
+int gb_timer_stop(gb_map *m, int64_t *ns);
+/* wait for every asynchronous operation issued on the handle */
+int gb_sync(gb_map *m);
+
+/* counters: [0] capacity (slots) [1] table bytes [2] rehash/grow count [3] windows inserted so far
+ * [4] last insert kernel time in ns (CUDA events) [5] fixed-stride fast path used (0/1) */
+int gb_map_stats(gb_map *m, int64_t stats[8]);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph  (trait Graph / MapGraph / object Graph, S/data/graph/Graph.scala)
+ * Nodes and edges are addressed by their index in the most recent gb_graph_counts/export (the
+ * reference's ids are not reproducible even reference-vs-reference).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Graph.buildGraph(k, kmersFreq) (Graph.scala:269-382) on the map's current contents */
+int gb_graph_build(gb_map *m, gb_graph **out);
+int gb_graph_destroy(gb_graph *g);
+/* getNodes.size, getEdges.size, getEdges.map(_.seq.length).sum (GraphBuilder.scala:39) */
+int gb_graph_counts(gb_graph *g, int64_t *n_nodes, int64_t *n_edges, int64_t *n_edge_bases);
+/* node_kmers[n_nodes]; edge_start/edge_end[n_edges] = node indices; edge_off[n_edges+1] in BASES into one
+ * 2-bit stream edge_bases_2bit[(n_edge_bases+3)/4] (base j at byte j/4, bits 2(j%4)).  Any pointer may be NULL. */
+int gb_graph_export(gb_graph *g, uint64_t *node_kmers, uint32_t *edge_start, uint32_t *edge_end,
+                    uint64_t *edge_off, uint8_t *edge_bases_2bit);
+/* Graph.components (Graph.scala:54-72): node_label[n_nodes] in 0..*n_components-1 (may be NULL) */
+int gb_graph_components(gb_graph *g, uint32_t *node_label, int64_t *n_components);
+/* graph.retain(components.maxBy(_.size)) (GraphBuilder.scala:52-54, MapGraph.retain Graph.scala:161-165);
+ * ties (the norm: strand twins) go to the component holding the smallest node k-mer */
+int gb_graph_retain_largest(gb_graph *g);
+/* MapGraph.simplifyGraph (Graph.scala:211-230) */
+int gb_graph_simplify(gb_graph *g);
+/* Graph.removeBubbles (Graph.scala:125-149), out-edges taken in Base.fromInt order */
+int gb_graph_remove_bubbles(gb_graph *g);
+/* removeEdge for a list of edge indices (Graph.scala:191-195; the call at GraphSimplifier.scala:316) */
+int gb_graph_remove_edges(gb_graph *g, const uint32_t *edge_idx, int64_t n);
+/* EXTENSION, no reference counterpart: one sweep of dead-end tip removal */
+int gb_graph_clip_tips(gb_graph *g, int64_t max_len, int64_t *removed);
+/* invariants of S/scripts/GraphSimplifier.scala:159-170 evaluated on the device; GB_E_INVARIANT if broken */
+int gb_graph_check(gb_graph *g);
+/* counters of the build: [0] stored k-mers seen [1] pointer-jumping launches [2] oriented k-mers on perfect
+ * cycles, dropped like the reference does (Graph.scala:375) [3] build time in ns (CUDA events) */
+int gb_graph_stats(gb_graph *g, int64_t stats[8]);
+
+/* ------------------------------------------------------------------------------------------------
+ * PartitionedDNAMap  (S/ds/PartitionedDNAMap.scala:15-63): one hash-prefix shard per GPU, one process
+ * (rank) per GPU, k-mers routed to their owner by an all-to-all over NVLink.
+ * Every gb_pmap_* call is collective: all ranks of the communicator call it in the same order.
+ * ---------------------------------------------------------------------------------------------- */
+#define GB_UNIQUE_ID_BYTES 128
+int gb_comm_unique_id(uint8_t id[GB_UNIQUE_ID_BYTES]);            /* rank 0, then broadcast by the host */
+int gb_comm_create(const uint8_t id[GB_UNIQUE_ID_BYTES], int rank, int n_ranks, int device, gb_comm **out);
+int gb_comm_destroy(gb_comm *c);
+
+/* new PartitionedDNAMap[Int](k) (PartitionedDNAMap.scala:15-28): this rank's shard, bound to the communicator */
+int gb_pmap_create(gb_comm *c, int k, int64_t min_capacity_per_shard, uint32_t flags, gb_map **out);
+/* FreqFilter.add over THIS RANK's slice of the read stream; k-mers go to partition(key) (60-63) */
+int gb_pmap_insert_reads(gb_map *m, const uint8_t *bin, size_t n_bytes, int64_t n_reads, int64_t *n_windows);
+int gb_pmap_insert_reads_device(gb_map *m, const uint8_t *d_bin, size_t n_bytes, const uint64_t *d_offsets,
+                                int64_t n_reads, int64_t *n_windows);
+/* size = sum over partitions (PartitionedDNAMap.scala:31) */
+int gb_pmap_size(gb_map *m, int64_t *size);
+/* deleteAll broadcast (49-51): no communication, every shard filters itself */
+int gb_pmap_delete_below(gb_map *m, int32_t min_count);
+/* apply/contains routed to the owner shard and back (33,53); every rank passes its own queries */
+int gb_pmap_lookup(gb_map *m, const uint64_t *keys, int64_t n, int32_t *counts, uint8_t *found);
+/* Graph.buildGraph over all shards; the compacted graph is materialised on every rank */
+int gb_pmap_graph_build(gb_map *m, gb_graph **out);
+/* owner shard of a k-mer (any function is unobservable in the reference) */
+int gb_pmap_owner(gb_map *m, const uint64_t *keys, int64_t n, int32_t *owner);
+/* the same partition(key) (PartitionedDNAMap.scala:60-63) for n_parts shards: host arithmetic, needs no GPU */
+int gb_owner_of(const uint64_t *keys, int64_t n, int n_parts, int32_t *owner);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
