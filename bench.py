@@ -71,7 +71,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -80,9 +80,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -93,7 +93,11 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if t_begin is None or (t_begin <= t <= t_end + 0.06)]
+        window = "timed region"
+        if not inside:  # region shorter than one sampling period: use the samples of warm-up + timed region
+            inside, window = [r for (_, r) in self.rows], "warm-up + timed region (timed region shorter than a sampling period)"
+        for r in inside:
             if len(r) < 6:
                 continue
             try:
@@ -104,7 +108,8 @@ class ClockSampler:
             for nm, v in zip(names, r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "window": window}
 
 
 def cpu_reference(b, n_reads, windows, threads, steps, warmup, sample_reads):
@@ -133,7 +138,7 @@ def cpu_reference(b, n_reads, windows, threads, steps, warmup, sample_reads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
@@ -220,9 +225,12 @@ def main():
         comm = None
         m = ArrayDNAMap(K, cap, device=local_rank)
 
+    insert_stats = {}
+
     def step_device():
         m.clear(cap)
         w = m.insert_reads_device(d_bin.data_ptr(), b.size, n_reads)
+        insert_stats.update(m.stats())  # table size and insert-kernel time before the filter shrinks the table
         m.delete_below(ROUNDS)
         return w
 
@@ -233,30 +241,32 @@ def main():
         return w, m.size  # the size read is the step's device->host result
 
     # ---------------- kernel leg: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         assert step_device() == windows
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = L.gb_launch_count()
     insert_ns = []
+    table_bytes = 0
     barrier()
     t0 = time.perf_counter()
     m.timer_start()
     for _ in range(args.steps):
         step_device()
-        insert_ns.append(m.stats()["last_insert_ns"])
+        insert_ns.append(insert_stats["last_insert_ns"])
     dev_ns = m.timer_stop()
     barrier()
-    wall = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    wall = t1 - t0
     launches = L.gb_launch_count() - launches0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t0, t1)
     step_s = max_over_ranks(dev_ns * 1e-9 / args.steps)
     wall_step_s = max_over_ranks(wall / args.steps)
     total_windows = sum_over_ranks(float(windows))
     value = total_windows / step_s
     kept_total = m.size
-    table_bytes = m.stats()["table_bytes"]
+    table_bytes = insert_stats["table_bytes"]
 
     # ---------------- e2e leg: host buffers through the reference-facing calls
     for _ in range(2):
@@ -273,18 +283,21 @@ def main():
     # ---------------- graph stage on the filtered table (timed once; collective for N > 1)
     graph = None
     if not args.no_graph:
-        step_device()
-        barrier()
-        t0 = time.perf_counter()
-        g = Graph.buildGraph(K, m)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        nn, ne, nb = g.counts()
-        nc, _ = g.components()
-        g.retain_largest()
-        g.simplifyGraph()
-        torch.cuda.synchronize()
-        t2 = time.perf_counter()
+        for rep in range(2):  # first pass warms the module, the pool and the allocator; the second is timed
+            step_device()
+            barrier()
+            t0 = time.perf_counter()
+            g = Graph.buildGraph(K, m)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            nn, ne, nb = g.counts()
+            nc, _ = g.components()
+            g.retain_largest()
+            g.simplifyGraph()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            if rep == 0:
+                g.close()
         graph = {"build_ms": max_over_ranks((t1 - t0) * 1e3), "build_kernels_ms": g.stats()["build_ns"] * 1e-6,
                  "components_retain_simplify_ms": max_over_ranks((t2 - t1) * 1e3),
                  "nodes": nn, "edges": ne, "edge_bases": nb, "components": nc, "jump_launches": g.stats()["jump_launches"],

@@ -39,7 +39,7 @@ static inline size_t base_words(int64_t n_bases) { return (size_t)((n_bases + 15
 constexpr unsigned long long TAG_UNRES = 0ull, TAG_RES = 1ull, TAG_TERM = 2ull, TAG_NONE = 3ull;
 __host__ __device__ __forceinline__ unsigned long long a_make(unsigned long long tag, unsigned long long ptr, unsigned long long dist)
 {
-    return (tag << 62) | (ptr << 31) | dist;
+    return (tag << 62) | (ptr << 31) | (dist & 0x7FFFFFFFull); // dist wraps only on perfect cycles, where it is unused
 }
 __host__ __device__ __forceinline__ unsigned int a_tag(unsigned long long a) { return (unsigned int)(a >> 62); }
 __host__ __device__ __forceinline__ unsigned int a_ptr(unsigned long long a) { return (unsigned int)((a >> 31) & 0x7FFFFFFFu); }

@@ -200,6 +200,9 @@ class _MapBase:
         """A fresh map on the same handle (new ArrayDNAMap[Int](k)), sized for min_capacity distinct keys."""
         capi.check(capi.lib().gb_map_clear(self.h, int(min_capacity)))
 
+    def sync(self):
+        capi.check(capi.lib().gb_sync(self.h))
+
     def timer_start(self):
         capi.check(capi.lib().gb_timer_start(self.h))
 

@@ -233,7 +233,8 @@ def test_remove_edges_then_simplify(gpu):
     # oracle edge ids = position among ALL edges ever created (all alive here) + 1
     oidx = [i + 1 for i in range(oes.size) if (by_id[int(oes[i])], by_id[int(oee[i])], obases[int(ooff[i]):int(ooff[i + 1])].tobytes()) in pick]
     g.removeEdges(np.array(gidx, np.uint32))
-    pyoracle.lib().go_graph_remove_edges(og.h, np.array(oidx, np.int64).ctypes.data, len(oidx))
+    oarr = np.array(oidx, np.int64)  # keep the array alive across the call
+    assert pyoracle.lib().go_graph_remove_edges(og.h, oarr.ctypes.data, oarr.size) == len(gidx)
     H.assert_graph_equal(g, og)
     g.simplifyGraph(); og.simplify()
     H.assert_graph_equal(g, og)
