@@ -39,7 +39,7 @@ def build(force=False, verbose=False):
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-shared", "-o", LIB + ".tmp"] + srcs + ["-lnccl", "-lcudart"]
+          ["-shared", "-o", LIB + ".tmp"] + srcs + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

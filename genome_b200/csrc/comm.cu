@@ -8,7 +8,8 @@
 //   all-to-all   : counts (P x u64), then grouped ncclSend/ncclRecv of the segments  (stream `route`)
 //   insert       : update(key, 1, _ + 1) for every received key                      (the map's stream)
 // Two buffer sets: batch b+1 is routed and exchanged while batch b is inserted.
-#include <nccl.h>
+#include <dlfcn.h>
+#include <nccl.h> // types only: the library is bound at run time (see NcclApi)
 
 #include <algorithm>
 #include <vector>
@@ -25,6 +26,65 @@ struct Comm {
     ncclComm_t nccl = nullptr;
     cudaStream_t stream = nullptr; // routing + collectives
 };
+
+// NCCL is bound with dlopen at the first gb_comm_* call, not at link time: a process that already holds an NCCL
+// (a JVM with its own, or Python with torch's bundled libnccl.so.2) shares that copy through the SONAME, and a
+// single-GPU user never needs NCCL at all.  GENOME_B200_NCCL names an explicit path.
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load()
+{
+    if (g_nccl.handle) return GB_OK;
+    const char *names[] = { getenv("GENOME_B200_NCCL"), "libnccl.so.2", "libnccl.so" };
+    void *h = nullptr;
+    for (const char *n : names)
+        if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) { set_error("cannot load NCCL (libnccl.so.2): %s", dlerror()); return GB_E_NCCL; }
+    NcclApi a;
+    a.handle = h;
+#define GB_SYM(field, name)                                                       \
+    *(void **)(&a.field) = dlsym(h, name);                                        \
+    if (!a.field) { set_error("NCCL symbol %s missing", name); return GB_E_NCCL; }
+    GB_SYM(GetUniqueId, "ncclGetUniqueId")
+    GB_SYM(CommInitRank, "ncclCommInitRank")
+    GB_SYM(CommDestroy, "ncclCommDestroy")
+    GB_SYM(GetErrorString, "ncclGetErrorString")
+    GB_SYM(GroupStart, "ncclGroupStart")
+    GB_SYM(GroupEnd, "ncclGroupEnd")
+    GB_SYM(Send, "ncclSend")
+    GB_SYM(Recv, "ncclRecv")
+    GB_SYM(AllReduce, "ncclAllReduce")
+    GB_SYM(AllGather, "ncclAllGather")
+    GB_SYM(Broadcast, "ncclBroadcast")
+#undef GB_SYM
+    g_nccl = a;
+    return GB_OK;
+}
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclCommDestroy g_nccl.CommDestroy
+#define ncclGetErrorString g_nccl.GetErrorString
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
+#define ncclSend g_nccl.Send
+#define ncclRecv g_nccl.Recv
+#define ncclAllReduce g_nccl.AllReduce
+#define ncclAllGather g_nccl.AllGather
+#define ncclBroadcast g_nccl.Broadcast
 
 static int nccl_fail(ncclResult_t r, const char *what, const char *file, int line)
 {
@@ -314,6 +374,7 @@ int gb_comm_unique_id(uint8_t id[GB_UNIQUE_ID_BYTES])
 {
     if (!id) { set_error("null argument"); return GB_E_ARG; }
     static_assert(sizeof(ncclUniqueId) <= GB_UNIQUE_ID_BYTES, "unique id does not fit");
+    GB_TRY(nccl_load());
     ncclUniqueId u;
     GB_NCCL(ncclGetUniqueId(&u));
     memset(id, 0, GB_UNIQUE_ID_BYTES);
@@ -326,6 +387,7 @@ int gb_comm_create(const uint8_t id[GB_UNIQUE_ID_BYTES], int rank, int n_ranks, 
     if (!id || !out) { set_error("null argument"); return GB_E_ARG; }
     *out = nullptr;
     if (n_ranks < 1 || n_ranks > MAX_RANKS || rank < 0 || rank >= n_ranks) { set_error("bad rank %d of %d", rank, n_ranks); return GB_E_ARG; }
+    GB_TRY(nccl_load());
     int ndev = 0;
     GB_CUDA(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) { set_error("device %d not present (%d devices)", device, ndev); return GB_E_CUDA; }

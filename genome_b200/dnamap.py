@@ -235,6 +235,7 @@ class Communicator:
     rank 0 to the others (any host transport: torch.distributed, a file, a socket)."""
 
     def __init__(self, rank, world, device, broadcast):
+        _prefer_torch_nccl()
         ident = np.zeros(capi.GB_UNIQUE_ID_BYTES, np.uint8)
         if rank == 0:
             capi.check(capi.lib().gb_comm_unique_id(capi.ptr(ident)))
@@ -248,6 +249,20 @@ class Communicator:
         if getattr(self, "h", None):
             capi.lib().gb_comm_destroy(self.h)
             self.h = None
+
+
+def _prefer_torch_nccl():
+    """The library binds NCCL with dlopen("libnccl.so.2").  If torch may be imported later in this process, make sure
+    the copy that gets bound is torch's bundled one (a newer system-wide copy loaded first would break torch)."""
+    import os
+    import sys
+    if "torch" in sys.modules or os.environ.get("GENOME_B200_NCCL"):
+        return
+    for p in sys.path:
+        cand = os.path.join(p, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["GENOME_B200_NCCL"] = cand
+            return
 
 
 def torch_broadcast(ident):

@@ -1,0 +1,83 @@
+"""Worker of tests/test_parity_multigpu.py (torch.distributed.run, one rank per GPU): PartitionedDNAMap over the
+library's NCCL all-to-all, checked against the oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from genome_b200.dnamap import Communicator, PairedEndData, PartitionedDNAMap, FreqFilter, owner_of, torch_broadcast  # noqa: E402
+from genome_b200.graph import Graph  # noqa: E402
+from oracle import pyoracle  # noqa: E402
+from tests import helpers as H  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = Communicator(rank, world, local, torch_broadcast)
+    for (k, glen, rl, cov, err, rounds, ragged, cap) in [(31, 60000, 100, 20, 0.01, 3, False, 1 << 20), (21, 20000, 80, 12, 0.02, 2, True, 0),
+                                                        (9, 3000, 40, 12, 0.02, 1, False, 0)]:
+        b, n, _ = H.small_reads(glen, rl, cov, err, seed=900 + k, ragged=ragged)  # same bytes on every rank
+        data = PairedEndData(b, n // 2)
+        mine = data.shard(rank, world)
+        m = PartitionedDNAMap(k, comm, cap)
+        w = m.insert_reads(mine)
+        om, ow = H.oracle_counts(b, n, k)
+        tw = torch.tensor([w], device="cuda")
+        dist.all_reduce(tw)
+        assert int(tw.item()) == ow, (int(tw.item()), ow)
+        assert m.size == om.size()
+        # this shard holds exactly the oracle's keys that it owns
+        ok, ov = om.export_sorted()
+        sel = owner_of(ok, world) == rank
+        gk, gv = m.export_sorted()
+        assert np.array_equal(gk, ok[sel]) and np.array_equal(gv, ov[sel])
+        assert m.local_size == int(sel.sum())
+        # routed lookups: every rank asks about its own mix of present and absent keys
+        rng = np.random.default_rng(rank)
+        q = np.concatenate([ok[rank::7][:3000], rng.integers(0, 1 << (2 * k), size=1000 + 10 * rank, dtype=np.uint64)])
+        counts, found = m.lookup(q)
+        for i in range(0, q.size, 13):
+            v = om.apply(int(q[i]))
+            assert found[i] == (v is not None) and counts[i] == (v or 0)
+        # deleteAll + buildGraph over all shards
+        m.delete_below(rounds)
+        om.delete_below(rounds)
+        assert m.size == om.size()
+        g = Graph.buildGraph(k, m)
+        og = pyoracle.OracleGraph(om)
+        H.assert_graph_equal(g, og)
+        g.retain_largest(); og.retain_largest()
+        g.simplifyGraph(); og.simplify()
+        H.assert_graph_equal(g, og)
+        g.close()
+        m.close()
+    # the device-resident entry point, fixed stride
+    k = 31
+    b, n, _ = H.small_reads(50000, 100, 10, 0.01, seed=321)
+    mine = PairedEndData(b, n // 2).shard(rank, world)
+    d = torch.zeros(mine.bin.size + 16, dtype=torch.uint8, device="cuda")
+    d[:mine.bin.size].copy_(torch.from_numpy(mine.bin))
+    m = PartitionedDNAMap(k, comm, 1 << 20)
+    m.insert_reads_device(d.data_ptr(), mine.bin.size, mine.n_reads)
+    om, ow = H.oracle_counts(b, n, k)
+    assert m.size == om.size()
+    ok, ov = om.export_sorted()
+    sel = owner_of(ok, world) == rank
+    gk, gv = m.export_sorted()
+    assert np.array_equal(gk, ok[sel]) and np.array_equal(gv, ov[sel])
+    m.close()
+    dist.barrier()
+    comm.close()
+    if rank == 0:
+        print("PMAP OK world", world)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

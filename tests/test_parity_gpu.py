@@ -330,3 +330,93 @@ def test_error_free_linear_genome_is_two_edges(gpu):
     assert g.counts()[:2] == (2, 1)
     g.simplifyGraph()
     assert g.counts()[:2] == (2, 1)
+
+
+def test_golden_fixture_on_gpu(gpu):
+    """The committed fixture (tests/golden/small_k15.json, written by make_golden.py from the oracle)."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "small_k15.json")))
+    b = np.frombuffer(bytes.fromhex(gold["bin_hex"]), np.uint8)
+    m = ArrayDNAMap(gold["k"])
+    assert m.insert_reads(b, gold["n_reads"]) == gold["windows"]
+    keys, vals = m.export_sorted()
+    assert [int(x) for x in keys] == gold["keys"] and [int(x) for x in vals] == gold["counts"]
+    m.delete_below(gold["rounds"])
+    g = Graph.buildGraph(gold["k"], m)
+    nodes, edges = H.canon_gpu_graph(g)
+    assert nodes == gold["nodes"]
+    assert [[u, v, s.hex()] for (u, v, s) in edges] == gold["edges"]
+    g.retain_largest()
+    g.simplifyGraph()
+    _, edges = H.canon_gpu_graph(g)
+    assert [[u, v, s.hex()] for (u, v, s) in edges] == gold["edges_after_retain_simplify"]
+
+
+def test_device_resident_stream_and_clear(gpu):
+    """gb_map_insert_reads_device (fixed stride and with explicit offsets) and gb_map_clear."""
+    import torch
+    k = 25
+    b, n, _ = H.small_reads(30000, 100, 10, 0.01, seed=55)
+    om, ow = H.oracle_counts(b, n, k)
+    ok, ov = om.export_sorted()
+    d = torch.zeros(b.size + 16, dtype=torch.uint8, device="cuda")
+    d[:b.size].copy_(torch.from_numpy(b))
+    m = ArrayDNAMap(k, 1 << 20)
+    for rep in range(2):
+        assert m.insert_reads_device(d.data_ptr(), b.size, n) == ow
+        gk, gv = m.export_sorted()
+        assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
+        m.clear(1 << 20)
+        assert m.size == 0
+    off = torch.from_numpy(PairedEndData(b, n // 2).record_offsets().astype(np.int64)).cuda()
+    assert m.insert_reads_device(d.data_ptr(), b.size, n, off.data_ptr()) == ow
+    gk, gv = m.export_sorted()
+    assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
+    # ragged stream with offsets
+    rb, rn, _ = H.small_reads(20000, 120, 8, 0.01, seed=56, ragged=True)
+    rm, rw = H.oracle_counts(rb, rn, k)
+    d2 = torch.zeros(rb.size + 16, dtype=torch.uint8, device="cuda")
+    d2[:rb.size].copy_(torch.from_numpy(rb))
+    off2 = torch.from_numpy(PairedEndData(rb, rn // 2).record_offsets().astype(np.int64)).cuda()
+    m.clear(0)
+    assert m.insert_reads_device(d2.data_ptr(), rb.size, rn, off2.data_ptr()) == rw
+    gk, gv = m.export_sorted()
+    rk, rv = rm.export_sorted()
+    assert np.array_equal(gk, rk) and np.array_equal(gv, rv)
+    # a ragged stream without offsets is refused
+    m.clear(0)
+    with pytest.raises(capi.GenomeError):
+        m.insert_reads_device(d2.data_ptr(), rb.size, rn)
+
+
+def test_full_size_properties_c1(gpu):
+    """BASELINE configs[0] at full size (4.6 Mbp, 100 bp error-free reads at 30x, k = 31) through size-independent
+    properties: sum of counts = windows; the kept set is the genome's k-mers; 4 nodes / 2 edges spelling the genome
+    span and its reverse complement; deleteAll is idempotent."""
+    k = 31
+    b, n, genome = synth.make_config("C1")
+    m = ArrayDNAMap(k, 6_000_000)
+    w = m.insert_reads(b, n)
+    assert w == n * (100 - k + 1)
+    keys, vals = m.export()
+    assert int(vals.astype(np.int64).sum()) == w
+    assert len(np.unique(keys)) == keys.size == m.size
+    m.delete_below(3)
+    s1 = m.size
+    m.delete_below(3)
+    assert m.size == s1
+    g = Graph.buildGraph(k, m)
+    nn, ne, nb = g.counts()
+    # 30x coverage with a threshold of 3 leaves a few gaps: every component is a strand pair of one linear contig
+    nc, label = g.components()
+    assert nn == 2 * nc and ne == nc and nn % 4 == 0
+    # sum of edge lengths = oriented kept k-mers - oriented node k-mers + edges (SURVEY 8c(iii)); no isolated k-mers
+    assert nb == (2 * s1 - nn) + ne
+    g.retain_largest()
+    g.simplifyGraph()
+    assert g.counts()[:2] == (2, 1)
+    node_kmer, es, ee, off, bases = g.export()
+    contig = synth.int_to_kmer(int(node_kmer[es[0]]), k) + synth.decode(bases)
+    gs = synth.decode(genome)
+    assert contig in gs or contig in synth.decode(H.revcomp_codes(genome))
