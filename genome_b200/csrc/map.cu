@@ -41,6 +41,12 @@ int pool_setup(int device)
     GB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     unsigned long long keep = ~0ull;
     GB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    // Random 16-byte slot accesses use one 32-byte sector of a 128-byte L2 line: ask L2 not to fetch the neighbours
+    // (ncu r1a: 138 B of DRAM reads per k-mer with the default granularity).  GENOME_B200_L2_FETCH overrides.
+    size_t gran = 32;
+    if (const char *e = getenv("GENOME_B200_L2_FETCH")) gran = (size_t)atoi(e);
+    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); // a hint: failure is not an error
+    cudaGetLastError();
     return GB_OK;
 }
 
