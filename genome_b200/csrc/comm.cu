@@ -16,15 +16,30 @@
 
 #include "common.cuh"
 #include "extract.cuh"
+#include "partition.cuh"
 
 namespace gb {
 
 constexpr int MAX_RANKS = 64;
 
+// one of the two staging sets of the sharded insert; lives as long as the communicator
+struct BatchBufs {
+    unsigned long long *send = nullptr, *recv = nullptr;
+    size_t send_cap = 0, recv_cap = 0;
+    unsigned long long *d_tot = nullptr, *h_tot = nullptr; // bucket totals (mine, received) and the upsert's chunk table
+    PartWork work;
+    cudaEvent_t exchanged = nullptr, inserted = nullptr;
+    bool in_flight = false;
+    int ensure(size_t ns, size_t nr);
+    void release();
+};
+
 struct Comm {
     int rank = 0, n_ranks = 1, device = 0;
     ncclComm_t nccl = nullptr;
-    cudaStream_t stream = nullptr; // routing + collectives
+    cudaStream_t stream = nullptr; // bucketing + collectives
+    BatchBufs bufs[2];
+    unsigned long long *d_scratch = nullptr, *h_scratch = nullptr;
 };
 
 // NCCL is bound with dlopen at the first gb_comm_* call, not at link time: a process that already holds an NCCL
@@ -97,80 +112,6 @@ static int nccl_fail(ncclResult_t r, const char *what, const char *file, int lin
         if (_r != ncclSuccess) return gb::nccl_fail(_r, #expr, __FILE__, __LINE__); \
     } while (0)
 
-// ---------------------------------------------------------------- routing kernels
-// pass 1: per-owner histogram of the batch (shared-memory histogram, one global atomic per owner per CTA)
-template <bool FIXED, bool V210>
-__global__ void __launch_bounds__(INSERT_THREADS)
-route_count_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes, const unsigned long long *__restrict__ offsets,
-                   unsigned int rec_bytes, long long read0, long long n_reads, int k, unsigned int parts,
-                   unsigned long long *owner_count)
-{
-    __shared__ ReadTile tile;
-    __shared__ unsigned int s_hist[MAX_RANKS];
-    const int tid = threadIdx.x;
-    const int nr = stage_tile<FIXED>(tile, bin, n_bytes, offsets, rec_bytes, read0, n_reads, k);
-    if (nr <= 0) return;
-    if (tid < MAX_RANKS) s_hist[tid] = 0;
-    __syncthreads();
-    const unsigned int total_items = tile.prefix[TILE_READS];
-    for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
-        unsigned long long key[SEG];
-        const int cnt = item_keys<V210>(tile, item, k, key);
-#pragma unroll
-        for (int j = 0; j < SEG; j++)
-            if (j < cnt) atomicAdd(&s_hist[owner_of(mix64(key[j]), parts)], 1u);
-    }
-    __syncthreads();
-    if (tid < (int)parts && s_hist[tid]) atomicAdd(&owner_count[tid], (unsigned long long)s_hist[tid]);
-}
-
-// pass 2: each CTA reserves its share of every owner's segment, then writes the keys
-template <bool FIXED, bool V210>
-__global__ void __launch_bounds__(INSERT_THREADS)
-route_scatter_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes, const unsigned long long *__restrict__ offsets,
-                     unsigned int rec_bytes, long long read0, long long n_reads, int k, unsigned int parts,
-                     const unsigned long long *seg_base, unsigned long long *seg_cursor, unsigned long long *send)
-{
-    __shared__ ReadTile tile;
-    __shared__ unsigned int s_hist[MAX_RANKS];
-    __shared__ unsigned long long s_base[MAX_RANKS];
-    const int tid = threadIdx.x;
-    const int nr = stage_tile<FIXED>(tile, bin, n_bytes, offsets, rec_bytes, read0, n_reads, k);
-    if (nr <= 0) return;
-    if (tid < MAX_RANKS) s_hist[tid] = 0;
-    __syncthreads();
-    const unsigned int total_items = tile.prefix[TILE_READS];
-    for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
-        unsigned long long key[SEG];
-        const int cnt = item_keys<V210>(tile, item, k, key);
-#pragma unroll
-        for (int j = 0; j < SEG; j++)
-            if (j < cnt) atomicAdd(&s_hist[owner_of(mix64(key[j]), parts)], 1u);
-    }
-    __syncthreads();
-    if (tid < (int)parts) {
-        s_base[tid] = seg_base[tid] + (s_hist[tid] ? atomicAdd(&seg_cursor[tid], (unsigned long long)s_hist[tid]) : 0);
-        s_hist[tid] = 0;
-    }
-    __syncthreads();
-    for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
-        unsigned long long key[SEG];
-        const int cnt = item_keys<V210>(tile, item, k, key);
-#pragma unroll
-        for (int j = 0; j < SEG; j++)
-            if (j < cnt) {
-                unsigned int o = owner_of(mix64(key[j]), parts);
-                send[s_base[o] + atomicAdd(&s_hist[o], 1u)] = key[j];
-            }
-    }
-}
-
-__global__ void owner_kernel(const unsigned long long *keys, long long n, unsigned int parts, int *owner)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) owner[i] = (int)owner_of(mix64(keys[i]), parts);
-}
-
 // ---------------------------------------------------------------- host helpers
 
 // variable all-to-all of u64 elements: send segment p (send_off[p], send_cnt[p]) goes to rank p
@@ -187,17 +128,32 @@ static int all_to_all_v(Comm *c, const unsigned long long *send, const unsigned 
     return GB_OK;
 }
 
+// fixed-size all-to-all: `row` u64 per pair, row p of d_send goes to rank p, row p of d_recv comes from rank p
+static int all_to_all_rows(Comm *c, const unsigned long long *d_send, unsigned long long *d_recv, size_t row)
+{
+    GB_NCCL(ncclGroupStart());
+    for (int p = 0; p < c->n_ranks; p++) {
+        GB_NCCL(ncclSend(d_send + (size_t)p * row, row, ncclUint64, p, c->nccl, c->stream));
+        GB_NCCL(ncclRecv(d_recv + (size_t)p * row, row, ncclUint64, p, c->nccl, c->stream));
+    }
+    GB_NCCL(ncclGroupEnd());
+    return GB_OK;
+}
+
+static int comm_scratch(Comm *c)
+{
+    if (c->d_scratch) return GB_OK;
+    GB_CUDA(cudaMalloc((void **)&c->d_scratch, 4 * MAX_BUCKETS * 8));
+    GB_CUDA(cudaHostAlloc((void **)&c->h_scratch, 4 * MAX_BUCKETS * 8, cudaHostAllocDefault));
+    return GB_OK;
+}
+
 // every rank contributes P counts; afterwards recv_cnt[p] = what rank p sends to me
 static int exchange_counts(Comm *c, unsigned long long *d_send_cnt, unsigned long long *d_recv_cnt,
                            unsigned long long *h_send_cnt, unsigned long long *h_recv_cnt)
 {
     const int P = c->n_ranks;
-    GB_NCCL(ncclGroupStart());
-    for (int p = 0; p < P; p++) {
-        GB_NCCL(ncclSend(d_send_cnt + p, 1, ncclUint64, p, c->nccl, c->stream));
-        GB_NCCL(ncclRecv(d_recv_cnt + p, 1, ncclUint64, p, c->nccl, c->stream));
-    }
-    GB_NCCL(ncclGroupEnd());
+    GB_TRY(all_to_all_rows(c, d_send_cnt, d_recv_cnt, 1));
     GB_CUDA(cudaMemcpyAsync(h_send_cnt, d_send_cnt, P * 8, cudaMemcpyDeviceToHost, c->stream));
     GB_CUDA(cudaMemcpyAsync(h_recv_cnt, d_recv_cnt, P * 8, cudaMemcpyDeviceToHost, c->stream));
     GB_CUDA(cudaStreamSynchronize(c->stream));
@@ -206,47 +162,49 @@ static int exchange_counts(Comm *c, unsigned long long *d_send_cnt, unsigned lon
 
 static int all_reduce_i64(Comm *c, int64_t *v, ncclRedOp_t op)
 {
-    DeviceBuf d;
-    GB_TRY(d.alloc(8));
-    GB_CUDA(cudaMemcpyAsync(d.p, v, 8, cudaMemcpyHostToDevice, c->stream));
-    GB_NCCL(ncclAllReduce(d.p, d.p, 1, ncclInt64, op, c->nccl, c->stream));
-    GB_CUDA(cudaMemcpyAsync(v, d.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    GB_TRY(comm_scratch(c));
+    GB_CUDA(cudaMemcpyAsync(c->d_scratch, v, 8, cudaMemcpyHostToDevice, c->stream));
+    GB_NCCL(ncclAllReduce(c->d_scratch, c->d_scratch, 1, ncclInt64, op, c->nccl, c->stream));
+    GB_CUDA(cudaMemcpyAsync(v, c->d_scratch, 8, cudaMemcpyDeviceToHost, c->stream));
     GB_CUDA(cudaStreamSynchronize(c->stream));
     return GB_OK;
 }
 
-struct BatchBufs {
-    unsigned long long *send = nullptr, *recv = nullptr;
-    size_t send_cap = 0, recv_cap = 0;
-    unsigned long long *d_cnt = nullptr; // [0..P) owner counts, [P..2P) seg base, [2P..3P) cursors, [3P..4P) recv counts
-    cudaEvent_t exchanged = nullptr, inserted = nullptr;
-    bool in_flight = false;
-    int64_t recv_total = 0;
-    ~BatchBufs()
-    {
-        if (send) cudaFree(send);
-        if (recv) cudaFree(recv);
-        if (d_cnt) cudaFree(d_cnt);
-        if (exchanged) cudaEventDestroy(exchanged);
-        if (inserted) cudaEventDestroy(inserted);
+int BatchBufs::ensure(size_t ns, size_t nr)
+{
+    if (ns > send_cap) {
+        if (send) GB_CUDA(cudaFree(send));
+        send = nullptr;
+        send_cap = ns + ns / 8 + 1024;
+        GB_CUDA(cudaMalloc((void **)&send, send_cap * 8));
     }
-    int ensure(size_t ns, size_t nr)
-    {
-        if (ns > send_cap) {
-            if (send) GB_CUDA(cudaFree(send));
-            send = nullptr;
-            send_cap = ns + ns / 8 + 1024;
-            GB_CUDA(cudaMalloc((void **)&send, send_cap * 8));
-        }
-        if (nr > recv_cap) {
-            if (recv) GB_CUDA(cudaFree(recv));
-            recv = nullptr;
-            recv_cap = nr + nr / 8 + 1024;
-            GB_CUDA(cudaMalloc((void **)&recv, recv_cap * 8));
-        }
-        return GB_OK;
+    if (nr > recv_cap) {
+        if (recv) GB_CUDA(cudaFree(recv));
+        recv = nullptr;
+        recv_cap = nr + nr / 8 + 1024;
+        GB_CUDA(cudaMalloc((void **)&recv, recv_cap * 8));
     }
-};
+    if (!d_tot) {
+        GB_CUDA(cudaMalloc((void **)&d_tot, (4 * MAX_BUCKETS + 8) * 8));
+        GB_CUDA(cudaHostAlloc((void **)&h_tot, (4 * MAX_BUCKETS + 8) * 8, cudaHostAllocDefault));
+        GB_CUDA(cudaEventCreateWithFlags(&exchanged, cudaEventDisableTiming));
+        GB_CUDA(cudaEventCreateWithFlags(&inserted, cudaEventDisableTiming));
+    }
+    return GB_OK;
+}
+
+void BatchBufs::release()
+{
+    if (send) cudaFree(send);
+    if (recv) cudaFree(recv);
+    if (d_tot) cudaFree(d_tot);
+    if (h_tot) cudaFreeHost(h_tot);
+    if (exchanged) cudaEventDestroy(exchanged);
+    if (inserted) cudaEventDestroy(inserted);
+    work.release();
+    send = recv = d_tot = h_tot = nullptr;
+    exchanged = inserted = nullptr;
+}
 
 // wait for every in-flight insert, fold the new-key counter into m->size
 static int drain(Map *m, BatchBufs bufs[2])
@@ -261,57 +219,86 @@ static int drain(Map *m, BatchBufs bufs[2])
     return GB_OK;
 }
 
-template <bool FIXED, bool V210>
-static int pmap_insert_t(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off, unsigned int rec,
-                         unsigned int len0, int64_t n_reads, const int64_t *h_win_prefix, int64_t *n_windows)
+// Sharded FreqFilter.add.  Per batch of reads, on the communicator's stream: bucket the canonical k-mers by
+// (owner shard, table slice) [partition.cu]; exchange the per-bucket counts; all-to-all the owner segments over
+// NVLink.  On the map's stream: upsert the received keys slice by slice (every source's sub-bucket of slice 0, then
+// of slice 1, ...), so the resident CTAs share one L2-sized slice of the shard.  Two buffer sets overlap the
+// exchange of batch b + 1 with the upsert of batch b.
+static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off, unsigned int rec,
+                       unsigned int len0, int64_t n_reads, const int64_t *h_win_prefix, int64_t *n_windows)
 {
     Comm *c = m->comm;
     const int P = c->n_ranks;
     const int k = m->k;
-    // batches of reads: bounded staging memory, and enough of them to overlap exchange with insert
-    const int64_t win_max = FIXED ? std::max<int64_t>(0, (int64_t)len0 - k + 1) : (255 - k + 1);
-    const int64_t batch_reads = std::max<int64_t>(TILE_READS, ((int64_t)(48ll << 20) / std::max<int64_t>(win_max, 1)) / TILE_READS * TILE_READS);
-    int64_t my_batches = (n_reads + batch_reads - 1) / batch_reads, batches = my_batches;
+    const bool fixed = d_off == nullptr;
+    const int64_t win_max = fixed ? std::max<int64_t>(0, (int64_t)len0 - k + 1) : (255 - k + 1);
+    // batches: enough of them to overlap exchange with upsert, bounded staging memory (<= 2^26 k-mers = 512 MiB each)
+    int64_t batch_reads = std::max<int64_t>(TILE_READS, (((int64_t)1 << 26) / std::max<int64_t>(win_max, 1)) / TILE_READS * TILE_READS);
+    int64_t quarter = ((n_reads + 3) / 4 + TILE_READS - 1) / TILE_READS * TILE_READS;
+    if (quarter >= TILE_READS * 64) batch_reads = std::min(batch_reads, quarter);
+    int64_t batches = n_reads ? (n_reads + batch_reads - 1) / batch_reads : 0;
+    int64_t lp = slice_bits_for(m->bits, P);
     GB_TRY(all_reduce_i64(c, &batches, ncclMax));
+    GB_TRY(all_reduce_i64(c, &lp, ncclMin)); // every rank must cut the same buckets
+    PartLayout pl;
+    pl.owners = P;
+    pl.lp_bits = (int)lp;
+    const int LP = 1 << pl.lp_bits, NB = pl.nb();
 
-    BatchBufs bufs[2];
-    for (int i = 0; i < 2; i++) {
-        GB_CUDA(cudaMalloc((void **)&bufs[i].d_cnt, 4 * MAX_RANKS * 8));
-        GB_CUDA(cudaEventCreateWithFlags(&bufs[i].exchanged, cudaEventDisableTiming));
-        GB_CUDA(cudaEventCreateWithFlags(&bufs[i].inserted, cudaEventDisableTiming));
-    }
+    BatchBufs *bufs = c->bufs;
     GB_TRY(map_zero_counters(m));
     GB_CUDA(cudaStreamSynchronize(m->stream));
     GB_CUDA(cudaEventRecord(m->ev0, m->stream));
 
-    int64_t windows = 0, pending_upper = 0; // pending_upper: keys handed to inserts not yet folded into m->size
-    std::vector<unsigned long long> h_cnt(4 * MAX_RANKS);
+    int64_t windows = 0, pending_upper = 0; // pending_upper: keys handed to upserts not yet folded into m->size
     for (int64_t b = 0; b < batches; b++) {
         BatchBufs &B = bufs[b & 1];
         const int64_t r0 = std::min(n_reads, b * batch_reads), r1 = std::min(n_reads, r0 + batch_reads), nr = r1 - r0;
-        const int64_t w_upper = FIXED ? nr * win_max : (h_win_prefix ? h_win_prefix[r1] - h_win_prefix[r0] : nr * win_max);
-        windows += FIXED || h_win_prefix ? w_upper : 0;
-        if (B.in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, B.inserted, 0)); // its buffers are being read
+        const int64_t w_upper = fixed ? nr * win_max : (h_win_prefix ? h_win_prefix[r1] - h_win_prefix[r0] : nr * win_max);
+        if (B.in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, B.inserted, 0)); // its buffers are still being read
         GB_TRY(B.ensure((size_t)w_upper, 0));
-        unsigned long long *cnt = B.d_cnt, *seg = B.d_cnt + MAX_RANKS, *cur = B.d_cnt + 2 * MAX_RANKS, *rcnt = B.d_cnt + 3 * MAX_RANKS;
-        GB_CUDA(cudaMemsetAsync(B.d_cnt, 0, 4 * MAX_RANKS * 8, c->stream));
-        const unsigned int grid = (unsigned int)((nr + TILE_READS - 1) / TILE_READS);
-        if (nr > 0) {
-            route_count_kernel<FIXED, V210><<<grid, INSERT_THREADS, 0, c->stream>>>(d_bin, n_bytes, d_off, rec, r0, nr, k, (unsigned int)P, cnt);
-            GB_LAUNCHED();
-        }
-        GB_TRY(exchange_counts(c, cnt, rcnt, h_cnt.data(), h_cnt.data() + MAX_RANKS));
-        unsigned long long *h_send = h_cnt.data(), *h_recv = h_cnt.data() + MAX_RANKS;
-        unsigned long long *h_soff = h_cnt.data() + 2 * MAX_RANKS, *h_roff = h_cnt.data() + 3 * MAX_RANKS;
+        ReadBatch rb;
+        rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = d_off; rb.rec_bytes = rec; rb.read0 = r0; rb.n_reads = nr;
+        // d_tot: [0, NB) my bucket totals (row o = what I send to owner o), [NB, 2NB) row s = what source s sends me
+        GB_TRY(part_count(rb, k, m->v210, pl, B.work, c->stream));
+        GB_CUDA(cudaMemcpyAsync(B.d_tot, B.work.bucket_total, NB * 8, cudaMemcpyDeviceToDevice, c->stream));
+        GB_TRY(all_to_all_rows(c, B.d_tot, B.d_tot + NB, (size_t)LP));
+        GB_CUDA(cudaMemcpyAsync(B.h_tot, B.d_tot, 2 * NB * 8, cudaMemcpyDeviceToHost, c->stream));
+        GB_TRY(part_scatter(rb, k, m->v210, pl, B.work, B.send, c->stream)); // runs while the host waits for the counts
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+        unsigned long long scnt[MAX_RANKS], soff[MAX_RANKS], rcnt[MAX_RANKS], roff[MAX_RANKS];
         unsigned long long st = 0, rt = 0;
-        for (int p = 0; p < P; p++) { h_soff[p] = st; st += h_send[p]; h_roff[p] = rt; rt += h_recv[p]; }
-        GB_TRY(B.ensure(0, (size_t)rt));
-        GB_CUDA(cudaMemcpyAsync(seg, h_soff, P * 8, cudaMemcpyHostToDevice, c->stream));
-        if (nr > 0) {
-            route_scatter_kernel<FIXED, V210><<<grid, INSERT_THREADS, 0, c->stream>>>(d_bin, n_bytes, d_off, rec, r0, nr, k, (unsigned int)P, seg, cur, B.send);
-            GB_LAUNCHED();
+        for (int p = 0; p < P; p++) {
+            unsigned long long s1 = 0, s2 = 0;
+            for (int l = 0; l < LP; l++) { s1 += B.h_tot[p * LP + l]; s2 += B.h_tot[NB + p * LP + l]; }
+            scnt[p] = s1; soff[p] = st; st += s1;
+            rcnt[p] = s2; roff[p] = rt; rt += s2;
         }
-        GB_TRY(all_to_all_v(c, B.send, h_soff, h_send, B.recv, h_roff, h_recv, ncclUint64));
+        windows += (int64_t)st;
+        GB_TRY(B.ensure(0, (size_t)rt));
+        GB_TRY(all_to_all_v(c, B.send, soff, scnt, B.recv, roff, rcnt, ncclUint64));
+        // chunk table of the upsert, slice-major: chunk (l, s) = source s's keys of slice l
+        unsigned long long *vstart = B.h_tot + 2 * NB, *coff = vstart + NB + 1;
+        {
+            unsigned long long within[MAX_RANKS];
+            for (int s = 0; s < P; s++) within[s] = 0;
+            // offset of (s, l) inside source s's segment = prefix over l; walk slices outermost to fill vstart in order
+            std::vector<unsigned long long> seg_off((size_t)NB);
+            for (int s = 0; s < P; s++) {
+                unsigned long long acc = 0;
+                for (int l = 0; l < LP; l++) { seg_off[(size_t)s * LP + l] = roff[s] + acc; acc += B.h_tot[NB + s * LP + l]; }
+            }
+            unsigned long long v = 0;
+            int ci = 0;
+            for (int l = 0; l < LP; l++)
+                for (int s = 0; s < P; s++, ci++) {
+                    vstart[ci] = v;
+                    coff[ci] = seg_off[(size_t)s * LP + l];
+                    v += B.h_tot[NB + s * LP + l];
+                }
+            vstart[NB] = v;
+        }
+        GB_CUDA(cudaMemcpyAsync(B.d_tot + 2 * NB, vstart, (2 * NB + 1) * 8, cudaMemcpyHostToDevice, c->stream));
         GB_CUDA(cudaEventRecord(B.exchanged, c->stream));
 
         // room for the received keys (every one may be new); grow only with the pipeline drained
@@ -327,10 +314,9 @@ static int pmap_insert_t(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
             }
         }
         GB_CUDA(cudaStreamWaitEvent(m->stream, B.exchanged, 0));
-        GB_TRY(map_launch_update_counts(m, B.recv, (int64_t)rt, m->stream));
+        GB_TRY(insert_key_chunks(m, B.recv, B.d_tot + 2 * NB, B.d_tot + 3 * NB + 1, NB, rt, m->stream));
         GB_CUDA(cudaEventRecord(B.inserted, m->stream));
         B.in_flight = true;
-        B.recv_total = (int64_t)rt;
         pending_upper += (int64_t)rt;
     }
     GB_CUDA(cudaEventRecord(m->ev1, m->stream));
@@ -349,19 +335,6 @@ static int check_pmap(gb_map *h, Map **m)
     GB_TRY(check_map(h, m));
     if (!(*m)->comm) { set_error("map is not bound to a communicator (use gb_pmap_create)"); return GB_E_STATE; }
     return GB_OK;
-}
-
-__global__ void count_windows_kernel(const uint8_t *bin, const unsigned long long *offsets, long long n_reads, int k,
-                                     unsigned long long *total)
-{
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long w = 0;
-    if (i < n_reads) {
-        int len = bin[offsets[i]];
-        w = len >= k ? len - k + 1 : 0;
-    }
-    w = __reduce_add_sync(0xFFFFFFFFu, (unsigned int)w);
-    if ((threadIdx.x & 31) == 0 && w) atomicAdd(total, w);
 }
 
 } // namespace gb
@@ -414,6 +387,10 @@ int gb_comm_destroy(gb_comm *h)
     Comm *c = reinterpret_cast<Comm *>(h);
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->bufs[0].release();
+    c->bufs[1].release();
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
     if (c->nccl) ncclCommDestroy(c->nccl);
     delete c;
     return GB_OK;
@@ -436,30 +413,18 @@ int gb_pmap_insert_reads_device(gb_map *h, const uint8_t *d_bin, size_t n_bytes,
     if (n_windows) *n_windows = 0;
     if (n_reads < 0 || (!d_bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
     // NOTE: collective -- a rank with no reads still takes part in every exchange
-    if (d_offsets || n_reads == 0) {
-        int64_t w = 0;
-        if (n_reads) {
-            DeviceBuf tot;
-            GB_TRY(tot.alloc(8));
-            GB_CUDA(cudaMemsetAsync(tot.p, 0, 8, m->stream));
-            count_windows_kernel<<<(unsigned int)((n_reads + 255) / 256), 256, 0, m->stream>>>(d_bin, (const unsigned long long *)d_offsets, n_reads, m->k, (unsigned long long *)tot.p);
-            GB_LAUNCHED();
-            GB_CUDA(cudaMemcpyAsync(&w, tot.p, 8, cudaMemcpyDeviceToHost, m->stream));
-            GB_CUDA(cudaStreamSynchronize(m->stream));
-        }
-        int r = m->v210 ? pmap_insert_t<false, true>(m, d_bin, n_bytes, (const unsigned long long *)d_offsets, 0, 0, n_reads, nullptr, nullptr)
-                        : pmap_insert_t<false, false>(m, d_bin, n_bytes, (const unsigned long long *)d_offsets, 0, 0, n_reads, nullptr, nullptr);
-        if (r == GB_OK) { m->windows += w; if (n_windows) *n_windows = w; }
-        return r;
-    }
+    if (d_offsets || n_reads == 0)
+        return pmap_insert(m, d_bin, n_bytes, n_reads ? (const unsigned long long *)d_offsets : nullptr, 0, 0, n_reads, nullptr, n_windows);
     uint8_t len0 = 0;
     GB_CUDA(cudaMemcpyAsync(&len0, d_bin, 1, cudaMemcpyDeviceToHost, m->stream));
     GB_CUDA(cudaStreamSynchronize(m->stream));
     unsigned int rec = 1 + (len0 + 3) / 4;
     if ((unsigned long long)n_reads * rec > n_bytes) { set_error("truncated .bin stream"); return GB_E_ARG; }
+    unsigned long long bad = 0;
+    GB_TRY(map_verify_fixed(m, d_bin, rec, len0, n_reads, &bad));
+    if (bad) { set_error("records are not fixed-length: pass d_offsets"); return GB_E_ARG; }
     m->fixed_stride = 1;
-    return m->v210 ? pmap_insert_t<true, true>(m, d_bin, n_bytes, nullptr, rec, len0, n_reads, nullptr, n_windows)
-                   : pmap_insert_t<true, false>(m, d_bin, n_bytes, nullptr, rec, len0, n_reads, nullptr, n_windows);
+    return pmap_insert(m, d_bin, n_bytes, nullptr, rec, len0, n_reads, nullptr, n_windows);
 }
 
 int gb_pmap_insert_reads(gb_map *h, const uint8_t *bin, size_t n_bytes, int64_t n_reads, int64_t *n_windows)
@@ -468,26 +433,35 @@ int gb_pmap_insert_reads(gb_map *h, const uint8_t *bin, size_t n_bytes, int64_t 
     GB_TRY(check_pmap(h, &m));
     if (n_windows) *n_windows = 0;
     if (n_reads < 0 || (!bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
+    if (n_reads == 0) return pmap_insert(m, nullptr, 0, nullptr, 0, 0, 0, nullptr, n_windows);
+    if (n_bytes == 0) { set_error("truncated .bin stream at read 0"); return GB_E_ARG; }
+    // fixed-stride fast path: copy n_reads records of the first record's size and let the device check every
+    // length byte (sound: equal length bytes at i * rec imply the record chain is i * rec); else scan on the host.
+    // The choice is local to the rank: the collective schedule (batch count) is agreed inside pmap_insert.
+    const unsigned int len0 = bin[0], rec = 1 + (len0 + 3) / 4;
+    DeviceBuf d_bin, d_off;
+    if ((unsigned long long)n_reads * rec <= n_bytes) {
+        const size_t used = (size_t)n_reads * rec;
+        GB_TRY(d_bin.alloc(used + 16, m->stream));
+        GB_CUDA(cudaMemcpyAsync(d_bin.p, bin, used, cudaMemcpyHostToDevice, m->stream));
+        unsigned long long bad = 0;
+        GB_TRY(map_verify_fixed(m, (const uint8_t *)d_bin.p, rec, len0, n_reads, &bad));
+        if (!bad) {
+            m->fixed_stride = 1;
+            return pmap_insert(m, (const uint8_t *)d_bin.p, used, nullptr, rec, len0, n_reads, nullptr, n_windows);
+        }
+    }
+    m->fixed_stride = 0;
     std::vector<unsigned long long> off;
     std::vector<int64_t> winp;
     GB_TRY(scan_records(bin, n_bytes, n_reads, m->k, off, winp));
     const size_t used = (size_t)off[(size_t)n_reads];
-    // fixed stride iff every record has the first record's length
-    bool fixed = n_reads > 0;
-    const unsigned int len0 = n_reads ? bin[0] : 0, rec = 1 + (len0 + 3) / 4;
-    for (int64_t r = 0; fixed && r < n_reads; r++) fixed = bin[off[(size_t)r]] == len0;
-    DeviceBuf d_bin, d_off;
-    GB_TRY(d_bin.alloc(used + 16));
-    if (used) GB_CUDA(cudaMemcpyAsync(d_bin.p, bin, used, cudaMemcpyHostToDevice, m->stream));
-    GB_TRY(d_off.alloc(off.size() * 8));
+    GB_TRY(d_bin.alloc(used + 16, m->stream));
+    GB_CUDA(cudaMemcpyAsync(d_bin.p, bin, used, cudaMemcpyHostToDevice, m->stream));
+    GB_TRY(d_off.alloc(off.size() * 8, m->stream));
     GB_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, m->stream));
     GB_CUDA(cudaStreamSynchronize(m->stream));
-    m->fixed_stride = fixed;
-    if (fixed)
-        return m->v210 ? pmap_insert_t<true, true>(m, (const uint8_t *)d_bin.p, used, nullptr, rec, len0, n_reads, nullptr, n_windows)
-                       : pmap_insert_t<true, false>(m, (const uint8_t *)d_bin.p, used, nullptr, rec, len0, n_reads, nullptr, n_windows);
-    return m->v210 ? pmap_insert_t<false, true>(m, (const uint8_t *)d_bin.p, used, (const unsigned long long *)d_off.p, 0, 0, n_reads, winp.data(), n_windows)
-                   : pmap_insert_t<false, false>(m, (const uint8_t *)d_bin.p, used, (const unsigned long long *)d_off.p, 0, 0, n_reads, winp.data(), n_windows);
+    return pmap_insert(m, (const uint8_t *)d_bin.p, used, (const unsigned long long *)d_off.p, 0, 0, n_reads, winp.data(), n_windows);
 }
 
 int gb_pmap_size(gb_map *h, int64_t *size)

@@ -198,6 +198,9 @@ struct Map {
     Slot *table = nullptr;
     int64_t size = 0;          // live keys (host mirror, exact after every call)
     int64_t grows = 0, windows = 0, last_insert_ns = 0, fixed_stride = 0;
+    int64_t phase_ns[3] = { 0, 0, 0 }; // last partitioned insert: count, scatter, upsert (0 = direct path used)
+    struct PartWork *part = nullptr;   // workspace of the partitioned insert (partition.cuh)
+    cudaEvent_t pe[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, t0 = nullptr, t1 = nullptr;
     // scratch

@@ -3,6 +3,8 @@
 // Replaces PairedEndData.getPairs.read (S/data/PairedEndData.scala:24-32), seq.sliding(k) and the canonical
 // rule of FreqFilter.add (S/data/FreqFilter.scala:29-33); paths relative to /root/reference.
 #pragma once
+#include <vector>
+
 #include "common.cuh"
 
 namespace gb {
@@ -32,15 +34,15 @@ __device__ __forceinline__ unsigned long long extract_bits(const unsigned int *s
     return ((unsigned long long)hi << 32) | lo;
 }
 
-// stages the tile of blockIdx.x; returns the number of reads in it (<= 0: nothing to do, uniform over the CTA).
+// stages tile number `tile_idx` of the batch; returns the number of reads in it (<= 0: nothing to do, uniform over the CTA).
 // Ends with a __syncthreads(): tile.* is readable by every thread on return.
 template <bool FIXED>
 __device__ __forceinline__ int stage_tile(ReadTile &tile, const uint8_t *__restrict__ bin, unsigned long long n_bytes,
                                           const unsigned long long *__restrict__ offsets, unsigned int rec_bytes,
-                                          long long read0, long long n_reads, int k)
+                                          long long read0, long long n_reads, int k, long long tile_idx)
 {
     const int tid = threadIdx.x;
-    const long long r0 = read0 + (long long)blockIdx.x * TILE_READS;
+    const long long r0 = read0 + tile_idx * TILE_READS;
     const int nr = (int)min((long long)TILE_READS, read0 + n_reads - r0);
     if (nr <= 0) return nr;
 
@@ -165,6 +167,7 @@ int map_budget(Map *m, int64_t incoming, int64_t *budget);
 int map_read_counters(Map *m, unsigned long long out[4]);
 int map_zero_counters(Map *m);
 int map_rebuild(Map *m, int new_bits, bool filter, int min_count);
+int map_verify_fixed(Map *m, const uint8_t *d_bin, unsigned int rec, unsigned int len0, int64_t n_reads, unsigned long long *bad);
 int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n, cudaStream_t st);
 int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d_vals, int64_t n, cudaStream_t st);
 int scan_records(const uint8_t *bin, size_t n_bytes, int64_t n_reads, int k, std::vector<unsigned long long> &off,

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "extract.cuh"
+#include "partition.cuh"
 
 namespace gb {
 
@@ -73,7 +74,7 @@ insert_reads_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes,
     __shared__ ReadTile tile;
     __shared__ unsigned int s_newkeys;
     const int tid = threadIdx.x;
-    const int nr = stage_tile<FIXED>(tile, bin, n_bytes, offsets, rec_bytes, read0, n_reads, k);
+    const int nr = stage_tile<FIXED>(tile, bin, n_bytes, offsets, rec_bytes, read0, n_reads, k, blockIdx.x);
     if (nr <= 0) return;
     if (tid == 0) s_newkeys = 0;
 
@@ -354,6 +355,70 @@ static int launch_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
     return GB_OK;
 }
 
+// counters[2] != 0 <=> some record of the fixed-stride stream has another length byte
+int map_verify_fixed(Map *m, const uint8_t *d_bin, unsigned int rec, unsigned int len0, int64_t n_reads, unsigned long long *bad)
+{
+    GB_TRY(map_zero_counters(m));
+    verify_fixed_kernel<<<grid_for((unsigned long long)n_reads, 256), 256, 0, m->stream>>>(d_bin, rec, len0, n_reads, m->d_counters);
+    GB_LAUNCHED();
+    unsigned long long c[4];
+    GB_TRY(map_read_counters(m, c));
+    *bad = c[2];
+    return GB_OK;
+}
+
+// 0 = choose by table size, 1 = direct (fused extract + upsert, random access), 2 = partitioned (L2-blocked)
+static int insert_mode()
+{
+    const char *e = getenv("GENOME_B200_INSERT");
+    if (!e) return 0;
+    if (!strcmp(e, "direct")) return 1;
+    if (!strcmp(e, "partitioned")) return 2;
+    return 0;
+}
+
+// L2-blocked insert of reads [read0, read0 + n_reads): count, scatter into table-slice buckets, upsert slice by slice
+static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off, unsigned int rec,
+                              int64_t read0, int64_t n_reads, int64_t windows_upper, int64_t *windows_done)
+{
+    cudaStream_t st = m->stream;
+    if (!m->part) m->part = new PartWork();
+    for (int i = 0; i < 4; i++)
+        if (!m->pe[i]) GB_CUDA(cudaEventCreate(&m->pe[i]));
+    PartLayout pl;
+    pl.owners = 1;
+    pl.lp_bits = slice_bits_for(m->bits, 1);
+    ReadBatch rb;
+    rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = d_off; rb.rec_bytes = rec; rb.read0 = read0; rb.n_reads = n_reads;
+    GB_CUDA(cudaEventRecord(m->pe[0], st));
+    GB_TRY(part_count(rb, m->k, m->v210, pl, *m->part, st));
+    GB_CUDA(cudaEventRecord(m->pe[1], st));
+    DeviceBuf keys;
+    GB_TRY(keys.alloc((size_t)(windows_upper ? windows_upper : 1) * 8, st));
+    GB_TRY(part_scatter(rb, m->k, m->v210, pl, *m->part, (unsigned long long *)keys.p, st));
+    GB_CUDA(cudaEventRecord(m->pe[2], st));
+    unsigned long long total = 0;
+    GB_CUDA(cudaMemcpyAsync(&total, m->part->bucket_base + pl.nb(), 8, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    if ((int64_t)total > windows_upper) { set_error("internal: %llu k-mers exceed the batch bound %lld", total, (long long)windows_upper); return GB_E_INVARIANT; }
+    // one chunk: the buckets are contiguous and already in slice order
+    unsigned long long desc[3] = { 0, total, 0 }; // vstart[0], vstart[1], off[0]
+    DeviceBuf d_desc;
+    GB_TRY(d_desc.alloc(sizeof desc, st));
+    GB_CUDA(cudaMemcpyAsync(d_desc.p, desc, sizeof desc, cudaMemcpyHostToDevice, st));
+    GB_TRY(insert_key_chunks(m, (const unsigned long long *)keys.p, (const unsigned long long *)d_desc.p,
+                             (const unsigned long long *)d_desc.p + 2, 1, total, st));
+    GB_CUDA(cudaEventRecord(m->pe[3], st));
+    GB_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < 3; i++) {
+        float ms = 0;
+        GB_CUDA(cudaEventElapsedTime(&ms, m->pe[i], m->pe[i + 1]));
+        m->phase_ns[i] += (int64_t)(ms * 1e6);
+    }
+    *windows_done = (int64_t)total;
+    return GB_OK;
+}
+
 // Core of gb_map_insert_reads*: the stream is on the device.  h_windows_prefix (optional, n_reads+1) gives
 // exact per-read window prefix sums for batching in the ragged case.
 static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off,
@@ -362,7 +427,8 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
 {
     GB_TRY(map_zero_counters(m));
     int64_t done = 0;
-    int64_t total_ns = 0;
+    int64_t total_ns = 0, part_windows = 0;
+    m->phase_ns[0] = m->phase_ns[1] = m->phase_ns[2] = 0;
     while (done < n_reads) {
         // how many reads fit the budget (whole tiles)
         int64_t left = n_reads - done;
@@ -386,9 +452,29 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
         }
         unsigned long long before[4], after[4];
         GB_TRY(map_read_counters(m, before));
+        const int64_t take_windows = fixed ? take * win_per_read_max
+                                           : (h_win_prefix ? h_win_prefix[done + take] - h_win_prefix[done] : take * win_per_read_max);
+        const int mode = insert_mode();
+        const bool partitioned = mode == 2 || (mode == 0 && ((size_t)sizeof(Slot) << m->bits) > (96u << 20) && take_windows >= (1 << 20));
         GB_CUDA(cudaEventRecord(m->ev0, m->stream));
-        if (fixed) GB_TRY(launch_insert<true>(m, d_bin, n_bytes, nullptr, rec, done, take));
-        else GB_TRY(launch_insert<false>(m, d_bin, n_bytes, d_off, 0, done, take));
+        if (partitioned) {
+            // bounded key staging: at most 2^28 k-mers (2 GiB) per pass
+            int64_t sub = take;
+            const int64_t per_read = std::max<int64_t>(1, fixed ? win_per_read_max : (255 - m->k + 1));
+            const int64_t max_reads = std::max<int64_t>(TILE_READS, (((int64_t)1 << 28) / per_read) / TILE_READS * TILE_READS);
+            for (int64_t o = 0; o < take; o += sub) {
+                sub = std::min(max_reads, take - o);
+                int64_t wu = fixed ? sub * win_per_read_max
+                                   : (h_win_prefix ? h_win_prefix[done + o + sub] - h_win_prefix[done + o] : sub * per_read);
+                int64_t wd = 0;
+                GB_TRY(insert_partitioned(m, d_bin, n_bytes, fixed ? nullptr : d_off, rec, done + o, sub, wu, &wd));
+                part_windows += wd;
+            }
+        } else if (fixed) {
+            GB_TRY(launch_insert<true>(m, d_bin, n_bytes, nullptr, rec, done, take));
+        } else {
+            GB_TRY(launch_insert<false>(m, d_bin, n_bytes, d_off, 0, done, take));
+        }
         GB_CUDA(cudaEventRecord(m->ev1, m->stream));
         GB_TRY(map_read_counters(m, after));
         float ms = 0;
@@ -399,6 +485,7 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
     }
     unsigned long long c[4];
     GB_TRY(map_read_counters(m, c));
+    c[3] += (unsigned long long)part_windows; // the direct kernel counts its windows on the device
     m->windows += (int64_t)c[3];
     m->last_insert_ns = total_ns;
     if (n_windows) *n_windows = (int64_t)c[3];
@@ -514,6 +601,9 @@ int gb_map_destroy(gb_map *h)
     if (m->d_overflow) cudaFree(m->d_overflow);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
+    for (int i = 0; i < 4; i++)
+        if (m->pe[i]) cudaEventDestroy(m->pe[i]);
+    if (m->part) { m->part->release(); delete m->part; }
     if (m->t0) cudaEventDestroy(m->t0);
     if (m->t1) cudaEventDestroy(m->t1);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -799,6 +889,8 @@ int gb_map_stats(gb_map *h, int64_t stats[8])
     stats[3] = m->windows;
     stats[4] = m->last_insert_ns;
     stats[5] = m->fixed_stride;
+    stats[6] = m->phase_ns[0] + m->phase_ns[1]; // partitioned insert: count + scatter
+    stats[7] = m->phase_ns[2];                  // partitioned insert: slice-ordered upsert
     return GB_OK;
 }
 

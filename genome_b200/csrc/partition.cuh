@@ -1,0 +1,55 @@
+// partition.cuh -- host API of partition.cu: canonical k-mers of a read batch grouped into buckets
+// (owner shard, table slice), and the L2-blocked bulk upsert that consumes such buckets.
+#pragma once
+#include "common.cuh"
+
+namespace gb {
+
+constexpr int MAX_BUCKETS = 512;
+constexpr int SLICE_LOG2_BYTES = 25; // a table slice of 32 MiB stays resident in the 126 MB L2 while it is filled
+
+// bucket = owner * (1 << lp_bits) + slice, owner = owner_of(h, owners), slice = top lp_bits of h (= of the slot index)
+struct PartLayout {
+    int owners = 1;
+    int lp_bits = 0;
+    int nb() const { return owners << lp_bits; }
+};
+
+struct ReadBatch {
+    const uint8_t *bin = nullptr;
+    unsigned long long n_bytes = 0;
+    const unsigned long long *offsets = nullptr; // device, n_reads + 1 entries; nullptr = fixed stride
+    unsigned int rec_bytes = 0;                  // fixed stride only
+    long long read0 = 0, n_reads = 0;
+};
+
+// per-CTA bucket histograms -> bucket bases; device arrays live in PartWork
+struct PartWork {
+    int grid = 0;
+    unsigned int *cta_hist = nullptr;        // [grid][nb] counts, then exclusive offsets inside the bucket
+    unsigned long long *bucket_base = nullptr; // [MAX_BUCKETS + 1] exclusive prefix of bucket totals; [nb] = total keys
+    unsigned long long *bucket_total = nullptr; // [MAX_BUCKETS]
+    cudaStream_t owner_stream = nullptr;
+    int ensure(cudaStream_t st);
+    void release();
+};
+
+inline int slice_bits_for(int table_bits, int owners)
+{
+    int lp = table_bits + 4 - SLICE_LOG2_BYTES; // 16-byte slots
+    if (lp < 0) lp = 0;
+    while ((owners << lp) > MAX_BUCKETS) lp--;
+    return lp < 0 ? 0 : lp;
+}
+
+// pass 1: count; fills w.cta_hist / w.bucket_total / w.bucket_base (all on `st`, no host synchronisation)
+int part_count(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, cudaStream_t st);
+// pass 2: write every canonical k-mer of the batch into its bucket's range of `out` (bucket-major order)
+int part_scatter(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, cudaStream_t st);
+
+// update(key, 1, _ + 1) for the keys of `n_chunks` ranges visited in order: chunk c holds the virtual positions
+// [vstart[c], vstart[c+1]) and starts at keys[off[c]].  d_vstart has n_chunks + 1 entries.  n_total = vstart[n_chunks].
+int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned long long *d_vstart, const unsigned long long *d_off,
+                      int n_chunks, unsigned long long n_total, cudaStream_t st);
+
+} // namespace gb

@@ -215,7 +215,8 @@ class _MapBase:
     def stats(self):
         s = (C.c_int64 * 8)()
         capi.check(capi.lib().gb_map_stats(self.h, s))
-        return dict(capacity=s[0], table_bytes=s[1], grows=s[2], windows=s[3], last_insert_ns=s[4], fixed_stride=s[5])
+        return dict(capacity=s[0], table_bytes=s[1], grows=s[2], windows=s[3], last_insert_ns=s[4], fixed_stride=s[5],
+                    bucket_ns=s[6], upsert_ns=s[7])
 
 
 class ArrayDNAMap(_MapBase):

@@ -100,7 +100,9 @@ int gb_timer_stop(gb_map *m, int64_t *ns);
 int gb_sync(gb_map *m);
 
 /* counters: [0] capacity (slots) [1] table bytes [2] rehash/grow count [3] windows inserted so far
- * [4] last insert kernel time in ns (CUDA events) [5] fixed-stride fast path used (0/1) */
+ * [4] last insert time in ns (CUDA events) [5] fixed-stride fast path used (0/1)
+ * [6] [7] when the last insert took the L2-blocked path: ns spent bucketing k-mers by table slice / upserting them
+ * (0 0 = the fused random-access kernel was used; GENOME_B200_INSERT=direct|partitioned forces a path) */
 int gb_map_stats(gb_map *m, int64_t stats[8]);
 
 /* ------------------------------------------------------------------------------------------------
