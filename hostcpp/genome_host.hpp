@@ -1,0 +1,152 @@
+// genome_host.hpp -- header-only C++ host mirror of the reference's operator surface over the C ABI
+// (include/genome_b200.h).  Same names and argument meaning as the Scala (paths relative to /root/reference,
+// S/ = src/main/scala/ru/ifmo/genome/):
+//   trait DNAMap[Int]      S/ds/ArrayDNAMap.scala:49-60      -> genome::DNAMap
+//   object FreqFilter      S/data/FreqFilter.scala:25-58     -> genome::FreqFilter::extractFilteredKmers
+//   object Graph / MapGraph S/data/graph/Graph.scala         -> genome::Graph::buildGraph, genome::MapGraph
+// Errors surface as genome::Error (the reference asserts / fails its Futures).  No CPU fallback exists.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../include/genome_b200.h"
+
+namespace genome {
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string &what) : std::runtime_error(what), code(c) {}
+};
+inline void check(int rc)
+{
+    if (rc != GB_OK) throw Error(rc, gb_last_error());
+}
+
+struct Edge {
+    uint32_t start, end;        // node indices
+    std::vector<uint8_t> seq;   // base codes A0 G1 C2 T3 (S/dna/Base.scala:13-16)
+};
+
+class MapGraph {
+  public:
+    explicit MapGraph(gb_graph *g) : g_(g) {}
+    MapGraph(const MapGraph &) = delete;
+    MapGraph &operator=(const MapGraph &) = delete;
+    MapGraph(MapGraph &&o) noexcept : g_(o.g_) { o.g_ = nullptr; }
+    ~MapGraph() { gb_graph_destroy(g_); }
+
+    std::vector<uint64_t> getNodes() const
+    {
+        int64_t n, e, b;
+        check(gb_graph_counts(g_, &n, &e, &b));
+        std::vector<uint64_t> k((size_t)n);
+        check(gb_graph_export(g_, k.data(), nullptr, nullptr, nullptr, nullptr));
+        return k;
+    }
+    std::vector<Edge> getEdges() const
+    {
+        int64_t n, e, b;
+        check(gb_graph_counts(g_, &n, &e, &b));
+        std::vector<uint32_t> s((size_t)e), t((size_t)e);
+        std::vector<uint64_t> off((size_t)e + 1);
+        std::vector<uint8_t> packed((size_t)(b + 3) / 4);
+        check(gb_graph_export(g_, nullptr, s.data(), t.data(), off.data(), packed.data()));
+        std::vector<Edge> out((size_t)e);
+        for (size_t i = 0; i < (size_t)e; i++) {
+            out[i].start = s[i];
+            out[i].end = t[i];
+            for (uint64_t j = off[i]; j < off[i + 1]; j++) out[i].seq.push_back((packed[j >> 2] >> (2 * (j & 3))) & 3);
+        }
+        return out;
+    }
+    // Graph.components (54-72): label per node, returns the number of components
+    int64_t components(std::vector<uint32_t> &label) const
+    {
+        int64_t n, e, b, nc = 0;
+        check(gb_graph_counts(g_, &n, &e, &b));
+        label.assign((size_t)n, 0);
+        check(gb_graph_components(g_, label.data(), &nc));
+        return nc;
+    }
+    void retainLargest() { check(gb_graph_retain_largest(g_)); }   // GraphBuilder.scala:52-54
+    void simplifyGraph() { check(gb_graph_simplify(g_)); }          // Graph.scala:211-230
+    void removeBubbles() { check(gb_graph_remove_bubbles(g_)); }    // Graph.scala:125-149
+    void removeEdges(const std::vector<uint32_t> &idx) { check(gb_graph_remove_edges(g_, idx.data(), (int64_t)idx.size())); }
+    gb_graph *handle() const { return g_; }
+
+  private:
+    gb_graph *g_;
+};
+
+class DNAMap {
+  public:
+    DNAMap(int k, int64_t minCapacity = 0, int device = 0, uint32_t flags = 0) : k_(k) { check(gb_map_create(k, minCapacity, device, flags, &m_)); }
+    DNAMap(const DNAMap &) = delete;
+    DNAMap &operator=(const DNAMap &) = delete;
+    ~DNAMap() { gb_map_destroy(m_); }
+
+    int64_t size() const { int64_t n; check(gb_map_size(m_, &n)); return n; }
+    // apply(key): (found, value)
+    std::pair<bool, int32_t> apply(uint64_t key) const
+    {
+        int32_t c = 0;
+        uint8_t f = 0;
+        check(gb_map_lookup(m_, &key, 1, &c, &f));
+        return { f != 0, c };
+    }
+    bool contains(uint64_t key) const { return apply(key).first; }
+    void update(uint64_t key, int32_t v) { check(gb_map_update(m_, &key, &v, 1)); }
+    // update(key, 1, _ + 1) for a batch (FreqFilter.scala:33)
+    void updateCounts(const std::vector<uint64_t> &keys) { check(gb_map_update_counts(m_, keys.data(), (int64_t)keys.size())); }
+    // deleteAll((k, v) => v < rounds) (FreqFilter.scala:55)
+    void deleteBelow(int32_t rounds) { check(gb_map_delete_below(m_, rounds)); }
+    // mapReduce / foreach: the host closure runs over the exported pairs
+    template <class F>
+    void foreach(F f) const
+    {
+        int64_t n = 0;
+        check(gb_map_export(m_, nullptr, nullptr, 0, &n));
+        std::vector<uint64_t> k((size_t)n);
+        std::vector<int32_t> v((size_t)n);
+        if (n) check(gb_map_export(m_, k.data(), v.data(), n, &n));
+        for (size_t i = 0; i < (size_t)n; i++) f(k[i], v[i]);
+    }
+    // FreqFilter.add over a `.bin` stream (host buffer); returns the number of k-windows
+    int64_t insertReads(const uint8_t *bin, size_t nBytes, int64_t nReads)
+    {
+        int64_t w = 0;
+        check(gb_map_insert_reads(m_, bin, nBytes, nReads, &w));
+        return w;
+    }
+    int k() const { return k_; }
+    gb_map *handle() const { return m_; }
+
+  private:
+    gb_map *m_ = nullptr;
+    int k_;
+};
+
+struct FreqFilter {
+    // extractFilteredKmers(data, k, rounds) (FreqFilter.scala:25-58); `pairs` = PairedEndData.count min genome.takeFirst
+    static void extractFilteredKmers(DNAMap &kmersFreq, const uint8_t *bin, size_t nBytes, int64_t pairs, int32_t rounds)
+    {
+        kmersFreq.insertReads(bin, nBytes, 2 * pairs);
+        kmersFreq.deleteBelow(rounds);
+    }
+};
+
+struct Graph {
+    // Graph.buildGraph(k, kmersFreq) (Graph.scala:269-382)
+    static MapGraph buildGraph(int k, const DNAMap &kmersFreq)
+    {
+        if (k != kmersFreq.k()) throw Error(GB_E_ARG, "k differs from the map's k");
+        gb_graph *g = nullptr;
+        check(gb_graph_build(kmersFreq.handle(), &g));
+        return MapGraph(g);
+    }
+};
+
+} // namespace genome

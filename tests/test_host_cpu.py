@@ -105,3 +105,24 @@ def test_multi_rank_routing_gloo():
                         "--master-port", "29731", script], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "ROUTING OK" in r.stdout
+
+
+def build_cpp_driver(tmp):
+    exe = os.path.join(tmp, "graph_builder")
+    libdir = os.path.join(ROOT, "genome_b200")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-O1", "-o", exe, os.path.join(ROOT, "hostcpp", "graph_builder.cpp"),
+                        "-L" + libdir, "-lgenome_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
+    exe = build_cpp_driver(str(tmp_path))
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    b = synth.pack_fixed(synth.sample_reads(synth.random_genome(2000, 1), 50, 20, 0.0, 2, insert=(20, 60)))
+    p = tmp_path / "r.bin"
+    p.write_bytes(b.tobytes())
+    r = subprocess.run([exe, str(p), "10", "21"], capture_output=True, text=True)
+    assert r.returncode == 1 and "CUDA" in r.stderr

@@ -420,3 +420,24 @@ def test_full_size_properties_c1(gpu):
     contig = synth.int_to_kmer(int(node_kmer[es[0]]), k) + synth.decode(bases)
     gs = synth.decode(genome)
     assert contig in gs or contig in synth.decode(H.revcomp_codes(genome))
+
+
+def test_cpp_host_driver(gpu, tmp_path):
+    """hostcpp/graph_builder.cpp (GraphBuilder.startup over the C++ mirror) prints the oracle's numbers."""
+    from tests.test_host_cpu import build_cpp_driver
+    import subprocess
+    exe = build_cpp_driver(str(tmp_path))
+    k = 21
+    b, n, _ = H.small_reads(20000, 80, 20, 0.01, seed=404)
+    p = tmp_path / "r.bin"
+    p.write_bytes(b.tobytes())
+    r = subprocess.run([exe, str(p), str(n // 2), str(k)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    om, _ = H.oracle_counts(b, n, k)
+    om.delete_below(3)
+    og = pyoracle.OracleGraph(om)
+    assert "Good reads count: %d" % om.size() in r.stdout
+    assert "Total edges length: %d" % og.counts()[2] in r.stdout
+    og.retain_largest()
+    og.simplify()
+    assert "Graph nodes: %d" % og.counts()[0] in r.stdout
