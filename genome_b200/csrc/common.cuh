@@ -196,6 +196,11 @@ struct Map {
     bool noncanonical = false; // keys were inserted through update/update_counts as-is
     int bits = 0;              // capacity = 1 << bits
     Slot *table = nullptr;
+    int alloc_bits = 0;        // the allocation behind `table` holds 1 << alloc_bits slots (>= bits)
+    Slot *spare = nullptr;     // the other table allocation of the clear / filter cycle, kept for reuse
+    int spare_bits = 0;
+    unsigned long long *stage = nullptr; // key staging of the partitioned insert and of the filter (grow-only)
+    size_t stage_cap = 0;
     int64_t size = 0;          // live keys (host mirror, exact after every call)
     int64_t grows = 0, windows = 0, last_insert_ns = 0, fixed_stride = 0;
     int64_t phase_ns[3] = { 0, 0, 0 }; // last partitioned insert: count, scatter, upsert (0 = direct path used)
@@ -245,7 +250,9 @@ inline unsigned int grid_for(unsigned long long n, int threads, int per_sm = 16)
     if (g > cap) g = cap;
     return (unsigned int)(g ? g : 1);
 }
-int map_alloc_table(Slot **t, int bits, cudaStream_t s);
+int map_swap_table(Map *m, int new_bits, Slot **old_table, int *old_alloc_bits);
+void map_retire_table(Map *m, Slot *t, int alloc_bits);
+int map_stage(Map *m, size_t n_u64);
 int pool_setup(int device);
 inline int bits_for(int64_t keys)
 {

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "extract.cuh"
 #include "partition.cuh"
+#include "scan.cuh"
 
 namespace gb {
 
@@ -177,25 +178,35 @@ __global__ void lookup_kernel(const unsigned long long *__restrict__ keys, long 
     if (found) found[i] = f;
 }
 
-// deleteAll(v < min_count): survivors are counted, then re-inserted into a table sized for them (the
-// reference tombstones and then rescales when load drops below 0.3, ArrayDNAMap.scala:164-173,217-230)
-__global__ void count_survivors_kernel(const Slot *table, unsigned long long n, int min_count,
-                                       unsigned long long *counters)
+// deleteAll(v < min_count) (ArrayDNAMap.scala:164-173,212-215): ONE streaming pass over the table compacts the
+// survivors into (key, count) arrays (warp-aggregated cursor), then they are re-inserted into a table sized for
+// them (the reference tombstones and rescales when the load drops below 0.3, ArrayDNAMap.scala:217-230).
+__global__ void __launch_bounds__(256)
+compact_survivors_kernel(const Slot *table, unsigned long long n, int min_count, unsigned long long *out_keys, int *out_vals,
+                         unsigned long long *counters)
 {
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned int c = 0;
-    for (; i < n; i += stride) {
-        Slot s = load_slot(table + i);
-        c += (s.key != EMPTY_KEY && s.count >= min_count);
+    // a CTA iteration covers 1024 consecutive slots (4 per thread) and takes ONE ticket from the global cursor
+    const unsigned long long tiles = (n + 1023) / 1024;
+    for (unsigned long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        Slot s[4];
+        unsigned int c = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned long long i = t * 1024 + (unsigned long long)j * 256 + threadIdx.x;
+            s[j].key = EMPTY_KEY;
+            s[j].count = 0;
+            if (i < n) s[j] = load_slot(table + i);
+            c += s[j].key != EMPTY_KEY && s[j].count >= min_count;
+        }
+        unsigned long long pos = block_alloc(c, &counters[1]);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (s[j].key != EMPTY_KEY && s[j].count >= min_count) {
+                out_keys[pos] = s[j].key;
+                out_vals[pos] = s[j].count;
+                pos++;
+            }
     }
-    c = __reduce_add_sync(0xFFFFFFFFu, c);
-    __shared__ unsigned int s_c;
-    if (threadIdx.x == 0) s_c = 0;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_c, c);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_c) atomicAdd(&counters[1], (unsigned long long)s_c);
 }
 
 __global__ void rehash_kernel(const Slot *old_table, unsigned long long n, int min_count, bool filter,
@@ -260,26 +271,70 @@ using namespace gb;
 
 namespace gb {
 
-int map_alloc_table(Slot **t, int bits, cudaStream_t s)
+// Table memory.  A FreqFilter pass cycles between a large table (counting) and a small one (after deleteAll), and
+// the next pass starts again with a large one: the map keeps both allocations (`table` and `spare`) and swaps them,
+// so that the steady state allocates nothing.  Everything happens in stream order on m->stream.
+static int init_table(Slot *t, int bits, cudaStream_t s)
 {
     unsigned long long n = 1ull << bits;
-    GB_CUDA(cudaMallocAsync((void **)t, n * sizeof(Slot), s));
-    init_table_kernel<<<grid_for(n, 256, 32), 256, 0, s>>>(*t, n);
+    init_table_kernel<<<grid_for(n, 256, 32), 256, 0, s>>>(t, n);
     GB_LAUNCHED();
+    return GB_OK;
+}
+
+void map_retire_table(Map *m, Slot *t, int alloc_bits)
+{
+    if (!t) return;
+    if (!m->spare) { m->spare = t; m->spare_bits = alloc_bits; return; }
+    if (alloc_bits > m->spare_bits) { std::swap(t, m->spare); std::swap(alloc_bits, m->spare_bits); }
+    cudaFreeAsync(t, m->stream);
+}
+
+// make an EMPTY table of 1 << new_bits slots current; the previous one is handed back (still valid on the stream:
+// the caller rehashes out of it and then retires it)
+int map_swap_table(Map *m, int new_bits, Slot **old_table, int *old_alloc_bits)
+{
+    Slot *nt = nullptr;
+    int na = new_bits;
+    if (m->spare && m->spare_bits >= new_bits) {
+        nt = m->spare;
+        na = m->spare_bits;
+        m->spare = nullptr;
+    } else {
+        GB_CUDA(cudaMallocAsync((void **)&nt, sizeof(Slot) << new_bits, m->stream));
+    }
+    GB_TRY(init_table(nt, new_bits, m->stream));
+    *old_table = m->table;
+    *old_alloc_bits = m->alloc_bits;
+    m->table = nt;
+    m->alloc_bits = na;
+    m->bits = new_bits;
+    return GB_OK;
+}
+
+int map_stage(Map *m, size_t n_u64)
+{
+    if (n_u64 <= m->stage_cap) return GB_OK;
+    if (m->stage) GB_CUDA(cudaFreeAsync(m->stage, m->stream));
+    m->stage = nullptr;
+    m->stage_cap = 0;
+    size_t want = n_u64 + n_u64 / 16 + 1024;
+    GB_CUDA(cudaMallocAsync((void **)&m->stage, want * 8, m->stream));
+    m->stage_cap = want;
     return GB_OK;
 }
 
 // rehash into a table of new_bits (optionally dropping counts below min_count)
 int map_rebuild(Map *m, int new_bits, bool filter, int min_count)
 {
-    Slot *nt = nullptr;
-    GB_TRY(map_alloc_table(&nt, new_bits, m->stream));
-    unsigned long long n = 1ull << m->bits;
-    rehash_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(m->table, n, min_count, filter, nt, new_bits);
+    Slot *old = nullptr;
+    int old_alloc = 0;
+    const int old_bits = m->bits;
+    GB_TRY(map_swap_table(m, new_bits, &old, &old_alloc));
+    unsigned long long n = 1ull << old_bits;
+    rehash_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(old, n, min_count, filter, m->table, new_bits);
     GB_LAUNCHED();
-    GB_CUDA(cudaFreeAsync(m->table, m->stream));
-    m->table = nt;
-    m->bits = new_bits;
+    map_retire_table(m, old, old_alloc);
     m->grows++;
     return GB_OK;
 }
@@ -393,9 +448,9 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
     GB_CUDA(cudaEventRecord(m->pe[0], st));
     GB_TRY(part_count(rb, m->k, m->v210, pl, *m->part, st));
     GB_CUDA(cudaEventRecord(m->pe[1], st));
-    DeviceBuf keys;
-    GB_TRY(keys.alloc((size_t)(windows_upper ? windows_upper : 1) * 8, st));
-    GB_TRY(part_scatter(rb, m->k, m->v210, pl, *m->part, (unsigned long long *)keys.p, st));
+    GB_TRY(map_stage(m, (size_t)(windows_upper ? windows_upper : 1) + 8));
+    unsigned long long *keys = m->stage, *d_desc = m->stage + windows_upper; // chunk descriptor behind the keys
+    GB_TRY(part_scatter(rb, m->k, m->v210, pl, *m->part, keys, st));
     GB_CUDA(cudaEventRecord(m->pe[2], st));
     unsigned long long total = 0;
     GB_CUDA(cudaMemcpyAsync(&total, m->part->bucket_base + pl.nb(), 8, cudaMemcpyDeviceToHost, st));
@@ -403,11 +458,8 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
     if ((int64_t)total > windows_upper) { set_error("internal: %llu k-mers exceed the batch bound %lld", total, (long long)windows_upper); return GB_E_INVARIANT; }
     // one chunk: the buckets are contiguous and already in slice order
     unsigned long long desc[3] = { 0, total, 0 }; // vstart[0], vstart[1], off[0]
-    DeviceBuf d_desc;
-    GB_TRY(d_desc.alloc(sizeof desc, st));
-    GB_CUDA(cudaMemcpyAsync(d_desc.p, desc, sizeof desc, cudaMemcpyHostToDevice, st));
-    GB_TRY(insert_key_chunks(m, (const unsigned long long *)keys.p, (const unsigned long long *)d_desc.p,
-                             (const unsigned long long *)d_desc.p + 2, 1, total, st));
+    GB_CUDA(cudaMemcpyAsync(d_desc, desc, sizeof desc, cudaMemcpyHostToDevice, st));
+    GB_TRY(insert_key_chunks(m, keys, d_desc, d_desc + 2, 1, total, st));
     GB_CUDA(cudaEventRecord(m->pe[3], st));
     GB_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < 3; i++) {
@@ -577,7 +629,11 @@ int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_ma
         if ((r = cudaEventCreate(&m->t0) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
         if ((r = cudaEventCreate(&m->t1) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
         if ((r = cudaMalloc((void **)&m->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess ? GB_OK : GB_E_OOM)) break;
-        if ((r = map_alloc_table(&m->table, m->bits, m->stream))) break;
+        {
+            Slot *none = nullptr;
+            int none_bits = 0;
+            if ((r = map_swap_table(m, m->bits, &none, &none_bits))) break;
+        }
         if ((r = cudaStreamSynchronize(m->stream) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
     } while (0);
     if (r != GB_OK) {
@@ -596,6 +652,8 @@ int gb_map_destroy(gb_map *h)
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->table) cudaFreeAsync(m->table, m->stream);
+    if (m->spare) cudaFreeAsync(m->spare, m->stream);
+    if (m->stage) cudaFreeAsync(m->stage, m->stream);
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->d_counters) cudaFree(m->d_counters);
     if (m->d_overflow) cudaFree(m->d_overflow);
@@ -754,15 +812,26 @@ int gb_map_delete_below(gb_map *h, int32_t min_count)
     Map *m;
     GB_TRY(check_map(h, &m));
     unsigned long long n = 1ull << m->bits;
+    if (m->size == 0) return GB_OK;
     GB_TRY(map_zero_counters(m));
-    count_survivors_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(m->table, n, min_count, m->d_counters);
+    // survivors go to the staging buffer: keys first, counts behind them
+    GB_TRY(map_stage(m, (size_t)m->size + (size_t)(m->size + 1) / 2));
+    unsigned long long *sk = m->stage;
+    int *sv = reinterpret_cast<int *>(m->stage + m->size);
+    compact_survivors_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(m->table, n, min_count, sk, sv, m->d_counters);
     GB_LAUNCHED();
     unsigned long long c[4];
     GB_TRY(map_read_counters(m, c));
     int64_t keep = (int64_t)c[1];
     if (keep == m->size) return GB_OK;
-    int nb = bits_for(keep);
-    GB_TRY(map_rebuild(m, nb, true, min_count));
+    // a fresh table sized for the survivors
+    Slot *old = nullptr;
+    int old_alloc = 0;
+    GB_TRY(map_swap_table(m, bits_for(keep), &old, &old_alloc));
+    map_retire_table(m, old, old_alloc);
+    m->grows++;
+    GB_TRY(map_zero_counters(m));
+    GB_TRY(map_launch_update_set(m, sk, sv, keep, m->stream));
     m->size = keep;
     return GB_OK;
 }
@@ -798,16 +867,12 @@ int gb_map_clear(gb_map *h, int64_t min_capacity)
     if (min_capacity < 0) { set_error("negative capacity"); return GB_E_ARG; }
     int nb = bits_for(min_capacity);
     if (nb != m->bits) {
-        Slot *nt = nullptr;
-        GB_CUDA(cudaFreeAsync(m->table, m->stream));
-        m->table = nullptr;
-        GB_TRY(map_alloc_table(&nt, nb, m->stream));
-        m->table = nt;
-        m->bits = nb;
+        Slot *old = nullptr;
+        int old_alloc = 0;
+        GB_TRY(map_swap_table(m, nb, &old, &old_alloc));
+        map_retire_table(m, old, old_alloc);
     } else {
-        unsigned long long n = 1ull << m->bits;
-        init_table_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(m->table, n);
-        GB_LAUNCHED();
+        GB_TRY(init_table(m->table, m->bits, m->stream));
     }
     m->size = 0;
     m->noncanonical = false;

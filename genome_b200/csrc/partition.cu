@@ -21,16 +21,21 @@ __device__ __forceinline__ unsigned int bucket_of(unsigned long long h, unsigned
     return (owner_of(h, owners) << lp_bits) | slice;
 }
 
-// persistent CTAs: CTA c takes tiles c, c + grid, ... in BOTH passes, so its per-bucket counts of pass 1 are exactly
-// the room it needs in pass 2 -- no global atomics, deterministic layout.
+// Persistent CTAs: CTA c takes tiles c, c + grid, ... and inside a tile warp w takes items w*32 + lane + 256*i, in
+// BOTH passes, so a warp's per-bucket counts of pass 1 are exactly the room it needs in pass 2: no global atomics,
+// no shared-memory atomics with a return value, deterministic layout.
+constexpr int WARPS = INSERT_THREADS / 32;
+constexpr int STAGE_MAX_BUCKETS = 128; // above this a warp round (256 keys) has < 2 keys per bucket: nothing to coalesce
+
 template <bool FIXED, bool V210>
 __global__ void __launch_bounds__(INSERT_THREADS)
-part_count_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, unsigned int *cta_hist)
+part_count_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, unsigned int *warp_hist)
 {
     __shared__ ReadTile tile;
-    __shared__ unsigned int s_hist[MAX_BUCKETS];
-    const int tid = threadIdx.x;
-    for (int b = tid; b < MAX_BUCKETS; b += INSERT_THREADS) s_hist[b] = 0;
+    extern __shared__ unsigned int s_dyn[]; // [WARPS][nb]
+    const int tid = threadIdx.x, warp = tid >> 5;
+    unsigned int *hist = s_dyn + (size_t)warp * nb;
+    for (unsigned int b = tid; b < WARPS * nb; b += INSERT_THREADS) s_dyn[b] = 0;
     const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         stage_tile<FIXED>(tile, rb.bin, rb.n_bytes, rb.offsets, rb.rec_bytes, rb.read0, rb.n_reads, k, t);
@@ -40,28 +45,29 @@ part_count_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigne
             const int cnt = item_keys<V210>(tile, item, k, key);
 #pragma unroll
             for (int j = 0; j < SEG; j++)
-                if (j < cnt) atomicAdd(&s_hist[bucket_of(mix64(key[j]), owners, lp_bits)], 1u);
+                if (j < cnt) atomicAdd(&hist[bucket_of(mix64(key[j]), owners, lp_bits)], 1u); // no return value: a RED
         }
         __syncthreads(); // the tile is overwritten by the next stage_tile
     }
     __syncthreads();
-    for (unsigned int b = tid; b < nb; b += INSERT_THREADS) cta_hist[(size_t)blockIdx.x * nb + b] = s_hist[b];
+    for (unsigned int i = tid; i < WARPS * nb; i += INSERT_THREADS)
+        warp_hist[(size_t)blockIdx.x * WARPS * nb + i] = s_dyn[i];
 }
 
-// one CTA per bucket: turn the column of per-CTA counts into exclusive offsets inside the bucket
+// one CTA per bucket: turn the column of per-warp counts into exclusive offsets inside the bucket
 __global__ void __launch_bounds__(256)
-part_offsets_kernel(unsigned int *cta_hist, int grid, unsigned int nb, unsigned long long *bucket_total)
+part_offsets_kernel(unsigned int *warp_hist, int rows, unsigned int nb, unsigned long long *bucket_total)
 {
     const unsigned int b = blockIdx.x;
-    const int per = (grid + 255) / 256;
-    const int c0 = threadIdx.x * per, c1 = min(grid, c0 + per);
+    const int per = (rows + 255) / 256;
+    const int c0 = min(rows, (int)threadIdx.x * per), c1 = min(rows, c0 + per);
     unsigned int sum = 0;
-    for (int c = c0; c < c1; c++) sum += cta_hist[(size_t)c * nb + b];
+    for (int c = c0; c < c1; c++) sum += warp_hist[(size_t)c * nb + b];
     unsigned long long run = block_alloc(sum, nullptr); // exclusive prefix over the threads of this CTA
     if (threadIdx.x == 255) bucket_total[b] = run + sum;
     for (int c = c0; c < c1; c++) {
-        unsigned int v = cta_hist[(size_t)c * nb + b];
-        cta_hist[(size_t)c * nb + b] = (unsigned int)run; // a bucket of one batch holds < 2^32 keys
+        unsigned int v = warp_hist[(size_t)c * nb + b];
+        warp_hist[(size_t)c * nb + b] = (unsigned int)run; // a bucket of one batch holds < 2^32 keys
         run += v;
     }
 }
@@ -82,32 +88,93 @@ part_bases_kernel(const unsigned long long *bucket_total, unsigned int nb, unsig
     }
 }
 
-template <bool FIXED, bool V210>
+// Pass 2.  A warp round = 32 items x SEG keys.  Ranks inside the round come from match.any (lanes with the same
+// bucket) plus a warp-private per-bucket counter, i.e. a warp-level multisplit.  STAGED: the round's keys are first
+// sorted by bucket in a warp-private staging area so that the global stores of consecutive lanes hit consecutive
+// addresses (a 32 B sector per 4 keys) instead of 32 different lines per store instruction.
+template <bool FIXED, bool V210, bool STAGED>
 __global__ void __launch_bounds__(INSERT_THREADS)
-part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, const unsigned int *cta_hist,
+part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, const unsigned int *warp_off,
                     const unsigned long long *bucket_base, unsigned long long *out)
 {
     __shared__ ReadTile tile;
-    __shared__ unsigned long long s_base[MAX_BUCKETS];
-    __shared__ unsigned int s_cur[MAX_BUCKETS];
-    const int tid = threadIdx.x;
-    for (unsigned int b = tid; b < MAX_BUCKETS; b += INSERT_THREADS) {
-        s_cur[b] = 0;
-        s_base[b] = b < nb ? bucket_base[b] + cta_hist[(size_t)blockIdx.x * nb + b] : 0;
-    }
+    extern __shared__ unsigned int s_dyn[];
+    // layout: wcur [WARPS][nb] u32 | rcnt [WARPS][nb] u32 (STAGED) | sdst [WARPS][256] u32 (STAGED) | skey [WARPS][256] u64 (STAGED)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned int *wcur = s_dyn + (size_t)warp * nb;
+    unsigned int *rcnt = s_dyn + (size_t)WARPS * nb + (size_t)warp * nb;
+    unsigned int *sdst = s_dyn + 2 * (size_t)WARPS * nb + (size_t)warp * (32 * SEG);
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(s_dyn + 2 * (size_t)WARPS * nb + (size_t)WARPS * (32 * SEG)) +
+                               (size_t)warp * (32 * SEG);
+    // position of the warp's next key of bucket b, relative to out[0] (a batch holds < 2^32 keys)
+    for (unsigned int b = lane; b < nb; b += 32)
+        wcur[b] = (unsigned int)bucket_base[b] + warp_off[((size_t)blockIdx.x * WARPS + warp) * nb + b];
+    const unsigned int lt = (1u << lane) - 1;
     const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         stage_tile<FIXED>(tile, rb.bin, rb.n_bytes, rb.offsets, rb.rec_bytes, rb.read0, rb.n_reads, k, t);
         const unsigned int total_items = tile.prefix[TILE_READS];
-        for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
+        // all lanes of a warp run the same number of rounds
+        for (unsigned int item0 = warp * 32; item0 < total_items; item0 += INSERT_THREADS) {
+            const unsigned int item = item0 + lane;
             unsigned long long key[SEG];
-            const int cnt = item_keys<V210>(tile, item, k, key);
+            int cnt = 0;
+            if (item < total_items) cnt = item_keys<V210>(tile, item, k, key);
+            if (STAGED) {
+                for (unsigned int b = lane; b < nb; b += 32) rcnt[b] = 0;
+                __syncwarp();
+            }
+            unsigned int bk[SEG], rk[SEG];
 #pragma unroll
-            for (int j = 0; j < SEG; j++)
-                if (j < cnt) {
-                    unsigned int b = bucket_of(mix64(key[j]), owners, lp_bits);
-                    out[s_base[b] + atomicAdd(&s_cur[b], 1u)] = key[j];
+            for (int j = 0; j < SEG; j++) {
+                const bool valid = j < cnt;
+                const unsigned int b = valid ? bucket_of(mix64(key[j]), owners, lp_bits) : 0xFFFFFFFFu;
+                const unsigned int peers = __match_any_sync(0xFFFFFFFFu, b);
+                const unsigned int rank = __popc(peers & lt);
+                unsigned int *ctr = STAGED ? rcnt : wcur;
+                const unsigned int base = valid ? ctr[b] : 0;
+                __syncwarp();
+                if (valid && rank == 0) ctr[b] = base + __popc(peers);
+                __syncwarp();
+                bk[j] = b;
+                rk[j] = base + rank;
+                if (!STAGED && valid) out[rk[j]] = key[j];
+            }
+            if (STAGED) {
+                // global positions from the warp cursors (read before they advance)
+                unsigned int gp[SEG];
+#pragma unroll
+                for (int j = 0; j < SEG; j++) gp[j] = j < cnt ? wcur[bk[j]] + rk[j] : 0;
+                __syncwarp();
+                // exclusive scan of the round's bucket counts -> start of each bucket's run in the staging area
+                unsigned int run = 0;
+                for (unsigned int b0 = 0; b0 < nb; b0 += 32) {
+                    const unsigned int b = b0 + lane;
+                    const unsigned int c = b < nb ? rcnt[b] : 0;
+                    unsigned int incl = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= d) incl += v;
+                    }
+                    if (b < nb) {
+                        rcnt[b] = run + incl - c;
+                        wcur[b] += c;
+                    }
+                    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
                 }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < SEG; j++)
+                    if (j < cnt) {
+                        const unsigned int idx = rcnt[bk[j]] + rk[j];
+                        skey[idx] = key[j];
+                        sdst[idx] = gp[j];
+                    }
+                __syncwarp();
+                for (unsigned int idx = lane; idx < run; idx += 32) out[sdst[idx]] = skey[idx];
+                __syncwarp();
+            }
         }
         __syncthreads();
     }
@@ -115,9 +182,8 @@ part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsig
 
 // ---------------------------------------------------------------- bulk upsert from key ranges
 constexpr int IK_THREADS = 256;
-constexpr int IK_PER_THREAD = 8;
-constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
 
+template <int IK_PER_THREAD>
 __global__ void __launch_bounds__(IK_THREADS)
 insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vstart,
                    const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Slot *table, int bits,
@@ -125,6 +191,7 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
 {
     __shared__ int s_chunk0;
     __shared__ unsigned int s_new;
+    constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
     const unsigned long long v0 = (unsigned long long)blockIdx.x * IK_PER_CTA;
     if (threadIdx.x == 0) {
         int lo = 0, hi = n_chunks; // last chunk with vstart <= v0
@@ -154,9 +221,26 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
     for (int j = 0; j < IK_PER_THREAD; j++)
         if (ok[j]) cur[j] = load_key(table + idx[j]);
     int nk = 0;
+    // the CAS round trips of a thread's keys overlap: all of them are issued before the first result is used
+    unsigned long long old[IK_PER_THREAD];
 #pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++)
-        if (ok[j]) nk += upsert_add(table, tmask, idx[j], cur[j], key[j], 1);
+    for (int j = 0; j < IK_PER_THREAD; j++) {
+        old[j] = cur[j];
+        if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < IK_PER_THREAD; j++) {
+        if (!ok[j]) continue;
+        const bool claimed = cur[j] == EMPTY_KEY && old[j] == EMPTY_KEY;
+        if (claimed || old[j] == key[j]) {
+            red_add_s32(&table[idx[j]].count, 1);
+            nk += claimed;
+        } else {
+            // the slot belongs to another key: linear probing from the next slot (rare at load <= 0.5)
+            unsigned long long nx = (idx[j] + 1) & tmask;
+            nk += upsert_add(table, tmask, nx, load_key(table + nx), key[j], 1);
+        }
+    }
     nk = __reduce_add_sync(0xFFFFFFFFu, nk);
     if ((threadIdx.x & 31) == 0 && nk) atomicAdd(&s_new, (unsigned int)nk);
     __syncthreads();
@@ -168,9 +252,9 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
 int PartWork::ensure(cudaStream_t st)
 {
     if (cta_hist) return GB_OK;
-    grid = SM_COUNT * 8; // 8 resident CTAs of 256 threads per SM (37 registers); persistent over the tiles
+    grid = SM_COUNT * 4; // persistent over the tiles; 4-5 CTAs of 256 threads fit the shared memory of an SM
     owner_stream = st;
-    GB_CUDA(cudaMalloc((void **)&cta_hist, (size_t)grid * MAX_BUCKETS * sizeof(unsigned int)));
+    GB_CUDA(cudaMalloc((void **)&cta_hist, (size_t)grid * WARPS * MAX_BUCKETS * sizeof(unsigned int)));
     GB_CUDA(cudaMalloc((void **)&bucket_base, (MAX_BUCKETS + 1) * sizeof(unsigned long long)));
     GB_CUDA(cudaMalloc((void **)&bucket_total, MAX_BUCKETS * sizeof(unsigned long long)));
     return GB_OK;
@@ -191,12 +275,13 @@ int part_count(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, Part
     const unsigned int nb = (unsigned int)pl.nb();
     if (nb > MAX_BUCKETS) { set_error("internal: %u buckets", nb); return GB_E_ARG; }
     const bool fixed = rb.offsets == nullptr;
-#define GB_PC(F, V) part_count_kernel<F, V><<<w.grid, INSERT_THREADS, 0, st>>>(rb, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist)
+    const size_t smem = (size_t)WARPS * nb * sizeof(unsigned int);
+#define GB_PC(F, V) part_count_kernel<F, V><<<w.grid, INSERT_THREADS, smem, st>>>(rb, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist)
     if (fixed) { if (v210) GB_PC(true, true); else GB_PC(true, false); }
     else { if (v210) GB_PC(false, true); else GB_PC(false, false); }
 #undef GB_PC
     GB_LAUNCHED();
-    part_offsets_kernel<<<nb, 256, 0, st>>>(w.cta_hist, w.grid, nb, w.bucket_total);
+    part_offsets_kernel<<<nb, 256, 0, st>>>(w.cta_hist, w.grid * WARPS, nb, w.bucket_total);
     GB_LAUNCHED();
     part_bases_kernel<<<1, MAX_BUCKETS, 0, st>>>(w.bucket_total, nb, w.bucket_base);
     GB_LAUNCHED();
@@ -207,9 +292,13 @@ int part_scatter(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, Pa
 {
     const unsigned int nb = (unsigned int)pl.nb();
     const bool fixed = rb.offsets == nullptr;
-#define GB_PS(F, V) part_scatter_kernel<F, V><<<w.grid, INSERT_THREADS, 0, st>>>(rb, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist, w.bucket_base, out)
-    if (fixed) { if (v210) GB_PS(true, true); else GB_PS(true, false); }
-    else { if (v210) GB_PS(false, true); else GB_PS(false, false); }
+    const bool staged = nb <= STAGE_MAX_BUCKETS && !getenv("GENOME_B200_NO_STAGING");
+    const size_t smem = staged ? (size_t)WARPS * (2 * nb * 4 + 32 * SEG * 12) : (size_t)WARPS * nb * 4;
+#define GB_PS(F, V, S) part_scatter_kernel<F, V, S><<<w.grid, INSERT_THREADS, smem, st>>>(rb, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist, w.bucket_base, out)
+#define GB_PS2(F, V) do { if (staged) GB_PS(F, V, true); else GB_PS(F, V, false); } while (0)
+    if (fixed) { if (v210) GB_PS2(true, true); else GB_PS2(true, false); }
+    else { if (v210) GB_PS2(false, true); else GB_PS2(false, false); }
+#undef GB_PS2
 #undef GB_PS
     GB_LAUNCHED();
     return GB_OK;
@@ -219,8 +308,13 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
                       int n_chunks, unsigned long long n_total, cudaStream_t st)
 {
     if (!n_total) return GB_OK;
-    unsigned long long grid = (n_total + IK_PER_CTA - 1) / IK_PER_CTA;
-    insert_keys_kernel<<<(unsigned int)grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->bits, m->d_counters);
+    static int per = 0;
+    if (!per) { const char *e = getenv("GENOME_B200_IK"); per = e ? atoi(e) : 4; }
+#define GB_IK(N)                                                                                                          \
+    insert_keys_kernel<N><<<(unsigned int)((n_total + IK_THREADS * N - 1) / (IK_THREADS * N)), IK_THREADS, 0, st>>>(       \
+        d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->bits, m->d_counters)
+    if (per == 8) GB_IK(8); else if (per == 16) GB_IK(16); else if (per == 2) GB_IK(2); else GB_IK(4);
+#undef GB_IK
     GB_LAUNCHED();
     return GB_OK;
 }
