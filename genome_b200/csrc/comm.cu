@@ -9,6 +9,7 @@
 //   insert       : update(key, 1, _ + 1) for every received key                      (the map's stream)
 // Two buffer sets: batch b+1 is routed and exchanged while batch b is inserted.
 #include <dlfcn.h>
+#include <time.h>
 #include <nccl.h> // types only: the library is bound at run time (see NcclApi)
 
 #include <algorithm>
@@ -20,7 +21,6 @@
 
 namespace gb {
 
-constexpr int MAX_RANKS = 64;
 
 // one of the two staging sets of the sharded insert; lives as long as the communicator
 struct BatchBufs {
@@ -38,8 +38,14 @@ struct Comm {
     int rank = 0, n_ranks = 1, device = 0;
     ncclComm_t nccl = nullptr;
     cudaStream_t stream = nullptr; // bucketing + collectives
-    BatchBufs bufs[2];
+    BatchBufs bufs[3];
     unsigned long long *d_scratch = nullptr, *h_scratch = nullptr;
+    // NVLink inboxes (fused routing): inbox[i] holds n_ranks regions of region_cap keys, region s is written by rank s
+    // through its peer mapping peer_inbox[i][me] obtained with CUDA IPC
+    unsigned long long *inbox[3] = { nullptr, nullptr, nullptr };
+    unsigned long long *peer_inbox[3][MAX_RANKS];
+    size_t region_cap = 0;
+    int p2p = -1; // -1 unknown, 0 NCCL send/recv staging, 1 peer stores
 };
 
 // NCCL is bound with dlopen at the first gb_comm_* call, not at link time: a process that already holds an NCCL
@@ -206,8 +212,75 @@ void BatchBufs::release()
     exchanged = inserted = nullptr;
 }
 
+static void close_inboxes(Comm *c)
+{
+    for (int i = 0; i < 3; i++) {
+        for (int p = 0; p < c->n_ranks; p++)
+            if (p != c->rank && c->peer_inbox[i][p]) cudaIpcCloseMemHandle(c->peer_inbox[i][p]);
+        if (c->inbox[i]) cudaFree(c->inbox[i]);
+        c->inbox[i] = nullptr;
+        for (int p = 0; p < MAX_RANKS; p++) c->peer_inbox[i][p] = nullptr;
+    }
+    c->region_cap = 0;
+}
+
+// collective: make sure every rank's three inboxes hold n_ranks regions of at least `want` keys and that every rank
+// has them mapped.  Returns with c->p2p = 1, or 0 when peer access is not possible (then NCCL send/recv is used).
+static int ensure_inboxes(Comm *c, size_t want)
+{
+    const int P = c->n_ranks;
+    if (c->p2p == 0) return GB_OK;
+    if (c->p2p < 0) {
+        int64_t ok = 1;
+        if (getenv("GENOME_B200_A2A") && !strcmp(getenv("GENOME_B200_A2A"), "nccl")) ok = 0;
+        int ndev = 0;
+        cudaGetDeviceCount(&ndev);
+        // ranks are the visible devices 0..P-1 of one box (one process per GPU): all of them must be peers of mine
+        for (int d = 0; ok && d < P; d++) {
+            if (d == c->device) continue;
+            int can = 0;
+            if (d >= ndev || cudaDeviceCanAccessPeer(&can, c->device, d) != cudaSuccess || !can) ok = 0;
+        }
+        cudaGetLastError();
+        GB_TRY(all_reduce_i64(c, &ok, ncclMin));
+        c->p2p = ok ? 1 : 0;
+        if (!c->p2p) return GB_OK;
+    }
+    int64_t need = (int64_t)want;
+    GB_TRY(all_reduce_i64(c, &need, ncclMax));
+    if ((size_t)need <= c->region_cap) return GB_OK;
+    GB_CUDA(cudaDeviceSynchronize());
+    close_inboxes(c);
+    const size_t cap = (size_t)need + (size_t)need / 16 + 1024;
+    GB_TRY(comm_scratch(c));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    for (int i = 0; i < 3; i++) {
+        GB_CUDA(cudaMalloc((void **)&c->inbox[i], cap * P * 8));
+        cudaIpcMemHandle_t mine;
+        GB_CUDA(cudaIpcGetMemHandle(&mine, c->inbox[i]));
+        // all-gather the 64-byte handles through device memory
+        unsigned long long *d_mine = c->d_scratch, *d_all = c->d_scratch + 8;
+        GB_CUDA(cudaMemcpyAsync(d_mine, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+        GB_NCCL(ncclAllGather(d_mine, d_all, 8, ncclUint64, c->nccl, c->stream));
+        std::vector<cudaIpcMemHandle_t> all((size_t)P);
+        GB_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)P * 64, cudaMemcpyDeviceToHost, c->stream));
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int p = 0; p < P; p++) {
+            if (p == c->rank) { c->peer_inbox[i][p] = c->inbox[i]; continue; }
+            void *ptr = nullptr;
+            GB_CUDA(cudaIpcOpenMemHandle(&ptr, all[(size_t)p], cudaIpcMemLazyEnablePeerAccess));
+            c->peer_inbox[i][p] = (unsigned long long *)ptr;
+        }
+    }
+    c->region_cap = cap;
+    // nobody may write into a peer's inbox before that peer has finished mapping: one more collective as a barrier
+    int64_t one = 1;
+    GB_TRY(all_reduce_i64(c, &one, ncclSum));
+    return GB_OK;
+}
+
 // wait for every in-flight insert, fold the new-key counter into m->size
-static int drain(Map *m, BatchBufs bufs[2])
+static int drain(Map *m, BatchBufs *bufs)
 {
     GB_CUDA(cudaStreamSynchronize(m->stream));
     unsigned long long c[4];
@@ -215,7 +288,7 @@ static int drain(Map *m, BatchBufs bufs[2])
     m->size += (int64_t)c[0];
     GB_TRY(map_zero_counters(m));
     GB_CUDA(cudaStreamSynchronize(m->stream));
-    bufs[0].in_flight = bufs[1].in_flight = false;
+    bufs[0].in_flight = bufs[1].in_flight = bufs[2].in_flight = false;
     return GB_OK;
 }
 
@@ -234,10 +307,17 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     const int64_t win_max = fixed ? std::max<int64_t>(0, (int64_t)len0 - k + 1) : (255 - k + 1);
     // batches: enough of them to overlap exchange with upsert, bounded staging memory (<= 2^26 k-mers = 512 MiB each)
     int64_t batch_reads = std::max<int64_t>(TILE_READS, (((int64_t)1 << 26) / std::max<int64_t>(win_max, 1)) / TILE_READS * TILE_READS);
-    int64_t quarter = ((n_reads + 3) / 4 + TILE_READS - 1) / TILE_READS * TILE_READS;
-    if (quarter >= TILE_READS * 64) batch_reads = std::min(batch_reads, quarter);
+    int want_batches = 2;
+    if (const char *e = getenv("GENOME_B200_BATCHES")) want_batches = std::max(1, atoi(e));
+    int64_t part = ((n_reads + want_batches - 1) / want_batches + TILE_READS - 1) / TILE_READS * TILE_READS;
+    if (part >= TILE_READS * 64) batch_reads = std::min(batch_reads, part);
     int64_t batches = n_reads ? (n_reads + batch_reads - 1) / batch_reads : 0;
     int64_t lp = slice_bits_for(m->bits, P);
+    // fewer buckets = longer runs per bucket in the staged bucket pass = fuller NVLink write packets; measured at
+    // P = 2: 16 slices/shard 4.1 ms, 64 slices/shard 6.0 ms per 96.6 M k-mers.  Below 8 slices the upsert leaves L2.
+    while (lp > 3 && (P << lp) > 32) lp--;
+    while (lp > 0 && (P << lp) > 128) lp--; // stay in the staged (sector-coalesced) regime
+    if (const char *e = getenv("GENOME_B200_LP")) lp = std::min<int64_t>(lp, std::max(0, atoi(e)));
     GB_TRY(all_reduce_i64(c, &batches, ncclMax));
     GB_TRY(all_reduce_i64(c, &lp, ncclMin)); // every rank must cut the same buckets
     PartLayout pl;
@@ -245,38 +325,82 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     pl.lp_bits = (int)lp;
     const int LP = 1 << pl.lp_bits, NB = pl.nb();
 
+    const bool trace = getenv("GENOME_B200_TRACE") && c->rank == 0;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now_ms();
+    if (trace) fprintf(stderr, "[pmap] %lld reads, %lld batches of %lld, LP=%d\n", (long long)n_reads, (long long)batches, (long long)batch_reads, LP);
+    std::vector<cudaEvent_t> tev; // trace only: 7 events per batch
+    auto mark = [&](cudaStream_t strm) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, strm);
+        tev.push_back(e);
+    };
     BatchBufs *bufs = c->bufs;
+    // fused routing: every rank's bucket pass stores straight into the owners' inboxes over NVLink
+    GB_TRY(ensure_inboxes(c, (size_t)std::min<int64_t>(batch_reads, std::max<int64_t>(n_reads, 1)) * (size_t)std::max<int64_t>(win_max, 1)));
+    const bool p2p = c->p2p == 1;
+    if (trace) fprintf(stderr, "[pmap] routing: %s\n", p2p ? "peer stores into NVLink inboxes" : "NCCL send/recv");
     GB_TRY(map_zero_counters(m));
     GB_CUDA(cudaStreamSynchronize(m->stream));
     GB_CUDA(cudaEventRecord(m->ev0, m->stream));
 
     int64_t windows = 0, pending_upper = 0; // pending_upper: keys handed to upserts not yet folded into m->size
     for (int64_t b = 0; b < batches; b++) {
-        BatchBufs &B = bufs[b & 1];
+        // three buffer sets: a rank that has received my counts of batch j knows my upsert of batch j - 2 is over
+        // (the wait below precedes them on my stream), so it may store batch j + 1 into set (j + 1) % 3 = (j - 2) % 3
+        BatchBufs &B = bufs[b % 3];
+        if (b >= 2 && bufs[(b - 2) % 3].in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, bufs[(b - 2) % 3].inserted, 0));
         const int64_t r0 = std::min(n_reads, b * batch_reads), r1 = std::min(n_reads, r0 + batch_reads), nr = r1 - r0;
         const int64_t w_upper = fixed ? nr * win_max : (h_win_prefix ? h_win_prefix[r1] - h_win_prefix[r0] : nr * win_max);
         if (B.in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, B.inserted, 0)); // its buffers are still being read
-        GB_TRY(B.ensure((size_t)w_upper, 0));
+        GB_TRY(B.ensure(p2p ? 0 : (size_t)w_upper, 0));
         ReadBatch rb;
         rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = d_off; rb.rec_bytes = rec; rb.read0 = r0; rb.n_reads = nr;
         // d_tot: [0, NB) my bucket totals (row o = what I send to owner o), [NB, 2NB) row s = what source s sends me
+        mark(c->stream);
         GB_TRY(part_count(rb, k, m->v210, pl, B.work, c->stream));
+        mark(c->stream);
         GB_CUDA(cudaMemcpyAsync(B.d_tot, B.work.bucket_total, NB * 8, cudaMemcpyDeviceToDevice, c->stream));
-        GB_TRY(all_to_all_rows(c, B.d_tot, B.d_tot + NB, (size_t)LP));
-        GB_CUDA(cudaMemcpyAsync(B.h_tot, B.d_tot, 2 * NB * 8, cudaMemcpyDeviceToHost, c->stream));
-        GB_TRY(part_scatter(rb, k, m->v210, pl, B.work, B.send, c->stream)); // runs while the host waits for the counts
+        if (!p2p) {
+            GB_TRY(all_to_all_rows(c, B.d_tot, B.d_tot + NB, (size_t)LP));
+            GB_CUDA(cudaMemcpyAsync(B.h_tot, B.d_tot, 2 * NB * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        mark(c->stream);
+        if (p2p) {
+            PeerOut po;
+            memset(&po, 0, sizeof po);
+            for (int p = 0; p < P; p++) po.base[p] = c->peer_inbox[b % 3][p] + (size_t)c->rank * c->region_cap;
+            GB_TRY(part_scatter_peers(rb, k, m->v210, pl, B.work, po, c->stream));
+            // the counts travel AFTER the keys on my stream: whoever has my counts has my keys
+            GB_TRY(all_to_all_rows(c, B.d_tot, B.d_tot + NB, (size_t)LP));
+            GB_CUDA(cudaMemcpyAsync(B.h_tot, B.d_tot, 2 * NB * 8, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            GB_TRY(part_scatter(rb, k, m->v210, pl, B.work, B.send, c->stream)); // runs while the host waits for the counts
+        }
+        mark(c->stream);
+        const double t_issue = now_ms();
         GB_CUDA(cudaStreamSynchronize(c->stream));
+        const double t_counts = now_ms();
         unsigned long long scnt[MAX_RANKS], soff[MAX_RANKS], rcnt[MAX_RANKS], roff[MAX_RANKS];
         unsigned long long st = 0, rt = 0;
         for (int p = 0; p < P; p++) {
             unsigned long long s1 = 0, s2 = 0;
             for (int l = 0; l < LP; l++) { s1 += B.h_tot[p * LP + l]; s2 += B.h_tot[NB + p * LP + l]; }
             scnt[p] = s1; soff[p] = st; st += s1;
-            rcnt[p] = s2; roff[p] = rt; rt += s2;
+            rcnt[p] = s2; roff[p] = p2p ? (unsigned long long)p * c->region_cap : rt; rt += s2;
         }
         windows += (int64_t)st;
-        GB_TRY(B.ensure(0, (size_t)rt));
-        GB_TRY(all_to_all_v(c, B.send, soff, scnt, B.recv, roff, rcnt, ncclUint64));
+        const unsigned long long *recv_keys = nullptr;
+        if (p2p) {
+            recv_keys = c->inbox[b % 3];
+        } else {
+            GB_TRY(B.ensure(0, (size_t)rt));
+            GB_TRY(all_to_all_v(c, B.send, soff, scnt, B.recv, roff, rcnt, ncclUint64));
+            recv_keys = B.recv;
+        }
+        mark(c->stream);
         // chunk table of the upsert, slice-major: chunk (l, s) = source s's keys of slice l
         unsigned long long *vstart = B.h_tot + 2 * NB, *coff = vstart + NB + 1;
         {
@@ -314,14 +438,28 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
             }
         }
         GB_CUDA(cudaStreamWaitEvent(m->stream, B.exchanged, 0));
-        GB_TRY(insert_key_chunks(m, B.recv, B.d_tot + 2 * NB, B.d_tot + 3 * NB + 1, NB, rt, m->stream));
+        mark(m->stream);
+        GB_TRY(insert_key_chunks(m, recv_keys, B.d_tot + 2 * NB, B.d_tot + 3 * NB + 1, NB, rt, m->stream));
+        mark(m->stream);
         GB_CUDA(cudaEventRecord(B.inserted, m->stream));
         B.in_flight = true;
         pending_upper += (int64_t)rt;
+        if (trace) fprintf(stderr, "[pmap] batch %lld: issued %.3f  bucketed+counts %.3f  enqueued %.3f ms (send %llu recv %llu)\n", (long long)b,
+                           t_issue - t_begin, t_counts - t_begin, now_ms() - t_begin, st, rt);
     }
     GB_CUDA(cudaEventRecord(m->ev1, m->stream));
     GB_TRY(drain(m, bufs));
     GB_CUDA(cudaStreamSynchronize(c->stream));
+    if (trace) {
+        fprintf(stderr, "[pmap] drained %.3f ms\n", now_ms() - t_begin);
+        for (size_t b = 0; b + 7 <= tev.size(); b += 7) {
+            float t[7];
+            for (int i = 0; i < 7; i++) cudaEventElapsedTime(&t[i], tev[0], tev[b + i]);
+            fprintf(stderr, "[pmap] gpu batch %zu: count %.3f-%.3f  counts-exchange -%.3f  scatter -%.3f  all-to-all -%.3f | upsert %.3f-%.3f\n",
+                    b / 7, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     float ms = 0;
     GB_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
     m->last_insert_ns = (int64_t)(ms * 1e6);
@@ -367,11 +505,16 @@ int gb_comm_create(const uint8_t id[GB_UNIQUE_ID_BYTES], int rank, int n_ranks, 
     GB_CUDA(cudaSetDevice(device));
     Comm *c = new Comm();
     c->rank = rank; c->n_ranks = n_ranks; c->device = device;
+    memset(c->peer_inbox, 0, sizeof c->peer_inbox);
     ncclUniqueId u;
     memcpy(&u, id, sizeof u);
     ncclResult_t r = ncclCommInitRank(&c->nccl, n_ranks, u, rank);
     if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank", __FILE__, __LINE__); }
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // the bucketing + exchange stream is the critical path of the sharded insert: its CTAs go first when SM slots free
+    // up under the (much larger) upsert grid that runs on the map's stream
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         ncclCommDestroy(c->nccl);
         delete c;
         set_error("stream creation failed");
@@ -387,8 +530,10 @@ int gb_comm_destroy(gb_comm *h)
     Comm *c = reinterpret_cast<Comm *>(h);
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    close_inboxes(c);
     c->bufs[0].release();
     c->bufs[1].release();
+    c->bufs[2].release();
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     if (c->nccl) ncclCommDestroy(c->nccl);

@@ -443,6 +443,7 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
     PartLayout pl;
     pl.owners = 1;
     pl.lp_bits = slice_bits_for(m->bits, 1);
+    if (const char *e = getenv("GENOME_B200_LP")) pl.lp_bits = std::max(0, std::min(pl.lp_bits + 3, atoi(e)));
     ReadBatch rb;
     rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = d_off; rb.rec_bytes = rec; rb.read0 = read0; rb.n_reads = n_reads;
     GB_CUDA(cudaEventRecord(m->pe[0], st));

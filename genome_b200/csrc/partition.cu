@@ -92,10 +92,12 @@ part_bases_kernel(const unsigned long long *bucket_total, unsigned int nb, unsig
 // bucket) plus a warp-private per-bucket counter, i.e. a warp-level multisplit.  STAGED: the round's keys are first
 // sorted by bucket in a warp-private staging area so that the global stores of consecutive lanes hit consecutive
 // addresses (a 32 B sector per 4 keys) instead of 32 different lines per store instruction.
-template <bool FIXED, bool V210, bool STAGED>
+// PEER: the position of a key is (owner, index inside the owner's segment) packed in 32 bits and the store goes to
+// the owner's inbox through its peer mapping -- the all-to-all happens inside this kernel, store by store.
+template <bool FIXED, bool V210, bool STAGED, bool PEER>
 __global__ void __launch_bounds__(INSERT_THREADS)
 part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, const unsigned int *warp_off,
-                    const unsigned long long *bucket_base, unsigned long long *out)
+                    const unsigned long long *bucket_base, unsigned long long *out, PeerOut peers)
 {
     __shared__ ReadTile tile;
     extern __shared__ unsigned int s_dyn[];
@@ -107,8 +109,18 @@ part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsig
     unsigned long long *skey = reinterpret_cast<unsigned long long *>(s_dyn + 2 * (size_t)WARPS * nb + (size_t)WARPS * (32 * SEG)) +
                                (size_t)warp * (32 * SEG);
     // position of the warp's next key of bucket b, relative to out[0] (a batch holds < 2^32 keys)
-    for (unsigned int b = lane; b < nb; b += 32)
-        wcur[b] = (unsigned int)bucket_base[b] + warp_off[((size_t)blockIdx.x * WARPS + warp) * nb + b];
+    for (unsigned int b = lane; b < nb; b += 32) {
+        unsigned int pos = (unsigned int)bucket_base[b] + warp_off[((size_t)blockIdx.x * WARPS + warp) * nb + b];
+        if (PEER) { // relative to the owner's segment, owner in the top bits
+            const unsigned int o = b >> lp_bits;
+            pos = (pos - (unsigned int)bucket_base[o << lp_bits]) | (o << P2P_REL_BITS);
+        }
+        wcur[b] = pos;
+    }
+    auto store = [&](unsigned int pos, unsigned long long key) {
+        if (PEER) peers.base[pos >> P2P_REL_BITS][pos & ((1u << P2P_REL_BITS) - 1)] = key;
+        else out[pos] = key;
+    };
     const unsigned int lt = (1u << lane) - 1;
     const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -138,7 +150,7 @@ part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsig
                 __syncwarp();
                 bk[j] = b;
                 rk[j] = base + rank;
-                if (!STAGED && valid) out[rk[j]] = key[j];
+                if (!STAGED && valid) store(rk[j], key[j]);
             }
             if (STAGED) {
                 // global positions from the warp cursors (read before they advance)
@@ -172,7 +184,7 @@ part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsig
                         sdst[idx] = gp[j];
                     }
                 __syncwarp();
-                for (unsigned int idx = lane; idx < run; idx += 32) out[sdst[idx]] = skey[idx];
+                for (unsigned int idx = lane; idx < run; idx += 32) store(sdst[idx], skey[idx]);
                 __syncwarp();
             }
         }
@@ -288,20 +300,36 @@ int part_count(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, Part
     return GB_OK;
 }
 
-int part_scatter(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, cudaStream_t st)
+static int launch_scatter(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out,
+                          const PeerOut *peers, cudaStream_t st)
 {
     const unsigned int nb = (unsigned int)pl.nb();
     const bool fixed = rb.offsets == nullptr;
     const bool staged = nb <= STAGE_MAX_BUCKETS && !getenv("GENOME_B200_NO_STAGING");
     const size_t smem = staged ? (size_t)WARPS * (2 * nb * 4 + 32 * SEG * 12) : (size_t)WARPS * nb * 4;
-#define GB_PS(F, V, S) part_scatter_kernel<F, V, S><<<w.grid, INSERT_THREADS, smem, st>>>(rb, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist, w.bucket_base, out)
-#define GB_PS2(F, V) do { if (staged) GB_PS(F, V, true); else GB_PS(F, V, false); } while (0)
+    PeerOut po;
+    memset(&po, 0, sizeof po);
+    if (peers) po = *peers;
+#define GB_PS(F, V, S, P) part_scatter_kernel<F, V, S, P><<<w.grid, INSERT_THREADS, smem, st>>>(rb, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist, w.bucket_base, out, po)
+#define GB_PS3(F, V, S) do { if (peers) GB_PS(F, V, S, true); else GB_PS(F, V, S, false); } while (0)
+#define GB_PS2(F, V) do { if (staged) GB_PS3(F, V, true); else GB_PS3(F, V, false); } while (0)
     if (fixed) { if (v210) GB_PS2(true, true); else GB_PS2(true, false); }
     else { if (v210) GB_PS2(false, true); else GB_PS2(false, false); }
 #undef GB_PS2
+#undef GB_PS3
 #undef GB_PS
     GB_LAUNCHED();
     return GB_OK;
+}
+
+int part_scatter(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, cudaStream_t st)
+{
+    return launch_scatter(rb, k, v210, pl, w, out, nullptr, st);
+}
+
+int part_scatter_peers(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, const PeerOut &peers, cudaStream_t st)
+{
+    return launch_scatter(rb, k, v210, pl, w, nullptr, &peers, st);
 }
 
 int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned long long *d_vstart, const unsigned long long *d_off,

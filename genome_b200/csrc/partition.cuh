@@ -6,7 +6,16 @@
 namespace gb {
 
 constexpr int MAX_BUCKETS = 512;
-constexpr int SLICE_LOG2_BYTES = 25; // a table slice of 32 MiB stays resident in the 126 MB L2 while it is filled
+constexpr int MAX_RANKS = 64;
+constexpr int P2P_REL_BITS = 26; // a sharded batch holds at most 2^26 k-mers
+
+// destination of pass 2 when the buckets of owner o go straight into o's inbox over NVLink (peer-mapped memory):
+// key number r of owner o's segment is stored at base[o][r]
+struct PeerOut {
+    unsigned long long *base[MAX_RANKS];
+};
+constexpr int SLICE_LOG2_BYTES = 26; // a table slice of 64 MiB stays resident in the 126 MB L2 while it is filled;
+                                     // measured on C2 (2.1 GB table): 8..32 slices within 1%, 64 slices 10% slower (bucket pass)
 
 // bucket = owner * (1 << lp_bits) + slice, owner = owner_of(h, owners), slice = top lp_bits of h (= of the slot index)
 struct PartLayout {
@@ -46,6 +55,8 @@ inline int slice_bits_for(int table_bits, int owners)
 int part_count(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, cudaStream_t st);
 // pass 2: write every canonical k-mer of the batch into its bucket's range of `out` (bucket-major order)
 int part_scatter(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, cudaStream_t st);
+// same, but owner o's buckets are written to peers.base[o] (its inbox region for this rank), not to one local array
+int part_scatter_peers(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, const PeerOut &peers, cudaStream_t st);
 
 // update(key, 1, _ + 1) for the keys of `n_chunks` ranges visited in order: chunk c holds the virtual positions
 // [vstart[c], vstart[c+1]) and starts at keys[off[c]].  d_vstart has n_chunks + 1 entries.  n_total = vstart[n_chunks].
