@@ -723,21 +723,11 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
     unsigned long long t = 0;
     for (int p = 0; p < P; p++) { offs[p] = t; t += sizes[p]; }
 
-    // local export to device arrays (through the host-free path: export kernel writes device buffers)
+    // every shard exports straight into its segment of the gathered arrays
     DeviceBuf all_keys, all_vals;
     GB_TRY(all_keys.alloc((size_t)t * 8));
     GB_TRY(all_vals.alloc((size_t)t * 4));
-    {
-        std::vector<uint64_t> hk((size_t)m->size);
-        std::vector<int32_t> hv((size_t)m->size);
-        int64_t nn = 0;
-        GB_TRY(gb_map_export(h, hk.data(), hv.data(), m->size, &nn));
-        if (nn) {
-            GB_CUDA(cudaMemcpyAsync((unsigned long long *)all_keys.p + offs[c->rank], hk.data(), (size_t)nn * 8, cudaMemcpyHostToDevice, c->stream));
-            GB_CUDA(cudaMemcpyAsync((int *)all_vals.p + offs[c->rank], hv.data(), (size_t)nn * 4, cudaMemcpyHostToDevice, c->stream));
-        }
-        GB_CUDA(cudaStreamSynchronize(c->stream));
-    }
+    GB_TRY(map_export_device(m, (unsigned long long *)all_keys.p + offs[c->rank], (int *)all_vals.p + offs[c->rank]));
     GB_NCCL(ncclGroupStart());
     for (int p = 0; p < P; p++) {
         if (!sizes[p]) continue;

@@ -167,6 +167,7 @@ int map_budget(Map *m, int64_t incoming, int64_t *budget);
 int map_read_counters(Map *m, unsigned long long out[4]);
 int map_zero_counters(Map *m);
 int map_rebuild(Map *m, int new_bits, bool filter, int min_count);
+int map_export_device(Map *m, unsigned long long *d_keys, int *d_vals);
 int map_verify_fixed(Map *m, const uint8_t *d_bin, unsigned int rec, unsigned int len0, int64_t n_reads, unsigned long long *bad);
 int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n, cudaStream_t st);
 int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d_vals, int64_t n, cudaStream_t st);

@@ -578,6 +578,22 @@ int check_map(gb_map *h, Map **m)
 
 } // namespace gb
 
+namespace gb {
+// mapReduce export into DEVICE arrays of m->size entries (synchronises the map's stream)
+int map_export_device(Map *m, unsigned long long *d_keys, int *d_vals)
+{
+    if (m->size == 0) return GB_OK;
+    unsigned long long n = 1ull << m->bits;
+    GB_TRY(map_zero_counters(m));
+    export_kernel<<<grid_for(n, 256, 16), 256, 0, m->stream>>>(m->table, n, d_keys, d_vals, (unsigned long long)m->size, m->d_counters);
+    GB_LAUNCHED();
+    unsigned long long c[4];
+    GB_TRY(map_read_counters(m, c));
+    if ((int64_t)c[1] != m->size) { set_error("internal: exported %llu keys, size is %lld", c[1], (long long)m->size); return GB_E_INVARIANT; }
+    return GB_OK;
+}
+} // namespace gb
+
 // ================================================================ C ABI
 
 extern "C" {
