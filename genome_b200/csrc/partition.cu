@@ -21,21 +21,20 @@ __device__ __forceinline__ unsigned int bucket_of(unsigned long long h, unsigned
     return (owner_of(h, owners) << lp_bits) | slice;
 }
 
-// Persistent CTAs: CTA c takes tiles c, c + grid, ... and inside a tile warp w takes items w*32 + lane + 256*i, in
-// BOTH passes, so a warp's per-bucket counts of pass 1 are exactly the room it needs in pass 2: no global atomics,
-// no shared-memory atomics with a return value, deterministic layout.
+// Persistent CTAs: CTA c takes tiles c, c + grid, ... in BOTH passes, so its per-bucket counts of pass 1 are exactly
+// the room it needs in pass 2: no global atomics, no shared-memory atomics with a return value, deterministic layout.
 constexpr int WARPS = INSERT_THREADS / 32;
-constexpr int STAGE_MAX_BUCKETS = 128; // above this a warp round (256 keys) has < 2 keys per bucket: nothing to coalesce
+constexpr int STAGE_MAX_BUCKETS = 128;           // the staged pass keeps per-bucket bookkeeping in shared memory
+constexpr int ROUND_KEYS = INSERT_THREADS * SEG; // keys a CTA stages per round
 
 template <bool FIXED, bool V210>
 __global__ void __launch_bounds__(INSERT_THREADS)
-part_count_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, unsigned int *warp_hist)
+part_count_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, unsigned int *cta_hist)
 {
     __shared__ ReadTile tile;
-    extern __shared__ unsigned int s_dyn[]; // [WARPS][nb]
-    const int tid = threadIdx.x, warp = tid >> 5;
-    unsigned int *hist = s_dyn + (size_t)warp * nb;
-    for (unsigned int b = tid; b < WARPS * nb; b += INSERT_THREADS) s_dyn[b] = 0;
+    __shared__ unsigned int s_hist[MAX_BUCKETS];
+    const int tid = threadIdx.x;
+    for (unsigned int b = tid; b < MAX_BUCKETS; b += INSERT_THREADS) s_hist[b] = 0;
     const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         stage_tile<FIXED>(tile, rb.bin, rb.n_bytes, rb.offsets, rb.rec_bytes, rb.read0, rb.n_reads, k, t);
@@ -45,29 +44,28 @@ part_count_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigne
             const int cnt = item_keys<V210>(tile, item, k, key);
 #pragma unroll
             for (int j = 0; j < SEG; j++)
-                if (j < cnt) atomicAdd(&hist[bucket_of(mix64(key[j]), owners, lp_bits)], 1u); // no return value: a RED
+                if (j < cnt) atomicAdd(&s_hist[bucket_of(mix64(key[j]), owners, lp_bits)], 1u); // no return value: a RED
         }
         __syncthreads(); // the tile is overwritten by the next stage_tile
     }
     __syncthreads();
-    for (unsigned int i = tid; i < WARPS * nb; i += INSERT_THREADS)
-        warp_hist[(size_t)blockIdx.x * WARPS * nb + i] = s_dyn[i];
+    for (unsigned int b = tid; b < nb; b += INSERT_THREADS) cta_hist[(size_t)blockIdx.x * nb + b] = s_hist[b];
 }
 
-// one CTA per bucket: turn the column of per-warp counts into exclusive offsets inside the bucket
+// one CTA per bucket: turn the column of per-CTA counts into exclusive offsets inside the bucket
 __global__ void __launch_bounds__(256)
-part_offsets_kernel(unsigned int *warp_hist, int rows, unsigned int nb, unsigned long long *bucket_total)
+part_offsets_kernel(unsigned int *cta_hist, int rows, unsigned int nb, unsigned long long *bucket_total)
 {
     const unsigned int b = blockIdx.x;
     const int per = (rows + 255) / 256;
     const int c0 = min(rows, (int)threadIdx.x * per), c1 = min(rows, c0 + per);
     unsigned int sum = 0;
-    for (int c = c0; c < c1; c++) sum += warp_hist[(size_t)c * nb + b];
+    for (int c = c0; c < c1; c++) sum += cta_hist[(size_t)c * nb + b];
     unsigned long long run = block_alloc(sum, nullptr); // exclusive prefix over the threads of this CTA
     if (threadIdx.x == 255) bucket_total[b] = run + sum;
     for (int c = c0; c < c1; c++) {
-        unsigned int v = warp_hist[(size_t)c * nb + b];
-        warp_hist[(size_t)c * nb + b] = (unsigned int)run; // a bucket of one batch holds < 2^32 keys
+        unsigned int v = cta_hist[(size_t)c * nb + b];
+        cta_hist[(size_t)c * nb + b] = (unsigned int)run; // a bucket of one batch holds < 2^32 keys
         run += v;
     }
 }
@@ -88,34 +86,36 @@ part_bases_kernel(const unsigned long long *bucket_total, unsigned int nb, unsig
     }
 }
 
-// Pass 2.  A warp round = 32 items x SEG keys.  Ranks inside the round come from match.any (lanes with the same
-// bucket) plus a warp-private per-bucket counter, i.e. a warp-level multisplit.  STAGED: the round's keys are first
-// sorted by bucket in a warp-private staging area so that the global stores of consecutive lanes hit consecutive
-// addresses (a 32 B sector per 4 keys) instead of 32 different lines per store instruction.
+// Pass 2, a CTA-level multisplit.  A round = 256 items x SEG keys.  Ranks inside a warp come from match.any (lanes
+// with the same bucket) plus a warp-private per-bucket counter; a prefix over the CTA's warps and a scan over the
+// buckets give every key its place in a staging area sorted by bucket, and the round is flushed with consecutive
+// threads storing consecutive keys: runs of ROUND_KEYS / nb keys (512 B at 32 buckets) per bucket instead of 32
+// scattered 8-byte stores per warp instruction.  That is what fills NVLink write packets when PEER.
 // PEER: the position of a key is (owner, index inside the owner's segment) packed in 32 bits and the store goes to
 // the owner's inbox through its peer mapping -- the all-to-all happens inside this kernel, store by store.
 template <bool FIXED, bool V210, bool STAGED, bool PEER>
-__global__ void __launch_bounds__(INSERT_THREADS)
-part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, const unsigned int *warp_off,
+__global__ void __launch_bounds__(INSERT_THREADS, 4)
+part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, const unsigned int *cta_off,
                     const unsigned long long *bucket_base, unsigned long long *out, PeerOut peers)
 {
     __shared__ ReadTile tile;
     extern __shared__ unsigned int s_dyn[];
-    // layout: wcur [WARPS][nb] u32 | rcnt [WARPS][nb] u32 (STAGED) | sdst [WARPS][256] u32 (STAGED) | skey [WARPS][256] u64 (STAGED)
+    // layout: bcur [nb] | rcnt [WARPS][nb] | bstart [nb + 1] | sdst [ROUND_KEYS] u32 | skey [ROUND_KEYS] u64   (the last three STAGED only)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    unsigned int *wcur = s_dyn + (size_t)warp * nb;
-    unsigned int *rcnt = s_dyn + (size_t)WARPS * nb + (size_t)warp * nb;
-    unsigned int *sdst = s_dyn + 2 * (size_t)WARPS * nb + (size_t)warp * (32 * SEG);
-    unsigned long long *skey = reinterpret_cast<unsigned long long *>(s_dyn + 2 * (size_t)WARPS * nb + (size_t)WARPS * (32 * SEG)) +
-                               (size_t)warp * (32 * SEG);
-    // position of the warp's next key of bucket b, relative to out[0] (a batch holds < 2^32 keys)
-    for (unsigned int b = lane; b < nb; b += 32) {
-        unsigned int pos = (unsigned int)bucket_base[b] + warp_off[((size_t)blockIdx.x * WARPS + warp) * nb + b];
+    unsigned int *bcur = s_dyn;
+    unsigned int *rcnt = s_dyn + nb + (size_t)warp * nb;
+    unsigned int *rcnt_all = s_dyn + nb;
+    unsigned int *bstart = s_dyn + nb + (size_t)WARPS * nb;
+    unsigned int *sdst = bstart + nb + 2; // + 2: keeps skey 8-byte aligned for even nb (nb is a power of two or owners << lp)
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(sdst + ROUND_KEYS); // offset 10 nb + 2 + ROUND_KEYS words: even
+    // position of the CTA's next key of bucket b, relative to out[0] (a batch holds < 2^32 keys)
+    for (unsigned int b = tid; b < nb; b += INSERT_THREADS) {
+        unsigned int pos = (unsigned int)bucket_base[b] + cta_off[(size_t)blockIdx.x * nb + b];
         if (PEER) { // relative to the owner's segment, owner in the top bits
             const unsigned int o = b >> lp_bits;
             pos = (pos - (unsigned int)bucket_base[o << lp_bits]) | (o << P2P_REL_BITS);
         }
-        wcur[b] = pos;
+        bcur[b] = pos;
     }
     auto store = [&](unsigned int pos, unsigned long long key) {
         if (PEER) peers.base[pos >> P2P_REL_BITS][pos & ((1u << P2P_REL_BITS) - 1)] = key;
@@ -123,72 +123,82 @@ part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsig
     };
     const unsigned int lt = (1u << lane) - 1;
     const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
+    __syncthreads();
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         stage_tile<FIXED>(tile, rb.bin, rb.n_bytes, rb.offsets, rb.rec_bytes, rb.read0, rb.n_reads, k, t);
         const unsigned int total_items = tile.prefix[TILE_READS];
-        // all lanes of a warp run the same number of rounds
-        for (unsigned int item0 = warp * 32; item0 < total_items; item0 += INSERT_THREADS) {
-            const unsigned int item = item0 + lane;
+        for (unsigned int item0 = 0; item0 < total_items; item0 += INSERT_THREADS) { // uniform over the CTA
+            const unsigned int item = item0 + tid;
             unsigned long long key[SEG];
             int cnt = 0;
             if (item < total_items) cnt = item_keys<V210>(tile, item, k, key);
-            if (STAGED) {
-                for (unsigned int b = lane; b < nb; b += 32) rcnt[b] = 0;
-                __syncwarp();
-            }
+            for (unsigned int b = lane; b < nb; b += 32) rcnt[b] = 0;
+            __syncwarp();
             unsigned int bk[SEG], rk[SEG];
 #pragma unroll
             for (int j = 0; j < SEG; j++) {
                 const bool valid = j < cnt;
                 const unsigned int b = valid ? bucket_of(mix64(key[j]), owners, lp_bits) : 0xFFFFFFFFu;
-                const unsigned int peers = __match_any_sync(0xFFFFFFFFu, b);
-                const unsigned int rank = __popc(peers & lt);
-                unsigned int *ctr = STAGED ? rcnt : wcur;
-                const unsigned int base = valid ? ctr[b] : 0;
+                const unsigned int peers_mask = __match_any_sync(0xFFFFFFFFu, b);
+                const unsigned int rank = __popc(peers_mask & lt);
+                const unsigned int base = valid ? rcnt[b] : 0;
                 __syncwarp();
-                if (valid && rank == 0) ctr[b] = base + __popc(peers);
+                if (valid && rank == 0) rcnt[b] = base + __popc(peers_mask);
                 __syncwarp();
                 bk[j] = b;
-                rk[j] = base + rank;
-                if (!STAGED && valid) store(rk[j], key[j]);
+                rk[j] = base + rank; // rank among this warp's keys of bucket b in this round
             }
-            if (STAGED) {
-                // global positions from the warp cursors (read before they advance)
-                unsigned int gp[SEG];
+            __syncthreads();
+            // per bucket: exclusive prefix over the warps (in place) and the round's total
+            if (tid < (int)nb) {
+                unsigned int acc = 0;
 #pragma unroll
-                for (int j = 0; j < SEG; j++) gp[j] = j < cnt ? wcur[bk[j]] + rk[j] : 0;
-                __syncwarp();
-                // exclusive scan of the round's bucket counts -> start of each bucket's run in the staging area
-                unsigned int run = 0;
-                for (unsigned int b0 = 0; b0 < nb; b0 += 32) {
-                    const unsigned int b = b0 + lane;
-                    const unsigned int c = b < nb ? rcnt[b] : 0;
-                    unsigned int incl = c;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                        if (lane >= d) incl += v;
-                    }
-                    if (b < nb) {
-                        rcnt[b] = run + incl - c;
-                        wcur[b] += c;
-                    }
-                    run += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                for (int w = 0; w < WARPS; w++) {
+                    unsigned int v = rcnt_all[(size_t)w * nb + tid];
+                    rcnt_all[(size_t)w * nb + tid] = acc;
+                    acc += v;
                 }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < SEG; j++)
-                    if (j < cnt) {
-                        const unsigned int idx = rcnt[bk[j]] + rk[j];
-                        skey[idx] = key[j];
-                        sdst[idx] = gp[j];
-                    }
-                __syncwarp();
-                for (unsigned int idx = lane; idx < run; idx += 32) store(sdst[idx], skey[idx]);
-                __syncwarp();
+                bstart[tid] = acc; // total, turned into the start below
             }
+            __syncthreads();
+            if (warp == 0) { // exclusive scan of up to 128 totals: 4 consecutive buckets per lane
+                unsigned int v[4], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const unsigned int b = lane * 4 + q;
+                    v[q] = b < nb ? bstart[b] : 0;
+                    sum += v[q];
+                }
+                unsigned int incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    unsigned int x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += x;
+                }
+                unsigned int run = incl - sum;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const unsigned int b = lane * 4 + q;
+                    if (b < nb) bstart[b] = run;
+                    run += v[q];
+                }
+                if (lane == 31) bstart[nb] = run;
+            }
+            __syncthreads();
+            const unsigned int round_total = bstart[nb];
+#pragma unroll
+            for (int j = 0; j < SEG; j++)
+                if (j < cnt) {
+                    const unsigned int in_bucket = rcnt[bk[j]] + rk[j];
+                    const unsigned int idx = bstart[bk[j]] + in_bucket;
+                    skey[idx] = key[j];
+                    sdst[idx] = bcur[bk[j]] + in_bucket;
+                }
+            __syncthreads();
+            for (unsigned int idx = tid; idx < round_total; idx += INSERT_THREADS) store(sdst[idx], skey[idx]);
+            if (tid < (int)nb) bcur[tid] += bstart[tid + 1] - bstart[tid];
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -266,7 +276,7 @@ int PartWork::ensure(cudaStream_t st)
     if (cta_hist) return GB_OK;
     grid = SM_COUNT * 4; // persistent over the tiles; 4-5 CTAs of 256 threads fit the shared memory of an SM
     owner_stream = st;
-    GB_CUDA(cudaMalloc((void **)&cta_hist, (size_t)grid * WARPS * MAX_BUCKETS * sizeof(unsigned int)));
+    GB_CUDA(cudaMalloc((void **)&cta_hist, (size_t)grid * MAX_BUCKETS * sizeof(unsigned int)));
     GB_CUDA(cudaMalloc((void **)&bucket_base, (MAX_BUCKETS + 1) * sizeof(unsigned long long)));
     GB_CUDA(cudaMalloc((void **)&bucket_total, MAX_BUCKETS * sizeof(unsigned long long)));
     return GB_OK;
@@ -287,13 +297,12 @@ int part_count(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, Part
     const unsigned int nb = (unsigned int)pl.nb();
     if (nb > MAX_BUCKETS) { set_error("internal: %u buckets", nb); return GB_E_ARG; }
     const bool fixed = rb.offsets == nullptr;
-    const size_t smem = (size_t)WARPS * nb * sizeof(unsigned int);
-#define GB_PC(F, V) part_count_kernel<F, V><<<w.grid, INSERT_THREADS, smem, st>>>(rb, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist)
+#define GB_PC(F, V) part_count_kernel<F, V><<<w.grid, INSERT_THREADS, 0, st>>>(rb, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist)
     if (fixed) { if (v210) GB_PC(true, true); else GB_PC(true, false); }
     else { if (v210) GB_PC(false, true); else GB_PC(false, false); }
 #undef GB_PC
     GB_LAUNCHED();
-    part_offsets_kernel<<<nb, 256, 0, st>>>(w.cta_hist, w.grid * WARPS, nb, w.bucket_total);
+    part_offsets_kernel<<<nb, 256, 0, st>>>(w.cta_hist, w.grid, nb, w.bucket_total);
     GB_LAUNCHED();
     part_bases_kernel<<<1, MAX_BUCKETS, 0, st>>>(w.bucket_total, nb, w.bucket_base);
     GB_LAUNCHED();
@@ -305,8 +314,9 @@ static int launch_scatter(const ReadBatch &rb, int k, bool v210, const PartLayou
 {
     const unsigned int nb = (unsigned int)pl.nb();
     const bool fixed = rb.offsets == nullptr;
-    const bool staged = nb <= STAGE_MAX_BUCKETS && !getenv("GENOME_B200_NO_STAGING");
-    const size_t smem = staged ? (size_t)WARPS * (2 * nb * 4 + 32 * SEG * 12) : (size_t)WARPS * nb * 4;
+    if (nb > STAGE_MAX_BUCKETS) { set_error("internal: %u buckets exceed the staged bucket pass", nb); return GB_E_ARG; }
+    const bool staged = true;
+    const size_t smem = ((size_t)nb * (2 + WARPS) + 4 + ROUND_KEYS) * 4 + (size_t)ROUND_KEYS * 8;
     PeerOut po;
     memset(&po, 0, sizeof po);
     if (peers) po = *peers;

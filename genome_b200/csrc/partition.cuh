@@ -47,7 +47,7 @@ inline int slice_bits_for(int table_bits, int owners)
 {
     int lp = table_bits + 4 - SLICE_LOG2_BYTES; // 16-byte slots
     if (lp < 0) lp = 0;
-    while ((owners << lp) > MAX_BUCKETS) lp--;
+    while (lp > 0 && (owners << lp) > 128) lp--; // the staged bucket pass handles at most 128 buckets
     return lp < 0 ? 0 : lp;
 }
 
