@@ -576,6 +576,7 @@ int gb_pmap_insert_reads(gb_map *h, const uint8_t *bin, size_t n_bytes, int64_t 
 {
     Map *m;
     GB_TRY(check_pmap(h, &m));
+    ArenaScope scope(&m->arena);
     if (n_windows) *n_windows = 0;
     if (n_reads < 0 || (!bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
     if (n_reads == 0) return pmap_insert(m, nullptr, 0, nullptr, 0, 0, 0, nullptr, n_windows);
@@ -647,6 +648,7 @@ int gb_pmap_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, 
 {
     Map *m;
     GB_TRY(check_pmap(h, &m));
+    ArenaScope scope(&m->arena);
     if (n < 0 || (n > 0 && !keys)) { set_error("bad arguments"); return GB_E_ARG; }
     Comm *c = m->comm;
     const int P = c->n_ranks;
@@ -704,6 +706,7 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
 {
     Map *m;
     GB_TRY(check_pmap(h, &m));
+    ArenaScope scope(&m->arena);
     if (!out) { set_error("null out pointer"); return GB_E_ARG; }
     *out = nullptr;
     Comm *c = m->comm;

@@ -186,6 +186,91 @@ __device__ __forceinline__ bool is_secondary(const Slot *table, int bits, int k,
 }
 #endif
 
+// ---------------------------------------------------------------- transient device memory
+// Every top-level call that needs scratch space takes it from the handle's ARENA: one cudaMalloc'ed block, bump
+// allocation, reset when the next top-level call on the handle begins (every such call ends synchronised).  The
+// stream-ordered pool (cudaMallocAsync) is not used: with GB-sized blocks coming and going it remaps physical memory
+// and stalls calls for 100s of ms (measured: graph builds of 3 ms taking 20..400 ms).
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, off = 0;
+    int depth = 0;
+    void *overflow[64];
+    int n_overflow = 0;
+    size_t overflow_bytes = 0;
+    int alloc(void **p, size_t n)
+    {
+        n = (n + 255) & ~(size_t)255;
+        if (!n) n = 256;
+        if (off + n <= cap) { *p = base + off; off += n; return GB_OK; }
+        if (n_overflow == 64) { set_error("scratch arena exhausted"); return GB_E_OOM; }
+        GB_CUDA(cudaMalloc(p, n));
+        overflow[n_overflow++] = *p;
+        overflow_bytes += n;
+        return GB_OK;
+    }
+    void reset()
+    {
+        if (n_overflow) { // grow: one block large enough for what the last call needed
+            cudaDeviceSynchronize();
+            for (int i = 0; i < n_overflow; i++) cudaFree(overflow[i]);
+            if (base) cudaFree(base);
+            size_t want = cap + overflow_bytes + (cap + overflow_bytes) / 4;
+            base = nullptr;
+            cap = cudaMalloc((void **)&base, want) == cudaSuccess ? want : 0;
+            cudaGetLastError();
+            n_overflow = 0;
+            overflow_bytes = 0;
+        }
+        off = 0;
+    }
+    void destroy()
+    {
+        for (int i = 0; i < n_overflow; i++) cudaFree(overflow[i]);
+        if (base) cudaFree(base);
+        base = nullptr;
+        cap = off = overflow_bytes = 0;
+        n_overflow = 0;
+    }
+};
+extern thread_local Arena *tl_arena;
+struct ArenaScope {
+    Arena *a, *prev;
+    explicit ArenaScope(Arena *arena) : a(arena), prev(tl_arena)
+    {
+        if (a->depth++ == 0) a->reset();
+        tl_arena = a;
+    }
+    ~ArenaScope()
+    {
+        a->depth--;
+        tl_arena = prev;
+    }
+};
+
+struct DeviceBuf {
+    void *p = nullptr;
+    bool owned = false;
+    DeviceBuf() = default;
+    DeviceBuf(const DeviceBuf &) = delete;
+    DeviceBuf &operator=(const DeviceBuf &) = delete;
+    ~DeviceBuf() { release(); }
+    void release()
+    {
+        if (p && owned) cudaFree(p);
+        p = nullptr;
+    }
+    // from the current arena when a top-level call opened one, else a plain cudaMalloc
+    int alloc(size_t n, cudaStream_t = nullptr)
+    {
+        release();
+        if (tl_arena) { owned = false; return tl_arena->alloc(&p, n ? n : 16); }
+        owned = true;
+        GB_CUDA(cudaMalloc(&p, n ? n : 16));
+        return GB_OK;
+    }
+};
+
 // ---------------------------------------------------------------- host-side handle state
 struct Comm;
 
@@ -210,38 +295,15 @@ struct Map {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, t0 = nullptr, t1 = nullptr;
     // scratch
     unsigned long long *d_counters = nullptr; // [0] new keys [1] overflow count [2] flags [3] windows
+    unsigned long long *d_spread = nullptr;   // spread new-key tallies of insert_keys_kernel (partition.cu)
     unsigned long long *d_overflow = nullptr; // overflow keys (cap overflow_cap)
     int64_t overflow_cap = 0;
     Comm *comm = nullptr;
+    Arena arena;
 };
 
 int map_reserve(Map *m, int64_t want_keys);
 int check_map(gb_map *h, Map **m);
-
-struct DeviceBuf {
-    void *p = nullptr;
-    DeviceBuf() = default;
-    DeviceBuf(const DeviceBuf &) = delete;
-    DeviceBuf &operator=(const DeviceBuf &) = delete;
-    cudaStream_t s = nullptr;
-    bool pooled = false;
-    ~DeviceBuf() { release(); }
-    void release()
-    {
-        if (p) { if (pooled) cudaFreeAsync(p, s); else cudaFree(p); }
-        p = nullptr;
-    }
-    int alloc(size_t n) { release(); pooled = false; GB_CUDA(cudaMalloc(&p, n ? n : 16)); return GB_OK; }
-    // stream-ordered, from the device pool (no device-wide synchronisation)
-    int alloc(size_t n, cudaStream_t stream)
-    {
-        release();
-        pooled = true;
-        s = stream;
-        GB_CUDA(cudaMallocAsync(&p, n ? n : 16, stream));
-        return GB_OK;
-    }
-};
 
 inline unsigned int grid_for(unsigned long long n, int threads, int per_sm = 16)
 {

@@ -6,6 +6,8 @@
 // stored key (s = 0) or its reverse complement (s = 1).  The reference materialises both strands
 // (termKmers = set ++ set.map(revComplement), Graph.scala:330-333), so every sweep below runs over 2n
 // oriented vertices.  For a palindromic key (even k) the s = 1 alias does not exist.
+#include <time.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -23,6 +25,7 @@ struct Graph {
     unsigned int *edge_end = nullptr;        // [n_edges]
     unsigned long long *edge_off = nullptr;  // [n_edges + 1], in bases, ascending
     unsigned int *bases = nullptr;           // 2-bit stream, 16 bases per word, base j at bits 2(j%16) of word j/16
+    Arena arena;
     int64_t stats[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // [0] kept k-mers [1] jump rounds [2] cycle vertices dropped [3] build ns
 };
 
@@ -746,6 +749,14 @@ static int build_graph(Map *m, Graph *g)
     const unsigned long long slots = 1ull << bits;
     cudaEvent_t ev0 = m->ev0, ev1 = m->ev1;
     GB_CUDA(cudaEventRecord(ev0, st));
+    const bool trace = getenv("GENOME_B200_TRACE") != nullptr;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now_ms();
+    auto tick = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[graph] %-28s %9.3f ms\n", what, now_ms() - t_begin);
+    };
 
     // ---- dense vertex ids in slot order
     const unsigned long long tiles = (slots + TILE - 1) / TILE;
@@ -760,12 +771,14 @@ static int build_graph(Map *m, Graph *g)
     if (n >= (1ull << 30)) { set_error("%llu stored k-mers on one GPU: the graph build addresses at most 2^30", n); return GB_E_CAPACITY; }
     g->stats[0] = (int64_t)n;
 
+    tick("counted vertices");
     Tmp<unsigned long long> keys;
     GB_TRY(keys.alloc(n, st));
     assign_vertices_kernel<V210><<<(unsigned int)tiles, 256, 0, st>>>(m->table, bits, k, dual, tile_cnt.p, keys.p);
     GB_LAUNCHED();
     tile_cnt.release();
 
+    tick("assigned vertices");
     // ---- in/out masks and unique neighbours
     Tmp<uint8_t> mask8;
     Tmp<unsigned int> nbr_out, nbr_in;
@@ -776,6 +789,7 @@ static int build_graph(Map *m, Graph *g)
     BuildArrays B{ keys.p, mask8.p, nbr_out.p, nbr_in.p, n, k };
     const unsigned long long n2 = 2 * n;
 
+    tick("masks");
     // ---- nodes and edge slots
     Tmp<unsigned long long> node_idx, edge_idx;
     GB_TRY(node_idx.alloc(n2, st));
@@ -788,6 +802,7 @@ static int build_graph(Map *m, Graph *g)
     const unsigned long long N = tot[0], E = tot[1];
     if (N >= 0xFFFFFFFFull || E >= (1ull << 31)) { set_error("graph too large: %llu nodes, %llu edges", N, E); return GB_E_CAPACITY; }
 
+    tick("classified + scanned");
     GB_CUDA(cudaMalloc((void **)&g->node_kmer, (N ? N : 1) * 8));
     GB_CUDA(cudaMalloc((void **)&g->edge_start, (E ? E : 1) * 4));
     GB_CUDA(cudaMalloc((void **)&g->edge_end, (E ? E : 1) * 4));
@@ -795,6 +810,7 @@ static int build_graph(Map *m, Graph *g)
     g->n_nodes = (int64_t)N;
     g->n_edges = (int64_t)E;
 
+    tick("graph arrays allocated");
     Tmp<unsigned long long> A;
     GB_TRY(A.alloc(n2, st));
     LAUNCH(init_vertices_kernel, n2, B, node_idx.p, A.p, g->node_kmer);
@@ -802,6 +818,7 @@ static int build_graph(Map *m, Graph *g)
            g->edge_off);
     node_idx.release();
 
+    tick("vertices + edge starts");
     // ---- list ranking: rank of every interior vertex from the head of its chain + the chain's edge id
     int rounds = 0, bound = 2;
     while ((1ull << (bound - 2)) < n2 + 1) bound++; // ceil(log2) + slack; each launch makes >= 1 jump
@@ -814,6 +831,7 @@ static int build_graph(Map *m, Graph *g)
     }
     g->stats[1] = rounds;
 
+    tick("list ranking");
     // ---- edge ends and lengths, base offsets, bases
     GB_CUDA(cudaMemsetAsync(total.p + 3, 0, 8, st));
     LAUNCH(close_edges_kernel, n2, B, A.p, g->edge_end, g->edge_off, total.p + 3);
@@ -827,9 +845,11 @@ static int build_graph(Map *m, Graph *g)
     GB_TRY(read_u64(total.p, fin, 4, st));
     g->n_bases = (int64_t)fin[0];
     g->stats[2] = (int64_t)fin[3];
+    tick("edges closed + scanned");
     GB_CUDA(cudaMalloc((void **)&g->bases, base_words(g->n_bases) * 4));
     GB_CUDA(cudaMemsetAsync(g->bases, 0, base_words(g->n_bases) * 4, st));
     LAUNCH(write_bases_kernel, n2, B, A.p, edge_idx.p, g->edge_off, edge_len.p, g->bases);
+    tick("bases written");
     GB_CUDA(cudaEventRecord(ev1, st));
     GB_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
@@ -944,6 +964,7 @@ int gb_map_neighbour_masks(gb_map *h, const uint64_t *keys, int64_t n, uint8_t *
 {
     Map *m;
     GB_TRY(check_map(h, &m));
+    ArenaScope scope(&m->arena);
     if (n < 0 || (n > 0 && (!keys || !masks))) { set_error("bad arguments"); return GB_E_ARG; }
     if (n == 0) return GB_OK;
     cudaStream_t st = m->stream;
@@ -962,6 +983,7 @@ int gb_graph_build(gb_map *h, gb_graph **out)
 {
     Map *m;
     GB_TRY(check_map(h, &m));
+    ArenaScope scope(&m->arena);
     if (!out) { set_error("null out pointer"); return GB_E_ARG; }
     *out = nullptr;
     Graph *g = new Graph();
@@ -985,6 +1007,7 @@ int gb_graph_destroy(gb_graph *h)
     cudaSetDevice(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
     graph_free_arrays(g);
+    g->arena.destroy();
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
     return GB_OK;
@@ -994,6 +1017,7 @@ int gb_graph_counts(gb_graph *h, int64_t *n_nodes, int64_t *n_edges, int64_t *n_
 {
     Graph *g;
     GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
     if (n_nodes) *n_nodes = g->n_nodes;
     if (n_edges) *n_edges = g->n_edges;
     if (n_edge_bases) *n_edge_bases = g->n_bases;
@@ -1004,6 +1028,7 @@ int gb_graph_stats(gb_graph *h, int64_t stats[8])
 {
     Graph *g;
     GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
     if (!stats) { set_error("null argument"); return GB_E_ARG; }
     memcpy(stats, g->stats, sizeof g->stats);
     return GB_OK;
@@ -1014,6 +1039,7 @@ int gb_graph_export(gb_graph *h, uint64_t *node_kmers, uint32_t *edge_start, uin
 {
     Graph *g;
     GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
     cudaStream_t st = g->stream;
     const size_t N = (size_t)g->n_nodes, E = (size_t)g->n_edges;
     if (node_kmers && N) GB_CUDA(cudaMemcpyAsync(node_kmers, g->node_kmer, N * 8, cudaMemcpyDeviceToHost, st));
@@ -1030,6 +1056,7 @@ int gb_graph_components(gb_graph *h, uint32_t *node_label, int64_t *n_components
 {
     Graph *g;
     GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
     cudaStream_t st = g->stream;
     const unsigned long long N = (unsigned long long)g->n_nodes;
     if (n_components) *n_components = 0;
@@ -1057,6 +1084,7 @@ int gb_graph_retain_largest(gb_graph *h)
 {
     Graph *g;
     GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
     cudaStream_t st = g->stream;
     const unsigned long long N = (unsigned long long)g->n_nodes, E = (unsigned long long)g->n_edges;
     if (!N) return GB_OK;
@@ -1084,6 +1112,7 @@ int gb_graph_simplify(gb_graph *h)
 {
     Graph *g;
     GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
     cudaStream_t st = g->stream;
     const unsigned long long N = (unsigned long long)g->n_nodes, E = (unsigned long long)g->n_edges;
     if (!N) return GB_OK;
@@ -1118,6 +1147,7 @@ int gb_graph_remove_bubbles(gb_graph *h)
 {
     Graph *g;
     GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
     cudaStream_t st = g->stream;
     const unsigned long long N = (unsigned long long)g->n_nodes, E = (unsigned long long)g->n_edges;
     if (!E) return GB_OK;
@@ -1135,6 +1165,7 @@ int gb_graph_remove_edges(gb_graph *h, const uint32_t *edge_idx, int64_t n)
 {
     Graph *g;
     GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
     cudaStream_t st = g->stream;
     if (n < 0 || (n > 0 && !edge_idx)) { set_error("bad arguments"); return GB_E_ARG; }
     if (n == 0) return GB_OK;
@@ -1153,6 +1184,7 @@ int gb_graph_clip_tips(gb_graph *h, int64_t max_len, int64_t *removed)
 {
     Graph *g;
     GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
     cudaStream_t st = g->stream;
     const unsigned long long N = (unsigned long long)g->n_nodes, E = (unsigned long long)g->n_edges;
     if (removed) *removed = 0;
@@ -1182,6 +1214,7 @@ int gb_graph_check(gb_graph *h)
 {
     Graph *g;
     GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
     cudaStream_t st = g->stream;
     const unsigned long long N = (unsigned long long)g->n_nodes, E = (unsigned long long)g->n_edges;
     if (!E) return GB_OK;

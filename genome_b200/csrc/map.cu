@@ -32,22 +32,18 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     return e == cudaErrorMemoryAllocation ? GB_E_OOM : GB_E_CUDA;
 }
 
+thread_local Arena *tl_arena = nullptr;
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-// Device allocations are stream-ordered and come from the device's default memory pool, which is told to keep
-// freed memory: tables are re-created every FreqFilter pass (clear, rescale, filter) and must not pay cudaMalloc.
-int pool_setup(int device)
+// one-time per-device settings
+int pool_setup(int)
 {
-    cudaMemPool_t pool;
-    GB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    unsigned long long keep = ~0ull;
-    GB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     // Random 16-byte slot accesses use one 32-byte sector of a 128-byte L2 line: ask L2 not to fetch the neighbours
-    // (ncu r1a: 138 B of DRAM reads per k-mer with the default granularity).  GENOME_B200_L2_FETCH overrides.
+    // (a hint; on B200 it changes nothing measurable: ncu r1a shows 128 B per miss either way).  GENOME_B200_L2_FETCH overrides.
     size_t gran = 32;
     if (const char *e = getenv("GENOME_B200_L2_FETCH")) gran = (size_t)atoi(e);
-    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); // a hint: failure is not an error
+    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
     cudaGetLastError();
     return GB_OK;
 }
@@ -287,7 +283,8 @@ void map_retire_table(Map *m, Slot *t, int alloc_bits)
     if (!t) return;
     if (!m->spare) { m->spare = t; m->spare_bits = alloc_bits; return; }
     if (alloc_bits > m->spare_bits) { std::swap(t, m->spare); std::swap(alloc_bits, m->spare_bits); }
-    cudaFreeAsync(t, m->stream);
+    cudaStreamSynchronize(m->stream); // the retired table may still be read by a rehash on the stream
+    cudaFree(t);
 }
 
 // make an EMPTY table of 1 << new_bits slots current; the previous one is handed back (still valid on the stream:
@@ -301,7 +298,7 @@ int map_swap_table(Map *m, int new_bits, Slot **old_table, int *old_alloc_bits)
         na = m->spare_bits;
         m->spare = nullptr;
     } else {
-        GB_CUDA(cudaMallocAsync((void **)&nt, sizeof(Slot) << new_bits, m->stream));
+        GB_CUDA(cudaMalloc((void **)&nt, sizeof(Slot) << new_bits));
     }
     GB_TRY(init_table(nt, new_bits, m->stream));
     *old_table = m->table;
@@ -315,11 +312,14 @@ int map_swap_table(Map *m, int new_bits, Slot **old_table, int *old_alloc_bits)
 int map_stage(Map *m, size_t n_u64)
 {
     if (n_u64 <= m->stage_cap) return GB_OK;
-    if (m->stage) GB_CUDA(cudaFreeAsync(m->stage, m->stream));
+    if (m->stage) {
+        GB_CUDA(cudaStreamSynchronize(m->stream));
+        GB_CUDA(cudaFree(m->stage));
+    }
     m->stage = nullptr;
     m->stage_cap = 0;
     size_t want = n_u64 + n_u64 / 16 + 1024;
-    GB_CUDA(cudaMallocAsync((void **)&m->stage, want * 8, m->stream));
+    GB_CUDA(cudaMalloc((void **)&m->stage, want * 8));
     m->stage_cap = want;
     return GB_OK;
 }
@@ -668,12 +668,14 @@ int gb_map_destroy(gb_map *h)
     Map *m = reinterpret_cast<Map *>(h);
     cudaSetDevice(m->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
-    if (m->table) cudaFreeAsync(m->table, m->stream);
-    if (m->spare) cudaFreeAsync(m->spare, m->stream);
-    if (m->stage) cudaFreeAsync(m->stage, m->stream);
+    if (m->table) cudaFree(m->table);
+    if (m->spare) cudaFree(m->spare);
+    if (m->stage) cudaFree(m->stage);
+    m->arena.destroy();
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->d_counters) cudaFree(m->d_counters);
     if (m->d_overflow) cudaFree(m->d_overflow);
+    if (m->d_spread) cudaFree(m->d_spread);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     for (int i = 0; i < 4; i++)
@@ -692,6 +694,7 @@ int gb_map_insert_reads_device(gb_map *h, const uint8_t *d_bin, size_t n_bytes, 
 {
     Map *m;
     GB_TRY(check_map(h, &m));
+    ArenaScope scope(&m->arena);
     if (n_windows) *n_windows = 0;
     if (n_reads < 0 || (!d_bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
     if (n_reads == 0) return GB_OK;
@@ -717,6 +720,7 @@ int gb_map_insert_reads(gb_map *h, const uint8_t *bin, size_t n_bytes, int64_t n
 {
     Map *m;
     GB_TRY(check_map(h, &m));
+    ArenaScope scope(&m->arena);
     if (n_windows) *n_windows = 0;
     if (n_reads < 0 || (!bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
     if (n_reads == 0) return GB_OK;
@@ -763,6 +767,7 @@ static int update_common(gb_map *h, const uint64_t *keys, const int32_t *vals, i
 {
     Map *m;
     GB_TRY(check_map(h, &m));
+    ArenaScope scope(&m->arena);
     if (n < 0 || (n > 0 && (!keys || (set && !vals)))) { set_error("bad arguments"); return GB_E_ARG; }
     if (n == 0) return GB_OK;
     unsigned long long kmask = (1ull << (2 * m->k)) - 1;
@@ -808,6 +813,7 @@ int gb_map_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, u
 {
     Map *m;
     GB_TRY(check_map(h, &m));
+    ArenaScope scope(&m->arena);
     if (n < 0 || (n > 0 && !keys)) { set_error("bad arguments"); return GB_E_ARG; }
     if (n == 0) return GB_OK;
     DeviceBuf dk, dc, df;
@@ -857,6 +863,7 @@ int gb_map_export(gb_map *h, uint64_t *keys, int32_t *vals, int64_t cap, int64_t
 {
     Map *m;
     GB_TRY(check_map(h, &m));
+    ArenaScope scope(&m->arena);
     if (n_out) *n_out = m->size;
     if (!keys && !vals) return GB_OK;
     if (cap < m->size) { set_error("export buffer too small: %lld < %lld", (long long)cap, (long long)m->size); return GB_E_CAPACITY; }

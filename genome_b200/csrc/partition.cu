@@ -205,30 +205,30 @@ part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsig
 // ---------------------------------------------------------------- bulk upsert from key ranges
 constexpr int IK_THREADS = 256;
 
+constexpr int SPREAD = 256; // new-key tallies are spread over this many counters: no same-address atomic storm
+
+// No CTA barrier anywhere: every thread finds its own chunk, every warp adds its new-key count to one of SPREAD
+// global counters (fold_new_keys_kernel sums them into counters[0] afterwards).
 template <int IK_PER_THREAD>
 __global__ void __launch_bounds__(IK_THREADS)
 insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vstart,
                    const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Slot *table, int bits,
-                   unsigned long long *counters)
+                   unsigned long long *spread)
 {
-    __shared__ int s_chunk0;
-    __shared__ unsigned int s_new;
     constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
     const unsigned long long v0 = (unsigned long long)blockIdx.x * IK_PER_CTA;
-    if (threadIdx.x == 0) {
-        int lo = 0, hi = n_chunks; // last chunk with vstart <= v0
+    int c = 0;
+    if (n_chunks > 1) { // last chunk with vstart <= v0 (uniform over the CTA: served from L1)
+        int lo = 0, hi = n_chunks;
         while (hi - lo > 1) {
             int mid = (lo + hi) >> 1;
             if (vstart[mid] <= v0) lo = mid; else hi = mid;
         }
-        s_chunk0 = lo;
-        s_new = 0;
+        c = lo;
     }
-    __syncthreads();
     const unsigned long long tmask = (1ull << bits) - 1;
     unsigned long long key[IK_PER_THREAD], idx[IK_PER_THREAD], cur[IK_PER_THREAD];
     bool ok[IK_PER_THREAD];
-    int c = s_chunk0;
 #pragma unroll
     for (int j = 0; j < IK_PER_THREAD; j++) {
         unsigned long long v = v0 + (unsigned long long)j * IK_THREADS + threadIdx.x;
@@ -264,9 +264,19 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
         }
     }
     nk = __reduce_add_sync(0xFFFFFFFFu, nk);
-    if ((threadIdx.x & 31) == 0 && nk) atomicAdd(&s_new, (unsigned int)nk);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_new) atomicAdd(&counters[0], (unsigned long long)s_new);
+    if ((threadIdx.x & 31) == 0 && nk)
+        atomicAdd(&spread[(blockIdx.x * (IK_THREADS / 32) + (threadIdx.x >> 5)) & (SPREAD - 1)], (unsigned long long)nk);
+}
+
+__global__ void __launch_bounds__(SPREAD)
+fold_new_keys_kernel(unsigned long long *spread, unsigned long long *counters)
+{
+    unsigned long long v = spread[threadIdx.x];
+    spread[threadIdx.x] = 0;
+    // block-wide sum: warp reduce then one atomic per warp (8 atomics)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counters[0], v);
 }
 
 // ---------------------------------------------------------------- host side
@@ -346,13 +356,19 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
                       int n_chunks, unsigned long long n_total, cudaStream_t st)
 {
     if (!n_total) return GB_OK;
+    if (!m->d_spread) {
+        GB_CUDA(cudaMalloc((void **)&m->d_spread, SPREAD * 8));
+        GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));
+    }
     static int per = 0;
     if (!per) { const char *e = getenv("GENOME_B200_IK"); per = e ? atoi(e) : 4; }
 #define GB_IK(N)                                                                                                          \
     insert_keys_kernel<N><<<(unsigned int)((n_total + IK_THREADS * N - 1) / (IK_THREADS * N)), IK_THREADS, 0, st>>>(       \
-        d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->bits, m->d_counters)
+        d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->bits, m->d_spread)
     if (per == 8) GB_IK(8); else if (per == 16) GB_IK(16); else if (per == 2) GB_IK(2); else GB_IK(4);
 #undef GB_IK
+    GB_LAUNCHED();
+    fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
     GB_LAUNCHED();
     return GB_OK;
 }

@@ -4,11 +4,12 @@
 
 namespace gb {
 
-// stream-ordered temporary device array
+// temporary device array: from the current arena (common.cuh), else a plain cudaMalloc
 template <typename T>
 struct Tmp {
     T *p = nullptr;
     cudaStream_t s = nullptr;
+    bool owned = false;
     Tmp() = default;
     Tmp(const Tmp &) = delete;
     Tmp &operator=(const Tmp &) = delete;
@@ -17,7 +18,10 @@ struct Tmp {
     {
         release();
         s = stream;
-        GB_CUDA(cudaMallocAsync((void **)&p, (n ? n : 1) * sizeof(T), stream));
+        const size_t bytes = (n ? n : 1) * sizeof(T);
+        if (tl_arena) { owned = false; return tl_arena->alloc((void **)&p, bytes); }
+        owned = true;
+        GB_CUDA(cudaMalloc((void **)&p, bytes));
         return GB_OK;
     }
     int zero(size_t n)
@@ -32,14 +36,8 @@ struct Tmp {
     }
     void release()
     {
-        if (p) cudaFreeAsync(p, s);
+        if (p && owned) { cudaStreamSynchronize(s); cudaFree(p); }
         p = nullptr;
-    }
-    T *take()
-    {
-        T *r = p;
-        p = nullptr;
-        return r;
     }
 };
 
