@@ -28,6 +28,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # first calls must not pay lazy kernel loading (10..400 ms stalls)
 
 K = 31
 ROUNDS = 3  # GraphBuilder.scala:30

@@ -90,6 +90,9 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError("libgenome_b200.so is missing: build it with `python -m genome_b200.build` "
                                "(there is no CPU fallback)")
+        # kernels are loaded when the library is, not at their first launch (lazy loading stalls first calls by 10..400 ms);
+        # only effective if CUDA has not been initialised in this process yet
+        os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
         L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         for name, (res, args) in SIGNATURES.items():
             f = getattr(L, name)
