@@ -312,7 +312,7 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     int64_t part = ((n_reads + want_batches - 1) / want_batches + TILE_READS - 1) / TILE_READS * TILE_READS;
     if (part >= TILE_READS * 64) batch_reads = std::min(batch_reads, part);
     int64_t batches = n_reads ? (n_reads + batch_reads - 1) / batch_reads : 0;
-    int64_t lp = slice_bits_for(m->bits, P);
+    int64_t lp = slice_bits_for(m->cap, P);
     // fewer buckets = longer runs per bucket in the staged bucket pass = fuller NVLink write packets; measured at
     // P = 2: 16 slices/shard 4.1 ms, 64 slices/shard 6.0 ms per 96.6 M k-mers.  Below 8 slices the upsert leaves L2.
     while (lp > 3 && (P << lp) > 32) lp--;
@@ -426,15 +426,15 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
         GB_CUDA(cudaEventRecord(B.exchanged, c->stream));
 
         // room for the received keys (every one may be new); grow only with the pipeline drained
-        int64_t cap = (int64_t)1 << m->bits;
+        int64_t cap = (int64_t)m->cap;
         if ((int64_t)(cap * 0.9) - m->size - pending_upper < (int64_t)rt || (m->size + pending_upper) * 10 > cap * 7) {
             GB_TRY(drain(m, bufs));
             pending_upper = 0;
             int64_t budget = 0;
             GB_TRY(map_budget(m, (int64_t)rt, &budget));
             while (budget < (int64_t)rt) { // map_budget guarantees only a minimum batch: force the size we need
-                GB_TRY(map_rebuild(m, m->bits + 1, false, 0));
-                budget = (int64_t)(((int64_t)1 << m->bits) * 0.9) - m->size;
+                GB_TRY(map_rebuild(m, m->cap * 2, false, 0));
+                budget = (int64_t)(m->cap * 0.9) - m->size;
             }
         }
         GB_CUDA(cudaStreamWaitEvent(m->stream, B.exchanged, 0));

@@ -108,7 +108,17 @@ GB_HD unsigned long long mix64(unsigned long long x)
     x ^= x >> 29;
     return x;
 }
-GB_HD unsigned long long slot_of(unsigned long long h, int bits) { return h >> (64 - bits); }
+// slot = floor(h * cap / 2^64): any capacity (not only powers of two), monotonic in h, so the top bits of h still
+// select contiguous slices of the table
+GB_HD unsigned long long slot_of(unsigned long long h, unsigned long long cap)
+{
+#ifdef __CUDA_ARCH__
+    return __umul64hi(h, cap);
+#else
+    return (unsigned long long)(((unsigned __int128)h * cap) >> 64);
+#endif
+}
+GB_HD unsigned long long next_slot(unsigned long long i, unsigned long long cap) { return i + 1 == cap ? 0 : i + 1; }
 GB_HD unsigned int owner_of(unsigned long long h, unsigned int parts)
 {
     return (unsigned int)(((h & 0xFFFFFFFFull) * parts) >> 32);
@@ -134,15 +144,14 @@ __device__ __forceinline__ void red_add_s32(int *p, int v)
 }
 
 // probe for `key`; returns slot index or -1
-__device__ __forceinline__ long long probe_find(const Slot *table, int bits, unsigned long long key, Slot *out)
+__device__ __forceinline__ long long probe_find(const Slot *table, unsigned long long cap, unsigned long long key, Slot *out)
 {
-    unsigned long long mask = (1ull << bits) - 1;
-    unsigned long long i = slot_of(mix64(key), bits);
+    unsigned long long i = slot_of(mix64(key), cap);
     for (;;) { // the table is never full (map_budget), so an EMPTY slot always ends the probe
         Slot s = load_slot(table + i);
         if (s.key == key) { *out = s; return (long long)i; }
         if (s.key == EMPTY_KEY) return -1;
-        i = (i + 1) & mask;
+        i = next_slot(i, cap);
     }
 }
 
@@ -153,20 +162,20 @@ __device__ __forceinline__ long long probe_find(const Slot *table, int bits, uns
 // orientations are stored, the numerically smaller key is the PRIMARY one: it alone carries a vertex id.
 // On success *slot is the primary stored slot and *strand = 1 when that stored key is rc(q) != q.
 template <bool V210>
-__device__ __forceinline__ bool find_oriented(const Slot *table, int bits, int k, bool dual,
+__device__ __forceinline__ bool find_oriented(const Slot *table, unsigned long long cap, int k, bool dual,
                                               unsigned long long q, Slot *slot, unsigned int *strand)
 {
     unsigned long long r = revcomp(q, k);
     int hq = scala_hash<V210>(q), hr = scala_hash<V210>(r);
     if (!dual && hq != hr) {
         unsigned long long c = hq < hr ? q : r;
-        if (probe_find(table, bits, c, slot) < 0) return false;
+        if (probe_find(table, cap, c, slot) < 0) return false;
         *strand = c != q;
         return true;
     }
     Slot sq, sr;
-    bool fq = probe_find(table, bits, q, &sq) >= 0;
-    bool fr = r != q && probe_find(table, bits, r, &sr) >= 0;
+    bool fq = probe_find(table, cap, q, &sq) >= 0;
+    bool fr = r != q && probe_find(table, cap, r, &sr) >= 0;
     if (!fq && !fr) return false;
     bool use_r = fr && (!fq || r < q);
     *slot = use_r ? sr : sq;
@@ -176,13 +185,13 @@ __device__ __forceinline__ bool find_oriented(const Slot *table, int bits, int k
 
 // a stored key is SECONDARY (no vertex of its own) when rc(key) is stored too and is numerically smaller
 template <bool V210>
-__device__ __forceinline__ bool is_secondary(const Slot *table, int bits, int k, bool dual, unsigned long long key)
+__device__ __forceinline__ bool is_secondary(const Slot *table, unsigned long long cap, int k, bool dual, unsigned long long key)
 {
     unsigned long long r = revcomp(key, k);
     if (r >= key) return false;
     if (!dual && scala_hash<V210>(key) != scala_hash<V210>(r)) return false;
     Slot s;
-    return probe_find(table, bits, r, &s) >= 0;
+    return probe_find(table, cap, r, &s) >= 0;
 }
 #endif
 
@@ -191,11 +200,17 @@ __device__ __forceinline__ bool is_secondary(const Slot *table, int bits, int k,
 // allocation, reset when the next top-level call on the handle begins (every such call ends synchronised).  The
 // stream-ordered pool (cudaMallocAsync) is not used: with GB-sized blocks coming and going it remaps physical memory
 // and stalls calls for 100s of ms (measured: graph builds of 3 ms taking 20..400 ms).
+// freed arena blocks are kept (per process) and handed to the next arena that grows: handles come and go (a Graph per
+// build, a replica map per sharded build) but their scratch memory is recycled without touching the driver
+void *arena_cache_get(size_t bytes, size_t *got);
+void arena_cache_put(void *p, size_t bytes);
+
 struct Arena {
     char *base = nullptr;
     size_t cap = 0, off = 0;
     int depth = 0;
     void *overflow[64];
+    size_t overflow_size[64];
     int n_overflow = 0;
     size_t overflow_bytes = 0;
     int alloc(void **p, size_t n)
@@ -204,8 +219,14 @@ struct Arena {
         if (!n) n = 256;
         if (off + n <= cap) { *p = base + off; off += n; return GB_OK; }
         if (n_overflow == 64) { set_error("scratch arena exhausted"); return GB_E_OOM; }
-        GB_CUDA(cudaMalloc(p, n));
-        overflow[n_overflow++] = *p;
+        size_t got = 0;
+        *p = arena_cache_get(n, &got);
+        if (!*p) {
+            GB_CUDA(cudaMalloc(p, n));
+            got = n;
+        }
+        overflow[n_overflow] = *p;
+        overflow_size[n_overflow++] = got;
         overflow_bytes += n;
         return GB_OK;
     }
@@ -213,12 +234,16 @@ struct Arena {
     {
         if (n_overflow) { // grow: one block large enough for what the last call needed
             cudaDeviceSynchronize();
-            for (int i = 0; i < n_overflow; i++) cudaFree(overflow[i]);
-            if (base) cudaFree(base);
-            size_t want = cap + overflow_bytes + (cap + overflow_bytes) / 4;
-            base = nullptr;
-            cap = cudaMalloc((void **)&base, want) == cudaSuccess ? want : 0;
-            cudaGetLastError();
+            for (int i = 0; i < n_overflow; i++) arena_cache_put(overflow[i], overflow_size[i]);
+            if (base) arena_cache_put(base, cap);
+            size_t want = cap + overflow_bytes + (cap + overflow_bytes) / 4, got = 0;
+            base = (char *)arena_cache_get(want, &got);
+            if (base) cap = got;
+            else {
+                cap = cudaMalloc((void **)&base, want) == cudaSuccess ? want : 0;
+                if (!cap) base = nullptr;
+                cudaGetLastError();
+            }
             n_overflow = 0;
             overflow_bytes = 0;
         }
@@ -226,8 +251,8 @@ struct Arena {
     }
     void destroy()
     {
-        for (int i = 0; i < n_overflow; i++) cudaFree(overflow[i]);
-        if (base) cudaFree(base);
+        for (int i = 0; i < n_overflow; i++) arena_cache_put(overflow[i], overflow_size[i]);
+        if (base) arena_cache_put(base, cap);
         base = nullptr;
         cap = off = overflow_bytes = 0;
         n_overflow = 0;
@@ -279,11 +304,11 @@ struct Map {
     int device = 0;
     bool v210 = false;
     bool noncanonical = false; // keys were inserted through update/update_counts as-is
-    int bits = 0;              // capacity = 1 << bits
+    unsigned long long cap = 0; // capacity in slots (any multiple of 1024)
     Slot *table = nullptr;
-    int alloc_bits = 0;        // the allocation behind `table` holds 1 << alloc_bits slots (>= bits)
+    unsigned long long alloc_cap = 0; // the allocation behind `table` holds this many slots (>= cap)
     Slot *spare = nullptr;     // the other table allocation of the clear / filter cycle, kept for reuse
-    int spare_bits = 0;
+    unsigned long long spare_cap = 0;
     unsigned long long *stage = nullptr; // key staging of the partitioned insert and of the filter (grow-only)
     size_t stage_cap = 0;
     int64_t size = 0;          // live keys (host mirror, exact after every call)
@@ -312,16 +337,16 @@ inline unsigned int grid_for(unsigned long long n, int threads, int per_sm = 16)
     if (g > cap) g = cap;
     return (unsigned int)(g ? g : 1);
 }
-int map_swap_table(Map *m, int new_bits, Slot **old_table, int *old_alloc_bits);
-void map_retire_table(Map *m, Slot *t, int alloc_bits);
+int map_swap_table(Map *m, unsigned long long new_cap, Slot **old_table, unsigned long long *old_alloc_cap);
+void map_retire_table(Map *m, Slot *t, unsigned long long alloc_cap);
 int map_stage(Map *m, size_t n_u64);
 int pool_setup(int device);
-inline int bits_for(int64_t keys)
+inline unsigned long long cap_for(int64_t keys)
 {
-    // smallest power of two with load <= 0.5, at least 2^10 slots
-    int b = 10;
-    while (((int64_t)1 << b) < keys * 2) b++;
-    return b;
+    // load <= 1/3 at `keys`, a multiple of 1024 slots, at least 1024
+    // measured on C2: load 0.22 -> 0.37 costs 10% in the upsert and 60% in the graph build's membership probes
+    unsigned long long c = ((unsigned long long)(keys > 0 ? keys : 0) * 3 + 1023) / 1024 * 1024;
+    return c < 1024 ? 1024 : c;
 }
 
 } // namespace gb

@@ -141,7 +141,7 @@ __device__ __forceinline__ unsigned long long load_key(const Slot *p)
 // update(key, 1, _ + 1) (S/ds/ArrayDNAMap.scala:129-150) starting at slot idx whose key was already loaded
 // into `cur`.  The caller guarantees the table never fills (map_budget), so the probe always terminates.
 // Returns 1 when the key was new.
-__device__ __forceinline__ int upsert_add(Slot *table, unsigned long long mask, unsigned long long idx,
+__device__ __forceinline__ int upsert_add(Slot *table, unsigned long long cap, unsigned long long idx,
                                           unsigned long long cur, unsigned long long key, int add)
 {
     for (;;) {
@@ -156,7 +156,7 @@ __device__ __forceinline__ int upsert_add(Slot *table, unsigned long long mask, 
                 return old == EMPTY_KEY;
             }
         }
-        idx = (idx + 1) & mask;
+        idx = next_slot(idx, cap);
         cur = load_key(table + idx);
     }
 }
@@ -166,7 +166,7 @@ __device__ __forceinline__ int upsert_add(Slot *table, unsigned long long mask, 
 int map_budget(Map *m, int64_t incoming, int64_t *budget);
 int map_read_counters(Map *m, unsigned long long out[4]);
 int map_zero_counters(Map *m);
-int map_rebuild(Map *m, int new_bits, bool filter, int min_count);
+int map_rebuild(Map *m, unsigned long long new_cap, bool filter, int min_count);
 int map_export_device(Map *m, unsigned long long *d_keys, int *d_vals);
 int map_verify_fixed(Map *m, const uint8_t *d_bin, unsigned int rec, unsigned int len0, int64_t n_reads, unsigned long long *bad);
 int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n, cudaStream_t st);

@@ -25,7 +25,9 @@ struct Graph {
     unsigned int *edge_end = nullptr;        // [n_edges]
     unsigned long long *edge_off = nullptr;  // [n_edges + 1], in bases, ascending
     unsigned int *bases = nullptr;           // 2-bit stream, 16 bases per word, base j at bits 2(j%16) of word j/16
-    Arena arena;
+    Arena arena;    // scratch of the operators
+    Arena store[2]; // the arrays above live in store[cur]; a rewrite builds the new ones in store[cur ^ 1]
+    int cur = 0;
     int64_t stats[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // [0] kept k-mers [1] jump rounds [2] cycle vertices dropped [3] build ns
 };
 
@@ -80,21 +82,21 @@ __device__ __forceinline__ unsigned long long oriented_kmer(unsigned long long k
 constexpr int TILE = 1024; // slots per CTA tile in the compaction passes (256 threads x 4)
 
 template <bool V210>
-__device__ __forceinline__ bool slot_is_vertex(const Slot *table, int bits, int k, bool dual, const Slot &s)
+__device__ __forceinline__ bool slot_is_vertex(const Slot *table, unsigned long long cap, int k, bool dual, const Slot &s)
 {
-    return s.key != EMPTY_KEY && !is_secondary<V210>(table, bits, k, dual, s.key);
+    return s.key != EMPTY_KEY && !is_secondary<V210>(table, cap, k, dual, s.key);
 }
 
 template <bool V210>
 __global__ void __launch_bounds__(256)
-count_vertices_kernel(const Slot *table, int bits, int k, bool dual, unsigned long long *tile_count)
+count_vertices_kernel(const Slot *table, unsigned long long cap, int k, bool dual, unsigned long long *tile_count)
 {
-    const unsigned long long n = 1ull << bits;
+    const unsigned long long n = cap;
     unsigned int c = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         unsigned long long i = (unsigned long long)blockIdx.x * TILE + j * 256 + threadIdx.x;
-        if (i < n) c += slot_is_vertex<V210>(table, bits, k, dual, load_slot(table + i));
+        if (i < n) c += slot_is_vertex<V210>(table, cap, k, dual, load_slot(table + i));
     }
     unsigned long long base = block_alloc(c, nullptr); // exclusive prefix inside the CTA, no counter
     __shared__ unsigned int s_total;
@@ -106,10 +108,10 @@ count_vertices_kernel(const Slot *table, int bits, int k, bool dual, unsigned lo
 // assigns vid in slot order (deterministic), writes keys[vid] and the slot's vid field
 template <bool V210>
 __global__ void __launch_bounds__(256)
-assign_vertices_kernel(Slot *table, int bits, int k, bool dual, const unsigned long long *tile_base,
+assign_vertices_kernel(Slot *table, unsigned long long cap, int k, bool dual, const unsigned long long *tile_base,
                        unsigned long long *keys)
 {
-    const unsigned long long n = 1ull << bits;
+    const unsigned long long n = cap;
     // thread t owns 4 CONSECUTIVE slots so that vids follow slot order
     unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * 4;
     Slot s[4];
@@ -120,7 +122,7 @@ assign_vertices_kernel(Slot *table, int bits, int k, bool dual, const unsigned l
         live[j] = false;
         if (i0 + j < n) {
             s[j] = load_slot(table + i0 + j);
-            live[j] = slot_is_vertex<V210>(table, bits, k, dual, s[j]);
+            live[j] = slot_is_vertex<V210>(table, cap, k, dual, s[j]);
         }
         c += live[j];
     }
@@ -138,7 +140,7 @@ assign_vertices_kernel(Slot *table, int bits, int k, bool dual, const unsigned l
 // mask8 = out | in << 4; nbr_out / nbr_in = the oriented neighbour when there is exactly one.
 template <bool V210>
 __global__ void __launch_bounds__(256)
-masks_kernel(const Slot *table, int bits, int k, bool dual, const unsigned long long *keys, unsigned long long n,
+masks_kernel(const Slot *table, unsigned long long cap, int k, bool dual, const unsigned long long *keys, unsigned long long n,
              uint8_t *mask8, unsigned int *nbr_out, unsigned int *nbr_in)
 {
     unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,11 +151,11 @@ masks_kernel(const Slot *table, int bits, int k, bool dual, const unsigned long 
     for (unsigned int b = 0; b < 4; b++) {
         Slot s;
         unsigned int strand;
-        if (find_oriented<V210>(table, bits, k, dual, kmer_append(x, k, b), &s, &strand)) {
+        if (find_oriented<V210>(table, cap, k, dual, kmer_append(x, k, b), &s, &strand)) {
             out |= 1u << b;
             so = 2 * s.vid + strand;
         }
-        if (find_oriented<V210>(table, bits, k, dual, kmer_prepend(x, k, b), &s, &strand)) {
+        if (find_oriented<V210>(table, cap, k, dual, kmer_prepend(x, k, b), &s, &strand)) {
             in |= 1u << b;
             si = 2 * s.vid + strand;
         }
@@ -165,7 +167,7 @@ masks_kernel(const Slot *table, int bits, int k, bool dual, const unsigned long 
 
 // gb_map_neighbour_masks: the same probes for arbitrary query k-mers
 template <bool V210>
-__global__ void query_masks_kernel(const Slot *table, int bits, int k, bool dual, const unsigned long long *q,
+__global__ void query_masks_kernel(const Slot *table, unsigned long long cap, int k, bool dual, const unsigned long long *q,
                                    long long n, uint8_t *masks)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,8 +178,8 @@ __global__ void query_masks_kernel(const Slot *table, int bits, int k, bool dual
     for (unsigned int b = 0; b < 4; b++) {
         Slot s;
         unsigned int strand;
-        if (find_oriented<V210>(table, bits, k, dual, kmer_append(x, k, b), &s, &strand)) out |= 1u << b;
-        if (find_oriented<V210>(table, bits, k, dual, kmer_prepend(x, k, b), &s, &strand)) in |= 1u << b;
+        if (find_oriented<V210>(table, cap, k, dual, kmer_append(x, k, b), &s, &strand)) out |= 1u << b;
+        if (find_oriented<V210>(table, cap, k, dual, kmer_prepend(x, k, b), &s, &strand)) in |= 1u << b;
     }
     masks[i] = (uint8_t)(out | (in << 4));
 }
@@ -252,7 +254,7 @@ __global__ void init_vertices_kernel(BuildArrays B, const unsigned long long *no
 // buildEdges (Graph.scala:349-365), first step of every edge: one thread per oriented vertex that is a node.
 // Edge ids follow (node index, base) order; out-bases are visited in Base.fromInt order (351).
 template <bool V210>
-__global__ void start_edges_kernel(BuildArrays B, const Slot *table, int bits, bool dual,
+__global__ void start_edges_kernel(BuildArrays B, const Slot *table, unsigned long long cap, bool dual,
                                    const unsigned long long *node_idx, const unsigned long long *edge_idx,
                                    unsigned long long *A, unsigned int *edge_start, unsigned int *edge_end,
                                    unsigned long long *edge_len)
@@ -268,7 +270,7 @@ __global__ void start_edges_kernel(BuildArrays B, const Slot *table, int bits, b
         if (!(out & (1u << b))) continue;
         Slot s;
         unsigned int strand = 0;
-        find_oriented<V210>(table, bits, B.k, dual, kmer_append(x, B.k, b), &s, &strand); // present by construction
+        find_oriented<V210>(table, cap, B.k, dual, kmer_append(x, B.k, b), &s, &strand); // present by construction
         unsigned int w = normalise(B, 2 * s.vid + strand), wo, wi;
         edge_start[e] = me;
         if (vertex_type(B, w, &wo, &wi) == TAG_TERM) {
@@ -716,12 +718,13 @@ static int check_graph(gb_graph *h, Graph **g)
 
 static void graph_free_arrays(Graph *g)
 {
-    if (g->node_kmer) cudaFree(g->node_kmer);
-    if (g->edge_start) cudaFree(g->edge_start);
-    if (g->edge_end) cudaFree(g->edge_end);
-    if (g->edge_off) cudaFree(g->edge_off);
-    if (g->bases) cudaFree(g->bases);
     g->node_kmer = nullptr; g->edge_start = g->edge_end = nullptr; g->edge_off = nullptr; g->bases = nullptr;
+}
+// graph arrays come from a store arena (no cudaMalloc in the steady state)
+template <typename T>
+static int store_alloc(Arena &a, T **p, size_t n)
+{
+    return a.alloc((void **)p, (n ? n : 1) * sizeof(T));
 }
 
 #define LAUNCH(kernel, n, ...)                                                                        \
@@ -744,9 +747,10 @@ template <bool V210>
 static int build_graph(Map *m, Graph *g)
 {
     cudaStream_t st = m->stream;
-    const int k = m->k, bits = m->bits;
+    const int k = m->k;
+    const unsigned long long bits = m->cap; // table capacity in slots (passed to the kernels as `cap`)
     const bool dual = m->noncanonical;
-    const unsigned long long slots = 1ull << bits;
+    const unsigned long long slots = bits;
     cudaEvent_t ev0 = m->ev0, ev1 = m->ev1;
     GB_CUDA(cudaEventRecord(ev0, st));
     const bool trace = getenv("GENOME_B200_TRACE") != nullptr;
@@ -803,10 +807,12 @@ static int build_graph(Map *m, Graph *g)
     if (N >= 0xFFFFFFFFull || E >= (1ull << 31)) { set_error("graph too large: %llu nodes, %llu edges", N, E); return GB_E_CAPACITY; }
 
     tick("classified + scanned");
-    GB_CUDA(cudaMalloc((void **)&g->node_kmer, (N ? N : 1) * 8));
-    GB_CUDA(cudaMalloc((void **)&g->edge_start, (E ? E : 1) * 4));
-    GB_CUDA(cudaMalloc((void **)&g->edge_end, (E ? E : 1) * 4));
-    GB_CUDA(cudaMalloc((void **)&g->edge_off, (E + 1) * 8));
+    g->cur = 0;
+    g->store[0].reset();
+    GB_TRY(store_alloc(g->store[0], &g->node_kmer, N));
+    GB_TRY(store_alloc(g->store[0], &g->edge_start, E));
+    GB_TRY(store_alloc(g->store[0], &g->edge_end, E));
+    GB_TRY(store_alloc(g->store[0], &g->edge_off, E + 1));
     g->n_nodes = (int64_t)N;
     g->n_edges = (int64_t)E;
 
@@ -846,7 +852,7 @@ static int build_graph(Map *m, Graph *g)
     g->n_bases = (int64_t)fin[0];
     g->stats[2] = (int64_t)fin[3];
     tick("edges closed + scanned");
-    GB_CUDA(cudaMalloc((void **)&g->bases, base_words(g->n_bases) * 4));
+    GB_TRY(store_alloc(g->store[0], &g->bases, base_words(g->n_bases)));
     GB_CUDA(cudaMemsetAsync(g->bases, 0, base_words(g->n_bases) * 4, st));
     LAUNCH(write_bases_kernel, n2, B, A.p, edge_idx.p, g->edge_off, edge_len.p, g->bases);
     tick("bases written");
@@ -875,11 +881,13 @@ static int apply_rewrite(Graph *g, Rewrite &rw)
     GB_TRY(read_u64(total.p, tot, 2, st));
     const unsigned long long N2 = tot[0], E2 = tot[1];
 
-    Graph ng;
-    GB_CUDA(cudaMalloc((void **)&ng.node_kmer, (N2 ? N2 : 1) * 8));
-    GB_CUDA(cudaMalloc((void **)&ng.edge_start, (E2 ? E2 : 1) * 4));
-    GB_CUDA(cudaMalloc((void **)&ng.edge_end, (E2 ? E2 : 1) * 4));
-    GB_CUDA(cudaMalloc((void **)&ng.edge_off, (E2 + 1) * 8));
+    struct { unsigned long long *node_kmer; unsigned int *edge_start, *edge_end; unsigned long long *edge_off; unsigned int *bases; } ng;
+    Arena &dst = g->store[g->cur ^ 1];
+    dst.reset();
+    GB_TRY(store_alloc(dst, &ng.node_kmer, N2));
+    GB_TRY(store_alloc(dst, &ng.edge_start, E2));
+    GB_TRY(store_alloc(dst, &ng.edge_end, E2));
+    GB_TRY(store_alloc(dst, &ng.edge_off, E2 + 1));
     GB_CUDA(cudaMemsetAsync(ng.edge_off, 0, (E2 + 1) * 8, st));
     LAUNCH(rw_nodes_kernel, N, rw.node_keep, new_node.p, g->node_kmer, N, ng.node_kmer);
     LAUNCH(rw_edges_kernel, E, rw.head, rw.dist, rw.tail, new_edge.p, new_node.p, g->edge_start, g->edge_end, g->edge_off, E,
@@ -887,12 +895,12 @@ static int apply_rewrite(Graph *g, Rewrite &rw)
     GB_TRY(exclusive_scan_u64(ng.edge_off, E2 + 1, total.p + 2, st));
     unsigned long long nb = 0;
     GB_TRY(read_u64(total.p + 2, &nb, 1, st));
-    GB_CUDA(cudaMalloc((void **)&ng.bases, base_words((int64_t)nb) * 4));
+    GB_TRY(store_alloc(dst, &ng.bases, base_words((int64_t)nb)));
     GB_CUDA(cudaMemsetAsync(ng.bases, 0, base_words((int64_t)nb) * 4, st));
     LAUNCH(rw_bases_kernel, (g->n_bases + 15) / 16, g->bases, (unsigned long long)g->n_bases, g->edge_off, E, rw.head, rw.dist,
            new_edge.p, ng.edge_off, ng.bases);
     GB_CUDA(cudaStreamSynchronize(st));
-    graph_free_arrays(g);
+    g->cur ^= 1;
     g->node_kmer = ng.node_kmer; g->edge_start = ng.edge_start; g->edge_end = ng.edge_end;
     g->edge_off = ng.edge_off; g->bases = ng.bases;
     g->n_nodes = (int64_t)N2; g->n_edges = (int64_t)E2; g->n_bases = (int64_t)nb;
@@ -972,8 +980,8 @@ int gb_map_neighbour_masks(gb_map *h, const uint64_t *keys, int64_t n, uint8_t *
     GB_TRY(dk.alloc((size_t)n * 8));
     GB_TRY(dm.alloc((size_t)n));
     GB_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    if (m->v210) LAUNCH(query_masks_kernel<true>, n, m->table, m->bits, m->k, m->noncanonical, (const unsigned long long *)dk.p, n, (uint8_t *)dm.p);
-    else LAUNCH(query_masks_kernel<false>, n, m->table, m->bits, m->k, m->noncanonical, (const unsigned long long *)dk.p, n, (uint8_t *)dm.p);
+    if (m->v210) LAUNCH(query_masks_kernel<true>, n, m->table, m->cap, m->k, m->noncanonical, (const unsigned long long *)dk.p, n, (uint8_t *)dm.p);
+    else LAUNCH(query_masks_kernel<false>, n, m->table, m->cap, m->k, m->noncanonical, (const unsigned long long *)dk.p, n, (uint8_t *)dm.p);
     GB_CUDA(cudaMemcpyAsync(masks, dm.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));
     return GB_OK;
@@ -1008,6 +1016,8 @@ int gb_graph_destroy(gb_graph *h)
     if (g->stream) cudaStreamSynchronize(g->stream);
     graph_free_arrays(g);
     g->arena.destroy();
+    g->store[0].destroy();
+    g->store[1].destroy();
     if (g->stream) cudaStreamDestroy(g->stream);
     delete g;
     return GB_OK;

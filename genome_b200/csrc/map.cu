@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -33,6 +34,49 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 }
 
 thread_local Arena *tl_arena = nullptr;
+
+// ---- arena block cache (see common.cuh): at most CACHE_SLOTS blocks, best fit, per device
+namespace {
+struct CachedBlock { void *p; size_t bytes; int device; };
+constexpr int CACHE_SLOTS = 16;
+CachedBlock g_cache[CACHE_SLOTS];
+int g_cache_n = 0;
+std::mutex g_cache_mu;
+}
+void *arena_cache_get(size_t bytes, size_t *got)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    int best = -1;
+    for (int i = 0; i < g_cache_n; i++)
+        if (g_cache[i].device == dev && g_cache[i].bytes >= bytes && (best < 0 || g_cache[i].bytes < g_cache[best].bytes)) best = i;
+    if (best < 0 || g_cache[best].bytes > 4 * bytes + (64u << 20)) return nullptr; // do not burn a huge block on a small request
+    void *p = g_cache[best].p;
+    *got = g_cache[best].bytes;
+    g_cache[best] = g_cache[--g_cache_n];
+    return p;
+}
+void arena_cache_put(void *p, size_t bytes)
+{
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    void *victim = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_mu);
+        if (g_cache_n < CACHE_SLOTS) {
+            g_cache[g_cache_n++] = { p, bytes, dev };
+        } else { // evict the smallest block
+            int small = 0;
+            for (int i = 1; i < g_cache_n; i++)
+                if (g_cache[i].bytes < g_cache[small].bytes) small = i;
+            if (g_cache[small].bytes < bytes) { victim = g_cache[small].p; g_cache[small] = { p, bytes, dev }; }
+            else victim = p;
+        }
+    }
+    if (victim) cudaFree(victim);
+}
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
@@ -65,7 +109,7 @@ template <bool FIXED, bool V210>
 __global__ void __launch_bounds__(INSERT_THREADS)
 insert_reads_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes,
                     const unsigned long long *__restrict__ offsets, unsigned int rec_bytes,
-                    long long read0, long long n_reads, int k, Slot *table, int bits,
+                    long long read0, long long n_reads, int k, Slot *table, unsigned long long cap,
                     unsigned long long *counters)
 {
     __shared__ ReadTile tile;
@@ -76,20 +120,19 @@ insert_reads_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes,
     if (tid == 0) s_newkeys = 0;
 
     const unsigned int total_items = tile.prefix[TILE_READS];
-    const unsigned long long tmask = (1ull << bits) - 1;
     int newkeys = 0;
 
     for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
         unsigned long long key[SEG], idx[SEG], cur[SEG];
         const int cnt = item_keys<V210>(tile, item, k, key);
 #pragma unroll
-        for (int j = 0; j < SEG; j++) idx[j] = slot_of(mix64(key[j]), bits);
+        for (int j = 0; j < SEG; j++) idx[j] = slot_of(mix64(key[j]), cap);
 #pragma unroll
         for (int j = 0; j < SEG; j++)
             if (j < cnt) cur[j] = load_key(table + idx[j]);
 #pragma unroll
         for (int j = 0; j < SEG; j++)
-            if (j < cnt) newkeys += upsert_add(table, tmask, idx[j], cur[j], key[j], 1);
+            if (j < cnt) newkeys += upsert_add(table, cap, idx[j], cur[j], key[j], 1);
     }
 
     // one global atomic per CTA for the size counter
@@ -137,16 +180,15 @@ __global__ void verify_fixed_kernel(const uint8_t *__restrict__ bin, unsigned in
 // update(key, 1, _ + 1) / update(key, v) for explicit keys
 template <bool SET>
 __global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ vals,
-                                   long long n, Slot *table, int bits, unsigned long long *counters)
+                                   long long n, Slot *table, unsigned long long cap, unsigned long long *counters)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned long long mask = (1ull << bits) - 1;
     int nk = 0;
     if (i < n) {
         unsigned long long key = keys[i];
-        unsigned long long idx = slot_of(mix64(key), bits);
+        unsigned long long idx = slot_of(mix64(key), cap);
         if (!SET) {
-            nk = upsert_add(table, mask, idx, load_key(table + idx), key, 1);
+            nk = upsert_add(table, cap, idx, load_key(table + idx), key, 1);
         } else {
             for (;;) {
                 unsigned long long cur = load_key(table + idx);
@@ -155,7 +197,7 @@ __global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, 
                     if (cur == EMPTY_KEY) { nk = 1; cur = key; }
                 }
                 if (cur == key) { atomicExch(&table[idx].count, vals[i]); break; }
-                idx = (idx + 1) & mask;
+                idx = next_slot(idx, cap);
             }
         }
     }
@@ -163,13 +205,13 @@ __global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, 
     if ((threadIdx.x & 31) == 0 && nk) atomicAdd(&counters[0], (unsigned long long)nk);
 }
 
-__global__ void lookup_kernel(const unsigned long long *__restrict__ keys, long long n, const Slot *table, int bits,
+__global__ void lookup_kernel(const unsigned long long *__restrict__ keys, long long n, const Slot *table, unsigned long long cap,
                               int *counts, uint8_t *found)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Slot s;
-    bool f = probe_find(table, bits, keys[i], &s) >= 0;
+    bool f = probe_find(table, cap, keys[i], &s) >= 0;
     if (counts) counts[i] = f ? s.count : 0;
     if (found) found[i] = f;
 }
@@ -206,22 +248,21 @@ compact_survivors_kernel(const Slot *table, unsigned long long n, int min_count,
 }
 
 __global__ void rehash_kernel(const Slot *old_table, unsigned long long n, int min_count, bool filter,
-                              Slot *new_table, int new_bits)
+                              Slot *new_table, unsigned long long new_cap)
 {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long mask = (1ull << new_bits) - 1;
     for (; i < n; i += stride) {
         Slot s = load_slot(old_table + i);
         if (s.key == EMPTY_KEY || (filter && s.count < min_count)) continue;
-        unsigned long long idx = slot_of(mix64(s.key), new_bits);
+        unsigned long long idx = slot_of(mix64(s.key), new_cap);
         for (;;) {
             unsigned long long cur = load_key(new_table + idx);
             if (cur == EMPTY_KEY && atomicCAS(&new_table[idx].key, EMPTY_KEY, s.key) == EMPTY_KEY) {
                 new_table[idx].count = s.count;
                 break;
             }
-            idx = (idx + 1) & mask;
+            idx = next_slot(idx, new_cap);
         }
     }
 }
@@ -270,42 +311,41 @@ namespace gb {
 // Table memory.  A FreqFilter pass cycles between a large table (counting) and a small one (after deleteAll), and
 // the next pass starts again with a large one: the map keeps both allocations (`table` and `spare`) and swaps them,
 // so that the steady state allocates nothing.  Everything happens in stream order on m->stream.
-static int init_table(Slot *t, int bits, cudaStream_t s)
+static int init_table(Slot *t, unsigned long long n, cudaStream_t s)
 {
-    unsigned long long n = 1ull << bits;
     init_table_kernel<<<grid_for(n, 256, 32), 256, 0, s>>>(t, n);
     GB_LAUNCHED();
     return GB_OK;
 }
 
-void map_retire_table(Map *m, Slot *t, int alloc_bits)
+void map_retire_table(Map *m, Slot *t, unsigned long long alloc_cap)
 {
     if (!t) return;
-    if (!m->spare) { m->spare = t; m->spare_bits = alloc_bits; return; }
-    if (alloc_bits > m->spare_bits) { std::swap(t, m->spare); std::swap(alloc_bits, m->spare_bits); }
+    if (!m->spare) { m->spare = t; m->spare_cap = alloc_cap; return; }
+    if (alloc_cap > m->spare_cap) { std::swap(t, m->spare); std::swap(alloc_cap, m->spare_cap); }
     cudaStreamSynchronize(m->stream); // the retired table may still be read by a rehash on the stream
     cudaFree(t);
 }
 
-// make an EMPTY table of 1 << new_bits slots current; the previous one is handed back (still valid on the stream:
+// make an EMPTY table of new_cap slots current; the previous one is handed back (still valid on the stream:
 // the caller rehashes out of it and then retires it)
-int map_swap_table(Map *m, int new_bits, Slot **old_table, int *old_alloc_bits)
+int map_swap_table(Map *m, unsigned long long new_cap, Slot **old_table, unsigned long long *old_alloc_cap)
 {
     Slot *nt = nullptr;
-    int na = new_bits;
-    if (m->spare && m->spare_bits >= new_bits) {
+    unsigned long long na = new_cap;
+    if (m->spare && m->spare_cap >= new_cap) {
         nt = m->spare;
-        na = m->spare_bits;
+        na = m->spare_cap;
         m->spare = nullptr;
     } else {
-        GB_CUDA(cudaMalloc((void **)&nt, sizeof(Slot) << new_bits));
+        GB_CUDA(cudaMalloc((void **)&nt, sizeof(Slot) * new_cap));
     }
-    GB_TRY(init_table(nt, new_bits, m->stream));
+    GB_TRY(init_table(nt, new_cap, m->stream));
     *old_table = m->table;
-    *old_alloc_bits = m->alloc_bits;
+    *old_alloc_cap = m->alloc_cap;
     m->table = nt;
-    m->alloc_bits = na;
-    m->bits = new_bits;
+    m->alloc_cap = na;
+    m->cap = new_cap;
     return GB_OK;
 }
 
@@ -324,15 +364,14 @@ int map_stage(Map *m, size_t n_u64)
     return GB_OK;
 }
 
-// rehash into a table of new_bits (optionally dropping counts below min_count)
-int map_rebuild(Map *m, int new_bits, bool filter, int min_count)
+// rehash into a table of new_cap slots (optionally dropping counts below min_count)
+int map_rebuild(Map *m, unsigned long long new_cap, bool filter, int min_count)
 {
     Slot *old = nullptr;
-    int old_alloc = 0;
-    const int old_bits = m->bits;
-    GB_TRY(map_swap_table(m, new_bits, &old, &old_alloc));
-    unsigned long long n = 1ull << old_bits;
-    rehash_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(old, n, min_count, filter, m->table, new_bits);
+    unsigned long long old_alloc = 0;
+    const unsigned long long n = m->cap;
+    GB_TRY(map_swap_table(m, new_cap, &old, &old_alloc));
+    rehash_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(old, n, min_count, filter, m->table, new_cap);
     GB_LAUNCHED();
     map_retire_table(m, old, old_alloc);
     m->grows++;
@@ -344,14 +383,14 @@ int map_rebuild(Map *m, int new_bits, bool filter, int min_count)
 // be issued before the next reserve through *budget.
 int map_budget(Map *m, int64_t incoming, int64_t *budget)
 {
-    int64_t cap = (int64_t)1 << m->bits;
+    int64_t cap = (int64_t)m->cap;
     int64_t room = (int64_t)(cap * 0.9) - m->size;
     int64_t min_batch = std::min<int64_t>(incoming, (int64_t)TILE_READS * 256);
     if (m->size * 10 > cap * 7 || room < min_batch) {
-        int nb = bits_for(std::max<int64_t>(m->size, 1) * 2);
-        while ((int64_t)(((int64_t)1 << nb) * 0.9) - m->size < min_batch) nb++;
-        if (nb > m->bits) GB_TRY(map_rebuild(m, nb, false, 0));
-        cap = (int64_t)1 << m->bits;
+        unsigned long long nc = cap_for(std::max<int64_t>(m->size, 1) * 2);
+        while ((int64_t)(nc * 0.9) - m->size < min_batch) nc *= 2;
+        if (nc > m->cap) GB_TRY(map_rebuild(m, nc, false, 0));
+        cap = (int64_t)m->cap;
         room = (int64_t)(cap * 0.9) - m->size;
     }
     *budget = room;
@@ -361,7 +400,7 @@ int map_budget(Map *m, int64_t incoming, int64_t *budget)
 int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n, cudaStream_t st)
 {
     if (n <= 0) return GB_OK;
-    update_keys_kernel<false><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, nullptr, n, m->table, m->bits, m->d_counters);
+    update_keys_kernel<false><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, nullptr, n, m->table, m->cap, m->d_counters);
     GB_LAUNCHED();
     return GB_OK;
 }
@@ -369,15 +408,15 @@ int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n
 int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d_vals, int64_t n, cudaStream_t st)
 {
     if (n <= 0) return GB_OK;
-    update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->bits, m->d_counters);
+    update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, m->d_counters);
     GB_LAUNCHED();
     return GB_OK;
 }
 
 int map_reserve(Map *m, int64_t want_keys)
 {
-    int nb = bits_for(want_keys);
-    if (nb > m->bits) return map_rebuild(m, nb, false, 0);
+    unsigned long long nc = cap_for(want_keys);
+    if (nc > m->cap) return map_rebuild(m, nc, false, 0);
     return GB_OK;
 }
 
@@ -402,10 +441,10 @@ static int launch_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
     unsigned int grid = (unsigned int)((n_reads + TILE_READS - 1) / TILE_READS);
     if (m->v210)
         insert_reads_kernel<FIXED, true><<<grid, INSERT_THREADS, 0, m->stream>>>(
-            d_bin, n_bytes, d_off, rec, read0, n_reads, m->k, m->table, m->bits, m->d_counters);
+            d_bin, n_bytes, d_off, rec, read0, n_reads, m->k, m->table, m->cap, m->d_counters);
     else
         insert_reads_kernel<FIXED, false><<<grid, INSERT_THREADS, 0, m->stream>>>(
-            d_bin, n_bytes, d_off, rec, read0, n_reads, m->k, m->table, m->bits, m->d_counters);
+            d_bin, n_bytes, d_off, rec, read0, n_reads, m->k, m->table, m->cap, m->d_counters);
     GB_LAUNCHED();
     return GB_OK;
 }
@@ -442,7 +481,7 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
         if (!m->pe[i]) GB_CUDA(cudaEventCreate(&m->pe[i]));
     PartLayout pl;
     pl.owners = 1;
-    pl.lp_bits = slice_bits_for(m->bits, 1);
+    pl.lp_bits = slice_bits_for(m->cap, 1);
     if (const char *e = getenv("GENOME_B200_LP")) pl.lp_bits = std::max(0, std::min(pl.lp_bits + 3, atoi(e)));
     ReadBatch rb;
     rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = d_off; rb.rec_bytes = rec; rb.read0 = read0; rb.n_reads = n_reads;
@@ -508,7 +547,7 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
         const int64_t take_windows = fixed ? take * win_per_read_max
                                            : (h_win_prefix ? h_win_prefix[done + take] - h_win_prefix[done] : take * win_per_read_max);
         const int mode = insert_mode();
-        const bool partitioned = mode == 2 || (mode == 0 && ((size_t)sizeof(Slot) << m->bits) > (96u << 20) && take_windows >= (1 << 20));
+        const bool partitioned = mode == 2 || (mode == 0 && ((size_t)sizeof(Slot) * m->cap) > (96u << 20) && take_windows >= (1 << 20));
         GB_CUDA(cudaEventRecord(m->ev0, m->stream));
         if (partitioned) {
             // bounded key staging: at most 2^28 k-mers (2 GiB) per pass
@@ -583,7 +622,7 @@ namespace gb {
 int map_export_device(Map *m, unsigned long long *d_keys, int *d_vals)
 {
     if (m->size == 0) return GB_OK;
-    unsigned long long n = 1ull << m->bits;
+    unsigned long long n = m->cap;
     GB_TRY(map_zero_counters(m));
     export_kernel<<<grid_for(n, 256, 16), 256, 0, m->stream>>>(m->table, n, d_keys, d_vals, (unsigned long long)m->size, m->d_counters);
     GB_LAUNCHED();
@@ -636,7 +675,7 @@ int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_ma
     m->k = k;
     m->device = device;
     m->v210 = (flags & GB_FLAG_HASH_SCALA_210) != 0;
-    m->bits = bits_for(min_capacity);
+    const unsigned long long cap0 = cap_for(min_capacity);
     int r = GB_OK;
     do {
         if ((r = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
@@ -648,8 +687,8 @@ int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_ma
         if ((r = cudaMalloc((void **)&m->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess ? GB_OK : GB_E_OOM)) break;
         {
             Slot *none = nullptr;
-            int none_bits = 0;
-            if ((r = map_swap_table(m, m->bits, &none, &none_bits))) break;
+            unsigned long long none_cap = 0;
+            if ((r = map_swap_table(m, cap0, &none, &none_cap))) break;
         }
         if ((r = cudaStreamSynchronize(m->stream) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
     } while (0);
@@ -821,7 +860,7 @@ int gb_map_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, u
     GB_TRY(dc.alloc((size_t)n * 4, m->stream));
     GB_TRY(df.alloc((size_t)n, m->stream));
     GB_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, m->stream));
-    lookup_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, m->stream>>>((const unsigned long long *)dk.p, n, m->table, m->bits,
+    lookup_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, m->stream>>>((const unsigned long long *)dk.p, n, m->table, m->cap,
                                                                           (int *)dc.p, (uint8_t *)df.p);
     GB_LAUNCHED();
     if (counts) GB_CUDA(cudaMemcpyAsync(counts, dc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
@@ -834,7 +873,7 @@ int gb_map_delete_below(gb_map *h, int32_t min_count)
 {
     Map *m;
     GB_TRY(check_map(h, &m));
-    unsigned long long n = 1ull << m->bits;
+    unsigned long long n = m->cap;
     if (m->size == 0) return GB_OK;
     GB_TRY(map_zero_counters(m));
     // survivors go to the staging buffer: keys first, counts behind them
@@ -849,8 +888,8 @@ int gb_map_delete_below(gb_map *h, int32_t min_count)
     if (keep == m->size) return GB_OK;
     // a fresh table sized for the survivors
     Slot *old = nullptr;
-    int old_alloc = 0;
-    GB_TRY(map_swap_table(m, bits_for(keep), &old, &old_alloc));
+    unsigned long long old_alloc = 0;
+    GB_TRY(map_swap_table(m, cap_for(keep), &old, &old_alloc));
     map_retire_table(m, old, old_alloc);
     m->grows++;
     GB_TRY(map_zero_counters(m));
@@ -871,7 +910,7 @@ int gb_map_export(gb_map *h, uint64_t *keys, int32_t *vals, int64_t cap, int64_t
     DeviceBuf dk, dv;
     GB_TRY(dk.alloc((size_t)m->size * 8, m->stream));
     GB_TRY(dv.alloc((size_t)m->size * 4, m->stream));
-    unsigned long long n = 1ull << m->bits;
+    unsigned long long n = m->cap;
     GB_TRY(map_zero_counters(m));
     export_kernel<<<grid_for(n, 256, 16), 256, 0, m->stream>>>(m->table, n, (unsigned long long *)dk.p, (int *)dv.p,
                                                              (unsigned long long)m->size, m->d_counters);
@@ -889,14 +928,14 @@ int gb_map_clear(gb_map *h, int64_t min_capacity)
     Map *m;
     GB_TRY(check_map(h, &m));
     if (min_capacity < 0) { set_error("negative capacity"); return GB_E_ARG; }
-    int nb = bits_for(min_capacity);
-    if (nb != m->bits) {
+    unsigned long long nb = cap_for(min_capacity);
+    if (nb != m->cap) {
         Slot *old = nullptr;
-        int old_alloc = 0;
+        unsigned long long old_alloc = 0;
         GB_TRY(map_swap_table(m, nb, &old, &old_alloc));
         map_retire_table(m, old, old_alloc);
     } else {
-        GB_TRY(init_table(m->table, m->bits, m->stream));
+        GB_TRY(init_table(m->table, m->cap, m->stream));
     }
     m->size = 0;
     m->noncanonical = false;
@@ -972,7 +1011,7 @@ int gb_map_stats(gb_map *h, int64_t stats[8])
     GB_TRY(check_map(h, &m));
     if (!stats) { set_error("null argument"); return GB_E_ARG; }
     memset(stats, 0, 8 * sizeof(int64_t));
-    stats[0] = (int64_t)1 << m->bits;
+    stats[0] = (int64_t)m->cap;
     stats[1] = stats[0] * (int64_t)sizeof(Slot);
     stats[2] = m->grows;
     stats[3] = m->windows;

@@ -212,7 +212,7 @@ constexpr int SPREAD = 256; // new-key tallies are spread over this many counter
 template <int IK_PER_THREAD>
 __global__ void __launch_bounds__(IK_THREADS)
 insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vstart,
-                   const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Slot *table, int bits,
+                   const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Slot *table, unsigned long long cap,
                    unsigned long long *spread)
 {
     constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
@@ -226,7 +226,6 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
         }
         c = lo;
     }
-    const unsigned long long tmask = (1ull << bits) - 1;
     unsigned long long key[IK_PER_THREAD], idx[IK_PER_THREAD], cur[IK_PER_THREAD];
     bool ok[IK_PER_THREAD];
 #pragma unroll
@@ -236,7 +235,7 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
         if (ok[j]) {
             while (v >= vstart[c + 1]) c++; // chunks ascend with v; empty chunks are skipped
             key[j] = __ldcs(keys + off[c] + (v - vstart[c]));
-            idx[j] = slot_of(mix64(key[j]), bits);
+            idx[j] = slot_of(mix64(key[j]), cap);
         }
     }
 #pragma unroll
@@ -259,8 +258,8 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
             nk += claimed;
         } else {
             // the slot belongs to another key: linear probing from the next slot (rare at load <= 0.5)
-            unsigned long long nx = (idx[j] + 1) & tmask;
-            nk += upsert_add(table, tmask, nx, load_key(table + nx), key[j], 1);
+            unsigned long long nx = next_slot(idx[j], cap);
+            nk += upsert_add(table, cap, nx, load_key(table + nx), key[j], 1);
         }
     }
     nk = __reduce_add_sync(0xFFFFFFFFu, nk);
@@ -364,7 +363,7 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
     if (!per) { const char *e = getenv("GENOME_B200_IK"); per = e ? atoi(e) : 4; }
 #define GB_IK(N)                                                                                                          \
     insert_keys_kernel<N><<<(unsigned int)((n_total + IK_THREADS * N - 1) / (IK_THREADS * N)), IK_THREADS, 0, st>>>(       \
-        d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->bits, m->d_spread)
+        d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread)
     if (per == 8) GB_IK(8); else if (per == 16) GB_IK(16); else if (per == 2) GB_IK(2); else GB_IK(4);
 #undef GB_IK
     GB_LAUNCHED();

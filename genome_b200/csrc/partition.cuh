@@ -43,10 +43,10 @@ struct PartWork {
     void release();
 };
 
-inline int slice_bits_for(int table_bits, int owners)
+inline int slice_bits_for(unsigned long long table_slots, int owners)
 {
-    int lp = table_bits + 4 - SLICE_LOG2_BYTES; // 16-byte slots
-    if (lp < 0) lp = 0;
+    int lp = 0; // smallest lp with table bytes / 2^lp <= slice size (16-byte slots)
+    while (((table_slots * 16) >> lp) > (1ull << SLICE_LOG2_BYTES)) lp++;
     while (lp > 0 && (owners << lp) > 128) lp--; // the staged bucket pass handles at most 128 buckets
     return lp < 0 ? 0 : lp;
 }
