@@ -740,8 +740,14 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
     GB_NCCL(ncclGroupEnd());
     GB_CUDA(cudaStreamSynchronize(c->stream));
 
-    gb_map *rh = nullptr;
-    GB_TRY(gb_map_create(m->k, (int64_t)t, m->device, m->v210 ? GB_FLAG_HASH_SCALA_210 : 0, &rh));
+    // the replica map is kept with the shard and reused by the next build (its table is GBs: no malloc per call)
+    gb_map *rh = reinterpret_cast<gb_map *>(m->replica);
+    if (!rh) {
+        GB_TRY(gb_map_create(m->k, (int64_t)t, m->device, m->v210 ? GB_FLAG_HASH_SCALA_210 : 0, &rh));
+        m->replica = reinterpret_cast<Map *>(rh);
+    } else {
+        GB_TRY(gb_map_clear(rh, (int64_t)t));
+    }
     Map *r = reinterpret_cast<Map *>(rh);
     r->noncanonical = dual != 0;
     int rc = map_zero_counters(r);
@@ -752,7 +758,6 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
         r->size = (int64_t)cn[0];
         rc = gb_graph_build(rh, out);
     }
-    gb_map_destroy(rh);
     return rc;
 }
 

@@ -324,6 +324,7 @@ struct Map {
     unsigned long long *d_overflow = nullptr; // overflow keys (cap overflow_cap)
     int64_t overflow_cap = 0;
     Comm *comm = nullptr;
+    Map *replica = nullptr;    // sharded maps: the all-gathered copy Graph.buildGraph runs on (comm.cu)
     Arena arena;
 };
 

@@ -706,6 +706,8 @@ int gb_map_destroy(gb_map *h)
     if (!h) return GB_OK;
     Map *m = reinterpret_cast<Map *>(h);
     cudaSetDevice(m->device);
+    if (m->replica) gb_map_destroy(reinterpret_cast<gb_map *>(m->replica));
+    m->replica = nullptr;
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->table) cudaFree(m->table);
     if (m->spare) cudaFree(m->spare);
