@@ -346,6 +346,23 @@ def main():
                     "phases_ms": {"bucket (count+offsets+scatter)": st["bucket_ns"] * 1e-6, "upsert": st["upsert_ns"] * 1e-6} if partitioned else None,
                     "random_access_ceiling_kmers_per_s": gups, "insert_vs_random_access_ceiling": (windows / ins_s) / gups,
                     "table_bytes": table_bytes, "distinct_keys": distinct}
+        if partitioned and args.workload == "C2" and args.scale == 1.0:
+            # dram__bytes_read.sum + dram__bytes_write.sum of one insert_keys_kernel launch on this workload
+            roofline["traffic"] = 2.569e9 + 0.803e9
+            roofline["traffic_source"] = "profiles/insert_r1e_ncu_full_summary.csv (ncu --set full, same workload)"
+    else:
+        # per-rank insert of the sharded map (part_count + part_scatter<PEER> + insert_keys overlapped): whole-insert
+        # algorithmic bytes (16 B table + stream per instance) against the slowest rank's event time; the first-touch
+        # term needs the distinct count before the filter, which the timed loop does not keep
+        ins_s = max_over_ranks(float(np.mean(insert_ns)) * 1e-9)
+        algo_bytes = 16.0 * windows + float(b.size)
+        if rank == 0:
+            roofline = {"bound": "hbm", "kernel": "sharded insert: part_count + part_scatter<PEER> (NVLink stores) + insert_keys_kernel",
+                        "achieved": algo_bytes / ins_s / 1e9, "peak": peak, "unit": "GB/s", "frac": algo_bytes / ins_s / 1e9 / peak,
+                        "traffic": None, "peak_source": peak_src, "insert_ms": ins_s * 1e3,
+                        "insert_kmers_per_s_per_gpu": windows / ins_s,
+                        "nvlink_bytes_out_per_gpu": 8.0 * windows * (world - 1) / world,
+                        "nvlink_gbs_out_per_gpu": 8.0 * windows * (world - 1) / world / ins_s / 1e9}
 
     # ---------------- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload
     cpu = None

@@ -209,7 +209,7 @@ constexpr int SPREAD = 256; // new-key tallies are spread over this many counter
 
 // No CTA barrier anywhere: every thread finds its own chunk, every warp adds its new-key count to one of SPREAD
 // global counters (fold_new_keys_kernel sums them into counters[0] afterwards).
-template <int IK_PER_THREAD>
+template <int IK_PER_THREAD, bool CAS_FIRST>
 __global__ void __launch_bounds__(IK_THREADS)
 insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vstart,
                    const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Slot *table, unsigned long long cap,
@@ -238,16 +238,25 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
             idx[j] = slot_of(mix64(key[j]), cap);
         }
     }
-#pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++)
-        if (ok[j]) cur[j] = load_key(table + idx[j]);
     int nk = 0;
-    // the CAS round trips of a thread's keys overlap: all of them are issued before the first result is used
     unsigned long long old[IK_PER_THREAD];
+    if (CAS_FIRST) {
+        // one L2 transaction instead of two for a new key: the CAS is the probe (it returns the resident key)
 #pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++) {
-        old[j] = cur[j];
-        if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
+        for (int j = 0; j < IK_PER_THREAD; j++) {
+            cur[j] = EMPTY_KEY;
+            if (ok[j]) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < IK_PER_THREAD; j++)
+            if (ok[j]) cur[j] = load_key(table + idx[j]);
+        // the CAS round trips of a thread's keys overlap: all of them are issued before the first result is used
+#pragma unroll
+        for (int j = 0; j < IK_PER_THREAD; j++) {
+            old[j] = cur[j];
+            if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
+        }
     }
 #pragma unroll
     for (int j = 0; j < IK_PER_THREAD; j++) {
@@ -359,12 +368,17 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
         GB_CUDA(cudaMalloc((void **)&m->d_spread, SPREAD * 8));
         GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));
     }
-    static int per = 0;
-    if (!per) { const char *e = getenv("GENOME_B200_IK"); per = e ? atoi(e) : 4; }
-#define GB_IK(N)                                                                                                          \
-    insert_keys_kernel<N><<<(unsigned int)((n_total + IK_THREADS * N - 1) / (IK_THREADS * N)), IK_THREADS, 0, st>>>(       \
+    static int per = 0, cas_first = 0;
+    if (!per) {
+        const char *e = getenv("GENOME_B200_IK");
+        per = e ? atoi(e) : 4;
+        cas_first = getenv("GENOME_B200_CAS_FIRST") != nullptr;
+    }
+#define GB_IK(N, C)                                                                                                       \
+    insert_keys_kernel<N, C><<<(unsigned int)((n_total + IK_THREADS * N - 1) / (IK_THREADS * N)), IK_THREADS, 0, st>>>(    \
         d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread)
-    if (per == 8) GB_IK(8); else if (per == 16) GB_IK(16); else if (per == 2) GB_IK(2); else GB_IK(4);
+    if (cas_first) { if (per == 2) GB_IK(2, true); else if (per == 8) GB_IK(8, true); else GB_IK(4, true); }
+    else if (per == 8) GB_IK(8, false); else if (per == 2) GB_IK(2, false); else GB_IK(4, false);
 #undef GB_IK
     GB_LAUNCHED();
     fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);

@@ -57,6 +57,23 @@ def main():
         H.assert_graph_equal(g, og)
         g.close()
         m.close()
+    # fewer pairs than ranks: some ranks hold no reads at all but still take part in every collective
+    k = 15
+    b, n, _ = H.small_reads(400, 60, 1, 0.0, seed=77)
+    n = 2 * max(1, min(n // 2, world - 1))
+    b = b[:n * (1 + 15)]
+    mine = PairedEndData(b, n // 2).shard(rank, world)
+    m = PartitionedDNAMap(k, comm)
+    w = m.insert_reads(mine)
+    om, ow = H.oracle_counts(b, n, k)
+    tw = torch.tensor([w], device="cuda")
+    dist.all_reduce(tw)
+    assert int(tw.item()) == ow
+    assert m.size == om.size()
+    g = Graph.buildGraph(k, m)
+    H.assert_graph_equal(g, pyoracle.OracleGraph(om))
+    g.close()
+    m.close()
     # the device-resident entry point, fixed stride
     k = 31
     b, n, _ = H.small_reads(50000, 100, 10, 0.01, seed=321)
