@@ -133,6 +133,19 @@ def cpu_reference(b, n_reads, windows, threads, steps, warmup, sample_reads):
             times.append(dt)
         del m
     t = float(np.mean(times))
+    # the graph stage of the same sample, serial like Graph.buildGraph's driver loop (Graph.scala:367-374 is chunk.par, but
+    # every probe is a blocking remote ask there): build, components + retain + simplify
+    m = pyoracle.OracleMap(K, partitions=1)
+    m.insert_reads(sb, n, threads=0)
+    m.delete_below(ROUNDS)
+    t0 = time.perf_counter()
+    g = pyoracle.OracleGraph(m)
+    t1 = time.perf_counter()
+    g.components()
+    g.retain_largest()
+    g.simplify()
+    t2 = time.perf_counter()
+    cpu_reference.graph = {"kept_kmers": m.size(), "build_ms": (t1 - t0) * 1e3, "components_retain_simplify_ms": (t2 - t1) * 1e3, "cores": 1}
     return w / t, t, n, w
 
 
@@ -167,7 +180,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, desc), "k": K, "rounds": ROUNDS},
             "cpu_baseline": {"value": v, "unit": "k-mers/s", "cores": cores, "kind": "port",
-                             "sample": "first %d of %d reads (%d k-mer instances) per step" % (n, n_reads, w)},
+                             "sample": "first %d of %d reads (%d k-mer instances) per step" % (n, n_reads, w),
+                             "graph": getattr(cpu_reference, "graph", None)},
             "e2e": {"value": v, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -369,7 +383,8 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         v, t, n, w = cpu_reference(b, n_reads, windows, cores, 2, 1, 400_000)
         cpu = {"value": v, "unit": "k-mers/s", "cores": cores, "kind": "port",
-               "sample": "first %d of %d reads (%d k-mer instances), %d partitions/threads, mean of 2 passes" % (n, n_reads, w, cores)}
+               "sample": "first %d of %d reads (%d k-mer instances), %d partitions/threads, mean of 2 passes" % (n, n_reads, w, cores),
+               "graph": getattr(cpu_reference, "graph", None)}
 
     if rank == 0:
         line = {

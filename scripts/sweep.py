@@ -67,6 +67,10 @@ if __name__ == "__main__":
             b, n, _ = synth.make_config("C2", coverage=cov)
             for k in (21, 25, 31):
                 run("C2 cov=%d" % cov, b, n, k, int(4.6e6 + n * 100 * 0.01 * (k - 9)) + 1_000_000)
+    if which == "huge":
+        # configs[3] (1 Gbp, 150 bp, 40x, 0.5% errors) scaled to 1/20 on ONE GPU: a multi-GB table, several key-staging passes
+        b, n, _ = synth.make_config("C4", scale=0.05)
+        run("C4 x0.05 (50 Mbp, 0.5% errors, 150 bp, 40x)", b, n, 31, 330_000_000, reps=2)
     if which in ("large", "all"):
         # configs[2] (100 Mbp, 5% repeats, 150 bp, 50x) scaled to 1/5 so that reads + table fit the time budget of one call
         b, n, _ = synth.make_config("C3", scale=0.2)
