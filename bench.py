@@ -36,6 +36,8 @@ WORKLOADS = {
     # name: (synth config, scale, note)
     "C2": dict(cfg="C2", desc="4.6 Mbp random genome, 1% substitutions, 100 bp reads at 30x, k=31 (BASELINE configs[1])"),
     "C1": dict(cfg="C1", desc="4.6 Mbp random genome, error-free 100 bp reads at 30x, k=31 (BASELINE configs[0])"),
+    # BASELINE configs[3] shape (150 bp reads at 40x, 0.5% errors); use --scale 0.05: 50 Mbp of genome and a 16 GB shard per GPU
+    "C4": dict(cfg="C4", desc="1 Gbp-class random genome x scale, 0.5% substitutions, 150 bp reads at 40x, k=31 (BASELINE configs[3] shape)"),
 }
 
 
