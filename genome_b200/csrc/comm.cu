@@ -27,7 +27,8 @@ struct BatchBufs {
     unsigned long long *send = nullptr, *recv = nullptr;
     size_t send_cap = 0, recv_cap = 0;
     unsigned long long *d_tot = nullptr, *h_tot = nullptr; // bucket totals (mine, received) and the upsert's chunk table
-    PartWork work;
+    PartWork work;  // bucket pass of the outgoing keys (communicator stream)
+    PartWork work2; // re-bucketing of the received keys by fine table slice (map stream; two-level routing)
     cudaEvent_t exchanged = nullptr, inserted = nullptr;
     bool in_flight = false;
     int ensure(size_t ns, size_t nr);
@@ -208,6 +209,7 @@ void BatchBufs::release()
     if (exchanged) cudaEventDestroy(exchanged);
     if (inserted) cudaEventDestroy(inserted);
     work.release();
+    work2.release();
     send = recv = d_tot = h_tot = nullptr;
     exchanged = inserted = nullptr;
 }
@@ -318,8 +320,19 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     while (lp > 3 && (P << lp) > 32) lp--;
     while (lp > 0 && (P << lp) > 128) lp--; // stay in the staged (sector-coalesced) regime
     if (const char *e = getenv("GENOME_B200_LP")) lp = std::min<int64_t>(lp, std::max(0, atoi(e)));
+    // Routing levels.  ONE: the wire buckets are (owner, table slice) and the receiver upserts them as they arrive --
+    // fewest passes, but #buckets = P x slices must stay small for NVLink (long store runs), so slices grow with the
+    // shard.  TWO: the wire buckets are owners only (longest runs) and the receiver re-buckets each batch by fine slice
+    // (one more local pass over 8 B keys) -- keeps the upsert L2-resident for multi-GB shards.
+    int64_t two_level = (int64_t)(sizeof(Slot) * m->cap > (4ull << 30));
+    if (const char *e = getenv("GENOME_B200_ROUTE")) two_level = !strcmp(e, "two") ? 1 : (!strcmp(e, "one") ? 0 : two_level);
+    GB_TRY(all_reduce_i64(c, &two_level, ncclMax));
+    if (two_level) lp = 0;
     GB_TRY(all_reduce_i64(c, &batches, ncclMax));
     GB_TRY(all_reduce_i64(c, &lp, ncclMin)); // every rank must cut the same buckets
+    PartLayout fine; // receiver-side slices of two-level routing
+    fine.owners = 1;
+    fine.lp_bits = slice_bits_for(m->cap, 1);
     PartLayout pl;
     pl.owners = P;
     pl.lp_bits = (int)lp;
@@ -341,7 +354,8 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     // fused routing: every rank's bucket pass stores straight into the owners' inboxes over NVLink
     GB_TRY(ensure_inboxes(c, (size_t)std::min<int64_t>(batch_reads, std::max<int64_t>(n_reads, 1)) * (size_t)std::max<int64_t>(win_max, 1)));
     const bool p2p = c->p2p == 1;
-    if (trace) fprintf(stderr, "[pmap] routing: %s\n", p2p ? "peer stores into NVLink inboxes" : "NCCL send/recv");
+    if (trace) fprintf(stderr, "[pmap] routing: %s, %s (%d wire buckets, %d slices)\n", p2p ? "peer stores into NVLink inboxes" : "NCCL send/recv",
+                       two_level ? "two-level" : "one-level", NB, two_level ? 1 << fine.lp_bits : LP);
     GB_TRY(map_zero_counters(m));
     GB_CUDA(cudaStreamSynchronize(m->stream));
     GB_CUDA(cudaEventRecord(m->ev0, m->stream));
@@ -404,8 +418,6 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
         // chunk table of the upsert, slice-major: chunk (l, s) = source s's keys of slice l
         unsigned long long *vstart = B.h_tot + 2 * NB, *coff = vstart + NB + 1;
         {
-            unsigned long long within[MAX_RANKS];
-            for (int s = 0; s < P; s++) within[s] = 0;
             // offset of (s, l) inside source s's segment = prefix over l; walk slices outermost to fill vstart in order
             std::vector<unsigned long long> seg_off((size_t)NB);
             for (int s = 0; s < P; s++) {
@@ -439,7 +451,21 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
         }
         GB_CUDA(cudaStreamWaitEvent(m->stream, B.exchanged, 0));
         mark(m->stream);
-        GB_TRY(insert_key_chunks(m, recv_keys, B.d_tot + 2 * NB, B.d_tot + 3 * NB + 1, NB, rt, m->stream));
+        if (two_level && rt) {
+            // re-bucket the received segments by fine slice into B.recv (unused by peer routing), then one ordered upsert
+            if (!p2p) { set_error("two-level routing needs peer routing (inbox + local staging)"); return GB_E_STATE; }
+            GB_TRY(B.ensure(0, (size_t)rt));
+            KeySource ks;
+            ks.keys = recv_keys; ks.vstart = B.d_tot + 2 * NB; ks.off = B.d_tot + 3 * NB + 1; ks.n_chunks = NB; ks.n_total = rt;
+            GB_TRY(part_count_keys(ks, fine, B.work2, m->stream));
+            GB_TRY(part_scatter_keys(ks, fine, B.work2, B.recv, m->stream));
+            unsigned long long *desc = B.h_tot + 4 * NB + 1; // vstart[0], vstart[1], off[0] of the single chunk
+            desc[0] = 0; desc[1] = rt; desc[2] = 0;
+            GB_CUDA(cudaMemcpyAsync(B.d_tot + 4 * NB + 1, desc, 3 * 8, cudaMemcpyHostToDevice, m->stream));
+            GB_TRY(insert_key_chunks(m, B.recv, B.d_tot + 4 * NB + 1, B.d_tot + 4 * NB + 3, 1, rt, m->stream));
+        } else {
+            GB_TRY(insert_key_chunks(m, recv_keys, B.d_tot + 2 * NB, B.d_tot + 3 * NB + 1, NB, rt, m->stream));
+        }
         mark(m->stream);
         GB_CUDA(cudaEventRecord(B.inserted, m->stream));
         B.in_flight = true;

@@ -27,26 +27,65 @@ constexpr int WARPS = INSERT_THREADS / 32;
 constexpr int STAGE_MAX_BUCKETS = 128;           // the staged pass keeps per-bucket bookkeeping in shared memory
 constexpr int ROUND_KEYS = INSERT_THREADS * SEG; // keys a CTA stages per round
 
-template <bool FIXED, bool V210>
+// keys of round `blk` of a KeySource for this thread: positions blk*ROUND_KEYS + j*256 + tid, j < SEG (coalesced);
+// returns how many of them exist (they are the first `cnt`: positions ascend with j)
+__device__ __forceinline__ int load_round_keys(const KeySource &ks, unsigned long long blk, unsigned long long key[SEG])
+{
+    const unsigned long long v0 = blk * ROUND_KEYS;
+    int c = 0;
+    if (ks.n_chunks > 1) { // last chunk with vstart <= v0
+        int lo = 0, hi = ks.n_chunks;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (ks.vstart[mid] <= v0) lo = mid; else hi = mid;
+        }
+        c = lo;
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < SEG; j++) {
+        const unsigned long long v = v0 + (unsigned long long)j * INSERT_THREADS + threadIdx.x;
+        if (v < ks.n_total) {
+            while (v >= ks.vstart[c + 1]) c++;
+            key[j] = __ldcs(ks.keys + ks.off[c] + (v - ks.vstart[c]));
+            cnt = j + 1;
+        }
+    }
+    return cnt;
+}
+
+template <bool FIXED, bool V210, bool SRC_KEYS>
 __global__ void __launch_bounds__(INSERT_THREADS)
-part_count_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, unsigned int *cta_hist)
+part_count_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int lp_bits, unsigned int nb, unsigned int *cta_hist)
 {
     __shared__ ReadTile tile;
     __shared__ unsigned int s_hist[MAX_BUCKETS];
     const int tid = threadIdx.x;
     for (unsigned int b = tid; b < MAX_BUCKETS; b += INSERT_THREADS) s_hist[b] = 0;
-    const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        stage_tile<FIXED>(tile, rb.bin, rb.n_bytes, rb.offsets, rb.rec_bytes, rb.read0, rb.n_reads, k, t);
-        const unsigned int total_items = tile.prefix[TILE_READS];
-        for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
+    __syncthreads();
+    if (SRC_KEYS) {
+        const unsigned long long n_blk = (ks.n_total + ROUND_KEYS - 1) / ROUND_KEYS;
+        for (unsigned long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
             unsigned long long key[SEG];
-            const int cnt = item_keys<V210>(tile, item, k, key);
+            const int cnt = load_round_keys(ks, blk, key);
 #pragma unroll
             for (int j = 0; j < SEG; j++)
-                if (j < cnt) atomicAdd(&s_hist[bucket_of(mix64(key[j]), owners, lp_bits)], 1u); // no return value: a RED
+                if (j < cnt) atomicAdd(&s_hist[bucket_of(mix64(key[j]), owners, lp_bits)], 1u);
         }
-        __syncthreads(); // the tile is overwritten by the next stage_tile
+    } else {
+        const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            stage_tile<FIXED>(tile, rb.bin, rb.n_bytes, rb.offsets, rb.rec_bytes, rb.read0, rb.n_reads, k, t);
+            const unsigned int total_items = tile.prefix[TILE_READS];
+            for (unsigned int item = tid; item < total_items; item += INSERT_THREADS) {
+                unsigned long long key[SEG];
+                const int cnt = item_keys<V210>(tile, item, k, key);
+#pragma unroll
+                for (int j = 0; j < SEG; j++)
+                    if (j < cnt) atomicAdd(&s_hist[bucket_of(mix64(key[j]), owners, lp_bits)], 1u); // no return value: a RED
+            }
+            __syncthreads(); // the tile is overwritten by the next stage_tile
+        }
     }
     __syncthreads();
     for (unsigned int b = tid; b < nb; b += INSERT_THREADS) cta_hist[(size_t)blockIdx.x * nb + b] = s_hist[b];
@@ -93,9 +132,9 @@ part_bases_kernel(const unsigned long long *bucket_total, unsigned int nb, unsig
 // scattered 8-byte stores per warp instruction.  That is what fills NVLink write packets when PEER.
 // PEER: the position of a key is (owner, index inside the owner's segment) packed in 32 bits and the store goes to
 // the owner's inbox through its peer mapping -- the all-to-all happens inside this kernel, store by store.
-template <bool FIXED, bool V210, bool STAGED, bool PEER>
+template <bool FIXED, bool V210, bool SRC_KEYS, bool PEER>
 __global__ void __launch_bounds__(INSERT_THREADS, 4)
-part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsigned int nb, const unsigned int *cta_off,
+part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int lp_bits, unsigned int nb, const unsigned int *cta_off,
                     const unsigned long long *bucket_base, unsigned long long *out, PeerOut peers)
 {
     __shared__ ReadTile tile;
@@ -122,82 +161,95 @@ part_scatter_kernel(ReadBatch rb, int k, unsigned int owners, int lp_bits, unsig
         else out[pos] = key;
     };
     const unsigned int lt = (1u << lane) - 1;
-    const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
     __syncthreads();
-    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        stage_tile<FIXED>(tile, rb.bin, rb.n_bytes, rb.offsets, rb.rec_bytes, rb.read0, rb.n_reads, k, t);
-        const unsigned int total_items = tile.prefix[TILE_READS];
-        for (unsigned int item0 = 0; item0 < total_items; item0 += INSERT_THREADS) { // uniform over the CTA
-            const unsigned int item = item0 + tid;
-            unsigned long long key[SEG];
-            int cnt = 0;
-            if (item < total_items) cnt = item_keys<V210>(tile, item, k, key);
-            for (unsigned int b = lane; b < nb; b += 32) rcnt[b] = 0;
+    // one round: the CTA's (up to) ROUND_KEYS keys, key[0..cnt) per thread, go out sorted by bucket
+    auto do_round = [&](const unsigned long long (&key)[SEG], int cnt) {
+        for (unsigned int b = lane; b < nb; b += 32) rcnt[b] = 0;
+        __syncwarp();
+        unsigned int bk[SEG], rk[SEG];
+#pragma unroll
+        for (int j = 0; j < SEG; j++) {
+            const bool valid = j < cnt;
+            const unsigned int b = valid ? bucket_of(mix64(key[j]), owners, lp_bits) : 0xFFFFFFFFu;
+            const unsigned int peers_mask = __match_any_sync(0xFFFFFFFFu, b);
+            const unsigned int rank = __popc(peers_mask & lt);
+            const unsigned int base = valid ? rcnt[b] : 0;
             __syncwarp();
-            unsigned int bk[SEG], rk[SEG];
+            if (valid && rank == 0) rcnt[b] = base + __popc(peers_mask);
+            __syncwarp();
+            bk[j] = b;
+            rk[j] = base + rank; // rank among this warp's keys of bucket b in this round
+        }
+        __syncthreads();
+        // per bucket: exclusive prefix over the warps (in place) and the round's total
+        if (tid < (int)nb) {
+            unsigned int acc = 0;
 #pragma unroll
-            for (int j = 0; j < SEG; j++) {
-                const bool valid = j < cnt;
-                const unsigned int b = valid ? bucket_of(mix64(key[j]), owners, lp_bits) : 0xFFFFFFFFu;
-                const unsigned int peers_mask = __match_any_sync(0xFFFFFFFFu, b);
-                const unsigned int rank = __popc(peers_mask & lt);
-                const unsigned int base = valid ? rcnt[b] : 0;
-                __syncwarp();
-                if (valid && rank == 0) rcnt[b] = base + __popc(peers_mask);
-                __syncwarp();
-                bk[j] = b;
-                rk[j] = base + rank; // rank among this warp's keys of bucket b in this round
+            for (int w = 0; w < WARPS; w++) {
+                unsigned int v = rcnt_all[(size_t)w * nb + tid];
+                rcnt_all[(size_t)w * nb + tid] = acc;
+                acc += v;
             }
-            __syncthreads();
-            // per bucket: exclusive prefix over the warps (in place) and the round's total
-            if (tid < (int)nb) {
-                unsigned int acc = 0;
+            bstart[tid] = acc; // total, turned into the start below
+        }
+        __syncthreads();
+        if (warp == 0) { // exclusive scan of up to 128 totals: 4 consecutive buckets per lane
+            unsigned int v[4], sum = 0;
 #pragma unroll
-                for (int w = 0; w < WARPS; w++) {
-                    unsigned int v = rcnt_all[(size_t)w * nb + tid];
-                    rcnt_all[(size_t)w * nb + tid] = acc;
-                    acc += v;
-                }
-                bstart[tid] = acc; // total, turned into the start below
+            for (int q = 0; q < 4; q++) {
+                const unsigned int b = lane * 4 + q;
+                v[q] = b < nb ? bstart[b] : 0;
+                sum += v[q];
             }
-            __syncthreads();
-            if (warp == 0) { // exclusive scan of up to 128 totals: 4 consecutive buckets per lane
-                unsigned int v[4], sum = 0;
+            unsigned int incl = sum;
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const unsigned int b = lane * 4 + q;
-                    v[q] = b < nb ? bstart[b] : 0;
-                    sum += v[q];
-                }
-                unsigned int incl = sum;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    unsigned int x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (lane >= d) incl += x;
-                }
-                unsigned int run = incl - sum;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const unsigned int b = lane * 4 + q;
-                    if (b < nb) bstart[b] = run;
-                    run += v[q];
-                }
-                if (lane == 31) bstart[nb] = run;
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned int x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= d) incl += x;
             }
-            __syncthreads();
-            const unsigned int round_total = bstart[nb];
+            unsigned int run = incl - sum;
 #pragma unroll
-            for (int j = 0; j < SEG; j++)
-                if (j < cnt) {
-                    const unsigned int in_bucket = rcnt[bk[j]] + rk[j];
-                    const unsigned int idx = bstart[bk[j]] + in_bucket;
-                    skey[idx] = key[j];
-                    sdst[idx] = bcur[bk[j]] + in_bucket;
-                }
-            __syncthreads();
-            for (unsigned int idx = tid; idx < round_total; idx += INSERT_THREADS) store(sdst[idx], skey[idx]);
-            if (tid < (int)nb) bcur[tid] += bstart[tid + 1] - bstart[tid];
-            __syncthreads();
+            for (int q = 0; q < 4; q++) {
+                const unsigned int b = lane * 4 + q;
+                if (b < nb) bstart[b] = run;
+                run += v[q];
+            }
+            if (lane == 31) bstart[nb] = run;
+        }
+        __syncthreads();
+        const unsigned int round_total = bstart[nb];
+#pragma unroll
+        for (int j = 0; j < SEG; j++)
+            if (j < cnt) {
+                const unsigned int in_bucket = rcnt[bk[j]] + rk[j];
+                const unsigned int idx = bstart[bk[j]] + in_bucket;
+                skey[idx] = key[j];
+                sdst[idx] = bcur[bk[j]] + in_bucket;
+            }
+        __syncthreads();
+        for (unsigned int idx = tid; idx < round_total; idx += INSERT_THREADS) store(sdst[idx], skey[idx]);
+        if (tid < (int)nb) bcur[tid] += bstart[tid + 1] - bstart[tid];
+        __syncthreads();
+    };
+    if (SRC_KEYS) {
+        const unsigned long long n_blk = (ks.n_total + ROUND_KEYS - 1) / ROUND_KEYS;
+        for (unsigned long long blk = blockIdx.x; blk < n_blk; blk += gridDim.x) {
+            unsigned long long key[SEG];
+            const int cnt = load_round_keys(ks, blk, key);
+            do_round(key, cnt);
+        }
+    } else {
+        const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            stage_tile<FIXED>(tile, rb.bin, rb.n_bytes, rb.offsets, rb.rec_bytes, rb.read0, rb.n_reads, k, t);
+            const unsigned int total_items = tile.prefix[TILE_READS];
+            for (unsigned int item0 = 0; item0 < total_items; item0 += INSERT_THREADS) { // uniform over the CTA
+                const unsigned int item = item0 + tid;
+                unsigned long long key[SEG];
+                int cnt = 0;
+                if (item < total_items) cnt = item_keys<V210>(tile, item, k, key);
+                do_round(key, cnt);
+            }
         }
     }
 }
@@ -309,17 +361,8 @@ void PartWork::release()
     bucket_base = bucket_total = nullptr;
 }
 
-int part_count(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, cudaStream_t st)
+static int finish_count(PartWork &w, unsigned int nb, cudaStream_t st)
 {
-    GB_TRY(w.ensure(st));
-    const unsigned int nb = (unsigned int)pl.nb();
-    if (nb > MAX_BUCKETS) { set_error("internal: %u buckets", nb); return GB_E_ARG; }
-    const bool fixed = rb.offsets == nullptr;
-#define GB_PC(F, V) part_count_kernel<F, V><<<w.grid, INSERT_THREADS, 0, st>>>(rb, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist)
-    if (fixed) { if (v210) GB_PC(true, true); else GB_PC(true, false); }
-    else { if (v210) GB_PC(false, true); else GB_PC(false, false); }
-#undef GB_PC
-    GB_LAUNCHED();
     part_offsets_kernel<<<nb, 256, 0, st>>>(w.cta_hist, w.grid, nb, w.bucket_total);
     GB_LAUNCHED();
     part_bases_kernel<<<1, MAX_BUCKETS, 0, st>>>(w.bucket_total, nb, w.bucket_base);
@@ -327,24 +370,50 @@ int part_count(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, Part
     return GB_OK;
 }
 
+int part_count(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, cudaStream_t st)
+{
+    GB_TRY(w.ensure(st));
+    const unsigned int nb = (unsigned int)pl.nb();
+    if (nb > MAX_BUCKETS) { set_error("internal: %u buckets", nb); return GB_E_ARG; }
+    const bool fixed = rb.offsets == nullptr;
+    KeySource none;
+#define GB_PC(F, V) part_count_kernel<F, V, false><<<w.grid, INSERT_THREADS, 0, st>>>(rb, none, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist)
+    if (fixed) { if (v210) GB_PC(true, true); else GB_PC(true, false); }
+    else { if (v210) GB_PC(false, true); else GB_PC(false, false); }
+#undef GB_PC
+    GB_LAUNCHED();
+    return finish_count(w, nb, st);
+}
+
+int part_count_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, cudaStream_t st)
+{
+    GB_TRY(w.ensure(st));
+    const unsigned int nb = (unsigned int)pl.nb();
+    if (nb > MAX_BUCKETS) { set_error("internal: %u buckets", nb); return GB_E_ARG; }
+    ReadBatch none;
+    part_count_kernel<true, false, true><<<w.grid, INSERT_THREADS, 0, st>>>(none, ks, 0, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist);
+    GB_LAUNCHED();
+    return finish_count(w, nb, st);
+}
+
+static size_t scatter_smem(unsigned int nb) { return ((size_t)nb * (2 + WARPS) + 4 + ROUND_KEYS) * 4 + (size_t)ROUND_KEYS * 8; }
+
 static int launch_scatter(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out,
                           const PeerOut *peers, cudaStream_t st)
 {
     const unsigned int nb = (unsigned int)pl.nb();
     const bool fixed = rb.offsets == nullptr;
     if (nb > STAGE_MAX_BUCKETS) { set_error("internal: %u buckets exceed the staged bucket pass", nb); return GB_E_ARG; }
-    const bool staged = true;
-    const size_t smem = ((size_t)nb * (2 + WARPS) + 4 + ROUND_KEYS) * 4 + (size_t)ROUND_KEYS * 8;
+    const size_t smem = scatter_smem(nb);
     PeerOut po;
     memset(&po, 0, sizeof po);
     if (peers) po = *peers;
-#define GB_PS(F, V, S, P) part_scatter_kernel<F, V, S, P><<<w.grid, INSERT_THREADS, smem, st>>>(rb, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist, w.bucket_base, out, po)
-#define GB_PS3(F, V, S) do { if (peers) GB_PS(F, V, S, true); else GB_PS(F, V, S, false); } while (0)
-#define GB_PS2(F, V) do { if (staged) GB_PS3(F, V, true); else GB_PS3(F, V, false); } while (0)
+    KeySource none;
+#define GB_PS(F, V, P) part_scatter_kernel<F, V, false, P><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist, w.bucket_base, out, po)
+#define GB_PS2(F, V) do { if (peers) GB_PS(F, V, true); else GB_PS(F, V, false); } while (0)
     if (fixed) { if (v210) GB_PS2(true, true); else GB_PS2(true, false); }
     else { if (v210) GB_PS2(false, true); else GB_PS2(false, false); }
 #undef GB_PS2
-#undef GB_PS3
 #undef GB_PS
     GB_LAUNCHED();
     return GB_OK;
@@ -358,6 +427,19 @@ int part_scatter(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, Pa
 int part_scatter_peers(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, const PeerOut &peers, cudaStream_t st)
 {
     return launch_scatter(rb, k, v210, pl, w, nullptr, &peers, st);
+}
+
+int part_scatter_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, unsigned long long *out, cudaStream_t st)
+{
+    const unsigned int nb = (unsigned int)pl.nb();
+    if (nb > STAGE_MAX_BUCKETS) { set_error("internal: %u buckets exceed the staged bucket pass", nb); return GB_E_ARG; }
+    ReadBatch none;
+    PeerOut po;
+    memset(&po, 0, sizeof po);
+    part_scatter_kernel<true, false, true, false><<<w.grid, INSERT_THREADS, scatter_smem(nb), st>>>(none, ks, 0, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist,
+                                                                                             w.bucket_base, out, po);
+    GB_LAUNCHED();
+    return GB_OK;
 }
 
 int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned long long *d_vstart, const unsigned long long *d_off,

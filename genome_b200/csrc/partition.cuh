@@ -32,6 +32,14 @@ struct ReadBatch {
     long long read0 = 0, n_reads = 0;
 };
 
+// keys already extracted (a received inbox): `n_chunks` ranges, chunk c = virtual positions [vstart[c], vstart[c+1])
+// starting at keys[off[c]]; all arrays on the device
+struct KeySource {
+    const unsigned long long *keys = nullptr, *vstart = nullptr, *off = nullptr;
+    int n_chunks = 0;
+    unsigned long long n_total = 0;
+};
+
 // per-CTA bucket histograms -> bucket bases; device arrays live in PartWork
 struct PartWork {
     int grid = 0;
@@ -57,6 +65,10 @@ int part_count(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, Part
 int part_scatter(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, cudaStream_t st);
 // same, but owner o's buckets are written to peers.base[o] (its inbox region for this rank), not to one local array
 int part_scatter_peers(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, const PeerOut &peers, cudaStream_t st);
+
+// the same two passes over keys that are already extracted: re-bucket a received batch by (fine) table slice
+int part_count_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, cudaStream_t st);
+int part_scatter_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, unsigned long long *out, cudaStream_t st);
 
 // update(key, 1, _ + 1) for the keys of `n_chunks` ranges visited in order: chunk c holds the virtual positions
 // [vstart[c], vstart[c+1]) and starts at keys[off[c]].  d_vstart has n_chunks + 1 entries.  n_total = vstart[n_chunks].
