@@ -9,12 +9,28 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def run_world(world, extra_env=None):
+    env = dict(os.environ)
+    env.update(extra_env or {})
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", str(29740 + world), os.path.join(ROOT, "tests", "nccl_worker.py")],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-6000:]
+    assert "PMAP OK world %d" % world in r.stdout
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_pmap_matches_oracle(gpu, world):
     if gpu < world:
         pytest.skip("needs %d GPUs, box has %d" % (world, gpu))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-                        "--master-port", str(29740 + world), os.path.join(ROOT, "tests", "nccl_worker.py")],
-                       capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-6000:]
-    assert "PMAP OK world %d" % world in r.stdout
+    run_world(world)
+
+
+@pytest.mark.parametrize("env", [{"GENOME_B200_ROUTE": "two"}, {"GENOME_B200_A2A": "nccl"}, {"GENOME_B200_BATCHES": "5", "GENOME_B200_LP": "1"}],
+                         ids=["two-level", "nccl-staged", "many-batches"])
+def test_pmap_routing_variants(gpu, env):
+    """The same sharded run through the other routing paths: receiver-side re-bucketing, NCCL send/recv staging instead of
+    peer stores, more batches than buffer sets."""
+    if gpu < 2:
+        pytest.skip("needs 2 GPUs, box has %d" % gpu)
+    run_world(2, env)
