@@ -776,14 +776,39 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
     }
     Map *r = reinterpret_cast<Map *>(rh);
     r->noncanonical = dual != 0;
+    // the gathered array is identical on every rank: its index is the vertex id everywhere, so the ranks can split the
+    // membership probes (the heaviest kernel of the build) and exchange the results
+    const bool as_vertices = t < (1ull << 30);
     int rc = map_zero_counters(r);
-    if (rc == GB_OK) rc = map_launch_update_set(r, (const unsigned long long *)all_keys.p, (const int *)all_vals.p, (int64_t)t, r->stream);
+    if (rc == GB_OK) rc = map_launch_update_set(r, (const unsigned long long *)all_keys.p, (const int *)all_vals.p, (int64_t)t, r->stream, as_vertices);
     unsigned long long cn[4];
     if (rc == GB_OK) rc = map_read_counters(r, cn);
-    if (rc == GB_OK) {
-        r->size = (int64_t)cn[0];
-        rc = gb_graph_build(rh, out);
-    }
+    if (rc != GB_OK) return rc;
+    r->size = (int64_t)cn[0];
+    if (!as_vertices) return gb_graph_build(rh, out);
+    r->kept_keys = (const unsigned long long *)all_keys.p;
+    r->kept_n = (int64_t)t;
+    r->kept_valid = true;
+    struct Ctx { Comm *c; const unsigned long long *offs, *sizes; } ctx{ c, offs.data(), sizes.data() };
+    ShardPlan sp;
+    sp.lo = offs[c->rank];
+    sp.hi = offs[c->rank] + sizes[c->rank];
+    sp.ctx = &ctx;
+    sp.gather = [](void *vctx, void *base, size_t elem) -> int {
+        Ctx *x = (Ctx *)vctx;
+        Comm *cc = x->c;
+        GB_NCCL(ncclGroupStart());
+        for (int p = 0; p < cc->n_ranks; p++) {
+            if (!x->sizes[p]) continue;
+            char *seg = (char *)base + x->offs[p] * elem;
+            GB_NCCL(ncclBroadcast(seg, seg, x->sizes[p] * elem, ncclUint8, p, cc->nccl, cc->stream));
+        }
+        GB_NCCL(ncclGroupEnd());
+        GB_CUDA(cudaStreamSynchronize(cc->stream));
+        return GB_OK;
+    };
+    rc = graph_build_sharded(rh, out, &sp);
+    r->kept_valid = false; // all_keys goes back to the arena with this call
     return rc;
 }
 

@@ -324,11 +324,25 @@ struct Map {
     unsigned long long *d_overflow = nullptr; // overflow keys (cap overflow_cap)
     int64_t overflow_cap = 0;
     Comm *comm = nullptr;
+    // after deleteAll (or in a replica): the stored keys as one device array whose index IS the vertex id written in
+    // the slots, so Graph.buildGraph needs no numbering pass.  Any mutation invalidates it.
+    const unsigned long long *kept_keys = nullptr;
+    int64_t kept_n = 0;
+    bool kept_valid = false;
     Map *replica = nullptr;    // sharded maps: the all-gathered copy Graph.buildGraph runs on (comm.cu)
     Arena arena;
 };
 
 int map_reserve(Map *m, int64_t want_keys);
+
+// sharded Graph.buildGraph: this rank computes the membership masks of vertices [lo, hi) only; gather(ctx, base, elem)
+// makes every rank's range of the device array `base` (elem bytes per vertex) visible on all ranks
+struct ShardPlan {
+    unsigned long long lo = 0, hi = 0;
+    int (*gather)(void *ctx, void *base, size_t elem_bytes) = nullptr;
+    void *ctx = nullptr;
+};
+int graph_build_sharded(gb_map *h, gb_graph **out, const ShardPlan *sp);
 int check_map(gb_map *h, Map **m);
 
 inline unsigned int grid_for(unsigned long long n, int threads, int per_sm = 16)

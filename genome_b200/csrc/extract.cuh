@@ -170,7 +170,7 @@ int map_rebuild(Map *m, unsigned long long new_cap, bool filter, int min_count);
 int map_export_device(Map *m, unsigned long long *d_keys, int *d_vals);
 int map_verify_fixed(Map *m, const uint8_t *d_bin, unsigned int rec, unsigned int len0, int64_t n_reads, unsigned long long *bad);
 int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n, cudaStream_t st);
-int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d_vals, int64_t n, cudaStream_t st);
+int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d_vals, int64_t n, cudaStream_t st, bool set_vid);
 int scan_records(const uint8_t *bin, size_t n_bytes, int64_t n_reads, int k, std::vector<unsigned long long> &off,
                  std::vector<int64_t> &winp);
 

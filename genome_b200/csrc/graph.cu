@@ -138,15 +138,23 @@ assign_vertices_kernel(Slot *table, unsigned long long cap, int k, bool dual, co
 
 // incoming / outcoming (Graph.scala:272-282) of every stored key: 8 membership probes, either orientation.
 // mask8 = out | in << 4; nbr_out / nbr_in = the oriented neighbour when there is exactly one.
+// `check_secondary`: keys[] came from a compacted array, not from the numbering pass, so an entry may be the SECONDARY
+// orientation of a k-mer stored twice (hash tie / as-is inserts): it is no vertex (mask 0 = isolated, never referenced).
 template <bool V210>
 __global__ void __launch_bounds__(256)
-masks_kernel(const Slot *table, unsigned long long cap, int k, bool dual, const unsigned long long *keys, unsigned long long n,
-             uint8_t *mask8, unsigned int *nbr_out, unsigned int *nbr_in)
+masks_kernel(const Slot *table, unsigned long long cap, int k, bool dual, const unsigned long long *keys, unsigned long long lo,
+             unsigned long long n, bool check_secondary, uint8_t *mask8, unsigned int *nbr_out, unsigned int *nbr_in)
 {
-    unsigned long long v = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
+    unsigned long long v = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= lo + n) return;
     const unsigned long long x = keys[v];
     unsigned int out = 0, in = 0, so = NONE32, si = NONE32;
+    if (check_secondary && is_secondary<V210>(table, cap, k, dual, x)) {
+        mask8[v] = 0;
+        nbr_out[v] = NONE32;
+        nbr_in[v] = NONE32;
+        return;
+    }
 #pragma unroll
     for (unsigned int b = 0; b < 4; b++) {
         Slot s;
@@ -744,7 +752,7 @@ static int read_u64(const unsigned long long *d, unsigned long long *h, int n, c
 }
 
 template <bool V210>
-static int build_graph(Map *m, Graph *g)
+static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
 {
     cudaStream_t st = m->stream;
     const int k = m->k;
@@ -762,26 +770,34 @@ static int build_graph(Map *m, Graph *g)
         fprintf(stderr, "[graph] %-28s %9.3f ms\n", what, now_ms() - t_begin);
     };
 
-    // ---- dense vertex ids in slot order
-    const unsigned long long tiles = (slots + TILE - 1) / TILE;
-    Tmp<unsigned long long> tile_cnt, total;
-    GB_TRY(tile_cnt.alloc(tiles, st));
-    GB_TRY(total.alloc(4, st));
-    count_vertices_kernel<V210><<<(unsigned int)tiles, 256, 0, st>>>(m->table, bits, k, dual, tile_cnt.p);
-    GB_LAUNCHED();
-    GB_TRY(exclusive_scan_u64(tile_cnt.p, tiles, total.p, st));
     unsigned long long n = 0;
-    GB_TRY(read_u64(total.p, &n, 1, st));
+    Tmp<unsigned long long> total, keys_tmp;
+    GB_TRY(total.alloc(4, st));
+    const unsigned long long *keys_p = nullptr;
+    const bool given = m->kept_valid;
+    if (given) {
+        // the filter (or the replica insert) left the stored keys as one array whose index is the slot's vid
+        n = (unsigned long long)m->kept_n;
+        keys_p = m->kept_keys;
+    } else {
+        // ---- dense vertex ids in slot order
+        const unsigned long long tiles = (slots + TILE - 1) / TILE;
+        Tmp<unsigned long long> tile_cnt;
+        GB_TRY(tile_cnt.alloc(tiles, st));
+        count_vertices_kernel<V210><<<(unsigned int)tiles, 256, 0, st>>>(m->table, bits, k, dual, tile_cnt.p);
+        GB_LAUNCHED();
+        GB_TRY(exclusive_scan_u64(tile_cnt.p, tiles, total.p, st));
+        GB_TRY(read_u64(total.p, &n, 1, st));
+        if (n >= (1ull << 30)) { set_error("%llu stored k-mers on one GPU: the graph build addresses at most 2^30", n); return GB_E_CAPACITY; }
+        tick("counted vertices");
+        GB_TRY(keys_tmp.alloc(n, st));
+        assign_vertices_kernel<V210><<<(unsigned int)tiles, 256, 0, st>>>(m->table, bits, k, dual, tile_cnt.p, keys_tmp.p);
+        GB_LAUNCHED();
+        keys_p = keys_tmp.p;
+    }
     if (n >= (1ull << 30)) { set_error("%llu stored k-mers on one GPU: the graph build addresses at most 2^30", n); return GB_E_CAPACITY; }
     g->stats[0] = (int64_t)n;
-
-    tick("counted vertices");
-    Tmp<unsigned long long> keys;
-    GB_TRY(keys.alloc(n, st));
-    assign_vertices_kernel<V210><<<(unsigned int)tiles, 256, 0, st>>>(m->table, bits, k, dual, tile_cnt.p, keys.p);
-    GB_LAUNCHED();
-    tile_cnt.release();
-
+    struct { const unsigned long long *p; } keys{ keys_p };
     tick("assigned vertices");
     // ---- in/out masks and unique neighbours
     Tmp<uint8_t> mask8;
@@ -789,7 +805,17 @@ static int build_graph(Map *m, Graph *g)
     GB_TRY(mask8.alloc(n, st));
     GB_TRY(nbr_out.alloc(n, st));
     GB_TRY(nbr_in.alloc(n, st));
-    LAUNCH(masks_kernel<V210>, n, m->table, bits, k, dual, keys.p, n, mask8.p, nbr_out.p, nbr_in.p);
+    {
+        // sharded build: this rank probes only its own range of the (identical) key array, then the ranks exchange ranges
+        const unsigned long long lo = sp ? sp->lo : 0, cnt = sp ? sp->hi - sp->lo : n;
+        LAUNCH(masks_kernel<V210>, cnt, m->table, bits, k, dual, keys.p, lo, cnt, given, mask8.p, nbr_out.p, nbr_in.p);
+        if (sp) {
+            GB_CUDA(cudaStreamSynchronize(st));
+            GB_TRY(sp->gather(sp->ctx, mask8.p, 1));
+            GB_TRY(sp->gather(sp->ctx, nbr_out.p, 4));
+            GB_TRY(sp->gather(sp->ctx, nbr_in.p, 4));
+        }
+    }
     BuildArrays B{ keys.p, mask8.p, nbr_out.p, nbr_in.p, n, k };
     const unsigned long long n2 = 2 * n;
 
@@ -962,6 +988,27 @@ static int components(Graph *g, Tmp<unsigned int> &parent)
     return GB_OK;
 }
 
+int graph_build_sharded(gb_map *h, gb_graph **out, const ShardPlan *sp)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    ArenaScope scope(&m->arena);
+    if (!out) { set_error("null out pointer"); return GB_E_ARG; }
+    *out = nullptr;
+    Graph *g = new Graph();
+    g->k = m->k;
+    g->device = m->device;
+    int r = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) == cudaSuccess ? GB_OK : GB_E_CUDA;
+    if (r == GB_OK) r = m->v210 ? build_graph<true>(m, g, sp) : build_graph<false>(m, g, sp);
+    if (r != GB_OK) {
+        cudaStreamSynchronize(m->stream);
+        gb_graph_destroy(reinterpret_cast<gb_graph *>(g));
+        return r;
+    }
+    *out = reinterpret_cast<gb_graph *>(g);
+    return GB_OK;
+}
+
 } // namespace gb
 
 using namespace gb;
@@ -987,26 +1034,7 @@ int gb_map_neighbour_masks(gb_map *h, const uint64_t *keys, int64_t n, uint8_t *
     return GB_OK;
 }
 
-int gb_graph_build(gb_map *h, gb_graph **out)
-{
-    Map *m;
-    GB_TRY(check_map(h, &m));
-    ArenaScope scope(&m->arena);
-    if (!out) { set_error("null out pointer"); return GB_E_ARG; }
-    *out = nullptr;
-    Graph *g = new Graph();
-    g->k = m->k;
-    g->device = m->device;
-    int r = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) == cudaSuccess ? GB_OK : GB_E_CUDA;
-    if (r == GB_OK) r = m->v210 ? build_graph<true>(m, g) : build_graph<false>(m, g);
-    if (r != GB_OK) {
-        cudaStreamSynchronize(m->stream);
-        gb_graph_destroy(reinterpret_cast<gb_graph *>(g));
-        return r;
-    }
-    *out = reinterpret_cast<gb_graph *>(g);
-    return GB_OK;
-}
+int gb_graph_build(gb_map *h, gb_graph **out) { return gb::graph_build_sharded(h, out, nullptr); }
 
 int gb_graph_destroy(gb_graph *h)
 {

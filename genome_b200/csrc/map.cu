@@ -178,9 +178,10 @@ __global__ void verify_fixed_kernel(const uint8_t *__restrict__ bin, unsigned in
 }
 
 // update(key, 1, _ + 1) / update(key, v) for explicit keys
+// SET: update(key, v); set_vid: additionally slot.vid = the key's index in `keys` (keys must be distinct then)
 template <bool SET>
 __global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ vals,
-                                   long long n, Slot *table, unsigned long long cap, unsigned long long *counters)
+                                   long long n, Slot *table, unsigned long long cap, unsigned long long *counters, bool set_vid = false)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int nk = 0;
@@ -196,7 +197,11 @@ __global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, 
                     cur = atomicCAS(&table[idx].key, EMPTY_KEY, key);
                     if (cur == EMPTY_KEY) { nk = 1; cur = key; }
                 }
-                if (cur == key) { atomicExch(&table[idx].count, vals[i]); break; }
+                if (cur == key) {
+                    atomicExch(&table[idx].count, vals[i]);
+                    if (set_vid) table[idx].vid = (unsigned int)i;
+                    break;
+                }
                 idx = next_slot(idx, cap);
             }
         }
@@ -341,6 +346,7 @@ int map_swap_table(Map *m, unsigned long long new_cap, Slot **old_table, unsigne
         GB_CUDA(cudaMalloc((void **)&nt, sizeof(Slot) * new_cap));
     }
     GB_TRY(init_table(nt, new_cap, m->stream));
+    m->kept_valid = false;
     *old_table = m->table;
     *old_alloc_cap = m->alloc_cap;
     m->table = nt;
@@ -405,10 +411,10 @@ int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n
     return GB_OK;
 }
 
-int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d_vals, int64_t n, cudaStream_t st)
+int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d_vals, int64_t n, cudaStream_t st, bool set_vid)
 {
     if (n <= 0) return GB_OK;
-    update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, m->d_counters);
+    update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, m->d_counters, set_vid);
     GB_LAUNCHED();
     return GB_OK;
 }
@@ -518,6 +524,7 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
                          const int64_t *h_win_prefix, int64_t *n_windows)
 {
     GB_TRY(map_zero_counters(m));
+    m->kept_valid = false;
     int64_t done = 0;
     int64_t total_ns = 0, part_windows = 0;
     m->phase_ns[0] = m->phase_ns[1] = m->phase_ns[2] = 0;
@@ -815,6 +822,7 @@ static int update_common(gb_map *h, const uint64_t *keys, const int32_t *vals, i
     for (int64_t i = 0; i < n; i++)
         if (keys[i] & ~kmask) { set_error("key %lld is longer than k = %d", (long long)i, m->k); return GB_E_K_RANGE; }
     m->noncanonical = true;
+    m->kept_valid = false;
     DeviceBuf dk, dv;
     GB_TRY(dk.alloc((size_t)n * 8, m->stream));
     GB_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, m->stream));
@@ -828,7 +836,7 @@ static int update_common(gb_map *h, const uint64_t *keys, const int32_t *vals, i
         GB_TRY(map_budget(m, n - done, &budget));
         int64_t take = std::min(n - done, std::max<int64_t>(budget, 1));
         GB_TRY(map_zero_counters(m));
-        if (set) GB_TRY(map_launch_update_set(m, (const unsigned long long *)dk.p + done, (const int *)dv.p + done, take, m->stream));
+        if (set) GB_TRY(map_launch_update_set(m, (const unsigned long long *)dk.p + done, (const int *)dv.p + done, take, m->stream, false));
         else GB_TRY(map_launch_update_counts(m, (const unsigned long long *)dk.p + done, take, m->stream));
         unsigned long long c[4];
         GB_TRY(map_read_counters(m, c));
@@ -878,7 +886,8 @@ int gb_map_delete_below(gb_map *h, int32_t min_count)
     unsigned long long n = m->cap;
     if (m->size == 0) return GB_OK;
     GB_TRY(map_zero_counters(m));
-    // survivors go to the staging buffer: keys first, counts behind them
+    // survivors go to the staging buffer (which a previous deleteAll's vertex array may occupy: it dies here)
+    m->kept_valid = false;
     GB_TRY(map_stage(m, (size_t)m->size + (size_t)(m->size + 1) / 2));
     unsigned long long *sk = m->stage;
     int *sv = reinterpret_cast<int *>(m->stage + m->size);
@@ -895,8 +904,13 @@ int gb_map_delete_below(gb_map *h, int32_t min_count)
     map_retire_table(m, old, old_alloc);
     m->grows++;
     GB_TRY(map_zero_counters(m));
-    GB_TRY(map_launch_update_set(m, sk, sv, keep, m->stream));
+    // survivors are distinct: their index in the compacted array becomes their vertex id (Graph.buildGraph skips numbering)
+    const bool as_vertices = keep < (1ll << 30);
+    GB_TRY(map_launch_update_set(m, sk, sv, keep, m->stream, as_vertices));
     m->size = keep;
+    m->kept_keys = sk;
+    m->kept_n = keep;
+    m->kept_valid = as_vertices;
     return GB_OK;
 }
 
@@ -940,6 +954,7 @@ int gb_map_clear(gb_map *h, int64_t min_capacity)
         GB_TRY(init_table(m->table, m->cap, m->stream));
     }
     m->size = 0;
+    m->kept_valid = false;
     m->noncanonical = false;
     m->windows = 0;
     return GB_OK;

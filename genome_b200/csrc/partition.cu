@@ -446,6 +446,7 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
                       int n_chunks, unsigned long long n_total, cudaStream_t st)
 {
     if (!n_total) return GB_OK;
+    m->kept_valid = false;
     if (!m->d_spread) {
         GB_CUDA(cudaMalloc((void **)&m->d_spread, SPREAD * 8));
         GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));

@@ -441,3 +441,32 @@ def test_cpp_host_driver(gpu, tmp_path):
     og.retain_largest()
     og.simplify()
     assert "Graph nodes: %d" % og.counts()[0] in r.stdout
+
+
+def test_build_twice_and_after_queries(gpu):
+    """Graph.buildGraph reuses the filter's vertex array: it must survive queries, a second build, a repeated deleteAll,
+    and be dropped by any mutation."""
+    k = 21
+    b, n, _ = H.small_reads(30000, 100, 20, 0.01, seed=808)
+    gm = FreqFilter.extractFilteredKmers(PairedEndData(b, n // 2), k, 3)
+    om, _ = H.oracle_counts(b, n, k)
+    om.delete_below(3)
+    og = pyoracle.OracleGraph(om)
+    g1 = Graph.buildGraph(k, gm)
+    H.assert_graph_equal(g1, og)
+    keys, _ = gm.export()
+    gm.lookup(keys[:1000])
+    gm.neighbour_masks(keys[:1000])
+    g2 = Graph.buildGraph(k, gm)
+    H.assert_graph_equal(g2, og)
+    gm.delete_below(3)  # removes nothing, but re-compacts the survivors in another order
+    g3 = Graph.buildGraph(k, gm)
+    H.assert_graph_equal(g3, og)
+    gm.delete_below(5)
+    om.delete_below(5)
+    H.assert_graph_equal(Graph.buildGraph(k, gm), pyoracle.OracleGraph(om))
+    extra = np.array([pyoracle.canonical(int(x) ^ 0x155, k) for x in keys[:50]], np.uint64)
+    gm.update_counts(extra)
+    for x in extra:
+        om.update1(int(x))
+    H.assert_graph_equal(Graph.buildGraph(k, gm), pyoracle.OracleGraph(om))
