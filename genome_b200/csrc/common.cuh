@@ -314,8 +314,12 @@ struct Map {
     int64_t size = 0;          // live keys (host mirror, exact after every call)
     int64_t grows = 0, windows = 0, last_insert_ns = 0, fixed_stride = 0;
     int64_t phase_ns[3] = { 0, 0, 0 }; // last partitioned insert: count, scatter, upsert (0 = direct path used)
-    struct PartWork *part = nullptr;   // workspace of the partitioned insert (partition.cuh)
-    cudaEvent_t pe[4] = { nullptr, nullptr, nullptr, nullptr };
+    struct PartWork *part = nullptr;   // workspaces of the partitioned insert (partition.cuh), one per staging half
+    struct PartWork *part2 = nullptr;
+    cudaEvent_t pe[4] = { nullptr, nullptr, nullptr, nullptr };   // bucket-stream begin/end, scratch
+    cudaEvent_t pready[2] = { nullptr, nullptr }, pfree[2] = { nullptr, nullptr }; // staging half filled / consumed
+    cudaEvent_t pup[16];               // upsert begin/end per sub-batch (timing)
+    int n_pup = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, t0 = nullptr, t1 = nullptr;
     // scratch

@@ -477,43 +477,94 @@ static int insert_mode()
     return 0;
 }
 
-// L2-blocked insert of reads [read0, read0 + n_reads): count, scatter into table-slice buckets, upsert slice by slice
+// L2-blocked insert of reads [read0, read0 + n_reads): bucket the canonical k-mers by table slice (count, scatter),
+// upsert slice by slice.  The range is cut into sub-batches and pipelined over two staging halves: the bucket pass of
+// sub-batch s + 1 (instruction bound, high-priority stream) overlaps the upsert of sub-batch s (L2 bound, map stream).
+// win_upper(r0, r1) = upper bound of the k-windows of reads [r0, r1).
+template <typename WinUpper>
 static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off, unsigned int rec,
-                              int64_t read0, int64_t n_reads, int64_t windows_upper, int64_t *windows_done)
+                              int64_t read0, int64_t n_reads, WinUpper win_upper, bool bound_is_exact)
 {
-    cudaStream_t st = m->stream;
+    cudaStream_t up = m->stream, bk = m->copy_stream;
     if (!m->part) m->part = new PartWork();
+    if (!m->part2) m->part2 = new PartWork();
     for (int i = 0; i < 4; i++)
         if (!m->pe[i]) GB_CUDA(cudaEventCreate(&m->pe[i]));
+    for (int i = 0; i < 2; i++) {
+        if (!m->pready[i]) GB_CUDA(cudaEventCreateWithFlags(&m->pready[i], cudaEventDisableTiming));
+        if (!m->pfree[i]) GB_CUDA(cudaEventCreateWithFlags(&m->pfree[i], cudaEventDisableTiming));
+    }
+    PartWork *work[2] = { m->part, m->part2 };
+    GB_TRY(work[0]->ensure(bk));
+    GB_TRY(work[1]->ensure(bk));
     PartLayout pl;
     pl.owners = 1;
     pl.lp_bits = slice_bits_for(m->cap, 1);
     if (const char *e = getenv("GENOME_B200_LP")) pl.lp_bits = std::max(0, std::min(pl.lp_bits + 3, atoi(e)));
-    ReadBatch rb;
-    rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = d_off; rb.rec_bytes = rec; rb.read0 = read0; rb.n_reads = n_reads;
-    GB_CUDA(cudaEventRecord(m->pe[0], st));
-    GB_TRY(part_count(rb, m->k, m->v210, pl, *m->part, st));
-    GB_CUDA(cudaEventRecord(m->pe[1], st));
-    GB_TRY(map_stage(m, (size_t)(windows_upper ? windows_upper : 1) + 8));
-    unsigned long long *keys = m->stage, *d_desc = m->stage + windows_upper; // chunk descriptor behind the keys
-    GB_TRY(part_scatter(rb, m->k, m->v210, pl, *m->part, keys, st));
-    GB_CUDA(cudaEventRecord(m->pe[2], st));
-    unsigned long long total = 0;
-    GB_CUDA(cudaMemcpyAsync(&total, m->part->bucket_base + pl.nb(), 8, cudaMemcpyDeviceToHost, st));
-    GB_CUDA(cudaStreamSynchronize(st));
-    if ((int64_t)total > windows_upper) { set_error("internal: %llu k-mers exceed the batch bound %lld", total, (long long)windows_upper); return GB_E_INVARIANT; }
-    // one chunk: the buckets are contiguous and already in slice order
-    unsigned long long desc[3] = { 0, total, 0 }; // vstart[0], vstart[1], off[0]
-    GB_CUDA(cudaMemcpyAsync(d_desc, desc, sizeof desc, cudaMemcpyHostToDevice, st));
-    GB_TRY(insert_key_chunks(m, keys, d_desc, d_desc + 2, 1, total, st));
-    GB_CUDA(cudaEventRecord(m->pe[3], st));
-    GB_CUDA(cudaStreamSynchronize(st));
-    for (int i = 0; i < 3; i++) {
-        float ms = 0;
-        GB_CUDA(cudaEventElapsedTime(&ms, m->pe[i], m->pe[i + 1]));
-        m->phase_ns[i] += (int64_t)(ms * 1e6);
+
+    // sub-batches of whole persistent-grid waves of tiles, about four of them
+    const int64_t tiles = (n_reads + TILE_READS - 1) / TILE_READS, grid = work[0]->grid;
+    // measured on C2 (one B200): 1 / 2 / 4 / 8 sub-batches = 2.95 / 3.13 / 3.20 / 3.93 ms -- on ONE GPU the two passes
+    // fight for the same SM slots and L2, so the default is no overlap; GENOME_B200_BATCHES turns the pipeline on
+    int want = 1;
+    if (const char *e = getenv("GENOME_B200_BATCHES")) want = std::max(1, atoi(e));
+    int64_t per_tiles = std::max<int64_t>(1, (tiles / want + grid / 2) / grid) * grid;
+    if (tiles < 2 * grid || want == 1) per_tiles = tiles;
+    const int64_t per_reads = per_tiles * TILE_READS;
+    const int64_t n_sub = (n_reads + per_reads - 1) / per_reads;
+    int64_t half = 0; // keys per staging half
+    for (int64_t s = 0; s < n_sub; s++) half = std::max(half, win_upper(read0 + s * per_reads, read0 + std::min(n_reads, (s + 1) * per_reads)));
+    GB_TRY(map_stage(m, (size_t)((n_sub > 1 ? 2 : 1) * (half + 8))));
+    if (n_sub == 1) bk = up; // nothing to overlap: one stream, no cross-stream events
+    // the bucket stream starts after everything already queued on the map's stream (clear, earlier inserts)
+    GB_CUDA(cudaEventRecord(m->pe[2], up));
+    if (bk != up) GB_CUDA(cudaStreamWaitEvent(bk, m->pe[2], 0));
+    GB_CUDA(cudaEventRecord(m->pe[0], bk));
+    m->n_pup = 0;
+    for (int64_t s = 0; s < n_sub; s++) {
+        const int h = (int)(s & 1);
+        const int64_t r0 = read0 + s * per_reads, nr = std::min(per_reads, read0 + n_reads - r0);
+        const int64_t wu = win_upper(r0, r0 + nr);
+        unsigned long long *keys = m->stage + (size_t)h * (half + 8), *d_desc = keys + half;
+        ReadBatch rb;
+        rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = d_off; rb.rec_bytes = rec; rb.read0 = r0; rb.n_reads = nr;
+        if (s >= 2) GB_CUDA(cudaStreamWaitEvent(bk, m->pfree[h], 0)); // the upsert of sub-batch s - 2 has consumed this half
+        GB_TRY(part_count(rb, m->k, m->v210, pl, *work[h], bk));
+        GB_TRY(part_scatter(rb, m->k, m->v210, pl, *work[h], keys, bk));
+        GB_TRY(make_single_chunk(work[h]->bucket_base + pl.nb(), d_desc, m->d_counters, bk));
+        if (bk != up) {
+            GB_CUDA(cudaEventRecord(m->pready[h], bk));
+            GB_CUDA(cudaStreamWaitEvent(up, m->pready[h], 0));
+        }
+        if (m->n_pup + 2 <= 16) {
+            for (int i = 0; i < 2; i++)
+                if (!m->pup[m->n_pup + i]) GB_CUDA(cudaEventCreate(&m->pup[m->n_pup + i]));
+            GB_CUDA(cudaEventRecord(m->pup[m->n_pup], up));
+        }
+        // the buckets are contiguous and already in slice order: one chunk; the launch is sized from the upper bound
+        unsigned long long total = (unsigned long long)wu;
+        if (!bound_is_exact) { // record lengths are only on the device: fetch the count (stalls the pipeline; rare path)
+            GB_CUDA(cudaMemcpyAsync(&total, work[h]->bucket_base + pl.nb(), 8, cudaMemcpyDeviceToHost, bk));
+            GB_CUDA(cudaStreamSynchronize(bk));
+        }
+        GB_TRY(insert_key_chunks(m, keys, d_desc, d_desc + 2, 1, total, up));
+        if (m->n_pup + 2 <= 16) {
+            GB_CUDA(cudaEventRecord(m->pup[m->n_pup + 1], up));
+            m->n_pup += 2;
+        }
+        GB_CUDA(cudaEventRecord(m->pfree[h], up));
     }
-    *windows_done = (int64_t)total;
+    if (bk != up) GB_CUDA(cudaEventRecord(m->pe[1], bk));
+    GB_CUDA(cudaStreamSynchronize(bk));
+    GB_CUDA(cudaStreamSynchronize(up));
+    float ms = 0;
+    // span of the bucket stream (one stream: up to the start of the upsert)
+    GB_CUDA(cudaEventElapsedTime(&ms, m->pe[0], bk != up ? m->pe[1] : m->pup[0]));
+    m->phase_ns[0] += (int64_t)(ms * 1e6);
+    for (int i = 0; i + 1 < m->n_pup; i += 2) {
+        GB_CUDA(cudaEventElapsedTime(&ms, m->pup[i], m->pup[i + 1]));
+        m->phase_ns[2] += (int64_t)(ms * 1e6);
+    }
     return GB_OK;
 }
 
@@ -526,7 +577,7 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
     GB_TRY(map_zero_counters(m));
     m->kept_valid = false;
     int64_t done = 0;
-    int64_t total_ns = 0, part_windows = 0;
+    int64_t total_ns = 0;
     m->phase_ns[0] = m->phase_ns[1] = m->phase_ns[2] = 0;
     while (done < n_reads) {
         // how many reads fit the budget (whole tiles)
@@ -557,17 +608,16 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
         const bool partitioned = mode == 2 || (mode == 0 && ((size_t)sizeof(Slot) * m->cap) > (96u << 20) && take_windows >= (1 << 20));
         GB_CUDA(cudaEventRecord(m->ev0, m->stream));
         if (partitioned) {
-            // bounded key staging: at most 2^28 k-mers (2 GiB) per pass
-            int64_t sub = take;
+            // bounded key staging: at most 2^28 k-mers (2 GiB) per call, pipelined inside
             const int64_t per_read = std::max<int64_t>(1, fixed ? win_per_read_max : (255 - m->k + 1));
             const int64_t max_reads = std::max<int64_t>(TILE_READS, (((int64_t)1 << 28) / per_read) / TILE_READS * TILE_READS);
-            for (int64_t o = 0; o < take; o += sub) {
-                sub = std::min(max_reads, take - o);
-                int64_t wu = fixed ? sub * win_per_read_max
-                                   : (h_win_prefix ? h_win_prefix[done + o + sub] - h_win_prefix[done + o] : sub * per_read);
-                int64_t wd = 0;
-                GB_TRY(insert_partitioned(m, d_bin, n_bytes, fixed ? nullptr : d_off, rec, done + o, sub, wu, &wd));
-                part_windows += wd;
+            auto win_upper = [&](int64_t r0, int64_t r1) -> int64_t {
+                if (fixed) return (r1 - r0) * win_per_read_max;
+                return h_win_prefix ? h_win_prefix[r1] - h_win_prefix[r0] : (r1 - r0) * per_read;
+            };
+            for (int64_t o = 0; o < take; o += max_reads) {
+                const int64_t sub = std::min(max_reads, take - o);
+                GB_TRY(insert_partitioned(m, d_bin, n_bytes, fixed ? nullptr : d_off, rec, done + o, sub, win_upper, fixed || h_win_prefix != nullptr));
             }
         } else if (fixed) {
             GB_TRY(launch_insert<true>(m, d_bin, n_bytes, nullptr, rec, done, take));
@@ -584,7 +634,6 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
     }
     unsigned long long c[4];
     GB_TRY(map_read_counters(m, c));
-    c[3] += (unsigned long long)part_windows; // the direct kernel counts its windows on the device
     m->windows += (int64_t)c[3];
     m->last_insert_ns = total_ns;
     if (n_windows) *n_windows = (int64_t)c[3];
@@ -679,6 +728,7 @@ int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_ma
     GB_CUDA(cudaSetDevice(device));
     GB_TRY(pool_setup(device));
     Map *m = new Map();
+    memset(m->pup, 0, sizeof m->pup);
     m->k = k;
     m->device = device;
     m->v210 = (flags & GB_FLAG_HASH_SCALA_210) != 0;
@@ -686,7 +736,11 @@ int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_ma
     int r = GB_OK;
     do {
         if ((r = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
-        if ((r = cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
+        {   // the bucket pass of the pipelined insert runs here: its CTAs go first when SM slots free up under the upsert grid
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            if ((r = cudaStreamCreateWithPriority(&m->copy_stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
+        }
         if ((r = cudaEventCreate(&m->ev0) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
         if ((r = cudaEventCreate(&m->ev1) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
         if ((r = cudaEventCreate(&m->t0) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
@@ -729,6 +783,13 @@ int gb_map_destroy(gb_map *h)
     for (int i = 0; i < 4; i++)
         if (m->pe[i]) cudaEventDestroy(m->pe[i]);
     if (m->part) { m->part->release(); delete m->part; }
+    if (m->part2) { m->part2->release(); delete m->part2; }
+    for (int i = 0; i < 2; i++) {
+        if (m->pready[i]) cudaEventDestroy(m->pready[i]);
+        if (m->pfree[i]) cudaEventDestroy(m->pfree[i]);
+    }
+    for (int i = 0; i < 16; i++)
+        if (m->pup[i]) cudaEventDestroy(m->pup[i]);
     if (m->t0) cudaEventDestroy(m->t0);
     if (m->t1) cudaEventDestroy(m->t1);
     if (m->stream) cudaStreamDestroy(m->stream);

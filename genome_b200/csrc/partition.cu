@@ -442,6 +442,21 @@ int part_scatter_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, un
     return GB_OK;
 }
 
+__global__ void make_desc_kernel(const unsigned long long *total, unsigned long long *desc, unsigned long long *counters)
+{
+    desc[0] = 0;      // vstart[0]
+    desc[1] = *total; // vstart[1]
+    desc[2] = 0;      // off[0]
+    atomicAdd(&counters[3], *total);
+}
+
+int make_single_chunk(const unsigned long long *d_total, unsigned long long *d_desc, unsigned long long *d_counters, cudaStream_t st)
+{
+    make_desc_kernel<<<1, 1, 0, st>>>(d_total, d_desc, d_counters);
+    GB_LAUNCHED();
+    return GB_OK;
+}
+
 int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned long long *d_vstart, const unsigned long long *d_off,
                       int n_chunks, unsigned long long n_total, cudaStream_t st)
 {

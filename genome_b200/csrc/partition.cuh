@@ -75,4 +75,7 @@ int part_scatter_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, un
 int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned long long *d_vstart, const unsigned long long *d_off,
                       int n_chunks, unsigned long long n_total, cudaStream_t st);
 
+// desc = { 0, *d_total, 0 } (the chunk table of ONE contiguous range) and counters[3] += *d_total, all on the stream
+int make_single_chunk(const unsigned long long *d_total, unsigned long long *d_desc, unsigned long long *d_counters, cudaStream_t st);
+
 } // namespace gb
