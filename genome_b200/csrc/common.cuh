@@ -143,10 +143,29 @@ __device__ __forceinline__ void red_add_s32(int *p, int v)
     asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// probe for `key`; returns slot index or -1
-__device__ __forceinline__ long long probe_find(const Slot *table, unsigned long long cap, unsigned long long key, Slot *out)
+// one-byte fingerprint of a key (never 0: 0 marks an empty slot in the fingerprint array)
+GB_HD unsigned int fp_tag(unsigned long long h) { return (unsigned int)((h >> 20) & 0xFF) | 1u; }
+
+// probe for `key`; returns slot index or -1.  With `fp` (one byte per slot, 0 = empty, else fp_tag of the resident key;
+// 1/16 of the table, L2-resident) the probe walks the fingerprints and touches the table only on a tag match: a
+// negative probe -- 3 of 4 in Graph.buildGraph -- costs no DRAM access.
+__device__ __forceinline__ long long probe_find(const Slot *table, unsigned long long cap, unsigned long long key, Slot *out,
+                                                const uint8_t *fp = nullptr)
 {
-    unsigned long long i = slot_of(mix64(key), cap);
+    const unsigned long long h = mix64(key);
+    unsigned long long i = slot_of(h, cap);
+    if (fp) {
+        const unsigned int tag = fp_tag(h);
+        for (;;) {
+            const unsigned int t = fp[i];
+            if (t == 0) return -1;
+            if (t == tag) {
+                Slot s = load_slot(table + i);
+                if (s.key == key) { *out = s; return (long long)i; }
+            }
+            i = next_slot(i, cap);
+        }
+    }
     for (;;) { // the table is never full (map_budget), so an EMPTY slot always ends the probe
         Slot s = load_slot(table + i);
         if (s.key == key) { *out = s; return (long long)i; }
@@ -163,19 +182,19 @@ __device__ __forceinline__ long long probe_find(const Slot *table, unsigned long
 // On success *slot is the primary stored slot and *strand = 1 when that stored key is rc(q) != q.
 template <bool V210>
 __device__ __forceinline__ bool find_oriented(const Slot *table, unsigned long long cap, int k, bool dual,
-                                              unsigned long long q, Slot *slot, unsigned int *strand)
+                                              unsigned long long q, Slot *slot, unsigned int *strand, const uint8_t *fp = nullptr)
 {
     unsigned long long r = revcomp(q, k);
     int hq = scala_hash<V210>(q), hr = scala_hash<V210>(r);
     if (!dual && hq != hr) {
         unsigned long long c = hq < hr ? q : r;
-        if (probe_find(table, cap, c, slot) < 0) return false;
+        if (probe_find(table, cap, c, slot, fp) < 0) return false;
         *strand = c != q;
         return true;
     }
     Slot sq, sr;
-    bool fq = probe_find(table, cap, q, &sq) >= 0;
-    bool fr = r != q && probe_find(table, cap, r, &sr) >= 0;
+    bool fq = probe_find(table, cap, q, &sq, fp) >= 0;
+    bool fr = r != q && probe_find(table, cap, r, &sr, fp) >= 0;
     if (!fq && !fr) return false;
     bool use_r = fr && (!fq || r < q);
     *slot = use_r ? sr : sq;
@@ -185,13 +204,14 @@ __device__ __forceinline__ bool find_oriented(const Slot *table, unsigned long l
 
 // a stored key is SECONDARY (no vertex of its own) when rc(key) is stored too and is numerically smaller
 template <bool V210>
-__device__ __forceinline__ bool is_secondary(const Slot *table, unsigned long long cap, int k, bool dual, unsigned long long key)
+__device__ __forceinline__ bool is_secondary(const Slot *table, unsigned long long cap, int k, bool dual, unsigned long long key,
+                                             const uint8_t *fp = nullptr)
 {
     unsigned long long r = revcomp(key, k);
     if (r >= key) return false;
     if (!dual && scala_hash<V210>(key) != scala_hash<V210>(r)) return false;
     Slot s;
-    return probe_find(table, cap, r, &s) >= 0;
+    return probe_find(table, cap, r, &s, fp) >= 0;
 }
 #endif
 
@@ -333,6 +353,8 @@ struct Map {
     const unsigned long long *kept_keys = nullptr;
     int64_t kept_n = 0;
     bool kept_valid = false;
+    uint8_t *fp = nullptr;     // fingerprint per slot, valid together with kept_valid (probe_find)
+    unsigned long long fp_cap = 0;
     Map *replica = nullptr;    // sharded maps: the all-gathered copy Graph.buildGraph runs on (comm.cu)
     Arena arena;
 };

@@ -143,16 +143,66 @@ assign_vertices_kernel(Slot *table, unsigned long long cap, int k, bool dual, co
 template <bool V210>
 __global__ void __launch_bounds__(256)
 masks_kernel(const Slot *table, unsigned long long cap, int k, bool dual, const unsigned long long *keys, unsigned long long lo,
-             unsigned long long n, bool check_secondary, uint8_t *mask8, unsigned int *nbr_out, unsigned int *nbr_in)
+             unsigned long long n, bool check_secondary, const uint8_t *fp, uint8_t *mask8, unsigned int *nbr_out, unsigned int *nbr_in)
 {
     unsigned long long v = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= lo + n) return;
     const unsigned long long x = keys[v];
     unsigned int out = 0, in = 0, so = NONE32, si = NONE32;
-    if (check_secondary && is_secondary<V210>(table, cap, k, dual, x)) {
+    if (check_secondary && is_secondary<V210>(table, cap, k, dual, x, fp)) {
         mask8[v] = 0;
         nbr_out[v] = NONE32;
         nbr_in[v] = NONE32;
+        return;
+    }
+    if (fp) {
+        // all 8 home fingerprints are fetched before the first one is looked at (they are L2 hits; 2 of 3 homes are
+        // empty at load 1/3, which settles most negative probes at once); only tag matches go to the table
+        unsigned long long cq[8], hm[8];
+        unsigned int tg[8], st[8], t0[8];
+        bool simple[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const unsigned long long q = j < 4 ? kmer_append(x, k, j) : kmer_prepend(x, k, j - 4);
+            const unsigned long long r = revcomp(q, k);
+            const int hq = scala_hash<V210>(q), hr = scala_hash<V210>(r);
+            simple[j] = !dual && hq != hr; // one stored orientation possible: the canonical one
+            cq[j] = hq < hr ? q : r;
+            st[j] = cq[j] != q;
+            const unsigned long long h = mix64(cq[j]);
+            hm[j] = slot_of(h, cap);
+            tg[j] = fp_tag(h);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) t0[j] = fp[hm[j]];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            Slot s;
+            unsigned int strand = st[j];
+            bool found = false;
+            if (!simple[j]) {
+                const unsigned long long q = j < 4 ? kmer_append(x, k, j) : kmer_prepend(x, k, j - 4);
+                found = find_oriented<V210>(table, cap, k, dual, q, &s, &strand, fp);
+            } else {
+                unsigned long long i = hm[j];
+                unsigned int t = t0[j];
+                while (t != 0) {
+                    if (t == tg[j]) {
+                        s = load_slot(table + i);
+                        if (s.key == cq[j]) { found = true; break; }
+                    }
+                    i = next_slot(i, cap);
+                    t = fp[i];
+                }
+            }
+            if (found) {
+                if (j < 4) { out |= 1u << j; so = 2 * s.vid + strand; }
+                else { in |= 1u << (j - 4); si = 2 * s.vid + strand; }
+            }
+        }
+        mask8[v] = (uint8_t)(out | (in << 4));
+        nbr_out[v] = so;
+        nbr_in[v] = si;
         return;
     }
 #pragma unroll
@@ -808,7 +858,9 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
     {
         // sharded build: this rank probes only its own range of the (identical) key array, then the ranks exchange ranges
         const unsigned long long lo = sp ? sp->lo : 0, cnt = sp ? sp->hi - sp->lo : n;
-        LAUNCH(masks_kernel<V210>, cnt, m->table, bits, k, dual, keys.p, lo, cnt, given, mask8.p, nbr_out.p, nbr_in.p);
+        // the fingerprint array is built together with the vertex array (deleteAll / replica insert)
+        const uint8_t *fp = given && !getenv("GENOME_B200_NO_FP") ? m->fp : nullptr;
+        LAUNCH(masks_kernel<V210>, cnt, m->table, bits, k, dual, keys.p, lo, cnt, given, fp, mask8.p, nbr_out.p, nbr_in.p);
         if (sp) {
             GB_CUDA(cudaStreamSynchronize(st));
             GB_TRY(sp->gather(sp->ctx, mask8.p, 1));

@@ -181,13 +181,15 @@ __global__ void verify_fixed_kernel(const uint8_t *__restrict__ bin, unsigned in
 // SET: update(key, v); set_vid: additionally slot.vid = the key's index in `keys` (keys must be distinct then)
 template <bool SET>
 __global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ vals,
-                                   long long n, Slot *table, unsigned long long cap, unsigned long long *counters, bool set_vid = false)
+                                   long long n, Slot *table, unsigned long long cap, unsigned long long *counters, bool set_vid = false,
+                                   uint8_t *fp = nullptr)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int nk = 0;
     if (i < n) {
         unsigned long long key = keys[i];
-        unsigned long long idx = slot_of(mix64(key), cap);
+        const unsigned long long h = mix64(key);
+        unsigned long long idx = slot_of(h, cap);
         if (!SET) {
             nk = upsert_add(table, cap, idx, load_key(table + idx), key, 1);
         } else {
@@ -200,6 +202,7 @@ __global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, 
                 if (cur == key) {
                     atomicExch(&table[idx].count, vals[i]);
                     if (set_vid) table[idx].vid = (unsigned int)i;
+                    if (fp) fp[idx] = (uint8_t)fp_tag(h);
                     break;
                 }
                 idx = next_slot(idx, cap);
@@ -411,10 +414,23 @@ int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n
     return GB_OK;
 }
 
+// set_vid: the table is EMPTY and the keys distinct; their index becomes the slot's vid and the fingerprint array is built
 int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d_vals, int64_t n, cudaStream_t st, bool set_vid)
 {
+    uint8_t *fp = nullptr;
+    if (set_vid) {
+        if (m->fp_cap < m->cap) {
+            if (m->fp) { GB_CUDA(cudaStreamSynchronize(st)); GB_CUDA(cudaFree(m->fp)); }
+            m->fp = nullptr;
+            m->fp_cap = 0;
+            GB_CUDA(cudaMalloc((void **)&m->fp, m->cap + m->cap / 8 + 1024));
+            m->fp_cap = m->cap + m->cap / 8 + 1024;
+        }
+        GB_CUDA(cudaMemsetAsync(m->fp, 0, m->cap, st));
+        fp = m->fp;
+    }
     if (n <= 0) return GB_OK;
-    update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, m->d_counters, set_vid);
+    update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, m->d_counters, set_vid, fp);
     GB_LAUNCHED();
     return GB_OK;
 }
@@ -773,6 +789,7 @@ int gb_map_destroy(gb_map *h)
     if (m->table) cudaFree(m->table);
     if (m->spare) cudaFree(m->spare);
     if (m->stage) cudaFree(m->stage);
+    if (m->fp) cudaFree(m->fp);
     m->arena.destroy();
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->d_counters) cudaFree(m->d_counters);
