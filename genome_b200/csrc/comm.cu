@@ -730,6 +730,10 @@ int gb_pmap_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, 
 // filtered table on every rank, and the single-GPU build runs on the replica (identical result on every rank).
 int gb_pmap_graph_build(gb_map *h, gb_graph **out)
 {
+    const bool trace = getenv("GENOME_B200_TRACE") != nullptr;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now_ms();
+    auto tick = [&](const char *what) { if (trace) fprintf(stderr, "[pgraph] %-26s %9.3f ms\n", what, now_ms() - t_begin); };
     Map *m;
     GB_TRY(check_pmap(h, &m));
     ArenaScope scope(&m->arena);
@@ -752,6 +756,7 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
     unsigned long long t = 0;
     for (int p = 0; p < P; p++) { offs[p] = t; t += sizes[p]; }
 
+    tick("sizes exchanged");
     // every shard exports straight into its segment of the gathered arrays
     DeviceBuf all_keys, all_vals;
     GB_TRY(all_keys.alloc((size_t)t * 8));
@@ -766,6 +771,7 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
     GB_NCCL(ncclGroupEnd());
     GB_CUDA(cudaStreamSynchronize(c->stream));
 
+    tick("keys gathered");
     // the replica map is kept with the shard and reused by the next build (its table is GBs: no malloc per call)
     gb_map *rh = reinterpret_cast<gb_map *>(m->replica);
     if (!rh) {
@@ -785,6 +791,7 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
     if (rc == GB_OK) rc = map_read_counters(r, cn);
     if (rc != GB_OK) return rc;
     r->size = (int64_t)cn[0];
+    tick("replica filled");
     if (!as_vertices) return gb_graph_build(rh, out);
     r->kept_keys = (const unsigned long long *)all_keys.p;
     r->kept_n = (int64_t)t;
@@ -808,6 +815,7 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
         return GB_OK;
     };
     rc = graph_build_sharded(rh, out, &sp);
+    tick("graph built");
     r->kept_valid = false; // all_keys goes back to the arena with this call
     return rc;
 }
