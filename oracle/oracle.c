@@ -785,6 +785,33 @@ int64_t go_graph_clip_tips(go_graph *g, int64_t max_len)
     return removed;
 }
 
+/* Graph.getGraphMap (S/data/graph/Graph.scala:90-119): the k-mer -> GraphPosition multimap as a list of putNew calls in
+ * the reference's order (nodes, then edges; ids = this oracle's ids).  Entry i: kmer[i] (oriented, NOT canonicalised),
+ * id[i] = node id with dist[i] = 0 (NodeGraphPosition) or edge id with dist[i] >= 1 (EdgeGraphPosition(edgeId, dist)).
+ * Returns the number of entries (= sum of edge lengths + nodes - edges, line 97); fills at most cap of them. */
+int64_t go_graph_map(const go_graph *g, uint64_t *kmer, int64_t *id, int32_t *dist, int64_t cap)
+{
+    int64_t n = 0;
+    for (int64_t i = 0; i < g->nn; i++) {
+        if (!g->nodes[i].alive) continue;
+        if (n < cap) { kmer[n] = g->nodes[i].kmer; id[n] = i + 1; dist[n] = 0; }
+        n++;
+    }
+    for (int64_t e = 0; e < g->ne; e++) {
+        const edge_t *ed = &g->edges[e];
+        if (!ed->alive) continue;
+        uint64_t seq = go_append(g->nodes[ed->start - 1].kmer, g->k, ed->seq[0]); /* edge.start.seq.drop(1) :+ start */
+        int32_t d = 1;
+        for (int64_t j = 1; j < ed->len; j++) { /* for (base <- edge.seq.tail) */
+            if (n < cap) { kmer[n] = seq; id[n] = e + 1; dist[n] = d; }
+            n++;
+            seq = go_append(seq, g->k, ed->seq[j]);
+            d++;
+        }
+    }
+    return n;
+}
+
 /* invariants asserted at S/scripts/GraphSimplifier.scala:159-170 */
 int go_graph_check(const go_graph *g)
 {

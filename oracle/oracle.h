@@ -72,6 +72,8 @@ void      go_graph_remove_bubbles(go_graph *g);                  /* Graph.remove
 int64_t   go_graph_remove_edges(go_graph *g, const int64_t *edge_ids, int64_t n); /* removeEdge 191-195 */
 /* EXTENSION (no reference semantics): one sweep of dead-end tip removal, see DESIGN.md */
 int64_t   go_graph_clip_tips(go_graph *g, int64_t max_len);
+/* Graph.getGraphMap 90-119 as the list of putNew(kmer, position) calls; dist 0 = NodeGraphPosition(id) */
+int64_t   go_graph_map(const go_graph *g, uint64_t *kmer, int64_t *id, int32_t *dist, int64_t cap);
 /* invariants of S/scripts/GraphSimplifier.scala:159-170; 0 = ok */
 int       go_graph_check(const go_graph *g);
 

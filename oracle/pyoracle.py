@@ -59,6 +59,7 @@ def lib():
         "go_graph_remove_edges": (i64, [vp, vp, i64]),
         "go_graph_clip_tips": (i64, [vp, i64]),
         "go_graph_check": (C.c_int, [vp]),
+        "go_graph_map": (i64, [vp, vp, vp, vp, i64]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -199,3 +200,12 @@ class OracleGraph:
 
     def check(self):
         return lib().go_graph_check(self.h)
+
+    def graph_map(self):
+        """Graph.getGraphMap (Graph.scala:90-119): (kmer, id, dist) arrays, dist 0 = node position."""
+        n = lib().go_graph_map(self.h, None, None, None, 0)
+        kmer = np.empty(n, np.uint64)
+        ident = np.empty(n, np.int64)
+        dist = np.empty(n, np.int32)
+        lib().go_graph_map(self.h, _ptr(kmer), _ptr(ident), _ptr(dist), n)
+        return kmer, ident, dist

@@ -1,0 +1,91 @@
+"""Host-side formats and the oracle's getGraphMap restatement (row 3): CPU only."""
+import numpy as np
+
+from genome_b200 import formats, synth
+from oracle import pyoracle
+from tests import helpers as H
+
+
+def fastq(pairs, n):
+    lines = []
+    for i, (a, b) in enumerate(pairs):
+        lines += ["@r%d" % i, a + b, "+", "I" * (len(a) + len(b))]
+    return [l + "\n" for l in lines]
+
+
+def test_convert2bin_follows_the_reference():
+    n, k = 36, 23
+    rng = np.random.default_rng(0)
+    rd = lambda m: "".join("AGCT"[c] for c in rng.integers(0, 4, size=m))
+    pairs = [(rd(36), rd(36)), (rd(20) + "N" + rd(15), rd(36)), (rd(36), "N" + rd(35)), (rd(36), rd(30))]
+    b, count, kmers, short = formats.convert2bin(fastq(pairs, n), n, k)
+    assert count == 4
+    reads = formats.read_bin(b, 8)
+    # takeWhile: cut at the first non-base; lower case is not a base either
+    assert [len(r) for r in reads] == [36, 36, 20, 36, 36, 0, 36, 30]
+    assert synth.decode(reads[2]) == pairs[1][0][:20]
+    assert synth.decode(reads[7]) == pairs[3][1]
+    assert kmers == sum(max(0, len(r) - k + 1) for r in reads)
+    assert short == 2  # the pairs with a read shorter than k: (20, 36) and (36, 0)
+    assert b.size == sum(1 + (len(r) + 3) // 4 for r in reads)
+    # the stream feeds the counting path unchanged
+    assert pyoracle.count_windows(b, 8, k) == kmers
+    # truncated input: a record without its quality line is dropped
+    b2, count2, _, _ = formats.convert2bin(fastq(pairs, n)[:-1], n, k)
+    assert count2 == 3 and np.array_equal(b2, b[:b2.size])
+    assert formats.convert2bin([], n, k)[1] == 0
+
+
+def test_read_bin_roundtrip_and_truncation():
+    rng = np.random.default_rng(1)
+    reads = [rng.integers(0, 4, size=int(m), dtype=np.uint8) for m in [0, 1, 4, 5, 100, 255]]
+    b = synth.pack_ragged(reads)
+    back = formats.read_bin(b, len(reads))
+    assert all(np.array_equal(x, y) for x, y in zip(back, reads))
+    try:
+        formats.read_bin(b[:-1], len(reads))
+        assert False
+    except ValueError:
+        pass
+
+
+def test_contigs_file(tmp_path):
+    p = tmp_path / "contigs"
+    formats.write_contigs([synth.encode("ACGT"), synth.encode("GG")], str(p))
+    assert p.read_text() == "ACGT\n>abacaba0\nGG\n>abacaba1\n"
+
+
+def test_graph_map_restatement():
+    """Graph.getGraphMap (Graph.scala:90-119): nodes + interior edge k-mers, each oriented k-mer exactly once; CheckGraph's
+    invariant (CheckGraph.scala:48-55): every k-mer of the genome that survived the filter is a key, in read orientation."""
+    k = 15
+    b, n, genome = H.small_reads(6000, 60, 30, 0.01, seed=12)
+    m, _ = H.oracle_counts(b, n, k)
+    m.delete_below(2)
+    g = pyoracle.OracleGraph(m)
+    kmer, ident, dist = g.graph_map()
+    nn, ne, nb = g.counts()
+    assert kmer.size == nb + nn - ne            # `total`, Graph.scala:97
+    assert len(set(kmer.tolist())) == kmer.size  # putNew never collides here: every oriented k-mer has one position
+    assert int((dist == 0).sum()) == nn
+    # positions are consistent with the edges: the k-mer at (edge, dist) is the window of start + seq that ends at seq[dist - 1]
+    node_kmer, node_id, es, ee, off, bases = g.export()
+    by_id = {int(i): int(x) for i, x in zip(node_id, node_kmer)}
+    # oracle edge ids: position among all edges ever created + 1; a fresh graph has none removed
+    for e in range(0, es.size, max(1, es.size // 50)):
+        s = synth.int_to_kmer(by_id[int(es[e])], k) + synth.decode(bases[int(off[e]):int(off[e + 1])])
+        sel = (ident == e + 1) & (dist > 0)
+        assert int(sel.sum()) == int(off[e + 1] - off[e]) - 1  # one entry per interior k-mer of the edge
+        for km, d in zip(kmer[sel].tolist(), dist[sel].tolist()):
+            assert synth.int_to_kmer(km, k) == s[d:d + k]
+    keys = set(kmer.tolist())
+    gs = synth.decode(genome)
+    found = missing = 0
+    for i in range(len(gs) - k + 1):
+        x = synth.kmer_to_int(gs[i:i + k])
+        if m.contains(x) or m.contains(pyoracle.revcomp(x, k)):
+            if x in keys:
+                found += 1
+            else:
+                missing += 1  # only isolated (0,0) k-mers and perfect cycles are absent (Graph.scala:375)
+    assert found > 0 and missing <= 0.001 * found
