@@ -1,13 +1,17 @@
-// comm.cu -- PartitionedDNAMap on one 8xB200 box: one hash shard per GPU (one rank = one process = one GPU),
-// k-mers routed to their owner shard by an NCCL all-to-all over NVLink.
+// comm.cu -- PartitionedDNAMap on one 8xB200 box: one hash shard per GPU (one rank = one process = one GPU).
 // Replaces S/ds/PartitionedDNAMap.scala:15-63 (paths relative to /root/reference).
 //
-// Insert pipeline per batch of reads (all ranks in lock step, same number of batches):
-//   route_count  : extract canonical k-mers, histogram by owner                      (stream `route`)
-//   route_scatter: re-extract, write every k-mer into its owner's segment of `send`  (stream `route`)
-//   all-to-all   : counts (P x u64), then grouped ncclSend/ncclRecv of the segments  (stream `route`)
-//   insert       : update(key, 1, _ + 1) for every received key                      (the map's stream)
-// Two buffer sets: batch b+1 is routed and exchanged while batch b is inserted.
+// Sharded insert, per batch of reads (all ranks in lock step, same number of batches), see pmap_insert:
+//   communicator stream (high priority):
+//     part_count                : canonical k-mers of the batch, histogram by (owner, table slice)      [partition.cu]
+//     part_scatter_kernel<PEER> : every k-mer is stored straight into its owner's NVLink inbox through the peer
+//                                 mapping (CUDA IPC) -- the all-to-all happens inside the bucket pass
+//     counts all-to-all (NCCL)  : tiny; travels after the keys on the sender's stream, so it doubles as "data ready"
+//   map stream:
+//     [two-level routing only: re-bucket the received keys by fine table slice]
+//     insert_keys_kernel        : update(key, 1, _ + 1) for the received keys, slice by slice (L2-blocked)
+// Three inbox/buffer sets; batch b + 1 is bucketed and exchanged while batch b is upserted.
+// GENOME_B200_A2A=nccl replaces the peer stores by staged ncclSend/ncclRecv segments (the baseline).
 #include <dlfcn.h>
 #include <time.h>
 #include <nccl.h> // types only: the library is bound at run time (see NcclApi)

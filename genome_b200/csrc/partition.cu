@@ -2,11 +2,11 @@
 //
 // A k-mer table far larger than the 126 MB L2 turns FreqFilter.add (S/data/FreqFilter.scala:28-36, paths relative
 // to /root/reference) into one random DRAM access per k-mer instance, and every miss moves a whole 128-byte line
-// (ncu, profiles/r1a: 138 B of DRAM reads per k-mer).  Instead:
+// (ncu, profiles/insert_r1a_ncu_full_summary.csv: 138 B of DRAM reads per k-mer).  Instead:
 //   1. part_count / part_scatter stream the read batch twice and write every canonical k-mer (8 B) into the bucket
 //      of the table SLICE it hashes to -- sequential traffic;
 //   2. insert_key_chunks walks the buckets in slice order, so the CTAs that are resident at any moment all update
-//      the same 32 MiB slice of the table, which lives in L2; DRAM sees each slice once in and once out.
+//      the same <= 64 MiB slice of the table, which lives in L2; DRAM sees each slice once in and once out.
 // The same buckets, with an owner-shard prefix, are what the sharded map sends over NVLink (comm.cu).
 #include "partition.cuh"
 
@@ -139,7 +139,7 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
 {
     __shared__ ReadTile tile;
     extern __shared__ unsigned int s_dyn[];
-    // layout: bcur [nb] | rcnt [WARPS][nb] | bstart [nb + 1] | sdst [ROUND_KEYS] u32 | skey [ROUND_KEYS] u64   (the last three STAGED only)
+    // layout: bcur [nb] | rcnt [WARPS][nb] | bstart [nb + 2] | sdst [ROUND_KEYS] u32 | skey [ROUND_KEYS] u64
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned int *bcur = s_dyn;
     unsigned int *rcnt = s_dyn + nb + (size_t)warp * nb;
