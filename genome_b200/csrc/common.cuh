@@ -340,13 +340,12 @@ struct Map {
     cudaEvent_t pready[2] = { nullptr, nullptr }, pfree[2] = { nullptr, nullptr }; // staging half filled / consumed
     cudaEvent_t pup[16];               // upsert begin/end per sub-batch (timing)
     int n_pup = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr;      // every mutating call is asynchronous on this stream
+    cudaStream_t copy_stream = nullptr; // high priority: the bucket pass of an overlapped (sub-batched) insert
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, t0 = nullptr, t1 = nullptr;
     // scratch
-    unsigned long long *d_counters = nullptr; // [0] new keys [1] overflow count [2] flags [3] windows
+    unsigned long long *d_counters = nullptr; // [0] new keys [1] survivors / exported [2] stream flags [3] k-windows
     unsigned long long *d_spread = nullptr;   // spread new-key tallies of insert_keys_kernel (partition.cu)
-    unsigned long long *d_overflow = nullptr; // overflow keys (cap overflow_cap)
-    int64_t overflow_cap = 0;
     Comm *comm = nullptr;
     // after deleteAll (or in a replica): the stored keys as one device array whose index IS the vertex id written in
     // the slots, so Graph.buildGraph needs no numbering pass.  Any mutation invalidates it.
@@ -359,7 +358,6 @@ struct Map {
     Arena arena;
 };
 
-int map_reserve(Map *m, int64_t want_keys);
 
 // sharded Graph.buildGraph: this rank computes the membership masks of vertices [lo, hi) only; gather(ctx, base, elem)
 // makes every rank's range of the device array `base` (elem bytes per vertex) visible on all ranks

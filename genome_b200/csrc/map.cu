@@ -435,13 +435,6 @@ int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d
     return GB_OK;
 }
 
-int map_reserve(Map *m, int64_t want_keys)
-{
-    unsigned long long nc = cap_for(want_keys);
-    if (nc > m->cap) return map_rebuild(m, nc, false, 0);
-    return GB_OK;
-}
-
 int map_read_counters(Map *m, unsigned long long out[4])
 {
     GB_CUDA(cudaMemcpyAsync(out, m->d_counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, m->stream));
@@ -793,7 +786,6 @@ int gb_map_destroy(gb_map *h)
     m->arena.destroy();
     if (m->stream) cudaStreamSynchronize(m->stream);
     if (m->d_counters) cudaFree(m->d_counters);
-    if (m->d_overflow) cudaFree(m->d_overflow);
     if (m->d_spread) cudaFree(m->d_spread);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
