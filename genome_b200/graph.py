@@ -87,6 +87,18 @@ class MapGraph:
     def check(self):
         capi.check(capi.lib().gb_graph_check(self.h))
 
+    def getGraphMap(self):
+        """Graph.getGraphMap (90-119) as arrays: (kmer u64[n], id u32[n], dist u32[n]); dist 0 = NodeGraphPosition(id),
+        dist >= 1 = EdgeGraphPosition(id, dist).  EXPERIMENTAL (csrc/graphmap.cu)."""
+        n = C.c_int64()
+        capi.check(capi.lib().gb_graph_positions(self.h, None, None, None, 0, C.byref(n)))
+        kmer = np.empty(n.value, np.uint64)
+        ident = np.empty(n.value, np.uint32)
+        dist = np.empty(n.value, np.uint32)
+        if n.value:
+            capi.check(capi.lib().gb_graph_positions(self.h, capi.ptr(kmer), capi.ptr(ident), capi.ptr(dist), n.value, C.byref(n)))
+        return kmer, ident, dist
+
     def stats(self):
         s = (C.c_int64 * 8)()
         capi.check(capi.lib().gb_graph_stats(self.h, s))
