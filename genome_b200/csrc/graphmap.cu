@@ -1,7 +1,8 @@
 // graphmap.cu -- Graph.getGraphMap (S/data/graph/Graph.scala:90-119, relative to /root/reference) as a bulk export:
 // the (k-mer, GraphPosition) pairs the reference feeds to putNew, nodes first, then the interior k-mers of every edge.
-// SURVEY 8(f) row 3.  EXPERIMENTAL: written at the end of round 1 without GPU time left to run it; its parity test
-// (tests/test_graphmap_gpu.py) only runs with GENOME_B200_EXPERIMENTAL=1 until it has been validated on a B200.
+// SURVEY 8(f) row 3.  Parity with the oracle's go_graph_map: tests/test_graphmap_gpu.py.  The DNAMap[GraphPosition] the
+// reference builds from these pairs (putNew / getAll) is the caller's: every oriented k-mer occurs once, so an
+// ArrayDNAMap with value = entry index serves as that multimap.
 #include "common.cuh"
 #include "graph_types.cuh"
 

@@ -89,7 +89,7 @@ class MapGraph:
 
     def getGraphMap(self):
         """Graph.getGraphMap (90-119) as arrays: (kmer u64[n], id u32[n], dist u32[n]); dist 0 = NodeGraphPosition(id),
-        dist >= 1 = EdgeGraphPosition(id, dist).  EXPERIMENTAL (csrc/graphmap.cu)."""
+        dist >= 1 = EdgeGraphPosition(id, dist)."""
         n = C.c_int64()
         capi.check(capi.lib().gb_graph_positions(self.h, None, None, None, 0, C.byref(n)))
         kmer = np.empty(n.value, np.uint64)

@@ -138,7 +138,7 @@ int gb_graph_check(gb_graph *g);
 /* Graph.getGraphMap (Graph.scala:90-119) as a bulk export: the (k-mer, GraphPosition) pairs the reference feeds to putNew.
  * Entry i: kmers[i] oriented as in the graph (not canonicalised); dists[i] == 0: NodeGraphPosition(node ids[i]);
  * dists[i] >= 1: EdgeGraphPosition(edge ids[i], dists[i]).  *n = nodes + edge bases - edges (line 97).  Call with all three
- * arrays NULL to get *n only.  EXPERIMENTAL in round 1 (see csrc/graphmap.cu). */
+ * arrays NULL to get *n only. */
 int gb_graph_positions(gb_graph *g, uint64_t *kmers, uint32_t *ids, uint32_t *dists, int64_t cap, int64_t *n);
 /* counters of the build: [0] stored k-mers seen [1] pointer-jumping launches [2] oriented k-mers on perfect
  * cycles, dropped like the reference does (Graph.scala:375) [3] build time in ns (CUDA events) */

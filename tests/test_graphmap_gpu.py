@@ -1,8 +1,4 @@
-"""Graph.getGraphMap on the device against the oracle's restatement.  EXPERIMENTAL: the kernel was
-written after round 1's GPU time had run out, so this test only runs with GENOME_B200_EXPERIMENTAL=1 until it has been
-seen green on a B200."""
-import os
-
+"""Graph.getGraphMap on the device against the oracle's restatement (Graph.scala:90-119)."""
 import numpy as np
 import pytest
 
@@ -11,7 +7,7 @@ from genome_b200.graph import Graph
 from oracle import pyoracle
 from tests import helpers as H
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("GENOME_B200_EXPERIMENTAL"), reason="experimental, not yet validated on a GPU")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("k,glen,rl,cov,err,rounds", [(31, 20000, 100, 30, 0.01, 3), (15, 5000, 60, 30, 0.01, 2), (8, 1500, 40, 10, 0.0, 1), (4, 120, 20, 6, 0.0, 1)])
