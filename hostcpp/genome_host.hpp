@@ -71,6 +71,19 @@ class MapGraph {
         check(gb_graph_components(g_, label.data(), &nc));
         return nc;
     }
+    // Graph.getGraphMap (90-119): the (k-mer, GraphPosition) pairs fed to putNew; dist 0 = NodeGraphPosition(id)
+    struct Position { uint64_t kmer; uint32_t id; uint32_t dist; };
+    std::vector<Position> getGraphMap() const
+    {
+        int64_t n = 0;
+        check(gb_graph_positions(g_, nullptr, nullptr, nullptr, 0, &n));
+        std::vector<uint64_t> k((size_t)n);
+        std::vector<uint32_t> id((size_t)n), d((size_t)n);
+        if (n) check(gb_graph_positions(g_, k.data(), id.data(), d.data(), n, &n));
+        std::vector<Position> out((size_t)n);
+        for (size_t i = 0; i < (size_t)n; i++) out[i] = { k[i], id[i], d[i] };
+        return out;
+    }
     void retainLargest() { check(gb_graph_retain_largest(g_)); }   // GraphBuilder.scala:52-54
     void simplifyGraph() { check(gb_graph_simplify(g_)); }          // Graph.scala:211-230
     void removeBubbles() { check(gb_graph_remove_bubbles(g_)); }    // Graph.scala:125-149

@@ -38,6 +38,7 @@ int main(int argc, char **argv)
         graph.retainLargest();
         graph.simplifyGraph();
         std::printf("Graph nodes: %zu\n", graph.getNodes().size());
+        std::printf("Node map: %zu\n", graph.getGraphMap().size()); // Graph.scala:117: nodeMap.size
     } catch (const genome::Error &e) {
         std::fprintf(stderr, "genome_b200 error %d: %s\n", e.code, e.what());
         return 1;

@@ -441,6 +441,7 @@ def test_cpp_host_driver(gpu, tmp_path):
     og.retain_largest()
     og.simplify()
     assert "Graph nodes: %d" % og.counts()[0] in r.stdout
+    assert "Node map: %d" % og.graph_map()[0].size in r.stdout
 
 
 def test_build_twice_and_after_queries(gpu):
