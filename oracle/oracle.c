@@ -839,3 +839,337 @@ int go_graph_check(const go_graph *g)
     }
     return 0;
 }
+
+/* ================================================================================================
+ * Paired-end path support: S/scripts/GraphSimplifier.scala
+ *   WalkingActor.reachable 43-72, WalkingActor.receive 77-126, annotate 192-206, the pair loop 213-248,
+ *   the per-node in x out matrix and node splitting 268-317.
+ * ============================================================================================== */
+
+/* int64 -> int64 open-addressing map (keys >= 0), the stand-in for the Scala mutable.Map / Set instances below */
+typedef struct { int64_t *k, *v; int64_t cap, n; } imap;
+static void imap_init(imap *m, int64_t cap) { m->cap = cap; m->n = 0; m->k = (int64_t *)malloc((size_t)cap * 8); m->v = (int64_t *)malloc((size_t)cap * 8); memset(m->k, 0xFF, (size_t)cap * 8); }
+static void imap_free(imap *m) { free(m->k); free(m->v); m->k = m->v = NULL; }
+static int64_t imap_slot(const imap *m, int64_t key)
+{
+    uint64_t h = (uint64_t)key * 0x9E3779B97F4A7C15ULL;
+    int64_t i = (int64_t)((h >> 20) & (uint64_t)(m->cap - 1));
+    while (m->k[i] != -1 && m->k[i] != key) i = (i + 1) & (m->cap - 1);
+    return i;
+}
+static int64_t *imap_get(const imap *m, int64_t key) { int64_t i = imap_slot(m, key); return m->k[i] == key ? &m->v[i] : NULL; }
+static void imap_put(imap *m, int64_t key, int64_t val)
+{
+    if ((m->n + 1) * 2 > m->cap) {
+        imap o = *m;
+        imap_init(m, o.cap * 2);
+        for (int64_t i = 0; i < o.cap; i++) if (o.k[i] != -1) imap_put(m, o.k[i], o.v[i]);
+        imap_free(&o);
+    }
+    int64_t i = imap_slot(m, key);
+    if (m->k[i] != key) { m->k[i] = key; m->n++; }
+    m->v[i] = val;
+}
+
+/* WalkingActor.reachable (43-72): Dijkstra from `node` BACKWARDS over in-edges, distances <= range.last; the result maps
+ * node id -> smallest distance.  (The LinkedHashMap cache of 41,66-69 only saves recomputation and is not restated.) */
+typedef struct { int64_t dist, node; } heap_item;
+static void reachable(const go_graph *g, int64_t node, int hi, imap *set)
+{
+    int64_t hn = 0, hc = 64;
+    heap_item *heap = (heap_item *)malloc((size_t)hc * sizeof *heap);
+    heap[hn++] = (heap_item){ 0, node };
+    while (hn) {
+        heap_item top = heap[0]; /* PriorityQueue with the reversed ordering of 47-51: smallest distance first */
+        heap[0] = heap[--hn];
+        for (int64_t i = 0;;) {
+            int64_t l = 2 * i + 1, r = l + 1, s = i;
+            if (l < hn && heap[l].dist < heap[s].dist) s = l;
+            if (r < hn && heap[r].dist < heap[s].dist) s = r;
+            if (s == i) break;
+            heap_item t = heap[i]; heap[i] = heap[s]; heap[s] = t; i = s;
+        }
+        if (imap_get(set, top.node)) continue;
+        imap_put(set, top.node, top.dist);
+        const node_t *u = &g->nodes[top.node - 1];
+        for (int j = 0; j < u->nin; j++) {
+            const edge_t *e = &g->edges[u->in[j] - 1];
+            int64_t d2 = top.dist + e->len;
+            if (d2 <= hi) {
+                if (hn == hc) { hc *= 2; heap = (heap_item *)realloc(heap, (size_t)hc * sizeof *heap); }
+                int64_t i = hn++;
+                heap[i] = (heap_item){ d2, e->start };
+                while (i && heap[(i - 1) / 2].dist > heap[i].dist) {
+                    heap_item t = heap[i]; heap[i] = heap[(i - 1) / 2]; heap[(i - 1) / 2] = t; i = (i - 1) / 2;
+                }
+            }
+        }
+    }
+    free(heap);
+}
+
+typedef struct {
+    const go_graph *g;
+    int lo, hi;
+    int64_t node2, dist2, end_edge; /* end_edge 0 = null */
+    imap reach, memo, *path_edges;
+} walk_ctx;
+
+static int64_t pair_key(const go_graph *g, int64_t e1, int64_t e2) { return e1 * (g->ne + 1) + e2; }
+
+/* the nested dfs of WalkingActor.receive (91-113); prev_edge 0 = null */
+static int walk_dfs(walk_ctx *c, int64_t node1, int64_t dist1, int64_t prev_edge)
+{
+    const go_graph *g = c->g;
+    /* memo keys are only ever created below the prune test, i.e. with dist1 <= hi */
+    int64_t mkey = dist1 <= c->hi ? prev_edge * (c->hi + 1) + dist1 : -1;
+    if (mkey >= 0) { int64_t *m = imap_get(&c->memo, mkey); if (m) return (int)*m; }
+    int64_t *r = imap_get(&c->reach, node1);
+    if (dist1 + c->dist2 + (r ? *r : c->hi + 1) > c->hi) return 0;
+    int cur = 0;
+    if (node1 == c->node2 && c->lo <= dist1 + c->dist2 && dist1 + c->dist2 <= c->hi) {
+        if (prev_edge && c->end_edge) imap_put(c->path_edges, pair_key(g, prev_edge, c->end_edge), 1);
+        cur = 1;
+    }
+    const node_t *nd = &g->nodes[node1 - 1];
+    for (int b = 0; b < 4; b++) {
+        int64_t eid = nd->out[b];
+        if (!eid) continue;
+        const edge_t *e = &g->edges[eid - 1];
+        int res = walk_dfs(c, e->end, dist1 + e->len, eid);
+        if (res && prev_edge) imap_put(c->path_edges, pair_key(g, prev_edge, eid), 1);
+        cur |= res;
+    }
+    imap_put(&c->memo, mkey, cur);
+    return cur;
+}
+
+/* WalkingActor.receive for one (pos1, pos2) (77-126).  A position is (id, dist): dist == 0 -> NodeGraphPosition(id),
+ * dist >= 1 -> EdgeGraphPosition(id, dist).  path_edges receives the (prevEdge.id, edge.id) pairs; returns `good`. */
+static int walk_positions(const go_graph *g, int64_t id1, int32_t d1, int64_t id2, int32_t d2, int lo, int hi, imap *path_edges)
+{
+    walk_ctx c;
+    c.g = g; c.lo = lo; c.hi = hi; c.path_edges = path_edges;
+    if (d2 == 0) { c.node2 = id2; c.dist2 = 0; c.end_edge = 0; }
+    else { c.node2 = g->edges[id2 - 1].start; c.dist2 = d2; c.end_edge = id2; }
+    int64_t start_edge = d1 == 0 ? 0 : id1;
+    imap_init(&c.reach, 64);
+    imap_init(&c.memo, 64);
+    reachable(g, c.node2, hi, &c.reach);
+    int64_t node0, dist0;
+    if (d1 == 0) { node0 = id1; dist0 = 0; }
+    else { node0 = g->edges[id1 - 1].end; dist0 = g->edges[id1 - 1].len - d1; }
+    int good = walk_dfs(&c, node0, dist0, start_edge);
+    imap_free(&c.reach);
+    imap_free(&c.memo);
+    return good;
+}
+
+int go_walk(const go_graph *g, int64_t id1, int32_t dist1, int64_t id2, int32_t dist2, int lo, int hi,
+            int64_t *pairs, int64_t cap, int64_t *n_pairs)
+{
+    imap pe;
+    imap_init(&pe, 64);
+    int good = walk_positions(g, id1, dist1, id2, dist2, lo, hi, &pe);
+    int64_t n = 0;
+    for (int64_t i = 0; i < pe.cap; i++) if (pe.k[i] != -1) {
+        if (n < cap) { pairs[2 * n] = pe.k[i] / (g->ne + 1); pairs[2 * n + 1] = pe.k[i] % (g->ne + 1); }
+        n++;
+    }
+    imap_free(&pe);
+    if (n_pairs) *n_pairs = n;
+    return good;
+}
+
+/* the graphMap of 188 as a sorted multimap: getAll(key) = every entry whose k-mer equals key (ArrayDNAMap.getAll 103-113) */
+typedef struct { uint64_t kmer; int64_t id; int32_t dist; } gm_entry;
+static int gm_cmp(const void *a, const void *b)
+{
+    const gm_entry *x = (const gm_entry *)a, *y = (const gm_entry *)b;
+    return x->kmer < y->kmer ? -1 : x->kmer > y->kmer;
+}
+static int64_t gm_get_all(const gm_entry *gm, int64_t n, uint64_t key, const gm_entry **first)
+{
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { int64_t mid = (lo + hi) / 2; if (gm[mid].kmer < key) lo = mid + 1; else hi = mid; }
+    int64_t c = 0;
+    while (lo + c < n && gm[lo + c].kmer == key) c++;
+    *first = gm + lo;
+    return c;
+}
+
+/* annotate (192-206): the pair is dropped when some edge position of the first list and some edge position of the second
+ * lie on the same edge with range.contains((dist2 - dist1) + k) */
+static int annotate_drops(const gm_entry *p1, int64_t n1, const gm_entry *p2, int64_t n2, int k, int lo, int hi)
+{
+    for (int64_t i = 0; i < n1; i++) {
+        if (p1[i].dist == 0) continue;
+        for (int64_t j = 0; j < n2; j++) {
+            if (p2[j].dist == 0) continue;
+            int64_t d = (int64_t)p2[j].dist - p1[i].dist + k;
+            if (p1[i].id == p2[j].id && lo <= d && d <= hi) return 1;
+        }
+    }
+    return 0;
+}
+
+static int pe_cmp(const void *a, const void *b)
+{
+    const int64_t *x = (const int64_t *)a, *y = (const int64_t *)b;
+    return x[0] < y[0] ? -1 : x[0] > y[0];
+}
+
+/* the pair loop of GraphSimplifier.startup (188-263) over the first n_pairs pairs of a `.bin` stream: pathsMap as (e1, e2, count)
+ * triples sorted by (e1, e2); *bad_pairs = badPairs (259-261); *walked = orientation cases that survived annotate with both
+ * position lists non-empty.  Returns the number of triples (fills at most cap), -1 on a truncated stream. */
+int64_t go_pair_support(const go_graph *g, const uint8_t *bin, size_t n_bytes, int64_t n_pairs, int lo, int hi,
+                        int64_t *e1, int64_t *e2, int32_t *cnt, int64_t cap, int64_t *bad_pairs, int64_t *walked)
+{
+    const int k = g->k;
+    int64_t gn = go_graph_map(g, NULL, NULL, NULL, 0);
+    uint64_t *gk = (uint64_t *)malloc((size_t)(gn ? gn : 1) * 8);
+    int64_t *gi = (int64_t *)malloc((size_t)(gn ? gn : 1) * 8);
+    int32_t *gd = (int32_t *)malloc((size_t)(gn ? gn : 1) * 4);
+    go_graph_map(g, gk, gi, gd, gn);
+    gm_entry *gm = (gm_entry *)malloc((size_t)(gn ? gn : 1) * sizeof *gm);
+    for (int64_t i = 0; i < gn; i++) gm[i] = (gm_entry){ gk[i], gi[i], gd[i] };
+    free(gk); free(gi); free(gd);
+    qsort(gm, (size_t)gn, sizeof *gm, gm_cmp);
+
+    imap paths; /* pathsMap: (e1, e2) -> count */
+    imap_init(&paths, 1024);
+    int64_t bad = 0, nwalked = 0;
+    size_t pos = 0;
+    for (int64_t p = 0; p < n_pairs; p++) {
+        uint64_t first[2] = { 0, 0 };
+        int len[2];
+        for (int r = 0; r < 2; r++) { /* PairedEndData.getPairs.read (20-36) */
+            if (pos >= n_bytes) { imap_free(&paths); free(gm); return -1; }
+            len[r] = bin[pos];
+            size_t nxt = pos + 1 + (size_t)(len[r] + 3) / 4;
+            if (nxt > n_bytes) { imap_free(&paths); free(gm); return -1; }
+            if (len[r] >= k)
+                for (int i = 0; i < k; i++) first[r] |= (uint64_t)read_base(bin + pos + 1, i) << (2 * i); /* p.take(k) */
+            pos = nxt;
+        }
+        if (len[0] < k || len[1] < k) continue; /* 213 */
+        /* f1..f4 (214-217) and the two orientation cases of 219 */
+        const uint64_t q1[2] = { first[0], first[1] }, q2[2] = { go_revcomp(first[1], k), go_revcomp(first[0], k) };
+        for (int c = 0; c < 2; c++) {
+            const gm_entry *p1, *p2;
+            int64_t n1 = gm_get_all(gm, gn, q1[c], &p1), n2 = gm_get_all(gm, gn, q2[c], &p2);
+            if (annotate_drops(p1, n1, p2, n2, k, lo, hi)) continue;
+            if (n1 == 0 || n2 == 0) continue; /* no futures: `if !list.isEmpty` (238) */
+            nwalked++;
+            imap pe;
+            imap_init(&pe, 64);
+            int good = 0;
+            for (int64_t i = 0; i < n1; i++)
+                for (int64_t j = 0; j < n2; j++)
+                    good |= walk_positions(g, p1[i].id, p1[i].dist, p2[j].id, p2[j].dist, lo, hi, &pe);
+            for (int64_t i = 0; i < pe.cap; i++) if (pe.k[i] != -1) { /* pathEdgesList.reduce(_ ++ _), one increment per pair of edges */
+                int64_t *v = imap_get(&paths, pe.k[i]);
+                imap_put(&paths, pe.k[i], v ? *v + 1 : 1);
+            }
+            if (!good) bad++;
+            imap_free(&pe);
+        }
+    }
+    int64_t n = paths.n;
+    int64_t *kv = (int64_t *)malloc((size_t)(n ? n : 1) * 16);
+    int64_t j = 0;
+    for (int64_t i = 0; i < paths.cap; i++) if (paths.k[i] != -1) { kv[2 * j] = paths.k[i]; kv[2 * j + 1] = paths.v[i]; j++; }
+    qsort(kv, (size_t)n, 16, pe_cmp);
+    for (int64_t i = 0; i < n && i < cap; i++) {
+        e1[i] = kv[2 * i] / (g->ne + 1); e2[i] = kv[2 * i] % (g->ne + 1); cnt[i] = (int32_t)kv[2 * i + 1];
+    }
+    free(kv); free(gm); imap_free(&paths);
+    if (bad_pairs) *bad_pairs = bad;
+    if (walked) *walked = nwalked;
+    return n;
+}
+
+/* MapGraph.replaceStart / replaceEnd (Graph.scala:197-209): the edge keeps its id */
+static void graph_replace_start(go_graph *g, int64_t eid, int64_t new_start)
+{
+    edge_t *e = &g->edges[eid - 1];
+    g->nodes[e->start - 1].out[e->seq[0]] = 0;
+    e->start = new_start;
+    g->nodes[new_start - 1].out[e->seq[0]] = eid;
+}
+static void graph_replace_end(go_graph *g, int64_t eid, int64_t new_end)
+{
+    edge_t *e = &g->edges[eid - 1];
+    node_in_del(&g->nodes[e->end - 1], eid);
+    e->end = new_end;
+    node_in_add(&g->nodes[new_end - 1], eid);
+}
+
+typedef struct { int nin, nout; int m[4][4]; int cutoff; int col_left[4], col_right[4]; } split_ctx;
+static void split_dfs_right(split_ctx *s, int j, int *l, int *r);
+static void split_dfs_left(split_ctx *s, int i, int *l, int *r) /* dfsLeft 281-291; l, r = bit sets */
+{
+    s->col_left[i] = 1;
+    *l |= 1 << i;
+    for (int j = 0; j < s->nout; j++) if (!s->col_right[j] && s->m[i][j] >= s->cutoff) split_dfs_right(s, j, l, r);
+}
+static void split_dfs_right(split_ctx *s, int j, int *l, int *r) /* dfsRight 292-302 */
+{
+    s->col_right[j] = 1;
+    *r |= 1 << j;
+    for (int i = 0; i < s->nin; i++) if (!s->col_left[i] && s->m[i][j] >= s->cutoff) split_dfs_left(s, i, l, r);
+}
+
+/* GraphSimplifier.startup 266-317 without the final simplifyGraph: for every node with in- and out-edges, the matrix
+ * m(i)(j) = pathsMap(in(i), out(j)), the connected components of the bipartite graph {m >= cutoff}; a component with
+ * out-edges moves to a fresh copy of the node (addNode(node.seq), replaceEnd, replaceStart), an in-edge alone in its
+ * component and every out-edge no component reached are removed.  The sweep covers the nodes present at the call
+ * (the reference iterates a ConcurrentHashMap while adding to it; a copy that does get visited is one component again and
+ * only moves once more, leaving an empty node for simplifyGraph -- same graph).  Returns the number of edges removed. */
+int64_t go_graph_split(go_graph *g, const int64_t *e1, const int64_t *e2, const int32_t *cnt, int64_t n, int32_t cutoff,
+                       int64_t *nodes_added)
+{
+    imap paths;
+    imap_init(&paths, 1024);
+    for (int64_t i = 0; i < n; i++) imap_put(&paths, pair_key(g, e1[i], e2[i]), cnt[i]);
+    int64_t nn0 = g->nn, added = 0, n_rm = 0, c_rm = 64;
+    int64_t *to_remove = (int64_t *)malloc((size_t)c_rm * 8);
+#define TO_REMOVE(id) do { if (n_rm == c_rm) { c_rm *= 2; to_remove = (int64_t *)realloc(to_remove, (size_t)c_rm * 8); } to_remove[n_rm++] = (id); } while (0)
+    for (int64_t v = 0; v < nn0; v++) {
+        if (!g->nodes[v].alive) continue;
+        int64_t in[4], out[4];
+        split_ctx s;
+        memset(&s, 0, sizeof s);
+        s.cutoff = cutoff;
+        if (g->nodes[v].nin > 4) { fprintf(stderr, "oracle: node with more than 4 in-edges\n"); abort(); }
+        for (int j = 0; j < g->nodes[v].nin; j++) in[s.nin++] = g->nodes[v].in[j];
+        for (int b = 0; b < 4; b++) if (g->nodes[v].out[b]) out[s.nout++] = g->nodes[v].out[b];
+        if (s.nin == 0 || s.nout == 0) continue;
+        for (int i = 0; i < s.nin; i++)
+            for (int j = 0; j < s.nout; j++) {
+                int64_t *c = imap_get(&paths, pair_key(g, in[i], out[j]));
+                s.m[i][j] = c ? (int)*c : 0;
+            }
+        for (int i = 0; i < s.nin; i++) {
+            if (s.col_left[i]) continue;
+            int l = 0, r = 0;
+            split_dfs_left(&s, i, &l, &r);
+            if (r == 0) {
+                TO_REMOVE(in[i]);
+            } else {
+                int64_t nid = graph_add_node(g, g->nodes[v].kmer);
+                added++;
+                for (int a = 0; a < s.nin; a++) if (l >> a & 1) graph_replace_end(g, in[a], nid);
+                for (int a = 0; a < s.nout; a++) if (r >> a & 1) graph_replace_start(g, out[a], nid);
+            }
+        }
+        for (int j = 0; j < s.nout; j++) if (!s.col_right[j]) TO_REMOVE(out[j]);
+    }
+#undef TO_REMOVE
+    int64_t removed = 0;
+    for (int64_t i = 0; i < n_rm; i++) if (g->edges[to_remove[i] - 1].alive) { graph_remove_edge(g, to_remove[i]); removed++; }
+    free(to_remove);
+    imap_free(&paths);
+    if (nodes_added) *nodes_added = added;
+    return removed;
+}

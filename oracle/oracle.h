@@ -77,6 +77,20 @@ int64_t   go_graph_map(const go_graph *g, uint64_t *kmer, int64_t *id, int32_t *
 /* invariants of S/scripts/GraphSimplifier.scala:159-170; 0 = ok */
 int       go_graph_check(const go_graph *g);
 
+/* ---- paired-end path support (S/scripts/GraphSimplifier.scala:33-127,188-317) ----
+ * A graph position is (id, dist): dist == 0 -> NodeGraphPosition(id), dist >= 1 -> EdgeGraphPosition(id, dist). */
+/* WalkingActor.receive (77-126) for one (pos1, pos2) and range lo..hi: returns `good`, writes the pathEdges set as
+ * (prevEdge.id, edge.id) pairs (at most cap of them), *n_pairs = size of the set */
+int       go_walk(const go_graph *g, int64_t id1, int32_t dist1, int64_t id2, int32_t dist2, int lo, int hi,
+                  int64_t *pairs, int64_t cap, int64_t *n_pairs);
+/* the pair loop (188-263) over the first n_pairs pairs of a `.bin` stream: pathsMap as (e1, e2, count) sorted by (e1, e2);
+ * returns the number of triples (fills at most cap), -1 on a truncated stream */
+int64_t   go_pair_support(const go_graph *g, const uint8_t *bin, size_t n_bytes, int64_t n_pairs, int lo, int hi,
+                          int64_t *e1, int64_t *e2, int32_t *cnt, int64_t cap, int64_t *bad_pairs, int64_t *walked);
+/* the in x out matrices, node splitting and edge removal of 266-317 (simplifyGraph excluded); returns edges removed */
+int64_t   go_graph_split(go_graph *g, const int64_t *e1, const int64_t *e2, const int32_t *cnt, int64_t n, int32_t cutoff,
+                         int64_t *nodes_added);
+
 #ifdef __cplusplus
 }
 #endif

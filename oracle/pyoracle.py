@@ -60,6 +60,9 @@ def lib():
         "go_graph_clip_tips": (i64, [vp, i64]),
         "go_graph_check": (C.c_int, [vp]),
         "go_graph_map": (i64, [vp, vp, vp, vp, i64]),
+        "go_walk": (C.c_int, [vp, i64, i32, i64, i32, C.c_int, C.c_int, vp, i64, C.POINTER(i64)]),
+        "go_pair_support": (i64, [vp, vp, C.c_size_t, i64, C.c_int, C.c_int, vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i64)]),
+        "go_graph_split": (i64, [vp, vp, vp, vp, i64, i32, C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -209,3 +212,33 @@ class OracleGraph:
         dist = np.empty(n, np.int32)
         lib().go_graph_map(self.h, _ptr(kmer), _ptr(ident), _ptr(dist), n)
         return kmer, ident, dist
+
+    def walk(self, pos1, pos2, lo, hi):
+        """WalkingActor.receive (GraphSimplifier.scala:77-126) for positions (id, dist): (good, sorted [(e1, e2)])."""
+        n = C.c_int64()
+        good = lib().go_walk(self.h, pos1[0], pos1[1], pos2[0], pos2[1], lo, hi, None, 0, C.byref(n))
+        pairs = np.empty(2 * n.value, np.int64)
+        lib().go_walk(self.h, pos1[0], pos1[1], pos2[0], pos2[1], lo, hi, _ptr(pairs), n.value, C.byref(n))
+        return bool(good), sorted((int(pairs[2 * i]), int(pairs[2 * i + 1])) for i in range(n.value))
+
+    def pair_support(self, bin_bytes, n_pairs, lo, hi):
+        """The pair loop of GraphSimplifier.startup (188-263): (e1 ids, e2 ids, counts, badPairs, walked cases)."""
+        buf = np.ascontiguousarray(bin_bytes, dtype=np.uint8)
+        bad, walked = C.c_int64(), C.c_int64()
+        n = lib().go_pair_support(self.h, _ptr(buf), buf.size, n_pairs, lo, hi, None, None, None, 0, C.byref(bad), C.byref(walked))
+        if n < 0:
+            raise ValueError("truncated .bin stream")
+        e1 = np.empty(n, np.int64)
+        e2 = np.empty(n, np.int64)
+        cnt = np.empty(n, np.int32)
+        lib().go_pair_support(self.h, _ptr(buf), buf.size, n_pairs, lo, hi, _ptr(e1), _ptr(e2), _ptr(cnt), n, C.byref(bad), C.byref(walked))
+        return e1, e2, cnt, bad.value, walked.value
+
+    def split(self, e1, e2, cnt, cutoff):
+        """GraphSimplifier.startup 266-317 without simplifyGraph: (edges removed, nodes added)."""
+        e1 = np.ascontiguousarray(e1, np.int64)
+        e2 = np.ascontiguousarray(e2, np.int64)
+        cnt = np.ascontiguousarray(cnt, np.int32)
+        added = C.c_int64()
+        removed = lib().go_graph_split(self.h, _ptr(e1), _ptr(e2), _ptr(cnt), e1.size, cutoff, C.byref(added))
+        return removed, added.value
