@@ -1026,6 +1026,21 @@ static int components(Graph *g, Tmp<unsigned int> &parent)
     return GB_OK;
 }
 
+__global__ void drop_flagged_kernel(const unsigned int *flag, unsigned long long n_edges, unsigned int *head)
+{
+    unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_edges && flag[e]) head[e] = NONE32;
+}
+
+int graph_remove_flagged(Graph *g, const unsigned int *d_flag)
+{
+    cudaStream_t st = g->stream;
+    RewriteBufs rb;
+    GB_TRY(rb.init(g));
+    LAUNCH(drop_flagged_kernel, g->n_edges, d_flag, (unsigned long long)g->n_edges, rb.rw.head);
+    return apply_rewrite(g, rb.rw);
+}
+
 int graph_build_sharded(gb_map *h, gb_graph **out, const ShardPlan *sp)
 {
     Map *m;

@@ -19,4 +19,9 @@ struct Graph {
     int64_t stats[8] = { 0, 0, 0, 0, 0, 0, 0, 0 }; // [0] kept k-mers [1] jump rounds [2] cycle vertices dropped [3] build ns
 };
 
+// Graph.getGraphMap entries into DEVICE arrays of n_nodes + n_bases - n_edges elements, on g->stream (graphmap.cu)
+int graph_positions_device(Graph *g, unsigned long long *d_kmer, unsigned int *d_id, unsigned int *d_dist);
+// removeEdge for every edge e with d_flag[e] != 0 (graph.cu); the caller holds an ArenaScope on g->arena
+int graph_remove_flagged(Graph *g, const unsigned int *d_flag);
+
 } // namespace gb

@@ -59,6 +59,23 @@ __global__ void edge_positions_kernel(const unsigned long long *node_kmer, const
     dist[out] = (unsigned int)d;
 }
 
+int graph_positions_device(Graph *g, unsigned long long *d_kmer, unsigned int *d_id, unsigned int *d_dist)
+{
+    cudaStream_t st = g->stream;
+    if (g->n_nodes) {
+        node_positions_kernel<<<(unsigned int)((g->n_nodes + 255) / 256), 256, 0, st>>>(g->node_kmer, (unsigned long long)g->n_nodes,
+                                                                                      d_kmer, d_id, d_dist);
+        GB_LAUNCHED();
+    }
+    if (g->n_bases) {
+        edge_positions_kernel<<<(unsigned int)((g->n_bases + 255) / 256), 256, 0, st>>>(
+            g->node_kmer, g->edge_start, g->edge_off, g->bases, (unsigned long long)g->n_edges, (unsigned long long)g->n_bases,
+            (unsigned long long)g->n_nodes, g->k, d_kmer, d_id, d_dist);
+        GB_LAUNCHED();
+    }
+    return GB_OK;
+}
+
 } // namespace gb
 
 using namespace gb;
@@ -79,17 +96,7 @@ extern "C" int gb_graph_positions(gb_graph *h, uint64_t *kmers, uint32_t *ids, u
     GB_TRY(dk.alloc((size_t)n * 8));
     GB_TRY(di.alloc((size_t)n * 4));
     GB_TRY(dd.alloc((size_t)n * 4));
-    if (g->n_nodes) {
-        node_positions_kernel<<<(unsigned int)((g->n_nodes + 255) / 256), 256, 0, st>>>(g->node_kmer, (unsigned long long)g->n_nodes,
-                                                                                      (unsigned long long *)dk.p, (unsigned int *)di.p, (unsigned int *)dd.p);
-        GB_LAUNCHED();
-    }
-    if (g->n_bases) {
-        edge_positions_kernel<<<(unsigned int)((g->n_bases + 255) / 256), 256, 0, st>>>(
-            g->node_kmer, g->edge_start, g->edge_off, g->bases, (unsigned long long)g->n_edges, (unsigned long long)g->n_bases,
-            (unsigned long long)g->n_nodes, g->k, (unsigned long long *)dk.p, (unsigned int *)di.p, (unsigned int *)dd.p);
-        GB_LAUNCHED();
-    }
+    GB_TRY(graph_positions_device(g, (unsigned long long *)dk.p, (unsigned int *)di.p, (unsigned int *)dd.p));
     if (kmers) GB_CUDA(cudaMemcpyAsync(kmers, dk.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     if (ids) GB_CUDA(cudaMemcpyAsync(ids, di.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (dists) GB_CUDA(cudaMemcpyAsync(dists, dd.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

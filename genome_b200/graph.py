@@ -99,6 +99,30 @@ class MapGraph:
             capi.check(capi.lib().gb_graph_positions(self.h, capi.ptr(kmer), capi.ptr(ident), capi.ptr(dist), n.value, C.byref(n)))
         return kmer, ident, dist
 
+    def pairSupport(self, data, takeFirst=None, range_=(180, 250)):
+        """The pair loop of GraphSimplifier.startup (S/scripts/GraphSimplifier.scala:188-263): graphMap.getAll of the first
+        k-mers of both reads in both orientations, annotate, and the WalkingActor walks (33-127), for the first `takeFirst`
+        pairs of `data` (a PairedEndData).  Returns (support uint32[n_edges, 4], badPairs, walked cases) with
+        support[e1, b] = pathsMap((e1, e2)), e2 = the out-edge of e1's end node starting with base b; `range_` is the
+        reference's `180 to 250` (153)."""
+        n_pairs = data.count if takeFirst is None else min(int(takeFirst), data.count)
+        ne = self.counts()[1]
+        support = np.zeros((ne, 4), np.uint32)
+        bad, walked = C.c_int64(), C.c_int64()
+        capi.check(capi.lib().gb_graph_pair_support(self.h, capi.ptr(data.bin), data.bin.size, n_pairs, int(range_[0]), int(range_[1]),
+                                                    capi.ptr(support), C.byref(bad), C.byref(walked)))
+        return support, bad.value, walked.value
+
+    def splitNodes(self, support, cutoff):
+        """The node sweep of GraphSimplifier.startup (268-316): in x out matrices thresholded at `cutoff`, one node copy per
+        supported component, unsupported edges removed.  Returns (edges removed, nodes added); call simplifyGraph next (318)."""
+        support = np.ascontiguousarray(support, dtype=np.uint32)
+        if support.size != 4 * self.counts()[1]:
+            raise ValueError("support must have 4 entries per edge of the current graph")
+        removed, added = C.c_int64(), C.c_int64()
+        capi.check(capi.lib().gb_graph_split_nodes(self.h, capi.ptr(support), int(cutoff), C.byref(removed), C.byref(added)))
+        return removed.value, added.value
+
     def stats(self):
         s = (C.c_int64 * 8)()
         capi.check(capi.lib().gb_graph_stats(self.h, s))

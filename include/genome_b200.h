@@ -140,6 +140,20 @@ int gb_graph_check(gb_graph *g);
  * dists[i] >= 1: EdgeGraphPosition(edge ids[i], dists[i]).  *n = nodes + edge bases - edges (line 97).  Call with all three
  * arrays NULL to get *n only. */
 int gb_graph_positions(gb_graph *g, uint64_t *kmers, uint32_t *ids, uint32_t *dists, int64_t cap, int64_t *n);
+/* The pair loop of GraphSimplifier.startup (S/scripts/GraphSimplifier.scala:188-263) with the WalkingActor walks (33-127) and
+ * annotate (192-206) over the first n_pairs read pairs of a HOST `.bin` stream: for both orientations of every pair whose
+ * reads are at least k long, graphMap.getAll of the first k-mers, the bounded walk between every pair of positions with
+ * range = range_lo..range_hi (the reference hard-codes 180 to 250, line 153; range_hi <= 511 here), and pathsMap.
+ * support[4 * e1 + b] = pathsMap((e1, e2)), e2 being the out-edge of e1's end node whose first base is b (a pathsMap key
+ * is always such a pair); support has 4 * n_edges entries.  *bad_pairs = badPairs (246-248), *walked_cases = orientation
+ * cases that reached the walkers.  Edge indices are those of the current gb_graph_export. */
+int gb_graph_pair_support(gb_graph *g, const uint8_t *bin, size_t n_bytes, int64_t n_pairs, int range_lo, int range_hi,
+                          uint32_t *support, int64_t *bad_pairs, int64_t *walked_cases);
+/* The node sweep of GraphSimplifier.startup (268-316): per node with in- and out-edges the matrix support >= cutoff, its
+ * bipartite components; each component with out-edges moves to a new copy of the node (addNode / replaceEnd / replaceStart),
+ * in-edges alone in their component and out-edges no component reached are removed.  The emptied originals stay until
+ * gb_graph_simplify, which the reference calls next (318).  support as filled by gb_graph_pair_support on this graph. */
+int gb_graph_split_nodes(gb_graph *g, const uint32_t *support, int32_t cutoff, int64_t *edges_removed, int64_t *nodes_added);
 /* counters of the build: [0] stored k-mers seen [1] pointer-jumping launches [2] oriented k-mers on perfect
  * cycles, dropped like the reference does (Graph.scala:375) [3] build time in ns (CUDA events) */
 int gb_graph_stats(gb_graph *g, int64_t stats[8]);

@@ -840,6 +840,13 @@ int go_graph_check(const go_graph *g)
     return 0;
 }
 
+/* ids of the live edges in go_graph_export order */
+void go_graph_edge_ids(const go_graph *g, int64_t *edge_id)
+{
+    int64_t n = 0;
+    for (int64_t i = 0; i < g->ne; i++) if (g->edges[i].alive) edge_id[n++] = i + 1;
+}
+
 /* ================================================================================================
  * Paired-end path support: S/scripts/GraphSimplifier.scala
  *   WalkingActor.reachable 43-72, WalkingActor.receive 77-126, annotate 192-206, the pair loop 213-248,

@@ -62,6 +62,7 @@ void      go_graph_counts(const go_graph *g, int64_t *n_nodes, int64_t *n_edges,
 /* live nodes in id order; live edges in id order; seq = one byte per base (code 0..3) */
 void      go_graph_export(const go_graph *g, uint64_t *node_kmer, int64_t *node_id,
                           int64_t *edge_start_id, int64_t *edge_end_id, int64_t *edge_off, uint8_t *edge_bases);
+void      go_graph_edge_ids(const go_graph *g, int64_t *edge_id); /* ids of the live edges, export order */
 /* components 54-72: label[i] for live node i (export order), returns number of components */
 int64_t   go_graph_components(const go_graph *g, int64_t *label);
 /* GraphBuilder.scala:52-54; tie rule (reference order is JDK-dependent): largest, then the component

@@ -52,6 +52,7 @@ def lib():
         "go_graph_free": (None, [vp]),
         "go_graph_counts": (None, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]),
         "go_graph_export": (None, [vp, vp, vp, vp, vp, vp, vp]),
+        "go_graph_edge_ids": (None, [vp, vp]),
         "go_graph_components": (i64, [vp, vp]),
         "go_graph_retain_largest": (None, [vp]),
         "go_graph_simplify": (None, [vp]),
@@ -182,6 +183,11 @@ class OracleGraph:
         bases = np.empty(nb, np.uint8)
         lib().go_graph_export(self.h, _ptr(node_kmer), _ptr(node_id), _ptr(es), _ptr(ee), _ptr(off), _ptr(bases))
         return node_kmer, node_id, es, ee, off, bases
+
+    def edge_ids(self):
+        ids = np.empty(self.counts()[1], np.int64)
+        lib().go_graph_edge_ids(self.h, _ptr(ids))
+        return ids
 
     def components(self):
         nn = self.counts()[0]
