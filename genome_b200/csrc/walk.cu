@@ -43,6 +43,14 @@ __global__ void posmap_insert_kernel(const unsigned long long *kmer, unsigned lo
     while (atomicCAS(&slot[s], NONE32, (unsigned int)i) != NONE32) s = next_slot(s, cap);
 }
 
+// fixed-stride check: equal length bytes at i * rec imply that the record chain is i * rec
+__global__ void walk_verify_fixed_kernel(const uint8_t *bin, unsigned int rec, unsigned int len0, unsigned long long n_reads,
+                                         unsigned int *ragged)
+{
+    unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_reads && bin[r * rec] != len0) atomicOr(ragged, 1u);
+}
+
 struct PairStream {
     const uint8_t *bin;
     const unsigned long long *off; // record offsets, or nullptr when every record has rec_bytes bytes
@@ -152,6 +160,22 @@ static GraphView view_of(const Graph *g, const unsigned int *out4)
         }                                                                                                     \
     } while (0)
 
+// CUDA events of one call (timings reported through gb_graph_stats)
+struct Events {
+    cudaEvent_t e[4] = { nullptr, nullptr, nullptr, nullptr };
+    ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+    int init()
+    {
+        for (cudaEvent_t &x : e) GB_CUDA(cudaEventCreate(&x));
+        return GB_OK;
+    }
+    int64_t ns(int a, int b) const
+    {
+        float ms = 0;
+        return cudaEventElapsedTime(&ms, e[a], e[b]) == cudaSuccess ? (int64_t)(ms * 1e6) : 0;
+    }
+};
+
 static int read_counters(const unsigned long long *d, unsigned long long *h, int n, cudaStream_t st)
 {
     GB_CUDA(cudaMemcpyAsync(h, d, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
@@ -182,28 +206,50 @@ extern "C" int gb_graph_pair_support(gb_graph *h, const uint8_t *bin, size_t n_b
     memset(support, 0, (size_t)E * 4 * sizeof(uint32_t));
     if (n_pairs == 0 || E == 0) return GB_OK;
 
-    // PairedEndData.getPairs framing (S/data/PairedEndData.scala:20-36) on the host; offsets travel only for ragged streams
-    std::vector<unsigned long long> off;
-    std::vector<int64_t> winp;
-    GB_TRY(scan_records(bin, n_bytes, 2 * n_pairs, g->k, off, winp));
-    const size_t used = (size_t)off[(size_t)(2 * n_pairs)];
-    const unsigned int rec = 1 + ((unsigned int)bin[0] + 3) / 4;
-    bool fixed = used == (size_t)(2 * n_pairs) * rec;
-    for (int64_t r = 0; fixed && r < 2 * n_pairs; r++) fixed = off[(size_t)r] == (unsigned long long)r * rec;
-
     const int64_t n_pos = g->n_nodes + g->n_bases - g->n_edges; // Graph.scala:97
     if (n_pos >= (int64_t)NONE32) { set_error("graph map of %lld entries exceeds 32-bit entry indices", (long long)n_pos); return GB_E_CAPACITY; }
+    if (n_bytes == 0) { set_error("truncated .bin stream at read 0"); return GB_E_ARG; }
 
+    // PairedEndData.getPairs framing (S/data/PairedEndData.scala:20-36).  Fixed-stride fast path as in gb_map_insert_reads: if
+    // the stream is long enough for 2 * n_pairs records of the first record's size, copy those bytes and let the device
+    // compare every length byte; otherwise (or if they differ) the record chain is scanned on the host and travels along.
+    const int64_t n_reads = 2 * n_pairs;
+    const unsigned int len0 = bin[0], rec = 1 + (len0 + 3) / 4;
+    bool fixed = (unsigned long long)n_reads * rec <= n_bytes;
     DeviceBuf d_bin, d_off;
-    GB_TRY(d_bin.alloc(used + 16));
-    GB_CUDA(cudaMemcpyAsync(d_bin.p, bin, used, cudaMemcpyHostToDevice, st));
+    size_t used = 0;
+    if (fixed) {
+        used = (size_t)n_reads * rec;
+        GB_TRY(d_bin.alloc(used + 16));
+        GB_CUDA(cudaMemcpyAsync(d_bin.p, bin, used, cudaMemcpyHostToDevice, st));
+        Tmp<unsigned int> ragged;
+        GB_TRY(ragged.alloc(1, st));
+        GB_TRY(ragged.zero(1));
+        WLAUNCH(walk_verify_fixed_kernel, n_reads, 256, (const uint8_t *)d_bin.p, rec, len0, (unsigned long long)n_reads, ragged.p);
+        unsigned int r = 0;
+        GB_CUDA(cudaMemcpyAsync(&r, ragged.p, 4, cudaMemcpyDeviceToHost, st));
+        GB_CUDA(cudaStreamSynchronize(st));
+        fixed = r == 0;
+    }
     if (!fixed) {
+        std::vector<unsigned long long> off;
+        std::vector<int64_t> winp;
+        GB_TRY(scan_records(bin, n_bytes, n_reads, g->k, off, winp));
+        const size_t need = (size_t)off[(size_t)n_reads];
+        if (need > used) {
+            GB_TRY(d_bin.alloc(need + 16));
+            GB_CUDA(cudaMemcpyAsync(d_bin.p, bin, need, cudaMemcpyHostToDevice, st));
+        }
         GB_TRY(d_off.alloc(off.size() * 8));
         GB_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+        GB_CUDA(cudaStreamSynchronize(st)); // `off` goes out of scope
     }
 
     Tmp<unsigned int> out4, slot, pid, pdist, d_support;
     Tmp<unsigned long long> pk, counters, cases[2];
+    Events ev;
+    GB_TRY(ev.init());
+    GB_CUDA(cudaEventRecord(ev.e[0], st));
     GB_TRY(out4.alloc(4 * N, st));
     GB_TRY(out4.fill_ff(4 * N));
     GraphView gv = view_of(g, out4.p);
@@ -226,6 +272,7 @@ extern "C" int gb_graph_pair_support(gb_graph *h, const uint8_t *bin, size_t n_b
     GB_TRY(counters.alloc(8, st));
     GB_TRY(counters.zero(8));
     GB_TRY(cases[0].alloc(4 * (size_t)n_pairs, st)); // two cases of two k-mers per pair
+    GB_CUDA(cudaEventRecord(ev.e[1], st));
 
     PairStream ps;
     ps.bin = (const uint8_t *)d_bin.p;
@@ -233,6 +280,7 @@ extern "C" int gb_graph_pair_support(gb_graph *h, const uint8_t *bin, size_t n_b
     ps.rec_bytes = rec;
     ps.n_pairs = (unsigned long long)n_pairs;
     WLAUNCH(walk_filter_kernel, n_pairs, 256, gv, pm, ps, range_lo, range_hi, cases[0].p, counters.p);
+    GB_CUDA(cudaEventRecord(ev.e[2], st));
     unsigned long long c[8];
     GB_TRY(read_counters(counters.p, c, 8, st));
     if (c[WC_ERROR]) { set_error("a k-mer occupies more than %d graph positions", WALK_MAXPOS); return GB_E_CAPACITY; }
@@ -241,6 +289,7 @@ extern "C" int gb_graph_pair_support(gb_graph *h, const uint8_t *bin, size_t n_b
     static const int tier_lmax[3] = { 32, 512, 8192 };
     static const unsigned long long tier_workers[3] = { 148ull * 128, 2048, 128 };
     unsigned long long n_cases = c[WC_LIST];
+    g->stats[7] = (int64_t)n_cases;
     int cur = 0;
     for (int tier = 0; tier < 3 && n_cases; tier++) {
         const unsigned long long workers = n_cases < tier_workers[tier] ? n_cases : tier_workers[tier];
@@ -258,8 +307,12 @@ extern "C" int gb_graph_pair_support(gb_graph *h, const uint8_t *bin, size_t n_b
         set_error("%llu read pairs see more than %d edges within %d bases: walk table exhausted", n_cases, tier_lmax[2], range_hi);
         return GB_E_CAPACITY;
     }
+    GB_CUDA(cudaEventRecord(ev.e[3], st));
     GB_CUDA(cudaMemcpyAsync(support, d_support.p, (size_t)E * 16, cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));
+    g->stats[4] = ev.ns(0, 1);
+    g->stats[5] = ev.ns(1, 2);
+    g->stats[6] = ev.ns(2, 3);
     if (bad_pairs) *bad_pairs = (int64_t)c[WC_BAD];
     if (walked_cases) *walked_cases = (int64_t)c[WC_WALKED];
     return GB_OK;

@@ -4,6 +4,7 @@
 //   trait DNAMap[Int]      S/ds/ArrayDNAMap.scala:49-60      -> genome::DNAMap
 //   object FreqFilter      S/data/FreqFilter.scala:25-58     -> genome::FreqFilter::extractFilteredKmers
 //   object Graph / MapGraph S/data/graph/Graph.scala         -> genome::Graph::buildGraph, genome::MapGraph
+//   GraphSimplifier's pair loop and node sweep S/scripts/GraphSimplifier.scala:188-317 -> MapGraph::pairSupport / splitNodes
 // Errors surface as genome::Error (the reference asserts / fails its Futures).  No CPU fallback exists.
 #pragma once
 #include <cstdint>
@@ -83,6 +84,26 @@ class MapGraph {
         std::vector<Position> out((size_t)n);
         for (size_t i = 0; i < (size_t)n; i++) out[i] = { k[i], id[i], d[i] };
         return out;
+    }
+    // the pair loop of GraphSimplifier.startup (S/scripts/GraphSimplifier.scala:188-263): pathsMap as support[4 * e1 + b]
+    // (e2 = the out-edge of e1's end node with first base b), badPairs and the number of walked orientation cases
+    struct PairSupport { std::vector<uint32_t> support; int64_t badPairs = 0, walkedCases = 0; };
+    PairSupport pairSupport(const uint8_t *bin, size_t nBytes, int64_t pairs, int rangeFirst = 180, int rangeLast = 250) const
+    {
+        int64_t n, e, b;
+        check(gb_graph_counts(g_, &n, &e, &b));
+        PairSupport r;
+        r.support.assign((size_t)e * 4, 0);
+        uint32_t none = 0;
+        check(gb_graph_pair_support(g_, bin, nBytes, pairs, rangeFirst, rangeLast, e ? r.support.data() : &none, &r.badPairs, &r.walkedCases));
+        return r;
+    }
+    // the node sweep of GraphSimplifier.startup (268-316): (edges removed, nodes added); simplifyGraph comes next (318)
+    std::pair<int64_t, int64_t> splitNodes(const std::vector<uint32_t> &support, int32_t cutoff)
+    {
+        int64_t removed = 0, added = 0;
+        check(gb_graph_split_nodes(g_, support.data(), cutoff, &removed, &added));
+        return { removed, added };
     }
     void retainLargest() { check(gb_graph_retain_largest(g_)); }   // GraphBuilder.scala:52-54
     void simplifyGraph() { check(gb_graph_simplify(g_)); }          // Graph.scala:211-230

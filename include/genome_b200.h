@@ -155,7 +155,9 @@ int gb_graph_pair_support(gb_graph *g, const uint8_t *bin, size_t n_bytes, int64
  * gb_graph_simplify, which the reference calls next (318).  support as filled by gb_graph_pair_support on this graph. */
 int gb_graph_split_nodes(gb_graph *g, const uint32_t *support, int32_t cutoff, int64_t *edges_removed, int64_t *nodes_added);
 /* counters of the build: [0] stored k-mers seen [1] pointer-jumping launches [2] oriented k-mers on perfect
- * cycles, dropped like the reference does (Graph.scala:375) [3] build time in ns (CUDA events) */
+ * cycles, dropped like the reference does (Graph.scala:375) [3] build time in ns (CUDA events);
+ * of the last gb_graph_pair_support on the handle, in ns (CUDA events): [4] out-edge table + graph map (positions, putNew)
+ * [5] pair filter (getAll x 4, annotate) [6] walks (all tiers); [7] orientation cases that survived the filter */
 int gb_graph_stats(gb_graph *g, int64_t stats[8]);
 
 /* ------------------------------------------------------------------------------------------------

@@ -1,11 +1,8 @@
 """Paired-end path support on the device (gb_graph_pair_support / gb_graph_split_nodes, csrc/walk.cu)
 against the oracle's restatement of GraphSimplifier.scala:33-127,188-317.
 
-The device functions are already checked against the oracle on the CPU (tests/test_walk_emul_cpu.py runs the same walk.cuh
-code serially); these tests cover the kernels proper.  They have NOT yet run on a B200 (the round's GPU budget was spent when
-they were written), so they only run when GENOME_B200_UNVALIDATED=1 -- to be enabled once they have passed there."""
-import os
-
+The device functions are also checked against the oracle on the CPU (tests/test_walk_emul_cpu.py runs the same walk.cuh
+code serially); these tests cover the kernels proper (first B200 run: gpurun_out/walk_check.log, all pass)."""
 import numpy as np
 import pytest
 
@@ -18,8 +15,7 @@ from tests import helpers as H
 from tests.test_walk_cpu import reads_of, two_chromosomes
 from tests.test_walk_emul_cpu import node_signatures
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("GENOME_B200_UNVALIDATED") != "1", reason="not yet validated on a B200")]
+pytestmark = pytest.mark.gpu
 
 
 def scenario(case):
