@@ -1,7 +1,8 @@
 // graph_simplifier.cpp -- GraphBuilder.startup followed by GraphSimplifier.startup (S/scripts/GraphSimplifier.scala:138-357,
 // relative to /root/reference) against the C++ host mirror.  The reference passes the graph between the two scripts as a
 // Kryo file; that format is not reproduced, so this driver runs both stages in one process.
-// Usage: graph_simplifier <reads.bin> <n_pairs> <k> <cutoff> [range_first range_last] [contigs_file]
+// Usage: graph_simplifier <reads.bin> <n_pairs> <k> <cutoff> [range_first range_last [contigs_file]]
+// Compiled and link-checked in the CPU tests; not yet run on a GPU (its calls are the ones tests/test_walk_gpu.py makes).
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -12,7 +13,7 @@
 
 int main(int argc, char **argv)
 {
-    if (argc < 5) { std::fprintf(stderr, "usage: %s <reads.bin> <n_pairs> <k> <cutoff> [range_first range_last] [contigs]\n", argv[0]); return 2; }
+    if (argc < 5) { std::fprintf(stderr, "usage: %s <reads.bin> <n_pairs> <k> <cutoff> [range_first range_last [contigs]]\n", argv[0]); return 2; }
     try {
         std::ifstream f(argv[1], std::ios::binary);
         std::vector<uint8_t> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
@@ -37,9 +38,9 @@ int main(int argc, char **argv)
         std::map<size_t, int64_t> lengths;
         for (auto &e : edges) { total += (int64_t)e.seq.size(); lengths[e.seq.size()]++; }
         std::printf("Total edges length: %lld\n", (long long)total);
-        if (argc > 7 || argc == 6) {
-            std::FILE *out = std::fopen(argv[argc - 1], "w");
-            if (!out) { std::perror(argv[argc - 1]); return 1; }
+        if (argc > 7) {
+            std::FILE *out = std::fopen(argv[7], "w");
+            if (!out) { std::perror(argv[7]); return 1; }
             static const char code[] = "AGCT";                     // Base.scala:13-16
             int i = 0;
             for (auto &e : edges) {                                // 338-347: the sequence line comes before its header

@@ -107,10 +107,10 @@ def test_multi_rank_routing_gloo():
     assert "ROUTING OK" in r.stdout
 
 
-def build_cpp_driver(tmp):
-    exe = os.path.join(tmp, "graph_builder")
+def build_cpp_driver(tmp, name="graph_builder"):
+    exe = os.path.join(tmp, name)
     libdir = os.path.join(ROOT, "genome_b200")
-    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-O1", "-o", exe, os.path.join(ROOT, "hostcpp", "graph_builder.cpp"),
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-O1", "-o", exe, os.path.join(ROOT, "hostcpp", name + ".cpp"),
                         "-L" + libdir, "-lgenome_b200", "-Wl,-rpath," + libdir], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     return exe
@@ -125,4 +125,17 @@ def test_cpp_host_mirror_compiles_and_fails_loudly_without_gpu(tmp_path):
     p = tmp_path / "r.bin"
     p.write_bytes(b.tobytes())
     r = subprocess.run([exe, str(p), "10", "21"], capture_output=True, text=True)
+    assert r.returncode == 1 and "CUDA" in r.stderr
+
+
+def test_cpp_graph_simplifier_driver_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """hostcpp/graph_simplifier.cpp: GraphBuilder + GraphSimplifier (pair support, node split) over the C++ mirror."""
+    exe = build_cpp_driver(str(tmp_path), "graph_simplifier")
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    b = synth.pack_fixed(synth.sample_reads(synth.random_genome(2000, 1), 50, 20, 0.0, 2, insert=(20, 60)))
+    p = tmp_path / "r.bin"
+    p.write_bytes(b.tobytes())
+    r = subprocess.run([exe, str(p), "10", "21", "5"], capture_output=True, text=True)
     assert r.returncode == 1 and "CUDA" in r.stderr
