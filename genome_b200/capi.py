@@ -67,6 +67,10 @@ SIGNATURES = {
     "gb_graph_check": (C.c_int, [_vp]),
     "gb_graph_stats": (C.c_int, [_vp, _pi64]),
     "gb_graph_positions": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _pi64]),
+    "gb_graph_map_create": (C.c_int, [_vp, _pp]),
+    "gb_graph_map_destroy": (C.c_int, [_vp]),
+    "gb_graph_map_size": (C.c_int, [_vp, _pi64]),
+    "gb_graph_map_get_all": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp]),
     "gb_graph_pair_support": (C.c_int, [_vp, _vp, _sz, _i64, C.c_int, C.c_int, _vp, _pi64, _pi64]),
     "gb_graph_split_nodes": (C.c_int, [_vp, _vp, _i32, _pi64, _pi64]),
     "gb_comm_unique_id": (C.c_int, [_vp]),

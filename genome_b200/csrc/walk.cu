@@ -136,6 +136,41 @@ __global__ void split_apply_kernel(GraphView g, const unsigned int *in4, const u
     }
 }
 
+// getAll / contains (S/ds/ArrayDNAMap.scala:103-113,232) for n keys, one key per thread (walk.cuh: posmap_lookup)
+__global__ void posmap_lookup_kernel(PosMap m, const unsigned long long *keys, long long n, int max_per, unsigned int *ids,
+                                     unsigned int *dists, unsigned int *counts)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    counts[i] = posmap_lookup(m, keys[i], max_per, ids ? ids + i * max_per : nullptr, dists ? dists + i * max_per : nullptr);
+}
+
+// the DNAMap[GraphPosition] of Graph.getGraphMap as its own handle: a snapshot, independent of the graph it came from
+struct GraphMap {
+    int k = 0, device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t n = 0;
+    unsigned long long cap = 0;
+    unsigned long long *kmer = nullptr;
+    unsigned int *id = nullptr, *dist = nullptr, *slot = nullptr;
+    Arena arena; // scratch of the lookups
+    PosMap view() const
+    {
+        PosMap m;
+        m.slot = slot; m.cap = cap; m.kmer = kmer; m.id = id; m.dist = dist;
+        return m;
+    }
+};
+
+static int graph_map_free(GraphMap *gm)
+{
+    if (gm->stream) { cudaStreamSynchronize(gm->stream); cudaStreamDestroy(gm->stream); }
+    cudaFree(gm->kmer); cudaFree(gm->id); cudaFree(gm->dist); cudaFree(gm->slot);
+    gm->arena.destroy();
+    delete gm;
+    return GB_OK;
+}
+
 static GraphView view_of(const Graph *g, const unsigned int *out4)
 {
     GraphView v;
@@ -370,5 +405,89 @@ extern "C" int gb_graph_split_nodes(gb_graph *h, const uint32_t *support, int32_
     if (nodes_added) *nodes_added = (int64_t)added;
     if (edges_removed) *edges_removed = (int64_t)tot[1];
     if (tot[1]) GB_TRY(graph_remove_flagged(g, kill.p)); // toRemove.foreach(removeEdge) (316)
+    return GB_OK;
+}
+
+// ---------------------------------------------------------------- DNAMap[GraphPosition]
+extern "C" int gb_graph_map_create(gb_graph *h, gb_graph_map **out)
+{
+    if (!h || !out) { set_error("null argument"); return GB_E_ARG; }
+    *out = nullptr;
+    Graph *g = reinterpret_cast<Graph *>(h);
+    GB_CUDA(cudaSetDevice(g->device));
+    const int64_t n = g->n_nodes + g->n_bases - g->n_edges; // Graph.scala:97
+    if (n >= (int64_t)NONE32) { set_error("graph map of %lld entries exceeds 32-bit entry indices", (long long)n); return GB_E_CAPACITY; }
+    GraphMap *gm = new GraphMap();
+    gm->k = g->k; gm->device = g->device; gm->n = n;
+    gm->cap = ((unsigned long long)n * 2 + 1024) / 1024 * 1024; // load <= 1/2
+    int rc = GB_OK;
+    auto fail = [&](int code) { graph_map_free(gm); return code; };
+    if (cudaStreamCreateWithFlags(&gm->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); return fail(GB_E_CUDA); }
+    if (cudaMalloc((void **)&gm->kmer, (size_t)(n ? n : 1) * 8) != cudaSuccess || cudaMalloc((void **)&gm->id, (size_t)(n ? n : 1) * 4) != cudaSuccess ||
+        cudaMalloc((void **)&gm->dist, (size_t)(n ? n : 1) * 4) != cudaSuccess || cudaMalloc((void **)&gm->slot, (size_t)gm->cap * 4) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("out of device memory for a graph map of %lld entries", (long long)n);
+        return fail(GB_E_OOM);
+    }
+    {
+        // the entries are produced on the graph's stream (they read the graph's arrays), the index on it too; the handle's own
+        // stream takes over once everything is in place
+        cudaStream_t st = g->stream;
+        if ((rc = graph_positions_device(g, gm->kmer, gm->id, gm->dist)) != GB_OK) return fail(rc);
+        if (cudaMemsetAsync(gm->slot, 0xFF, (size_t)gm->cap * 4, st) != cudaSuccess) { set_error("cudaMemset failed"); return fail(GB_E_CUDA); }
+        if (n) {
+            posmap_insert_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(gm->kmer, (unsigned long long)n, gm->slot, gm->cap);
+            note_launch();
+            if (cudaGetLastError() != cudaSuccess) { set_error("posmap_insert_kernel launch failed"); return fail(GB_E_CUDA); }
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("graph map build failed"); return fail(GB_E_CUDA); }
+    }
+    *out = reinterpret_cast<gb_graph_map *>(gm);
+    return GB_OK;
+}
+
+extern "C" int gb_graph_map_destroy(gb_graph_map *h)
+{
+    if (!h) return GB_OK;
+    GraphMap *gm = reinterpret_cast<GraphMap *>(h);
+    cudaSetDevice(gm->device);
+    return graph_map_free(gm);
+}
+
+extern "C" int gb_graph_map_size(gb_graph_map *h, int64_t *size)
+{
+    if (!h || !size) { set_error("null argument"); return GB_E_ARG; }
+    *size = reinterpret_cast<GraphMap *>(h)->n;
+    return GB_OK;
+}
+
+extern "C" int gb_graph_map_get_all(gb_graph_map *h, const uint64_t *keys, int64_t n, int max_per_key, uint32_t *ids, uint32_t *dists,
+                                    uint32_t *counts)
+{
+    if (!h) { set_error("null graph map handle"); return GB_E_ARG; }
+    GraphMap *gm = reinterpret_cast<GraphMap *>(h);
+    if (n < 0 || max_per_key < 0 || (n > 0 && (!keys || !counts))) { set_error("bad arguments"); return GB_E_ARG; }
+    if (n == 0) return GB_OK;
+    const unsigned long long kmask = (1ull << (2 * gm->k)) - 1;
+    for (int64_t i = 0; i < n; i++)
+        if (keys[i] & ~kmask) { set_error("key %lld is longer than k = %d", (long long)i, gm->k); return GB_E_K_RANGE; }
+    GB_CUDA(cudaSetDevice(gm->device));
+    ArenaScope scope(&gm->arena);
+    cudaStream_t st = gm->stream;
+    const bool want = max_per_key > 0 && (ids || dists);
+    Tmp<unsigned long long> dk;
+    Tmp<unsigned int> di, dd, dc;
+    GB_TRY(dk.alloc((size_t)n, st));
+    GB_TRY(dc.alloc((size_t)n, st));
+    if (want && ids) GB_TRY(di.alloc((size_t)n * max_per_key, st));
+    if (want && dists) GB_TRY(dd.alloc((size_t)n * max_per_key, st));
+    GB_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    if (di.p) GB_CUDA(cudaMemsetAsync(di.p, 0xFF, (size_t)n * max_per_key * 4, st));
+    if (dd.p) GB_CUDA(cudaMemsetAsync(dd.p, 0xFF, (size_t)n * max_per_key * 4, st));
+    WLAUNCH(posmap_lookup_kernel, n, 256, gm->view(), dk.p, (long long)n, want ? max_per_key : 0, di.p, dd.p, dc.p);
+    GB_CUDA(cudaMemcpyAsync(counts, dc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (di.p) GB_CUDA(cudaMemcpyAsync(ids, di.p, (size_t)n * max_per_key * 4, cudaMemcpyDeviceToHost, st));
+    if (dd.p) GB_CUDA(cudaMemcpyAsync(dists, dd.p, (size_t)n * max_per_key * 4, cudaMemcpyDeviceToHost, st));
+    GB_CUDA(cudaStreamSynchronize(st));
     return GB_OK;
 }

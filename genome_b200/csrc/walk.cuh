@@ -74,6 +74,26 @@ GB_HD int posmap_get_all(const PosMap &m, unsigned long long key, Pos *out, int 
     }
 }
 
+// getAll (ArrayDNAMap.scala:103-113) into plain arrays: returns the number of positions under `key` (contains = count > 0,
+// 232); the first max_per of them go to ids / dists (either may be null)
+GB_HD unsigned int posmap_lookup(const PosMap &m, unsigned long long key, int max_per, unsigned int *ids, unsigned int *dists)
+{
+    unsigned int n = 0;
+    unsigned long long i = slot_of(mix64(key), m.cap);
+    for (;;) {
+        const unsigned int e = m.slot[i];
+        if (e == NONE32) return n;
+        if (m.kmer[e] == key) {
+            if ((int)n < max_per) {
+                if (ids) ids[n] = m.id[e];
+                if (dists) dists[n] = m.dist[e];
+            }
+            n++;
+        }
+        i = next_slot(i, m.cap);
+    }
+}
+
 // annotate (GraphSimplifier.scala:192-206)
 GB_HD bool annotate_drops(const Pos *p1, int n1, const Pos *p2, int n2, int k, int lo, int hi)
 {

@@ -99,6 +99,12 @@ class MapGraph:
             capi.check(capi.lib().gb_graph_positions(self.h, capi.ptr(kmer), capi.ptr(ident), capi.ptr(dist), n.value, C.byref(n)))
         return kmer, ident, dist
 
+    def graphMap(self):
+        """Graph.getGraphMap (90-119) as a device-resident DNAMap[GraphPosition] (a snapshot of the current graph)."""
+        h = C.c_void_p()
+        capi.check(capi.lib().gb_graph_map_create(self.h, C.byref(h)))
+        return GraphPositionMap(h, self.k)
+
     def pairSupport(self, data, takeFirst=None, range_=(180, 250)):
         """The pair loop of GraphSimplifier.startup (S/scripts/GraphSimplifier.scala:188-263): graphMap.getAll of the first
         k-mers of both reads in both orientations, annotate, and the WalkingActor walks (33-127), for the first `takeFirst`
@@ -128,6 +134,50 @@ class MapGraph:
         capi.check(capi.lib().gb_graph_stats(self.h, s))
         return dict(kept_kmers=s[0], jump_launches=s[1], cycle_vertices=s[2], build_ns=s[3],
                     pair_support_map_ns=s[4], pair_support_filter_ns=s[5], pair_support_walk_ns=s[6], pair_support_cases=s[7])
+
+
+class GraphPositionMap:
+    """The DNAMap[GraphPosition] of Graph.getGraphMap (Graph.scala:92-117): `size`, `getAll`, `contains` of trait DNAMap
+    (S/ds/ArrayDNAMap.scala:49-60) in bulk.  Keys are k-mers as u64, oriented as given (the map holds both strands)."""
+
+    def __init__(self, handle, k):
+        self.h = handle
+        self.k = k
+
+    def close(self):
+        if getattr(self, "h", None):
+            capi.lib().gb_graph_map_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def size(self):
+        n = C.c_int64()
+        capi.check(capi.lib().gb_graph_map_size(self.h, C.byref(n)))
+        return n.value
+
+    def getAll(self, keys, max_per_key=4):
+        """(counts u32[n], ids u32[n, max_per_key], dists u32[n, max_per_key]); dist 0 = NodeGraphPosition(id), dist >= 1 =
+        EdgeGraphPosition(id, dist); unused entries are 0xFFFFFFFF.  counts[i] may exceed max_per_key (multimap, Q13)."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        n = keys.size
+        counts = np.zeros(n, np.uint32)
+        ids = np.full((n, max_per_key), 0xFFFFFFFF, np.uint32)
+        dists = np.full((n, max_per_key), 0xFFFFFFFF, np.uint32)
+        capi.check(capi.lib().gb_graph_map_get_all(self.h, capi.ptr(keys), n, int(max_per_key), capi.ptr(ids), capi.ptr(dists),
+                                                   capi.ptr(counts)))
+        return counts, ids, dists
+
+    def contains(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        counts = np.zeros(keys.size, np.uint32)
+        capi.check(capi.lib().gb_graph_map_get_all(self.h, capi.ptr(keys), keys.size, 0, None, None, capi.ptr(counts)))
+        return counts > 0
 
 
 class Graph:

@@ -85,6 +85,32 @@ class MapGraph {
         for (size_t i = 0; i < (size_t)n; i++) out[i] = { k[i], id[i], d[i] };
         return out;
     }
+    // Graph.getGraphMap as a device-resident DNAMap[GraphPosition] (a snapshot): size / getAll / contains in bulk
+    class GraphMap {
+    public:
+        explicit GraphMap(gb_graph *g) { check(gb_graph_map_create(g, &m_)); }
+        ~GraphMap() { gb_graph_map_destroy(m_); }
+        GraphMap(const GraphMap &) = delete;
+        GraphMap &operator=(const GraphMap &) = delete;
+        int64_t size() const { int64_t n = 0; check(gb_graph_map_size(m_, &n)); return n; }
+        // getAll (S/ds/ArrayDNAMap.scala:103-113): counts[i] positions under keys[i], the first maxPer in ids / dists
+        void getAll(const std::vector<uint64_t> &keys, int maxPer, std::vector<uint32_t> &ids, std::vector<uint32_t> &dists,
+                    std::vector<uint32_t> &counts) const
+        {
+            ids.assign(keys.size() * (size_t)maxPer, 0xFFFFFFFFu);
+            dists.assign(keys.size() * (size_t)maxPer, 0xFFFFFFFFu);
+            counts.assign(keys.size(), 0);
+            check(gb_graph_map_get_all(m_, keys.data(), (int64_t)keys.size(), maxPer, ids.data(), dists.data(), counts.data()));
+        }
+        std::vector<uint32_t> contains(const std::vector<uint64_t> &keys) const // ArrayDNAMap.scala:232
+        {
+            std::vector<uint32_t> counts(keys.size(), 0);
+            check(gb_graph_map_get_all(m_, keys.data(), (int64_t)keys.size(), 0, nullptr, nullptr, counts.data()));
+            return counts;
+        }
+    private:
+        gb_graph_map *m_ = nullptr;
+    };
     // the pair loop of GraphSimplifier.startup (S/scripts/GraphSimplifier.scala:188-263): pathsMap as support[4 * e1 + b]
     // (e2 = the out-edge of e1's end node with first base b), badPairs and the number of walked orientation cases
     struct PairSupport { std::vector<uint32_t> support; int64_t badPairs = 0, walkedCases = 0; };

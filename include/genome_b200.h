@@ -36,6 +36,7 @@ extern "C" {
 typedef struct gb_map gb_map;     /* DNAMap[Int]: one shard (one GPU) of the k-mer count table */
 typedef struct gb_graph gb_graph; /* Graph / MapGraph */
 typedef struct gb_comm gb_comm;   /* the set of shards of a PartitionedDNAMap: one rank per GPU */
+typedef struct gb_graph_map gb_graph_map; /* DNAMap[GraphPosition] as built by Graph.getGraphMap */
 
 const char *gb_last_error(void);
 /* diagnostics: kernels launched by this library in this process so far */
@@ -140,6 +141,18 @@ int gb_graph_check(gb_graph *g);
  * dists[i] >= 1: EdgeGraphPosition(edge ids[i], dists[i]).  *n = nodes + edge bases - edges (line 97).  Call with all three
  * arrays NULL to get *n only. */
 int gb_graph_positions(gb_graph *g, uint64_t *kmers, uint32_t *ids, uint32_t *dists, int64_t cap, int64_t *n);
+/* Graph.getGraphMap (Graph.scala:90-119) as a DEVICE-resident DNAMap[GraphPosition]: putNew (S/ds/ArrayDNAMap.scala:152-162)
+ * of every entry gb_graph_positions lists.  A snapshot: later changes of the graph do not show, the handle outlives the graph.
+ * EXPERIMENTAL this round: covered by the emulation tests only, its GPU test is gated (tests/test_graphmap_gpu.py). */
+int gb_graph_map_create(gb_graph *g, gb_graph_map **out);
+int gb_graph_map_destroy(gb_graph_map *gm);
+int gb_graph_map_size(gb_graph_map *gm, int64_t *size);               /* nodeMap.size (Graph.scala:117) */
+/* getAll (ArrayDNAMap.scala:103-113) / contains (232) for n k-mers, oriented as given (the map holds both strands, no
+ * canonicalisation): counts[i] = number of positions under keys[i]; the first max_per_key of them are written to
+ * ids / dists [i * max_per_key ...] (dist 0: NodeGraphPosition(id), else EdgeGraphPosition(id, dist); unused = 0xFFFFFFFF).
+ * ids and dists may be NULL (contains only). */
+int gb_graph_map_get_all(gb_graph_map *gm, const uint64_t *keys, int64_t n, int max_per_key, uint32_t *ids, uint32_t *dists,
+                         uint32_t *counts);
 /* The pair loop of GraphSimplifier.startup (S/scripts/GraphSimplifier.scala:188-263) with the WalkingActor walks (33-127) and
  * annotate (192-206) over the first n_pairs read pairs of a HOST `.bin` stream: for both orientations of every pair whose
  * reads are at least k long, graphMap.getAll of the first k-mers, the bounded walk between every pair of positions with

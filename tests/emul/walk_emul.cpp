@@ -146,4 +146,22 @@ int64_t emul_split(int k, uint64_t n_nodes, uint64_t n_edges, const uint64_t *no
     return (int64_t)base[n_nodes];
 }
 
+// gb_graph_map_create + gb_graph_map_get_all, serially: putNew of every entry (posmap_insert_kernel), then posmap_lookup per key
+int emul_graph_map_get_all(uint64_t n_pos, const uint64_t *pos_kmer, const uint32_t *pos_id, const uint32_t *pos_dist, uint64_t n_keys,
+                           const uint64_t *keys, int max_per, uint32_t *ids, uint32_t *dists, uint32_t *counts)
+{
+    const unsigned long long cap = (n_pos * 2 + 1024) / 1024 * 1024;
+    std::vector<uint32_t> slot(cap, NONE32);
+    for (uint64_t i = 0; i < n_pos; i++) {
+        unsigned long long s = slot_of(mix64(pos_kmer[i]), cap);
+        while (slot[s] != NONE32) s = next_slot(s, cap);
+        slot[s] = (uint32_t)i;
+    }
+    PosMap m;
+    m.slot = slot.data(); m.cap = cap; m.kmer = (const unsigned long long *)pos_kmer; m.id = pos_id; m.dist = pos_dist;
+    for (uint64_t i = 0; i < n_keys; i++)
+        counts[i] = posmap_lookup(m, keys[i], max_per, ids ? ids + i * max_per : nullptr, dists ? dists + i * max_per : nullptr);
+    return 0;
+}
+
 } // extern "C"

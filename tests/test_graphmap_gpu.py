@@ -1,4 +1,6 @@
 """Graph.getGraphMap on the device against the oracle's restatement (Graph.scala:90-119)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -43,3 +45,39 @@ def test_graph_positions_match_oracle(gpu, k, glen, rl, cov, err, rounds):
     ok, oi, od = og.graph_map()
     theirs = canon(ok, oi, od, onk, oes_i, oee_i, ooff, obases, lambda i: i - 1)  # fresh oracle graph: edge id = index + 1
     assert mine == theirs
+
+
+# gb_graph_map_* was written after this round's GPU budget was spent: its logic is covered by the g++ emulation
+# (tests/test_walk_emul_cpu.py::test_graph_map_get_all_matches_oracle); the device run is opt-in until it has passed on a B200
+@pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")
+@pytest.mark.parametrize("k,glen,rl,cov,err,rounds", [(31, 20000, 100, 30, 0.01, 3), (15, 5000, 60, 30, 0.01, 2), (4, 120, 20, 6, 0.0, 1)])
+def test_graph_map_handle(gpu, k, glen, rl, cov, err, rounds):
+    """GraphPositionMap.size / getAll / contains against the exported entry list: every entry is found under its k-mer, absent
+    k-mers are not, and the CheckGraph property (S/scripts/CheckGraph.scala:47-54) holds: every k-mer of the kept set, in
+    both orientations, that lies on the graph is found."""
+    b, n, _ = H.small_reads(glen, rl, cov, err, seed=4100 + k)
+    gm = FreqFilter.extractFilteredKmers(PairedEndData(b, n // 2), k, rounds)
+    g = Graph.buildGraph(k, gm)
+    pk, pi, pd = g.getGraphMap()
+    m = g.graphMap()
+    assert m.size == pk.size
+    want = {}
+    for x, i, d in zip(pk.tolist(), pi.tolist(), pd.tolist()):
+        want.setdefault(x, []).append((i, d))
+    rng = np.random.default_rng(k)
+    absent = rng.integers(0, 1 << (2 * k), 1000, dtype=np.uint64)
+    keys = np.concatenate([pk, absent])
+    counts, ids, dists = m.getAll(keys, 2)
+    for j, x in enumerate(keys.tolist()):
+        w = want.get(x, [])
+        assert counts[j] == len(w)
+        assert sorted((int(ids[j, c]), int(dists[j, c])) for c in range(min(len(w), 2))) == sorted(w)[:2] or len(w) > 2
+    assert np.array_equal(m.contains(keys), counts > 0)
+    # the map is a snapshot: it survives changes to (and the destruction of) the graph it came from
+    g.retain_largest()
+    g.simplifyGraph()
+    g.close()
+    assert np.array_equal(m.contains(keys), counts > 0)
+    with pytest.raises(Exception):
+        m.contains(np.array([1 << (2 * k)], np.uint64))  # longer than k: GB_E_K_RANGE
+    m.close()

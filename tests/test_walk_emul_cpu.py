@@ -254,3 +254,46 @@ def test_split_matches_oracle(emul, case, cutoff):
     assert got == want
     if case == "noisy":
         assert added > 0
+
+
+@pytest.mark.parametrize("case", ["fresh", "after_split"])
+def test_graph_map_get_all_matches_oracle(emul, case):
+    """The DNAMap[GraphPosition] handle (gb_graph_map_create / gb_graph_map_get_all): putNew of every getGraphMap entry and
+    getAll / contains per key (posmap_lookup), against a dict built from the oracle's graph_map.  After a node split the
+    copies of a node share its k-mer: multimap semantics (putNew never dedupes)."""
+    k, L = 15, 50
+    og, b, n_reads = noisy_graph(k, 6000, L, 40, 0.02, 91, (60, 100), rounds=2)
+    if case == "after_split":
+        e1, e2, cnt, _, _ = og.pair_support(b, n_reads // 2, 90, 155)
+        _, added = og.split(e1, e2, cnt, 3)
+        assert added > 0
+    lay = DeviceLayout(og)
+    pk, pi, pd = lay.positions(og)
+    want = {}
+    for x, i, d in zip(pk.tolist(), pi.tolist(), pd.tolist()):
+        want.setdefault(x, []).append((i, d))
+    rng = np.random.default_rng(5)
+    absent = rng.integers(0, 1 << (2 * k), 500, dtype=np.uint64)
+    keys = np.concatenate([pk[rng.permutation(pk.size)[:2000]], absent])
+    max_per = 3
+    counts = np.zeros(keys.size, np.uint32)
+    ids = np.full((keys.size, max_per), NONE32, np.uint32)
+    dists = np.full((keys.size, max_per), NONE32, np.uint32)
+    emul.emul_graph_map_get_all(C.c_uint64(pk.size), ptr(pk), ptr(pi), ptr(pd), C.c_uint64(keys.size), ptr(keys), max_per, ptr(ids),
+                                ptr(dists), ptr(counts))
+    multi = 0
+    for j, x in enumerate(keys.tolist()):
+        w = want.get(x, [])
+        assert counts[j] == len(w)
+        got = sorted((int(ids[j, c]), int(dists[j, c])) for c in range(min(len(w), max_per)))
+        if len(w) <= max_per:
+            assert got == sorted(w)
+        else:
+            assert set(got) <= set(w)
+        assert np.all(ids[j, len(w):] == NONE32)
+        multi += len(w) > 1
+    assert (multi > 0) == (case == "after_split")
+    # contains only: no output arrays
+    c2 = np.zeros(keys.size, np.uint32)
+    emul.emul_graph_map_get_all(C.c_uint64(pk.size), ptr(pk), ptr(pi), ptr(pd), C.c_uint64(keys.size), ptr(keys), 0, None, None, ptr(c2))
+    assert np.array_equal(c2, counts)
