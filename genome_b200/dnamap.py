@@ -6,7 +6,7 @@ S/ = src/main/scala/ru/ifmo/genome/):
   class ArrayDNAMap        S/ds/ArrayDNAMap.scala:62-243     -> one shard on one GPU
   class PartitionedDNAMap  S/ds/PartitionedDNAMap.scala:15-63 -> one shard per rank, NCCL all-to-all routing
   object FreqFilter        S/data/FreqFilter.scala:25-58
-  class PairedEndData      S/data/PairedEndData.scala:12-41   (the `.bin` stream; header object not reproduced)
+  class PairedEndData      S/data/PairedEndData.scala:12-41   (the `.bin` stream + the header object file)
 
 Keys are Long1DNASeq values: one uint64 per k-mer, base i at bits 2i (S/dna/DNASeq.scala:80-85).  Bulk calls take
 numpy arrays.  Scala closures cannot cross a C ABI; the three the hot path uses are dedicated entry points
@@ -33,6 +33,22 @@ class PairedEndData:
     @property
     def n_reads(self):
         return 2 * self.count
+
+    @staticmethod
+    def apply(path):
+        """object PairedEndData.apply(f) (PairedEndData.scala:38-41): read the Java-serialised header at `path`, then the
+        `.bin` stream it names (a relative name is resolved like java.io.File: against the working directory)."""
+        from . import formats
+        with open(path, "rb") as f:
+            count, insert, bin_path = formats.read_paired_end_header(f.read())
+        return PairedEndData(np.fromfile(bin_path, dtype=np.uint8), count, insert)
+
+    def write(self, path, bin_path):
+        """PairedEndData.write(f) (14-18) plus the stream itself: `bin_path` receives the records, `path` the header."""
+        from . import formats
+        self.bin.tofile(bin_path)
+        with open(path, "wb") as f:
+            f.write(formats.write_paired_end_header(self.count, self.insert, bin_path))
 
     def record_offsets(self):
         """Byte offset of every record (n_reads + 1 entries); raises on a truncated stream."""

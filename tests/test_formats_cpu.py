@@ -1,7 +1,9 @@
 """Host-side formats and the oracle's getGraphMap restatement (row 3): CPU only."""
 import numpy as np
+import pytest
 
 from genome_b200 import formats, synth
+from genome_b200 import formats as F
 from oracle import pyoracle
 from tests import helpers as H
 
@@ -89,3 +91,66 @@ def test_graph_map_restatement():
             else:
                 missing += 1  # only isolated (0,0) k-mers and perfect cycles are absent (Graph.scala:375)
     assert found > 0 and missing <= 0.001 * found
+
+
+def test_paired_end_header_round_trip_and_known_bytes():
+    """PairedEndData.write / PairedEndData(f) (S/data/PairedEndData.scala:14-18,38-41): the Java object stream of the header.
+    The java.io.File part is checked against the JDK's well-known serial form (class descriptor with serialVersionUID
+    0x042DA4450E0DE4FF, flags SC_SERIALIZABLE | SC_WRITE_METHOD, one String field `path`, separator char as block data)."""
+    b = F.write_paired_end_header(690000, 200, "/data/ecoli.bin")
+    assert b[:4] == bytes.fromhex("aced0005")
+    assert F.read_paired_end_header(b) == (690000, 200, "/data/ecoli.bin")
+    file_part = bytes.fromhex("7372000c6a6176612e696f2e46696c65042da4450e0de4ff0300014c0004706174687400124c6a6176612f6c616e672f537472696e673b7870"
+                              "74000f2f646174612f65636f6c692e62696e7702002f78")
+    assert b.endswith(file_part)
+    # class descriptor: name, serialVersionUID 1 (@SerialVersionUID(1L), PairedEndData.scala:11), SC_SERIALIZABLE, 3 fields
+    name = b"ru.ifmo.genome.data.PairedEndData"
+    assert b[4:6] == b"\x73\x72" and b[6:8] == len(name).to_bytes(2, "big") and b[8:8 + len(name)] == name
+    assert b[8 + len(name):8 + len(name) + 11] == (1).to_bytes(8, "big") + b"\x02\x00\x03"
+    # count is a Long: values beyond 32 bits survive
+    assert F.read_paired_end_header(F.write_paired_end_header(1 << 40, -1, "x"))[:2] == (1 << 40, -1)
+
+
+def test_paired_end_header_reader_is_order_independent():
+    """A stream a different JVM could have written: object field first in the descriptor is impossible for ObjectStreamClass,
+    but back references (TC_REFERENCE) to an earlier type string and a superclass-free second object are legal; fields are
+    found by name."""
+    import struct
+    utf = lambda s: struct.pack(">H", len(s)) + s.encode()
+    out = bytearray(bytes.fromhex("aced0005"))
+    out += b"\x73\x72" + utf("ru.ifmo.genome.data.PairedEndData") + struct.pack(">q", 1) + b"\x02" + struct.pack(">H", 4)
+    out += b"I" + utf("insert") + b"J" + utf("count")                      # other order than ours
+    out += b"L" + utf("aux") + b"\x74" + utf("Ljava/io/File;")             # handle 0x7e0001 = this type string
+    out += b"L" + utf("bin") + b"\x71" + struct.pack(">I", 0x7E0001)       # reference to it
+    out += b"\x78\x70"
+    out += struct.pack(">iq", 321, 99)
+    out += b"\x70"                                                          # aux = null
+    out += b"\x73\x72" + utf("java.io.File") + struct.pack(">q", 301077366599181567) + b"\x03" + struct.pack(">H", 1)
+    out += b"L" + utf("path") + b"\x74" + utf("Ljava/lang/String;") + b"\x78\x70"
+    out += b"\x74" + utf("C:\\reads.bin") + b"\x77\x02" + struct.pack(">H", ord("\\")) + b"\x78"
+    assert F.read_paired_end_header(bytes(out)) == (99, 321, "C:\\reads.bin")
+
+
+@pytest.mark.parametrize("bad", ["magic", "truncated", "class"])
+def test_paired_end_header_errors(bad):
+    b = bytearray(F.write_paired_end_header(5, 200, "a.bin"))
+    if bad == "magic":
+        b[0] = 0
+    elif bad == "truncated":
+        b = b[:-6]
+    else:
+        b[10] ^= 1   # another class name
+    with pytest.raises(ValueError):
+        F.read_paired_end_header(bytes(b))
+
+
+def test_paired_end_data_files(tmp_path):
+    """Convert2bin's two outputs (`<name>.bin` + the header object `<name>`, Convert2bin.scala:18,83) written and read back
+    through the PairedEndData mirror."""
+    from genome_b200.dnamap import PairedEndData
+    genome = synth.random_genome(3000, 3)
+    reads = synth.sample_reads(genome, 40, 200, 0.0, 4)
+    d = PairedEndData(synth.pack_fixed(reads), 100, insert=200)
+    d.write(str(tmp_path / "reads"), str(tmp_path / "reads.bin"))
+    e = PairedEndData.apply(str(tmp_path / "reads"))
+    assert (e.count, e.insert) == (100, 200) and np.array_equal(e.bin, d.bin)
