@@ -154,3 +154,23 @@ def test_paired_end_data_files(tmp_path):
     d.write(str(tmp_path / "reads"), str(tmp_path / "reads.bin"))
     e = PairedEndData.apply(str(tmp_path / "reads"))
     assert (e.count, e.insert) == (100, 200) and np.array_equal(e.bin, d.bin)
+
+
+def test_checkgraph_host_logic():
+    """CheckGraph.scala:37-41,46-47 and N50.scala:14-31: the host-side parts (no device)."""
+    from genome_b200 import checkgraph as CG
+    st = CG.contig_stats([10, 201, 200, 500, 300, 1000])
+    assert st == dict(count=4, size=2001, n50=500, max=1000)   # contigs(4 / 2) of [201, 300, 500, 1000]
+    with pytest.raises(IndexError):
+        CG.contig_stats([5, 200])
+    k = 5
+    line = "ACGTNACGTAC"
+    keys, starts, short = CG.line_windows(line, k)
+    want = [i for i in range(len(line) - k + 1) if "N" not in line[i:i + k]]
+    assert starts.tolist() == want and short == 0
+    assert [synth.int_to_kmer(int(x), k) for x in keys] == [line[i:i + k] for i in want]
+    assert CG.line_windows("ACG", k)[2] == 1 and CG.line_windows("ANG", k)[2] == 0 and CG.line_windows("", k)[2] == 0
+    # N50: pairs sorted by length; the crossing pair; the trailing pair without a comma is invisible to the reference's regex
+    out, pairs, ge100 = CG.n50("hist: Map(100 -> 2, 50 -> 4, 300 -> 1, 7 -> 9)")
+    assert pairs == [(50, 4), (100, 2), (300, 1)] and ge100 == 3
+    assert out == [(100, 2)]   # total 700: 200 < 350 <= 400

@@ -81,3 +81,22 @@ def test_graph_map_handle(gpu, k, glen, rl, cov, err, rounds):
     with pytest.raises(Exception):
         m.contains(np.array([1 << (2 * k)], np.uint64))  # longer than k: GB_E_K_RANGE
     m.close()
+
+
+@pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")
+def test_check_graph_finds_every_genome_kmer(gpu):
+    """CheckGraph.startup (S/scripts/CheckGraph.scala:18-56) on an error-free read set that covers the genome: every k-window
+    of the genome FASTA is on the graph; windows of an unrelated sequence are reported."""
+    from genome_b200 import checkgraph, synth
+    k = 21
+    genome = synth.random_genome(30000, 77)
+    reads = synth.sample_reads(genome, 100, 12000, 0.0, 78)
+    b = synth.pack_fixed(reads)
+    gm = FreqFilter.extractFilteredKmers(PairedEndData(b, reads.shape[0] // 2), k, 1)
+    g = Graph.buildGraph(k, gm)
+    covered = synth.decode(genome[2000:28000])   # the ends may be under-sampled
+    other = synth.decode(synth.random_genome(300, 79))
+    stats, missing = checkgraph.check_graph(g, [">chr", covered[:13000], covered[13000:], "ACGTN", other])
+    assert stats["max"] > 200 and stats["count"] >= 1
+    lens = sorted(set(m[0] for m in missing))
+    assert lens == [300] and len(missing) == 300 - k + 1   # only the unrelated line (and none of "ACGTN": no full window)
