@@ -1,0 +1,217 @@
+"""The sharded Graph.buildGraph (genome_b200/csrc/sgraph.cuh: minimizer re-routing, per-rank index / masks / list ranking,
+segment list, global assembly) compiled with g++ and run over P in-process ranks (tests/emul/sgraph_emul.cpp) against the
+oracle's restatement of Graph.scala:269-382.  The per-item functors AND the orchestration are the code the CUDA library
+runs; only the launches (serial loops here), the memory and the fabric differ.  The device runs are in
+tests/test_sgraph_gpu.py (virtual shards on one GPU) and tests/test_parity_multigpu.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from genome_b200 import synth
+from oracle import pyoracle
+from tests import helpers as H
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = os.path.join(HERE, "emul", "sgraph_emul.cpp")
+    out = os.path.join(HERE, "_build", "libsgraph_emul.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    deps = [src] + [os.path.join(ROOT, "genome_b200", "csrc", f) for f in ("sgraph.cuh", "common.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+                               "-I" + cuda_inc, "-o", out, src])
+    return C.CDLL(out)
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def sharded_build(emul, k, keys, P, dual=False, split="even", seed=0):
+    """Runs the emulated build with the kept keys dealt to P ranks (`split`: even / skewed / all on the last rank) and
+    returns (canonical graph as in tests/helpers.py, stats dict)."""
+    keys = np.ascontiguousarray(keys, np.uint64)
+    rng = np.random.default_rng(seed)
+    keys = keys[rng.permutation(keys.size)]
+    if split == "even":
+        cuts = [keys.size * r // P for r in range(P + 1)]
+    elif split == "skewed":
+        cuts = sorted(rng.integers(0, keys.size + 1, P - 1).tolist())
+        cuts = [0] + cuts + [keys.size]
+    else:
+        cuts = [0] * P + [keys.size]
+    off = np.array(cuts, np.uint64)
+    out = np.zeros(8, np.uint64)
+    rc = emul.emul_sharded_build(k, int(dual), 0, P, ptr(keys), ptr(off), ptr(out), None, None, None, None, None)
+    assert rc == 0, rc
+    N, E, B = int(out[0]), int(out[1]), int(out[2])
+    node_kmer = np.zeros(max(N, 1), np.uint64)
+    es = np.zeros(max(E, 1), np.uint32)
+    ee = np.zeros(max(E, 1), np.uint32)
+    eo = np.zeros(E + 1, np.uint64)
+    words = np.zeros((B + 15) // 16 + 1, np.uint32)
+    rc = emul.emul_sharded_build(k, int(dual), 0, P, ptr(keys), ptr(off), ptr(out), ptr(node_kmer), ptr(es), ptr(ee), ptr(eo), ptr(words))
+    assert rc == 0
+    bases = np.zeros(words.size * 16, np.uint8)
+    for j in range(16):
+        bases[j::16] = (words >> np.uint32(2 * j)) & 3
+    nk = [int(x) for x in node_kmer[:N]]
+    assert int(eo[E]) == B and np.all(np.diff(eo.astype(np.int64)) > 0)
+    edges = sorted((nk[int(es[i])], nk[int(ee[i])], bases[int(eo[i]):int(eo[i + 1])].tobytes()) for i in range(E))
+    stats = dict(kept=int(out[3]), segments=int(out[4]), cycle_vertices=int(out[5]), jump_rounds=int(out[6]), seg_rounds=int(out[7]))
+    return (sorted(nk), edges), (N, E, B), stats
+
+
+def oracle_graph(b, n, k, rounds):
+    om, _ = H.oracle_counts(b, n, k)
+    om.delete_below(rounds)
+    return om, pyoracle.OracleGraph(om)
+
+
+@pytest.mark.parametrize("k", [3, 4, 8, 15, 16, 21, 31])
+@pytest.mark.parametrize("P", [1, 2, 5, 8])
+def test_neighbour_owner_is_the_owner_of_the_neighbour(emul, k, P):
+    """The incremental owner of the 8 neighbours (one m-mer hash each, from the parts of x) equals the owner computed from
+    scratch, and a k-mer shares its owner with its reverse complement."""
+    rng = np.random.default_rng(100 * k + P)
+    full, incr, full_rc = np.zeros(9, np.uint32), np.zeros(8, np.uint32), np.zeros(9, np.uint32)
+    xs = rng.integers(0, 1 << (2 * k), 300, dtype=np.uint64).tolist()
+    xs += [0, (1 << (2 * k)) - 1, int("01" * k, 2)]   # poly-A, poly-T, poly-G: every m-mer equal
+    seen = set()
+    for x in xs:
+        emul.emul_owners(k, P, C.c_uint64(x), ptr(full), ptr(incr))
+        assert np.array_equal(full[1:], incr), (k, P, x)
+        assert full.max() < P
+        emul.emul_owners(k, P, C.c_uint64(pyoracle.revcomp(x, k)), ptr(full_rc), ptr(incr))
+        assert full_rc[0] == full[0]
+        seen.add(int(full[0]))
+    if k >= 15:
+        assert len(seen) == P   # every rank owns something
+
+
+GRAPH_CASES = [
+    # k, genome, read_len, coverage, err, rounds   (tests/test_parity_gpu.py GRAPH_CASES)
+    (31, 20000, 100, 30, 0.0, 3),
+    (31, 20000, 100, 30, 0.01, 3),
+    (21, 30000, 100, 25, 0.02, 2),
+    (15, 5000, 60, 30, 0.01, 2),
+    (11, 3000, 50, 20, 0.0, 1),
+    (9, 4000, 40, 15, 0.03, 1),
+    (8, 1500, 40, 10, 0.0, 1),   # even k: palindromes
+    (6, 600, 30, 10, 0.02, 1),
+    (4, 120, 20, 6, 0.0, 1),
+    (5, 300, 20, 4, 0.0, 1),
+    (3, 40, 12, 3, 0.0, 1),
+]
+
+
+@pytest.mark.parametrize("k,glen,rl,cov,err,rounds", GRAPH_CASES)
+def test_sharded_build_matches_oracle(emul, k, glen, rl, cov, err, rounds):
+    b, n, _ = H.small_reads(glen, rl, cov, err, seed=2000 + k)
+    om, og = oracle_graph(b, n, k, rounds)
+    want = H.canon_oracle_graph(og)
+    keys, _ = om.export()
+    for P, split in [(1, "even"), (2, "even"), (3, "skewed"), (8, "even"), (8, "last"), (16, "skewed")]:
+        got, counts, st = sharded_build(emul, k, keys, P, split=split, seed=P)
+        assert counts == og.counts(), (P, split)
+        assert got == want, (P, split)
+        assert st["kept"] == keys.size
+        if P == 1:
+            assert st["segments"] == 0
+
+
+def test_segments_are_a_small_fraction(emul):
+    """The point of minimizer ownership: chains break into rank-local runs ~(k - m + 2) / 2 vertices long, so the segment
+    list that crosses the fabric is an order of magnitude shorter than the vertex list (hash ownership: 7 of 8 links)."""
+    k = 31
+    b, n, _ = H.small_reads(60000, 100, 30, 0.0, seed=77)
+    om, og = oracle_graph(b, n, k, 2)
+    keys, _ = om.export()
+    got, counts, st = sharded_build(emul, k, keys, 8)
+    assert got == H.canon_oracle_graph(og)
+    interior = 2 * keys.size
+    assert 0 < st["segments"] < interior / 6, st
+    assert st["seg_rounds"] >= 1
+
+
+def test_noncanonical_keys_both_orientations(emul):
+    """Keys stored as given (update without canonicalisation): both orientations of a k-mer may be stored; the smaller one
+    is the vertex, the other one is nothing (common.cuh find_oriented / is_secondary)."""
+    k = 9
+    rng = np.random.default_rng(3)
+    genome = synth.random_genome(2000, 99)
+    fw = np.array([synth.kmer_to_int(synth.decode(genome[i:i + k])) for i in range(genome.size - k + 1)], np.uint64)
+    rc = np.array([pyoracle.revcomp(int(x), k) for x in fw], np.uint64)
+    pick = rng.random(fw.size)
+    keys = np.unique(np.concatenate([fw[pick < 0.6], rc[pick > 0.4]]))
+    om = pyoracle.OracleMap(k)
+    for x in keys:
+        om.update1(int(x))
+    og = pyoracle.OracleGraph(om)
+    stored, _ = om.export()
+    for P in (1, 4, 8):
+        got, counts, _ = sharded_build(emul, k, stored, P, dual=True)
+        assert counts == og.counts()
+        assert got == H.canon_oracle_graph(og)
+
+
+@pytest.mark.parametrize("P", [1, 2, 8])
+def test_perfect_cycle_is_dropped(emul, P):
+    """A circular sequence with no branch has no terminal k-mer (Graph.scala:375): with P > 1 the cycle runs through several
+    ranks, so it is the SEGMENT list that fails to resolve."""
+    k = 11
+    genome = synth.random_genome(500, 8)
+    circ = np.concatenate([genome, genome[:k - 1]])
+    keys = np.array([pyoracle.canonical(synth.kmer_to_int(synth.decode(circ[i:i + k])), k) for i in range(genome.size)], np.uint64)
+    got, counts, st = sharded_build(emul, k, keys, P)
+    assert counts == (0, 0, 0)
+    assert st["cycle_vertices"] == 2 * genome.size
+    if P > 1:
+        assert st["segments"] > 0
+
+
+def test_cycle_next_to_a_real_graph(emul):
+    """A perfect cycle and a branching component side by side: the cycle vanishes, the rest is exact."""
+    k = 15
+    g1 = synth.random_genome(400, 22)
+    circ = np.concatenate([g1, g1[:k - 1]])
+    cyc = [pyoracle.canonical(synth.kmer_to_int(synth.decode(circ[i:i + k])), k) for i in range(g1.size)]
+    b, n, _ = H.small_reads(3000, 50, 20, 0.01, seed=5)
+    om, _ = H.oracle_counts(b, n, k)
+    om.delete_below(2)
+    for x in cyc:
+        om.update1(int(x))
+    og = pyoracle.OracleGraph(om)
+    keys, _ = om.export()
+    for P in (1, 3, 8):
+        got, counts, st = sharded_build(emul, k, keys, P)
+        assert got == H.canon_oracle_graph(og)
+        assert st["cycle_vertices"] == 2 * g1.size
+
+
+def test_empty_and_tiny_inputs(emul):
+    for P in (1, 4):
+        got, counts, _ = sharded_build(emul, 15, np.zeros(0, np.uint64), P)
+        assert counts == (0, 0, 0)
+        # one isolated k-mer: (0, 0) vertices are no nodes (Graph.scala:323)
+        got, counts, _ = sharded_build(emul, 15, np.array([pyoracle.canonical(12345, 15)], np.uint64), P)
+        assert counts == (0, 0, 0)
+        # two overlapping k-mers: 4 nodes, 2 edges of length 1
+        x = synth.kmer_to_int("ACGTTGCAAGGCTTA")
+        y = synth.kmer_to_int("CGTTGCAAGGCTTAC")
+        om = pyoracle.OracleMap(15)
+        for v in (x, y):
+            om.update1(pyoracle.canonical(v, 15))
+        og = pyoracle.OracleGraph(om)
+        keys, _ = om.export()
+        got, counts, _ = sharded_build(emul, 15, keys, P)
+        assert counts == og.counts() == (4, 2, 2)
+        assert got == H.canon_oracle_graph(og)
