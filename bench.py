@@ -319,7 +319,9 @@ def main():
                  "components_retain_simplify_ms": max_over_ranks((t2 - t1) * 1e3),
                  "nodes": nn, "edges": ne, "edge_bases": nb, "components": nc, "jump_launches": g.stats()["jump_launches"],
                  "after_simplify": g.counts(), "kept_kmers": kept_total,
-                 "sharding": "replicated after all-gather of the shards" if world > 1 else "single GPU"}
+                 "sharding": ("single GPU" if world == 1 else
+                              "sharded: minimizer owners, rank-local list ranking, segment list (GENOME_B200_PGRAPH=sharded)"
+                              if os.environ.get("GENOME_B200_PGRAPH") == "sharded" else "replicated after all-gather of the shards")}
         g.close()
 
     # ---------------- roofline of the dominant kernel (insert), live CUDA-event durations from inside the library

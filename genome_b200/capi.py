@@ -55,6 +55,7 @@ SIGNATURES = {
     "gb_bench_random_atomics": (C.c_int, [C.c_int, _sz, _i64, C.c_int, _pi64]),
     "gb_map_stats": (C.c_int, [_vp, _pi64]),
     "gb_graph_build": (C.c_int, [_vp, _pp]),
+    "gb_graph_build_virtual_shards": (C.c_int, [_vp, C.c_int, _pp]),
     "gb_graph_destroy": (C.c_int, [_vp]),
     "gb_graph_counts": (C.c_int, [_vp, _pi64, _pi64, _pi64]),
     "gb_graph_export": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),

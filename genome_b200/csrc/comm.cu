@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "extract.cuh"
 #include "partition.cuh"
+#include "sgraph_fabric.cuh"
 
 namespace gb {
 
@@ -51,6 +52,10 @@ struct Comm {
     unsigned long long *peer_inbox[3][MAX_RANKS];
     size_t region_cap = 0;
     int p2p = -1; // -1 unknown, 0 NCCL send/recv staging, 1 peer stores
+    // peer window of the sharded graph build (sgraph.cuh): keys, index, masks and vertex entries of this rank, mapped by all
+    void *window = nullptr;
+    void *peer_window[MAX_RANKS];
+    size_t window_cap_of[MAX_RANKS]; // capacity of every rank's window (all ranks track all: the sizes are global knowledge)
 };
 
 // NCCL is bound with dlopen at the first gb_comm_* call, not at link time: a process that already holds an NCCL
@@ -284,6 +289,108 @@ static int ensure_inboxes(Comm *c, size_t want)
     GB_TRY(all_reduce_i64(c, &one, ncclSum));
     return GB_OK;
 }
+
+static void close_windows(Comm *c)
+{
+    for (int p = 0; p < c->n_ranks; p++)
+        if (p != c->rank && c->peer_window[p]) cudaIpcCloseMemHandle(c->peer_window[p]);
+    if (c->window) cudaFree(c->window);
+    c->window = nullptr;
+    for (int p = 0; p < MAX_RANKS; p++) { c->peer_window[p] = nullptr; c->window_cap_of[p] = 0; }
+}
+
+// The fabric of the sharded Graph.buildGraph (sgraph_fabric.cuh) for one rank per GPU: NCCL for the collectives, CUDA IPC for
+// the peer windows (NVLink loads / stores from inside the kernels).  Everything runs on the communicator's stream.
+struct NcclFabric : sg::Fabric {
+    Comm *c;
+    explicit NcclFabric(Comm *comm) : c(comm)
+    {
+        P = comm->n_ranks;
+        mine.push_back(comm->rank);
+    }
+    int allgather_host(const void *const *contrib, void *const *all, size_t bytes) override
+    {
+        GB_TRY(comm_scratch(c));
+        if (bytes > 256 || bytes * (size_t)P > 4096) { set_error("allgather_host: %zu bytes", bytes); return GB_E_ARG; }
+        uint8_t *d_mine = (uint8_t *)c->d_scratch, *d_all = (uint8_t *)c->d_scratch + 256;
+        GB_CUDA(cudaMemcpyAsync(d_mine, contrib[0], bytes, cudaMemcpyHostToDevice, c->stream));
+        GB_NCCL(ncclAllGather(d_mine, d_all, bytes, ncclUint8, c->nccl, c->stream));
+        GB_CUDA(cudaMemcpyAsync(all[0], d_all, bytes * (size_t)P, cudaMemcpyDeviceToHost, c->stream));
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+        return GB_OK;
+    }
+    // every rank knows every rank's size, so all of them agree without talking on whether any window has to grow; if one
+    // does, the mappings are rebuilt everywhere (rare: the windows are kept across builds and grow with 25 % slack)
+    int windows(const size_t *bytes_of_rank, void **window, sg::PeerPtrs *peers) override
+    {
+        bool grow = false;
+        for (int r = 0; r < P; r++) grow = grow || bytes_of_rank[r] > c->window_cap_of[r];
+        if (grow) {
+            GB_CUDA(cudaDeviceSynchronize());
+            GB_TRY(barrier_sync()); // nobody is still reading a window that is about to go away
+            const bool mine_grows = bytes_of_rank[c->rank] > c->window_cap_of[c->rank];
+            for (int p = 0; p < P; p++)
+                if (p != c->rank && c->peer_window[p]) { cudaIpcCloseMemHandle(c->peer_window[p]); c->peer_window[p] = nullptr; }
+            for (int r = 0; r < P; r++)
+                if (bytes_of_rank[r] > c->window_cap_of[r]) c->window_cap_of[r] = bytes_of_rank[r] + bytes_of_rank[r] / 4 + 4096;
+            if (mine_grows) {
+                if (c->window) GB_CUDA(cudaFree(c->window));
+                c->window = nullptr;
+                GB_CUDA(cudaMalloc(&c->window, c->window_cap_of[c->rank]));
+            }
+            GB_TRY(comm_scratch(c));
+            cudaIpcMemHandle_t h;
+            GB_CUDA(cudaIpcGetMemHandle(&h, c->window));
+            unsigned long long *d_mine = c->d_scratch, *d_all = c->d_scratch + 8;
+            GB_CUDA(cudaMemcpyAsync(d_mine, &h, 64, cudaMemcpyHostToDevice, c->stream));
+            GB_NCCL(ncclAllGather(d_mine, d_all, 8, ncclUint64, c->nccl, c->stream));
+            std::vector<cudaIpcMemHandle_t> all((size_t)P);
+            GB_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)P * 64, cudaMemcpyDeviceToHost, c->stream));
+            GB_CUDA(cudaStreamSynchronize(c->stream));
+            for (int p = 0; p < P; p++) {
+                if (p == c->rank) { c->peer_window[p] = c->window; continue; }
+                void *ptr = nullptr;
+                GB_CUDA(cudaIpcOpenMemHandle(&ptr, all[(size_t)p], cudaIpcMemLazyEnablePeerAccess));
+                c->peer_window[p] = ptr;
+            }
+        }
+        GB_TRY(barrier_sync()); // every rank has its mappings, and has finished with the windows' previous contents
+        window[0] = c->window;
+        for (int p = 0; p < P; p++) peers[0].p[p] = c->peer_window[p];
+        return GB_OK;
+    }
+    int alltoallv_u64(const sg::u64 *const *send, const sg::Row *soff, const sg::Row *scnt, sg::u64 *const *recv, const sg::Row *roff,
+                      const sg::Row *rcnt) override
+    {
+        return all_to_all_v(c, send[0], soff[0].v, scnt[0].v, recv[0], roff[0].v, rcnt[0].v, ncclUint64);
+    }
+    // stream-ordered: my later kernels start after every rank has reached this point of its own stream
+    int barrier() override
+    {
+        GB_TRY(comm_scratch(c));
+        GB_NCCL(ncclAllReduce(c->d_scratch + 1024, c->d_scratch + 1024, 1, ncclUint64, ncclSum, c->nccl, c->stream));
+        return GB_OK;
+    }
+    int barrier_sync()
+    {
+        GB_TRY(barrier());
+        GB_CUDA(cudaStreamSynchronize(c->stream));
+        return GB_OK;
+    }
+    int allgatherv_u64(sg::u64 *const *buf, const sg::u64 *off, const sg::u64 *cnt) override
+    {
+        GB_NCCL(ncclGroupStart());
+        for (int p = 0; p < P; p++)
+            if (cnt[p]) GB_NCCL(ncclBroadcast(buf[0] + off[p], buf[0] + off[p], cnt[p], ncclUint64, p, c->nccl, c->stream));
+        GB_NCCL(ncclGroupEnd());
+        return GB_OK;
+    }
+    int allreduce_sum(void *buf, size_t count, int elem_bytes) override
+    {
+        if (count) GB_NCCL(ncclAllReduce(buf, buf, count, elem_bytes == 8 ? ncclUint64 : ncclUint32, ncclSum, c->nccl, c->stream));
+        return GB_OK;
+    }
+};
 
 // wait for every in-flight insert, fold the new-key counter into m->size
 static int drain(Map *m, BatchBufs *bufs)
@@ -536,6 +643,8 @@ int gb_comm_create(const uint8_t id[GB_UNIQUE_ID_BYTES], int rank, int n_ranks, 
     Comm *c = new Comm();
     c->rank = rank; c->n_ranks = n_ranks; c->device = device;
     memset(c->peer_inbox, 0, sizeof c->peer_inbox);
+    memset(c->peer_window, 0, sizeof c->peer_window);
+    memset(c->window_cap_of, 0, sizeof c->window_cap_of);
     ncclUniqueId u;
     memcpy(&u, id, sizeof u);
     ncclResult_t r = ncclCommInitRank(&c->nccl, n_ranks, u, rank);
@@ -561,6 +670,7 @@ int gb_comm_destroy(gb_comm *h)
     cudaSetDevice(c->device);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     close_inboxes(c);
+    close_windows(c);
     c->bufs[0].release();
     c->bufs[1].release();
     c->bufs[2].release();
@@ -748,6 +858,20 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
     int64_t total = m->size, dual = m->noncanonical;
     GB_TRY(all_reduce_i64(c, &total, ncclSum));
     GB_TRY(all_reduce_i64(c, &dual, ncclMax));
+    // GENOME_B200_PGRAPH=sharded: no replica -- minimizer re-routing, rank-local list ranking, segment list (sgraph.cuh).
+    // Needs peer access between all ranks; every rank reads the same environment, so the choice is collective.
+    const char *mode = getenv("GENOME_B200_PGRAPH");
+    if (mode && !strcmp(mode, "sharded") && P <= sg::MAXR) {
+        GB_TRY(ensure_inboxes(c, 0)); // settles c->p2p (collective)
+        if (c->p2p == 1) {
+            GB_CUDA(cudaStreamSynchronize(m->stream));
+            NcclFabric fab(c);
+            Map *maps[1] = { m };
+            const int rc = graph_build_on_fabric(fab, maps, c->stream, dual != 0, out);
+            tick("sharded graph built");
+            return rc;
+        }
+    }
     // per-rank sizes
     DeviceBuf d_sizes;
     GB_TRY(d_sizes.alloc(MAX_RANKS * 8 * 2));

@@ -28,15 +28,12 @@
 #include <vector>
 
 #include "common.cuh"
+#include "sgraph_fabric.cuh"
 
 namespace gb {
 namespace sg {
 
-typedef unsigned long long u64;
-typedef unsigned int u32;
 typedef uint8_t u8;
-
-constexpr int MAXR = 16; // ranks of one sharded build (one NVSwitch box has 8)
 
 // ---------------------------------------------------------------- backend interface
 struct Exec; // one per rank driven by this process: CUDA stream + arena, or nothing at all (emulation)
@@ -52,32 +49,6 @@ int sg_scan(Exec &ex, u64 *data, u64 n, u64 *total_host);          // in-place e
 template <class Op> int sg_launch(Exec &ex, u64 n, const Op &op);  // op(i) for i in [0, n)
 
 template <typename T> static int sg_new(Exec &ex, T **p, size_t n) { return sg_alloc(ex, (void **)p, (n ? n : 1) * sizeof(T)); }
-
-struct PeerPtrs { void *p[MAXR]; };
-struct Row { u64 v[MAXR]; };
-
-// the P ranks of one build.  `mine` lists the ranks this process drives: exactly one in the one-process-per-GPU form, all
-// P in the single-process form (virtual shards / emulation).  Every call is collective over the processes; arrays indexed
-// [l] run over `mine`.
-struct Fabric {
-    int P = 1;
-    std::vector<int> mine;
-    virtual ~Fabric() {}
-    // host data: every rank contributes `bytes`; all[l] receives P * bytes in rank order
-    virtual int allgather_host(const void *const *contrib, void *const *all, size_t bytes) = 0;
-    // peer-visible memory: window[l] of bytes_of_rank[mine[l]] bytes; peers[l].p[r] = rank r's window as seen from mine[l]
-    virtual int windows(const size_t *bytes_of_rank, void **window, PeerPtrs *peers) = 0;
-    // u64 elements, host-known counts: send[l] + soff[l].v[p] (scnt[l].v[p] elements) lands in rank p's recv at its roff.v[mine[l]]
-    virtual int alltoallv_u64(const u64 *const *send, const Row *soff, const Row *scnt, u64 *const *recv, const Row *roff,
-                              const Row *rcnt) = 0;
-    // all device work issued so far by every rank is complete and visible to its peers before anything issued later starts
-    virtual int barrier() = 0;
-    // in place: elements [off[p], off[p] + cnt[p]) of buf[l] are rank p's; afterwards every rank holds all of them
-    virtual int allgatherv_u64(u64 *const *buf, const u64 *off, const u64 *cnt) = 0;
-    // the process's copy of a global output array: element-wise sum over the processes (one writer per element).  The
-    // ranks of one process share their copy, so the single-process form has nothing to do.
-    virtual int allreduce_sum(void *buf, size_t count, int elem_bytes) = 0;
-};
 
 // ---------------------------------------------------------------- per-item helpers
 #define SG_HD __host__ __device__ __forceinline__

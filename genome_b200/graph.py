@@ -192,3 +192,15 @@ class Graph:
         fn = capi.lib().gb_pmap_graph_build if isinstance(kmersFreq, PartitionedDNAMap) else capi.lib().gb_graph_build
         capi.check(fn(kmersFreq.h, C.byref(h)))
         return MapGraph(h, k)
+
+    @staticmethod
+    def buildGraphVirtualShards(k, kmersFreq, n_shards):
+        """The sharded form of Graph.buildGraph (csrc/sgraph.cuh: minimizer re-routing, rank-local list ranking, segment list)
+        over `n_shards` virtual ranks on the map's one device -- the multi-GPU algorithm, checkable on a single GPU."""
+        if k != kmersFreq.k:
+            raise ValueError("k differs from the map's k")
+        if isinstance(kmersFreq, PartitionedDNAMap):
+            raise ValueError("virtual shards run on a single-GPU map; a PartitionedDNAMap shards over its GPUs (GENOME_B200_PGRAPH=sharded)")
+        h = C.c_void_p()
+        capi.check(capi.lib().gb_graph_build_virtual_shards(kmersFreq.h, int(n_shards), C.byref(h)))
+        return MapGraph(h, k)

@@ -114,6 +114,11 @@ int gb_map_stats(gb_map *m, int64_t stats[8]);
 
 /* Graph.buildGraph(k, kmersFreq) (Graph.scala:269-382) on the map's current contents */
 int gb_graph_build(gb_map *m, gb_graph **out);
+/* The SHARDED form of Graph.buildGraph (csrc/sgraph.cuh: the build gb_pmap_graph_build runs over the GPUs of a box when
+ * GENOME_B200_PGRAPH=sharded) over n_shards VIRTUAL ranks on this map's one device: same result as gb_graph_build up to
+ * node / edge numbering.  A diagnostic entry point: it exists so that the multi-GPU algorithm can be checked and profiled
+ * on a single GPU.  1 <= n_shards <= 16.  EXPERIMENTAL this round (device test opt-in, tests/test_sgraph_gpu.py). */
+int gb_graph_build_virtual_shards(gb_map *m, int n_shards, gb_graph **out);
 int gb_graph_destroy(gb_graph *g);
 /* getNodes.size, getEdges.size, getEdges.map(_.seq.length).sum (GraphBuilder.scala:39) */
 int gb_graph_counts(gb_graph *g, int64_t *n_nodes, int64_t *n_edges, int64_t *n_edge_bases);
