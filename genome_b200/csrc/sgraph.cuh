@@ -91,6 +91,23 @@ SG_HD u32 at_cas32(u32 *p, u32 cmp, u32 v)
     return o;
 #endif
 }
+// `*(base + which) += 1` for every calling lane, returning the value before this lane's increment.  On the device the lanes
+// of a warp that hit the same counter are combined into one atomic (P counters take millions of hits: the owner histogram
+// and the scatter cursors); the order inside a group follows the lane number.
+SG_HD u64 at_inc64_grouped(u64 *base, u32 which)
+{
+#ifdef __CUDA_ARCH__
+    const u32 active = __activemask();
+    const u32 peers = __match_any_sync(active, which);
+    const u32 lane = threadIdx.x & 31, leader = (u32)__ffs((int)peers) - 1;
+    u64 first = 0;
+    if (lane == leader) first = atomicAdd(base + which, (u64)__popc(peers));
+    first = __shfl_sync(peers, first, (int)leader);
+    return first + (u64)__popc(peers & ((1u << lane) - 1));
+#else
+    return at_add64(base + which, 1);
+#endif
+}
 SG_HD int popc4(u32 m) { return (int)((m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1)); }
 SG_HD u32 first_bit4(u32 m) { return (m & 1) ? 0u : (m & 2) ? 1u : (m & 4) ? 2u : 3u; }
 
@@ -288,11 +305,11 @@ SG_HD u32 succ_of(const Ctx &c, const Local &L, u32 u)
 // ---------------------------------------------------------------- ops (one item per call)
 struct OwnerCountOp { // histogram of the owners of this rank's kept keys
     const u64 *keys; int k, m, P; u64 *cnt;
-    SG_HD void operator()(u64 i) const { at_add64(cnt + owner_of_kmer(keys[i], k, m, P), 1); }
+    SG_HD void operator()(u64 i) const { at_inc64_grouped(cnt, owner_of_kmer(keys[i], k, m, P)); }
 };
 struct OwnerScatterOp { // keys grouped by owner (cursor = exclusive offsets of the histogram)
     const u64 *keys; int k, m, P; u64 *cursor; u64 *out;
-    SG_HD void operator()(u64 i) const { out[at_add64(cursor + owner_of_kmer(keys[i], k, m, P), 1)] = keys[i]; }
+    SG_HD void operator()(u64 i) const { out[at_inc64_grouped(cursor, owner_of_kmer(keys[i], k, m, P))] = keys[i]; }
 };
 struct IndexInsertOp { // putNew of entry i: first free slot from the key's home
     const u64 *keys; u32 *slot; u64 cap;

@@ -6,6 +6,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../genome_b200/csrc/sgraph.cuh"
@@ -65,7 +68,134 @@ template <class Op> int sg_launch(Exec &, u64 n, const Op &op)
 using namespace gb;
 using namespace gb::sg;
 
+// ---- one THREAD per rank, each with its own Fabric object that drives exactly one rank: the control flow of the
+// one-process-per-GPU form (own copy of the global arrays, real sums, real exchanges), minus NCCL and CUDA IPC
+struct Hub {
+    int P;
+    std::mutex mu;
+    std::condition_variable cv;
+    int waiting = 0;
+    unsigned long generation = 0;
+    std::vector<const void *> ptr;
+    std::vector<Row> row_a, row_b;
+    explicit Hub(int n) : P(n), ptr((size_t)n), row_a((size_t)n), row_b((size_t)n) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned long gen = generation;
+        if (++waiting == P) { waiting = 0; generation++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return generation != gen; });
+    }
+};
+struct ThreadFabric : Fabric {
+    Hub &hub;
+    Exec &ex;
+    int me;
+    ThreadFabric(Hub &h, Exec &e, int rank) : hub(h), ex(e), me(rank)
+    {
+        P = h.P;
+        mine.push_back(rank);
+    }
+    int allgather_host(const void *const *contrib, void *const *all, size_t bytes) override
+    {
+        hub.ptr[(size_t)me] = contrib[0];
+        hub.wait();
+        for (int r = 0; r < P; r++) memcpy((char *)all[0] + (size_t)r * bytes, hub.ptr[(size_t)r], bytes);
+        hub.wait();
+        return GB_OK;
+    }
+    int windows(const size_t *bytes_of_rank, void **window, PeerPtrs *peers) override
+    {
+        GB_TRY(sg_alloc(ex, &window[0], bytes_of_rank[me]));
+        hub.ptr[(size_t)me] = window[0];
+        hub.wait();
+        for (int r = 0; r < P; r++) peers[0].p[r] = (void *)hub.ptr[(size_t)r];
+        hub.wait();
+        return GB_OK;
+    }
+    int alltoallv_u64(const u64 *const *send, const Row *soff, const Row *scnt, u64 *const *recv, const Row *roff, const Row *rcnt) override
+    {
+        hub.ptr[(size_t)me] = send[0];
+        hub.row_a[(size_t)me] = soff[0];
+        hub.row_b[(size_t)me] = scnt[0];
+        hub.wait();
+        int rc = GB_OK;
+        for (int p = 0; p < P; p++) {
+            if (hub.row_b[(size_t)p].v[me] != rcnt[0].v[p]) rc = GB_E_INVARIANT;
+            else memcpy(recv[0] + roff[0].v[p], (const u64 *)hub.ptr[(size_t)p] + hub.row_a[(size_t)p].v[me], (size_t)rcnt[0].v[p] * 8);
+        }
+        hub.wait();
+        return rc;
+    }
+    int barrier() override { hub.wait(); return GB_OK; }
+    int allgatherv_u64(u64 *const *buf, const u64 *off, const u64 *cnt) override
+    {
+        hub.ptr[(size_t)me] = buf[0];
+        hub.wait();
+        for (int p = 0; p < P; p++)
+            if (p != me) memcpy(buf[0] + off[p], (const u64 *)hub.ptr[(size_t)p] + off[p], (size_t)cnt[p] * 8);
+        hub.wait();
+        return GB_OK;
+    }
+    int allreduce_sum(void *buf, size_t count, int elem_bytes) override
+    {
+        hub.ptr[(size_t)me] = buf;
+        hub.wait();
+        std::vector<u64> sum(count, 0);
+        for (int p = 0; p < P; p++)
+            for (size_t i = 0; i < count; i++)
+                sum[i] += elem_bytes == 8 ? ((const u64 *)hub.ptr[(size_t)p])[i] : (u64)((const u32 *)hub.ptr[(size_t)p])[i];
+        hub.wait();
+        for (size_t i = 0; i < count; i++) {
+            if (elem_bytes == 8) ((u64 *)buf)[i] = sum[i];
+            else ((u32 *)buf)[i] = (u32)sum[i];
+        }
+        hub.wait();
+        return GB_OK;
+    }
+};
+
 extern "C" {
+
+// the build with one thread per rank (ThreadFabric): every rank's copy of the result must be the same graph.  Returns 0, a
+// GB_E_* code, or 1000 + r when rank r's copy differs from rank 0's.  Output = rank 0's copy (same layout as below).
+int emul_sharded_build_threads(int k, int dual, int v210, int P, const uint64_t *keys, const uint64_t *off, uint64_t *out,
+                               uint64_t *node_kmer, uint32_t *edge_start, uint32_t *edge_end, uint64_t *edge_off, uint32_t *bases)
+{
+    Hub hub(P);
+    std::vector<Exec> ex((size_t)P);
+    std::vector<Result> res((size_t)P);
+    std::vector<int> rcs((size_t)P, 0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < P; r++)
+        th.emplace_back([&, r] {
+            ThreadFabric fab(hub, ex[(size_t)r], r);
+            std::vector<RankInput> in{ RankInput{ &ex[(size_t)r], (const u64 *)keys + off[r], off[r + 1] - off[r] } };
+            rcs[(size_t)r] = build(fab, in, k, dual != 0, v210 != 0, &res[(size_t)r]);
+        });
+    for (auto &t : th) t.join();
+    for (int r = 0; r < P; r++)
+        if (rcs[(size_t)r] != GB_OK) return rcs[(size_t)r];
+    const Result &a = res[0];
+    for (int r = 1; r < P; r++) {
+        const Result &b = res[(size_t)r];
+        if (a.n_nodes != b.n_nodes || a.n_edges != b.n_edges || a.n_bases != b.n_bases || a.segments != b.segments ||
+            a.cycle_vertices != b.cycle_vertices || memcmp(a.node_kmer, b.node_kmer, a.n_nodes * 8) ||
+            memcmp(a.edge_start, b.edge_start, a.n_edges * 4) || memcmp(a.edge_end, b.edge_end, a.n_edges * 4) ||
+            memcmp(a.edge_off, b.edge_off, (a.n_edges + 1) * 8) || memcmp(a.bases, b.bases, ((a.n_bases + 15) / 16) * 4))
+            return 1000 + r;
+    }
+    out[0] = a.n_nodes; out[1] = a.n_edges; out[2] = a.n_bases;
+    out[3] = a.kept; out[4] = a.segments; out[5] = a.cycle_vertices; out[6] = (uint64_t)a.jump_rounds; out[7] = (uint64_t)a.seg_rounds;
+    if (node_kmer) {
+        memcpy(node_kmer, a.node_kmer, a.n_nodes * 8);
+        memcpy(edge_start, a.edge_start, a.n_edges * 4);
+        memcpy(edge_end, a.edge_end, a.n_edges * 4);
+        memcpy(edge_off, a.edge_off, (a.n_edges + 1) * 8);
+        memcpy(bases, a.bases, ((a.n_bases + 15) / 16) * 4);
+    }
+    return 0;
+}
 
 // the sharded build over P in-process ranks; rank r starts with keys[off[r] .. off[r + 1]).  Two-call pattern: with
 // node_kmer == NULL only the sizes (out[0..2] = nodes, edges, bases) and stats (out[3..7] = kept, segments, cycle vertices,

@@ -27,7 +27,7 @@ def emul():
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
-                               "-I" + cuda_inc, "-o", out, src])
+                               "-pthread", "-I" + cuda_inc, "-o", out, src])
     return C.CDLL(out)
 
 
@@ -35,7 +35,7 @@ def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def sharded_build(emul, k, keys, P, dual=False, split="even", seed=0):
+def sharded_build(emul, k, keys, P, dual=False, split="even", seed=0, threads=False):
     """Runs the emulated build with the kept keys dealt to P ranks (`split`: even / skewed / all on the last rank) and
     returns (canonical graph as in tests/helpers.py, stats dict)."""
     keys = np.ascontiguousarray(keys, np.uint64)
@@ -50,7 +50,8 @@ def sharded_build(emul, k, keys, P, dual=False, split="even", seed=0):
         cuts = [0] * P + [keys.size]
     off = np.array(cuts, np.uint64)
     out = np.zeros(8, np.uint64)
-    rc = emul.emul_sharded_build(k, int(dual), 0, P, ptr(keys), ptr(off), ptr(out), None, None, None, None, None)
+    fn = emul.emul_sharded_build_threads if threads else emul.emul_sharded_build
+    rc = fn(k, int(dual), 0, P, ptr(keys), ptr(off), ptr(out), None, None, None, None, None)
     assert rc == 0, rc
     N, E, B = int(out[0]), int(out[1]), int(out[2])
     node_kmer = np.zeros(max(N, 1), np.uint64)
@@ -58,7 +59,7 @@ def sharded_build(emul, k, keys, P, dual=False, split="even", seed=0):
     ee = np.zeros(max(E, 1), np.uint32)
     eo = np.zeros(E + 1, np.uint64)
     words = np.zeros((B + 15) // 16 + 1, np.uint32)
-    rc = emul.emul_sharded_build(k, int(dual), 0, P, ptr(keys), ptr(off), ptr(out), ptr(node_kmer), ptr(es), ptr(ee), ptr(eo), ptr(words))
+    rc = fn(k, int(dual), 0, P, ptr(keys), ptr(off), ptr(out), ptr(node_kmer), ptr(es), ptr(ee), ptr(eo), ptr(words))
     assert rc == 0
     bases = np.zeros(words.size * 16, np.uint8)
     for j in range(16):
@@ -215,3 +216,30 @@ def test_empty_and_tiny_inputs(emul):
         got, counts, _ = sharded_build(emul, 15, keys, P)
         assert counts == og.counts() == (4, 2, 2)
         assert got == H.canon_oracle_graph(og)
+
+
+@pytest.mark.parametrize("k,glen,rl,cov,err,rounds", [c for c in GRAPH_CASES if c[0] in (31, 21, 9, 8, 4)])
+def test_one_thread_per_rank_matches_oracle(emul, k, glen, rl, cov, err, rounds):
+    """The one-process-per-GPU control flow: P threads, each driving ONE rank through its own Fabric object, its own copy of
+    the global graph arrays, real sums and exchanges between the copies (ThreadFabric in tests/emul/sgraph_emul.cpp).  Every
+    rank must end with the same graph, equal to the oracle's; vertex numbering is deterministic here, so the emulated ranks'
+    copies are compared byte for byte."""
+    b, n, _ = H.small_reads(glen, rl, cov, err, seed=2000 + k)
+    om, og = oracle_graph(b, n, k, rounds)
+    want = H.canon_oracle_graph(og)
+    keys, _ = om.export()
+    for P, split in [(2, "even"), (4, "skewed"), (8, "even"), (8, "last")]:
+        got, counts, st = sharded_build(emul, k, keys, P, split=split, seed=P, threads=True)
+        assert counts == og.counts(), (P, split)
+        assert got == want, (P, split)
+
+
+def test_one_thread_per_rank_cycle_and_dual(emul):
+    k = 11
+    genome = synth.random_genome(500, 8)
+    circ = np.concatenate([genome, genome[:k - 1]])
+    keys = np.array([pyoracle.canonical(synth.kmer_to_int(synth.decode(circ[i:i + k])), k) for i in range(genome.size)], np.uint64)
+    got, counts, st = sharded_build(emul, k, keys, 4, threads=True)
+    assert counts == (0, 0, 0) and st["cycle_vertices"] == 2 * genome.size
+    got, counts, st = sharded_build(emul, 15, np.zeros(0, np.uint64), 3, threads=True)
+    assert counts == (0, 0, 0)
