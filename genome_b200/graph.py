@@ -132,7 +132,8 @@ class MapGraph:
     def stats(self):
         s = (C.c_int64 * 8)()
         capi.check(capi.lib().gb_graph_stats(self.h, s))
-        return dict(kept_kmers=s[0], jump_launches=s[1], cycle_vertices=s[2], build_ns=s[3],
+        # s[4] is shared: a graph fresh from the sharded build reports its segment count there until pairSupport overwrites it
+        return dict(kept_kmers=s[0], jump_launches=s[1], cycle_vertices=s[2], build_ns=s[3], segments=s[4],
                     pair_support_map_ns=s[4], pair_support_filter_ns=s[5], pair_support_walk_ns=s[6], pair_support_cases=s[7])
 
 

@@ -1,0 +1,21 @@
+#!/bin/bash
+# First GPU call of round 2: everything that was written after round 1's GPU budget ran out, in one gpurun call.
+#   gpurun --timeout 1500 -- 'bash scripts/r2_validate.sh'            (1 GPU: virtual shards, graph map handle, CheckGraph)
+#   gpurun --gpus 2 --timeout 1500 -- 'bash scripts/r2_validate.sh'   (adds the NCCL + IPC fabric at 2 ranks)
+# Writes gpurun_out/r2_validate.log, gpurun_out/r2_sgraph_timing.json.  No -x: every opt-in test reports on its own.
+mkdir -p gpurun_out
+export GENOME_B200_UNVALIDATED=1
+{
+  echo "== opt-in device tests"
+  timeout 1200 python -m pytest tests/test_sgraph_gpu.py tests/test_graphmap_gpu.py -q -m gpu 2>&1 | tail -25
+  NGPU=$(python -c "import torch; print(torch.cuda.device_count())")
+  if [ "$NGPU" -ge 2 ]; then
+    echo "== sharded graph build over $NGPU ranks"
+    timeout 900 python -m pytest tests/test_parity_multigpu.py -q -m gpu -k sharded_graph_build 2>&1 | tail -15
+  fi
+  echo "== timing: single-GPU build vs virtual shards (C2)"
+  timeout 600 python scripts/sgraph_timing.py > gpurun_out/r2_sgraph_timing.json 2> gpurun_out/r2_sgraph_timing.err
+  tail -5 gpurun_out/r2_sgraph_timing.json
+  tail -5 gpurun_out/r2_sgraph_timing.err
+} > gpurun_out/r2_validate.log 2>&1
+tail -60 gpurun_out/r2_validate.log

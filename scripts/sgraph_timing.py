@@ -1,0 +1,47 @@
+"""Graph.buildGraph on one GPU: the single-GPU build against the sharded build over P virtual ranks (csrc/sgraph.cuh), same
+filtered table.  One JSON object on stdout; GENOME_B200_TRACE=1 adds the per-phase trace of the single-GPU build on stderr.
+Usage: python scripts/sgraph_timing.py [C2] [scale]"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from genome_b200 import synth  # noqa: E402
+from genome_b200.dnamap import ArrayDNAMap  # noqa: E402
+from genome_b200.graph import Graph  # noqa: E402
+
+cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
+scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+K = 31
+b, n, _ = synth.make_config(cfg, scale=scale)
+m = ArrayDNAMap(K, int(b.size * 1.2))
+m.insert_reads(b, n)
+m.delete_below(3)
+out = {"workload": cfg, "scale": scale, "kept_kmers": m.size, "builds": []}
+
+
+def timed(label, build):
+    best = None
+    for rep in range(4):   # the first passes settle the arenas
+        m.sync()
+        t0 = time.perf_counter()
+        g = build()
+        m.sync()
+        ms = (time.perf_counter() - t0) * 1e3
+        st = g.stats()
+        rec = {"build": label, "wall_ms": ms, "device_ms": st["build_ns"] * 1e-6, "counts": g.counts(), "jump_launches": st["jump_launches"],
+               "cycle_vertices": st["cycle_vertices"], "segments": st["segments"] if label != "single" else 0}
+        g.close()
+        if rep >= 2 and (best is None or rec["device_ms"] < best["device_ms"]):
+            best = rec
+    out["builds"].append(best)
+    sys.stderr.write("%s\n" % best)
+
+
+timed("single", lambda: Graph.buildGraph(K, m))
+for P in (1, 2, 4, 8):
+    timed("virtual_shards_%d" % P, lambda: Graph.buildGraphVirtualShards(K, m, P))
+ref = out["builds"][0]["counts"]
+out["all_equal_counts"] = all(r["counts"] == ref for r in out["builds"])
+print(json.dumps(out))
