@@ -27,7 +27,8 @@ def emul():
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
-                               "-pthread", "-I" + cuda_inc, "-o", out, src])
+                               "-pthread", "-Wl,-Bsymbolic", "-I" + cuda_inc, "-o", out, src])   # -Bsymbolic: the library binds its own
+        # gb::sg::* symbols; the product library (loaded RTLD_GLOBAL by genome_b200.capi) exports the CUDA versions of them
     return C.CDLL(out)
 
 

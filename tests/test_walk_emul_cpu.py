@@ -28,7 +28,8 @@ def emul():
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
-                               "-I" + cuda_inc, "-o", out, src])
+                               "-Wl,-Bsymbolic", "-I" + cuda_inc, "-o", out, src])   # own symbols first: the product library
+        # (loaded RTLD_GLOBAL by genome_b200.capi) exports functions of the same names
     return C.CDLL(out)
 
 
