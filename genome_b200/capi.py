@@ -74,6 +74,8 @@ SIGNATURES = {
     "gb_graph_map_get_all": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _vp]),
     "gb_graph_pair_support": (C.c_int, [_vp, _vp, _sz, _i64, C.c_int, C.c_int, _vp, _pi64, _pi64]),
     "gb_graph_split_nodes": (C.c_int, [_vp, _vp, _i32, _pi64, _pi64]),
+    "gb_comm_allreduce_sum_u32": (C.c_int, [_vp, _vp, _i64]),
+    "gb_comm_allreduce_sum_i64": (C.c_int, [_vp, _vp, _i64]),
     "gb_comm_unique_id": (C.c_int, [_vp]),
     "gb_comm_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _pp]),
     "gb_comm_destroy": (C.c_int, [_vp]),

@@ -681,6 +681,30 @@ int gb_comm_destroy(gb_comm *h)
     return GB_OK;
 }
 
+// element-wise sum of a HOST array over the ranks, in place (host composition of per-rank partial results: the paired-end
+// support counts of GraphSimplifier.scala:239-245 when every rank walks its own slice of the pairs on its copy of the graph)
+static int comm_allreduce_host(gb_comm *h, void *host, int64_t n, size_t elem, ncclDataType_t type)
+{
+    if (!h) { set_error("null communicator"); return GB_E_ARG; }
+    if (n < 0 || (n > 0 && !host)) { set_error("bad arguments"); return GB_E_ARG; }
+    Comm *c = reinterpret_cast<Comm *>(h);
+    GB_CUDA(cudaSetDevice(c->device));
+    // collective even when n == 0 on this rank would be a mismatch: n must be the same everywhere (documented)
+    if (n == 0) return GB_OK;
+    void *d = nullptr;
+    GB_CUDA(cudaMalloc(&d, (size_t)n * elem));
+    int rc = GB_OK;
+    if (cudaMemcpyAsync(d, host, (size_t)n * elem, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = GB_E_CUDA;
+    if (rc == GB_OK && ncclAllReduce(d, d, (size_t)n, type, ncclSum, c->nccl, c->stream) != ncclSuccess) rc = GB_E_NCCL;
+    if (rc == GB_OK && cudaMemcpyAsync(host, d, (size_t)n * elem, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = GB_E_CUDA;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == GB_OK) rc = GB_E_CUDA;
+    cudaFree(d);
+    if (rc != GB_OK) set_error("all-reduce of %lld host elements failed", (long long)n);
+    return rc;
+}
+int gb_comm_allreduce_sum_u32(gb_comm *h, uint32_t *host, int64_t n) { return comm_allreduce_host(h, host, n, 4, ncclUint32); }
+int gb_comm_allreduce_sum_i64(gb_comm *h, int64_t *host, int64_t n) { return comm_allreduce_host(h, host, n, 8, ncclInt64); }
+
 int gb_pmap_create(gb_comm *ch, int k, int64_t min_capacity_per_shard, uint32_t flags, gb_map **out)
 {
     if (!ch) { set_error("null communicator"); return GB_E_ARG; }

@@ -65,6 +65,17 @@ class PairedEndData:
         off[self.n_reads] = pos
         return off
 
+    def take(self, n_pairs):
+        """The first n_pairs pairs (`data.getPairs.take(takeFirst)`, GraphSimplifier.scala:211)."""
+        n_pairs = min(int(n_pairs), self.count)
+        if n_pairs == self.count:
+            return self
+        if self.bin.size and self.n_reads and _fixed_record(self.bin, self.n_reads):
+            rec = 1 + (int(self.bin[0]) + 3) // 4
+            return PairedEndData(self.bin[:2 * n_pairs * rec], n_pairs, self.insert)
+        off = self.record_offsets()
+        return PairedEndData(self.bin[:int(off[2 * n_pairs])], n_pairs, self.insert)
+
     def shard(self, rank, world):
         """This rank's slice of the pair stream, in file order (pairs are never split)."""
         lo, hi = shard_range(self.count, rank, world)
@@ -261,6 +272,16 @@ class Communicator:
         capi.check(capi.lib().gb_comm_create(capi.ptr(ident), int(rank), int(world), int(device), C.byref(h)))
         self.h = h
         self.rank, self.world, self.device = rank, world, device
+
+    def allreduce_sum(self, a):
+        """Element-wise sum over the ranks of a uint32 or int64 host array, in place (same shape on every rank)."""
+        if a.dtype == np.uint32:
+            capi.check(capi.lib().gb_comm_allreduce_sum_u32(self.h, capi.ptr(a), a.size))
+        elif a.dtype == np.int64:
+            capi.check(capi.lib().gb_comm_allreduce_sum_i64(self.h, capi.ptr(a), a.size))
+        else:
+            raise TypeError("uint32 or int64")
+        return a
 
     def close(self):
         if getattr(self, "h", None):

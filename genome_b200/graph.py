@@ -105,16 +105,25 @@ class MapGraph:
         capi.check(capi.lib().gb_graph_map_create(self.h, C.byref(h)))
         return GraphPositionMap(h, self.k)
 
-    def pairSupport(self, data, takeFirst=None, range_=(180, 250)):
+    def pairSupport(self, data, takeFirst=None, range_=(180, 250), comm=None):
         """The pair loop of GraphSimplifier.startup (S/scripts/GraphSimplifier.scala:188-263): graphMap.getAll of the first
         k-mers of both reads in both orientations, annotate, and the WalkingActor walks (33-127), for the first `takeFirst`
         pairs of `data` (a PairedEndData).  Returns (support uint32[n_edges, 4], badPairs, walked cases) with
         support[e1, b] = pathsMap((e1, e2)), e2 = the out-edge of e1's end node starting with base b; `range_` is the
-        reference's `180 to 250` (153)."""
+        reference's `180 to 250` (153).  `comm` (a Communicator): the pair loop is split over its ranks."""
         n_pairs = data.count if takeFirst is None else min(int(takeFirst), data.count)
         ne = self.counts()[1]
         support = np.zeros((ne, 4), np.uint32)
         bad, walked = C.c_int64(), C.c_int64()
+        if comm is not None and comm.world > 1:
+            # every rank holds the same graph (Graph.buildGraph over a PartitionedDNAMap) and ALL pairs: it walks its own
+            # slice of the first n_pairs pairs, then the per-rank counts are summed (pairs are independent, 213-248)
+            mine = data.take(n_pairs).shard(comm.rank, comm.world)
+            capi.check(capi.lib().gb_graph_pair_support(self.h, capi.ptr(mine.bin), mine.bin.size, mine.count, int(range_[0]),
+                                                        int(range_[1]), capi.ptr(support), C.byref(bad), C.byref(walked)))
+            comm.allreduce_sum(support)
+            tot = comm.allreduce_sum(np.array([bad.value, walked.value], np.int64))
+            return support, int(tot[0]), int(tot[1])
         capi.check(capi.lib().gb_graph_pair_support(self.h, capi.ptr(data.bin), data.bin.size, n_pairs, int(range_[0]), int(range_[1]),
                                                     capi.ptr(support), C.byref(bad), C.byref(walked)))
         return support, bad.value, walked.value

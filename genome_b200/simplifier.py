@@ -16,11 +16,11 @@ class GraphSimplifier:
         self.takeFirst = takeFirst
         self.log = {}
 
-    def startup(self, graph, data, outfile=None, contigs=None):
+    def startup(self, graph, data, outfile=None, contigs=None, comm=None):
         """One iteration (`for (it <- 0 until 1)`, 156) on a MapGraph and a PairedEndData; the graph is modified in place.
         `outfile` receives the per-node matrices (line format of 312), `contigs` the contig file (338-347)."""
         graph.check()                                                   # the asserts of 159-170
-        support, bad, walked = graph.pairSupport(data, self.takeFirst, self.range)
+        support, bad, walked = graph.pairSupport(data, self.takeFirst, self.range, comm)  # comm: pairs split over the GPUs
         self.log["bad_pairs"] = bad                                     # "Bad pairs: " (265)
         self.log["walked_cases"] = walked
         if outfile is not None:

@@ -187,6 +187,11 @@ int gb_graph_stats(gb_graph *g, int64_t stats[8]);
 int gb_comm_unique_id(uint8_t id[GB_UNIQUE_ID_BYTES]);            /* rank 0, then broadcast by the host */
 int gb_comm_create(const uint8_t id[GB_UNIQUE_ID_BYTES], int rank, int n_ranks, int device, gb_comm **out);
 int gb_comm_destroy(gb_comm *c);
+/* Element-wise sum over the ranks of a HOST array, in place; collective, same n on every rank.  For host-side compositions of
+ * per-rank partial results: with the graph identical on every rank (gb_pmap_graph_build), each rank runs gb_graph_pair_support
+ * on its own slice of the pairs and the support counts, badPairs and walked cases are summed (GraphSimplifier.scala:239-265). */
+int gb_comm_allreduce_sum_u32(gb_comm *c, uint32_t *host, int64_t n);
+int gb_comm_allreduce_sum_i64(gb_comm *c, int64_t *host, int64_t n);
 
 /* new PartitionedDNAMap[Int](k) (PartitionedDNAMap.scala:15-28): this rank's shard, bound to the communicator */
 int gb_pmap_create(gb_comm *c, int k, int64_t min_capacity_per_shard, uint32_t flags, gb_map **out);

@@ -11,7 +11,7 @@ export GENOME_B200_UNVALIDATED=1
   NGPU=$(python -c "import torch; print(torch.cuda.device_count())")
   if [ "$NGPU" -ge 2 ]; then
     echo "== sharded graph build over $NGPU ranks"
-    timeout 900 python -m pytest tests/test_parity_multigpu.py -q -m gpu -k sharded_graph_build 2>&1 | tail -15
+    timeout 900 python -m pytest tests/test_parity_multigpu.py -q -m gpu -k "sharded_graph_build or pmap_matches_oracle" 2>&1 | tail -20
   fi
   echo "== timing: single-GPU build vs virtual shards (C2)"
   timeout 600 python scripts/sgraph_timing.py > gpurun_out/r2_sgraph_timing.json 2> gpurun_out/r2_sgraph_timing.err

@@ -89,11 +89,47 @@ def main():
     gk, gv = m.export_sorted()
     assert np.array_equal(gk, ok[sel]) and np.array_equal(gv, ov[sel])
     m.close()
+    if os.environ.get("GENOME_B200_UNVALIDATED"):
+        pair_support_over_ranks(comm, rank, world)
     dist.barrier()
     comm.close()
     if rank == 0:
         print("PMAP OK world", world)
     dist.destroy_process_group()
+
+
+def pair_support_over_ranks(comm, rank, world):
+    """GraphSimplifier's pair loop split over the ranks (MapGraph.pairSupport(comm=...)): the graph is built from the shards
+    (identical on every rank), every rank walks its slice of the pairs, counts are summed; against the oracle's pathsMap.
+    Opt-in (GENOME_B200_UNVALIDATED=1) until it has passed on a multi-GPU box."""
+    from genome_b200 import synth
+    from genome_b200.simplifier import GraphSimplifier
+    k, L = 15, 50
+    genome = synth.random_genome(6000, 91)
+    n_reads = (int(40 * 6000 / L) // 2) * 2
+    reads = synth.sample_reads(genome, L, n_reads, 0.02, 92, insert=(60, 100))
+    b = synth.pack_fixed(reads)
+    data = PairedEndData(b, n_reads // 2)
+    m = PartitionedDNAMap(k, comm)
+    m.insert_reads(data.shard(rank, world))
+    m.delete_below(2)
+    om, _ = H.oracle_counts(b, n_reads, k)
+    om.delete_below(2)
+    g = Graph.buildGraph(k, m)
+    og = pyoracle.OracleGraph(om)
+    H.assert_graph_equal(g, og)
+    support, bad, walked = g.pairSupport(data, None, (90, 155), comm)
+    e1, e2, cnt, obad, owalked = og.pair_support(b, n_reads // 2, 90, 155)
+    assert (bad, walked) == (obad, owalked), (bad, walked, obad, owalked)
+    assert int(support.sum()) == int(np.sum(cnt)) and int((support > 0).sum()) == len(cnt)
+    single = g.pairSupport(data, None, (90, 155))   # every rank alone on all pairs: same counts
+    assert np.array_equal(single[0], support) and single[1:] == (bad, walked)
+    GraphSimplifier((90, 155), cutoff=3).startup(g, data, comm=comm)
+    removed, added = og.split(e1, e2, cnt, 3)
+    og.simplify()
+    H.assert_graph_equal(g, og)
+    g.close()
+    m.close()
 
 
 if __name__ == "__main__":

@@ -298,3 +298,39 @@ def test_graph_map_get_all_matches_oracle(emul, case):
     c2 = np.zeros(keys.size, np.uint32)
     emul.emul_graph_map_get_all(C.c_uint64(pk.size), ptr(pk), ptr(pi), ptr(pd), C.c_uint64(keys.size), ptr(keys), 0, None, None, ptr(c2))
     assert np.array_equal(c2, counts)
+
+
+def test_pair_support_is_additive_over_pair_slices(emul):
+    """The multi-GPU form of the pair loop (MapGraph.pairSupport(comm=...)): every rank walks its own contiguous slice of the
+    pairs on its copy of the graph and the counts are summed.  Pairs are independent (GraphSimplifier.scala:213-248), so the
+    sum over PairedEndData.shard slices must equal the whole -- checked here through the emulated device code, with the
+    slices cut by the same host code the ranks use (fixed and ragged records)."""
+    from genome_b200.dnamap import PairedEndData
+    k, L = 15, 50
+    for ragged in (False, True):
+        og, b, n_reads = noisy_graph(k, 6000, L, 40, 0.02, 91, (60, 100), rounds=2, ragged=ragged)
+        lay = DeviceLayout(og)
+        whole, bad, walked, over = emul_support(emul, lay, og, b, n_reads // 2, 90, 155)
+        assert over == 0 and walked > 0
+        data = PairedEndData(b, n_reads // 2)
+        for world in (2, 3, 8):
+            acc = np.zeros_like(whole)
+            tb = tw = tp = 0
+            for rank in range(world):
+                mine = data.shard(rank, world)
+                s, sb, sw, so = emul_support(emul, lay, og, mine.bin, mine.count, 90, 155)
+                assert so == 0
+                acc += s
+                tb, tw, tp = tb + sb, tw + sw, tp + mine.count
+            assert tp == data.count
+            assert (tb, tw) == (bad, walked)
+            assert np.array_equal(acc, whole)
+        # takeFirst, then the slices of that prefix
+        first = data.take(data.count // 3)
+        wf, bf, wkf, _ = emul_support(emul, lay, og, first.bin, first.count, 90, 155)
+        acc = np.zeros_like(wf)
+        for rank in range(4):
+            mine = first.shard(rank, 4)
+            acc += emul_support(emul, lay, og, mine.bin, mine.count, 90, 155)[0]
+        assert np.array_equal(acc, wf)
+        assert first.count == data.count // 3 and data.take(10 ** 9) is data
