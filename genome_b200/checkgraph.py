@@ -3,6 +3,7 @@ S/ = src/main/scala/ru/ifmo/genome/):
 
   CheckGraph.startup   S/scripts/CheckGraph.scala:18-56   contig statistics + "is every k-mer of a FASTA on the graph"
   N50                  S/scripts/N50.scala:11-32          the N50 of a logged `length -> count` histogram line
+  KmersCalculator      S/scripts/KmersCalculator.scala:16-28   distinct k-windows (as read, not canonical) of a one-record FASTA
 
 CheckGraph's per-window `graphMap.contains(read)()` round trip (line 51) becomes one bulk `GraphPositionMap.contains` per
 FASTA line.  Host logic only; the device work is behind MapGraph.graphMap().
@@ -87,3 +88,38 @@ def n50(line):
             out.append((a, b))
         run += a * b
     return out, pairs, sum(b for a, b in pairs if a >= 100)
+
+
+def sequence_windows(fasta_lines, k):
+    """KmersCalculator.scala:23-27: `getLines().drop(1)` (only the FIRST line is treated as a header), all characters
+    concatenated, every character must be a base (`Base.fromChar` throws otherwise), then `seq.sliding(k)`.  Returns
+    (sequence length, k-windows as u64 in reading order).  A sequence shorter than k yields Scala's single short window, which
+    is one distinct sequence: reported as one window of value 0 with `short=True` in the third element."""
+    it = iter(fasta_lines)
+    next(it, None)
+    text = "".join(line.rstrip("\r\n") for line in it)
+    bad = [c for c in set(text) if c not in _CODE]
+    if bad:
+        raise ValueError("not a base: %r (Base.fromChar, S/dna/Base.scala:20)" % bad[0])
+    n = len(text)
+    if n == 0:
+        return 0, np.zeros(0, np.uint64), False
+    if n < k:
+        return n, np.zeros(1, np.uint64), True
+    codes = np.array([_CODE[c] for c in text], np.uint64)
+    keys = np.zeros(n - k + 1, np.uint64)
+    for j in range(k):
+        keys |= codes[j:n - k + 1 + j] << np.uint64(2 * j)
+    return n, keys, False
+
+
+def kmers_calculator(fasta_lines, k=19):
+    """KmersCalculator (k = 19 hard-coded there, line 21): (sequence length, number of distinct k-windows) with the windows
+    counted on the device: a DNAMap of the windows AS READ (`update` without canonicalisation), then `size`."""
+    from .dnamap import ArrayDNAMap
+    n, keys, short = sequence_windows(fasta_lines, k)
+    if short or keys.size == 0:
+        return n, int(keys.size)
+    with ArrayDNAMap(k, int(keys.size * 2)) as m:
+        m.update_counts(keys)
+        return n, m.size

@@ -174,3 +174,17 @@ def test_checkgraph_host_logic():
     out, pairs, ge100 = CG.n50("hist: Map(100 -> 2, 50 -> 4, 300 -> 1, 7 -> 9)")
     assert pairs == [(50, 4), (100, 2), (300, 1)] and ge100 == 3
     assert out == [(100, 2)]   # total 700: 200 < 350 <= 400
+
+
+def test_kmers_calculator_windows():
+    """KmersCalculator.scala:23-27, host part: header dropped, lines concatenated, windows in reading order (not canonical)."""
+    from genome_b200 import checkgraph as CG
+    n, keys, short = CG.sequence_windows([">chr1 test\n", "ACGTAC\n", "GTTA\n"], 4)
+    text = "ACGTACGTTA"
+    assert n == 10 and not short
+    assert [synth.int_to_kmer(int(x), 4) for x in keys] == [text[i:i + 4] for i in range(7)]
+    assert len(set(keys.tolist())) == len({text[i:i + 4] for i in range(7)}) == 6   # ACGT twice
+    assert CG.sequence_windows([">h", "ACG"], 4) == (3, pytest.approx(np.zeros(1)), True)
+    assert CG.sequence_windows([">h"], 4)[0] == 0
+    with pytest.raises(ValueError):
+        CG.sequence_windows([">h", "ACNT"], 2)

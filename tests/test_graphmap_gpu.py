@@ -100,3 +100,15 @@ def test_check_graph_finds_every_genome_kmer(gpu):
     assert stats["max"] > 200 and stats["count"] >= 1
     lens = sorted(set(m[0] for m in missing))
     assert lens == [300] and len(missing) == 300 - k + 1   # only the unrelated line (and none of "ACGTN": no full window)
+
+
+@pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")
+def test_kmers_calculator(gpu):
+    """KmersCalculator (S/scripts/KmersCalculator.scala:16-28): distinct k-windows of a FASTA record, counted on the device."""
+    from genome_b200 import checkgraph, synth
+    text = synth.decode(synth.random_genome(50000, 5))
+    text = text + text[1000:9000]   # a repeat: 8000 - 18 windows seen twice
+    lines = [">x"] + [text[i:i + 70] for i in range(0, len(text), 70)]
+    n, distinct = checkgraph.kmers_calculator(lines, 19)
+    assert n == len(text)
+    assert distinct == len({text[i:i + 19] for i in range(len(text) - 18)})
