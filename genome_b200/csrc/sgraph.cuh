@@ -181,22 +181,35 @@ SG_HD u32 owner_of_kmer(u64 x, int k, int m, int P)
     const MinParts mp = min_parts(x, revcomp(x, k), k, m);
     return owner_from_hash(min3(mp.first, mp.mid, mp.last), P);
 }
-// owner of x.drop(1) :+ b (succ = true) or b +: x.take(k-1) (succ = false), from the parts of x
-SG_HD u32 neighbour_owner(const MinParts &mp, u64 x, u64 rcx, int k, int m, int P, bool succ, u32 b)
+// the neighbour x.drop(1) :+ b (succ = true) or b +: x.take(k-1) (succ = false): the k-mer, its reverse complement (one shift
+// of rc(x), no bit reversal) and its owner from the parts of x
+struct Neighbour {
+    u64 q, rq;
+    u32 owner;
+};
+SG_HD Neighbour neighbour_of(const MinParts &mp, u64 x, u64 rcx, int k, int m, int P, bool succ, u32 b)
 {
     const u64 mm = (1ull << (2 * m)) - 1;
     const int w = k - m + 1;
+    Neighbour nb;
     u32 h;
     if (succ) {
-        const u64 q = kmer_append(x, k, b), rq = kmer_prepend(rcx, k, 3u - b);
-        const u32 hn = mmer_hash((q >> (2 * (w - 1))) & mm, rq & mm);
+        nb.q = kmer_append(x, k, b);
+        nb.rq = kmer_prepend(rcx, k, 3u - b);
+        const u32 hn = mmer_hash((nb.q >> (2 * (w - 1))) & mm, nb.rq & mm);
         h = w > 1 ? min3(mp.mid, mp.last, hn) : hn;
     } else {
-        const u64 q = kmer_prepend(x, k, b), rq = kmer_append(rcx, k, 3u - b);
-        const u32 hn = mmer_hash(q & mm, (rq >> (2 * (k - m))) & mm);
+        nb.q = kmer_prepend(x, k, b);
+        nb.rq = kmer_append(rcx, k, 3u - b);
+        const u32 hn = mmer_hash(nb.q & mm, (nb.rq >> (2 * (k - m))) & mm);
         h = w > 1 ? min3(mp.first, mp.mid, hn) : hn;
     }
-    return owner_from_hash(h, P);
+    nb.owner = owner_from_hash(h, P);
+    return nb;
+}
+SG_HD u32 neighbour_owner(const MinParts &mp, u64 x, u64 rcx, int k, int m, int P, bool succ, u32 b)
+{
+    return neighbour_of(mp, x, rcx, k, m, P, succ, b).owner;
 }
 
 // ---- membership in one rank's index
@@ -214,10 +227,9 @@ SG_HD bool probe_idx(const Peer &t, u64 key, u32 *vid)
 // Graph.buildGraph.contains (Graph.scala:270) with the orientation rules of common.cuh find_oriented: one probe of the
 // canonical orientation unless the two hashes tie or keys were inserted as-is (dual); if both orientations are stored the
 // numerically smaller key is the primary one.  *g = the primary vertex, strand bit set when the stored key is rc(q) != q.
-SG_HD bool find_g(const Ctx &c, u32 owner, u64 q, u32 *g)
+SG_HD bool find_g(const Ctx &c, u32 owner, u64 q, u64 r /* = revcomp(q) */, u32 *g)
 {
     const Peer &t = c.peer[owner];
-    const u64 r = revcomp(q, c.k);
     const int hq = khash(c, q), hr = khash(c, r);
     u32 v;
     if (!c.dual && hq != hr) {
@@ -331,8 +343,9 @@ struct MasksOp { // incoming / outcoming (Graph.scala:272-282) of every stored k
             const MinParts mp = min_parts(x, rcx, c.k, c.m);
             for (u32 b = 0; b < 4; b++) {
                 u32 g;
-                if (find_g(c, neighbour_owner(mp, x, rcx, c.k, c.m, c.P, true, b), kmer_append(x, c.k, b), &g)) { out |= 1u << b; so = g; }
-                if (find_g(c, neighbour_owner(mp, x, rcx, c.k, c.m, c.P, false, b), kmer_prepend(x, c.k, b), &g)) { in |= 1u << b; si = g; }
+                const Neighbour s = neighbour_of(mp, x, rcx, c.k, c.m, c.P, true, b), p = neighbour_of(mp, x, rcx, c.k, c.m, c.P, false, b);
+                if (find_g(c, s.owner, s.q, s.rq, &g)) { out |= 1u << b; so = g; }
+                if (find_g(c, p.owner, p.q, p.rq, &g)) { in |= 1u << b; si = g; }
             }
         }
         mask8[v] = (u8)(out | (in << 4));
@@ -401,7 +414,7 @@ struct StartEdgesOp { // buildEdges (Graph.scala:349-365), first step of every e
             if (!(out & (1u << b))) continue;
             const u64 q = kmer_append(x, c.k, b);
             u32 w = NONE32;
-            find_g(c, owner_of_kmer(q, c.k, c.m, c.P), q, &w); // present by construction
+            find_g(c, owner_of_kmer(q, c.k, c.m, c.P), q, revcomp(q, c.k), &w); // present by construction
             w = normalise(c, w);
             G.edge_start[e] = my_node;
             L.edge_first[e - L.edge_base] = w;

@@ -236,8 +236,10 @@ void emul_owners(int k, int P, uint64_t x, uint32_t *full9, uint32_t *incr8)
     for (u32 b = 0; b < 4; b++) {
         full9[1 + b] = owner_of_kmer(kmer_append(x, k, b), k, m, P);
         full9[5 + b] = owner_of_kmer(kmer_prepend(x, k, b), k, m, P);
-        incr8[b] = neighbour_owner(mp, x, rcx, k, m, P, true, b);
-        incr8[4 + b] = neighbour_owner(mp, x, rcx, k, m, P, false, b);
+        const Neighbour s = neighbour_of(mp, x, rcx, k, m, P, true, b), p = neighbour_of(mp, x, rcx, k, m, P, false, b);
+        // the shifted reverse complements must be the reverse complements: a wrong one is reported as an impossible owner
+        incr8[b] = s.rq == revcomp(s.q, k) && s.q == kmer_append(x, k, b) ? s.owner : 0xFFFFFFFFu;
+        incr8[4 + b] = p.rq == revcomp(p.q, k) && p.q == kmer_prepend(x, k, b) ? p.owner : 0xFFFFFFFFu;
     }
 }
 
