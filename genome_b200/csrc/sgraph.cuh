@@ -488,10 +488,12 @@ struct CloseOp { // the last interior vertex of every chain closes its edge: end
         const u32 u = (u32)uu;
         const u64 a = c.peer[c.me].A[u];
         if (a_tag(a) == TAG_RES) {
+            // terminal or not is read off the (immutable) mask byte: an interior successor's entry may be changing right now
+            // (its owner's FinalizeOp), a terminal's entry is final since InitVerticesOp
             const u32 s = succ_of(c, L, u);
-            const u64 as = ld64(c.peer[g_rank(c, s)].A + g_idx(c, s));
-            if (a_tag(as) == TAG_TERM) {
-                G.edge_end[a_ptr(a)] = (u32)as;
+            u32 so, si;
+            if (vertex_type(c, s, &so, &si) == TAG_TERM) {
+                G.edge_end[a_ptr(a)] = (u32)ld64(c.peer[g_rank(c, s)].A + g_idx(c, s));
                 G.edge_len[a_ptr(a)] = (u64)a_dist(a) + 2;
             }
         } else if (a_tag(a) == TAG_UNRES) {
@@ -504,9 +506,9 @@ struct CloseNodeEdgesOp { // node -> node edges of length 1
     SG_HD void operator()(u64 j) const
     {
         const u32 w = L.edge_first[j];
-        const u64 a = ld64(c.peer[g_rank(c, w)].A + g_idx(c, w));
-        if (a_tag(a) == TAG_TERM) {
-            G.edge_end[L.edge_base + j] = (u32)a;
+        u32 wo, wi;
+        if (vertex_type(c, w, &wo, &wi) == TAG_TERM) {
+            G.edge_end[L.edge_base + j] = (u32)ld64(c.peer[g_rank(c, w)].A + g_idx(c, w));
             G.edge_len[L.edge_base + j] = 1;
         }
     }

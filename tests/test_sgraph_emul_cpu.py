@@ -244,3 +244,30 @@ def test_one_thread_per_rank_cycle_and_dual(emul):
     assert counts == (0, 0, 0) and st["cycle_vertices"] == 2 * genome.size
     got, counts, st = sharded_build(emul, 15, np.zeros(0, np.uint64), 3, threads=True)
     assert counts == (0, 0, 0)
+
+
+def test_barrier_placement_under_thread_sanitizer(tmp_path):
+    """One thread per rank under -fsanitize=thread (tests/emul/sgraph_tsan_main.cpp): a read of a peer's window that no
+    Fabric barrier orders after the peer's write is a reported data race.  The first run found one (CloseOp reading an
+    interior successor's entry while its owner's FinalizeOp rewrites it -- benign for whole-word accesses, removed anyway by
+    deciding "terminal or not" on the immutable mask byte)."""
+    exe = str(tmp_path / "sg_tsan")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", "-I" + cuda_inc, "-o", exe,
+                        os.path.join(HERE, "emul", "sgraph_tsan_main.cpp")], capture_output=True, text=True)
+    if r.returncode != 0 and "tsan" in (r.stderr or "").lower():
+        pytest.skip("no ThreadSanitizer runtime: " + r.stderr[-200:])
+    assert r.returncode == 0, r.stderr[-2000:]
+    for k, glen, rl, cov, err, rounds, P in [(31, 20000, 100, 30, 0.01, 3, 8), (8, 1500, 40, 10, 0.0, 1, 3), (11, 3000, 50, 20, 0.0, 1, 16)]:
+        b, n, _ = H.small_reads(glen, rl, cov, err, seed=2000 + k)
+        om, og = oracle_graph(b, n, k, rounds)
+        keys, _ = om.export()
+        path = str(tmp_path / ("keys_%d.bin" % k))
+        np.ascontiguousarray(keys, np.uint64).tofile(path)
+        r = subprocess.run([exe, str(k), str(P), path], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66"))
+        if "unexpected memory mapping" in r.stderr:
+            pytest.skip("ThreadSanitizer cannot run under this kernel's address-space layout")
+        assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:3000]
+        assert r.returncode == 0, (r.returncode, r.stderr[-500:])
+        assert r.stdout.strip() == "rc 0 nodes %d edges %d bases %d" % og.counts()
