@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")  # first calls must not pay lazy kernel loading (10..400 ms stalls)
 
 K = 31
+COVERAGE = None   # --coverage: BASELINE configs[4] sweeps only; None = the named config's coverage
 ROUNDS = 3  # GraphBuilder.scala:30
 WORKLOADS = {
     # name: (synth config, scale, note)
@@ -48,7 +49,7 @@ def make_workload(name, rank, world, scale):
     c = dict(synth.CONFIGS[WORKLOADS[name]["cfg"]])
     G = int(c["genome"] * scale) * world
     genome = synth.random_genome(G, c["seed"])
-    n_reads = (int(c["coverage"] * G / c["read_len"] / world) // 2) * 2
+    n_reads = (int((COVERAGE or c["coverage"]) * G / c["read_len"] / world) // 2) * 2
     parts, done, i = [], 0, 0
     while done < n_reads:
         m = min(1 << 20, n_reads - done)
@@ -159,15 +160,23 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--scale", type=float, default=1.0, help="genome scale (debugging only; 1.0 is the named config)")
+    ap.add_argument("--k", type=int, default=31, help="BASELINE configs[4] sweeps only; 31 is every named config's k")
+    ap.add_argument("--coverage", type=float, default=None, help="BASELINE configs[4] sweeps only; default = the named config's")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
+    global K, COVERAGE
+    K, COVERAGE = args.k, args.coverage
+    if not 1 <= K <= 31:
+        raise SystemExit("--k must be in 1..31")
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
     desc = WORKLOADS[args.workload]["desc"]
+    if K != 31 or COVERAGE is not None:
+        desc += " -- SWEEP VARIANT (BASELINE configs[4]): k=%d, coverage %s" % (K, "as named" if COVERAGE is None else "%gx" % COVERAGE)
 
     if args.impl == "reference":
         if rank != 0:
