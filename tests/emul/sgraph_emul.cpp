@@ -29,17 +29,17 @@ struct Exec {
 int sg_alloc(Exec &ex, void **p, size_t bytes)
 {
     // poison: a read of memory the algorithm never wrote should not look like a plausible value
-    *p = malloc(bytes + 64);
+    *p = malloc(bytes ? bytes : 1); // exact size: an address-sanitizer build of this harness sees every overrun
     if (!*p) return GB_E_OOM;
-    memset(*p, 0xA5, bytes + 64);
+    memset(*p, 0xA5, bytes);
     ex.owned.push_back(*p);
     return GB_OK;
 }
 int sg_graph_alloc(Exec &ex, void **p, size_t bytes)
 {
-    *p = malloc(bytes + 64);
+    *p = malloc(bytes ? bytes : 1);
     if (!*p) return GB_E_OOM;
-    memset(*p, 0xA5, bytes + 64);
+    memset(*p, 0xA5, bytes);
     ex.graph.push_back(*p);
     return GB_OK;
 }

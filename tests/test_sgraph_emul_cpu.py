@@ -246,17 +246,20 @@ def test_one_thread_per_rank_cycle_and_dual(emul):
     assert counts == (0, 0, 0)
 
 
-def test_barrier_placement_under_thread_sanitizer(tmp_path):
-    """One thread per rank under -fsanitize=thread (tests/emul/sgraph_tsan_main.cpp): a read of a peer's window that no
-    Fabric barrier orders after the peer's write is a reported data race.  The first run found one (CloseOp reading an
-    interior successor's entry while its owner's FinalizeOp rewrites it -- benign for whole-word accesses, removed anyway by
-    deciding "terminal or not" on the immutable mask byte)."""
-    exe = str(tmp_path / "sg_tsan")
+@pytest.mark.parametrize("sanitizer", ["thread", "address,undefined"])
+def test_thread_per_rank_under_sanitizers(tmp_path, sanitizer):
+    """One thread per rank (tests/emul/sgraph_tsan_main.cpp) under -fsanitize=thread: a read of a peer's window that no Fabric
+    barrier orders after the peer's write is a reported data race -- this checks the BARRIER PLACEMENT of sg::build.  The first
+    run found one (CloseOp reading an interior successor's entry while its owner's FinalizeOp rewrites it -- benign for
+    whole-word accesses, removed anyway by deciding "terminal or not" on the immutable mask byte).  Under
+    -fsanitize=address,undefined the same run checks every index the functors compute (the harness allocates exact sizes):
+    an overrun here would be an overrun in the kernels."""
+    exe = str(tmp_path / "sg_san")
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-pthread", "-I" + cuda_inc, "-o", exe,
-                        os.path.join(HERE, "emul", "sgraph_tsan_main.cpp")], capture_output=True, text=True)
-    if r.returncode != 0 and "tsan" in (r.stderr or "").lower():
-        pytest.skip("no ThreadSanitizer runtime: " + r.stderr[-200:])
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=" + sanitizer, "-fno-sanitize-recover=undefined", "-pthread",
+                        "-I" + cuda_inc, "-o", exe, os.path.join(HERE, "emul", "sgraph_tsan_main.cpp")], capture_output=True, text=True)
+    if r.returncode != 0 and "san" in (r.stderr or "").lower() and "cannot find" in r.stderr:
+        pytest.skip("sanitizer runtime not installed: " + r.stderr[-200:])
     assert r.returncode == 0, r.stderr[-2000:]
     for k, glen, rl, cov, err, rounds, P in [(31, 20000, 100, 30, 0.01, 3, 8), (8, 1500, 40, 10, 0.0, 1, 3), (11, 3000, 50, 20, 0.0, 1, 16)]:
         b, n, _ = H.small_reads(glen, rl, cov, err, seed=2000 + k)
@@ -265,9 +268,9 @@ def test_barrier_placement_under_thread_sanitizer(tmp_path):
         path = str(tmp_path / ("keys_%d.bin" % k))
         np.ascontiguousarray(keys, np.uint64).tofile(path)
         r = subprocess.run([exe, str(k), str(P), path], capture_output=True, text=True, timeout=600,
-                           env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66"))
+                           env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66", ASAN_OPTIONS="detect_leaks=0"))
         if "unexpected memory mapping" in r.stderr:
-            pytest.skip("ThreadSanitizer cannot run under this kernel's address-space layout")
-        assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:3000]
+            pytest.skip("the sanitizer cannot run under this kernel's address-space layout")
+        assert "WARNING: ThreadSanitizer" not in r.stderr and "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
         assert r.returncode == 0, (r.returncode, r.stderr[-500:])
         assert r.stdout.strip() == "rc 0 nodes %d edges %d bases %d" % og.counts()
