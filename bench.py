@@ -37,6 +37,9 @@ WORKLOADS = {
     # name: (synth config, scale, note)
     "C2": dict(cfg="C2", desc="4.6 Mbp random genome, 1% substitutions, 100 bp reads at 30x, k=31 (BASELINE configs[1])"),
     "C1": dict(cfg="C1", desc="4.6 Mbp random genome, error-free 100 bp reads at 30x, k=31 (BASELINE configs[0])"),
+    # BASELINE configs[2]: the genome is scale x world x 100 Mbp, so `--workload C3 --scale 0.125 --gpus 8` (0.25 at 4, 0.5 at 2)
+    # is the named 100 Mbp genome sharded over the GPUs
+    "C3": dict(cfg="C3", desc="100 Mbp-class genome x scale with 5% interspersed repeats, error-free 150 bp reads at 50x, k=31 (BASELINE configs[2])"),
     # BASELINE configs[3] shape (150 bp reads at 40x, 0.5% errors); use --scale 0.05: 50 Mbp of genome and a 16 GB shard per GPU
     "C4": dict(cfg="C4", desc="1 Gbp-class random genome x scale, 0.5% substitutions, 150 bp reads at 40x, k=31 (BASELINE configs[3] shape)"),
 }
@@ -49,6 +52,8 @@ def make_workload(name, rank, world, scale):
     c = dict(synth.CONFIGS[WORKLOADS[name]["cfg"]])
     G = int(c["genome"] * scale) * world
     genome = synth.random_genome(G, c["seed"])
+    if c["repeats"] > 0:
+        genome = synth.add_repeats(genome, c["repeats"], c["seed"] + 1)   # same seed on every rank: the same genome
     n_reads = (int((COVERAGE or c["coverage"]) * G / c["read_len"] / world) // 2) * 2
     parts, done, i = [], 0, 0
     while done < n_reads:
