@@ -188,3 +188,27 @@ def test_kmers_calculator_windows():
     assert CG.sequence_windows([">h"], 4)[0] == 0
     with pytest.raises(ValueError):
         CG.sequence_windows([">h", "ACNT"], 2)
+
+
+def test_graph_builder_histograms_on_oracle_graph():
+    """GraphBuilder.scala:41-47: the two component histograms, computed from exported arrays; checked here on the oracle's graph
+    against a direct per-component tally."""
+    from genome_b200.builder import component_histograms
+    b, n, _ = H.small_reads(4000, 40, 15, 0.03, seed=2009)
+    om, _ = H.oracle_counts(b, n, 9)
+    om.delete_below(1)
+    og = pyoracle.OracleGraph(om)
+    node_kmer, node_id, es, ee, off, bases = og.export()
+    nc, label = og.components()
+    idx = {int(i): j for j, i in enumerate(node_id)}
+    es_i = np.array([idx[int(x)] for x in es], np.int64)
+    hist, hist2, comp_nodes = component_histograms(nc, label, es_i, off)
+    sizes, lens = {}, {}
+    for c in range(nc):
+        nodes = np.flatnonzero(label == c)
+        sizes[len(nodes)] = sizes.get(len(nodes), 0) + 1
+        total = sum(int(off[e + 1] - off[e]) for e in range(es_i.size) if label[es_i[e]] == c)
+        lens[total] = lens.get(total, 0) + 1
+    assert hist == sorted(sizes.items()) and hist2 == sorted(lens.items())
+    assert sum(c for _, c in hist) == nc and int(comp_nodes.max()) == max(sizes)
+    assert component_histograms(0, np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(1, np.uint64))[:2] == ([], [])
