@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 export GENOME_B200_UNVALIDATED=1
 {
   echo "== opt-in device tests"
-  timeout 1200 python -m pytest tests/test_sgraph_gpu.py tests/test_graphmap_gpu.py -q -m gpu 2>&1 | tail -25
+  timeout 1200 python -m pytest tests/test_sgraph_gpu.py tests/test_graphmap_gpu.py tests/test_scripts_gpu.py -q -m gpu 2>&1 | tail -25
   NGPU=$(python -c "import torch; print(torch.cuda.device_count())")
   if [ "$NGPU" -ge 2 ]; then
     echo "== sharded graph build over $NGPU ranks"
