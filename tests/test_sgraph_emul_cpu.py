@@ -274,3 +274,28 @@ def test_thread_per_rank_under_sanitizers(tmp_path, sanitizer):
         assert "WARNING: ThreadSanitizer" not in r.stderr and "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[:3000]
         assert r.returncode == 0, (r.returncode, r.stderr[-500:])
         assert r.stdout.strip() == "rc 0 nodes %d edges %d bases %d" % og.counts()
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 7])
+def test_random_dense_kmer_sets(emul, k):
+    """Random subsets of the whole k-mer space for small k: dense tangles with self-loops, hairpins (x followed by rc(x)),
+    palindromes (even k) and perfect cycles that read sets rarely produce; stored canonically (FreqFilter.add) or as given."""
+    rng = np.random.default_rng(700 + k)
+    space = 1 << (2 * k)
+    for trial in range(12):
+        frac = [0.05, 0.2, 0.5, 0.9][trial % 4]
+        xs = np.flatnonzero(rng.random(space) < frac).astype(np.uint64)
+        if xs.size == 0:
+            continue
+        dual = trial % 3 == 2
+        om = pyoracle.OracleMap(k)
+        for x in xs.tolist():
+            om.update1(x if dual else pyoracle.canonical(x, k))
+        og = pyoracle.OracleGraph(om)
+        keys, _ = om.export()
+        want = H.canon_oracle_graph(og)
+        P = int(rng.integers(1, 9))
+        for threads in (False, True):
+            got, counts, _ = sharded_build(emul, k, keys, P, dual=dual, split=["even", "skewed", "last"][trial % 3], seed=trial, threads=threads)
+            assert counts == og.counts(), (k, trial, P, dual, threads)
+            assert got == want, (k, trial, P, dual, threads)

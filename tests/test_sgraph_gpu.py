@@ -86,3 +86,31 @@ def test_virtual_shards_equal_single_gpu_build_at_size(gpu):
         assert gp.counts() == g1.counts()
         assert H.canon_gpu_graph(gp) == H.canon_gpu_graph(g1)
         assert gp.stats()["cycle_vertices"] == g1.stats()["cycle_vertices"]
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 6, 7])
+def test_random_dense_kmer_sets(gpu, k):
+    """Random subsets of the whole k-mer space for small k (tests/test_sgraph_emul_cpu.py has the same sets): self-loops,
+    hairpins, palindromes, perfect cycles; through BOTH device builds (gb_graph_build and the virtual shards)."""
+    rng = np.random.default_rng(700 + k)
+    space = 1 << (2 * k)
+    for trial in range(12):
+        frac = [0.05, 0.2, 0.5, 0.9][trial % 4]
+        xs = np.flatnonzero(rng.random(space) < frac).astype(np.uint64)
+        if xs.size == 0:
+            continue
+        dual = trial % 3 == 2
+        keys = xs if dual else np.array([pyoracle.canonical(int(x), k) for x in xs], np.uint64)
+        om = pyoracle.OracleMap(k)
+        for x in keys.tolist():
+            om.update1(x)
+        og = pyoracle.OracleGraph(om)
+        gm = ArrayDNAMap(k)
+        gm.update_counts(keys)
+        assert gm.size == om.size()
+        P = int(rng.integers(1, 9))
+        for g in (Graph.buildGraph(k, gm), Graph.buildGraphVirtualShards(k, gm, P)):
+            assert g.counts() == og.counts(), (k, trial, P, dual)
+            H.assert_graph_equal(g, og)
+            g.close()
+        gm.close()
