@@ -17,5 +17,8 @@ export GENOME_B200_UNVALIDATED=1
   timeout 600 python scripts/sgraph_timing.py > gpurun_out/r2_sgraph_timing.json 2> gpurun_out/r2_sgraph_timing.err
   tail -5 gpurun_out/r2_sgraph_timing.json
   tail -5 gpurun_out/r2_sgraph_timing.err
+  echo "== timing: the same on a graph that does not fit L2 (C4 x 0.05: ~50 M kept k-mers)"
+  timeout 900 python scripts/sgraph_timing.py C4 0.05 > gpurun_out/r2_sgraph_timing_c4.json 2> gpurun_out/r2_sgraph_timing_c4.err
+  tail -5 gpurun_out/r2_sgraph_timing_c4.err
 } > gpurun_out/r2_validate.log 2>&1
 tail -60 gpurun_out/r2_validate.log
