@@ -40,7 +40,7 @@ def timed(label, build):
 
 
 timed("single", lambda: Graph.buildGraph(K, m))
-for P in (1, 2, 4, 8):
+for P in (1, 2, 4, 8, 16):
     timed("virtual_shards_%d" % P, lambda: Graph.buildGraphVirtualShards(K, m, P))
 ref = out["builds"][0]["counts"]
 out["all_equal_counts"] = all(r["counts"] == ref for r in out["builds"])
