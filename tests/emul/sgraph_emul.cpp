@@ -155,7 +155,69 @@ struct ThreadFabric : Fabric {
     }
 };
 
+// ---- one PROCESS per rank: the collectives are callbacks into the host program (tests/gloo_sgraph_worker.py implements them
+// with torch.distributed over gloo and POSIX shared memory for the peer windows), so peers live in other address spaces and
+// a rank sees their windows at addresses of its own -- the situation of CUDA IPC mappings + NCCL
 extern "C" {
+struct EmulFabricCallbacks {
+    int (*allgather)(const void *mine, void *all, uint64_t bytes);
+    int (*window)(uint64_t my_bytes, void **mine, void **peers /* [P] */);
+    int (*alltoallv)(const uint64_t *send, const uint64_t *soff, const uint64_t *scnt, uint64_t *recv, const uint64_t *roff,
+                     const uint64_t *rcnt);
+    int (*barrier)(void);
+    int (*allgatherv)(uint64_t *buf, const uint64_t *off, const uint64_t *cnt);
+    int (*allreduce_sum)(void *buf, uint64_t count, int elem_bytes);
+};
+}
+struct CallbackFabric : Fabric {
+    const EmulFabricCallbacks &cb;
+    CallbackFabric(const EmulFabricCallbacks &c, int n_ranks, int rank) : cb(c)
+    {
+        P = n_ranks;
+        mine.push_back(rank);
+    }
+    int allgather_host(const void *const *contrib, void *const *all, size_t bytes) override { return cb.allgather(contrib[0], all[0], bytes); }
+    int windows(const size_t *bytes_of_rank, void **window, PeerPtrs *peers) override
+    {
+        for (int r = 0; r < MAXR; r++) peers[0].p[r] = nullptr;
+        return cb.window(bytes_of_rank[mine[0]], &window[0], peers[0].p);
+    }
+    int alltoallv_u64(const u64 *const *send, const Row *soff, const Row *scnt, u64 *const *recv, const Row *roff, const Row *rcnt) override
+    {
+        return cb.alltoallv((const uint64_t *)send[0], (const uint64_t *)soff[0].v, (const uint64_t *)scnt[0].v, (uint64_t *)recv[0],
+                            (const uint64_t *)roff[0].v, (const uint64_t *)rcnt[0].v);
+    }
+    int barrier() override { return cb.barrier(); }
+    int allgatherv_u64(u64 *const *buf, const u64 *off, const u64 *cnt) override
+    {
+        return cb.allgatherv((uint64_t *)buf[0], (const uint64_t *)off, (const uint64_t *)cnt);
+    }
+    int allreduce_sum(void *buf, size_t count, int elem_bytes) override { return cb.allreduce_sum(buf, count, elem_bytes); }
+};
+
+extern "C" {
+
+// this process's rank of a build whose fabric is `cb`; two-call pattern like emul_sharded_build (sizes first)
+int emul_sharded_build_rank(int k, int dual, int v210, int P, int rank, const uint64_t *keys, uint64_t n, const EmulFabricCallbacks *cb,
+                            uint64_t *out, uint64_t *node_kmer, uint32_t *edge_start, uint32_t *edge_end, uint64_t *edge_off, uint32_t *bases)
+{
+    Exec ex;
+    CallbackFabric fab(*cb, P, rank);
+    std::vector<RankInput> in{ RankInput{ &ex, (const u64 *)keys, n } };
+    Result res;
+    const int rc = build(fab, in, k, dual != 0, v210 != 0, &res);
+    if (rc != GB_OK) return rc;
+    out[0] = res.n_nodes; out[1] = res.n_edges; out[2] = res.n_bases;
+    out[3] = res.kept; out[4] = res.segments; out[5] = res.cycle_vertices; out[6] = (uint64_t)res.jump_rounds; out[7] = (uint64_t)res.seg_rounds;
+    if (node_kmer) {
+        memcpy(node_kmer, res.node_kmer, res.n_nodes * 8);
+        memcpy(edge_start, res.edge_start, res.n_edges * 4);
+        memcpy(edge_end, res.edge_end, res.n_edges * 4);
+        memcpy(edge_off, res.edge_off, (res.n_edges + 1) * 8);
+        memcpy(bases, res.bases, ((res.n_bases + 15) / 16) * 4);
+    }
+    return 0;
+}
 
 // the build with one thread per rank (ThreadFabric): every rank's copy of the result must be the same graph.  Returns 0, a
 // GB_E_* code, or 1000 + r when rank r's copy differs from rank 0's.  Output = rank 0's copy (same layout as below).

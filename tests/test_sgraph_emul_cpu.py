@@ -299,3 +299,18 @@ def test_random_dense_kmer_sets(emul, k):
             got, counts, _ = sharded_build(emul, k, keys, P, dual=dual, split=["even", "skewed", "last"][trial % 3], seed=trial, threads=threads)
             assert counts == og.counts(), (k, trial, P, dual, threads)
             assert got == want, (k, trial, P, dual, threads)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_one_process_per_rank_gloo(emul, world):
+    """world_size 2 and 3 over gloo: one PROCESS per rank, the Fabric's collectives done by torch.distributed, the peer windows
+    in /dev/shm and mapped at different addresses in every process (tests/gloo_sgraph_worker.py) -- the CPU stand-in for NCCL +
+    CUDA IPC.  Every rank checks its copy of the graph against the oracle."""
+    import sys
+    script = os.path.join(HERE, "gloo_sgraph_worker.py")
+    port = str(29750 + world)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", port, script], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-5000:]
+    assert "SGRAPH GLOO OK world %d" % world in r.stdout
