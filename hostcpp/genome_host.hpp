@@ -207,6 +207,15 @@ struct Graph {
         check(gb_graph_build(kmersFreq.handle(), &g));
         return MapGraph(g);
     }
+    // the sharded form of buildGraph (csrc/sgraph.cuh) over nShards virtual ranks on the map's one device: the multi-GPU
+    // algorithm on a single GPU, same graph up to node / edge numbering
+    static MapGraph buildGraphVirtualShards(int k, const DNAMap &kmersFreq, int nShards)
+    {
+        if (k != kmersFreq.k()) throw Error(GB_E_ARG, "k differs from the map's k");
+        gb_graph *g = nullptr;
+        check(gb_graph_build_virtual_shards(kmersFreq.handle(), nShards, &g));
+        return MapGraph(g);
+    }
 };
 
 } // namespace genome
