@@ -371,7 +371,9 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_kmer": dom_bytes / windows, "kernel_ms": dom_s * 1e3,
-                    "insert_path": "partitioned (L2-blocked): part_count + part_scatter + insert_keys" if partitioned else "direct: insert_reads_kernel",
+                    "insert_path": ("partitioned (L2-blocked), single pass: part_scatter<SLABS> + insert_keys (GENOME_B200_COUNTLESS)"
+                                    if partitioned and os.environ.get("GENOME_B200_COUNTLESS") else
+                                    "partitioned (L2-blocked): part_count + part_scatter + insert_keys" if partitioned else "direct: insert_reads_kernel"),
                     "insert_ms": ins_s * 1e3, "insert_kmers_per_s": windows / ins_s,
                     "insert_algorithmic_bytes_per_kmer": algo_bytes / windows,
                     "insert_frac": algo_bytes / ins_s / 1e9 / peak,

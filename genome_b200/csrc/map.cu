@@ -523,7 +523,12 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
     const int64_t n_sub = (n_reads + per_reads - 1) / per_reads;
     int64_t half = 0; // keys per staging half
     for (int64_t s = 0; s < n_sub; s++) half = std::max(half, win_upper(read0 + s * per_reads, read0 + std::min(n_reads, (s + 1) * per_reads)));
-    GB_TRY(map_stage(m, (size_t)((n_sub > 1 ? 2 : 1) * (half + 8))));
+    // GENOME_B200_COUNTLESS=1 (one sub-batch only): no count pass, per-(bucket, CTA) slabs instead of exact bucket ranges
+    const unsigned int nbk = (unsigned int)pl.nb();
+    const unsigned int slab = getenv("GENOME_B200_COUNTLESS") && n_sub == 1 && pl.owners == 1 && nbk <= 128
+                                  ? slab_keys_for((unsigned long long)half, nbk, (int)grid) : 0;
+    const size_t slab_keys = (size_t)slab * nbk * (size_t)grid, n_slab_chunks = (size_t)nbk * (size_t)grid;
+    GB_TRY(map_stage(m, slab ? slab_keys + 2 * n_slab_chunks + 8 : (size_t)((n_sub > 1 ? 2 : 1) * (half + 8))));
     if (n_sub == 1) bk = up; // nothing to overlap: one stream, no cross-stream events
     // the bucket stream starts after everything already queued on the map's stream (clear, earlier inserts)
     GB_CUDA(cudaEventRecord(m->pe[2], up));
@@ -538,9 +543,14 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
         ReadBatch rb;
         rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = d_off; rb.rec_bytes = rec; rb.read0 = r0; rb.n_reads = nr;
         if (s >= 2) GB_CUDA(cudaStreamWaitEvent(bk, m->pfree[h], 0)); // the upsert of sub-batch s - 2 has consumed this half
-        GB_TRY(part_count(rb, m->k, m->v210, pl, *work[h], bk));
-        GB_TRY(part_scatter(rb, m->k, m->v210, pl, *work[h], keys, bk));
-        GB_TRY(make_single_chunk(work[h]->bucket_base + pl.nb(), d_desc, m->d_counters, bk));
+        if (slab) {
+            d_desc = keys + slab_keys;
+            GB_TRY(part_scatter_slabs(rb, m->k, m->v210, pl, *work[h], keys, slab, d_desc, m, bk));
+        } else {
+            GB_TRY(part_count(rb, m->k, m->v210, pl, *work[h], bk));
+            GB_TRY(part_scatter(rb, m->k, m->v210, pl, *work[h], keys, bk));
+            GB_TRY(make_single_chunk(work[h]->bucket_base + pl.nb(), d_desc, m->d_counters, bk));
+        }
         if (bk != up) {
             GB_CUDA(cudaEventRecord(m->pready[h], bk));
             GB_CUDA(cudaStreamWaitEvent(up, m->pready[h], 0));
@@ -552,11 +562,16 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
         }
         // the buckets are contiguous and already in slice order: one chunk; the launch is sized from the upper bound
         unsigned long long total = (unsigned long long)wu;
+        if (slab) {
+            // the chunk table holds the exact count on the device (keys in slabs; overflowed keys were upserted by the bucket pass)
+            GB_TRY(insert_key_chunks(m, keys, d_desc, d_desc + n_slab_chunks + 1, (int)n_slab_chunks, total, up, true));
+        } else {
         if (!bound_is_exact) { // record lengths are only on the device: fetch the count (stalls the pipeline; rare path)
             GB_CUDA(cudaMemcpyAsync(&total, work[h]->bucket_base + pl.nb(), 8, cudaMemcpyDeviceToHost, bk));
             GB_CUDA(cudaStreamSynchronize(bk));
         }
         GB_TRY(insert_key_chunks(m, keys, d_desc, d_desc + 2, 1, total, up));
+        }
         if (m->n_pup + 2 <= 16) {
             GB_CUDA(cudaEventRecord(m->pup[m->n_pup + 1], up));
             m->n_pup += 2;

@@ -8,6 +8,8 @@
 //   2. insert_key_chunks walks the buckets in slice order, so the CTAs that are resident at any moment all update
 //      the same <= 64 MiB slice of the table, which lives in L2; DRAM sees each slice once in and once out.
 // The same buckets, with an owner-shard prefix, are what the sharded map sends over NVLink (comm.cu).
+#include <math.h>
+
 #include "partition.cuh"
 
 #include "extract.cuh"
@@ -20,6 +22,8 @@ __device__ __forceinline__ unsigned int bucket_of(unsigned long long h, unsigned
     unsigned int slice = lp_bits ? (unsigned int)(h >> (64 - lp_bits)) : 0u;
     return (owner_of(h, owners) << lp_bits) | slice;
 }
+
+constexpr int SPREAD = 256; // new-key tallies are spread over this many counters: no same-address atomic storm
 
 // Persistent CTAs: CTA c takes tiles c, c + grid, ... in BOTH passes, so its per-bucket counts of pass 1 are exactly
 // the room it needs in pass 2: no global atomics, no shared-memory atomics with a return value, deterministic layout.
@@ -132,10 +136,24 @@ part_bases_kernel(const unsigned long long *bucket_total, unsigned int nb, unsig
 // scattered 8-byte stores per warp instruction.  That is what fills NVLink write packets when PEER.
 // PEER: the position of a key is (owner, index inside the owner's segment) packed in 32 bits and the store goes to
 // the owner's inbox through its peer mapping -- the all-to-all happens inside this kernel, store by store.
-template <bool FIXED, bool V210, bool SRC_KEYS, bool PEER>
+// SLABS (GENOME_B200_COUNTLESS=1, single-GPU path only): there is NO count pass.  CTA c owns, for every bucket b, the slab
+// [(b * grid + c) * slab, + slab) of `out`, sized for its expected share plus 8 sigma; what it wrote goes to so.count[b * grid +
+// c], and make_slab_chunks_kernel turns the counts into the chunk table of the upsert (bucket-major, so slice order is kept).
+// A key that does not fit its slab is upserted right here, with the random access of the direct path: always correct, and only
+// pathological inputs (one bucket far above its share within one CTA's tiles) ever take it.
+struct SlabOut {
+    unsigned int slab = 0;              // keys per (bucket, CTA) slab
+    unsigned int *count = nullptr;      // [nb][grid]
+    Slot *table = nullptr;              // overflow path
+    unsigned long long cap = 0;
+    unsigned long long *spread = nullptr;   // new-key tallies (fold_new_keys_kernel)
+    unsigned long long *overflowed = nullptr; // keys that took the overflow path (they count as k-windows too)
+};
+
+template <bool FIXED, bool V210, bool SRC_KEYS, bool PEER, bool SLABS>
 __global__ void __launch_bounds__(INSERT_THREADS, 4)
 part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int lp_bits, unsigned int nb, const unsigned int *cta_off,
-                    const unsigned long long *bucket_base, unsigned long long *out, PeerOut peers)
+                    const unsigned long long *bucket_base, unsigned long long *out, PeerOut peers, SlabOut so)
 {
     __shared__ ReadTile tile;
     extern __shared__ unsigned int s_dyn[];
@@ -149,6 +167,10 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
     unsigned long long *skey = reinterpret_cast<unsigned long long *>(sdst + ROUND_KEYS); // offset 10 nb + 2 + ROUND_KEYS words: even
     // position of the CTA's next key of bucket b, relative to out[0] (a batch holds < 2^32 keys)
     for (unsigned int b = tid; b < nb; b += INSERT_THREADS) {
+        if (SLABS) {
+            bcur[b] = (b * gridDim.x + blockIdx.x) * so.slab; // < 2^32: checked by the host
+            continue;
+        }
         unsigned int pos = (unsigned int)bucket_base[b] + cta_off[(size_t)blockIdx.x * nb + b];
         if (PEER) { // relative to the owner's segment, owner in the top bits
             const unsigned int o = b >> lp_bits;
@@ -224,11 +246,25 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
                 const unsigned int in_bucket = rcnt[bk[j]] + rk[j];
                 const unsigned int idx = bstart[bk[j]] + in_bucket;
                 skey[idx] = key[j];
-                sdst[idx] = bcur[bk[j]] + in_bucket;
+                unsigned int pos = bcur[bk[j]] + in_bucket;
+                if (SLABS && pos >= (bk[j] * gridDim.x + blockIdx.x + 1) * so.slab) pos = 0xFFFFFFFFu; // beyond the slab
+                sdst[idx] = pos;
             }
         __syncthreads();
-        for (unsigned int idx = tid; idx < round_total; idx += INSERT_THREADS) store(sdst[idx], skey[idx]);
-        if (tid < (int)nb) bcur[tid] += bstart[tid + 1] - bstart[tid];
+        for (unsigned int idx = tid; idx < round_total; idx += INSERT_THREADS) {
+            if (SLABS && sdst[idx] == 0xFFFFFFFFu) {
+                const unsigned long long key1 = skey[idx], i = slot_of(mix64(key1), so.cap);
+                if (upsert_add(so.table, so.cap, i, load_key(so.table + i), key1, 1)) atomicAdd(&so.spread[blockIdx.x & (SPREAD - 1)], 1ull);
+                atomicAdd(so.overflowed, 1ull);
+                continue;
+            }
+            store(sdst[idx], skey[idx]);
+        }
+        if (SLABS) { // a full slab stays full: no 32-bit wrap
+            if (tid < (int)nb) bcur[tid] = min(bcur[tid] + (bstart[tid + 1] - bstart[tid]), (tid * gridDim.x + blockIdx.x + 1) * so.slab);
+        } else {
+            if (tid < (int)nb) bcur[tid] += bstart[tid + 1] - bstart[tid];
+        }
         __syncthreads();
     };
     if (SRC_KEYS) {
@@ -252,16 +288,21 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
             }
         }
     }
+    if (SLABS) { // do_round ends with a barrier: bcur is final
+        for (unsigned int b = tid; b < nb; b += INSERT_THREADS) {
+            const unsigned int used = bcur[b] - (b * gridDim.x + blockIdx.x) * so.slab;
+            so.count[(size_t)b * gridDim.x + blockIdx.x] = min(used, so.slab);
+        }
+    }
 }
 
 // ---------------------------------------------------------------- bulk upsert from key ranges
 constexpr int IK_THREADS = 256;
 
-constexpr int SPREAD = 256; // new-key tallies are spread over this many counters: no same-address atomic storm
-
 // No CTA barrier anywhere: every thread finds its own chunk, every warp adds its new-key count to one of SPREAD
 // global counters (fold_new_keys_kernel sums them into counters[0] afterwards).
-template <int IK_PER_THREAD, bool CAS_FIRST>
+// DEV_TOTAL: n_total is only an upper bound (it sized the grid); the exact number of keys is vstart[n_chunks].
+template <int IK_PER_THREAD, bool CAS_FIRST, bool DEV_TOTAL>
 __global__ void __launch_bounds__(IK_THREADS)
 insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vstart,
                    const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Slot *table, unsigned long long cap,
@@ -269,6 +310,10 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
 {
     constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
     const unsigned long long v0 = (unsigned long long)blockIdx.x * IK_PER_CTA;
+    if (DEV_TOTAL) {
+        n_total = min(n_total, vstart[n_chunks]);
+        if (v0 >= n_total) return;
+    }
     int c = 0;
     if (n_chunks > 1) { // last chunk with vstart <= v0 (uniform over the CTA: served from L1)
         int lo = 0, hi = n_chunks;
@@ -409,7 +454,7 @@ static int launch_scatter(const ReadBatch &rb, int k, bool v210, const PartLayou
     memset(&po, 0, sizeof po);
     if (peers) po = *peers;
     KeySource none;
-#define GB_PS(F, V, P) part_scatter_kernel<F, V, false, P><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist, w.bucket_base, out, po)
+#define GB_PS(F, V, P) part_scatter_kernel<F, V, false, P, false><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist, w.bucket_base, out, po, SlabOut())
 #define GB_PS2(F, V) do { if (peers) GB_PS(F, V, true); else GB_PS(F, V, false); } while (0)
     if (fixed) { if (v210) GB_PS2(true, true); else GB_PS2(true, false); }
     else { if (v210) GB_PS2(false, true); else GB_PS2(false, false); }
@@ -436,8 +481,82 @@ int part_scatter_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, un
     ReadBatch none;
     PeerOut po;
     memset(&po, 0, sizeof po);
-    part_scatter_kernel<true, false, true, false><<<w.grid, INSERT_THREADS, scatter_smem(nb), st>>>(none, ks, 0, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist,
-                                                                                             w.bucket_base, out, po);
+    part_scatter_kernel<true, false, true, false, false><<<w.grid, INSERT_THREADS, scatter_smem(nb), st>>>(none, ks, 0, (unsigned int)pl.owners, pl.lp_bits, nb,
+                                                                                                    w.cta_hist, w.bucket_base, out, po, SlabOut());
+    GB_LAUNCHED();
+    return GB_OK;
+}
+
+// ---- the single-pass variant (GENOME_B200_COUNTLESS=1)
+// keys per (bucket, CTA) slab for a batch of at most `total` keys: the expected share plus 8 standard deviations of a binomial
+// draw, rounded up to 64 keys (512 B).  0 = the slabs would not fit 32-bit positions: use the counted passes.
+unsigned int slab_keys_for(unsigned long long total, unsigned int nb, int grid)
+{
+    const double e = (double)total / ((double)nb * grid);
+    const unsigned long long slab = (((unsigned long long)(e + 8.0 * sqrt(e + 1.0)) + 64) + 63) / 64 * 64;
+    if (slab * nb * (unsigned long long)grid >= 0xFFF00000ull) return 0; // positions are 32-bit, with room for one round above a limit
+    return (unsigned int)slab;
+}
+
+// chunk table of the slabs, bucket-major: chunk c = (bucket c / grid, CTA c % grid) holds count[c] keys at out[c * slab].
+// desc = vstart[n_chunks + 1] | off[n_chunks]; counters[3] (k-windows) += keys in slabs + keys that took the overflow path.
+__global__ void __launch_bounds__(1024)
+make_slab_chunks_kernel(const unsigned int *count, unsigned int n_chunks, unsigned int slab, unsigned long long *vstart, unsigned long long *off,
+                        const unsigned long long *overflowed, unsigned long long *counters)
+{
+    __shared__ unsigned long long s_part[1024];
+    const unsigned int per = (n_chunks + 1023) / 1024, c0 = min(n_chunks, threadIdx.x * per), c1 = min(n_chunks, c0 + per);
+    unsigned long long sum = 0;
+    for (unsigned int c = c0; c < c1; c++) sum += count[c];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long acc = 0;
+        for (int i = 0; i < 1024; i++) { const unsigned long long v = s_part[i]; s_part[i] = acc; acc += v; }
+        vstart[n_chunks] = acc;
+        atomicAdd(&counters[3], acc + *overflowed);
+    }
+    __syncthreads();
+    unsigned long long run = s_part[threadIdx.x];
+    for (unsigned int c = c0; c < c1; c++) {
+        vstart[c] = run;
+        off[c] = (unsigned long long)c * slab;
+        run += count[c];
+    }
+}
+
+// pass 2 without pass 1: `out` holds nb * grid slabs of `slab` keys; d_desc receives the chunk table (2 * nb * grid + 1 words).
+// `spread` / `overflowed` / the table are for the keys that do not fit their slab.
+int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, unsigned int slab,
+                       unsigned long long *d_desc, Map *m, cudaStream_t st)
+{
+    GB_TRY(w.ensure(st));
+    const unsigned int nb = (unsigned int)pl.nb();
+    if (nb > STAGE_MAX_BUCKETS || pl.owners != 1) { set_error("internal: slab bucket pass with %u buckets, %d owners", nb, pl.owners); return GB_E_ARG; }
+    if (!m->d_spread) {
+        GB_CUDA(cudaMalloc((void **)&m->d_spread, SPREAD * 8));
+        GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));
+    }
+    const bool fixed = rb.offsets == nullptr;
+    const size_t smem = scatter_smem(nb);
+    const unsigned int n_chunks = nb * (unsigned int)w.grid;
+    SlabOut so;
+    so.slab = slab;
+    so.count = w.cta_hist; // [nb][grid] here (the counted passes use it as [grid][nb])
+    so.table = m->table;
+    so.cap = m->cap;
+    so.spread = m->d_spread;
+    so.overflowed = w.bucket_total; // one word is enough; the counted passes are not running
+    GB_CUDA(cudaMemsetAsync(so.overflowed, 0, 8, st));
+    PeerOut po;
+    memset(&po, 0, sizeof po);
+    KeySource none;
+#define GB_PSS(F, V) part_scatter_kernel<F, V, false, false, true><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, 1u, pl.lp_bits, nb, nullptr, nullptr, out, po, so)
+    if (fixed) { if (v210) GB_PSS(true, true); else GB_PSS(true, false); }
+    else { if (v210) GB_PSS(false, true); else GB_PSS(false, false); }
+#undef GB_PSS
+    GB_LAUNCHED();
+    make_slab_chunks_kernel<<<1, 1024, 0, st>>>(so.count, n_chunks, slab, d_desc, d_desc + n_chunks + 1, so.overflowed, m->d_counters);
     GB_LAUNCHED();
     return GB_OK;
 }
@@ -458,7 +577,7 @@ int make_single_chunk(const unsigned long long *d_total, unsigned long long *d_d
 }
 
 int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned long long *d_vstart, const unsigned long long *d_off,
-                      int n_chunks, unsigned long long n_total, cudaStream_t st)
+                      int n_chunks, unsigned long long n_total, cudaStream_t st, bool total_is_upper_bound)
 {
     if (!n_total) return GB_OK;
     m->kept_valid = false;
@@ -472,11 +591,12 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
         per = e ? atoi(e) : 4;
         cas_first = getenv("GENOME_B200_CAS_FIRST") != nullptr;
     }
-#define GB_IK(N, C)                                                                                                       \
-    insert_keys_kernel<N, C><<<(unsigned int)((n_total + IK_THREADS * N - 1) / (IK_THREADS * N)), IK_THREADS, 0, st>>>(    \
+#define GB_IK(N, C, D)                                                                                                       \
+    insert_keys_kernel<N, C, D><<<(unsigned int)((n_total + IK_THREADS * N - 1) / (IK_THREADS * N)), IK_THREADS, 0, st>>>(    \
         d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread)
-    if (cas_first) { if (per == 2) GB_IK(2, true); else if (per == 8) GB_IK(8, true); else GB_IK(4, true); }
-    else if (per == 8) GB_IK(8, false); else if (per == 2) GB_IK(2, false); else GB_IK(4, false);
+    if (total_is_upper_bound) GB_IK(4, false, true);
+    else if (cas_first) { if (per == 2) GB_IK(2, true, false); else if (per == 8) GB_IK(8, true, false); else GB_IK(4, true, false); }
+    else if (per == 8) GB_IK(8, false, false); else if (per == 2) GB_IK(2, false, false); else GB_IK(4, false, false);
 #undef GB_IK
     GB_LAUNCHED();
     fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);

@@ -7,12 +7,24 @@ mkdir -p gpurun_out
 export GENOME_B200_UNVALIDATED=1
 {
   echo "== opt-in device tests"
-  timeout 1200 python -m pytest tests/test_sgraph_gpu.py tests/test_graphmap_gpu.py tests/test_scripts_gpu.py -q -m gpu 2>&1 | tail -25
+  timeout 1200 python -m pytest tests/test_sgraph_gpu.py tests/test_graphmap_gpu.py tests/test_scripts_gpu.py tests/test_countless_gpu.py -q -m gpu 2>&1 | tail -25
   NGPU=$(python -c "import torch; print(torch.cuda.device_count())")
   if [ "$NGPU" -ge 2 ]; then
     echo "== sharded graph build over $NGPU ranks"
     timeout 900 python -m pytest tests/test_parity_multigpu.py -q -m gpu -k "sharded_graph_build or pmap_matches_oracle" 2>&1 | tail -20
   fi
+  echo "== bench: default vs single-pass bucket pass (GENOME_B200_COUNTLESS=1)"
+  timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
+  GENOME_B200_COUNTLESS=1 timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/r2_bench_countless.json 2> gpurun_out/r2_bench_countless.err
+  python -c "
+import json
+for f in ('default', 'countless'):
+    try:
+        d = json.loads(open('gpurun_out/r2_bench_%s.json' % f).read().strip().splitlines()[-1])
+        print(f, '%.3f ms/step' % d['ms_per_step'], d['roofline'].get('phases_ms'), d['roofline'].get('insert_ms'))
+    except Exception as e:
+        print(f, 'failed', e)
+"
   echo "== timing: single-GPU build vs virtual shards (C2)"
   timeout 600 python scripts/sgraph_timing.py > gpurun_out/r2_sgraph_timing.json 2> gpurun_out/r2_sgraph_timing.err
   tail -5 gpurun_out/r2_sgraph_timing.json

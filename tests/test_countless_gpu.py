@@ -1,0 +1,79 @@
+"""The single-pass bucket pass (GENOME_B200_COUNTLESS=1: per-(bucket, CTA) slabs instead of a count pass, csrc/partition.cu
+part_scatter_kernel<..., SLABS>) against the oracle.  Written after this round's GPU budget was spent (the default kernels'
+SASS is unchanged by it: compared instruction for instruction); opt-in until run on a B200."""
+import os
+
+import numpy as np
+import pytest
+
+from genome_b200 import synth
+from genome_b200.dnamap import ArrayDNAMap
+from oracle import pyoracle
+from tests import helpers as H
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")]
+
+
+@pytest.fixture
+def countless(monkeypatch):
+    monkeypatch.setenv("GENOME_B200_INSERT", "partitioned")   # small tables take the direct path otherwise
+    monkeypatch.setenv("GENOME_B200_COUNTLESS", "1")
+    return monkeypatch
+
+
+def check(b, n, k, cap=0):
+    om, ow = H.oracle_counts(b, n, k)
+    gm = ArrayDNAMap(k, cap)
+    gw = gm.insert_reads(b, n)
+    assert gw == ow == pyoracle.count_windows(b, n, k)
+    assert gm.size == om.size()
+    gk, gv = gm.export_sorted()
+    ok, ov = om.export_sorted()
+    assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
+    # a second batch into the same table (the table is no longer empty; sizes the slabs anew)
+    gw2 = gm.insert_reads(b, n)
+    assert gw2 == ow
+    gk, gv = gm.export_sorted()
+    assert np.array_equal(gk, ok) and np.array_equal(gv, 2 * ov)
+    gm.delete_below(3)
+    om.delete_below(2)   # counts doubled: v < 3 on 2v  <=>  v < 2
+    assert gm.size == om.size()
+    gm.close()
+
+
+@pytest.mark.parametrize("k,read_len,ragged,err", [
+    (31, 100, False, 0.01), (21, 100, True, 0.01), (25, 150, False, 0.005), (31, 255, True, 0.0), (15, 36, False, 0.02),
+    (8, 50, True, 0.0), (4, 30, False, 0.0), (1, 10, False, 0.0), (16, 100, False, 0.0),
+])
+def test_countless_insert_matches_oracle(gpu, countless, k, read_len, ragged, err):
+    b, n, _ = H.small_reads(20000, read_len, 12, err, seed=1000 + k, ragged=ragged)
+    check(b, n, k)
+
+
+def test_countless_overflow_path(gpu, countless):
+    """Every read is the same sequence: all windows fall into a handful of buckets, so almost every key overflows its slab and
+    is upserted by the bucket pass itself (random access).  Counts and the k-window total must still be exact."""
+    k = 21
+    one = synth.random_genome(100, 5)
+    reads = np.tile(one, (60000, 1))
+    check(synth.pack_fixed(reads), reads.shape[0], k)
+    # and a mono-base stream: ONE key in total
+    reads = np.zeros((40000, 80), np.uint8)
+    check(synth.pack_fixed(reads), reads.shape[0], k)
+
+
+def test_countless_at_size(gpu, countless):
+    """1.5 M reads of a 5 Mbp genome with 1 % errors (the C2 shape): enough keys for real slabs (hundreds per (bucket, CTA)),
+    compared through size-independent properties and against the default path."""
+    k = 31
+    b, n, _ = synth.make_config("C2", scale=0.25)
+    gm = ArrayDNAMap(k, int(b.size * 1.2))
+    w = gm.insert_reads(b, n)
+    gk, gv = gm.export_sorted()
+    assert int(gv.astype(np.int64).sum()) == w and np.unique(gk).size == gk.size
+    countless.delenv("GENOME_B200_COUNTLESS")
+    ref = ArrayDNAMap(k, int(b.size * 1.2))
+    assert ref.insert_reads(b, n) == w
+    rk, rv = ref.export_sorted()
+    assert np.array_equal(gk, rk) and np.array_equal(gv, rv)
