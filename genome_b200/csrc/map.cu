@@ -664,6 +664,109 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
     return GB_OK;
 }
 
+// gb_map_insert_reads with GENOME_B200_COUNTLESS=1 on a fixed-stride HOST stream: the host-to-device copy is cut into chunks
+// (copy stream) and the single-pass bucket pass of chunk c (map stream) runs while chunk c + 1 is still on the wire.  Nothing
+// touches the table before every chunk has been verified: keys go to the slabs or to the overflow list (LIST mode of
+// partition.cu), and the upsert starts after the last chunk.  *handled = false: conditions not met, or the stream turned
+// out ragged / the overflow list filled up -- the table is untouched and the caller takes the ordinary path.
+// Written after this round's GPU budget was spent; opt-in, tests/test_countless_gpu.py.
+static int insert_host_pipelined(Map *m, const uint8_t *bin, int64_t n_reads, unsigned int rec, unsigned int len0, int64_t *n_windows,
+                                 bool *handled)
+{
+    *handled = false;
+    if (!getenv("GENOME_B200_COUNTLESS") || (int)len0 < m->k) return GB_OK;
+    const int64_t per_read = (int64_t)len0 - m->k + 1, want = n_reads * per_read;
+    if (want < (1 << 20) || want > ((int64_t)1 << 28)) return GB_OK; // small: not worth it; large: the ordinary path batches
+    int64_t budget = 0;
+    GB_TRY(map_budget(m, want, &budget));
+    if (want > budget) return GB_OK;
+    const int mode = insert_mode();
+    if (!(mode == 2 || (mode == 0 && ((size_t)sizeof(Slot) * m->cap) > (96u << 20)))) return GB_OK;
+    if (!m->part) m->part = new PartWork();
+    PartWork &w = *m->part;
+    GB_TRY(w.ensure(m->stream));
+    PartLayout pl;
+    pl.owners = 1;
+    pl.lp_bits = slice_bits_for(m->cap, 1);
+    const unsigned int nb = (unsigned int)pl.nb();
+    if (nb > 128) return GB_OK;
+    const unsigned long long ovf_cap = (unsigned long long)want / 16 + 65536;
+    const unsigned int slab = slab_keys_for((unsigned long long)want, nb, w.grid); // 0: slab positions would not fit 32 bits
+    if (!slab) return GB_OK;
+    const size_t n_chunks = (size_t)nb * (size_t)w.grid, slab_keys = (size_t)slab * n_chunks;
+    GB_TRY(map_stage(m, slab_keys + (size_t)ovf_cap + 2 * n_chunks + 16));
+    unsigned long long *keys = m->stage, *d_desc = keys + slab_keys + ovf_cap;
+    const size_t used = (size_t)n_reads * rec;
+    DeviceBuf d_bin;
+    GB_TRY(d_bin.alloc(used + 16, m->stream));
+
+    int n_copy = 4;
+    if (const char *e = getenv("GENOME_B200_H2D_CHUNKS")) n_copy = std::max(1, std::min(16, atoi(e)));
+    const int64_t per_chunk = std::max<int64_t>(TILE_READS, ((n_reads + n_copy - 1) / n_copy + TILE_READS - 1) / TILE_READS * TILE_READS);
+    cudaEvent_t entry = nullptr, copied[16];
+    for (auto &e : copied) e = nullptr;
+    struct Guard {
+        cudaEvent_t *entry, *copied;
+        ~Guard()
+        {
+            if (*entry) cudaEventDestroy(*entry);
+            for (int i = 0; i < 16; i++)
+                if (copied[i]) cudaEventDestroy(copied[i]);
+        }
+    } guard{ &entry, copied };
+    GB_CUDA(cudaEventCreateWithFlags(&entry, cudaEventDisableTiming));
+    if (!m->pe[0])
+        for (int i = 0; i < 4; i++) GB_CUDA(cudaEventCreate(&m->pe[i]));
+
+    GB_TRY(map_zero_counters(m));
+    m->phase_ns[0] = m->phase_ns[1] = m->phase_ns[2] = 0;
+    GB_CUDA(cudaEventRecord(m->ev0, m->stream));
+    GB_TRY(slab_list_begin(pl, w, m->stream));
+    // the copy stream may not write arena memory that work already queued on the map's stream could still be reading
+    GB_CUDA(cudaEventRecord(entry, m->stream));
+    GB_CUDA(cudaStreamWaitEvent(m->copy_stream, entry, 0));
+    int ci = 0;
+    for (int64_t r0 = 0; r0 < n_reads; r0 += per_chunk, ci++) {
+        const int64_t nr = std::min(per_chunk, n_reads - r0);
+        GB_CUDA(cudaMemcpyAsync((uint8_t *)d_bin.p + (size_t)r0 * rec, bin + (size_t)r0 * rec, (size_t)nr * rec, cudaMemcpyHostToDevice, m->copy_stream));
+        GB_CUDA(cudaEventCreateWithFlags(&copied[ci], cudaEventDisableTiming));
+        GB_CUDA(cudaEventRecord(copied[ci], m->copy_stream));
+        GB_CUDA(cudaStreamWaitEvent(m->stream, copied[ci], 0));
+        verify_fixed_kernel<<<grid_for((unsigned long long)nr, 256), 256, 0, m->stream>>>((const uint8_t *)d_bin.p + (size_t)r0 * rec, rec, len0, nr,
+                                                                                       m->d_counters);
+        GB_LAUNCHED();
+        ReadBatch rb;
+        rb.bin = (const uint8_t *)d_bin.p; rb.n_bytes = used; rb.offsets = nullptr; rb.rec_bytes = rec; rb.read0 = r0; rb.n_reads = nr;
+        GB_TRY(slab_list_range(rb, m->k, m->v210, pl, w, keys, slab, ovf_cap, m->stream));
+    }
+    GB_TRY(slab_list_end(pl, w, slab, ovf_cap, d_desc, m, m->stream));
+    GB_CUDA(cudaEventRecord(m->pe[0], m->stream));
+    // ragged? overflow list full?  (one synchronisation, like the ordinary path's verification)
+    unsigned long long c[4], flags[2] = { 0, 0 };
+    GB_CUDA(cudaMemcpyAsync(flags, w.bucket_total, 16, cudaMemcpyDeviceToHost, m->stream));
+    GB_TRY(map_read_counters(m, c));
+    if (c[2] || (unsigned int)flags[1]) {
+        GB_TRY(map_zero_counters(m)); // counters[3] was advanced by slab_list_end
+        return GB_OK;
+    }
+    GB_TRY(insert_key_chunks(m, keys, d_desc, d_desc + n_chunks + 2, (int)n_chunks + 1, (unsigned long long)want, m->stream, true));
+    GB_CUDA(cudaEventRecord(m->ev1, m->stream));
+    GB_TRY(map_read_counters(m, c));
+    float ms = 0;
+    GB_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->pe[0]));
+    m->phase_ns[0] = (int64_t)(ms * 1e6); // copy + bucket pass, overlapped
+    GB_CUDA(cudaEventElapsedTime(&ms, m->pe[0], m->ev1));
+    m->phase_ns[2] = (int64_t)(ms * 1e6);
+    GB_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+    m->last_insert_ns = (int64_t)(ms * 1e6);
+    m->size += (int64_t)c[0];
+    m->windows += (int64_t)c[3];
+    m->fixed_stride = 1;
+    if (n_windows) *n_windows = (int64_t)c[3];
+    *handled = true;
+    return GB_OK;
+}
+
 // host scan of the record chain (PairedEndData.getPairs.read, PairedEndData.scala:24-32)
 int scan_records(const uint8_t *bin, size_t n_bytes, int64_t n_reads, int k,
                         std::vector<unsigned long long> &off, std::vector<int64_t> &winp)
@@ -864,6 +967,11 @@ int gb_map_insert_reads(gb_map *h, const uint8_t *bin, size_t n_bytes, int64_t n
     // i*rec imply the record chain is i*rec).  Otherwise scan the chain on the host.
     unsigned int len0 = bin[0], rec = 1 + (len0 + 3) / 4;
     bool try_fixed = (unsigned long long)n_reads * rec <= n_bytes;
+    if (try_fixed) { // opt-in: chunked copy overlapped with the single-pass bucket pass
+        bool handled = false;
+        GB_TRY(insert_host_pipelined(m, bin, n_reads, rec, len0, n_windows, &handled));
+        if (handled) return GB_OK;
+    }
     DeviceBuf d_bin, d_off;
     if (try_fixed) {
         size_t used = (size_t)n_reads * rec;

@@ -148,6 +148,13 @@ struct SlabOut {
     unsigned long long cap = 0;
     unsigned long long *spread = nullptr;   // new-key tallies (fold_new_keys_kernel)
     unsigned long long *overflowed = nullptr; // keys that took the overflow path (they count as k-windows too)
+    // LIST mode (ovf != nullptr; the chunked host insert): the bucket pass must not touch the table (the stream is not verified
+    // yet), so a key that does not fit its slab is appended to ovf[0 .. ovf_cap) instead (cursor = *overflowed); if that region
+    // fills up too, *failed is set and the caller falls back to the counted passes.  The slab cursors persist across launches
+    // in `count`, so consecutive launches over consecutive read ranges fill the same slabs.
+    unsigned long long *ovf = nullptr;
+    unsigned long long ovf_cap = 0;
+    unsigned int *failed = nullptr;
 };
 
 template <bool FIXED, bool V210, bool SRC_KEYS, bool PEER, bool SLABS>
@@ -168,7 +175,7 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
     // position of the CTA's next key of bucket b, relative to out[0] (a batch holds < 2^32 keys)
     for (unsigned int b = tid; b < nb; b += INSERT_THREADS) {
         if (SLABS) {
-            bcur[b] = (b * gridDim.x + blockIdx.x) * so.slab; // < 2^32: checked by the host
+            bcur[b] = (b * gridDim.x + blockIdx.x) * so.slab + so.count[(size_t)b * gridDim.x + blockIdx.x]; // < 2^32: checked by the host
             continue;
         }
         unsigned int pos = (unsigned int)bucket_base[b] + cta_off[(size_t)blockIdx.x * nb + b];
@@ -253,9 +260,15 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
         __syncthreads();
         for (unsigned int idx = tid; idx < round_total; idx += INSERT_THREADS) {
             if (SLABS && sdst[idx] == 0xFFFFFFFFu) {
-                const unsigned long long key1 = skey[idx], i = slot_of(mix64(key1), so.cap);
-                if (upsert_add(so.table, so.cap, i, load_key(so.table + i), key1, 1)) atomicAdd(&so.spread[blockIdx.x & (SPREAD - 1)], 1ull);
-                atomicAdd(so.overflowed, 1ull);
+                const unsigned long long key1 = skey[idx];
+                if (so.ovf) {
+                    const unsigned long long at = atomicAdd(so.overflowed, 1ull);
+                    if (at < so.ovf_cap) so.ovf[at] = key1; else *so.failed = 1u;
+                } else {
+                    const unsigned long long i = slot_of(mix64(key1), so.cap);
+                    if (upsert_add(so.table, so.cap, i, load_key(so.table + i), key1, 1)) atomicAdd(&so.spread[blockIdx.x & (SPREAD - 1)], 1ull);
+                    atomicAdd(so.overflowed, 1ull);
+                }
                 continue;
             }
             store(sdst[idx], skey[idx]);
@@ -500,9 +513,10 @@ unsigned int slab_keys_for(unsigned long long total, unsigned int nb, int grid)
 
 // chunk table of the slabs, bucket-major: chunk c = (bucket c / grid, CTA c % grid) holds count[c] keys at out[c * slab].
 // desc = vstart[n_chunks + 1] | off[n_chunks]; counters[3] (k-windows) += keys in slabs + keys that took the overflow path.
+// ovf_cap > 0 (LIST mode): one more chunk, number n_chunks, for the overflow region that follows the slabs in `out`.
 __global__ void __launch_bounds__(1024)
 make_slab_chunks_kernel(const unsigned int *count, unsigned int n_chunks, unsigned int slab, unsigned long long *vstart, unsigned long long *off,
-                        const unsigned long long *overflowed, unsigned long long *counters)
+                        const unsigned long long *overflowed, unsigned long long *counters, unsigned long long ovf_cap)
 {
     __shared__ unsigned long long s_part[1024];
     const unsigned int per = (n_chunks + 1023) / 1024, c0 = min(n_chunks, threadIdx.x * per), c1 = min(n_chunks, c0 + per);
@@ -514,7 +528,14 @@ make_slab_chunks_kernel(const unsigned int *count, unsigned int n_chunks, unsign
         unsigned long long acc = 0;
         for (int i = 0; i < 1024; i++) { const unsigned long long v = s_part[i]; s_part[i] = acc; acc += v; }
         vstart[n_chunks] = acc;
-        atomicAdd(&counters[3], acc + *overflowed);
+        if (ovf_cap) { // the overflow list is upserted like any chunk (its keys hit any slice: random access for those few)
+            const unsigned long long in_list = min(*overflowed, ovf_cap);
+            vstart[n_chunks + 1] = acc + in_list;
+            off[n_chunks] = (unsigned long long)n_chunks * slab;
+            atomicAdd(&counters[3], acc + in_list);
+        } else {
+            atomicAdd(&counters[3], acc + *overflowed);
+        }
     }
     __syncthreads();
     unsigned long long run = s_part[threadIdx.x];
@@ -548,6 +569,7 @@ int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &
     so.spread = m->d_spread;
     so.overflowed = w.bucket_total; // one word is enough; the counted passes are not running
     GB_CUDA(cudaMemsetAsync(so.overflowed, 0, 8, st));
+    GB_CUDA(cudaMemsetAsync(so.count, 0, (size_t)n_chunks * 4, st)); // the kernel resumes from these cursors
     PeerOut po;
     memset(&po, 0, sizeof po);
     KeySource none;
@@ -556,7 +578,46 @@ int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &
     else { if (v210) GB_PSS(false, true); else GB_PSS(false, false); }
 #undef GB_PSS
     GB_LAUNCHED();
-    make_slab_chunks_kernel<<<1, 1024, 0, st>>>(so.count, n_chunks, slab, d_desc, d_desc + n_chunks + 1, so.overflowed, m->d_counters);
+    make_slab_chunks_kernel<<<1, 1024, 0, st>>>(so.count, n_chunks, slab, d_desc, d_desc + n_chunks + 1, so.overflowed, m->d_counters, 0ull);
+    GB_LAUNCHED();
+    return GB_OK;
+}
+
+// LIST mode, one launch per read range (the chunked host insert of map.cu).  begin: zero the cursors; range: one bucket-pass
+// launch over rb; end: chunk table with the overflow chunk, desc = vstart[n_chunks + 2] | off[n_chunks + 1].
+// out = nb * grid slabs | overflow region of ovf_cap keys.  w.bucket_total[0] = overflow cursor, [1] = failed flag.
+int slab_list_begin(const PartLayout &pl, PartWork &w, cudaStream_t st)
+{
+    GB_TRY(w.ensure(st));
+    GB_CUDA(cudaMemsetAsync(w.bucket_total, 0, 16, st));
+    GB_CUDA(cudaMemsetAsync(w.cta_hist, 0, (size_t)pl.nb() * w.grid * 4, st));
+    return GB_OK;
+}
+int slab_list_range(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, unsigned int slab,
+                    unsigned long long ovf_cap, cudaStream_t st)
+{
+    const unsigned int nb = (unsigned int)pl.nb();
+    if (nb > STAGE_MAX_BUCKETS || pl.owners != 1 || rb.offsets) { set_error("internal: slab list pass misuse"); return GB_E_ARG; }
+    SlabOut so;
+    so.slab = slab;
+    so.count = w.cta_hist;
+    so.overflowed = w.bucket_total;
+    so.ovf = out + (size_t)slab * nb * (size_t)w.grid;
+    so.ovf_cap = ovf_cap;
+    so.failed = reinterpret_cast<unsigned int *>(w.bucket_total + 1);
+    PeerOut po;
+    memset(&po, 0, sizeof po);
+    KeySource none;
+    const size_t smem = scatter_smem(nb);
+    if (v210) part_scatter_kernel<true, true, false, false, true><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, 1u, pl.lp_bits, nb, nullptr, nullptr, out, po, so);
+    else part_scatter_kernel<true, false, false, false, true><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, 1u, pl.lp_bits, nb, nullptr, nullptr, out, po, so);
+    GB_LAUNCHED();
+    return GB_OK;
+}
+int slab_list_end(const PartLayout &pl, PartWork &w, unsigned int slab, unsigned long long ovf_cap, unsigned long long *d_desc, Map *m, cudaStream_t st)
+{
+    const unsigned int n_chunks = (unsigned int)pl.nb() * (unsigned int)w.grid;
+    make_slab_chunks_kernel<<<1, 1024, 0, st>>>(w.cta_hist, n_chunks, slab, d_desc, d_desc + n_chunks + 2, w.bucket_total, m->d_counters, ovf_cap);
     GB_LAUNCHED();
     return GB_OK;
 }

@@ -78,6 +78,11 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
 
 // the single-pass bucket pass (no count pass; GENOME_B200_COUNTLESS=1, single-GPU insert): see part_scatter_kernel<..., SLABS>
 unsigned int slab_keys_for(unsigned long long total, unsigned int nb, int grid);
+// the same in LIST mode for the chunked host insert: begin / one launch per read range / end (see partition.cu)
+int slab_list_begin(const PartLayout &pl, PartWork &w, cudaStream_t st);
+int slab_list_range(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, unsigned int slab,
+                    unsigned long long ovf_cap, cudaStream_t st);
+int slab_list_end(const PartLayout &pl, PartWork &w, unsigned int slab, unsigned long long ovf_cap, unsigned long long *d_desc, Map *m, cudaStream_t st);
 int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, unsigned int slab,
                        unsigned long long *d_desc, Map *m, cudaStream_t st);
 

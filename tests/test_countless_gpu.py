@@ -63,6 +63,34 @@ def test_countless_overflow_path(gpu, countless):
     check(synth.pack_fixed(reads), reads.shape[0], k)
 
 
+def test_countless_overflow_list(gpu, countless):
+    """The chunked host insert keeps overflowing keys in a list (it may not touch the table before the whole stream is
+    verified).  4 % identical reads among random ones: their windows overflow the slabs of a few buckets but fit the list
+    (1/16 of the keys); 30 %: the list fills up, the call falls back to the ordinary path.  Exact either way."""
+    k = 25
+    genome = synth.random_genome(400000, 9)
+    for frac in (0.04, 0.3):
+        reads = synth.sample_reads(genome, 100, 40000, 0.0, 10)
+        n_same = int(frac * reads.shape[0])
+        reads[:n_same] = reads[0]
+        check(synth.pack_fixed(reads), reads.shape[0], k, cap=1 << 22)
+
+
+def test_countless_ragged_stream_falls_back(gpu, countless):
+    """A stream whose first records have equal lengths but that is ragged further on: the chunked path verifies on the device
+    chunk by chunk and must leave the table untouched when it finds out."""
+    k = 21
+    genome = synth.random_genome(300000, 11)
+    reads = synth.sample_reads(genome, 100, 30000, 0.0, 12)
+    lst = [reads[i] for i in range(reads.shape[0])]
+    lst[25000] = lst[25000][:60]   # one short record, in the last chunk
+    lst += [reads[0], reads[1]]    # two spare records: the stream stays long enough for a fixed-stride attempt on 30 000 reads
+    b = synth.pack_ragged(lst)
+    n = reads.shape[0]
+    assert n * 26 <= b.size
+    check(b, n, k, cap=1 << 22)
+
+
 def test_countless_at_size(gpu, countless):
     """1.5 M reads of a 5 Mbp genome with 1 % errors (the C2 shape): enough keys for real slabs (hundreds per (bucket, CTA)),
     compared through size-independent properties and against the default path."""
