@@ -21,7 +21,7 @@ import json
 for f in ('default', 'countless'):
     try:
         d = json.loads(open('gpurun_out/r2_bench_%s.json' % f).read().strip().splitlines()[-1])
-        print(f, '%.3f ms/step' % d['ms_per_step'], d['roofline'].get('phases_ms'), d['roofline'].get('insert_ms'))
+        print(f, '%.3f ms/step device' % d['ms_per_step'], '%.3f ms/step e2e' % d['e2e']['ms_per_step'], d['roofline'].get('phases_ms'), d['roofline'].get('insert_ms'))
     except Exception as e:
         print(f, 'failed', e)
 "
