@@ -8,6 +8,8 @@ export GENOME_B200_UNVALIDATED=1
 {
   echo "== opt-in device tests"
   timeout 1200 python -m pytest tests/test_sgraph_gpu.py tests/test_graphmap_gpu.py tests/test_scripts_gpu.py tests/test_countless_gpu.py -q -m gpu 2>&1 | tail -25
+  echo "== sharded graph build through the NCCL fabric, one rank (works on a one-GPU box)"
+  timeout 600 python -m pytest tests/test_parity_multigpu.py -q -m gpu -k "sharded_graph_build and 1" 2>&1 | tail -8
   NGPU=$(python -c "import torch; print(torch.cuda.device_count())")
   if [ "$NGPU" -ge 2 ]; then
     echo "== sharded graph build over $NGPU ranks"

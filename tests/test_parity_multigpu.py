@@ -37,10 +37,11 @@ def test_pmap_routing_variants(gpu, env):
 
 
 @pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")
-@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("world", [1, 2, 8])
 def test_pmap_sharded_graph_build(gpu, world):
     """Graph.buildGraph over the shards WITHOUT a replica (csrc/sgraph.cuh over the NCCL + CUDA-IPC fabric of comm.cu): the
-    same worker, same oracle comparisons, with GENOME_B200_PGRAPH=sharded.  Opt-in until it has passed on a B200 box."""
+    same worker, same oracle comparisons, with GENOME_B200_PGRAPH=sharded.  world = 1 runs the NCCL fabric (single-rank
+    collectives, no IPC mapping to open) on a one-GPU box.  Opt-in until it has passed on a B200 box."""
     if gpu < world:
         pytest.skip("needs %d GPUs, box has %d" % (world, gpu))
     run_world(world, {"GENOME_B200_PGRAPH": "sharded"})
