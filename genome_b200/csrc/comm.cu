@@ -889,6 +889,8 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
         GB_TRY(ensure_inboxes(c, 0)); // settles c->p2p (collective)
         if (c->p2p == 1) {
             GB_CUDA(cudaStreamSynchronize(m->stream));
+            // scratch for this rank's share after the re-routing (about its own size; twice that leaves room for imbalance)
+            GB_TRY(m->arena.reserve((size_t)m->size * 2 * 140 + (size_t)total * 4 + ((size_t)64 << 20)));
             NcclFabric fab(c);
             Map *maps[1] = { m };
             const int rc = graph_build_on_fabric(fab, maps, c->stream, dual != 0, out);

@@ -269,6 +269,26 @@ struct Arena {
         }
         off = 0;
     }
+    // make the base block at least `want` bytes before a call that will make many allocations (each allocation beyond the
+    // base costs one of the 64 overflow entries).  Only at the start of a scope, before anything was handed out.
+    int reserve(size_t want)
+    {
+        if (off != 0 || n_overflow != 0 || want <= cap) return GB_OK;
+        cudaDeviceSynchronize(); // the old block may still be in use by work queued earlier
+        if (base) arena_cache_put(base, cap);
+        size_t got = 0;
+        base = (char *)arena_cache_get(want, &got);
+        if (base) { cap = got; return GB_OK; }
+        cap = 0;
+        if (cudaMalloc((void **)&base, want) != cudaSuccess) {
+            base = nullptr;
+            cudaGetLastError();
+            set_error("out of device memory for %zu bytes of scratch", want);
+            return GB_E_OOM;
+        }
+        cap = want;
+        return GB_OK;
+    }
     void destroy()
     {
         for (int i = 0; i < n_overflow; i++) arena_cache_put(overflow[i], overflow_size[i]);

@@ -20,13 +20,39 @@
 namespace gb {
 namespace sg {
 
+// Scratch of one build: a few large chunks (8 MB, doubling) taken from the calling handle's arena and handed out by bumping.
+// A build makes ~15 allocations per rank, a virtual-shard build 16 times that; the arena itself keeps at most 64 blocks
+// beyond its base, which such a build would exhaust on its first call (the arena regrows to one block for the next call).
+struct Pool {
+    Arena *arena = nullptr; // an ArenaScope is open on it
+    char *cur = nullptr;
+    size_t left = 0, next = (size_t)8 << 20;
+    int alloc(void **p, size_t bytes)
+    {
+        bytes = (bytes + 255) & ~(size_t)255;
+        if (!bytes) bytes = 256;
+        if (bytes > left) {
+            const size_t want = bytes > next ? bytes : next;
+            if (next < ((size_t)1 << 30)) next *= 2;
+            void *c = nullptr;
+            GB_TRY(arena->alloc(&c, want));
+            cur = (char *)c;
+            left = want;
+        }
+        *p = cur;
+        cur += bytes;
+        left -= bytes;
+        return GB_OK;
+    }
+};
+
 struct Exec {
     cudaStream_t st = nullptr;
-    Arena *scratch = nullptr; // the calling handle's arena (an ArenaScope is open on it)
+    Pool *scratch = nullptr;
     Arena *store = nullptr;   // the resulting graph's store arena
 };
 
-int sg_alloc(Exec &ex, void **p, size_t bytes) { return ex.scratch->alloc(p, bytes ? bytes : 16); }
+int sg_alloc(Exec &ex, void **p, size_t bytes) { return ex.scratch->alloc(p, bytes); }
 int sg_graph_alloc(Exec &ex, void **p, size_t bytes) { return ex.store->alloc(p, bytes ? bytes : 16); }
 int sg_zero(Exec &ex, void *p, size_t bytes)
 {
@@ -88,7 +114,7 @@ int sg_launch(Exec &ex, u64 n, const Op &op)
 // the kept k-mers of each local rank come out of its map (all live keys; counts are not needed), the result goes into a
 // fresh Graph handle
 static int build_with(sg::Fabric &fab, Map *const *maps, const std::vector<std::pair<const unsigned long long *, unsigned long long>> *given,
-                      cudaStream_t stream, Arena *scratch, int device, int k, bool dual, bool v210, gb_graph **out)
+                      cudaStream_t stream, sg::Pool *scratch, int device, int k, bool dual, bool v210, gb_graph **out)
 {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     GB_CUDA(cudaEventCreate(&ev0));
@@ -150,7 +176,9 @@ static int build_with(sg::Fabric &fab, Map *const *maps, const std::vector<std::
 int graph_build_on_fabric(sg::Fabric &fab, Map *const *maps, cudaStream_t stream, bool dual, gb_graph **out)
 {
     Map *m = maps[0];
-    return build_with(fab, maps, nullptr, stream, &m->arena, m->device, m->k, dual, m->v210, out);
+    sg::Pool pool;
+    pool.arena = &m->arena;
+    return build_with(fab, maps, nullptr, stream, &pool, m->device, m->k, dual, m->v210, out);
 }
 
 } // namespace gb
@@ -167,6 +195,8 @@ extern "C" int gb_graph_build_virtual_shards(gb_map *h, int n_shards, gb_graph *
     if (n_shards < 1 || n_shards > sg::MAXR) { set_error("n_shards must be in 1..%d", sg::MAXR); return GB_E_ARG; }
     // every live key of the map, dealt to the virtual ranks in table order
     const unsigned long long n = (unsigned long long)m->size;
+    // ~120 B of scratch per key (export, staging, window, neighbours, three scan arrays) + a replicated segment list per rank
+    GB_TRY(m->arena.reserve((size_t)n * (140 + 2 * (size_t)n_shards) + ((size_t)64 << 20)));
     DeviceBuf keys, vals;
     GB_TRY(keys.alloc((size_t)n * 8));
     GB_TRY(vals.alloc((size_t)n * 4));
@@ -178,11 +208,13 @@ extern "C" int gb_graph_build_virtual_shards(gb_map *h, int n_shards, gb_graph *
     }
     std::vector<sg::Exec *> none((size_t)n_shards, nullptr);
     // the fabric copies through the ranks' Execs, which build_with creates: a LocalFabric over one shared Exec does the same
+    sg::Pool pool;
+    pool.arena = &m->arena;
     sg::Exec shared;
     shared.st = m->stream;
-    shared.scratch = &m->arena;
+    shared.scratch = &pool;
     shared.store = nullptr;
     for (auto &e : none) e = &shared;
     sg::LocalFabric fab(n_shards, none);
-    return build_with(fab, nullptr, &given, m->stream, &m->arena, m->device, m->k, m->noncanonical, m->v210, out);
+    return build_with(fab, nullptr, &given, m->stream, &pool, m->device, m->k, m->noncanonical, m->v210, out);
 }
