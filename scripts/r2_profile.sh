@@ -21,6 +21,6 @@ GENOME_B200_COUNTLESS=1 $NCU --set full --import-source on -k regex:"part_scatte
 
 python scripts/sgraph_timing.py C2 > gpurun_out/sgraph_timing_r2.json 2> gpurun_out/sgraph_timing_r2.err || exit 1
 # the 8-rank virtual build: one launch of each heavy functor (masks, classify, jump, segment jump, close, bases)
-$NCU --set full --import-source on -k regex:"items_kernel" -c 40 -o gpurun_out/prof_sgraph_r2 -f \
+SG_P=8 $NCU --set full --import-source on -k regex:"items_kernel" -c 160 -o gpurun_out/prof_sgraph_r2 -f \
     python scripts/sgraph_timing.py C2 > gpurun_out/ncu_sgraph_r2.log 2>&1
 ls -la gpurun_out/*.ncu-rep

@@ -40,7 +40,7 @@ def timed(label, build):
 
 
 timed("single", lambda: Graph.buildGraph(K, m))
-for P in (1, 2, 4, 8, 16):
+for P in [int(x) for x in os.environ.get("SG_P", "1,2,4,8,16").split(",")]:   # SG_P=8: one shard count only (profiling)
     timed("virtual_shards_%d" % P, lambda: Graph.buildGraphVirtualShards(K, m, P))
 ref = out["builds"][0]["counts"]
 out["all_equal_counts"] = all(r["counts"] == ref for r in out["builds"])
