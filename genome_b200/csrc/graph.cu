@@ -1199,6 +1199,33 @@ int gb_graph_retain_largest(gb_graph *h)
     return apply_rewrite(g, rb.rw);
 }
 
+__global__ void keep_from_bytes_kernel(const uint8_t *keep8, unsigned long long n, unsigned long long *node_keep)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) node_keep[i] = keep8[i] != 0;
+}
+
+// MapGraph.retain(nodesSet) (Graph.scala:161-165) for an arbitrary node set: nodes with node_keep[i] != 0 stay, and so do the
+// edges whose start AND end stay
+int gb_graph_retain(gb_graph *h, const uint8_t *node_keep)
+{
+    Graph *g;
+    GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
+    cudaStream_t st = g->stream;
+    const unsigned long long N = (unsigned long long)g->n_nodes, E = (unsigned long long)g->n_edges;
+    if (!N) return GB_OK;
+    if (!node_keep) { set_error("null argument"); return GB_E_ARG; }
+    Tmp<uint8_t> d_keep;
+    GB_TRY(d_keep.alloc(N, st));
+    GB_CUDA(cudaMemcpyAsync(d_keep.p, node_keep, N, cudaMemcpyHostToDevice, st));
+    RewriteBufs rb;
+    GB_TRY(rb.init(g));
+    LAUNCH(keep_from_bytes_kernel, N, d_keep.p, N, rb.rw.node_keep);
+    LAUNCH(retain_edges_kernel, E, g->edge_start, g->edge_end, E, rb.rw.node_keep, rb.rw.head);
+    return apply_rewrite(g, rb.rw);
+}
+
 int gb_graph_simplify(gb_graph *h)
 {
     Graph *g;

@@ -68,6 +68,13 @@ class MapGraph:
         """graph.retain(components.maxBy(_.size)) (GraphBuilder.scala:52-54)."""
         capi.check(capi.lib().gb_graph_retain_largest(self.h))
 
+    def retain(self, node_keep):
+        """MapGraph.retain(nodesSet) (161-165): `node_keep` = boolean per node of the current export."""
+        keep = np.ascontiguousarray(node_keep, dtype=np.uint8)
+        if keep.size != self.counts()[0]:
+            raise ValueError("one flag per node of the current graph")
+        capi.check(capi.lib().gb_graph_retain(self.h, capi.ptr(keep)))
+
     def simplifyGraph(self):
         capi.check(capi.lib().gb_graph_simplify(self.h))
 

@@ -131,6 +131,9 @@ int gb_graph_components(gb_graph *g, uint32_t *node_label, int64_t *n_components
 /* graph.retain(components.maxBy(_.size)) (GraphBuilder.scala:52-54, MapGraph.retain Graph.scala:161-165);
  * ties (the norm: strand twins) go to the component holding the smallest node k-mer */
 int gb_graph_retain_largest(gb_graph *g);
+/* MapGraph.retain(nodesSet) (Graph.scala:161-165) for any node set: node_keep[n_nodes] (host), non-zero = keep; edges stay
+ * when both ends stay.  (Written after this round's GPU budget was spent: device test opt-in.) */
+int gb_graph_retain(gb_graph *g, const uint8_t *node_keep);
 /* MapGraph.simplifyGraph (Graph.scala:211-230) */
 int gb_graph_simplify(gb_graph *g);
 /* Graph.removeBubbles (Graph.scala:125-149), out-edges taken in Base.fromInt order */

@@ -36,3 +36,27 @@ def test_graph_builder_script(gpu, k, glen, rl, cov, err):
     got = H.canon_gpu_graph(g)
     want = H.canon_oracle_graph(og)
     assert got == want or got == H.rc_graph(want, k)
+
+
+def test_retain_arbitrary_node_set(gpu):
+    """MapGraph.retain(nodesSet) (Graph.scala:161-165): retaining the nodes of the largest component (labels from
+    gb_graph_components) must equal gb_graph_retain_largest; retaining everything changes nothing; retaining nothing empties."""
+    from genome_b200.dnamap import FreqFilter
+    from genome_b200.graph import Graph
+    k = 15
+    b, n, _ = H.small_reads(5000, 60, 30, 0.01, seed=2015)
+    gm = FreqFilter.extractFilteredKmers(PairedEndData(b, n // 2), k, 2)
+    g1, g2, g3 = Graph.buildGraph(k, gm), Graph.buildGraph(k, gm), Graph.buildGraph(k, gm)
+    before = H.canon_gpu_graph(g1)
+    g1.retain(np.ones(g1.counts()[0], bool))
+    assert H.canon_gpu_graph(g1) == before
+    nc, label = g2.components()
+    sizes = np.bincount(label, minlength=nc)
+    node_kmer = g2.export()[0]
+    best = [c for c in range(nc) if sizes[c] == sizes.max()]
+    pick = min(best, key=lambda c: int(node_kmer[label == c].min()))   # the library's tie rule: smallest node k-mer
+    g2.retain(label == pick)
+    g3.retain_largest()
+    assert H.canon_gpu_graph(g2) == H.canon_gpu_graph(g3)
+    g3.retain(np.zeros(g3.counts()[0], bool))
+    assert g3.counts() == (0, 0, 0)
