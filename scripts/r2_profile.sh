@@ -23,4 +23,8 @@ python scripts/sgraph_timing.py C2 > gpurun_out/sgraph_timing_r2.json 2> gpurun_
 # the 8-rank virtual build: one launch of each heavy functor (masks, classify, jump, segment jump, close, bases)
 SG_P=8 $NCU --set full --import-source on -k regex:"items_kernel" -c 160 -o gpurun_out/prof_sgraph_r2 -f \
     python scripts/sgraph_timing.py C2 > gpurun_out/ncu_sgraph_r2.log 2>&1
+# paired-end path support (DESIGN 3.6 was timed but never profiled): filter + walk kernels
+python scripts/walk_timing.py > gpurun_out/walk_timing_r2.json 2> gpurun_out/walk_timing_r2.err && \
+$NCU --set full --import-source on -k regex:"walk_|posmap_" -c 12 -o gpurun_out/prof_walk_r2 -f \
+    python scripts/walk_timing.py > gpurun_out/ncu_walk_r2.log 2>&1
 ls -la gpurun_out/*.ncu-rep
