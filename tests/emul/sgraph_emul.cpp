@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../genome_b200/csrc/sgraph.cuh"
+#include "../../genome_b200/csrc/superkmer.cuh"
 
 namespace gb {
 void set_error(const char *, ...) {}
@@ -286,6 +287,28 @@ int emul_sharded_build(int k, int dual, int v210, int P, const uint64_t *keys, c
         memcpy(bases, res.bases, ((res.n_bases + 15) / 16) * 4);
     }
     return 0;
+}
+
+// the super-k-mer splitting (superkmer.cuh) of a fixed-stride `.bin` stream: two passes like the device code would run them.
+// per_owner[P] receives the record counts; with `records` != NULL owner o's records are written, 16 bytes each, one owner
+// after the other (o's block starts at record sum(per_owner[0..o))).  Returns the number of k-windows.
+uint64_t emul_superkmers(const uint8_t *bin, uint32_t rec_bytes, uint64_t n_reads, int k, int P, uint64_t *per_owner, uint64_t *records)
+{
+    Exec ex;
+    const int m = minimizer_len(k);
+    uint64_t windows = 0;
+    for (int o = 0; o < P; o++) per_owner[o] = 0;
+    sg_launch(ex, n_reads, SkCountOp{ bin, rec_bytes, k, m, P, (u64 *)per_owner, (u64 *)&windows });
+    if (records) {
+        std::vector<u64> cursor((size_t)P, 0);
+        std::vector<u64 *> out((size_t)P);
+        uint64_t at = 0;
+        for (int o = 0; o < P; o++) { out[(size_t)o] = (u64 *)records + 2 * at; at += per_owner[o]; }
+        sg_launch(ex, n_reads, SkEmitOp{ bin, rec_bytes, k, m, P, cursor.data(), out.data() });
+        for (int o = 0; o < P; o++)
+            if (cursor[(size_t)o] != per_owner[o]) return ~0ull;
+    }
+    return windows;
 }
 
 // owner of a k-mer and of its 8 neighbours (4 successors, then 4 predecessors): incremental form vs full recomputation
