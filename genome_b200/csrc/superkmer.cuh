@@ -8,7 +8,8 @@
 // STATUS: the splitting logic only, as backend-agnostic per-item code (one read per call), checked on the CPU through
 // tests/emul/sgraph_emul.cpp (tests/test_superkmer_emul_cpu.py): the records reproduce the reads' k-window multiset exactly and
 // every window of a record has the record's owner.  Not wired into comm.cu yet (the NVLink measurements that motivate it are
-// in DESIGN.md; the receiver needs "fixed stride, per-record length" in extract.cuh).
+// in DESIGN.md).  Receiver side: extract.cuh's stage_tile<FIXED> already reads every record's own length byte, so a record
+// stream is insertable as it is; the host-side fixed-stride verification and exact window bounds are what must be relaxed.
 #pragma once
 #include "sgraph.cuh"
 
