@@ -40,6 +40,7 @@ SIGNATURES = {
     "gb_map_destroy": (C.c_int, [_vp]),
     "gb_map_insert_reads": (C.c_int, [_vp, _vp, _sz, _i64, _pi64]),
     "gb_map_insert_reads_device": (C.c_int, [_vp, _vp, _sz, _vp, _i64, _pi64]),
+    "gb_map_insert_records_device": (C.c_int, [_vp, _vp, _sz, C.c_uint32, _i64, C.c_uint32, _pi64]),
     "gb_map_update_counts": (C.c_int, [_vp, _vp, _i64]),
     "gb_map_update": (C.c_int, [_vp, _vp, _vp, _i64]),
     "gb_map_size": (C.c_int, [_vp, _pi64]),

@@ -177,6 +177,21 @@ __global__ void verify_fixed_kernel(const uint8_t *__restrict__ bin, unsigned in
     if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicOr(&counters[2], 1ull);
 }
 
+// records at a fixed stride with their own length bytes (gb_map_insert_records_device): every length must fit the stride and
+// stay at or below max_len; counters[2] != 0 otherwise
+__global__ void verify_records_kernel(const uint8_t *__restrict__ bin, unsigned int rec_bytes, unsigned int max_len, long long n_reads,
+                                      unsigned long long *counters)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    int bad = 0;
+    for (; i < n_reads; i += stride) {
+        const unsigned int len = bin[(unsigned long long)i * rec_bytes];
+        bad |= len > max_len || 1 + (len + 3) / 4 > rec_bytes;
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && (threadIdx.x & 31) == 0) atomicOr(&counters[2], 1ull);
+}
+
 // update(key, 1, _ + 1) / update(key, v) for explicit keys
 // SET: update(key, v); set_vid: additionally slot.vid = the key's index in `keys` (keys must be distinct then)
 template <bool SET>
@@ -594,9 +609,10 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
 
 // Core of gb_map_insert_reads*: the stream is on the device.  h_windows_prefix (optional, n_reads+1) gives
 // exact per-read window prefix sums for batching in the ragged case.
+// lengths_vary (fixed stride only): len0 is the LARGEST record length, window counts derived from it are upper bounds
 static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off,
                          bool fixed, unsigned int rec, unsigned int len0, int64_t n_reads,
-                         const int64_t *h_win_prefix, int64_t *n_windows)
+                         const int64_t *h_win_prefix, int64_t *n_windows, bool lengths_vary = false)
 {
     GB_TRY(map_zero_counters(m));
     m->kept_valid = false;
@@ -641,7 +657,8 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
             };
             for (int64_t o = 0; o < take; o += max_reads) {
                 const int64_t sub = std::min(max_reads, take - o);
-                GB_TRY(insert_partitioned(m, d_bin, n_bytes, fixed ? nullptr : d_off, rec, done + o, sub, win_upper, fixed || h_win_prefix != nullptr));
+                GB_TRY(insert_partitioned(m, d_bin, n_bytes, fixed ? nullptr : d_off, rec, done + o, sub, win_upper,
+                                          (fixed && !lengths_vary) || h_win_prefix != nullptr));
             }
         } else if (fixed) {
             GB_TRY(launch_insert<true>(m, d_bin, n_bytes, nullptr, rec, done, take));
@@ -1002,6 +1019,26 @@ int gb_map_insert_reads(gb_map *h, const uint8_t *bin, size_t n_bytes, int64_t n
     GB_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, m->stream));
     return insert_device(m, (const uint8_t *)d_bin.p, used, (const unsigned long long *)d_off.p, false, 0, 0, n_reads,
                          winp.data(), n_windows);
+}
+
+int gb_map_insert_records_device(gb_map *h, const uint8_t *d_bin, size_t n_bytes, uint32_t rec_bytes, int64_t n_records, uint32_t max_len,
+                                 int64_t *n_windows)
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    ArenaScope scope(&m->arena);
+    if (n_windows) *n_windows = 0;
+    if (n_records < 0 || (!d_bin && n_records > 0) || rec_bytes < 1 || rec_bytes > (uint32_t)MAX_REC_BYTES || max_len > 255) { set_error("bad arguments"); return GB_E_ARG; }
+    if (n_records == 0) return GB_OK;
+    if ((unsigned long long)n_records * rec_bytes > n_bytes) { set_error("truncated record stream"); return GB_E_ARG; }
+    GB_TRY(map_zero_counters(m));
+    verify_records_kernel<<<grid_for((unsigned long long)n_records, 256), 256, 0, m->stream>>>(d_bin, rec_bytes, max_len, n_records, m->d_counters);
+    GB_LAUNCHED();
+    unsigned long long c[4];
+    GB_TRY(map_read_counters(m, c));
+    if (c[2]) { set_error("a record is longer than max_len = %u or than its %u-byte stride", max_len, rec_bytes); return GB_E_ARG; }
+    m->fixed_stride = 1;
+    return insert_device(m, d_bin, n_bytes, nullptr, true, rec_bytes, max_len, n_records, nullptr, n_windows, true);
 }
 
 static int update_common(gb_map *h, const uint64_t *keys, const int32_t *vals, int64_t n, bool set)

@@ -183,6 +183,13 @@ class _MapBase:
                                                             capi.ptr(d_offsets_ptr), int(n_reads), C.byref(w)))
         return w.value
 
+    def insert_records_device(self, d_bin_ptr, n_bytes, rec_bytes, n_records, max_len):
+        """Records at a fixed stride with their own length bytes (padded ragged reads; super-k-mer records), in device memory."""
+        w = C.c_int64()
+        capi.check(capi.lib().gb_map_insert_records_device(self.h, capi.ptr(int(d_bin_ptr)), int(n_bytes), int(rec_bytes), int(n_records),
+                                                           int(max_len), C.byref(w)))
+        return w.value
+
     # ---- deleteAll / mapReduce / foreach
     def delete_below(self, rounds):
         """deleteAll((k, v) => v < rounds) (FreqFilter.scala:55)."""

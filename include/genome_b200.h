@@ -71,6 +71,13 @@ int gb_map_insert_reads(gb_map *m, const uint8_t *bin, size_t n_bytes, int64_t n
 int gb_map_insert_reads_device(gb_map *m, const uint8_t *d_bin, size_t n_bytes, const uint64_t *d_offsets,
                                int64_t n_reads, int64_t *n_windows);
 
+/* same for n_records records laid out at a FIXED STRIDE of rec_bytes, each with its own length byte (<= max_len, and
+ * 1 + ceil(len / 4) <= rec_bytes; the rest of a record is padding): ragged reads without an offset array, and the receiving
+ * end of the super-k-mer wire format (csrc/superkmer.cuh: 16-byte records, max_len 52).  Records shorter than k contribute
+ * nothing (FreqFilter.scala:29).  (Written after this round's GPU budget was spent: device test opt-in.) */
+int gb_map_insert_records_device(gb_map *m, const uint8_t *d_bin, size_t n_bytes, uint32_t rec_bytes, int64_t n_records, uint32_t max_len,
+                                 int64_t *n_windows);
+
 /* update(key, 1, _ + 1) for n keys taken as they are (DNAMap.update(key, v0, f), ArrayDNAMap.scala:198-203
  * with the closure of FreqFilter.scala:33).  Keys need not be canonical. */
 int gb_map_update_counts(gb_map *m, const uint64_t *keys, int64_t n);

@@ -105,3 +105,45 @@ def test_countless_at_size(gpu, countless):
     assert ref.insert_reads(b, n) == w
     rk, rv = ref.export_sorted()
     assert np.array_equal(gk, rk) and np.array_equal(gv, rv)
+
+
+@pytest.mark.parametrize("k,P", [(31, 8), (21, 2)])
+def test_superkmer_records_insert_like_the_reads(gpu, k, P):
+    """The receiving end of the super-k-mer wire format (csrc/superkmer.cuh), on one GPU: the reads are cut into 16-byte
+    records on the CPU (the g++ build of the splitting code), the records go through gb_map_insert_records_device -- fixed
+    stride, per-record lengths -- and the table must equal the oracle's table of the READS.  Also with the single-pass bucket
+    pass, whose upsert takes the exact total from the device."""
+    import torch
+    from tests.test_sgraph_emul_cpu import load_emul
+    from tests.test_superkmer_emul_cpu import split
+    lib = load_emul()
+    genome = synth.random_genome(300000, 21)
+    reads = synth.sample_reads(genome, 100, 60000, 0.01, 22)
+    b = synth.pack_fixed(reads)
+    w, per_owner, recs = split(lib, b, reads.shape[0], 26, k, P)
+    om, ow = H.oracle_counts(b, reads.shape[0], k)
+    assert w == ow
+    ok, ov = om.export_sorted()
+    d = torch.zeros(recs.size + 16, dtype=torch.uint8, device="cuda")
+    d[:recs.size].copy_(torch.from_numpy(np.ascontiguousarray(recs).reshape(-1)))
+    for env in ({}, {"GENOME_B200_INSERT": "partitioned"}, {"GENOME_B200_INSERT": "partitioned", "GENOME_B200_COUNTLESS": "1"}):
+        old = {k_: os.environ.get(k_) for k_ in ("GENOME_B200_INSERT", "GENOME_B200_COUNTLESS")}
+        try:
+            for k_ in old:
+                os.environ.pop(k_, None)
+            os.environ.update(env)
+            gm = ArrayDNAMap(k, 1 << 22)
+            assert gm.insert_records_device(d.data_ptr(), recs.size, 16, recs.shape[0], 52) == w
+            gk, gv = gm.export_sorted()
+            assert np.array_equal(gk, ok) and np.array_equal(gv, ov), env
+            gm.close()
+        finally:
+            for k_, v in old.items():
+                os.environ.pop(k_, None)
+                if v is not None:
+                    os.environ[k_] = v
+    # a record longer than max_len is an argument error, the table stays as it was
+    gm = ArrayDNAMap(k, 1 << 20)
+    with pytest.raises(Exception):
+        gm.insert_records_device(d.data_ptr(), recs.size, 16, recs.shape[0], 40)
+    assert gm.size == 0

@@ -18,18 +18,23 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-@pytest.fixture(scope="module")
-def emul():
+def load_emul():
+    """Builds (when stale) and loads tests/emul/sgraph_emul.cpp; also used by device tests that need the CPU side of a format."""
     src = os.path.join(HERE, "emul", "sgraph_emul.cpp")
     out = os.path.join(HERE, "_build", "libsgraph_emul.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    deps = [src] + [os.path.join(ROOT, "genome_b200", "csrc", f) for f in ("sgraph.cuh", "common.cuh")]
+    deps = [src] + [os.path.join(ROOT, "genome_b200", "csrc", f) for f in ("sgraph.cuh", "sgraph_fabric.cuh", "superkmer.cuh", "common.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
                                "-pthread", "-Wl,-Bsymbolic", "-I" + cuda_inc, "-o", out, src])   # -Bsymbolic: the library binds its own
         # gb::sg::* symbols; the product library (loaded RTLD_GLOBAL by genome_b200.capi) exports the CUDA versions of them
     return C.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    return load_emul()
 
 
 def ptr(a):
