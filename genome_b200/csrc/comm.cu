@@ -23,6 +23,7 @@
 #include "extract.cuh"
 #include "partition.cuh"
 #include "sgraph_fabric.cuh"
+#include "superkmer.cuh"
 
 namespace gb {
 
@@ -392,6 +393,79 @@ struct NcclFabric : sg::Fabric {
     }
 };
 
+// ---------------------------------------------------------------- super-k-mer wire format (GENOME_B200_WIRE=superkmer)
+template <class Op>
+__global__ void __launch_bounds__(128) sk_items_kernel(unsigned long long n, Op op)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) op(i);
+}
+
+// owner of a key under the map's ownership rule (both rules are orientation-blind: x and rc(x) share the owner)
+static inline int32_t pmap_owner_of(const Map *m, unsigned long long key, int P)
+{
+    if (m->owner_mode == 1) return (int32_t)sg::owner_of_kmer(key, m->k, sg::minimizer_len(m->k), P);
+    return (int32_t)owner_of(mix64(key), (unsigned int)P);
+}
+
+// Sharded FreqFilter.add with super-k-mers on the wire (csrc/superkmer.cuh): every read is cut into runs
+// of k-windows with one minimizer owner, each run is one 16-byte record; the records are grouped by owner in a local buffer
+// (count pass + emit pass, one thread per read), exchanged with grouped ncclSend / ncclRecv (~1.5 B per k-window instead of
+// 8), and every rank inserts what it received through the single-GPU path (map_insert_records: the L2-blocked insert with
+// the records as its reads).  One batch per call, no overlap of exchange and insert yet.  Collective.
+// Written after this round's GPU budget was spent: opt-in, tests/test_parity_multigpu.py (GENOME_B200_UNVALIDATED=1).
+static int pmap_insert_superkmers(Map *m, const uint8_t *d_bin, const unsigned long long *d_off, unsigned int rec, int64_t n_reads,
+                                  int64_t *n_windows)
+{
+    Comm *c = m->comm;
+    const int P = c->n_ranks, k = m->k, mlen = sg::minimizer_len(k);
+    if (sg::sk_max_windows(k) < 1) { set_error("super-k-mer records hold 52 bases: k = %d does not fit", k); return GB_E_K_RANGE; }
+    cudaStream_t st = c->stream;
+    GB_CUDA(cudaStreamSynchronize(m->stream)); // d_bin may have been produced on the map's stream
+    DeviceBuf d_cnt, d_cursor, d_out;
+    GB_TRY(d_cnt.alloc((2 * MAX_RANKS + 2) * 8));
+    GB_TRY(d_cursor.alloc(MAX_RANKS * 8));
+    GB_TRY(d_out.alloc(MAX_RANKS * 8));
+    unsigned long long *cnt = (unsigned long long *)d_cnt.p, *win = cnt + 2 * MAX_RANKS;
+    GB_CUDA(cudaMemsetAsync(cnt, 0, (2 * MAX_RANKS + 2) * 8, st));
+    GB_CUDA(cudaMemsetAsync(d_cursor.p, 0, MAX_RANKS * 8, st));
+    const unsigned int grid = (unsigned int)((n_reads + 127) / 128);
+    if (n_reads > 0) {
+        sk_items_kernel<<<grid, 128, 0, st>>>((unsigned long long)n_reads, sg::SkCountOp{ d_bin, d_off, rec, k, mlen, P, cnt, win });
+        GB_LAUNCHED();
+    }
+    // counts to their owners; offsets on both sides
+    std::vector<unsigned long long> scnt(P), rcnt(P), soff(P), roff(P);
+    GB_TRY(exchange_counts(c, cnt, cnt + MAX_RANKS, scnt.data(), rcnt.data()));
+    unsigned long long my_windows = 0;
+    GB_CUDA(cudaMemcpy(&my_windows, win, 8, cudaMemcpyDeviceToHost));
+    unsigned long long ns = 0, nr = 0;
+    for (int p = 0; p < P; p++) { soff[p] = 2 * ns; ns += scnt[p]; roff[p] = 2 * nr; nr += rcnt[p]; }
+    DeviceBuf d_send, d_recv;
+    GB_TRY(d_send.alloc((size_t)ns * 16 + 16));
+    GB_TRY(d_recv.alloc((size_t)nr * 16 + 32));
+    std::vector<unsigned long long *> out(P);
+    for (int p = 0; p < P; p++) out[p] = (unsigned long long *)d_send.p + soff[p];
+    GB_CUDA(cudaMemcpyAsync(d_out.p, out.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
+    if (n_reads > 0) {
+        sk_items_kernel<<<grid, 128, 0, st>>>((unsigned long long)n_reads, sg::SkEmitOp{ d_bin, d_off, rec, k, mlen, P, (unsigned long long *)d_cursor.p,
+                                                                                          (unsigned long long *const *)d_out.p });
+        GB_LAUNCHED();
+    }
+    // 2 u64 per record
+    std::vector<unsigned long long> scnt2(P), rcnt2(P);
+    for (int p = 0; p < P; p++) { scnt2[p] = 2 * scnt[p]; rcnt2[p] = 2 * rcnt[p]; }
+    GB_TRY(all_to_all_v(c, (const unsigned long long *)d_send.p, soff.data(), scnt2.data(), (unsigned long long *)d_recv.p, roff.data(), rcnt2.data(),
+                        ncclUint64));
+    GB_CUDA(cudaStreamSynchronize(st)); // `out` (host) and the send buffer are free again; the records are here
+    int64_t w_local = 0;
+    GB_TRY(map_insert_records(m, (const uint8_t *)d_recv.p, (size_t)nr * 16, 16, (int64_t)nr, (unsigned int)sg::SK_MAX_BASES, &w_local));
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    m->fixed_stride = d_off ? 0 : 1;
+    if (n_windows) *n_windows = (int64_t)my_windows; // updates issued for THIS rank's reads, like the k-mer wire path
+    return GB_OK;
+}
+
 // wait for every in-flight insert, fold the new-key counter into m->size
 static int drain(Map *m, BatchBufs *bufs)
 {
@@ -413,6 +487,7 @@ static int drain(Map *m, BatchBufs *bufs)
 static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off, unsigned int rec,
                        unsigned int len0, int64_t n_reads, const int64_t *h_win_prefix, int64_t *n_windows)
 {
+    if (m->owner_mode == 1) return pmap_insert_superkmers(m, d_bin, d_off, rec, n_reads, n_windows);
     Comm *c = m->comm;
     const int P = c->n_ranks;
     const int k = m->k;
@@ -711,6 +786,9 @@ int gb_pmap_create(gb_comm *ch, int k, int64_t min_capacity_per_shard, uint32_t 
     Comm *c = reinterpret_cast<Comm *>(ch);
     GB_TRY(gb_map_create(k, min_capacity_per_shard, c->device, flags, out));
     reinterpret_cast<Map *>(*out)->comm = c;
+    // every rank reads the same environment: the ownership rule is a property of the whole sharded map
+    const char *wire = getenv("GENOME_B200_WIRE");
+    if (wire && !strcmp(wire, "superkmer")) reinterpret_cast<Map *>(*out)->owner_mode = 1;
     return GB_OK;
 }
 
@@ -797,6 +875,11 @@ int gb_pmap_owner(gb_map *h, const uint64_t *keys, int64_t n, int32_t *owner)
     Map *m;
     GB_TRY(check_pmap(h, &m));
     if (n < 0 || (n > 0 && (!keys || !owner))) { set_error("bad arguments"); return GB_E_ARG; }
+    if (m->owner_mode == 1) {
+        if (n < 0 || (n > 0 && (!keys || !owner))) { set_error("bad arguments"); return GB_E_ARG; }
+        for (int64_t i = 0; i < n; i++) owner[i] = pmap_owner_of(m, keys[i], m->comm->n_ranks);
+        return GB_OK;
+    }
     return gb_owner_of(keys, n, m->comm->n_ranks, owner);
 }
 
@@ -820,7 +903,7 @@ int gb_pmap_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, 
     std::vector<unsigned long long> h_send((size_t)n), scnt(P, 0), soff(P, 0), rcnt(P, 0), roff(P, 0), fill(P, 0);
     std::vector<int64_t> origin((size_t)n);
     std::vector<int32_t> own((size_t)n);
-    for (int64_t i = 0; i < n; i++) { own[(size_t)i] = (int32_t)owner_of(mix64(keys[i]), (unsigned int)P); scnt[own[(size_t)i]]++; }
+    for (int64_t i = 0; i < n; i++) { own[(size_t)i] = pmap_owner_of(m, keys[i], P); scnt[own[(size_t)i]]++; }
     unsigned long long st = 0;
     for (int p = 0; p < P; p++) { soff[p] = st; st += scnt[p]; }
     for (int64_t i = 0; i < n; i++) {

@@ -367,6 +367,7 @@ struct Map {
     unsigned long long *d_counters = nullptr; // [0] new keys [1] survivors / exported [2] stream flags [3] k-windows
     unsigned long long *d_spread = nullptr;   // spread new-key tallies of insert_keys_kernel (partition.cu)
     Comm *comm = nullptr;
+    int owner_mode = 0; // sharded maps: 0 = owner by hash prefix, 1 = owner by minimizer (super-k-mer wire format, comm.cu)
     // after deleteAll (or in a replica): the stored keys as one device array whose index IS the vertex id written in
     // the slots, so Graph.buildGraph needs no numbering pass.  Any mutation invalidates it.
     const unsigned long long *kept_keys = nullptr;

@@ -168,6 +168,9 @@ int map_read_counters(Map *m, unsigned long long out[4]);
 int map_zero_counters(Map *m);
 int map_rebuild(Map *m, unsigned long long new_cap, bool filter, int min_count);
 int map_export_device(Map *m, unsigned long long *d_keys, int *d_vals);
+// FreqFilter.add over records at a fixed stride with their own length bytes (<= max_len), already verified; map.cu
+int map_insert_records(Map *m, const uint8_t *d_bin, size_t n_bytes, unsigned int rec_bytes, int64_t n_records, unsigned int max_len,
+                       int64_t *n_windows);
 int map_verify_fixed(Map *m, const uint8_t *d_bin, unsigned int rec, unsigned int len0, int64_t n_reads, unsigned long long *bad);
 int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n, cudaStream_t st);
 int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d_vals, int64_t n, cudaStream_t st, bool set_vid);

@@ -1040,6 +1040,19 @@ int gb_map_insert_records_device(gb_map *h, const uint8_t *d_bin, size_t n_bytes
     m->fixed_stride = 1;
     return insert_device(m, d_bin, n_bytes, nullptr, true, rec_bytes, max_len, n_records, nullptr, n_windows, true);
 }
+} // extern "C"
+
+namespace gb {
+int map_insert_records(Map *m, const uint8_t *d_bin, size_t n_bytes, unsigned int rec_bytes, int64_t n_records, unsigned int max_len,
+                       int64_t *n_windows)
+{
+    if (n_windows) *n_windows = 0;
+    if (n_records <= 0) return GB_OK;
+    return insert_device(m, d_bin, n_bytes, nullptr, true, rec_bytes, max_len, n_records, nullptr, n_windows, true);
+}
+} // namespace gb
+
+extern "C" {
 
 static int update_common(gb_map *h, const uint64_t *keys, const int32_t *vals, int64_t n, bool set)
 {

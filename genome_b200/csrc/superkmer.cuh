@@ -74,21 +74,23 @@ SG_HD int sk_split_read(const u8 *rec, int k, int m, int P, Emit emit)
 }
 
 // one read per item: counts the records per owner (first pass) ...
+// (record r starts at bin + offsets[r], or at bin + r * rec_bytes when offsets == nullptr)
 struct SkCountOp {
-    const u8 *bin; u32 rec_bytes; int k, m, P; u64 *per_owner; u64 *windows;
+    const u8 *bin; const u64 *offsets; u32 rec_bytes; int k, m, P; u64 *per_owner; u64 *windows;
     SG_HD void operator()(u64 r) const
     {
         u64 *po = per_owner;
-        const int nw = sk_split_read(bin + r * rec_bytes, k, m, P, [po](u32 owner, int, int) { at_add64(po + owner, 1); });
+        const u8 *rec = bin + (offsets ? offsets[r] : r * rec_bytes);
+        const int nw = sk_split_read(rec, k, m, P, [po](u32 owner, int, int) { at_add64(po + owner, 1); });
         if (nw) at_add64(windows, (u64)nw);
     }
 };
 // ... and writes them: record number c of owner o goes to out[o] + 2 * c (cursor[o] starts at 0; out[o] holds per_owner[o] records)
 struct SkEmitOp {
-    const u8 *bin; u32 rec_bytes; int k, m, P; u64 *cursor; u64 *const *out;
+    const u8 *bin; const u64 *offsets; u32 rec_bytes; int k, m, P; u64 *cursor; u64 *const *out;
     SG_HD void operator()(u64 r) const
     {
-        const u8 *rec = bin + r * rec_bytes;
+        const u8 *rec = bin + (offsets ? offsets[r] : r * rec_bytes);
         u64 *cur = cursor;
         u64 *const *o = out;
         sk_split_read(rec, k, m, P, [rec, cur, o](u32 owner, int s, int nb) {

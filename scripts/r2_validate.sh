@@ -9,11 +9,11 @@ export GENOME_B200_UNVALIDATED=1
   echo "== opt-in device tests"
   timeout 1200 python -m pytest tests/test_sgraph_gpu.py tests/test_graphmap_gpu.py tests/test_scripts_gpu.py tests/test_countless_gpu.py -q -m gpu 2>&1 | tail -25
   echo "== sharded graph build through the NCCL fabric, one rank (works on a one-GPU box)"
-  timeout 600 python -m pytest tests/test_parity_multigpu.py -q -m gpu -k "sharded_graph_build and 1" 2>&1 | tail -8
+  timeout 600 python -m pytest tests/test_parity_multigpu.py -q -m gpu -k "(sharded_graph_build or superkmer_wire) and 1" 2>&1 | tail -10
   NGPU=$(python -c "import torch; print(torch.cuda.device_count())")
   if [ "$NGPU" -ge 2 ]; then
     echo "== sharded graph build over $NGPU ranks"
-    timeout 900 python -m pytest tests/test_parity_multigpu.py -q -m gpu -k "sharded_graph_build or pmap_matches_oracle" 2>&1 | tail -20
+    timeout 900 python -m pytest tests/test_parity_multigpu.py -q -m gpu -k "sharded_graph_build or pmap_matches_oracle or superkmer_wire" 2>&1 | tail -24
   fi
   echo "== bench: default vs single-pass bucket pass (GENOME_B200_COUNTLESS=1)"
   timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err

@@ -298,13 +298,13 @@ uint64_t emul_superkmers(const uint8_t *bin, uint32_t rec_bytes, uint64_t n_read
     const int m = minimizer_len(k);
     uint64_t windows = 0;
     for (int o = 0; o < P; o++) per_owner[o] = 0;
-    sg_launch(ex, n_reads, SkCountOp{ bin, rec_bytes, k, m, P, (u64 *)per_owner, (u64 *)&windows });
+    sg_launch(ex, n_reads, SkCountOp{ bin, nullptr, rec_bytes, k, m, P, (u64 *)per_owner, (u64 *)&windows });
     if (records) {
         std::vector<u64> cursor((size_t)P, 0);
         std::vector<u64 *> out((size_t)P);
         uint64_t at = 0;
         for (int o = 0; o < P; o++) { out[(size_t)o] = (u64 *)records + 2 * at; at += per_owner[o]; }
-        sg_launch(ex, n_reads, SkEmitOp{ bin, rec_bytes, k, m, P, cursor.data(), out.data() });
+        sg_launch(ex, n_reads, SkEmitOp{ bin, nullptr, rec_bytes, k, m, P, cursor.data(), out.data() });
         for (int o = 0; o < P; o++)
             if (cursor[(size_t)o] != per_owner[o]) return ~0ull;
     }

@@ -34,7 +34,7 @@ def main():
         assert m.size == om.size()
         # this shard holds exactly the oracle's keys that it owns
         ok, ov = om.export_sorted()
-        sel = owner_of(ok, world) == rank
+        sel = m.owner(ok) == rank   # the map's own ownership rule (hash prefix, or minimizer with GENOME_B200_WIRE=superkmer)
         gk, gv = m.export_sorted()
         assert np.array_equal(gk, ok[sel]) and np.array_equal(gv, ov[sel])
         assert m.local_size == int(sel.sum())
@@ -85,7 +85,7 @@ def main():
     om, ow = H.oracle_counts(b, n, k)
     assert m.size == om.size()
     ok, ov = om.export_sorted()
-    sel = owner_of(ok, world) == rank
+    sel = m.owner(ok) == rank   # the map's own ownership rule (hash prefix, or minimizer with GENOME_B200_WIRE=superkmer)
     gk, gv = m.export_sorted()
     assert np.array_equal(gk, ok[sel]) and np.array_equal(gv, ov[sel])
     m.close()

@@ -45,3 +45,16 @@ def test_pmap_sharded_graph_build(gpu, world):
     if gpu < world:
         pytest.skip("needs %d GPUs, box has %d" % (world, gpu))
     run_world(world, {"GENOME_B200_PGRAPH": "sharded"})
+
+
+@pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_pmap_superkmer_wire(gpu, world):
+    """The sharded insert with super-k-mers on the wire (GENOME_B200_WIRE=superkmer: minimizer owners, 16-byte records,
+    csrc/superkmer.cuh + comm.cu pmap_insert_superkmers): same worker, same oracle comparisons (shard contents are checked
+    through the map's own owner function); together with the sharded graph build, whose re-routing then finds every key at
+    home.  Opt-in until it has passed on a B200 box."""
+    if gpu < world:
+        pytest.skip("needs %d GPUs, box has %d" % (world, gpu))
+    run_world(world, {"GENOME_B200_WIRE": "superkmer"})
+    run_world(world, {"GENOME_B200_WIRE": "superkmer", "GENOME_B200_PGRAPH": "sharded"})
