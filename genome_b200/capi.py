@@ -90,6 +90,7 @@ SIGNATURES = {
     "gb_pmap_graph_build": (C.c_int, [_vp, _pp]),
     "gb_pmap_owner": (C.c_int, [_vp, _vp, _i64, _vp]),
     "gb_owner_of": (C.c_int, [_vp, _i64, C.c_int, _vp]),
+    "gb_owner_of_minimizer": (C.c_int, [_vp, _i64, C.c_int, C.c_int, _vp]),
 }
 
 _LIB = None

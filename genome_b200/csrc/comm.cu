@@ -891,6 +891,16 @@ int gb_owner_of(const uint64_t *keys, int64_t n, int n_parts, int32_t *owner)
     return GB_OK;
 }
 
+// the ownership rule of a GENOME_B200_WIRE=superkmer map (and of the sharded graph build): minimizer owner; host arithmetic
+int gb_owner_of_minimizer(const uint64_t *keys, int64_t n, int k, int n_parts, int32_t *owner)
+{
+    if (n < 0 || n_parts < 1 || (n > 0 && (!keys || !owner))) { set_error("bad arguments"); return GB_E_ARG; }
+    if (k < 1 || k > 31) { set_error("k = %d outside 1..31", k); return GB_E_K_RANGE; }
+    const int m = sg::minimizer_len(k);
+    for (int64_t i = 0; i < n; i++) owner[i] = (int32_t)sg::owner_of_kmer(keys[i], k, m, n_parts);
+    return GB_OK;
+}
+
 int gb_pmap_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, uint8_t *found)
 {
     Map *m;

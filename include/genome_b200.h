@@ -221,6 +221,10 @@ int gb_pmap_graph_build(gb_map *m, gb_graph **out);
 int gb_pmap_owner(gb_map *m, const uint64_t *keys, int64_t n, int32_t *owner);
 /* the same partition(key) (PartitionedDNAMap.scala:60-63) for n_parts shards: host arithmetic, needs no GPU */
 int gb_owner_of(const uint64_t *keys, int64_t n, int n_parts, int32_t *owner);
+/* the other ownership rule, used by maps created under GENOME_B200_WIRE=superkmer and by the sharded graph build: the hash of the
+ * k-mer's minimizer (smallest hashed canonical m-mer), shared by a k-mer, its reverse complement and ~90 % of its (k-1)-overlap
+ * neighbours; host arithmetic, needs no GPU */
+int gb_owner_of_minimizer(const uint64_t *keys, int64_t n, int k, int n_parts, int32_t *owner);
 
 #ifdef __cplusplus
 }

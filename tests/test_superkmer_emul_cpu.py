@@ -91,3 +91,23 @@ def test_short_and_boundary_reads(emul):
     lens = sorted(recs[:, 0].astype(int).tolist())
     # one owner: runs break only at 32 windows (52 bases): 21 -> [21]; 22 -> [22]; 72 -> [52, 40]; 73 -> [52, 41]; 74 -> [52, 42]; 100 -> [52, 52, 36]
     assert lens == sorted([21, 22, 52, 40, 52, 41, 52, 42, 52, 52, 36])
+
+
+def test_library_minimizer_owner_matches_the_emulation(emul):
+    """gb_owner_of_minimizer (host arithmetic inside libgenome_b200.so, what gb_pmap_lookup routes by under
+    GENOME_B200_WIRE=superkmer) against the g++ build of the same header; and the reverse complement shares the owner."""
+    from genome_b200 import capi
+    rng = np.random.default_rng(11)
+    full, incr = np.zeros(9, np.uint32), np.zeros(8, np.uint32)
+    for k in (8, 21, 31):
+        keys = rng.integers(0, 1 << (2 * k), 400, dtype=np.uint64)
+        rc = np.array([pyoracle.revcomp(int(x), k) for x in keys], np.uint64)
+        for P in (1, 3, 8):
+            own = np.zeros(keys.size, np.int32)
+            own_rc = np.zeros(keys.size, np.int32)
+            capi.check(capi.lib().gb_owner_of_minimizer(ptr(keys), keys.size, k, P, ptr(own)))
+            capi.check(capi.lib().gb_owner_of_minimizer(ptr(rc), rc.size, k, P, ptr(own_rc)))
+            assert np.array_equal(own, own_rc) and own.min() >= 0 and own.max() < P
+            for x, o in zip(keys[:80].tolist(), own[:80].tolist()):
+                emul.emul_owners(k, P, C.c_uint64(x), ptr(full), ptr(incr))
+                assert int(full[0]) == o
