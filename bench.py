@@ -414,7 +414,9 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, desc), "k": K, "rounds": ROUNDS, "reads_per_gpu": n_reads,
                        "kmer_instances_per_gpu": windows, "genome_bp": G, "scale": args.scale,
-                       "sharding": "hash-prefix shard per GPU, NCCL all-to-all" if world > 1 else "one table",
+                       "sharding": ("one table" if world == 1 else
+                                    "minimizer-owner shard per GPU, 16-byte super-k-mer records over NCCL (GENOME_B200_WIRE=superkmer)"
+                                    if os.environ.get("GENOME_B200_WIRE") == "superkmer" else "hash-prefix shard per GPU, NCCL all-to-all"),
                        "l2": "table (%.2f GB) is re-initialised and randomly written every step: far larger than the 126 MB L2" % (table_bytes / 1e9)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "graph": graph,
         }
