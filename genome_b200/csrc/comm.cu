@@ -422,6 +422,11 @@ static int pmap_insert_superkmers(Map *m, const uint8_t *d_bin, const unsigned l
     if (sg::sk_max_windows(k) < 1) { set_error("super-k-mer records hold 52 bases: k = %d does not fit", k); return GB_E_K_RANGE; }
     cudaStream_t st = c->stream;
     GB_CUDA(cudaStreamSynchronize(m->stream)); // d_bin may have been produced on the map's stream
+    cudaEvent_t e0 = nullptr, e1 = nullptr; // the whole call on the device clock: split + exchange + insert
+    GB_CUDA(cudaEventCreate(&e0));
+    GB_CUDA(cudaEventCreate(&e1));
+    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev_guard{ e0, e1 };
+    GB_CUDA(cudaEventRecord(e0, st));
     DeviceBuf d_cnt, d_cursor, d_out;
     GB_TRY(d_cnt.alloc((2 * MAX_RANKS + 2) * 8));
     GB_TRY(d_cursor.alloc(MAX_RANKS * 8));
@@ -461,6 +466,12 @@ static int pmap_insert_superkmers(Map *m, const uint8_t *d_bin, const unsigned l
     int64_t w_local = 0;
     GB_TRY(map_insert_records(m, (const uint8_t *)d_recv.p, (size_t)nr * 16, 16, (int64_t)nr, (unsigned int)sg::SK_MAX_BASES, &w_local));
     GB_CUDA(cudaStreamSynchronize(m->stream));
+    GB_CUDA(cudaEventRecord(e1, st));
+    GB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    GB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    m->phase_ns[0] = (int64_t)(ms * 1e6) - m->last_insert_ns; // split + exchange (everything but the local insert)
+    m->last_insert_ns = (int64_t)(ms * 1e6);
     m->fixed_stride = d_off ? 0 : 1;
     if (n_windows) *n_windows = (int64_t)my_windows; // updates issued for THIS rank's reads, like the k-mer wire path
     return GB_OK;
