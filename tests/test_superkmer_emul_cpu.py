@@ -111,3 +111,18 @@ def test_library_minimizer_owner_matches_the_emulation(emul):
             for x, o in zip(keys[:80].tolist(), own[:80].tolist()):
                 emul.emul_owners(k, P, C.c_uint64(x), ptr(full), ptr(incr))
                 assert int(full[0]) == o
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_superkmer_routing_gloo(emul, world):
+    """world_size 2 and 3 over gloo (tests/gloo_superkmer_worker.py): split -> route records to minimizer owners -> insert what
+    arrived; the shards are exactly the owner's keys with the single-map counts."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    port = str(29760 + world)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", port, os.path.join(here, "gloo_superkmer_worker.py")], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-5000:]
+    assert "SUPERKMER ROUTING OK world %d" % world in r.stdout
