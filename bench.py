@@ -390,7 +390,16 @@ def main():
         # term needs the distinct count before the filter, which the timed loop does not keep
         ins_s = max_over_ranks(float(np.mean(insert_ns)) * 1e-9)
         algo_bytes = 16.0 * windows + float(b.size)
-        if rank == 0:
+        superkmer = os.environ.get("GENOME_B200_WIRE") == "superkmer"
+        if rank == 0 and superkmer:
+            # 16-byte records of ~10 windows each: the exact wire volume is not kept by the timed loop; 1.6 B per window is the
+            # CPU-measured figure for k = 31, P = 8 (tests/test_superkmer_emul_cpu.py), stated as an estimate
+            roofline = {"bound": "hbm", "kernel": "sharded insert, super-k-mer wire: split (count + emit) + NCCL exchange + local partitioned insert",
+                        "achieved": algo_bytes / ins_s / 1e9, "peak": peak, "unit": "GB/s", "frac": algo_bytes / ins_s / 1e9 / peak,
+                        "traffic": None, "peak_source": peak_src, "insert_ms": ins_s * 1e3,
+                        "insert_kmers_per_s_per_gpu": windows / ins_s,
+                        "nvlink_bytes_out_per_gpu_estimate": 1.6 * windows * (world - 1) / world}
+        elif rank == 0:
             roofline = {"bound": "hbm", "kernel": "sharded insert: part_count + part_scatter<PEER> (NVLink stores) + insert_keys_kernel",
                         "achieved": algo_bytes / ins_s / 1e9, "peak": peak, "unit": "GB/s", "frac": algo_bytes / ins_s / 1e9 / peak,
                         "traffic": None, "peak_source": peak_src, "insert_ms": ins_s * 1e3,
