@@ -319,3 +319,17 @@ def test_one_process_per_rank_gloo(emul, world):
                         "--master-port", port, script], capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-5000:]
     assert "SGRAPH GLOO OK world %d" % world in r.stdout
+
+
+def test_golden_fixture(emul):
+    """The committed fixture tests/golden/small_k15.json (keys after the filter -> nodes and edges): the sharded build must
+    reproduce the committed graph, for every rank count."""
+    import json
+    fx = json.load(open(os.path.join(HERE, "golden", "small_k15.json")))
+    k, rounds = fx["k"], fx["rounds"]
+    keys = np.array([x for x, c in zip(fx["keys"], fx["counts"]) if c >= rounds], np.uint64)
+    want = (sorted(fx["nodes"]), sorted((u, v, bytes.fromhex(s)) for u, v, s in fx["edges"]))
+    for P in (1, 2, 8):
+        for threads in (False, True):
+            got, counts, _ = sharded_build(emul, k, keys, P, threads=threads)
+            assert got == want
