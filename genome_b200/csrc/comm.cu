@@ -394,11 +394,45 @@ struct NcclFabric : sg::Fabric {
 };
 
 // ---------------------------------------------------------------- super-k-mer wire format (GENOME_B200_WIRE=superkmer)
-template <class Op>
-__global__ void __launch_bounds__(128) sk_items_kernel(unsigned long long n, Op op)
+// One thread per read around the CPU-checked functors of superkmer.cuh.  Their per-record atomics go to SHARED memory here
+// (millions of records on P counters would serialise in L2): a CTA counts into shared counters and adds them to the global
+// ones once; the emit kernel counts first, reserves one block per owner for the whole CTA, then emits through shared cursors.
+constexpr int SK_THREADS = 128;
+static_assert(SK_THREADS >= MAX_RANKS, "one thread per owner in the CTA epilogues");
+__global__ void __launch_bounds__(SK_THREADS) sk_count_kernel(unsigned long long n, sg::SkCountOp op)
 {
-    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) op(i);
+    __shared__ unsigned long long s_cnt[MAX_RANKS + 1]; // [owner] records, [MAX_RANKS] k-windows
+    for (int i = threadIdx.x; i <= MAX_RANKS; i += SK_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const unsigned long long r = (unsigned long long)blockIdx.x * SK_THREADS + threadIdx.x;
+    sg::SkCountOp local = op;
+    local.per_owner = s_cnt;
+    local.windows = s_cnt + MAX_RANKS;
+    if (r < n) local(r);
+    __syncthreads();
+    if ((int)threadIdx.x < op.P && s_cnt[threadIdx.x]) atomicAdd(op.per_owner + threadIdx.x, s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0 && s_cnt[MAX_RANKS]) atomicAdd(op.windows, s_cnt[MAX_RANKS]);
+}
+__global__ void __launch_bounds__(SK_THREADS) sk_emit_kernel(unsigned long long n, sg::SkEmitOp op)
+{
+    __shared__ unsigned long long s_cnt[MAX_RANKS + 1], s_cur[MAX_RANKS];
+    __shared__ unsigned long long *s_out[MAX_RANKS];
+    for (int i = threadIdx.x; i <= MAX_RANKS; i += SK_THREADS) s_cnt[i] = 0;
+    __syncthreads();
+    const unsigned long long r = (unsigned long long)blockIdx.x * SK_THREADS + threadIdx.x;
+    if (r < n) sg::SkCountOp{ op.bin, op.offsets, op.rec_bytes, op.k, op.m, op.P, s_cnt, s_cnt + MAX_RANKS }(r);
+    __syncthreads();
+    if ((int)threadIdx.x < op.P) {
+        const unsigned long long mine = s_cnt[threadIdx.x];
+        const unsigned long long base = mine ? atomicAdd(op.cursor + threadIdx.x, mine) : 0; // this CTA's block of owner's records
+        s_out[threadIdx.x] = op.out[threadIdx.x] + 2 * base;
+        s_cur[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    sg::SkEmitOp local = op;
+    local.cursor = s_cur;
+    local.out = s_out;
+    if (r < n) local(r);
 }
 
 // owner of a key under the map's ownership rule (both rules are orientation-blind: x and rc(x) share the owner)
@@ -434,9 +468,9 @@ static int pmap_insert_superkmers(Map *m, const uint8_t *d_bin, const unsigned l
     unsigned long long *cnt = (unsigned long long *)d_cnt.p, *win = cnt + 2 * MAX_RANKS;
     GB_CUDA(cudaMemsetAsync(cnt, 0, (2 * MAX_RANKS + 2) * 8, st));
     GB_CUDA(cudaMemsetAsync(d_cursor.p, 0, MAX_RANKS * 8, st));
-    const unsigned int grid = (unsigned int)((n_reads + 127) / 128);
+    const unsigned int grid = (unsigned int)((n_reads + SK_THREADS - 1) / SK_THREADS);
     if (n_reads > 0) {
-        sk_items_kernel<<<grid, 128, 0, st>>>((unsigned long long)n_reads, sg::SkCountOp{ d_bin, d_off, rec, k, mlen, P, cnt, win });
+        sk_count_kernel<<<grid, SK_THREADS, 0, st>>>((unsigned long long)n_reads, sg::SkCountOp{ d_bin, d_off, rec, k, mlen, P, cnt, win });
         GB_LAUNCHED();
     }
     // counts to their owners; offsets on both sides
@@ -453,8 +487,8 @@ static int pmap_insert_superkmers(Map *m, const uint8_t *d_bin, const unsigned l
     for (int p = 0; p < P; p++) out[p] = (unsigned long long *)d_send.p + soff[p];
     GB_CUDA(cudaMemcpyAsync(d_out.p, out.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
     if (n_reads > 0) {
-        sk_items_kernel<<<grid, 128, 0, st>>>((unsigned long long)n_reads, sg::SkEmitOp{ d_bin, d_off, rec, k, mlen, P, (unsigned long long *)d_cursor.p,
-                                                                                          (unsigned long long *const *)d_out.p });
+        sk_emit_kernel<<<grid, SK_THREADS, 0, st>>>((unsigned long long)n_reads, sg::SkEmitOp{ d_bin, d_off, rec, k, mlen, P, (unsigned long long *)d_cursor.p,
+                                                                                               (unsigned long long *const *)d_out.p });
         GB_LAUNCHED();
     }
     // 2 u64 per record
