@@ -139,3 +139,18 @@ def test_cpp_graph_simplifier_driver_compiles_and_fails_loudly_without_gpu(tmp_p
     p.write_bytes(b.tobytes())
     r = subprocess.run([exe, str(p), "10", "21", "5"], capture_output=True, text=True)
     assert r.returncode == 1 and "CUDA" in r.stderr
+
+
+def test_every_entry_point_has_a_binding_line_and_a_ctypes_signature():
+    """include/genome_b200.h is the boundary: every function it declares must appear in the Scala/JNA trait of INTEGRATION.md
+    (the binding a maintainer of the reference adds) and in the ctypes table the tests and bench.py call through."""
+    import re
+    from genome_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "genome_b200.h")).read()
+    names = re.findall(r"^[a-z_0-9 \*]*\b(gb_[a-z_0-9]+)\(", hdr, flags=re.M)
+    assert len(names) >= 55 and len(set(names)) == len(names)
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing_doc = [n for n in names if "def %s(" % n not in doc]
+    assert not missing_doc, missing_doc
+    missing_sig = [n for n in names if n not in capi.SIGNATURES and n not in ("gb_last_error", "gb_launch_count", "gb_version")]
+    assert not missing_sig, missing_sig
