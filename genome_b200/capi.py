@@ -63,6 +63,7 @@ SIGNATURES = {
     "gb_graph_components": (C.c_int, [_vp, _vp, _pi64]),
     "gb_graph_retain_largest": (C.c_int, [_vp]),
     "gb_graph_retain": (C.c_int, [_vp, _vp]),
+    "gb_graph_edit": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "gb_graph_simplify": (C.c_int, [_vp]),
     "gb_graph_remove_bubbles": (C.c_int, [_vp]),
     "gb_graph_remove_edges": (C.c_int, [_vp, _vp, _i64]),

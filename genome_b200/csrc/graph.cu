@@ -1298,6 +1298,143 @@ int gb_graph_remove_edges(gb_graph *h, const uint32_t *edge_idx, int64_t n)
     return apply_rewrite(g, rb.rw);
 }
 
+// ---- the fine-grained mutators of trait Graph (Graph.scala:31-36) in bulk
+__global__ void edit_replace_kernel(const unsigned int *idx, const unsigned int *ns, const unsigned int *ne, long long n, unsigned int *edge_start,
+                                    unsigned int *edge_end)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (ns[i] != NONE32) edge_start[idx[i]] = ns[i]; // replaceStart (197-202)
+    if (ne[i] != NONE32) edge_end[idx[i]] = ne[i];   // replaceEnd (204-209)
+}
+__global__ void edit_append_offsets_kernel(const unsigned long long *add_off, long long n_add, unsigned long long base, unsigned long long *edge_off)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n_add) edge_off[i] = base + add_off[i]; // edge_off points at the old end: entry 0 rewrites the old total with itself
+}
+__global__ void edit_append_bases_kernel(const uint8_t *codes, unsigned long long n, unsigned long long at, unsigned int *bases)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) put_base(bases, at + i, codes[i] & 3u);
+}
+__global__ void edit_drop_nodes_kernel(const unsigned int *idx, long long n, unsigned long long *node_keep)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) node_keep[idx[i]] = 0;
+}
+__global__ void edit_check_ends_kernel(const unsigned int *edge_start, const unsigned int *edge_end, unsigned long long n_edges,
+                                       const unsigned long long *node_keep, unsigned int *bad)
+{
+    unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n_edges && (!node_keep[edge_start[e]] || !node_keep[edge_end[e]])) *bad = 1;
+}
+
+// replaceStart / replaceEnd, addNode / addEdge, removeNode (Graph.scala:172-209) in bulk, applied in that order.
+// New nodes get the indices n_nodes, n_nodes + 1, ...; new edges n_edges, ... (they may start or end at new nodes, and
+// replacements may name new nodes too).  removeNode only drops a node, like the reference's (185-187): removing one that an
+// edge still starts or ends at is refused with GB_E_INVARIANT (the array form cannot hold a dangling end); node and edge
+// indices are compacted by the removal like by every other operator.
+int gb_graph_edit(gb_graph *h, int64_t n_replace, const uint32_t *edge_idx, const uint32_t *new_start, const uint32_t *new_end,
+                  int64_t n_add_nodes, const uint64_t *add_node_kmers, int64_t n_add_edges, const uint32_t *add_start,
+                  const uint32_t *add_end, const uint64_t *add_off, const uint8_t *add_bases, int64_t n_remove_nodes,
+                  const uint32_t *remove_nodes)
+{
+    Graph *g;
+    GB_TRY(check_graph(h, &g));
+    ArenaScope scope(&g->arena);
+    cudaStream_t st = g->stream;
+    if (n_replace < 0 || n_add_nodes < 0 || n_add_edges < 0 || n_remove_nodes < 0 || (n_replace && (!edge_idx || !new_start || !new_end)) ||
+        (n_add_nodes && !add_node_kmers) || (n_add_edges && (!add_start || !add_end || !add_off || !add_bases)) ||
+        (n_remove_nodes && !remove_nodes)) { set_error("bad arguments"); return GB_E_ARG; }
+    const int64_t N0 = g->n_nodes, E0 = g->n_edges, N1 = N0 + n_add_nodes, E1 = E0 + n_add_edges;
+    const unsigned long long kmask = (1ull << (2 * g->k)) - 1;
+    for (int64_t i = 0; i < n_add_nodes; i++)
+        if (add_node_kmers[i] & ~kmask) { set_error("new node %lld: k-mer longer than k = %d", (long long)i, g->k); return GB_E_K_RANGE; }
+    for (int64_t i = 0; i < n_replace; i++)
+        if ((int64_t)edge_idx[i] >= E0 || (new_start[i] != NONE32 && (int64_t)new_start[i] >= N1) || (new_end[i] != NONE32 && (int64_t)new_end[i] >= N1)) {
+            set_error("replacement %lld out of range", (long long)i);
+            return GB_E_ARG;
+        }
+    unsigned long long add_bases_n = 0;
+    for (int64_t i = 0; i < n_add_edges; i++) {
+        if ((int64_t)add_start[i] >= N1 || (int64_t)add_end[i] >= N1 || add_off[i + 1] <= add_off[i] || (i == 0 && add_off[0] != 0)) {
+            set_error("new edge %lld: end out of range or empty sequence", (long long)i);
+            return GB_E_ARG;
+        }
+        add_bases_n = add_off[i + 1];
+    }
+    for (int64_t i = 0; i < n_remove_nodes; i++)
+        if ((int64_t)remove_nodes[i] >= N1) { set_error("node %u out of range", remove_nodes[i]); return GB_E_ARG; }
+    if (N1 >= 0xFFFFFFFFll || E1 >= (1ll << 31)) { set_error("graph too large"); return GB_E_CAPACITY; }
+
+    // 1. replaceStart / replaceEnd in place (new node indices are valid once step 2 has run; nothing reads them before)
+    if (n_replace) {
+        Tmp<unsigned int> di, ds, de;
+        GB_TRY(di.alloc((size_t)n_replace, st)); GB_TRY(ds.alloc((size_t)n_replace, st)); GB_TRY(de.alloc((size_t)n_replace, st));
+        GB_CUDA(cudaMemcpyAsync(di.p, edge_idx, (size_t)n_replace * 4, cudaMemcpyHostToDevice, st));
+        GB_CUDA(cudaMemcpyAsync(ds.p, new_start, (size_t)n_replace * 4, cudaMemcpyHostToDevice, st));
+        GB_CUDA(cudaMemcpyAsync(de.p, new_end, (size_t)n_replace * 4, cudaMemcpyHostToDevice, st));
+        LAUNCH(edit_replace_kernel, n_replace, di.p, ds.p, de.p, (long long)n_replace, g->edge_start, g->edge_end);
+    }
+    // 2. addNode / addEdge: the arrays grow into the other store
+    if (n_add_nodes || n_add_edges) {
+        const unsigned long long nb0 = (unsigned long long)g->n_bases, nb1 = nb0 + add_bases_n;
+        struct { unsigned long long *node_kmer; unsigned int *edge_start, *edge_end; unsigned long long *edge_off; unsigned int *bases; } ng;
+        Arena &dst = g->store[g->cur ^ 1];
+        dst.reset();
+        GB_TRY(store_alloc(dst, &ng.node_kmer, (size_t)N1));
+        GB_TRY(store_alloc(dst, &ng.edge_start, (size_t)E1));
+        GB_TRY(store_alloc(dst, &ng.edge_end, (size_t)E1));
+        GB_TRY(store_alloc(dst, &ng.edge_off, (size_t)E1 + 1));
+        GB_TRY(store_alloc(dst, &ng.bases, base_words((int64_t)nb1)));
+        GB_CUDA(cudaMemsetAsync(ng.bases, 0, base_words((int64_t)nb1) * 4, st));
+        if (N0) GB_CUDA(cudaMemcpyAsync(ng.node_kmer, g->node_kmer, (size_t)N0 * 8, cudaMemcpyDeviceToDevice, st));
+        if (E0) {
+            GB_CUDA(cudaMemcpyAsync(ng.edge_start, g->edge_start, (size_t)E0 * 4, cudaMemcpyDeviceToDevice, st));
+            GB_CUDA(cudaMemcpyAsync(ng.edge_end, g->edge_end, (size_t)E0 * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        GB_CUDA(cudaMemcpyAsync(ng.edge_off, g->edge_off, (size_t)(E0 + 1) * 8, cudaMemcpyDeviceToDevice, st));
+        if (nb0) GB_CUDA(cudaMemcpyAsync(ng.bases, g->bases, (size_t)((nb0 + 15) / 16) * 4, cudaMemcpyDeviceToDevice, st));
+        if (n_add_nodes) GB_CUDA(cudaMemcpyAsync(ng.node_kmer + N0, add_node_kmers, (size_t)n_add_nodes * 8, cudaMemcpyHostToDevice, st));
+        if (n_add_edges) {
+            GB_CUDA(cudaMemcpyAsync(ng.edge_start + E0, add_start, (size_t)n_add_edges * 4, cudaMemcpyHostToDevice, st));
+            GB_CUDA(cudaMemcpyAsync(ng.edge_end + E0, add_end, (size_t)n_add_edges * 4, cudaMemcpyHostToDevice, st));
+            Tmp<unsigned long long> d_off;
+            Tmp<uint8_t> d_codes;
+            GB_TRY(d_off.alloc((size_t)n_add_edges + 1, st));
+            GB_TRY(d_codes.alloc((size_t)add_bases_n, st));
+            GB_CUDA(cudaMemcpyAsync(d_off.p, add_off, (size_t)(n_add_edges + 1) * 8, cudaMemcpyHostToDevice, st));
+            GB_CUDA(cudaMemcpyAsync(d_codes.p, add_bases, (size_t)add_bases_n, cudaMemcpyHostToDevice, st));
+            LAUNCH(edit_append_offsets_kernel, n_add_edges + 1, d_off.p, (long long)n_add_edges, nb0, ng.edge_off + E0);
+            LAUNCH(edit_append_bases_kernel, add_bases_n, d_codes.p, add_bases_n, nb0, ng.bases);
+        }
+        GB_CUDA(cudaStreamSynchronize(st));
+        g->cur ^= 1;
+        g->node_kmer = ng.node_kmer; g->edge_start = ng.edge_start; g->edge_end = ng.edge_end;
+        g->edge_off = ng.edge_off; g->bases = ng.bases;
+        g->n_nodes = N1; g->n_edges = E1; g->n_bases = (int64_t)nb1;
+    }
+    // 3. removeNode
+    if (n_remove_nodes) {
+        Tmp<unsigned int> dr, bad;
+        GB_TRY(dr.alloc((size_t)n_remove_nodes, st));
+        GB_TRY(bad.alloc(1, st));
+        GB_TRY(bad.zero(1));
+        GB_CUDA(cudaMemcpyAsync(dr.p, remove_nodes, (size_t)n_remove_nodes * 4, cudaMemcpyHostToDevice, st));
+        RewriteBufs rb;
+        GB_TRY(rb.init(g));
+        LAUNCH(edit_drop_nodes_kernel, n_remove_nodes, dr.p, (long long)n_remove_nodes, rb.rw.node_keep);
+        LAUNCH(edit_check_ends_kernel, g->n_edges, g->edge_start, g->edge_end, (unsigned long long)g->n_edges, rb.rw.node_keep, bad.p);
+        unsigned int b = 0;
+        GB_CUDA(cudaMemcpyAsync(&b, bad.p, 4, cudaMemcpyDeviceToHost, st));
+        GB_CUDA(cudaStreamSynchronize(st));
+        if (b) { set_error("removeNode: an edge still starts or ends at a removed node"); return GB_E_INVARIANT; }
+        return apply_rewrite(g, rb.rw);
+    }
+    GB_CUDA(cudaStreamSynchronize(st));
+    return GB_OK;
+}
+
 int gb_graph_clip_tips(gb_graph *h, int64_t max_len, int64_t *removed)
 {
     Graph *g;

@@ -75,6 +75,27 @@ class MapGraph:
             raise ValueError("one flag per node of the current graph")
         capi.check(capi.lib().gb_graph_retain(self.h, capi.ptr(keep)))
 
+    def edit(self, replace=(), add_nodes=(), add_edges=(), remove_nodes=()):
+        """The fine-grained mutators of trait Graph in bulk (gb_graph_edit), applied in this order:
+        replace = [(edge, new_start or None, new_end or None)]  -- replaceStart / replaceEnd (197-209)
+        add_nodes = [kmer u64], add_edges = [(start, end, base codes)]  -- addNode / addEdge (172-184); returns their indices
+        remove_nodes = [node]  -- removeNode (185-187)."""
+        NONE = 0xFFFFFFFF
+        nn, ne, _ = self.counts()
+        ridx = np.array([r[0] for r in replace], np.uint32)
+        rs = np.array([NONE if r[1] is None else r[1] for r in replace], np.uint32)
+        re_ = np.array([NONE if r[2] is None else r[2] for r in replace], np.uint32)
+        nk = np.array(list(add_nodes), np.uint64)
+        es = np.array([e[0] for e in add_edges], np.uint32)
+        ee = np.array([e[1] for e in add_edges], np.uint32)
+        off = np.zeros(len(add_edges) + 1, np.uint64)
+        off[1:] = np.cumsum([len(e[2]) for e in add_edges]) if add_edges else []
+        codes = np.concatenate([np.asarray(e[2], np.uint8) for e in add_edges]) if add_edges else np.zeros(0, np.uint8)
+        rm = np.array(list(remove_nodes), np.uint32)
+        capi.check(capi.lib().gb_graph_edit(self.h, ridx.size, capi.ptr(ridx), capi.ptr(rs), capi.ptr(re_), nk.size, capi.ptr(nk), es.size,
+                                            capi.ptr(es), capi.ptr(ee), capi.ptr(off), capi.ptr(codes), rm.size, capi.ptr(rm)))
+        return list(range(nn, nn + nk.size)), list(range(ne, ne + es.size))
+
     def simplifyGraph(self):
         capi.check(capi.lib().gb_graph_simplify(self.h))
 

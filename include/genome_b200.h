@@ -147,6 +147,20 @@ int gb_graph_simplify(gb_graph *g);
 int gb_graph_remove_bubbles(gb_graph *g);
 /* removeEdge for a list of edge indices (Graph.scala:191-195; the call at GraphSimplifier.scala:316) */
 int gb_graph_remove_edges(gb_graph *g, const uint32_t *edge_idx, int64_t n);
+/* The remaining mutators of trait Graph (Graph.scala:31-36) in bulk, applied in this order:
+ *   replaceStart / replaceEnd (197-209): for i < n_replace, edge edge_idx[i] gets start new_start[i] and end new_end[i]
+ *                                        (0xFFFFFFFF = keep);
+ *   addNode (172-176) / addEdge (178-184): n_add_nodes nodes with k-mers add_node_kmers[] get the indices n_nodes, n_nodes + 1,
+ *                                        ...; n_add_edges edges (add_start[i] -> add_end[i], bases add_bases[add_off[i] ..
+ *                                        add_off[i + 1]) as one code per byte, add_off[0] = 0) get the indices n_edges, ...;
+ *                                        replacements and new edges may name the new nodes;
+ *   removeNode (185-187): the listed nodes are dropped; like the reference's it does not touch edges, so a node that an edge
+ *                                        still starts or ends at is refused (GB_E_INVARIANT; the earlier steps stay applied).
+ * Every array is a host array; any count may be 0.  (Written after this round's GPU budget was spent: device test opt-in.) */
+int gb_graph_edit(gb_graph *g, int64_t n_replace, const uint32_t *edge_idx, const uint32_t *new_start, const uint32_t *new_end,
+                  int64_t n_add_nodes, const uint64_t *add_node_kmers, int64_t n_add_edges, const uint32_t *add_start,
+                  const uint32_t *add_end, const uint64_t *add_off, const uint8_t *add_bases, int64_t n_remove_nodes,
+                  const uint32_t *remove_nodes);
 /* EXTENSION, no reference counterpart: one sweep of dead-end tip removal */
 int gb_graph_clip_tips(gb_graph *g, int64_t max_len, int64_t *removed);
 /* invariants of S/scripts/GraphSimplifier.scala:159-170 evaluated on the device; GB_E_INVARIANT if broken */

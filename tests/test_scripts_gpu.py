@@ -60,3 +60,42 @@ def test_retain_arbitrary_node_set(gpu):
     assert H.canon_gpu_graph(g2) == H.canon_gpu_graph(g3)
     g3.retain(np.zeros(g3.counts()[0], bool))
     assert g3.counts() == (0, 0, 0)
+
+
+def test_graph_edit_mutators(gpu):
+    """addNode / addEdge / replaceStart / replaceEnd / removeNode (Graph.scala:172-209) through gb_graph_edit: a round trip that
+    must leave the graph as it was, with the intermediate states checked through the export."""
+    from genome_b200.dnamap import FreqFilter
+    from genome_b200.graph import Graph
+    k = 15
+    b, n, _ = H.small_reads(5000, 60, 30, 0.01, seed=2015)
+    g = Graph.buildGraph(k, FreqFilter.extractFilteredKmers(PairedEndData(b, n // 2), k, 2))
+    before = H.canon_gpu_graph(g)
+    nn, ne, nb = g.counts()
+    assert ne > 0
+    x, y = (1 << (2 * k)) - 1, (1 << (2 * k)) - 2   # poly-T and a neighbour: not nodes of a random 5 kbp genome
+    assert x not in before[0] and y not in before[0]
+    new_nodes, new_edges = g.edit(add_nodes=[x, y], add_edges=[(nn, nn + 1, [0, 1, 2]), (nn + 1, 0, [3])])
+    assert new_nodes == [nn, nn + 1] and new_edges == [ne, ne + 1]
+    assert g.counts() == (nn + 2, ne + 2, nb + 4)
+    node_kmer, es, ee, off, bases = g.export()
+    assert (int(node_kmer[nn]), int(node_kmer[nn + 1])) == (x, y)
+    assert (int(es[ne]), int(ee[ne]), bases[int(off[ne]):int(off[ne + 1])].tolist()) == (nn, nn + 1, [0, 1, 2])
+    assert (int(es[ne + 1]), int(ee[ne + 1]), bases[int(off[ne + 1]):int(off[ne + 2])].tolist()) == (nn + 1, 0, [3])
+    assert H.canon_gpu_graph(g)[1][:0] == [] and len(H.canon_gpu_graph(g)[1]) == ne + 2
+    # replaceEnd / replaceStart and back
+    old_s, old_e = int(es[0]), int(ee[0])
+    g.edit(replace=[(0, None, nn)])
+    assert int(g.export()[2][0]) == nn and int(g.export()[1][0]) == old_s
+    g.edit(replace=[(0, nn + 1, old_e)])
+    assert (int(g.export()[1][0]), int(g.export()[2][0])) == (nn + 1, old_e)
+    g.edit(replace=[(0, old_s, None)])
+    # removeNode refuses a node that still has edges, then succeeds once they are gone
+    with pytest.raises(Exception):
+        g.edit(remove_nodes=[nn])
+    assert g.counts() == (nn + 2, ne + 2, nb + 4)
+    g.removeEdges([ne, ne + 1])
+    g.edit(remove_nodes=[nn, nn + 1])
+    assert g.counts() == (nn, ne, nb)
+    assert H.canon_gpu_graph(g) == before
+    g.check()
