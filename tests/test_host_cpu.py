@@ -154,3 +154,16 @@ def test_every_entry_point_has_a_binding_line_and_a_ctypes_signature():
     assert not missing_doc, missing_doc
     missing_sig = [n for n in names if n not in capi.SIGNATURES and n not in ("gb_last_error", "gb_launch_count", "gb_version")]
     assert not missing_sig, missing_sig
+
+
+def test_ctypes_signatures_have_the_headers_arity():
+    """A ctypes table that disagrees with the header on the NUMBER of arguments corrupts the call silently: compare them."""
+    import re
+    from genome_b200 import capi
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "genome_b200.h")).read(), flags=re.S)
+    protos = re.findall(r"^\s*(?:const\s+)?[a-z_0-9]+[ \*]+\b(gb_[a-z_0-9]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.M | re.S)
+    assert len(protos) >= 55
+    for name, args in protos:
+        n = 0 if args.strip() in ("", "void") else len(args.split(","))
+        if name in capi.SIGNATURES:
+            assert len(capi.SIGNATURES[name][1]) == n, name
