@@ -540,8 +540,8 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
     for (int64_t s = 0; s < n_sub; s++) half = std::max(half, win_upper(read0 + s * per_reads, read0 + std::min(n_reads, (s + 1) * per_reads)));
     // GENOME_B200_COUNTLESS=1 (one sub-batch only): no count pass, per-(bucket, CTA) slabs instead of exact bucket ranges
     const unsigned int nbk = (unsigned int)pl.nb();
-    const unsigned int slab = getenv("GENOME_B200_COUNTLESS") && n_sub == 1 && pl.owners == 1 && nbk <= 128
-                                  ? slab_keys_for((unsigned long long)half, nbk, (int)grid) : 0;
+    const unsigned int slab = getenv("GENOME_B200_COUNTLESS") && n_sub == 1 && pl.owners == 1 && nbk <= 128 && half >= (1 << 20)
+                                  ? slab_keys_for(slab_cta_keys(n_reads, (unsigned long long)half, (int)grid), nbk, (int)grid) : 0;
     const size_t slab_keys = (size_t)slab * nbk * (size_t)grid, n_slab_chunks = (size_t)nbk * (size_t)grid;
     GB_TRY(map_stage(m, slab ? slab_keys + 2 * n_slab_chunks + 8 : (size_t)((n_sub > 1 ? 2 : 1) * (half + 8))));
     if (n_sub == 1) bk = up; // nothing to overlap: one stream, no cross-stream events
@@ -708,7 +708,7 @@ static int insert_host_pipelined(Map *m, const uint8_t *bin, int64_t n_reads, un
     const unsigned int nb = (unsigned int)pl.nb();
     if (nb > 128) return GB_OK;
     const unsigned long long ovf_cap = (unsigned long long)want / 16 + 65536;
-    const unsigned int slab = slab_keys_for((unsigned long long)want, nb, w.grid); // 0: slab positions would not fit 32 bits
+    const unsigned int slab = slab_keys_for(slab_cta_keys(n_reads, (unsigned long long)want, w.grid), nb, w.grid); // 0: positions would not fit 32 bits
     if (!slab) return GB_OK;
     const size_t n_chunks = (size_t)nb * (size_t)w.grid, slab_keys = (size_t)slab * n_chunks;
     GB_TRY(map_stage(m, slab_keys + (size_t)ovf_cap + 2 * n_chunks + 16));

@@ -501,14 +501,25 @@ int part_scatter_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, un
 }
 
 // ---- the single-pass variant (GENOME_B200_COUNTLESS=1)
-// keys per (bucket, CTA) slab for a batch of at most `total` keys: the expected share plus 8 standard deviations of a binomial
-// draw, rounded up to 64 keys (512 B).  0 = the slabs would not fit 32-bit positions: use the counted passes.
-unsigned int slab_keys_for(unsigned long long total, unsigned int nb, int grid)
+// keys per (bucket, CTA) slab.  A CTA takes every grid-th tile, so what it can see is bounded by its number of tiles, not by
+// total / grid (a batch with fewer tiles than CTAs leaves most CTAs idle and the busy ones with a whole tile each):
+// cta_keys = tiles per CTA x reads per tile x windows per read; the slab is that share of one bucket plus 8 standard
+// deviations of a binomial draw, rounded up to 64 keys (512 B).  0 = the slabs would not fit 32-bit positions.
+unsigned int slab_keys_for(unsigned long long cta_keys, unsigned int nb, int grid)
 {
-    const double e = (double)total / ((double)nb * grid);
+    const double e = (double)cta_keys / (double)nb;
     const unsigned long long slab = (((unsigned long long)(e + 8.0 * sqrt(e + 1.0)) + 64) + 63) / 64 * 64;
     if (slab * nb * (unsigned long long)grid >= 0xFFF00000ull) return 0; // positions are 32-bit, with room for one round above a limit
     return (unsigned int)slab;
+}
+// upper bound of the keys one CTA of a `grid`-CTA bucket pass sees in a batch of n_reads reads with at most `windows` k-windows
+unsigned long long slab_cta_keys(long long n_reads, unsigned long long windows, int grid)
+{
+    if (n_reads <= 0) return 0;
+    const unsigned long long tiles = ((unsigned long long)n_reads + TILE_READS - 1) / TILE_READS;
+    const unsigned long long per_cta = (tiles + (unsigned long long)grid - 1) / (unsigned long long)grid;
+    const unsigned long long per_read = (windows + (unsigned long long)n_reads - 1) / (unsigned long long)n_reads;
+    return per_cta * TILE_READS * per_read;
 }
 
 // chunk table of the slabs, bucket-major: chunk c = (bucket c / grid, CTA c % grid) holds count[c] keys at out[c * slab].

@@ -77,7 +77,8 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
                       int n_chunks, unsigned long long n_total, cudaStream_t st, bool total_is_upper_bound = false);
 
 // the single-pass bucket pass (no count pass; GENOME_B200_COUNTLESS=1, single-GPU insert): see part_scatter_kernel<..., SLABS>
-unsigned int slab_keys_for(unsigned long long total, unsigned int nb, int grid);
+unsigned int slab_keys_for(unsigned long long cta_keys, unsigned int nb, int grid);
+unsigned long long slab_cta_keys(long long n_reads, unsigned long long windows, int grid);
 // the same in LIST mode for the chunked host insert: begin / one launch per read range / end (see partition.cu)
 int slab_list_begin(const PartLayout &pl, PartWork &w, cudaStream_t st);
 int slab_list_range(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, unsigned int slab,
