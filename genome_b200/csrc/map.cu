@@ -708,7 +708,16 @@ static int insert_host_pipelined(Map *m, const uint8_t *bin, int64_t n_reads, un
     const unsigned int nb = (unsigned int)pl.nb();
     if (nb > 128) return GB_OK;
     const unsigned long long ovf_cap = (unsigned long long)want / 16 + 65536;
-    const unsigned int slab = slab_keys_for(slab_cta_keys(n_reads, (unsigned long long)want, w.grid), nb, w.grid); // 0: positions would not fit 32 bits
+    int n_copy = 4;
+    if (const char *e = getenv("GENOME_B200_H2D_CHUNKS")) n_copy = std::max(1, std::min(16, atoi(e)));
+    const int64_t per_chunk = std::max<int64_t>(TILE_READS, ((n_reads + n_copy - 1) / n_copy + TILE_READS - 1) / TILE_READS * TILE_READS);
+    // every chunk is its own launch and deals its tiles to the CTAs from CTA 0 on: a CTA sees the sum of its shares
+    unsigned long long cta_keys = 0;
+    for (int64_t r0 = 0; r0 < n_reads; r0 += per_chunk) {
+        const int64_t nr = std::min(per_chunk, n_reads - r0);
+        cta_keys += slab_cta_keys(nr, (unsigned long long)(nr * per_read), w.grid);
+    }
+    const unsigned int slab = slab_keys_for(cta_keys, nb, w.grid); // 0: positions would not fit 32 bits
     if (!slab) return GB_OK;
     const size_t n_chunks = (size_t)nb * (size_t)w.grid, slab_keys = (size_t)slab * n_chunks;
     GB_TRY(map_stage(m, slab_keys + (size_t)ovf_cap + 2 * n_chunks + 16));
@@ -717,9 +726,6 @@ static int insert_host_pipelined(Map *m, const uint8_t *bin, int64_t n_reads, un
     DeviceBuf d_bin;
     GB_TRY(d_bin.alloc(used + 16, m->stream));
 
-    int n_copy = 4;
-    if (const char *e = getenv("GENOME_B200_H2D_CHUNKS")) n_copy = std::max(1, std::min(16, atoi(e)));
-    const int64_t per_chunk = std::max<int64_t>(TILE_READS, ((n_reads + n_copy - 1) / n_copy + TILE_READS - 1) / TILE_READS * TILE_READS);
     cudaEvent_t entry = nullptr, copied[16];
     for (auto &e : copied) e = nullptr;
     struct Guard {
