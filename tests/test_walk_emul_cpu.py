@@ -22,13 +22,15 @@ NONE32 = 0xFFFFFFFF
 @pytest.fixture(scope="module")
 def emul():
     src = os.path.join(HERE, "emul", "walk_emul.cpp")
-    out = os.path.join(HERE, "_build", "libwalk_emul.so")
+    sanitize = bool(os.environ.get("GB_EMUL_SANITIZE"))   # set by test_walk_code_under_address_sanitizer's child process
+    out = os.path.join(HERE, "_build", "libwalk_emul_asan.so" if sanitize else "libwalk_emul.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     deps = [src] + [os.path.join(ROOT, "genome_b200", "csrc", f) for f in ("walk.cuh", "common.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
-                               "-Wl,-Bsymbolic", "-I" + cuda_inc, "-o", out, src])   # own symbols first: the product library
+        subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function"] +
+                              (["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"] if sanitize else []) +
+                              ["-Wl,-Bsymbolic", "-I" + cuda_inc, "-o", out, src])   # own symbols first: the product library
         # (loaded RTLD_GLOBAL by genome_b200.capi) exports functions of the same names
     return C.CDLL(out)
 
@@ -334,3 +336,22 @@ def test_pair_support_is_additive_over_pair_slices(emul):
             acc += emul_support(emul, lay, og, mine.bin, mine.count, 90, 155)[0]
         assert np.array_equal(acc, wf)
         assert first.count == data.count // 3 and data.take(10 ** 9) is data
+
+
+def test_walk_code_under_address_sanitizer():
+    """The walk / split device functions (walk.cuh) once more, with the harness built with -fsanitize=address,undefined and the
+    sanitizer runtime preloaded into a child pytest: every index these functions compute on the local edge tables, the bitsets
+    and the caller's arrays is checked (numpy's buffers come from the intercepted malloc).  An overrun here is an overrun in
+    walk_cases_kernel / split_nodes_kernel."""
+    import sys
+    if os.environ.get("GB_EMUL_SANITIZE"):
+        pytest.skip("this IS the sanitized child")
+    libs = [subprocess.run(["gcc", "-print-file-name=" + n], capture_output=True, text=True).stdout.strip() for n in ("libasan.so", "libubsan.so")]
+    if not all(os.path.isabs(p) and os.path.exists(p) for p in libs):
+        pytest.skip("no sanitizer runtime next to gcc")
+    env = dict(os.environ, GB_EMUL_SANITIZE="1", LD_PRELOAD=" ".join(libs), ASAN_OPTIONS="detect_leaks=0:verify_asan_link_order=0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-p", "no:cacheprovider",
+                        "-k", "bitset_walk or long_range or pair_support_matches or split_matches or graph_map_get_all"],
+                       capture_output=True, text=True, env=env, timeout=1500, cwd=ROOT)
+    assert "ERROR: AddressSanitizer" not in r.stderr + r.stdout and "runtime error" not in r.stderr + r.stdout, (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0, (r.stdout + r.stderr)[-4000:]
