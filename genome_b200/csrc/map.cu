@@ -491,6 +491,14 @@ int map_verify_fixed(Map *m, const uint8_t *d_bin, unsigned int rec, unsigned in
     return GB_OK;
 }
 
+// the single-pass variants (GENOME_B200_COUNTLESS) leave small batches to the counted passes: below this many k-windows the
+// slabs (one per bucket and CTA, each at least 128 keys) would dwarf the batch.  GENOME_B200_COUNTLESS_MIN lowers it for tests.
+static int64_t countless_min()
+{
+    const char *e = getenv("GENOME_B200_COUNTLESS_MIN");
+    return e ? std::max<int64_t>(1, atoll(e)) : ((int64_t)1 << 20);
+}
+
 // 0 = choose by table size, 1 = direct (fused extract + upsert, random access), 2 = partitioned (L2-blocked)
 static int insert_mode()
 {
@@ -540,7 +548,7 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
     for (int64_t s = 0; s < n_sub; s++) half = std::max(half, win_upper(read0 + s * per_reads, read0 + std::min(n_reads, (s + 1) * per_reads)));
     // GENOME_B200_COUNTLESS=1 (one sub-batch only): no count pass, per-(bucket, CTA) slabs instead of exact bucket ranges
     const unsigned int nbk = (unsigned int)pl.nb();
-    const unsigned int slab = getenv("GENOME_B200_COUNTLESS") && n_sub == 1 && pl.owners == 1 && nbk <= 128 && half >= (1 << 20)
+    const unsigned int slab = getenv("GENOME_B200_COUNTLESS") && n_sub == 1 && pl.owners == 1 && nbk <= 128 && half >= countless_min()
                                   ? slab_keys_for(slab_cta_keys(n_reads, (unsigned long long)half, (int)grid), nbk, (int)grid) : 0;
     const size_t slab_keys = (size_t)slab * nbk * (size_t)grid, n_slab_chunks = (size_t)nbk * (size_t)grid;
     GB_TRY(map_stage(m, slab ? slab_keys + 2 * n_slab_chunks + 8 : (size_t)((n_sub > 1 ? 2 : 1) * (half + 8))));
@@ -693,7 +701,7 @@ static int insert_host_pipelined(Map *m, const uint8_t *bin, int64_t n_reads, un
     *handled = false;
     if (!getenv("GENOME_B200_COUNTLESS") || (int)len0 < m->k) return GB_OK;
     const int64_t per_read = (int64_t)len0 - m->k + 1, want = n_reads * per_read;
-    if (want < (1 << 20) || want > ((int64_t)1 << 28)) return GB_OK; // small: not worth it; large: the ordinary path batches
+    if (want < countless_min() || want > ((int64_t)1 << 28)) return GB_OK; // small: not worth it; large: the ordinary path batches
     int64_t budget = 0;
     GB_TRY(map_budget(m, want, &budget));
     if (want > budget) return GB_OK;

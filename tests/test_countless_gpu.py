@@ -47,6 +47,9 @@ def check(b, n, k, cap=0):
     (8, 50, True, 0.0), (4, 30, False, 0.0), (1, 10, False, 0.0), (16, 100, False, 0.0),
 ])
 def test_countless_insert_matches_oracle(gpu, countless, k, read_len, ragged, err):
+    """The parity cases of the table (tests/test_parity_gpu.py) through the slab bucket pass -- fixed-stride cases also
+    through the chunked host insert.  These batches are small (a few 100 k windows): GENOME_B200_COUNTLESS_MIN lets them in."""
+    countless.setenv("GENOME_B200_COUNTLESS_MIN", "1")
     b, n, _ = H.small_reads(20000, read_len, 12, err, seed=1000 + k, ragged=ragged)
     check(b, n, k)
 
