@@ -3,7 +3,9 @@ of the sharded insert with super-k-mers on the wire (comm.cu pmap_insert_superkm
 every rank cuts ITS slice of the reads into records (the g++ build of csrc/superkmer.cuh), the records travel to their
 minimizer owners, every rank inserts what it received (the oracle's FreqFilter.add over the records as reads).  Checks: the
 shards are disjoint, each holds exactly the keys the library's ownership rule (gb_owner_of_minimizer) gives it, and their
-union with counts equals the single-map result."""
+union with counts equals the single-map result; then every shard is filtered and the sharded Graph.buildGraph (the g++ build of
+csrc/sgraph.cuh over the gloo fabric of tests/gloo_sgraph_worker.py) runs straight from the minimizer-owned shards and must give
+the oracle's graph of all reads: the whole multi-GPU path, reads to graph, with processes instead of GPUs."""
 import os
 import sys
 
@@ -18,12 +20,14 @@ from oracle import pyoracle  # noqa: E402
 from tests import helpers as H  # noqa: E402
 from tests.test_sgraph_emul_cpu import load_emul, ptr  # noqa: E402
 from tests.test_superkmer_emul_cpu import split, to_ragged_bin  # noqa: E402
+from tests.gloo_sgraph_worker import GlooFabric, run_build  # noqa: E402
 
 
 def main():
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     lib = load_emul()
+    fab = GlooFabric(rank, world, "sk" + os.environ.get("MASTER_PORT", "0"))
     for k, read_len in ((31, 100), (21, 80)):
         b, n, _ = H.small_reads(30000, read_len, 10, 0.01, seed=40 + k)   # same bytes on every rank
         mine = PairedEndData(b, n // 2).shard(rank, world)
@@ -51,6 +55,16 @@ def main():
         windows = [None] * world
         dist.all_gather_object(windows, w)
         assert sum(windows) == ow
+        # the whole sharded path: filter every shard, then the sharded Graph.buildGraph straight from the minimizer-owned shards
+        # (its re-routing finds every key at home) -- against the oracle's graph of all reads
+        shard.delete_below(2)
+        whole.delete_below(2)
+        kept, _ = shard.export()
+        og = pyoracle.OracleGraph(whole)
+        got, counts, _ = run_build(lib, fab, k, False, kept, rank, world)
+        assert counts == og.counts(), (rank, k, counts, og.counts())
+        assert got == H.canon_oracle_graph(og), (rank, k)
+    fab.close()
     dist.barrier()
     if rank == 0:
         print("SUPERKMER ROUTING OK world", world)
