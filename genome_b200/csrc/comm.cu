@@ -452,6 +452,7 @@ static int pmap_insert_superkmers(Map *m, const uint8_t *d_bin, const unsigned l
                                   int64_t *n_windows)
 {
     Comm *c = m->comm;
+    ArenaScope scope(&m->arena); // count / send / receive buffers: from the map's arena (no cudaMalloc per call in the steady state)
     const int P = c->n_ranks, k = m->k, mlen = sg::minimizer_len(k);
     if (sg::sk_max_windows(k) < 1) { set_error("super-k-mer records hold 52 bases: k = %d does not fit", k); return GB_E_K_RANGE; }
     cudaStream_t st = c->stream;
