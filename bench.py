@@ -379,6 +379,9 @@ def main():
                     "insert_frac": algo_bytes / ins_s / 1e9 / peak,
                     "phases_ms": {"bucket (count+offsets+scatter)": st["bucket_ns"] * 1e-6, "upsert": st["upsert_ns"] * 1e-6} if partitioned else None,
                     "random_access_ceiling_kmers_per_s": gups, "insert_vs_random_access_ceiling": (windows / ins_s) / gups,
+                    # one 32 B sector in and one dirty sector out per insert = 64 B/instance is the THEORETICAL
+                    # random-access roofline (peak / 64 B inserts/s); the L2-blocked path may exceed it, which is its point
+                    "insert_vs_64B_sector_roofline": (windows / ins_s) * 64.0 / (peak * 1e9),
                     "table_bytes": table_bytes, "distinct_keys": distinct}
         if partitioned and args.workload == "C2" and args.scale == 1.0:
             # dram__bytes_read.sum + dram__bytes_write.sum of one insert_keys_kernel launch on this workload
