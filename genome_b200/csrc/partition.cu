@@ -314,8 +314,25 @@ constexpr int IK_THREADS = 256;
 
 // No CTA barrier anywhere: every thread finds its own chunk, every warp adds its new-key count to one of SPREAD
 // global counters (fold_new_keys_kernel sums them into counters[0] afterwards).
+// claim an EMPTY slot and give it count 1 in ONE 128-bit compare-and-swap (the slot is 16 bytes: key | count | vid; an untouched
+// slot is {EMPTY_KEY, 0, NONE32}, init_table_kernel).  Returns the key that was there (EMPTY_KEY = claimed), *exact = the rest
+// matched too.  sm_90+: atom.cas.b128.
+__device__ __forceinline__ unsigned long long claim_slot_128(Slot *slot, unsigned long long key, bool *won)
+{
+    const unsigned long long exp_hi = (unsigned long long)NONE32 << 32, new_hi = ((unsigned long long)NONE32 << 32) | 1ull;
+    unsigned long long old_lo, old_hi;
+    asm volatile("{\n\t.reg .b128 e, n, o;\n\tmov.b128 e, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\tatom.global.cas.b128 o, [%6], e, n;\n\tmov.b128 {%0, %1}, o;\n\t}"
+                 : "=l"(old_lo), "=l"(old_hi)
+                 : "l"(EMPTY_KEY), "l"(exp_hi), "l"(key), "l"(new_hi), "l"(slot)
+                 : "memory");
+    *won = old_lo == EMPTY_KEY && old_hi == exp_hi;
+    return old_lo;
+}
+
 // DEV_TOTAL: n_total is only an upper bound (it sized the grid); the exact number of keys is vstart[n_chunks].
-template <int IK_PER_THREAD, bool CAS_FIRST, bool DEV_TOTAL>
+// CLAIM128 (GENOME_B200_CAS128=1): a new key costs load + one 128-bit CAS instead of load + CAS + red (2 L2 transactions
+// instead of 3; new keys are 31 % of the instances on C2).
+template <int IK_PER_THREAD, bool CAS_FIRST, bool DEV_TOTAL, bool CLAIM128 = false>
 __global__ void __launch_bounds__(IK_THREADS)
 insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vstart,
                    const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Slot *table, unsigned long long cap,
@@ -350,6 +367,29 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
     }
     int nk = 0;
     unsigned long long old[IK_PER_THREAD];
+    if (CLAIM128) {
+#pragma unroll
+        for (int j = 0; j < IK_PER_THREAD; j++)
+            if (ok[j]) cur[j] = load_key(table + idx[j]);
+        bool won[IK_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < IK_PER_THREAD; j++) {
+            won[j] = false;
+            old[j] = cur[j];
+            if (ok[j] && cur[j] == EMPTY_KEY) old[j] = claim_slot_128(table + idx[j], key[j], &won[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < IK_PER_THREAD; j++) {
+            if (!ok[j]) continue;
+            if (won[j]) nk++;                                                        // claimed with count 1: done
+            else if (old[j] == key[j]) red_add_s32(&table[idx[j]].count, 1);
+            else nk += upsert_add(table, cap, idx[j], old[j], key[j], 1);             // someone else's slot (or not exactly empty): generic path
+        }
+        nk = __reduce_add_sync(0xFFFFFFFFu, nk);
+        if ((threadIdx.x & 31) == 0 && nk)
+            atomicAdd(&spread[(blockIdx.x * (IK_THREADS / 32) + (threadIdx.x >> 5)) & (SPREAD - 1)], (unsigned long long)nk);
+        return;
+    }
     if (CAS_FIRST) {
         // one L2 transaction instead of two for a new key: the CAS is the probe (it returns the resident key)
 #pragma unroll
@@ -666,6 +706,13 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
 #define GB_IK(N, C, D)                                                                                                       \
     insert_keys_kernel<N, C, D><<<(unsigned int)((n_total + IK_THREADS * N - 1) / (IK_THREADS * N)), IK_THREADS, 0, st>>>(    \
         d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread)
+    const bool cas128 = getenv("GENOME_B200_CAS128") != nullptr; // read per call: tests switch it inside one process
+    if (cas128) {
+        if (total_is_upper_bound) insert_keys_kernel<4, false, true, true><<<(unsigned int)((n_total + IK_THREADS * 4 - 1) / (IK_THREADS * 4)), IK_THREADS, 0, st>>>(
+            d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread);
+        else insert_keys_kernel<4, false, false, true><<<(unsigned int)((n_total + IK_THREADS * 4 - 1) / (IK_THREADS * 4)), IK_THREADS, 0, st>>>(
+            d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread);
+    } else
     if (total_is_upper_bound) GB_IK(4, false, true);
     else if (cas_first) { if (per == 2) GB_IK(2, true, false); else if (per == 8) GB_IK(8, true, false); else GB_IK(4, true, false); }
     else if (per == 8) GB_IK(8, false, false); else if (per == 2) GB_IK(2, false, false); else GB_IK(4, false, false);

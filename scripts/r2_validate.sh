@@ -12,7 +12,8 @@ export GENOME_B200_UNVALIDATED=1
              "tests/test_graphmap_gpu.py" "tests/test_scripts_gpu.py" \
              "tests/test_countless_gpu.py -k countless_insert_matches_oracle" "tests/test_countless_gpu.py -k overflow_path" \
              "tests/test_countless_gpu.py -k overflow_list" "tests/test_countless_gpu.py -k ragged_stream" \
-             "tests/test_countless_gpu.py -k at_size" "tests/test_countless_gpu.py -k superkmer_records"; do
+             "tests/test_countless_gpu.py -k at_size" "tests/test_countless_gpu.py -k superkmer_records" \
+             "tests/test_countless_gpu.py -k cas128"; do
     echo "-- $sel"
     timeout 900 python -m pytest $sel -q -m gpu 2>&1 | tail -6
   done
@@ -26,9 +27,11 @@ export GENOME_B200_UNVALIDATED=1
   echo "== bench: default vs single-pass bucket pass (GENOME_B200_COUNTLESS=1)"
   timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err
   GENOME_B200_COUNTLESS=1 timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/r2_bench_countless.json 2> gpurun_out/r2_bench_countless.err
+  GENOME_B200_CAS128=1 timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/r2_bench_cas128.json 2> gpurun_out/r2_bench_cas128.err
+  GENOME_B200_CAS128=1 GENOME_B200_COUNTLESS=1 timeout 300 python bench.py --steps 30 --warmup 3 --no-cpu-baseline --no-graph > gpurun_out/r2_bench_countless_cas128.json 2> gpurun_out/r2_bench_countless_cas128.err
   python -c "
 import json
-for f in ('default', 'countless'):
+for f in ('default', 'countless', 'cas128', 'countless_cas128'):
     try:
         d = json.loads(open('gpurun_out/r2_bench_%s.json' % f).read().strip().splitlines()[-1])
         print(f, '%.3f ms/step device' % d['ms_per_step'], '%.3f ms/step e2e' % d['e2e']['ms_per_step'], d['roofline'].get('phases_ms'), d['roofline'].get('insert_ms'))

@@ -150,3 +150,28 @@ def test_superkmer_records_insert_like_the_reads(gpu, k, P):
     with pytest.raises(Exception):
         gm.insert_records_device(d.data_ptr(), recs.size, 16, recs.shape[0], 40)
     assert gm.size == 0
+
+
+@pytest.mark.parametrize("single_pass", [False, True], ids=["counted", "single-pass"])
+def test_cas128_claim(gpu, monkeypatch, single_pass):
+    """GENOME_B200_CAS128=1: a new key is claimed WITH its count by one 128-bit compare-and-swap (insert_keys_kernel<...,
+    CLAIM128>, atom.cas.b128) instead of CAS + red.  Same tables as the default path, with and without the single pass;
+    duplicate-heavy and singleton-heavy inputs, and a second batch into the filled table (no slot is 'exactly empty' twice)."""
+    monkeypatch.setenv("GENOME_B200_INSERT", "partitioned")
+    monkeypatch.setenv("GENOME_B200_CAS128", "1")
+    if single_pass:
+        monkeypatch.setenv("GENOME_B200_COUNTLESS", "1")
+        monkeypatch.setenv("GENOME_B200_COUNTLESS_MIN", "1")
+    for k, read_len, ragged, err in [(31, 100, False, 0.01), (21, 100, True, 0.02), (15, 36, False, 0.0), (4, 30, False, 0.0)]:
+        b, n, _ = H.small_reads(20000, read_len, 12, err, seed=1000 + k, ragged=ragged)
+        check(b, n, k)
+    b, n, _ = synth.make_config("C2", scale=0.25)
+    gm = ArrayDNAMap(31, int(b.size * 1.2))
+    w = gm.insert_reads(b, n)
+    gk, gv = gm.export_sorted()
+    monkeypatch.delenv("GENOME_B200_CAS128")
+    monkeypatch.delenv("GENOME_B200_COUNTLESS", raising=False)
+    ref = ArrayDNAMap(31, int(b.size * 1.2))
+    assert ref.insert_reads(b, n) == w
+    rk, rv = ref.export_sorted()
+    assert np.array_equal(gk, rk) and np.array_equal(gv, rv)
