@@ -17,6 +17,8 @@ export GENOME_B200_UNVALIDATED=1
     echo "-- $sel"
     timeout 900 python -m pytest $sel -q -m gpu 2>&1 | tail -6
   done
+  echo "== ungated parity suite incl. insert_path=direct|partitioned and the full-size C1/C2 oracle equality"
+  timeout 1200 python -m pytest tests/test_parity_gpu.py -q -m gpu --durations=8 2>&1 | tail -25
   echo "== sharded graph build through the NCCL fabric, one rank (works on a one-GPU box)"
   timeout 600 python -m pytest tests/test_parity_multigpu.py -q -m gpu -k "(sharded_graph_build or superkmer_wire) and 1" 2>&1 | tail -10
   NGPU=$(python -c "import torch; print(torch.cuda.device_count())")

@@ -12,6 +12,14 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["direct", "partitioned"])
+def insert_path(request, monkeypatch):
+    """Both insert paths against the oracle: small tables take the direct kernel by default, the L2-blocked path
+    (part_count / part_scatter / insert_keys: the one bench.py times and every BASELINE config takes) is forced here."""
+    monkeypatch.setenv("GENOME_B200_INSERT", request.param)
+    return request.param
+
+
 def gpu_map_from(bin_bytes, n_reads, k, min_capacity=0):
     m = ArrayDNAMap(k, min_capacity)
     w = m.insert_reads(bin_bytes, n_reads)
@@ -23,11 +31,12 @@ def gpu_map_from(bin_bytes, n_reads, k, min_capacity=0):
     (31, 255, True, 0.0), (15, 36, False, 0.02), (8, 50, True, 0.0), (4, 30, False, 0.0), (1, 10, False, 0.0),
     (30, 64, True, 0.01), (16, 100, False, 0.0),
 ])
-def test_insert_counts_match_oracle(gpu, k, read_len, ragged, err):
+def test_insert_counts_match_oracle(gpu, insert_path, k, read_len, ragged, err):
     b, n, _ = H.small_reads(20000, read_len, 12, err, seed=1000 + k, ragged=ragged)
     om, ow = H.oracle_counts(b, n, k)
     gm, gw = gpu_map_from(b, n, k)
     assert gw == ow == pyoracle.count_windows(b, n, k)
+    assert (gm.stats()["upsert_ns"] > 0) == (insert_path == "partitioned" and gw > 0)
     assert gm.size == om.size()
     gk, gv = gm.export_sorted()
     ok, ov = om.export_sorted()
@@ -42,7 +51,7 @@ def test_insert_counts_match_oracle(gpu, k, read_len, ragged, err):
     assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
 
 
-def test_insert_grows_from_small_table(gpu):
+def test_insert_grows_from_small_table(gpu, insert_path):
     b, n, _ = H.small_reads(200000, 100, 8, 0.01, seed=7)
     om, ow = H.oracle_counts(b, n, 31)
     gm, gw = gpu_map_from(b, n, 31, min_capacity=0)
@@ -52,7 +61,7 @@ def test_insert_grows_from_small_table(gpu):
     assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
 
 
-def test_presized_equals_grown(gpu):
+def test_presized_equals_grown(gpu, insert_path):
     b, n, _ = H.small_reads(100000, 100, 10, 0.01, seed=8)
     a, _ = gpu_map_from(b, n, 31, min_capacity=0)
     c, _ = gpu_map_from(b, n, 31, min_capacity=4_000_000)
@@ -420,6 +429,38 @@ def test_full_size_properties_c1(gpu):
     contig = synth.int_to_kmer(int(node_kmer[es[0]]), k) + synth.decode(bases)
     gs = synth.decode(genome)
     assert contig in gs or contig in synth.decode(H.revcomp_codes(genome))
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2"])
+def test_full_size_oracle_equality(gpu, cfg):
+    """BASELINE configs[0] and configs[1] at FULL size (4.6 Mbp, 100 bp x 30x, k = 31; C2 with 1 % errors = the bench
+    workload, L2-blocked insert path) against the oracle: sorted (k-mer, count) table, kept set after deleteAll(v < 3),
+    node set and edge multiset of Graph.buildGraph, and again after retain + simplifyGraph.  About 90 s of oracle time."""
+    k = 31
+    b, n, _ = synth.make_config(cfg)
+    om, ow = H.oracle_counts(b, n, k)
+    gm = ArrayDNAMap(k, 34_000_000 if cfg == "C2" else 6_000_000)
+    assert gm.insert_reads(b, n) == ow == n * (100 - k + 1)
+    assert gm.stats()["upsert_ns"] > 0, "the L2-blocked insert path (the benchmarked one) must be the one tested here"
+    gk, gv = gm.export_sorted()
+    ok, ov = om.export_sorted()
+    assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
+    del gk, gv, ok, ov
+    gm.delete_below(3)
+    om.delete_below(3)
+    assert gm.size == om.size()
+    gk, gv = gm.export_sorted()
+    ok, ov = om.export_sorted()
+    assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
+    g = Graph.buildGraph(k, gm)
+    og = pyoracle.OracleGraph(om)
+    assert g.counts() == og.counts()
+    g.check()
+    H.assert_graph_equal(g, og)
+    g.retain_largest(); og.retain_largest()
+    g.simplifyGraph(); og.simplify()
+    assert g.counts() == og.counts()
+    H.assert_graph_equal(g, og)
 
 
 def test_cpp_host_driver(gpu, tmp_path):
