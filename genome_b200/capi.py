@@ -54,7 +54,10 @@ SIGNATURES = {
     "gb_timer_stop": (C.c_int, [_vp, _pi64]),
     "gb_launch_count": (C.c_longlong, []),
     "gb_bench_random_atomics": (C.c_int, [C.c_int, _sz, _i64, C.c_int, _pi64]),
+    "gb_tune": (C.c_int, [C.c_char_p, _i64, _pi64]),
+    "gb_tune_get": (C.c_int, [C.c_char_p, _pi64]),
     "gb_map_stats": (C.c_int, [_vp, _pi64]),
+    "gb_map_phase_ns": (C.c_int, [_vp, _pi64]),
     "gb_graph_build": (C.c_int, [_vp, _pp]),
     "gb_graph_build_virtual_shards": (C.c_int, [_vp, C.c_int, _pp]),
     "gb_graph_destroy": (C.c_int, [_vp]),
@@ -113,6 +116,51 @@ def lib():
             f.restype, f.argtypes = res, args
         _LIB = L
     return _LIB
+
+
+TUNE_ENV = "GENOME_B200_TUNE"   # "key=value,key=value": read by THIS harness (bench.py, the multi-process test workers), not by the library
+
+
+def tune_from_env():
+    """Apply GENOME_B200_TUNE (harness-side convenience for processes started by torchrun / gpurun scripts)."""
+    spec = os.environ.get(TUNE_ENV, "")
+    out = {}
+    for item in filter(None, (x.strip() for x in spec.split(","))):
+        key, _, val = item.partition("=")
+        set_tune(key.strip(), int(val or "1"))
+        out[key.strip()] = int(val or "1")
+    return out
+
+
+def set_tune(name, value):
+    """gb_tune: returns the previous value."""
+    prev = C.c_int64(0)
+    check(lib().gb_tune(name.encode(), int(value), C.byref(prev)))
+    return prev.value
+
+
+def get_tune(name):
+    v = C.c_int64(0)
+    check(lib().gb_tune_get(name.encode(), C.byref(v)))
+    return v.value
+
+
+class tuned:
+    """with capi.tuned(insert_path=2, single_pass_min=1): ...  -- sets the keys, restores them on exit."""
+
+    def __init__(self, **kw):
+        self.kw = kw
+        self.prev = {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.prev[k] = set_tune(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k, v in self.prev.items():
+            set_tune(k, v)
+        return False
 
 
 def check(code):

@@ -244,7 +244,7 @@ static int ensure_inboxes(Comm *c, size_t want)
     if (c->p2p == 0) return GB_OK;
     if (c->p2p < 0) {
         int64_t ok = 1;
-        if (getenv("GENOME_B200_A2A") && !strcmp(getenv("GENOME_B200_A2A"), "nccl")) ok = 0;
+        if (g_tune.a2a_nccl) ok = 0;
         int ndev = 0;
         cudaGetDeviceCount(&ndev);
         // ranks are the visible devices 0..P-1 of one box (one process per GPU): all of them must be peers of mine
@@ -390,6 +390,17 @@ struct NcclFabric : sg::Fabric {
     {
         if (count) GB_NCCL(ncclAllReduce(buf, buf, count, elem_bytes == 8 ? ncclUint64 : ncclUint32, ncclSum, c->nccl, c->stream));
         return GB_OK;
+    }
+    double t_last = 0;
+    void tick(const char *what) override
+    {
+        if (!g_tune.trace) return;
+        cudaStreamSynchronize(c->stream);
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        const double now = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+        if (c->rank == 0 && t_last > 0) fprintf(stderr, "[sgraph] %-32s +%8.3f ms\n", what, now - t_last);
+        t_last = now;
     }
 };
 
@@ -541,8 +552,7 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     const int64_t win_max = fixed ? std::max<int64_t>(0, (int64_t)len0 - k + 1) : (255 - k + 1);
     // batches: enough of them to overlap exchange with upsert, bounded staging memory (<= 2^26 k-mers = 512 MiB each)
     int64_t batch_reads = std::max<int64_t>(TILE_READS, (((int64_t)1 << 26) / std::max<int64_t>(win_max, 1)) / TILE_READS * TILE_READS);
-    int want_batches = 2;
-    if (const char *e = getenv("GENOME_B200_BATCHES")) want_batches = std::max(1, atoi(e));
+    const int want_batches = g_tune.batches > 0 ? (int)g_tune.batches : 2;
     int64_t part = ((n_reads + want_batches - 1) / want_batches + TILE_READS - 1) / TILE_READS * TILE_READS;
     if (part >= TILE_READS * 64) batch_reads = std::min(batch_reads, part);
     int64_t batches = n_reads ? (n_reads + batch_reads - 1) / batch_reads : 0;
@@ -551,13 +561,13 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     // P = 2: 16 slices/shard 4.1 ms, 64 slices/shard 6.0 ms per 96.6 M k-mers.  Below 8 slices the upsert leaves L2.
     while (lp > 3 && (P << lp) > 32) lp--;
     while (lp > 0 && (P << lp) > 128) lp--; // stay in the staged (sector-coalesced) regime
-    if (const char *e = getenv("GENOME_B200_LP")) lp = std::min<int64_t>(lp, std::max(0, atoi(e)));
+    if (g_tune.slice_bits >= 0) lp = std::min<int64_t>(lp, g_tune.slice_bits);
     // Routing levels.  ONE: the wire buckets are (owner, table slice) and the receiver upserts them as they arrive --
     // fewest passes, but #buckets = P x slices must stay small for NVLink (long store runs), so slices grow with the
     // shard.  TWO: the wire buckets are owners only (longest runs) and the receiver re-buckets each batch by fine slice
     // (one more local pass over 8 B keys) -- keeps the upsert L2-resident for multi-GB shards.
     int64_t two_level = (int64_t)(sizeof(Slot) * m->cap > (4ull << 30));
-    if (const char *e = getenv("GENOME_B200_ROUTE")) two_level = !strcmp(e, "two") ? 1 : (!strcmp(e, "one") ? 0 : two_level);
+    if (g_tune.route) two_level = g_tune.route == 2;
     GB_TRY(all_reduce_i64(c, &two_level, ncclMax));
     if (two_level) lp = 0;
     GB_TRY(all_reduce_i64(c, &batches, ncclMax));
@@ -570,7 +580,7 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     pl.lp_bits = (int)lp;
     const int LP = 1 << pl.lp_bits, NB = pl.nb();
 
-    const bool trace = getenv("GENOME_B200_TRACE") && c->rank == 0;
+    const bool trace = g_tune.trace && c->rank == 0;
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_begin = now_ms();
     if (trace) fprintf(stderr, "[pmap] %lld reads, %lld batches of %lld, LP=%d\n", (long long)n_reads, (long long)batches, (long long)batch_reads, LP);
@@ -832,9 +842,8 @@ int gb_pmap_create(gb_comm *ch, int k, int64_t min_capacity_per_shard, uint32_t 
     Comm *c = reinterpret_cast<Comm *>(ch);
     GB_TRY(gb_map_create(k, min_capacity_per_shard, c->device, flags, out));
     reinterpret_cast<Map *>(*out)->comm = c;
-    // every rank reads the same environment: the ownership rule is a property of the whole sharded map
-    const char *wire = getenv("GENOME_B200_WIRE");
-    if (wire && !strcmp(wire, "superkmer")) reinterpret_cast<Map *>(*out)->owner_mode = 1;
+    // every rank must be tuned alike: the ownership rule is a property of the whole sharded map
+    if (g_tune.wire_superkmer) reinterpret_cast<Map *>(*out)->owner_mode = 1;
     return GB_OK;
 }
 
@@ -1007,7 +1016,7 @@ int gb_pmap_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, 
 // filtered table on every rank, and the single-GPU build runs on the replica (identical result on every rank).
 int gb_pmap_graph_build(gb_map *h, gb_graph **out)
 {
-    const bool trace = getenv("GENOME_B200_TRACE") != nullptr;
+    const bool trace = g_tune.trace != 0;
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_begin = now_ms();
     auto tick = [&](const char *what) { if (trace) fprintf(stderr, "[pgraph] %-26s %9.3f ms\n", what, now_ms() - t_begin); };
@@ -1023,8 +1032,7 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
     GB_TRY(all_reduce_i64(c, &dual, ncclMax));
     // GENOME_B200_PGRAPH=sharded: no replica -- minimizer re-routing, rank-local list ranking, segment list (sgraph.cuh).
     // Needs peer access between all ranks; every rank reads the same environment, so the choice is collective.
-    const char *mode = getenv("GENOME_B200_PGRAPH");
-    if (mode && !strcmp(mode, "sharded") && P <= sg::MAXR) {
+    if (g_tune.pgraph_sharded && P <= sg::MAXR) {
         GB_TRY(ensure_inboxes(c, 0)); // settles c->p2p (collective)
         if (c->p2p == 1) {
             GB_CUDA(cudaStreamSynchronize(m->stream));

@@ -34,6 +34,25 @@ void note_launch();
         if (_r != GB_OK) return _r; \
     } while (0)
 
+// ---------------------------------------------------------------- tuning and test hooks (gb_tune, include/genome_b200.h)
+// The library reads no environment variables on its data path.  Every choice below has a measured default;
+// the others exist so that the parity tests can force a path that small inputs would not take by themselves.
+struct Tuning {
+    long long insert_path = 0;          // 0 = by table size, 1 = direct (fused extract + upsert), 2 = L2-blocked (bucket pass + slice-ordered upsert)
+    long long single_pass = 1;          // L2-blocked insert on one GPU: bucket pass without a count pass (per-(bucket, CTA) slabs)
+    long long single_pass_min = 1 << 20; // ... for batches of at least this many k-windows (smaller ones: the slabs would dwarf the batch)
+    long long slice_bits = -1;          // table slices of the L2-blocked insert = 2^slice_bits; -1 = from the table size (64 MiB slices)
+    long long batches = 0;              // sub-batches of one insert call; 0 = default (1 on one GPU, 2 sharded)
+    long long h2d_chunks = 4;           // host insert: chunks of the host-to-device copy overlapped with the bucket pass
+    long long prefetch = 0;             // slice-ordered upsert asks L2 for the next table slice while it fills the current one
+    long long route = 0;                // sharded insert: 0 = by shard size, 1 = one level (owner, slice) on the wire, 2 = two levels
+    long long a2a_nccl = 0;             // sharded insert: staged ncclSend/ncclRecv instead of stores into the peers' inboxes
+    long long wire_superkmer = 0;       // sharded maps created from now on: minimizer owners, 16-byte super-k-mer records on the wire
+    long long pgraph_sharded = 0;       // Graph.buildGraph over shards without a replica (sgraph.cuh)
+    long long trace = 0;                // phase timings on stderr
+};
+extern Tuning g_tune;
+
 // ---------------------------------------------------------------- table layout
 // One 16-byte slot per key: a 32-byte DRAM sector holds two slots, so the key compare, the count
 // update and the graph-phase vertex id of one k-mer touch exactly one sector.
@@ -363,6 +382,10 @@ struct Map {
     cudaStream_t stream = nullptr;      // every mutating call is asynchronous on this stream
     cudaStream_t copy_stream = nullptr; // high priority: the bucket pass of an overlapped (sub-batched) insert
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, t0 = nullptr, t1 = nullptr;
+    cudaEvent_t fev[4] = { nullptr, nullptr, nullptr, nullptr }; // phase boundaries of deleteAll / Graph.buildGraph (gb_map_phase_ns)
+    int64_t filter_ns[2] = { 0, 0 };   // last deleteAll: table sweep (compact_survivors_kernel), re-insert of the survivors
+    int64_t slots_swept = 0;           // slots the last deleteAll streamed
+    int64_t graph_ns[4] = { 0, 0, 0, 0 }; // last Graph.buildGraph on this map: membership probes, list ranking (ns), jump launches, vertices
     // scratch
     unsigned long long *d_counters = nullptr; // [0] new keys [1] survivors / exported [2] stream flags [3] k-windows
     unsigned long long *d_spread = nullptr;   // spread new-key tallies of insert_keys_kernel (partition.cu)

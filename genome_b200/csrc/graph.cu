@@ -797,7 +797,7 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
     const unsigned long long slots = bits;
     cudaEvent_t ev0 = m->ev0, ev1 = m->ev1;
     GB_CUDA(cudaEventRecord(ev0, st));
-    const bool trace = getenv("GENOME_B200_TRACE") != nullptr;
+    const bool trace = g_tune.trace != 0;
     auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const double t_begin = now_ms();
     auto tick = [&](const char *what) {
@@ -835,6 +835,7 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
     g->stats[0] = (int64_t)n;
     struct { const unsigned long long *p; } keys{ keys_p };
     tick("assigned vertices");
+    GB_CUDA(cudaEventRecord(m->fev[0], st));
     // ---- in/out masks and unique neighbours
     Tmp<uint8_t> mask8;
     Tmp<unsigned int> nbr_out, nbr_in;
@@ -845,8 +846,9 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
         // sharded build: this rank probes only its own range of the (identical) key array, then the ranks exchange ranges
         const unsigned long long lo = sp ? sp->lo : 0, cnt = sp ? sp->hi - sp->lo : n;
         // the fingerprint array is built together with the vertex array (deleteAll / replica insert)
-        const uint8_t *fp = given && !getenv("GENOME_B200_NO_FP") ? m->fp : nullptr;
+        const uint8_t *fp = given ? m->fp : nullptr;
         LAUNCH(masks_kernel<V210>, cnt, m->table, bits, k, dual, keys.p, lo, cnt, given, fp, mask8.p, nbr_out.p, nbr_in.p);
+        GB_CUDA(cudaEventRecord(m->fev[1], st));
         if (sp) {
             GB_CUDA(cudaStreamSynchronize(st));
             GB_TRY(sp->gather(sp->ctx, mask8.p, 1));
@@ -892,6 +894,7 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
     // ---- list ranking: rank of every interior vertex from the head of its chain + the chain's edge id
     int rounds = 0, bound = 2;
     while ((1ull << (bound - 2)) < n2 + 1) bound++; // ceil(log2) + slack; each launch makes >= 1 jump
+    GB_CUDA(cudaEventRecord(m->fev[2], st));
     unsigned long long pending = 1;
     while (pending && rounds < bound) {
         GB_CUDA(cudaMemsetAsync(total.p + 2, 0, 8, st));
@@ -900,6 +903,7 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
         rounds++;
     }
     g->stats[1] = rounds;
+    GB_CUDA(cudaEventRecord(m->fev[3], st));
 
     tick("list ranking");
     // ---- edge ends and lengths, base offsets, bases
@@ -925,6 +929,12 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
     float ms = 0;
     GB_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     g->stats[3] = (int64_t)(ms * 1e6);
+    GB_CUDA(cudaEventElapsedTime(&ms, m->fev[0], m->fev[1]));
+    m->graph_ns[0] = (int64_t)(ms * 1e6); // masks_kernel (membership probes)
+    GB_CUDA(cudaEventElapsedTime(&ms, m->fev[2], m->fev[3]));
+    m->graph_ns[1] = (int64_t)(ms * 1e6); // list ranking: all jump_kernel launches
+    m->graph_ns[2] = rounds;
+    m->graph_ns[3] = (int64_t)n;
     return GB_OK;
 }
 

@@ -34,6 +34,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 }
 
 thread_local Arena *tl_arena = nullptr;
+Tuning g_tune;
 
 // ---- arena block cache (see common.cuh): at most CACHE_SLOTS blocks, best fit, per device
 namespace {
@@ -84,10 +85,8 @@ void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int pool_setup(int)
 {
     // Random 16-byte slot accesses use one 32-byte sector of a 128-byte L2 line: ask L2 not to fetch the neighbours
-    // (a hint; on B200 it changes nothing measurable: ncu r1a shows 128 B per miss either way).  GENOME_B200_L2_FETCH overrides.
-    size_t gran = 32;
-    if (const char *e = getenv("GENOME_B200_L2_FETCH")) gran = (size_t)atoi(e);
-    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    // (a hint; on B200 it changes nothing measurable: ncu r1a shows 128 B per miss either way).
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     cudaGetLastError();
     return GB_OK;
 }
@@ -148,22 +147,18 @@ insert_reads_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes,
     }
 }
 
-// empirical random-access ceiling (R_gups): what the insert kernel does to the table with hashing,
-// probing and extraction stripped away -- one 8-byte key read and one 4-byte red.add per update, 8 updates per
-// thread in flight, addresses uniform over the table.
+// empirical random-access ceiling (R_gups): ONE random 64-bit atomicAdd (no return value: a RED) per element
+// over an array of the table's size; no hashing of keys, no probing, no preceding load; 8 updates per thread in flight.
 __global__ void __launch_bounds__(256)
-random_atomics_kernel(Slot *table, unsigned long long mask, long long n, unsigned long long seed)
+random_atomics_kernel(unsigned long long *words, unsigned long long n_words, long long n, unsigned long long seed)
 {
     long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
-    unsigned long long idx[8], cur[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) idx[j] = mix64((unsigned long long)(i0 + j) * 0x9E3779B97F4A7C15ull + seed) & mask;
 #pragma unroll
     for (int j = 0; j < 8; j++)
-        if (i0 + j < n) cur[j] = load_key(table + idx[j]);
-#pragma unroll
-    for (int j = 0; j < 8; j++)
-        if (i0 + j < n) red_add_s32(&table[idx[j]].count, (int)(cur[j] & 1) + 1);
+        if (i0 + j < n) {
+            const unsigned long long idx = __umul64hi(mix64((unsigned long long)(i0 + j) * 0x9E3779B97F4A7C15ull + seed), n_words);
+            atomicAdd(words + idx, 1ull);
+        }
 }
 
 // every record of a fixed-stride stream must carry the same length byte; counters[2] != 0 otherwise
@@ -491,23 +486,12 @@ int map_verify_fixed(Map *m, const uint8_t *d_bin, unsigned int rec, unsigned in
     return GB_OK;
 }
 
-// the single-pass variants (GENOME_B200_COUNTLESS) leave small batches to the counted passes: below this many k-windows the
-// slabs (one per bucket and CTA, each at least 128 keys) would dwarf the batch.  GENOME_B200_COUNTLESS_MIN lowers it for tests.
-static int64_t countless_min()
-{
-    const char *e = getenv("GENOME_B200_COUNTLESS_MIN");
-    return e ? std::max<int64_t>(1, atoll(e)) : ((int64_t)1 << 20);
-}
+// the single-pass bucket pass leaves small batches to the counted passes: below g_tune.single_pass_min k-windows the slabs
+// (one per bucket and CTA, each at least 128 keys) would dwarf the batch
+static int64_t countless_min() { return std::max<int64_t>(1, g_tune.single_pass_min); }
 
 // 0 = choose by table size, 1 = direct (fused extract + upsert, random access), 2 = partitioned (L2-blocked)
-static int insert_mode()
-{
-    const char *e = getenv("GENOME_B200_INSERT");
-    if (!e) return 0;
-    if (!strcmp(e, "direct")) return 1;
-    if (!strcmp(e, "partitioned")) return 2;
-    return 0;
-}
+static int insert_mode() { return (int)g_tune.insert_path; }
 
 // L2-blocked insert of reads [read0, read0 + n_reads): bucket the canonical k-mers by table slice (count, scatter),
 // upsert slice by slice.  The range is cut into sub-batches and pipelined over two staging halves: the bucket pass of
@@ -532,23 +516,24 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
     PartLayout pl;
     pl.owners = 1;
     pl.lp_bits = slice_bits_for(m->cap, 1);
-    if (const char *e = getenv("GENOME_B200_LP")) pl.lp_bits = std::max(0, std::min(pl.lp_bits + 3, atoi(e)));
+    if (g_tune.slice_bits >= 0) pl.lp_bits = (int)std::max<long long>(0, std::min<long long>(pl.lp_bits + 3, g_tune.slice_bits));
+    while ((1 << pl.lp_bits) > 128) pl.lp_bits--;
 
     // sub-batches of whole persistent-grid waves of tiles, about four of them
     const int64_t tiles = (n_reads + TILE_READS - 1) / TILE_READS, grid = work[0]->grid;
     // measured on C2 (one B200): 1 / 2 / 4 / 8 sub-batches = 2.95 / 3.13 / 3.20 / 3.93 ms -- on ONE GPU the two passes
     // fight for the same SM slots and L2, so the default is no overlap; GENOME_B200_BATCHES turns the pipeline on
-    int want = 1;
-    if (const char *e = getenv("GENOME_B200_BATCHES")) want = std::max(1, atoi(e));
+    const int want = (int)std::max<long long>(1, g_tune.batches);
     int64_t per_tiles = std::max<int64_t>(1, (tiles / want + grid / 2) / grid) * grid;
     if (tiles < 2 * grid || want == 1) per_tiles = tiles;
     const int64_t per_reads = per_tiles * TILE_READS;
     const int64_t n_sub = (n_reads + per_reads - 1) / per_reads;
     int64_t half = 0; // keys per staging half
     for (int64_t s = 0; s < n_sub; s++) half = std::max(half, win_upper(read0 + s * per_reads, read0 + std::min(n_reads, (s + 1) * per_reads)));
-    // GENOME_B200_COUNTLESS=1 (one sub-batch only): no count pass, per-(bucket, CTA) slabs instead of exact bucket ranges
+    // single pass (one sub-batch only): no count pass, per-(bucket, CTA) slabs instead of exact bucket ranges.  Measured on C2
+    // (profiles/r2a_bench_*.json): bucket pass 0.995 -> 0.765 ms, upsert over the slab chunks 1.83 -> 1.95 ms
     const unsigned int nbk = (unsigned int)pl.nb();
-    const unsigned int slab = getenv("GENOME_B200_COUNTLESS") && n_sub == 1 && pl.owners == 1 && nbk <= 128 && half >= countless_min()
+    const unsigned int slab = g_tune.single_pass && n_sub == 1 && pl.owners == 1 && nbk <= 128 && half >= countless_min()
                                   ? slab_keys_for(slab_cta_keys(n_reads, (unsigned long long)half, (int)grid), nbk, (int)grid) : 0;
     const size_t slab_keys = (size_t)slab * nbk * (size_t)grid, n_slab_chunks = (size_t)nbk * (size_t)grid;
     GB_TRY(map_stage(m, slab ? slab_keys + 2 * n_slab_chunks + 8 : (size_t)((n_sub > 1 ? 2 : 1) * (half + 8))));
@@ -587,13 +572,13 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
         unsigned long long total = (unsigned long long)wu;
         if (slab) {
             // the chunk table holds the exact count on the device (keys in slabs; overflowed keys were upserted by the bucket pass)
-            GB_TRY(insert_key_chunks(m, keys, d_desc, d_desc + n_slab_chunks + 1, (int)n_slab_chunks, total, up, true));
+            GB_TRY(insert_key_chunks(m, keys, d_desc, d_desc + n_slab_chunks + 1, (int)n_slab_chunks, total, up, true, g_tune.prefetch ? pl.lp_bits : 0));
         } else {
         if (!bound_is_exact) { // record lengths are only on the device: fetch the count (stalls the pipeline; rare path)
             GB_CUDA(cudaMemcpyAsync(&total, work[h]->bucket_base + pl.nb(), 8, cudaMemcpyDeviceToHost, bk));
             GB_CUDA(cudaStreamSynchronize(bk));
         }
-        GB_TRY(insert_key_chunks(m, keys, d_desc, d_desc + 2, 1, total, up));
+        GB_TRY(insert_key_chunks(m, keys, d_desc, d_desc + 2, 1, total, up, false, g_tune.prefetch && n_sub == 1 ? pl.lp_bits : 0));
         }
         if (m->n_pup + 2 <= 16) {
             GB_CUDA(cudaEventRecord(m->pup[m->n_pup + 1], up));
@@ -689,17 +674,17 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
     return GB_OK;
 }
 
-// gb_map_insert_reads with GENOME_B200_COUNTLESS=1 on a fixed-stride HOST stream: the host-to-device copy is cut into chunks
+// gb_map_insert_reads on a fixed-stride HOST stream (single-pass bucket pass): the host-to-device copy is cut into chunks
 // (copy stream) and the single-pass bucket pass of chunk c (map stream) runs while chunk c + 1 is still on the wire.  Nothing
 // touches the table before every chunk has been verified: keys go to the slabs or to the overflow list (LIST mode of
 // partition.cu), and the upsert starts after the last chunk.  *handled = false: conditions not met, or the stream turned
 // out ragged / the overflow list filled up -- the table is untouched and the caller takes the ordinary path.
-// Written after this round's GPU budget was spent; opt-in, tests/test_countless_gpu.py.
+// Measured on C2 (profiles/r2a_bench_*.json): 4.45 -> 3.88 ms per step from a pinned host buffer.
 static int insert_host_pipelined(Map *m, const uint8_t *bin, int64_t n_reads, unsigned int rec, unsigned int len0, int64_t *n_windows,
                                  bool *handled)
 {
     *handled = false;
-    if (!getenv("GENOME_B200_COUNTLESS") || (int)len0 < m->k) return GB_OK;
+    if (!g_tune.single_pass || (int)len0 < m->k) return GB_OK;
     const int64_t per_read = (int64_t)len0 - m->k + 1, want = n_reads * per_read;
     if (want < countless_min() || want > ((int64_t)1 << 28)) return GB_OK; // small: not worth it; large: the ordinary path batches
     int64_t budget = 0;
@@ -716,8 +701,7 @@ static int insert_host_pipelined(Map *m, const uint8_t *bin, int64_t n_reads, un
     const unsigned int nb = (unsigned int)pl.nb();
     if (nb > 128) return GB_OK;
     const unsigned long long ovf_cap = (unsigned long long)want / 16 + 65536;
-    int n_copy = 4;
-    if (const char *e = getenv("GENOME_B200_H2D_CHUNKS")) n_copy = std::max(1, std::min(16, atoi(e)));
+    const int n_copy = (int)std::max<long long>(1, std::min<long long>(16, g_tune.h2d_chunks));
     const int64_t per_chunk = std::max<int64_t>(TILE_READS, ((n_reads + n_copy - 1) / n_copy + TILE_READS - 1) / TILE_READS * TILE_READS);
     // every chunk is its own launch and deals its tiles to the CTAs from CTA 0 on: a CTA sees the sum of its shares
     unsigned long long cta_keys = 0;
@@ -903,6 +887,8 @@ int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_ma
         if ((r = cudaEventCreate(&m->ev1) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
         if ((r = cudaEventCreate(&m->t0) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
         if ((r = cudaEventCreate(&m->t1) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
+        for (int i = 0; i < 4 && r == GB_OK; i++) r = cudaEventCreate(&m->fev[i]) == cudaSuccess ? GB_OK : GB_E_CUDA;
+        if (r) break;
         if ((r = cudaMalloc((void **)&m->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess ? GB_OK : GB_E_OOM)) break;
         {
             Slot *none = nullptr;
@@ -938,6 +924,8 @@ int gb_map_destroy(gb_map *h)
     if (m->d_spread) cudaFree(m->d_spread);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
+    for (int i = 0; i < 4; i++)
+        if (m->fev[i]) cudaEventDestroy(m->fev[i]);
     for (int i = 0; i < 4; i++)
         if (m->pe[i]) cudaEventDestroy(m->pe[i]);
     if (m->part) { m->part->release(); delete m->part; }
@@ -1148,10 +1136,19 @@ int gb_map_delete_below(gb_map *h, int32_t min_count)
     GB_TRY(map_stage(m, (size_t)m->size + (size_t)(m->size + 1) / 2));
     unsigned long long *sk = m->stage;
     int *sv = reinterpret_cast<int *>(m->stage + m->size);
+    GB_CUDA(cudaEventRecord(m->fev[0], m->stream));
     compact_survivors_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(m->table, n, min_count, sk, sv, m->d_counters);
     GB_LAUNCHED();
+    GB_CUDA(cudaEventRecord(m->fev[1], m->stream));
     unsigned long long c[4];
     GB_TRY(map_read_counters(m, c));
+    {
+        float ms = 0;
+        GB_CUDA(cudaEventElapsedTime(&ms, m->fev[0], m->fev[1]));
+        m->filter_ns[0] = (int64_t)(ms * 1e6);
+        m->filter_ns[1] = 0;
+        m->slots_swept = (int64_t)n;
+    }
     int64_t keep = (int64_t)c[1];
     if (keep == m->size) return GB_OK;
     // a fresh table sized for the survivors
@@ -1163,7 +1160,10 @@ int gb_map_delete_below(gb_map *h, int32_t min_count)
     GB_TRY(map_zero_counters(m));
     // survivors are distinct: their index in the compacted array becomes their vertex id (Graph.buildGraph skips numbering)
     const bool as_vertices = keep < (1ll << 30);
+    GB_CUDA(cudaEventRecord(m->fev[2], m->stream));
     GB_TRY(map_launch_update_set(m, sk, sv, keep, m->stream, as_vertices));
+    GB_CUDA(cudaEventRecord(m->fev[3], m->stream));
+    m->filter_ns[1] = -1; // resolved lazily by gb_map_phase_ns (the call stays asynchronous)
     m->size = keep;
     m->kept_keys = sk;
     m->kept_n = keep;
@@ -1219,6 +1219,37 @@ int gb_map_clear(gb_map *h, int64_t min_capacity)
 
 long long gb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+static long long *tune_field(const char *name)
+{
+    static const struct { const char *name; long long Tuning::*field; } table[] = {
+        { "insert_path", &Tuning::insert_path }, { "single_pass", &Tuning::single_pass }, { "single_pass_min", &Tuning::single_pass_min },
+        { "slice_bits", &Tuning::slice_bits }, { "batches", &Tuning::batches }, { "h2d_chunks", &Tuning::h2d_chunks },
+        { "prefetch", &Tuning::prefetch }, { "route", &Tuning::route }, { "a2a_nccl", &Tuning::a2a_nccl },
+        { "wire_superkmer", &Tuning::wire_superkmer }, { "pgraph_sharded", &Tuning::pgraph_sharded }, { "trace", &Tuning::trace },
+    };
+    if (name)
+        for (const auto &e : table)
+            if (!strcmp(name, e.name)) return &(g_tune.*(e.field));
+    return nullptr;
+}
+
+int gb_tune(const char *name, int64_t value, int64_t *previous)
+{
+    long long *f = tune_field(name);
+    if (!f) { set_error("unknown tuning key '%s'", name ? name : "(null)"); return GB_E_ARG; }
+    if (previous) *previous = *f;
+    *f = value;
+    return GB_OK;
+}
+
+int gb_tune_get(const char *name, int64_t *value)
+{
+    long long *f = tune_field(name);
+    if (!f || !value) { set_error("unknown tuning key '%s'", name ? name : "(null)"); return GB_E_ARG; }
+    *value = *f;
+    return GB_OK;
+}
+
 int gb_timer_start(gb_map *h)
 {
     Map *m;
@@ -1252,20 +1283,19 @@ int gb_bench_random_atomics(int device, size_t table_bytes, int64_t n_updates, i
 {
     if (!ns_per_iter || table_bytes < 1024 || n_updates <= 0 || iters <= 0) { set_error("bad arguments"); return GB_E_ARG; }
     GB_CUDA(cudaSetDevice(device));
-    unsigned long long slots = 1;
-    while (slots * 2 * sizeof(Slot) <= table_bytes) slots *= 2;
-    Slot *t = nullptr;
-    GB_CUDA(cudaMalloc((void **)&t, slots * sizeof(Slot)));
-    GB_CUDA(cudaMemset(t, 0, slots * sizeof(Slot)));
+    const unsigned long long words = table_bytes / 8; // the table's actual size, not rounded to a power of two
+    unsigned long long *t = nullptr;
+    GB_CUDA(cudaMalloc((void **)&t, words * 8));
+    GB_CUDA(cudaMemset(t, 0, words * 8));
     cudaEvent_t e0, e1;
     GB_CUDA(cudaEventCreate(&e0));
     GB_CUDA(cudaEventCreate(&e1));
     unsigned int grid = (unsigned int)((n_updates + 256 * 8 - 1) / (256 * 8));
-    random_atomics_kernel<<<grid, 256>>>(t, slots - 1, n_updates, 1);
+    random_atomics_kernel<<<grid, 256>>>(t, words, n_updates, 1);
     GB_LAUNCHED();
     GB_CUDA(cudaEventRecord(e0));
     for (int i = 0; i < iters; i++) {
-        random_atomics_kernel<<<grid, 256>>>(t, slots - 1, n_updates, 2 + i);
+        random_atomics_kernel<<<grid, 256>>>(t, words, n_updates, 2 + i);
         GB_LAUNCHED();
     }
     GB_CUDA(cudaEventRecord(e1));
@@ -1276,6 +1306,29 @@ int gb_bench_random_atomics(int device, size_t table_bytes, int64_t n_updates, i
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     GB_CUDA(cudaFree(t));
+    return GB_OK;
+}
+
+int gb_map_phase_ns(gb_map *h, int64_t ns[8])
+{
+    Map *m;
+    GB_TRY(check_map(h, &m));
+    if (!ns) { set_error("null argument"); return GB_E_ARG; }
+    if (m->filter_ns[1] < 0) {
+        GB_CUDA(cudaEventSynchronize(m->fev[3]));
+        float ms = 0;
+        GB_CUDA(cudaEventElapsedTime(&ms, m->fev[2], m->fev[3]));
+        m->filter_ns[1] = (int64_t)(ms * 1e6);
+    }
+    memset(ns, 0, 8 * sizeof(int64_t));
+    ns[0] = m->phase_ns[0] + m->phase_ns[1]; // L2-blocked insert: bucket pass
+    ns[1] = m->phase_ns[2];                  // L2-blocked insert: slice-ordered upsert
+    ns[2] = m->filter_ns[0];                 // deleteAll: table sweep
+    ns[3] = m->filter_ns[1];                 // deleteAll: survivors into their new table
+    ns[4] = m->slots_swept;                  // slots the sweep streamed (16 B each)
+    ns[5] = m->graph_ns[0];                  // Graph.buildGraph: membership probes (masks_kernel)
+    ns[6] = m->graph_ns[1];                  // Graph.buildGraph: list ranking (all jump_kernel launches)
+    ns[7] = m->graph_ns[2];                  // ... and how many launches that took
     return GB_OK;
 }
 

@@ -311,32 +311,21 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
 
 // ---------------------------------------------------------------- bulk upsert from key ranges
 constexpr int IK_THREADS = 256;
+constexpr int IK_PER_THREAD = 4; // measured 2 / 4 / 8 / 16 keys per thread: 1.78 / 1.80 / 2.07 / 3.70 ms on C2
 
 // No CTA barrier anywhere: every thread finds its own chunk, every warp adds its new-key count to one of SPREAD
 // global counters (fold_new_keys_kernel sums them into counters[0] afterwards).
-// claim an EMPTY slot and give it count 1 in ONE 128-bit compare-and-swap (the slot is 16 bytes: key | count | vid; an untouched
-// slot is {EMPTY_KEY, 0, NONE32}, init_table_kernel).  Returns the key that was there (EMPTY_KEY = claimed), *exact = the rest
-// matched too.  sm_90+: atom.cas.b128.
-__device__ __forceinline__ unsigned long long claim_slot_128(Slot *slot, unsigned long long key, bool *won)
-{
-    const unsigned long long exp_hi = (unsigned long long)NONE32 << 32, new_hi = ((unsigned long long)NONE32 << 32) | 1ull;
-    unsigned long long old_lo, old_hi;
-    asm volatile("{\n\t.reg .b128 e, n, o;\n\tmov.b128 e, {%2, %3};\n\tmov.b128 n, {%4, %5};\n\tatom.global.cas.b128 o, [%6], e, n;\n\tmov.b128 {%0, %1}, o;\n\t}"
-                 : "=l"(old_lo), "=l"(old_hi)
-                 : "l"(EMPTY_KEY), "l"(exp_hi), "l"(key), "l"(new_hi), "l"(slot)
-                 : "memory");
-    *won = old_lo == EMPTY_KEY && old_hi == exp_hi;
-    return old_lo;
-}
-
+// Measured and dropped (round 2, profiles/r2a_bench_*.json): claiming a new key together with its count by one 128-bit
+// compare-and-swap (1.865 ms against 1.834 ms), CAS-first probing, 2 / 8 / 16 keys per thread.
 // DEV_TOTAL: n_total is only an upper bound (it sized the grid); the exact number of keys is vstart[n_chunks].
-// CLAIM128 (GENOME_B200_CAS128=1): a new key costs load + one 128-bit CAS instead of load + CAS + red (2 L2 transactions
-// instead of 3; new keys are 31 % of the instances on C2).
-template <int IK_PER_THREAD, bool CAS_FIRST, bool DEV_TOTAL, bool CLAIM128 = false>
+// PREFETCH: the keys come in table-slice order (one slice = [slice_lo, slice_lo + slice_slots) of the table); while the
+// resident CTAs work on slice s, each of them asks L2 for its share of slice s + 1 (one 128-byte line per thread), so that
+// the table loads of the next slice hit L2 instead of waiting for DRAM.
+template <bool DEV_TOTAL>
 __global__ void __launch_bounds__(IK_THREADS)
 insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vstart,
                    const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Slot *table, unsigned long long cap,
-                   unsigned long long *spread)
+                   unsigned long long *spread, int prefetch_bits)
 {
     constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
     const unsigned long long v0 = (unsigned long long)blockIdx.x * IK_PER_CTA;
@@ -365,48 +354,34 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
             idx[j] = slot_of(mix64(key[j]), cap);
         }
     }
+    if (prefetch_bits > 0 && ok[0]) {
+        // slice of this CTA's first key, and how far the CTA is through that slice's keys, estimated from the hash itself:
+        // inside a slice the keys are in no particular order, so the share is taken from the CTA's position in the launch
+        const unsigned long long h0 = mix64(key[0]);
+        const unsigned long long slice = h0 >> (64 - prefetch_bits), n_slices = 1ull << prefetch_bits;
+        if (slice + 1 < n_slices) {
+            // slots of slice s: [ceil(s * cap / n_slices) .. ): monotonic slot_of => contiguous
+            const unsigned long long lo = slot_of((slice + 1) << (64 - prefetch_bits), cap);
+            const unsigned long long hi = slice + 2 < n_slices ? slot_of((slice + 2) << (64 - prefetch_bits), cap) : cap;
+            const unsigned long long lines = ((hi - lo) * sizeof(Slot) + 127) / 128;
+            // the CTAs of one slice are about n_total / n_slices / IK_PER_CTA many: CTA number q among them takes lines q, q + that, ...
+            const unsigned long long per_slice = max(1ull, n_total / n_slices / IK_PER_CTA);
+            const unsigned long long q = blockIdx.x % per_slice;
+            const char *base = reinterpret_cast<const char *>(table + lo);
+            for (unsigned long long l = q * IK_THREADS + threadIdx.x; l < lines; l += per_slice * IK_THREADS)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + l * 128));
+        }
+    }
     int nk = 0;
     unsigned long long old[IK_PER_THREAD];
-    if (CLAIM128) {
 #pragma unroll
-        for (int j = 0; j < IK_PER_THREAD; j++)
-            if (ok[j]) cur[j] = load_key(table + idx[j]);
-        bool won[IK_PER_THREAD];
+    for (int j = 0; j < IK_PER_THREAD; j++)
+        if (ok[j]) cur[j] = load_key(table + idx[j]);
+    // the CAS round trips of a thread's keys overlap: all of them are issued before the first result is used
 #pragma unroll
-        for (int j = 0; j < IK_PER_THREAD; j++) {
-            won[j] = false;
-            old[j] = cur[j];
-            if (ok[j] && cur[j] == EMPTY_KEY) old[j] = claim_slot_128(table + idx[j], key[j], &won[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < IK_PER_THREAD; j++) {
-            if (!ok[j]) continue;
-            if (won[j]) nk++;                                                        // claimed with count 1: done
-            else if (old[j] == key[j]) red_add_s32(&table[idx[j]].count, 1);
-            else nk += upsert_add(table, cap, idx[j], old[j], key[j], 1);             // someone else's slot (or not exactly empty): generic path
-        }
-        nk = __reduce_add_sync(0xFFFFFFFFu, nk);
-        if ((threadIdx.x & 31) == 0 && nk)
-            atomicAdd(&spread[(blockIdx.x * (IK_THREADS / 32) + (threadIdx.x >> 5)) & (SPREAD - 1)], (unsigned long long)nk);
-        return;
-    }
-    if (CAS_FIRST) {
-        // one L2 transaction instead of two for a new key: the CAS is the probe (it returns the resident key)
-#pragma unroll
-        for (int j = 0; j < IK_PER_THREAD; j++) {
-            cur[j] = EMPTY_KEY;
-            if (ok[j]) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < IK_PER_THREAD; j++)
-            if (ok[j]) cur[j] = load_key(table + idx[j]);
-        // the CAS round trips of a thread's keys overlap: all of them are issued before the first result is used
-#pragma unroll
-        for (int j = 0; j < IK_PER_THREAD; j++) {
-            old[j] = cur[j];
-            if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
-        }
+    for (int j = 0; j < IK_PER_THREAD; j++) {
+        old[j] = cur[j];
+        if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
     }
 #pragma unroll
     for (int j = 0; j < IK_PER_THREAD; j++) {
@@ -689,7 +664,7 @@ int make_single_chunk(const unsigned long long *d_total, unsigned long long *d_d
 }
 
 int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned long long *d_vstart, const unsigned long long *d_off,
-                      int n_chunks, unsigned long long n_total, cudaStream_t st, bool total_is_upper_bound)
+                      int n_chunks, unsigned long long n_total, cudaStream_t st, bool total_is_upper_bound, int prefetch_bits)
 {
     if (!n_total) return GB_OK;
     m->kept_valid = false;
@@ -697,26 +672,11 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
         GB_CUDA(cudaMalloc((void **)&m->d_spread, SPREAD * 8));
         GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));
     }
-    static int per = 0, cas_first = 0;
-    if (!per) {
-        const char *e = getenv("GENOME_B200_IK");
-        per = e ? atoi(e) : 4;
-        cas_first = getenv("GENOME_B200_CAS_FIRST") != nullptr;
-    }
-#define GB_IK(N, C, D)                                                                                                       \
-    insert_keys_kernel<N, C, D><<<(unsigned int)((n_total + IK_THREADS * N - 1) / (IK_THREADS * N)), IK_THREADS, 0, st>>>(    \
-        d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread)
-    const bool cas128 = getenv("GENOME_B200_CAS128") != nullptr; // read per call: tests switch it inside one process
-    if (cas128) {
-        if (total_is_upper_bound) insert_keys_kernel<4, false, true, true><<<(unsigned int)((n_total + IK_THREADS * 4 - 1) / (IK_THREADS * 4)), IK_THREADS, 0, st>>>(
-            d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread);
-        else insert_keys_kernel<4, false, false, true><<<(unsigned int)((n_total + IK_THREADS * 4 - 1) / (IK_THREADS * 4)), IK_THREADS, 0, st>>>(
-            d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread);
-    } else
-    if (total_is_upper_bound) GB_IK(4, false, true);
-    else if (cas_first) { if (per == 2) GB_IK(2, true, false); else if (per == 8) GB_IK(8, true, false); else GB_IK(4, true, false); }
-    else if (per == 8) GB_IK(8, false, false); else if (per == 2) GB_IK(2, false, false); else GB_IK(4, false, false);
-#undef GB_IK
+    const unsigned int grid = (unsigned int)((n_total + IK_THREADS * IK_PER_THREAD - 1) / (IK_THREADS * IK_PER_THREAD));
+    if (total_is_upper_bound)
+        insert_keys_kernel<true><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread, prefetch_bits);
+    else
+        insert_keys_kernel<false><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread, prefetch_bits);
     GB_LAUNCHED();
     fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
     GB_LAUNCHED();

@@ -614,6 +614,7 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
         }
     }
 
+    fab.tick("owners counted");
     // ---- 2. peer windows, keys to their owners, index
     std::vector<size_t> wbytes(P);
     for (int r = 0; r < P; r++) wbytes[r] = WindowLayout(n_of[r]).bytes;
@@ -665,6 +666,7 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
     }
     GB_TRY(fab.barrier());
 
+    fab.tick("windows + re-routing + index");
     // ---- 3. masks
     std::vector<Local> loc(nl);
     std::vector<u32 *> nbr_out(nl), nbr_in(nl);
@@ -678,6 +680,7 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
     }
     GB_TRY(fab.barrier());
 
+    fab.tick("masks");
     // ---- 4. classify, numbering
     std::vector<u64> tot((size_t)nl * 3), tot_all((size_t)nl * 3 * P);
     for (int l = 0; l < nl; l++) {
@@ -711,6 +714,7 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
         return GB_E_CAPACITY;
     }
 
+    fab.tick("classify + scans");
     // ---- 5. the global arrays of this process, vertex entries, first step of every edge
     Exec &ex0 = *in[0].ex;
     Global G;
@@ -737,6 +741,7 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
     }
     GB_TRY(fab.barrier());
 
+    fab.tick("vertices + edge starts");
     // ---- 6. list ranking over local links
     int jump_rounds = 0;
     for (int l = 0; l < nl; l++) {
@@ -757,6 +762,7 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
     }
     GB_TRY(fab.barrier());
 
+    fab.tick("local list ranking");
     // ---- 7. segment list: fill, gather, rank, fold back
     int seg_rounds = 0;
     {
@@ -788,6 +794,7 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
         }
     }
 
+    fab.tick("segments");
     // ---- 8. edge ends and lengths
     std::vector<u64> cyc(nl, 0), cyc_all((size_t)nl * P);
     for (int l = 0; l < nl; l++) {
@@ -811,6 +818,7 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
     GB_TRY(fab.allreduce_sum(G.edge_end, (size_t)E, 4));
     GB_TRY(fab.allreduce_sum(G.edge_len, (size_t)E, 8));
 
+    fab.tick("edges closed + array sums");
     // ---- 9. offsets and bases
     u64 *edge_len;
     GB_TRY(sg_new(ex0, &edge_len, (size_t)E + 1));
@@ -825,6 +833,7 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
     for (int l = 0; l < nl; l++) GB_TRY(sg_sync(*in[l].ex));
     GB_TRY(fab.allreduce_sum(G.bases, base_words(n_bases), 4));
     GB_TRY(fab.barrier()); // nobody releases its window while a peer may still read it
+    fab.tick("bases written + summed");
 
     res->node_kmer = G.node_kmer; res->edge_start = G.edge_start; res->edge_end = G.edge_end;
     res->edge_off = G.edge_len; res->bases = G.bases;

@@ -38,6 +38,8 @@ struct Fabric {
     // the process's copy of a global output array: element-wise sum over the processes (one writer per element).  The
     // ranks of one process share their copy, so the single-process form has nothing to do.
     virtual int allreduce_sum(void *buf, size_t count, int elem_bytes) = 0;
+    // phase marker of sg::build (debugging aid: the NCCL fabric prints elapsed times when gb_tune("trace") is set)
+    virtual void tick(const char *) {}
 };
 
 } // namespace sg

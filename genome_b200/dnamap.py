@@ -253,6 +253,13 @@ class _MapBase:
                     bucket_ns=s[6], upsert_ns=s[7])
 
 
+    def phase_ns(self):
+        s = (C.c_int64 * 8)()
+        capi.check(capi.lib().gb_map_phase_ns(self.h, s))
+        return dict(bucket_ns=s[0], upsert_ns=s[1], filter_sweep_ns=s[2], filter_reinsert_ns=s[3], slots_swept=s[4],
+                    graph_masks_ns=s[5], graph_rank_ns=s[6], graph_jump_launches=s[7])
+
+
 class ArrayDNAMap(_MapBase):
     """new ArrayDNAMap[Int](k) (S/ds/ArrayDNAMap.scala:62-72): one open-addressing table in one GPU's HBM."""
 

@@ -41,9 +41,17 @@ typedef struct gb_graph_map gb_graph_map; /* DNAMap[GraphPosition] as built by G
 const char *gb_last_error(void);
 /* diagnostics: kernels launched by this library in this process so far */
 long long gb_launch_count(void);
-/* diagnostics: empirical random-access ceiling of a table of table_bytes (one 8-byte key read + one 4-byte
- * red.add per update, no hashing or probing): ns per pass of n_updates, averaged over iters passes */
+/* diagnostics: empirical random-access ceiling R_gups of SURVEY 8(d): a bare kernel doing ONE random 64-bit atomicAdd per
+ * element over an array of exactly table_bytes (no hashing, no probing, no preceding load): ns per pass of n_updates,
+ * averaged over iters passes */
 int gb_bench_random_atomics(int device, size_t table_bytes, int64_t n_updates, int iters, int64_t *ns_per_iter);
+/* tuning and test hooks (process-wide; not part of the reference surface).  The library reads no environment variable on
+ * its data path: every default is a measured choice, and the parity tests use these keys to force a path that
+ * small inputs would not take by themselves.  Keys: insert_path (0 auto, 1 direct, 2 L2-blocked), single_pass,
+ * single_pass_min, slice_bits, batches, h2d_chunks, prefetch, route (0 auto, 1 one level, 2 two levels), a2a_nccl,
+ * wire_superkmer, pgraph_sharded, trace.  *previous (optional) receives the old value. */
+int gb_tune(const char *name, int64_t value, int64_t *previous);
+int gb_tune_get(const char *name, int64_t *value);
 int gb_version(void);
 int gb_device_count(int *n);
 
@@ -110,8 +118,13 @@ int gb_sync(gb_map *m);
 /* counters: [0] capacity (slots) [1] table bytes [2] rehash/grow count [3] windows inserted so far
  * [4] last insert time in ns (CUDA events) [5] fixed-stride fast path used (0/1)
  * [6] [7] when the last insert took the L2-blocked path: ns spent bucketing k-mers by table slice / upserting them
- * (0 0 = the fused random-access kernel was used; GENOME_B200_INSERT=direct|partitioned forces a path) */
+ * (0 0 = the fused random-access kernel was used; gb_tune("insert_path") forces a path) */
 int gb_map_stats(gb_map *m, int64_t stats[8]);
+/* CUDA-event durations (ns) of the handle's last calls, for the roofline report: [0] bucket pass and [1] slice-ordered upsert of
+ * the last L2-blocked insert, [2] table sweep and [3] re-insert of the survivors of the last deleteAll, [4] slots that sweep
+ * streamed (16 bytes each), [5] membership probes and [6] list ranking of the last Graph.buildGraph on this map, [7] the number of
+ * pointer-jumping launches of that ranking */
+int gb_map_phase_ns(gb_map *m, int64_t ns[8]);
 
 /* ------------------------------------------------------------------------------------------------
  * Graph  (trait Graph / MapGraph / object Graph, S/data/graph/Graph.scala)

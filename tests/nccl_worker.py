@@ -19,6 +19,8 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from genome_b200 import capi
+    capi.tune_from_env()   # GENOME_B200_TUNE of the test that started this world (read by the harness, not by the library)
     comm = Communicator(rank, world, local, torch_broadcast)
     for (k, glen, rl, cov, err, rounds, ragged, cap) in [(31, 60000, 100, 20, 0.01, 3, False, 1 << 20), (21, 20000, 80, 12, 0.02, 2, True, 0),
                                                         (9, 3000, 40, 12, 0.02, 1, False, 0)]:
@@ -34,7 +36,7 @@ def main():
         assert m.size == om.size()
         # this shard holds exactly the oracle's keys that it owns
         ok, ov = om.export_sorted()
-        sel = m.owner(ok) == rank   # the map's own ownership rule (hash prefix, or minimizer with GENOME_B200_WIRE=superkmer)
+        sel = m.owner(ok) == rank   # the map's own ownership rule (hash prefix, or minimizer with wire_superkmer)
         gk, gv = m.export_sorted()
         assert np.array_equal(gk, ok[sel]) and np.array_equal(gv, ov[sel])
         assert m.local_size == int(sel.sum())
@@ -85,12 +87,11 @@ def main():
     om, ow = H.oracle_counts(b, n, k)
     assert m.size == om.size()
     ok, ov = om.export_sorted()
-    sel = m.owner(ok) == rank   # the map's own ownership rule (hash prefix, or minimizer with GENOME_B200_WIRE=superkmer)
+    sel = m.owner(ok) == rank   # the map's own ownership rule (hash prefix, or minimizer with wire_superkmer)
     gk, gv = m.export_sorted()
     assert np.array_equal(gk, ok[sel]) and np.array_equal(gv, ov[sel])
     m.close()
-    if os.environ.get("GENOME_B200_UNVALIDATED"):
-        pair_support_over_ranks(comm, rank, world)
+    pair_support_over_ranks(comm, rank, world)
     dist.barrier()
     comm.close()
     if rank == 0:
@@ -100,8 +101,7 @@ def main():
 
 def pair_support_over_ranks(comm, rank, world):
     """GraphSimplifier's pair loop split over the ranks (MapGraph.pairSupport(comm=...)): the graph is built from the shards
-    (identical on every rank), every rank walks its slice of the pairs, counts are summed; against the oracle's pathsMap.
-    Opt-in (GENOME_B200_UNVALIDATED=1) until it has passed on a multi-GPU box."""
+    (identical on every rank), every rank walks its slice of the pairs, counts are summed; against the oracle's pathsMap."""
     from genome_b200 import synth
     from genome_b200.simplifier import GraphSimplifier
     k, L = 15, 50

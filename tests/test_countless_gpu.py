@@ -1,6 +1,6 @@
-"""The single-pass bucket pass (GENOME_B200_COUNTLESS=1: per-(bucket, CTA) slabs instead of a count pass, csrc/partition.cu
-part_scatter_kernel<..., SLABS>) against the oracle.  Written after this round's GPU budget was spent (the default kernels'
-SASS is unchanged by it: compared instruction for instruction); opt-in until run on a B200."""
+"""The single-pass bucket pass (per-(bucket, CTA) slabs instead of a count pass, csrc/partition.cu
+part_scatter_kernel<..., SLABS>; the default for large batches) against the oracle, forced onto small inputs, and its
+corner cases: slab overflow, the overflow list of the chunked host insert, ragged streams, super-k-mer records."""
 import os
 
 import numpy as np
@@ -11,15 +11,16 @@ from genome_b200.dnamap import ArrayDNAMap
 from oracle import pyoracle
 from tests import helpers as H
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")]
+from genome_b200 import capi
+
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture
-def countless(monkeypatch):
-    monkeypatch.setenv("GENOME_B200_INSERT", "partitioned")   # small tables take the direct path otherwise
-    monkeypatch.setenv("GENOME_B200_COUNTLESS", "1")
-    return monkeypatch
+def countless():
+    # small tables take the direct path otherwise; single_pass_min lets batches of a few 100 k windows in
+    with capi.tuned(insert_path=2, single_pass=1, single_pass_min=1):
+        yield
 
 
 def check(b, n, k, cap=0):
@@ -48,8 +49,7 @@ def check(b, n, k, cap=0):
 ])
 def test_countless_insert_matches_oracle(gpu, countless, k, read_len, ragged, err):
     """The parity cases of the table (tests/test_parity_gpu.py) through the slab bucket pass -- fixed-stride cases also
-    through the chunked host insert.  These batches are small (a few 100 k windows): GENOME_B200_COUNTLESS_MIN lets them in."""
-    countless.setenv("GENOME_B200_COUNTLESS_MIN", "1")
+    through the chunked host insert."""
     b, n, _ = H.small_reads(20000, read_len, 12, err, seed=1000 + k, ragged=ragged)
     check(b, n, k)
 
@@ -96,16 +96,16 @@ def test_countless_ragged_stream_falls_back(gpu, countless):
 
 def test_countless_at_size(gpu, countless):
     """1.5 M reads of a 5 Mbp genome with 1 % errors (the C2 shape): enough keys for real slabs (hundreds per (bucket, CTA)),
-    compared through size-independent properties and against the default path."""
+    compared through size-independent properties and against the counted bucket pass."""
     k = 31
     b, n, _ = synth.make_config("C2", scale=0.25)
     gm = ArrayDNAMap(k, int(b.size * 1.2))
     w = gm.insert_reads(b, n)
     gk, gv = gm.export_sorted()
     assert int(gv.astype(np.int64).sum()) == w and np.unique(gk).size == gk.size
-    countless.delenv("GENOME_B200_COUNTLESS")
-    ref = ArrayDNAMap(k, int(b.size * 1.2))
-    assert ref.insert_reads(b, n) == w
+    with capi.tuned(single_pass=0):
+        ref = ArrayDNAMap(k, int(b.size * 1.2))
+        assert ref.insert_reads(b, n) == w
     rk, rv = ref.export_sorted()
     assert np.array_equal(gk, rk) and np.array_equal(gv, rv)
 
@@ -129,49 +129,15 @@ def test_superkmer_records_insert_like_the_reads(gpu, k, P):
     ok, ov = om.export_sorted()
     d = torch.zeros(recs.size + 16, dtype=torch.uint8, device="cuda")
     d[:recs.size].copy_(torch.from_numpy(np.ascontiguousarray(recs).reshape(-1)))
-    for env in ({}, {"GENOME_B200_INSERT": "partitioned"}, {"GENOME_B200_INSERT": "partitioned", "GENOME_B200_COUNTLESS": "1"}):
-        old = {k_: os.environ.get(k_) for k_ in ("GENOME_B200_INSERT", "GENOME_B200_COUNTLESS")}
-        try:
-            for k_ in old:
-                os.environ.pop(k_, None)
-            os.environ.update(env)
+    for env in (dict(insert_path=1), dict(insert_path=2, single_pass=0), dict(insert_path=2, single_pass=1, single_pass_min=1)):
+        with capi.tuned(**env):
             gm = ArrayDNAMap(k, 1 << 22)
             assert gm.insert_records_device(d.data_ptr(), recs.size, 16, recs.shape[0], 52) == w
             gk, gv = gm.export_sorted()
             assert np.array_equal(gk, ok) and np.array_equal(gv, ov), env
             gm.close()
-        finally:
-            for k_, v in old.items():
-                os.environ.pop(k_, None)
-                if v is not None:
-                    os.environ[k_] = v
     # a record longer than max_len is an argument error, the table stays as it was
     gm = ArrayDNAMap(k, 1 << 20)
     with pytest.raises(Exception):
         gm.insert_records_device(d.data_ptr(), recs.size, 16, recs.shape[0], 40)
     assert gm.size == 0
-
-
-@pytest.mark.parametrize("single_pass", [False, True], ids=["counted", "single-pass"])
-def test_cas128_claim(gpu, monkeypatch, single_pass):
-    """GENOME_B200_CAS128=1: a new key is claimed WITH its count by one 128-bit compare-and-swap (insert_keys_kernel<...,
-    CLAIM128>, atom.cas.b128) instead of CAS + red.  Same tables as the default path, with and without the single pass;
-    duplicate-heavy and singleton-heavy inputs, and a second batch into the filled table (no slot is 'exactly empty' twice)."""
-    monkeypatch.setenv("GENOME_B200_INSERT", "partitioned")
-    monkeypatch.setenv("GENOME_B200_CAS128", "1")
-    if single_pass:
-        monkeypatch.setenv("GENOME_B200_COUNTLESS", "1")
-        monkeypatch.setenv("GENOME_B200_COUNTLESS_MIN", "1")
-    for k, read_len, ragged, err in [(31, 100, False, 0.01), (21, 100, True, 0.02), (15, 36, False, 0.0), (4, 30, False, 0.0)]:
-        b, n, _ = H.small_reads(20000, read_len, 12, err, seed=1000 + k, ragged=ragged)
-        check(b, n, k)
-    b, n, _ = synth.make_config("C2", scale=0.25)
-    gm = ArrayDNAMap(31, int(b.size * 1.2))
-    w = gm.insert_reads(b, n)
-    gk, gv = gm.export_sorted()
-    monkeypatch.delenv("GENOME_B200_CAS128")
-    monkeypatch.delenv("GENOME_B200_COUNTLESS", raising=False)
-    ref = ArrayDNAMap(31, int(b.size * 1.2))
-    assert ref.insert_reads(b, n) == w
-    rk, rv = ref.export_sorted()
-    assert np.array_equal(gk, rk) and np.array_equal(gv, rv)

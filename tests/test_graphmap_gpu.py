@@ -48,8 +48,7 @@ def test_graph_positions_match_oracle(gpu, k, glen, rl, cov, err, rounds):
 
 
 # gb_graph_map_* was written after this round's GPU budget was spent: its logic is covered by the g++ emulation
-# (tests/test_walk_emul_cpu.py::test_graph_map_get_all_matches_oracle); the device run is opt-in until it has passed on a B200
-@pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")
+# (tests/test_walk_emul_cpu.py::test_graph_map_get_all_matches_oracle)
 @pytest.mark.parametrize("k,glen,rl,cov,err,rounds", [(31, 20000, 100, 30, 0.01, 3), (15, 5000, 60, 30, 0.01, 2), (4, 120, 20, 6, 0.0, 1)])
 def test_graph_map_handle(gpu, k, glen, rl, cov, err, rounds):
     """GraphPositionMap.size / getAll / contains against the exported entry list: every entry is found under its k-mer, absent
@@ -83,7 +82,6 @@ def test_graph_map_handle(gpu, k, glen, rl, cov, err, rounds):
     m.close()
 
 
-@pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")
 def test_check_graph_finds_every_genome_kmer(gpu):
     """CheckGraph.startup (S/scripts/CheckGraph.scala:18-56) on an error-free read set that covers the genome: every k-window
     of the genome FASTA is on the graph; windows of an unrelated sequence are reported."""
@@ -102,7 +100,6 @@ def test_check_graph_finds_every_genome_kmer(gpu):
     assert lens == [300] and len(missing) == 300 - k + 1   # only the unrelated line (and none of "ACGTN": no full window)
 
 
-@pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")
 def test_kmers_calculator(gpu):
     """KmersCalculator (S/scripts/KmersCalculator.scala:16-28): distinct k-windows of a FASTA record, counted on the device."""
     from genome_b200 import checkgraph, synth

@@ -12,12 +12,16 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["direct", "partitioned"])
-def insert_path(request, monkeypatch):
-    """Both insert paths against the oracle: small tables take the direct kernel by default, the L2-blocked path
-    (part_count / part_scatter / insert_keys: the one bench.py times and every BASELINE config takes) is forced here."""
-    monkeypatch.setenv("GENOME_B200_INSERT", request.param)
-    return request.param
+@pytest.fixture(params=["direct", "partitioned", "single-pass"])
+def insert_path(request):
+    """Every insert path against the oracle.  Small tables take the direct kernel by default; the L2-blocked path (the one
+    bench.py times and every BASELINE config takes) is forced here, once with the counted bucket pass (part_count +
+    part_scatter: also what the sharded map runs) and once with the single-pass one (part_scatter<SLABS>, the default for
+    large batches), both followed by insert_keys_kernel."""
+    kw = {"direct": dict(insert_path=1), "partitioned": dict(insert_path=2, single_pass=0),
+          "single-pass": dict(insert_path=2, single_pass=1, single_pass_min=1)}[request.param]
+    with capi.tuned(**kw):
+        yield request.param
 
 
 def gpu_map_from(bin_bytes, n_reads, k, min_capacity=0):
@@ -36,7 +40,7 @@ def test_insert_counts_match_oracle(gpu, insert_path, k, read_len, ragged, err):
     om, ow = H.oracle_counts(b, n, k)
     gm, gw = gpu_map_from(b, n, k)
     assert gw == ow == pyoracle.count_windows(b, n, k)
-    assert (gm.stats()["upsert_ns"] > 0) == (insert_path == "partitioned" and gw > 0)
+    assert (gm.stats()["upsert_ns"] > 0) == (insert_path != "direct" and gw > 0)
     assert gm.size == om.size()
     gk, gv = gm.export_sorted()
     ok, ov = om.export_sorted()

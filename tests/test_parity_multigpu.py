@@ -26,7 +26,7 @@ def test_pmap_matches_oracle(gpu, world):
     run_world(world)
 
 
-@pytest.mark.parametrize("env", [{"GENOME_B200_ROUTE": "two"}, {"GENOME_B200_A2A": "nccl"}, {"GENOME_B200_BATCHES": "5", "GENOME_B200_LP": "1"}],
+@pytest.mark.parametrize("env", [{"GENOME_B200_TUNE": "route=2"}, {"GENOME_B200_TUNE": "a2a_nccl=1"}, {"GENOME_B200_TUNE": "batches=5,slice_bits=1"}],
                          ids=["two-level", "nccl-staged", "many-batches"])
 def test_pmap_routing_variants(gpu, env):
     """The same sharded run through the other routing paths: receiver-side re-bucketing, NCCL send/recv staging instead of
@@ -36,25 +36,23 @@ def test_pmap_routing_variants(gpu, env):
     run_world(2, env)
 
 
-@pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")
 @pytest.mark.parametrize("world", [1, 2, 8])
 def test_pmap_sharded_graph_build(gpu, world):
     """Graph.buildGraph over the shards WITHOUT a replica (csrc/sgraph.cuh over the NCCL + CUDA-IPC fabric of comm.cu): the
-    same worker, same oracle comparisons, with GENOME_B200_PGRAPH=sharded.  world = 1 runs the NCCL fabric (single-rank
-    collectives, no IPC mapping to open) on a one-GPU box.  Opt-in until it has passed on a B200 box."""
+    same worker, same oracle comparisons, with pgraph_sharded = 1 (gb_tune).  world = 1 runs the NCCL fabric (single-rank
+    collectives, no IPC mapping to open) on a one-GPU box."""
     if gpu < world:
         pytest.skip("needs %d GPUs, box has %d" % (world, gpu))
-    run_world(world, {"GENOME_B200_PGRAPH": "sharded"})
+    run_world(world, {"GENOME_B200_TUNE": "pgraph_sharded=1"})
 
 
-@pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")
 @pytest.mark.parametrize("world", [1, 2, 8])
 def test_pmap_superkmer_wire(gpu, world):
-    """The sharded insert with super-k-mers on the wire (GENOME_B200_WIRE=superkmer: minimizer owners, 16-byte records,
+    """The sharded insert with super-k-mers on the wire (gb_tune wire_superkmer = 1: minimizer owners, 16-byte records,
     csrc/superkmer.cuh + comm.cu pmap_insert_superkmers): same worker, same oracle comparisons (shard contents are checked
     through the map's own owner function); together with the sharded graph build, whose re-routing then finds every key at
-    home.  Opt-in until it has passed on a B200 box."""
+    home."""
     if gpu < world:
         pytest.skip("needs %d GPUs, box has %d" % (world, gpu))
-    run_world(world, {"GENOME_B200_WIRE": "superkmer"})
-    run_world(world, {"GENOME_B200_WIRE": "superkmer", "GENOME_B200_PGRAPH": "sharded"})
+    run_world(world, {"GENOME_B200_TUNE": "wire_superkmer=1"})
+    run_world(world, {"GENOME_B200_TUNE": "wire_superkmer=1,pgraph_sharded=1"})

@@ -1,6 +1,6 @@
 """The reference's driver scripts mirrored over the C ABI, end to end on the device: GraphBuilder.startup
 (S/scripts/GraphBuilder.scala:18-59) against the oracle.  Compositions of entry points that have their own parity tests; written
-after this round's GPU budget was spent, so opt-in until run on a B200."""
+after round 1's GPU budget was spent; first run on a B200 in round 2 (profiles/r2a_validate_1gpu.log)."""
 import os
 
 import numpy as np
@@ -11,8 +11,7 @@ from genome_b200.dnamap import PairedEndData
 from oracle import pyoracle
 from tests import helpers as H
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("k,glen,rl,cov,err", [(31, 20000, 100, 30, 0.01), (15, 5000, 60, 30, 0.01), (9, 4000, 40, 15, 0.03)])

@@ -1,7 +1,7 @@
 """The sharded Graph.buildGraph (csrc/sgraph.cuh) on the device: P virtual ranks on one GPU against the oracle and against
 the single-GPU build.  The same functors and orchestration pass tests/test_sgraph_emul_cpu.py through a g++ backend; these
 tests cover the CUDA backend (launches, atomics, scans, arena memory).  Written after this round's GPU budget was spent:
-opt-in until they have passed on a B200."""
+first run on a B200 in round 2 (profiles/r2a_validate_1gpu.log)."""
 import os
 
 import numpy as np
@@ -14,8 +14,7 @@ from oracle import pyoracle
 from tests import helpers as H
 from tests.test_sgraph_emul_cpu import GRAPH_CASES
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("GENOME_B200_UNVALIDATED"), reason="not yet run on a B200 (set GENOME_B200_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("k,glen,rl,cov,err,rounds", GRAPH_CASES)
