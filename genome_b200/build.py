@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgenome_b200.so")
-SOURCES = ["map.cu", "partition.cu", "graph.cu", "graphmap.cu", "walk.cu", "sgraph.cu", "comm.cu"]
+SOURCES = ["map.cu", "partition.cu", "graph.cu", "graphmap.cu", "walk.cu", "sgraph.cu", "comm.cu", "microbench.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function", "--threads", "4",

@@ -45,6 +45,11 @@ long long gb_launch_count(void);
  * element over an array of exactly table_bytes (no hashing, no probing, no preceding load): ns per pass of n_updates,
  * averaged over iters passes */
 int gb_bench_random_atomics(int device, size_t table_bytes, int64_t n_updates, int iters, int64_t *ns_per_iter);
+/* diagnostics: update(key, 1, _ + 1) with the table slice in SHARED memory (one CTA per bucket of keys_per_bucket synthetic keys with
+ * C2's multiplicity profile: slice of 2^slots_log2 slots initialised on chip, shared-memory atomics, slice streamed out once): ns per
+ * pass over n_buckets buckets; *distinct_keys (optional) = keys claimed per pass.  The design question of DESIGN.md 3.1. */
+int gb_bench_smem_upsert(int device, int slots_log2, int64_t keys_per_bucket, int64_t n_buckets, int ctas_per_sm, int iters,
+                         int64_t *ns_per_iter, int64_t *distinct_keys);
 /* tuning and test hooks (process-wide; not part of the reference surface).  The library reads no environment variable on
  * its data path: every default is a measured choice, and the parity tests use these keys to force a path that
  * small inputs would not take by themselves.  Keys: insert_path (0 auto, 1 direct, 2 L2-blocked), single_pass,
