@@ -34,7 +34,8 @@ class GraphBuilder:
 
     def startup(self, data, comm=None, min_capacity=0):
         """Returns the MapGraph after `retain(maxComponent)`; self.log holds what the reference logs.  `comm`: a Communicator,
-        then `data` is this rank's slice of the pairs and the map is a PartitionedDNAMap over the communicator's GPUs."""
+        then the map is a PartitionedDNAMap over its GPUs; `data` is the WHOLE data set on every rank (each takes its own slice, the
+        same convention as GraphSimplifier.startup)."""
         kmers = FreqFilter.extractFilteredKmers(data, self.k, self.rounds, comm=comm, min_capacity=min_capacity)   # 32
         self.log["good_reads_count"] = kmers.size                      # "Good reads count: " (34) -- the kept k-mers, sic
         graph = Graph.buildGraph(self.k, kmers)                         # 36

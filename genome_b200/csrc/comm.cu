@@ -962,6 +962,11 @@ int gb_pmap_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, 
     GB_TRY(check_pmap(h, &m));
     ArenaScope scope(&m->arena);
     if (n < 0 || (n > 0 && !keys)) { set_error("bad arguments"); return GB_E_ARG; }
+    {   // collective: every rank must take the same exit
+        int64_t bad = check_keys(m, keys, n) != GB_OK;
+        GB_TRY(all_reduce_i64(m->comm, &bad, ncclMax));
+        if (bad) { set_error("a query key is longer than k = %d (on some rank)", m->k); return GB_E_K_RANGE; }
+    }
     Comm *c = m->comm;
     const int P = c->n_ranks;
     // bucket the queries by owner on the host (they come from the host), remember where each one came from

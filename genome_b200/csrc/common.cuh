@@ -412,6 +412,8 @@ struct ShardPlan {
 };
 int graph_build_sharded(gb_map *h, gb_graph **out, const ShardPlan *sp);
 int check_map(gb_map *h, Map **m);
+// assert(key.length == k) of apply / contains (S/ds/ArrayDNAMap.scala:182-206): a query with bits above 2k is an error
+int check_keys(const Map *m, const uint64_t *keys, int64_t n);
 
 inline unsigned int grid_for(unsigned long long n, int threads, int per_sm = 16)
 {

@@ -1085,6 +1085,7 @@ int gb_map_neighbour_masks(gb_map *h, const uint64_t *keys, int64_t n, uint8_t *
     ArenaScope scope(&m->arena);
     if (n < 0 || (n > 0 && (!keys || !masks))) { set_error("bad arguments"); return GB_E_ARG; }
     if (n == 0) return GB_OK;
+    GB_TRY(check_keys(m, keys, n));
     cudaStream_t st = m->stream;
     DeviceBuf dk, dm;
     GB_TRY(dk.alloc((size_t)n * 8));

@@ -805,6 +805,14 @@ int scan_records(const uint8_t *bin, size_t n_bytes, int64_t n_reads, int k,
     return GB_OK;
 }
 
+int check_keys(const Map *m, const uint64_t *keys, int64_t n)
+{
+    const unsigned long long kmask = (1ull << (2 * m->k)) - 1;
+    for (int64_t i = 0; i < n; i++)
+        if (keys[i] & ~kmask) { set_error("key %lld is longer than k = %d", (long long)i, m->k); return GB_E_K_RANGE; }
+    return GB_OK;
+}
+
 int check_map(gb_map *h, Map **m)
 {
     if (!h) { set_error("null map handle"); return GB_E_ARG; }
@@ -1063,9 +1071,7 @@ static int update_common(gb_map *h, const uint64_t *keys, const int32_t *vals, i
     ArenaScope scope(&m->arena);
     if (n < 0 || (n > 0 && (!keys || (set && !vals)))) { set_error("bad arguments"); return GB_E_ARG; }
     if (n == 0) return GB_OK;
-    unsigned long long kmask = (1ull << (2 * m->k)) - 1;
-    for (int64_t i = 0; i < n; i++)
-        if (keys[i] & ~kmask) { set_error("key %lld is longer than k = %d", (long long)i, m->k); return GB_E_K_RANGE; }
+    GB_TRY(check_keys(m, keys, n));
     m->noncanonical = true;
     m->kept_valid = false;
     DeviceBuf dk, dv;
@@ -1110,6 +1116,7 @@ int gb_map_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, u
     ArenaScope scope(&m->arena);
     if (n < 0 || (n > 0 && !keys)) { set_error("bad arguments"); return GB_E_ARG; }
     if (n == 0) return GB_OK;
+    GB_TRY(check_keys(m, keys, n));
     DeviceBuf dk, dc, df;
     GB_TRY(dk.alloc((size_t)n * 8, m->stream));
     GB_TRY(dc.alloc((size_t)n * 4, m->stream));

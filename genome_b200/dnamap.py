@@ -373,8 +373,14 @@ class FreqFilter:
     @staticmethod
     def extractFilteredKmers(data, k, rounds, comm=None, min_capacity=0, device=0, take_first=None):
         """extractFilteredKmers(data, k, rounds): count every canonical k-window of the first `take_first` pairs
-        (genome.takeFirst), then deleteAll(v < rounds).  With `comm`, `data` is this rank's slice."""
-        n_reads = data.n_reads if take_first is None else min(data.n_reads, 2 * int(take_first))
+        (genome.takeFirst), then deleteAll(v < rounds).  `data` is always the WHOLE data set -- the same convention as
+        GraphBuilder.startup, GraphSimplifier.startup and MapGraph.pairSupport: with `comm` the first `take_first` pairs of the
+        file are selected and THEN every rank takes its slice of them (PairedEndData.take(...).shard(rank, world))."""
+        if take_first is not None:
+            data = data.take(int(take_first))
+        if comm is not None:
+            data = data.shard(comm.rank, comm.world)
+        n_reads = data.n_reads
         kmers = PartitionedDNAMap(k, comm, min_capacity) if comm is not None else ArrayDNAMap(k, min_capacity, device)
         kmers.insert_reads(data, n_reads)
         kmers.delete_below(rounds)

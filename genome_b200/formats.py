@@ -49,11 +49,14 @@ def convert2bin(lines, n=36, k=23):
             break
         line = line.rstrip("\r\n")
         next(it, None)                       # '+' line
-        quality = next(it, None)             # read (and split) but unused: the quality filter is commented out (42-43)
+        quality = next(it, None)             # split like the bases; its VALUES are unused (the quality filter is commented out, 42-43)
         if quality is None:
             # in.readLine().splitAt(n) on null throws in the reference; a truncated last record is dropped here
             break
-        s1, s2 = filtered(line[:n]), filtered(line[n:])
+        quality = quality.rstrip("\r\n")
+        q1, q2 = quality[:n], quality[n:]
+        # `line1 zip quality1` (61-62): a read is cut to the length of its quality segment before takeWhile
+        s1, s2 = filtered(line[:n][:len(q1)]), filtered(line[n:][:len(q2)])
         if len(s1) < k or len(s2) < k:
             short += 1
         reads.append(s1)

@@ -212,3 +212,15 @@ def test_graph_builder_histograms_on_oracle_graph():
     assert hist == sorted(sizes.items()) and hist2 == sorted(lens.items())
     assert sum(c for _, c in hist) == nc and int(comp_nodes.max()) == max(sizes)
     assert component_histograms(0, np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(1, np.uint64))[:2] == ([], [])
+
+
+def test_convert2bin_cuts_reads_to_their_quality_segment():
+    """Convert2bin.scala:61-62 zips the bases with the quality string, so a read is as long as the shorter of the two."""
+    import io
+    from genome_b200 import formats
+    n, k = 8, 3
+    fq = "@r\nACGTACGTGGCCAATT\n+\nIIIIIIIIIIII\n"   # 16 bases, 12 qualities: mate 1 keeps 8, mate 2 keeps 4
+    b, pairs, kmers, short = formats.convert2bin(io.StringIO(fq), n, k)
+    reads = formats.read_bin(b, 2)
+    assert pairs == 1 and [len(r) for r in reads] == [8, 4]
+    assert kmers == (8 - k + 1) + (4 - k + 1) and short == 0

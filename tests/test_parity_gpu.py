@@ -148,6 +148,15 @@ def test_lookup_update_and_masks(gpu):
     assert np.array_equal(a, c) and np.array_equal(bv, d)
     with pytest.raises(capi.GenomeError):
         m2.update_counts(np.array([1 << (2 * k)], np.uint64))
+    # apply / contains assert key.length == k (ArrayDNAMap.scala:182-206): a query with bits above 2k is an error, and the
+    # empty-slot sentinel is not a key
+    for bad in (1 << (2 * k), 0xFFFFFFFFFFFFFFFF):
+        with pytest.raises(capi.GenomeError) as e:
+            m2.lookup(np.array([bad], np.uint64))
+        assert e.value.name == "GB_E_K_RANGE"
+        with pytest.raises(capi.GenomeError) as e:
+            m2.neighbour_masks(np.array([bad], np.uint64))
+        assert e.value.name == "GB_E_K_RANGE"
 
 
 GRAPH_CASES = [
