@@ -44,7 +44,6 @@ struct Tuning {
     long long slice_bits = -1;          // table slices of the L2-blocked insert = 2^slice_bits; -1 = from the table size (64 MiB slices)
     long long batches = 0;              // sub-batches of one insert call; 0 = default (1 on one GPU, 2 sharded)
     long long h2d_chunks = 4;           // host insert: chunks of the host-to-device copy overlapped with the bucket pass
-    long long prefetch = 0;             // slice-ordered upsert asks L2 for the next table slice while it fills the current one
     long long route = 0;                // sharded insert: 0 = by shard size, 1 = one level (owner, slice) on the wire, 2 = two levels
     long long a2a_nccl = 0;             // sharded insert: staged ncclSend/ncclRecv instead of stores into the peers' inboxes
     long long wire_superkmer = 0;       // sharded maps created from now on: minimizer owners, 16-byte super-k-mer records on the wire

@@ -315,17 +315,15 @@ constexpr int IK_PER_THREAD = 4; // measured 2 / 4 / 8 / 16 keys per thread: 1.7
 
 // No CTA barrier anywhere: every thread finds its own chunk, every warp adds its new-key count to one of SPREAD
 // global counters (fold_new_keys_kernel sums them into counters[0] afterwards).
-// Measured and dropped (round 2, profiles/r2a_bench_*.json): claiming a new key together with its count by one 128-bit
-// compare-and-swap (1.865 ms against 1.834 ms), CAS-first probing, 2 / 8 / 16 keys per thread.
+// Measured and dropped (round 2, profiles/r2a_bench_*.json, r2b_insert_sweep.jsonl): claiming a new key together with its count
+// by one 128-bit compare-and-swap (1.865 ms against 1.834 ms), CAS-first probing, 2 / 8 / 16 keys per thread, prefetching the
+// next table slice into L2 while the current one is filled (2.22 against 2.15 ms).
 // DEV_TOTAL: n_total is only an upper bound (it sized the grid); the exact number of keys is vstart[n_chunks].
-// PREFETCH: the keys come in table-slice order (one slice = [slice_lo, slice_lo + slice_slots) of the table); while the
-// resident CTAs work on slice s, each of them asks L2 for its share of slice s + 1 (one 128-byte line per thread), so that
-// the table loads of the next slice hit L2 instead of waiting for DRAM.
 template <bool DEV_TOTAL>
 __global__ void __launch_bounds__(IK_THREADS)
 insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vstart,
                    const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Slot *table, unsigned long long cap,
-                   unsigned long long *spread, int prefetch_bits)
+                   unsigned long long *spread)
 {
     constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
     const unsigned long long v0 = (unsigned long long)blockIdx.x * IK_PER_CTA;
@@ -352,24 +350,6 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
             while (v >= vstart[c + 1]) c++; // chunks ascend with v; empty chunks are skipped
             key[j] = __ldcs(keys + off[c] + (v - vstart[c]));
             idx[j] = slot_of(mix64(key[j]), cap);
-        }
-    }
-    if (prefetch_bits > 0 && ok[0]) {
-        // slice of this CTA's first key, and how far the CTA is through that slice's keys, estimated from the hash itself:
-        // inside a slice the keys are in no particular order, so the share is taken from the CTA's position in the launch
-        const unsigned long long h0 = mix64(key[0]);
-        const unsigned long long slice = h0 >> (64 - prefetch_bits), n_slices = 1ull << prefetch_bits;
-        if (slice + 1 < n_slices) {
-            // slots of slice s: [ceil(s * cap / n_slices) .. ): monotonic slot_of => contiguous
-            const unsigned long long lo = slot_of((slice + 1) << (64 - prefetch_bits), cap);
-            const unsigned long long hi = slice + 2 < n_slices ? slot_of((slice + 2) << (64 - prefetch_bits), cap) : cap;
-            const unsigned long long lines = ((hi - lo) * sizeof(Slot) + 127) / 128;
-            // the CTAs of one slice are about n_total / n_slices / IK_PER_CTA many: CTA number q among them takes lines q, q + that, ...
-            const unsigned long long per_slice = max(1ull, n_total / n_slices / IK_PER_CTA);
-            const unsigned long long q = blockIdx.x % per_slice;
-            const char *base = reinterpret_cast<const char *>(table + lo);
-            for (unsigned long long l = q * IK_THREADS + threadIdx.x; l < lines; l += per_slice * IK_THREADS)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + l * 128));
         }
     }
     int nk = 0;
@@ -410,6 +390,56 @@ fold_new_keys_kernel(unsigned long long *spread, unsigned long long *counters)
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counters[0], v);
+}
+
+// The same upsert over the SLABS of the single-pass bucket pass: slab number s = (bucket, CTA of the bucket pass) holds count[s]
+// keys at keys[s * slab], and CTA (s, part) takes keys [part * 1024, ...) of it.  The launch is sized for full slabs; a CTA
+// whose part lies beyond count[s] leaves at once.  No chunk table, no search: measured on C2 the search over the 19 k-entry
+// chunk table cost the generic kernel 0.2 ms (2.15 against 1.95 ms).  Slabs are bucket-major, so slice order is kept.
+__global__ void __launch_bounds__(IK_THREADS)
+insert_slabs_kernel(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ count, unsigned int slab,
+                    unsigned int ctas_per_slab, Slot *table, unsigned long long cap, unsigned long long *spread)
+{
+    constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
+    const unsigned int s = blockIdx.x / ctas_per_slab, part = blockIdx.x - s * ctas_per_slab;
+    const unsigned int n = min(count[s], slab), v0 = part * IK_PER_CTA;
+    if (v0 >= n) return;
+    const unsigned long long *src = keys + (size_t)s * slab + v0;
+    unsigned long long key[IK_PER_THREAD], idx[IK_PER_THREAD], cur[IK_PER_THREAD], old[IK_PER_THREAD];
+    bool ok[IK_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < IK_PER_THREAD; j++) {
+        const unsigned int i = (unsigned int)j * IK_THREADS + threadIdx.x;
+        ok[j] = v0 + i < n;
+        if (ok[j]) {
+            key[j] = __ldcs(src + i);
+            idx[j] = slot_of(mix64(key[j]), cap);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < IK_PER_THREAD; j++)
+        if (ok[j]) cur[j] = load_key(table + idx[j]);
+#pragma unroll
+    for (int j = 0; j < IK_PER_THREAD; j++) {
+        old[j] = cur[j];
+        if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
+    }
+    int nk = 0;
+#pragma unroll
+    for (int j = 0; j < IK_PER_THREAD; j++) {
+        if (!ok[j]) continue;
+        const bool claimed = cur[j] == EMPTY_KEY && old[j] == EMPTY_KEY;
+        if (claimed || old[j] == key[j]) {
+            red_add_s32(&table[idx[j]].count, 1);
+            nk += claimed;
+        } else {
+            unsigned long long nx = next_slot(idx[j], cap);
+            nk += upsert_add(table, cap, nx, load_key(table + nx), key[j], 1);
+        }
+    }
+    nk = __reduce_add_sync(0xFFFFFFFFu, nk);
+    if ((threadIdx.x & 31) == 0 && nk)
+        atomicAdd(&spread[(blockIdx.x * (IK_THREADS / 32) + (threadIdx.x >> 5)) & (SPREAD - 1)], (unsigned long long)nk);
 }
 
 // ---------------------------------------------------------------- host side
@@ -537,45 +567,32 @@ unsigned long long slab_cta_keys(long long n_reads, unsigned long long windows, 
     return per_cta * TILE_READS * per_read;
 }
 
-// chunk table of the slabs, bucket-major: chunk c = (bucket c / grid, CTA c % grid) holds count[c] keys at out[c * slab].
-// desc = vstart[n_chunks + 1] | off[n_chunks]; counters[3] (k-windows) += keys in slabs + keys that took the overflow path.
-// ovf_cap > 0 (LIST mode): one more chunk, number n_chunks, for the overflow region that follows the slabs in `out`.
+// after the slab bucket pass: counters[3] (k-windows) += keys in slabs + keys that left through the overflow path.
+// ovf_cap > 0 (LIST mode): desc = { 0, keys in the overflow list, 0 } = the chunk table of that list (vstart[0], vstart[1], off[0]).
 __global__ void __launch_bounds__(1024)
-make_slab_chunks_kernel(const unsigned int *count, unsigned int n_chunks, unsigned int slab, unsigned long long *vstart, unsigned long long *off,
-                        const unsigned long long *overflowed, unsigned long long *counters, unsigned long long ovf_cap)
+slab_finish_kernel(const unsigned int *count, unsigned int n_slabs, unsigned int slab, const unsigned long long *overflowed,
+                   unsigned long long *counters, unsigned long long ovf_cap, unsigned long long *desc)
 {
-    __shared__ unsigned long long s_part[1024];
-    const unsigned int per = (n_chunks + 1023) / 1024, c0 = min(n_chunks, threadIdx.x * per), c1 = min(n_chunks, c0 + per);
     unsigned long long sum = 0;
-    for (unsigned int c = c0; c < c1; c++) sum += count[c];
-    s_part[threadIdx.x] = sum;
+    for (unsigned int c = threadIdx.x; c < n_slabs; c += 1024) sum += min(count[c], slab);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_down_sync(0xFFFFFFFFu, sum, d);
+    __shared__ unsigned long long s_part[32];
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long acc = 0;
-        for (int i = 0; i < 1024; i++) { const unsigned long long v = s_part[i]; s_part[i] = acc; acc += v; }
-        vstart[n_chunks] = acc;
-        if (ovf_cap) { // the overflow list is upserted like any chunk (its keys hit any slice: random access for those few)
-            const unsigned long long in_list = min(*overflowed, ovf_cap);
-            vstart[n_chunks + 1] = acc + in_list;
-            off[n_chunks] = (unsigned long long)n_chunks * slab;
-            atomicAdd(&counters[3], acc + in_list);
-        } else {
-            atomicAdd(&counters[3], acc + *overflowed);
-        }
-    }
-    __syncthreads();
-    unsigned long long run = s_part[threadIdx.x];
-    for (unsigned int c = c0; c < c1; c++) {
-        vstart[c] = run;
-        off[c] = (unsigned long long)c * slab;
-        run += count[c];
+        for (int i = 0; i < 32; i++) acc += s_part[i];
+        const unsigned long long extra = ovf_cap ? min(*overflowed, ovf_cap) : *overflowed;
+        atomicAdd(&counters[3], acc + extra);
+        if (desc) { desc[0] = 0; desc[1] = ovf_cap ? extra : 0; desc[2] = 0; }
     }
 }
 
-// pass 2 without pass 1: `out` holds nb * grid slabs of `slab` keys; d_desc receives the chunk table (2 * nb * grid + 1 words).
+// pass 2 without pass 1: `out` holds nb * grid slabs of `slab` keys, w.cta_hist their fill counts ([bucket][CTA]).
 // `spread` / `overflowed` / the table are for the keys that do not fit their slab.
 int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, unsigned int slab,
-                       unsigned long long *d_desc, Map *m, cudaStream_t st)
+                       Map *m, cudaStream_t st)
 {
     GB_TRY(w.ensure(st));
     const unsigned int nb = (unsigned int)pl.nb();
@@ -604,13 +621,13 @@ int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &
     else { if (v210) GB_PSS(false, true); else GB_PSS(false, false); }
 #undef GB_PSS
     GB_LAUNCHED();
-    make_slab_chunks_kernel<<<1, 1024, 0, st>>>(so.count, n_chunks, slab, d_desc, d_desc + n_chunks + 1, so.overflowed, m->d_counters, 0ull);
+    slab_finish_kernel<<<1, 1024, 0, st>>>(so.count, n_chunks, slab, so.overflowed, m->d_counters, 0ull, nullptr);
     GB_LAUNCHED();
     return GB_OK;
 }
 
 // LIST mode, one launch per read range (the chunked host insert of map.cu).  begin: zero the cursors; range: one bucket-pass
-// launch over rb; end: chunk table with the overflow chunk, desc = vstart[n_chunks + 2] | off[n_chunks + 1].
+// launch over rb; end: k-window total and the 3-word chunk table of the overflow list in d_desc.
 // out = nb * grid slabs | overflow region of ovf_cap keys.  w.bucket_total[0] = overflow cursor, [1] = failed flag.
 int slab_list_begin(const PartLayout &pl, PartWork &w, cudaStream_t st)
 {
@@ -643,7 +660,7 @@ int slab_list_range(const ReadBatch &rb, int k, bool v210, const PartLayout &pl,
 int slab_list_end(const PartLayout &pl, PartWork &w, unsigned int slab, unsigned long long ovf_cap, unsigned long long *d_desc, Map *m, cudaStream_t st)
 {
     const unsigned int n_chunks = (unsigned int)pl.nb() * (unsigned int)w.grid;
-    make_slab_chunks_kernel<<<1, 1024, 0, st>>>(w.cta_hist, n_chunks, slab, d_desc, d_desc + n_chunks + 2, w.bucket_total, m->d_counters, ovf_cap);
+    slab_finish_kernel<<<1, 1024, 0, st>>>(w.cta_hist, n_chunks, slab, w.bucket_total, m->d_counters, ovf_cap, d_desc);
     GB_LAUNCHED();
     return GB_OK;
 }
@@ -663,8 +680,26 @@ int make_single_chunk(const unsigned long long *d_total, unsigned long long *d_d
     return GB_OK;
 }
 
+int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d_count, unsigned int slab, unsigned int n_slabs, cudaStream_t st)
+{
+    if (!n_slabs || !slab) return GB_OK;
+    m->kept_valid = false;
+    if (!m->d_spread) {
+        GB_CUDA(cudaMalloc((void **)&m->d_spread, SPREAD * 8));
+        GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));
+    }
+    const unsigned int per = (slab + IK_THREADS * IK_PER_THREAD - 1) / (IK_THREADS * IK_PER_THREAD);
+    const unsigned long long grid = (unsigned long long)n_slabs * per;
+    if (grid >= 0x7FFFFFFFull) { set_error("internal: %llu slab CTAs", grid); return GB_E_ARG; }
+    insert_slabs_kernel<<<(unsigned int)grid, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, m->table, m->cap, m->d_spread);
+    GB_LAUNCHED();
+    fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
+    GB_LAUNCHED();
+    return GB_OK;
+}
+
 int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned long long *d_vstart, const unsigned long long *d_off,
-                      int n_chunks, unsigned long long n_total, cudaStream_t st, bool total_is_upper_bound, int prefetch_bits)
+                      int n_chunks, unsigned long long n_total, cudaStream_t st, bool total_is_upper_bound)
 {
     if (!n_total) return GB_OK;
     m->kept_valid = false;
@@ -674,9 +709,9 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
     }
     const unsigned int grid = (unsigned int)((n_total + IK_THREADS * IK_PER_THREAD - 1) / (IK_THREADS * IK_PER_THREAD));
     if (total_is_upper_bound)
-        insert_keys_kernel<true><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread, prefetch_bits);
+        insert_keys_kernel<true><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread);
     else
-        insert_keys_kernel<false><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread, prefetch_bits);
+        insert_keys_kernel<false><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread);
     GB_LAUNCHED();
     fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
     GB_LAUNCHED();

@@ -73,10 +73,8 @@ int part_scatter_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, un
 // update(key, 1, _ + 1) for the keys of `n_chunks` ranges visited in order: chunk c holds the virtual positions
 // [vstart[c], vstart[c+1]) and starts at keys[off[c]].  d_vstart has n_chunks + 1 entries.  n_total = vstart[n_chunks].
 // total_is_upper_bound: n_total only sizes the launch, the exact number of keys is d_vstart[n_chunks] on the device.
-// prefetch_bits > 0: the keys come in order of the top `prefetch_bits` bits of their hash (table slices), all of them, and the
-// kernel prefetches slice s + 1 into L2 while slice s is being filled.
 int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned long long *d_vstart, const unsigned long long *d_off,
-                      int n_chunks, unsigned long long n_total, cudaStream_t st, bool total_is_upper_bound = false, int prefetch_bits = 0);
+                      int n_chunks, unsigned long long n_total, cudaStream_t st, bool total_is_upper_bound = false);
 
 // the single-pass bucket pass (no count pass; GENOME_B200_COUNTLESS=1, single-GPU insert): see part_scatter_kernel<..., SLABS>
 unsigned int slab_keys_for(unsigned long long cta_keys, unsigned int nb, int grid);
@@ -87,7 +85,9 @@ int slab_list_range(const ReadBatch &rb, int k, bool v210, const PartLayout &pl,
                     unsigned long long ovf_cap, cudaStream_t st);
 int slab_list_end(const PartLayout &pl, PartWork &w, unsigned int slab, unsigned long long ovf_cap, unsigned long long *d_desc, Map *m, cudaStream_t st);
 int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, unsigned int slab,
-                       unsigned long long *d_desc, Map *m, cudaStream_t st);
+                       Map *m, cudaStream_t st);
+// the upsert over those slabs (slab s holds min(d_count[s], slab) keys at d_keys + s * slab), in slab order = slice order
+int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d_count, unsigned int slab, unsigned int n_slabs, cudaStream_t st);
 
 // desc = { 0, *d_total, 0 } (the chunk table of ONE contiguous range) and counters[3] += *d_total, all on the stream
 int make_single_chunk(const unsigned long long *d_total, unsigned long long *d_desc, unsigned long long *d_counters, cudaStream_t st);

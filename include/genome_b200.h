@@ -53,7 +53,7 @@ int gb_bench_smem_upsert(int device, int slots_log2, int64_t keys_per_bucket, in
 /* tuning and test hooks (process-wide; not part of the reference surface).  The library reads no environment variable on
  * its data path: every default is a measured choice, and the parity tests use these keys to force a path that
  * small inputs would not take by themselves.  Keys: insert_path (0 auto, 1 direct, 2 L2-blocked), single_pass,
- * single_pass_min, slice_bits, batches, h2d_chunks, prefetch, route (0 auto, 1 one level, 2 two levels), a2a_nccl,
+ * single_pass_min, slice_bits, batches, h2d_chunks, route (0 auto, 1 one level, 2 two levels), a2a_nccl,
  * wire_superkmer, pgraph_sharded, trace.  *previous (optional) receives the old value. */
 int gb_tune(const char *name, int64_t value, int64_t *previous);
 int gb_tune_get(const char *name, int64_t *value);
