@@ -505,7 +505,10 @@ def main():
                     "insert_ms": ins_s * 1e3, "insert_kmers_per_s": windows / ins_s,
                     "insert_frac": algo_bytes / ins_s / 1e9 / peak,
                     "step_frac": algo_bytes / R["step_s"] / 1e9 / peak,
-                    "phases_ms": {"bucket pass": st["bucket_ns"] * 1e-6, "upsert": st["upsert_ns"] * 1e-6} if partitioned else None,
+                    "phases_ms": {"bucket pass": st["bucket_ns"] * 1e-6, "upsert": st["upsert_ns"] * 1e-6,
+                                  "deleteAll sweep": R["phase"]["filter_sweep_ns"] * 1e-6, "deleteAll survivors into their table": R["phase"]["filter_reinsert_ns"] * 1e-6,
+                                  "rest of the step (clear, counters, launch gaps)": (R["step_s"] - ins_s) * 1e3 - (R["phase"]["filter_sweep_ns"] + R["phase"]["filter_reinsert_ns"]) * 1e-6}
+                    if partitioned else None,
                     "random_access_ceiling": {"kernel": "one random 64-bit atomicAdd per element over an array of the table's size (SURVEY 8d R_gups)",
                                               "updates_per_s": gups, "insert_vs_ceiling": (windows / ins_s) / gups},
                     # one 32 B sector in and one dirty sector out per insert = 64 B/instance is the THEORETICAL

@@ -49,6 +49,7 @@ struct Tuning {
     long long wire_superkmer = 0;       // sharded maps created from now on: minimizer owners, 16-byte super-k-mer records on the wire
     long long pgraph_sharded = 0;       // Graph.buildGraph over shards without a replica (sgraph.cuh)
     long long trace = 0;                // phase timings on stderr
+    long long exp = 0;                  // A/B bits of the experiment in progress (0 in production; see scripts/r2_insert_sweep.py)
 };
 extern Tuning g_tune;
 

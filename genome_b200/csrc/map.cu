@@ -484,7 +484,8 @@ int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d
         fp = m->fp;
     }
     if (n <= 0) return GB_OK;
-    if (set_vid) place_distinct_kernel<<<(unsigned int)((n + 511) / 512), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, fp, m->d_counters);
+    if (set_vid && (g_tune.exp & 1)) update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, m->d_counters, true, fp);
+    else if (set_vid) place_distinct_kernel<<<(unsigned int)((n + 511) / 512), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, fp, m->d_counters);
     else update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, m->d_counters, false, nullptr);
     GB_LAUNCHED();
     return GB_OK;
@@ -1279,7 +1280,7 @@ static long long *tune_field(const char *name)
         { "insert_path", &Tuning::insert_path }, { "single_pass", &Tuning::single_pass }, { "single_pass_min", &Tuning::single_pass_min },
         { "slice_bits", &Tuning::slice_bits }, { "batches", &Tuning::batches }, { "h2d_chunks", &Tuning::h2d_chunks },
         { "route", &Tuning::route }, { "a2a_nccl", &Tuning::a2a_nccl },
-        { "wire_superkmer", &Tuning::wire_superkmer }, { "pgraph_sharded", &Tuning::pgraph_sharded }, { "trace", &Tuning::trace },
+        { "wire_superkmer", &Tuning::wire_superkmer }, { "pgraph_sharded", &Tuning::pgraph_sharded }, { "trace", &Tuning::trace }, { "exp", &Tuning::exp },
     };
     if (name)
         for (const auto &e : table)

@@ -54,7 +54,7 @@ int gb_bench_smem_upsert(int device, int slots_log2, int64_t keys_per_bucket, in
  * its data path: every default is a measured choice, and the parity tests use these keys to force a path that
  * small inputs would not take by themselves.  Keys: insert_path (0 auto, 1 direct, 2 L2-blocked), single_pass,
  * single_pass_min, slice_bits, batches, h2d_chunks, route (0 auto, 1 one level, 2 two levels), a2a_nccl,
- * wire_superkmer, pgraph_sharded, trace.  *previous (optional) receives the old value. */
+ * wire_superkmer, pgraph_sharded, trace, exp (A/B bits of an experiment in progress; 0 in production).  *previous (optional) receives the old value. */
 int gb_tune(const char *name, int64_t value, int64_t *previous);
 int gb_tune_get(const char *name, int64_t *value);
 int gb_version(void);
