@@ -55,6 +55,7 @@ SIGNATURES = {
     "gb_launch_count": (C.c_longlong, []),
     "gb_bench_random_atomics": (C.c_int, [C.c_int, _sz, _i64, C.c_int, _pi64]),
     "gb_bench_smem_upsert": (C.c_int, [C.c_int, C.c_int, _i64, _i64, C.c_int, C.c_int, _pi64, _pi64]),
+    "gb_bench_l2_requests": (C.c_int, [C.c_int, _sz, _i64, C.c_int, C.c_int, _pi64]),
     "gb_tune": (C.c_int, [C.c_char_p, _i64, _pi64]),
     "gb_tune_get": (C.c_int, [C.c_char_p, _pi64]),
     "gb_map_stats": (C.c_int, [_vp, _pi64]),

@@ -71,9 +71,79 @@ bench_smem_upsert_kernel(const unsigned long long *__restrict__ keys, unsigned l
     if ((threadIdx.x & 31) == 0 && nk) atomicAdd(new_keys, (unsigned long long)nk);
 }
 
+// request-rate probe of the L2-atomics upsert's access pattern, hashing and probing stripped away: every update touches one random
+// 16-byte slot of a region that fits L2.  mode 1: 8-byte load only; 2: 4-byte red.add only; 3: load then red (what the upsert does
+// for a key that is already there); 4: load, then 64-bit CAS, then red (a new key).  4 updates per thread in flight like the upsert.
+__global__ void __launch_bounds__(256)
+bench_l2_requests_kernel(Slot *table, unsigned long long slots, long long n, int mode, unsigned long long seed, unsigned long long *sink)
+{
+    const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x);
+    const long long stride = (long long)gridDim.x * 256;
+    unsigned long long idx[4], cur[4], acc = 0;
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const long long i = i0 + j * stride;
+        ok[j] = i < n;
+        idx[j] = __umul64hi(mix64((unsigned long long)i * 0x9E3779B97F4A7C15ull + seed), slots);
+    }
+    if (mode != 2) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (ok[j]) {
+                asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(cur[j]) : "l"(&table[idx[j]].key));
+                acc += cur[j];
+            }
+    }
+    if (mode == 4) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (ok[j]) acc += atomicCAS(&table[idx[j]].key, cur[j], cur[j] + 1);
+    }
+    if (mode >= 2) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (ok[j]) red_add_s32(&table[idx[j]].count, mode == 2 ? 1 : (int)(cur[j] & 1) + 1);
+    }
+    if (acc == 0x123456789ull) *sink = acc; // keeps the loads alive
+}
+
 } // namespace gb
 
 using namespace gb;
+
+extern "C" int gb_bench_l2_requests(int device, size_t region_bytes, int64_t n_updates, int mode, int iters, int64_t *ns_per_iter)
+{
+    if (!ns_per_iter || region_bytes < 1024 || n_updates <= 0 || iters <= 0 || mode < 1 || mode > 4) { set_error("bad arguments"); return GB_E_ARG; }
+    GB_CUDA(cudaSetDevice(device));
+    const unsigned long long slots = region_bytes / sizeof(Slot);
+    Slot *t = nullptr;
+    unsigned long long *sink = nullptr;
+    GB_CUDA(cudaMalloc((void **)&t, slots * sizeof(Slot)));
+    GB_CUDA(cudaMalloc((void **)&sink, 8));
+    GB_CUDA(cudaMemset(t, 0, slots * sizeof(Slot)));
+    cudaEvent_t e0, e1;
+    GB_CUDA(cudaEventCreate(&e0));
+    GB_CUDA(cudaEventCreate(&e1));
+    const unsigned int grid = (unsigned int)((n_updates + 1023) / 1024);
+    bench_l2_requests_kernel<<<grid, 256>>>(t, slots, n_updates, mode, 1, sink);
+    GB_LAUNCHED();
+    GB_CUDA(cudaEventRecord(e0));
+    for (int i = 0; i < iters; i++) {
+        bench_l2_requests_kernel<<<grid, 256>>>(t, slots, n_updates, mode, 2 + i, sink);
+        GB_LAUNCHED();
+    }
+    GB_CUDA(cudaEventRecord(e1));
+    GB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    GB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    *ns_per_iter = (int64_t)(ms * 1e6 / iters);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(t);
+    cudaFree(sink);
+    return GB_OK;
+}
 
 extern "C" int gb_bench_smem_upsert(int device, int slots_log2, int64_t keys_per_bucket, int64_t n_buckets, int ctas_per_sm, int iters,
                                     int64_t *ns_per_iter, int64_t *distinct_keys)

@@ -196,17 +196,22 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
         for (unsigned int b = lane; b < nb; b += 32) rcnt[b] = 0;
         __syncwarp();
         unsigned int bk[SEG], rk[SEG];
+        // all SEG match.any first: they are independent, and their latency (a quarter of this kernel's stall samples when each
+        // was consumed at once, profiles/r2b) overlaps
+#pragma unroll
+        for (int j = 0; j < SEG; j++) {
+            bk[j] = j < cnt ? bucket_of(mix64(key[j]), owners, lp_bits) : 0xFFFFFFFFu;
+            rk[j] = __match_any_sync(0xFFFFFFFFu, bk[j]);
+        }
 #pragma unroll
         for (int j = 0; j < SEG; j++) {
             const bool valid = j < cnt;
-            const unsigned int b = valid ? bucket_of(mix64(key[j]), owners, lp_bits) : 0xFFFFFFFFu;
-            const unsigned int peers_mask = __match_any_sync(0xFFFFFFFFu, b);
+            const unsigned int b = bk[j], peers_mask = rk[j];
             const unsigned int rank = __popc(peers_mask & lt);
             const unsigned int base = valid ? rcnt[b] : 0;
             __syncwarp();
             if (valid && rank == 0) rcnt[b] = base + __popc(peers_mask);
             __syncwarp();
-            bk[j] = b;
             rk[j] = base + rank; // rank among this warp's keys of bucket b in this round
         }
         __syncthreads();

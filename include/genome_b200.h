@@ -50,6 +50,10 @@ int gb_bench_random_atomics(int device, size_t table_bytes, int64_t n_updates, i
  * pass over n_buckets buckets; *distinct_keys (optional) = keys claimed per pass.  The design question of DESIGN.md 3.1. */
 int gb_bench_smem_upsert(int device, int slots_log2, int64_t keys_per_bucket, int64_t n_buckets, int ctas_per_sm, int iters,
                          int64_t *ns_per_iter, int64_t *distinct_keys);
+/* diagnostics: the request rate of the upsert's access pattern with hashing and probing stripped away: n_updates random 16-byte
+ * slots of a region of region_bytes (choose it to fit L2 or not); mode 1 = 8-byte load, 2 = 4-byte red.add, 3 = load then red
+ * (an existing key), 4 = load, 64-bit CAS, red (a new key); 4 updates per thread in flight.  ns per pass. */
+int gb_bench_l2_requests(int device, size_t region_bytes, int64_t n_updates, int mode, int iters, int64_t *ns_per_iter);
 /* tuning and test hooks (process-wide; not part of the reference surface).  The library reads no environment variable on
  * its data path: every default is a measured choice, and the parity tests use these keys to force a path that
  * small inputs would not take by themselves.  Keys: insert_path (0 auto, 1 direct, 2 L2-blocked), single_pass,

@@ -29,19 +29,24 @@ for gb_ in (0.25, 1.0, 1.93, 4.0):
     capi.check(L.gb_bench_random_atomics(0, int(gb_ * 1e9), 96_600_000, 5, C.byref(ns)))
     print(json.dumps({"bench": "random_atomics_u64", "table_gb": gb_, "updates": 96_600_000, "ms": ns.value * 1e-6, "gupdates_per_s": 96.6e6 / ns.value}), flush=True)
 
+for region_mb in (64, 2048):
+    for mode, what in ((1, "load"), (2, "red"), (3, "load+red"), (4, "load+cas+red")):
+        ns = C.c_int64()
+        capi.check(L.gb_bench_l2_requests(0, region_mb << 20, 96_600_000, mode, 5, C.byref(ns)))
+        print(json.dumps({"bench": "l2_requests", "region_mb": region_mb, "mode": what, "ms": ns.value * 1e-6, "gupdates_per_s": 96.6e6 / ns.value,
+                          "cycles_per_update_per_sm_at_1.965GHz": ns.value * 1e-9 * 1.965e9 * 148 / 96.6e6}), flush=True)
+
 b, n, _ = synth.make_config("C2")
 d = torch.zeros(b.size + 16, dtype=torch.uint8, device="cuda")
 d[:b.size].copy_(torch.from_numpy(b))
 cap = 40_200_000
 VARIANTS = [
     ("default (single pass)", {}),
-    ("prefetch", dict(prefetch=1)),
+    ("default again", {}),
+    ("exp=1: survivors through update_keys_kernel", dict(exp=1)),
     ("slices=64", dict(slice_bits=6)),
-    ("slices=64 + prefetch", dict(slice_bits=6, prefetch=1)),
-    ("slices=128 + prefetch", dict(slice_bits=7, prefetch=1)),
     ("slices=16", dict(slice_bits=4)),
     ("counted passes", dict(single_pass=0)),
-    ("counted + prefetch", dict(single_pass=0, prefetch=1)),
     ("counted, 2 sub-batches", dict(single_pass=0, batches=2)),
     ("direct (no bucket pass)", dict(insert_path=1)),
 ]
