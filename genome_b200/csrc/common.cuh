@@ -45,7 +45,8 @@ struct Tuning {
     long long batches = 0;              // sub-batches of one insert call; 0 = default (1 on one GPU, 2 sharded)
     long long h2d_chunks = 4;           // host insert: chunks of the host-to-device copy overlapped with the bucket pass
     long long route = 0;                // sharded insert: 0 = by shard size, 1 = one level (owner, slice) on the wire, 2 = two levels
-    long long a2a_nccl = 0;             // sharded insert: staged ncclSend/ncclRecv instead of stores into the peers' inboxes
+    long long a2a = 0;                  // sharded insert: 0 = the bucket pass stores into the peers' inboxes (NVLink stores), 1 = staged
+                                        // ncclSend/ncclRecv, 2 = local bucket pass + copy-engine pushes into the inboxes
     long long wire_superkmer = 0;       // sharded maps created from now on: minimizer owners, 16-byte super-k-mer records on the wire
     long long pgraph_sharded = 0;       // Graph.buildGraph over shards without a replica (sgraph.cuh)
     long long trace = 0;                // phase timings on stderr
@@ -143,6 +144,9 @@ GB_HD unsigned int owner_of(unsigned long long h, unsigned int parts)
     return (unsigned int)(((h & 0xFFFFFFFFull) * parts) >> 32);
 }
 
+// one-byte fingerprint of a key (never 0: 0 marks an empty slot in the fingerprint array)
+GB_HD unsigned int fp_tag(unsigned long long h) { return (unsigned int)((h >> 20) & 0xFF) | 1u; }
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device memory access helpers
 // table slots are read with L1 bypass (random access, no reuse inside an SM; L1 is not coherent)
@@ -162,8 +166,6 @@ __device__ __forceinline__ void red_add_s32(int *p, int v)
     asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// one-byte fingerprint of a key (never 0: 0 marks an empty slot in the fingerprint array)
-GB_HD unsigned int fp_tag(unsigned long long h) { return (unsigned int)((h >> 20) & 0xFF) | 1u; }
 
 // probe for `key`; returns slot index or -1.  With `fp` (one byte per slot, 0 = empty, else fp_tag of the resident key;
 // 1/16 of the table, L2-resident) the probe walks the fingerprints and touches the table only on a tag match: a

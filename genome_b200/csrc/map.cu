@@ -1279,7 +1279,7 @@ static long long *tune_field(const char *name)
     static const struct { const char *name; long long Tuning::*field; } table[] = {
         { "insert_path", &Tuning::insert_path }, { "single_pass", &Tuning::single_pass }, { "single_pass_min", &Tuning::single_pass_min },
         { "slice_bits", &Tuning::slice_bits }, { "batches", &Tuning::batches }, { "h2d_chunks", &Tuning::h2d_chunks },
-        { "route", &Tuning::route }, { "a2a_nccl", &Tuning::a2a_nccl },
+        { "route", &Tuning::route }, { "a2a", &Tuning::a2a },
         { "wire_superkmer", &Tuning::wire_superkmer }, { "pgraph_sharded", &Tuning::pgraph_sharded }, { "trace", &Tuning::trace }, { "exp", &Tuning::exp },
     };
     if (name)

@@ -125,6 +125,8 @@ SG_HD u32 a_dist(u64 a) { return (u32)(a & 0x7FFFFFFFu); }
 struct Peer {
     const u64 *keys; // [n] the rank's k-mers; index = local vertex id
     const u32 *slot; // [cap] open-addressing index over keys, NONE32 = free
+    const u8 *tag;   // [cap] fingerprint of the key behind slot[i] (fp_tag of its hash, never 0), 0 = free: a negative probe -- 3 of
+                     // 4 in Graph.buildGraph -- ends on one byte, and a tag mismatch skips the two dependent loads (slot, key)
     const u8 *mask8; // [n] out | in << 4 of the stored orientation
     u64 *A;          // [2n] vertex entries
     u64 n, cap;
@@ -213,16 +215,24 @@ SG_HD u32 neighbour_owner(const MinParts &mp, u64 x, u64 rcx, int k, int m, int 
 }
 
 // ---- membership in one rank's index
+// the probe from slot i on, with the tag of slot i already loaded (t8): MasksOp fetches the 8 home tags of a key together
+SG_HD bool probe_from(const Peer &t, u64 key, u32 tg, u64 i, u32 t8, u32 *vid)
+{
+    for (;;) {
+        if (t8 == 0) return false;
+        if (t8 == tg) {
+            const u32 e = t.slot[i];
+            if (t.keys[e] == key) { *vid = e; return true; }
+        }
+        i = next_slot(i, t.cap);
+        t8 = t.tag[i];
+    }
+}
 SG_HD bool probe_idx(const Peer &t, u64 key, u32 *vid)
 {
     if (t.n == 0) return false;
-    u64 i = slot_of(mix64(key), t.cap);
-    for (;;) {
-        const u32 e = t.slot[i];
-        if (e == NONE32) return false;
-        if (t.keys[e] == key) { *vid = e; return true; }
-        i = next_slot(i, t.cap);
-    }
+    const u64 h = mix64(key), i = slot_of(h, t.cap);
+    return probe_from(t, key, fp_tag(h), i, t.tag[i], vid);
 }
 // Graph.buildGraph.contains (Graph.scala:270) with the orientation rules of common.cuh find_oriented: one probe of the
 // canonical orientation unless the two hashes tie or keys were inserted as-is (dual); if both orientations are stored the
@@ -323,12 +333,14 @@ struct OwnerScatterOp { // keys grouped by owner (cursor = exclusive offsets of 
     const u64 *keys; int k, m, P; u64 *cursor; u64 *out;
     SG_HD void operator()(u64 i) const { out[at_inc64_grouped(cursor, owner_of_kmer(keys[i], k, m, P))] = keys[i]; }
 };
-struct IndexInsertOp { // putNew of entry i: first free slot from the key's home
-    const u64 *keys; u32 *slot; u64 cap;
+struct IndexInsertOp { // putNew of entry i: first free slot from the key's home; the slot's tag follows (read only after a barrier)
+    const u64 *keys; u32 *slot; u8 *tag; u64 cap;
     SG_HD void operator()(u64 i) const
     {
-        u64 s = slot_of(mix64(keys[i]), cap);
+        const u64 h = mix64(keys[i]);
+        u64 s = slot_of(h, cap);
         while (at_cas32(slot + s, NONE32, (u32)i) != NONE32) s = next_slot(s, cap);
+        tag[s] = (u8)fp_tag(h);
     }
 };
 struct MasksOp { // incoming / outcoming (Graph.scala:272-282) of every stored key
@@ -341,11 +353,44 @@ struct MasksOp { // incoming / outcoming (Graph.scala:272-282) of every stored k
         if (!is_secondary(c, me, x)) { // a secondary orientation is no vertex: mask 0 = isolated, never referenced
             const u64 rcx = revcomp(x, c.k);
             const MinParts mp = min_parts(x, rcx, c.k, c.m);
-            for (u32 b = 0; b < 4; b++) {
-                u32 g;
-                const Neighbour s = neighbour_of(mp, x, rcx, c.k, c.m, c.P, true, b), p = neighbour_of(mp, x, rcx, c.k, c.m, c.P, false, b);
-                if (find_g(c, s.owner, s.q, s.rq, &g)) { out |= 1u << b; so = g; }
-                if (find_g(c, p.owner, p.q, p.rq, &g)) { in |= 1u << b; si = g; }
+            // the 8 queries first (j = 2b: successor by base b, 2b + 1: predecessor), then their 8 home tags in flight
+            // together -- the owner's index may sit behind an NVLink load -- then the (few) probes that go on
+            u64 cq[8];                 // the orientation to look up (canonical unless the hashes tie or keys are dual)
+            u32 home[8], meta[8], t8[8]; // meta: owner | tag << 8 | strand << 16 | generic << 17
+#pragma unroll
+            for (u32 j = 0; j < 8; j++) {
+                const Neighbour nb = neighbour_of(mp, x, rcx, c.k, c.m, c.P, (j & 1) == 0, j >> 1);
+                const int hq = khash(c, nb.q), hr = khash(c, nb.rq);
+                if (!c.dual && hq != hr) {
+                    cq[j] = hq < hr ? nb.q : nb.rq;
+                    const u64 h = mix64(cq[j]);
+                    home[j] = (u32)slot_of(h, c.peer[nb.owner].cap); // cap < 2^32: a rank holds fewer than 2^30 keys
+                    meta[j] = nb.owner | (fp_tag(h) << 8) | ((u32)(cq[j] != nb.q) << 16);
+                } else {
+                    cq[j] = nb.q;
+                    home[j] = 0;
+                    meta[j] = nb.owner | (1u << 17);
+                }
+            }
+#pragma unroll
+            for (u32 j = 0; j < 8; j++) {
+                const Peer &t = c.peer[meta[j] & 0xFF];
+                t8[j] = (meta[j] >> 17) || t.n == 0 ? 0u : (u32)t.tag[home[j]];
+            }
+#pragma unroll
+            for (u32 j = 0; j < 8; j++) {
+                const u32 owner = meta[j] & 0xFF;
+                u32 g = 0;
+                bool found;
+                if (meta[j] >> 17) {
+                    found = find_g(c, owner, cq[j], revcomp(cq[j], c.k), &g);
+                } else {
+                    u32 vid = 0;
+                    found = probe_from(c.peer[owner], cq[j], (meta[j] >> 8) & 0xFF, home[j], t8[j], &vid);
+                    g = g_make(c, owner, 2 * vid + ((meta[j] >> 16) & 1));
+                }
+                if (!found) continue;
+                if ((j & 1) == 0) { out |= 1u << (j >> 1); so = g; } else { in |= 1u << (j >> 1); si = g; }
             }
         }
         mask8[v] = (u8)(out | (in << 4));
@@ -560,16 +605,17 @@ struct Result {
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline u64 index_cap(u64 n) { return (n * 2 + 1024) / 1024 * 1024; } // load <= 1/2
-// peer window of a rank with n keys: keys | A | slot | mask8
+// peer window of a rank with n keys: keys | A | slot | mask8 | tag
 struct WindowLayout {
-    size_t keys, A, slot, mask8, bytes;
+    size_t keys, A, slot, mask8, tag, bytes;
     explicit WindowLayout(u64 n)
     {
         keys = 0;
         A = align256(keys + (size_t)n * 8);
         slot = align256(A + (size_t)n * 16);
         mask8 = align256(slot + (size_t)index_cap(n) * 4);
-        bytes = align256(mask8 + (size_t)n);
+        tag = align256(mask8 + (size_t)n);
+        bytes = align256(tag + (size_t)index_cap(n));
     }
 };
 inline size_t base_words(u64 n_bases) { return (size_t)((n_bases + 15) / 16) + 2; }
@@ -632,10 +678,11 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
             c.peer[r].A = (u64 *)(b + wl.A);
             c.peer[r].slot = (const u32 *)(b + wl.slot);
             c.peer[r].mask8 = (const u8 *)(b + wl.mask8);
+            c.peer[r].tag = (const u8 *)(b + wl.tag);
             c.peer[r].n = n_of[r];
             c.peer[r].cap = index_cap(n_of[r]);
         }
-        for (int r = P; r < MAXR; r++) c.peer[r] = Peer{ nullptr, nullptr, nullptr, nullptr, 0, 0 };
+        for (int r = P; r < MAXR; r++) c.peer[r] = Peer{ nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0 };
     }
     {
         std::vector<u64 *> send(nl), recv(nl);
@@ -662,7 +709,8 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
         Exec &ex = *in[l].ex;
         const Peer &me = ctx[l].peer[ctx[l].me];
         GB_TRY(sg_fill_ff(ex, (void *)me.slot, (size_t)me.cap * 4));
-        GB_TRY(sg_launch(ex, me.n, IndexInsertOp{ me.keys, (u32 *)me.slot, me.cap }));
+        GB_TRY(sg_zero(ex, (void *)me.tag, (size_t)me.cap));
+        GB_TRY(sg_launch(ex, me.n, IndexInsertOp{ me.keys, (u32 *)me.slot, (u8 *)me.tag, me.cap }));
     }
     GB_TRY(fab.barrier());
 

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Where the sharded insert and the sharded graph build lose time at N GPUs: traces + tuning variants (tuning run: no parity leg).
-#   gpurun --gpus N --timeout 1500 -- 'bash scripts/r2_multi_sweep.sh'
+#   gpurun --gpus N --timeout 1500 -- 'bash scripts/r2_multi_sweep.sh [tests]'
 mkdir -p gpurun_out
 NGPU=$(python -c "import torch; print(torch.cuda.device_count())")
 LOG=gpurun_out/r2_msweep_${NGPU}.log
@@ -21,14 +21,15 @@ except Exception as e:
 PY
 }
 {
-  TAILN=60 run trace "trace=1"
-  TAILN=40 run sgraph_trace "trace=1,pgraph_sharded=1"
+  if [ "$1" = "tests" ]; then
+    echo "== sharded parity tests at $NGPU GPUs"
+    timeout 1200 python -m pytest tests/test_parity_multigpu.py -q -m gpu -x 2>&1 | tail -8
+  fi
+  TAILN=14 run dma_trace "trace=1,a2a=2" --no-graph
+  TAILN=12 run sgraph_trace "trace=1,pgraph_sharded=1"
   run default ""
-  run sgraph "pgraph_sharded=1"
-  run batches4 "batches=4" --no-graph
-  run batches1 "batches=1" --no-graph
-  run route2 "route=2" --no-graph
-  run slices16 "slice_bits=4" --no-graph
-  run slices4 "slice_bits=2" --no-graph
+  run dma "a2a=2" --no-graph
+  run dma_b4 "a2a=2,batches=4" --no-graph
+  run dma_b3_s16 "a2a=2,batches=3,slice_bits=4" --no-graph
 } > $LOG 2>&1
 cat $LOG

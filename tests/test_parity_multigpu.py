@@ -26,8 +26,9 @@ def test_pmap_matches_oracle(gpu, world):
     run_world(world)
 
 
-@pytest.mark.parametrize("env", [{"GENOME_B200_TUNE": "route=2"}, {"GENOME_B200_TUNE": "a2a_nccl=1"}, {"GENOME_B200_TUNE": "batches=5,slice_bits=1"}],
-                         ids=["two-level", "nccl-staged", "many-batches"])
+@pytest.mark.parametrize("env", [{"GENOME_B200_TUNE": "route=2"}, {"GENOME_B200_TUNE": "a2a=1"}, {"GENOME_B200_TUNE": "batches=5,slice_bits=1"},
+                                 {"GENOME_B200_TUNE": "a2a=2"}, {"GENOME_B200_TUNE": "a2a=2,batches=5,route=2"}],
+                         ids=["two-level", "nccl-staged", "many-batches", "dma-push", "dma-push-many-batches-two-level"])
 def test_pmap_routing_variants(gpu, env):
     """The same sharded run through the other routing paths: receiver-side re-bucketing, NCCL send/recv staging instead of
     peer stores, more batches than buffer sets."""
