@@ -339,7 +339,7 @@ def main():
     def make_map(cap):
         return PartitionedDNAMap(K, comm, cap) if world > 1 else ArrayDNAMap(K, cap, device=local_rank)
 
-    def run_workload(name, scale, steps, warmup, with_e2e, with_graph):
+    def run_workload(name, scale, steps, warmup, with_e2e, with_graph, identities=False):
         """Timed loop over one synthetic workload; returns a dict of raw measurements (all ranks call it together)."""
         b, n_reads, windows, G, distinct_total = make_workload(name, rank, world, scale)
         cap = int(distinct_total / world * 1.15) + 1024  # distinct keys expected on this shard
@@ -367,6 +367,16 @@ def main():
             m.delete_below(ROUNDS)
             return w, m.size  # the size read is the step's device->host result
 
+        if identities and cap <= 250_000_000:  # beyond that the export alone is GBs per rank
+            # size-independent properties at full size: the counts of all shards add up to the k-windows issued, no key twice
+            m.clear(cap)
+            assert m.insert_reads_device(d_bin.data_ptr(), b.size, n_reads) == windows
+            ek, ev = m.export()
+            tot = sum_over_ranks(float(ev.astype(np.int64).sum()))
+            out["identities"] = {"sum_of_counts_equals_kmer_instances": bool(tot == sum_over_ranks(float(windows))),
+                                 "keys_distinct_on_this_shard": bool(np.unique(ek).size == ek.size),
+                                 "distinct_keys_total": int(sum_over_ranks(float(ek.size)))}
+            del ek, ev
         sampler = ClockSampler(local_rank)
         sampler.start()
         for _ in range(warmup):
@@ -428,7 +438,11 @@ def main():
                 after = g.counts()
                 g.close()
             ph = m.phase_ns()
+            # sum of edge lengths = (2 kept - oriented terminals - oriented k-mers that are isolated or on perfect
+            # cycles) + edges; isolated k-mers are not counted by the build, so the identity is reported as its slack (>= 0, even)
+            slack = (2 * out["kept_total"] - nn + ne) - nb - gs["cycle_vertices"]
             out["graph"] = {"build_ms": float(np.median(build)), "build_ms_all": build, "build_kernels_ms": float(np.median(kern)),
+                            "edge_length_identity_slack_isolated_kmers": int(slack),
                             "components_retain_simplify_ms": float(np.median(simp)), "timed_passes": reps,
                             "nodes": nn, "edges": ne, "edge_bases": nb, "components": nc, "jump_launches": gs["jump_launches"],
                             "after_simplify": after, "kept_kmers": out["kept_total"],
@@ -455,7 +469,7 @@ def main():
                 print(json.dumps({"parity_checked": False, "parity": parity}))
             raise SystemExit("bench.py: the CUDA path differs from the oracle -- nothing is timed")
 
-    R = run_workload(args.workload, args.scale, args.steps, args.warmup, True, not args.no_graph)
+    R = run_workload(args.workload, args.scale, args.steps, args.warmup, True, not args.no_graph, identities=args.workload != "C2" or args.scale != 1.0)
     m, b, n_reads, windows, cap = R["m"], R["b"], R["n_reads"], R["windows"], R["cap"]
     value = R["total_windows"] / R["step_s"]
     table_bytes = R["table_bytes"]
@@ -563,11 +577,11 @@ def main():
     # ---------------- N > 1: BASELINE configs[2] as named (the 100 Mbp genome over the N GPUs), a few steps
     named = None
     if world > 1 and not args.no_named and args.workload == "C2" and args.scale == 1.0:
-        Rn = run_workload("C3", 1.0 / world, 5, 3, False, not args.no_graph)
+        Rn = run_workload("C3", 1.0 / world, 5, 3, False, not args.no_graph, identities=True)
         named = {"C3": {"workload": "BASELINE configs[2]: 100 Mbp genome with 5% interspersed repeats, 150 bp reads at 50x, k=31, one shard per GPU",
                         "genome_bp": Rn["G"], "kmer_instances_total": Rn["total_windows"], "ms_per_step": Rn["step_s"] * 1e3,
                         "value": Rn["total_windows"] / Rn["step_s"], "unit": "k-mers/s", "steps": 5, "kept_kmers": Rn["kept_total"],
-                        "table_bytes_per_gpu": Rn["table_bytes"], "graph": Rn.get("graph")}}
+                        "table_bytes_per_gpu": Rn["table_bytes"], "identities": Rn.get("identities"), "graph": Rn.get("graph")}}
         release(Rn)
 
     if rank == 0:
@@ -583,7 +597,7 @@ def main():
                                     else "hash-prefix shard per GPU, keys stored into the owners' NVLink inboxes by the bucket pass"),
                        "tuning": tuning or "defaults",
                        "l2": "table (%.2f GB) is re-initialised and randomly written every step: far larger than the 126 MB L2" % (table_bytes / 1e9)},
-            "parity_checked": bool(parity and parity["ok"]), "parity": parity,
+            "parity_checked": bool(parity and parity["ok"]), "parity": parity, "identities": R.get("identities"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "graph": graph,
         }
         if roofline:

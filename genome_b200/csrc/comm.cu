@@ -29,13 +29,18 @@ namespace gb {
 
 
 // one of the two staging sets of the sharded insert; lives as long as the communicator
+// buffer sets of the sharded insert (staging, inbox, events), used round-robin by the batches of one call.  Peer stores need 3 (a rank
+// that has my counts of batch j knows my upsert of j - 2 is over); the copy-engine pipeline issues the transfer of batch j + 1 before
+// it has the counts of batch j, hence 4 (see pmap_insert).
+constexpr int NSETS = 4;
+
 struct BatchBufs {
     unsigned long long *send = nullptr, *recv = nullptr;
     size_t send_cap = 0, recv_cap = 0;
     unsigned long long *d_tot = nullptr, *h_tot = nullptr; // bucket totals (mine, received) and the upsert's chunk table
     PartWork work;  // bucket pass of the outgoing keys (communicator stream)
     PartWork work2; // re-bucketing of the received keys by fine table slice (map stream; two-level routing)
-    cudaEvent_t exchanged = nullptr, inserted = nullptr;
+    cudaEvent_t exchanged = nullptr, inserted = nullptr, scattered = nullptr;
     bool in_flight = false;
     int ensure(size_t ns, size_t nr);
     void release();
@@ -45,12 +50,13 @@ struct Comm {
     int rank = 0, n_ranks = 1, device = 0;
     ncclComm_t nccl = nullptr;
     cudaStream_t stream = nullptr; // bucketing + collectives
-    BatchBufs bufs[3];
+    BatchBufs bufs[NSETS];
+    cudaStream_t xfer = nullptr;   // copy-engine pushes + the count exchange that follows them
     unsigned long long *d_scratch = nullptr, *h_scratch = nullptr;
     // NVLink inboxes (fused routing): inbox[i] holds n_ranks regions of region_cap keys, region s is written by rank s
     // through its peer mapping peer_inbox[i][me] obtained with CUDA IPC
-    unsigned long long *inbox[3] = { nullptr, nullptr, nullptr };
-    unsigned long long *peer_inbox[3][MAX_RANKS];
+    unsigned long long *inbox[NSETS] = {};
+    unsigned long long *peer_inbox[NSETS][MAX_RANKS];
     size_t region_cap = 0;
     int p2p = -1; // -1 unknown, 0 NCCL send/recv staging, 1 peer stores
     // peer window of the sharded graph build (sgraph.cuh): keys, index, masks and vertex entries of this rank, mapped by all
@@ -146,12 +152,13 @@ static int all_to_all_v(Comm *c, const unsigned long long *send, const unsigned 
 }
 
 // fixed-size all-to-all: `row` u64 per pair, row p of d_send goes to rank p, row p of d_recv comes from rank p
-static int all_to_all_rows(Comm *c, const unsigned long long *d_send, unsigned long long *d_recv, size_t row)
+static int all_to_all_rows(Comm *c, const unsigned long long *d_send, unsigned long long *d_recv, size_t row, cudaStream_t st = nullptr)
 {
+    if (!st) st = c->stream;
     GB_NCCL(ncclGroupStart());
     for (int p = 0; p < c->n_ranks; p++) {
-        GB_NCCL(ncclSend(d_send + (size_t)p * row, row, ncclUint64, p, c->nccl, c->stream));
-        GB_NCCL(ncclRecv(d_recv + (size_t)p * row, row, ncclUint64, p, c->nccl, c->stream));
+        GB_NCCL(ncclSend(d_send + (size_t)p * row, row, ncclUint64, p, c->nccl, st));
+        GB_NCCL(ncclRecv(d_recv + (size_t)p * row, row, ncclUint64, p, c->nccl, st));
     }
     GB_NCCL(ncclGroupEnd());
     return GB_OK;
@@ -206,6 +213,7 @@ int BatchBufs::ensure(size_t ns, size_t nr)
         GB_CUDA(cudaHostAlloc((void **)&h_tot, (4 * MAX_BUCKETS + 8) * 8, cudaHostAllocDefault));
         GB_CUDA(cudaEventCreateWithFlags(&exchanged, cudaEventDisableTiming));
         GB_CUDA(cudaEventCreateWithFlags(&inserted, cudaEventDisableTiming));
+        GB_CUDA(cudaEventCreateWithFlags(&scattered, cudaEventDisableTiming));
     }
     return GB_OK;
 }
@@ -218,15 +226,16 @@ void BatchBufs::release()
     if (h_tot) cudaFreeHost(h_tot);
     if (exchanged) cudaEventDestroy(exchanged);
     if (inserted) cudaEventDestroy(inserted);
+    if (scattered) cudaEventDestroy(scattered);
     work.release();
     work2.release();
     send = recv = d_tot = h_tot = nullptr;
-    exchanged = inserted = nullptr;
+    exchanged = inserted = scattered = nullptr;
 }
 
 static void close_inboxes(Comm *c)
 {
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < NSETS; i++) {
         for (int p = 0; p < c->n_ranks; p++)
             if (p != c->rank && c->peer_inbox[i][p]) cudaIpcCloseMemHandle(c->peer_inbox[i][p]);
         if (c->inbox[i]) cudaFree(c->inbox[i]);
@@ -266,7 +275,7 @@ static int ensure_inboxes(Comm *c, size_t want)
     const size_t cap = (size_t)need + (size_t)need / 16 + 1024;
     GB_TRY(comm_scratch(c));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < NSETS; i++) {
         GB_CUDA(cudaMalloc((void **)&c->inbox[i], cap * P * 8));
         cudaIpcMemHandle_t mine;
         GB_CUDA(cudaIpcGetMemHandle(&mine, c->inbox[i]));
@@ -532,7 +541,7 @@ static int drain(Map *m, BatchBufs *bufs)
     m->size += (int64_t)c[0];
     GB_TRY(map_zero_counters(m));
     GB_CUDA(cudaStreamSynchronize(m->stream));
-    bufs[0].in_flight = bufs[1].in_flight = bufs[2].in_flight = false;
+    for (int i = 0; i < NSETS; i++) bufs[i].in_flight = false;
     return GB_OK;
 }
 
@@ -604,11 +613,16 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     GB_CUDA(cudaEventRecord(m->ev0, m->stream));
 
     int64_t windows = 0, pending_upper = 0; // pending_upper: keys handed to upserts not yet folded into m->size
-    for (int64_t b = 0; b < batches; b++) {
-        // three buffer sets: a rank that has received my counts of batch j knows my upsert of batch j - 2 is over
-        // (the wait below precedes them on my stream), so it may store batch j + 1 into set (j + 1) % 3 = (j - 2) % 3
-        BatchBufs &B = bufs[b % 3];
-        if (b >= 2 && bufs[(b - 2) % 3].in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, bufs[(b - 2) % 3].inserted, 0));
+    double t_issue = 0;
+    // ---- stage A of batch b, on the communicator's stream: bucket the canonical k-mers of the batch's reads by (owner, slice) and
+    // get them to their owners, followed by the per-bucket counts ("whoever has my counts has my keys").
+    // Buffer sets: a rank that has received my counts of batch j knows my upsert of batch j - 2 is over (the wait below precedes
+    // them on my stream).  With peer stores it has them before it writes batch j + 1, which may therefore reuse set (j - 2) % 3;
+    // the copy-engine pipeline issues the transfer of batch j + 1 before it has the counts of batch j (only those of j - 1): one
+    // more set.  Both use NSETS = 4.
+    auto stage_a = [&](int64_t b) -> int {
+        BatchBufs &B = bufs[b % NSETS];
+        if (b >= 2 && bufs[(b - 2) % NSETS].in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, bufs[(b - 2) % NSETS].inserted, 0));
         const int64_t r0 = std::min(n_reads, b * batch_reads), r1 = std::min(n_reads, r0 + batch_reads), nr = r1 - r0;
         const int64_t w_upper = fixed ? nr * win_max : (h_win_prefix ? h_win_prefix[r1] - h_win_prefix[r0] : nr * win_max);
         if (B.in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, B.inserted, 0)); // its buffers are still being read
@@ -626,28 +640,32 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
         }
         mark(c->stream);
         if (p2p && dma) {
-            // the bucket pass writes LOCAL staging memory (as fast as on one GPU); the owner segments -- contiguous: buckets are
-            // owner-major -- are then pushed into the owners' inboxes by the copy engines, which run at NVLink speed beside the
-            // kernels instead of stalling the bucket pass on remote stores (measured at P = 4: 0.67 ms per 48 M keys with remote
-            // stores, 0.35 ms local).  The sizes come from the count pass: one host read of NB totals.
-            GB_CUDA(cudaMemcpyAsync(B.h_tot, B.d_tot, NB * 8, cudaMemcpyDeviceToHost, c->stream));
+            // The bucket pass writes LOCAL staging memory (as fast as on one GPU); the owner segments -- contiguous: buckets are
+            // owner-major -- are then pushed into the owners' inboxes by the COPY ENGINES on a second stream, at NVLink speed and
+            // beside the kernels (the next batch's bucket pass, the previous batch's upsert), instead of stalling the bucket pass on
+            // remote stores (measured at P = 4: 0.67 ms per 48 M keys with remote stores, 0.35 ms local).  The sizes come from the
+            // count pass: one host read of NB totals, taken while the scatter behind it runs.
+            GB_CUDA(cudaMemcpyAsync(B.h_tot + 3 * MAX_BUCKETS, B.d_tot, NB * 8, cudaMemcpyDeviceToHost, c->stream));
             GB_CUDA(cudaEventRecord(B.exchanged, c->stream));
             GB_TRY(part_scatter(rb, k, m->v210, pl, B.work, B.send, c->stream));
+            GB_CUDA(cudaEventRecord(B.scattered, c->stream));
             GB_CUDA(cudaEventSynchronize(B.exchanged)); // the totals are on the host; the scatter queued behind them is running
+            GB_CUDA(cudaStreamWaitEvent(c->xfer, B.scattered, 0));
             unsigned long long off = 0;
             for (int p = 0; p < P; p++) {
                 unsigned long long cnt = 0;
-                for (int l = 0; l < LP; l++) cnt += B.h_tot[p * LP + l];
-                if (cnt) GB_CUDA(cudaMemcpyAsync(c->peer_inbox[b % 3][p] + (size_t)c->rank * c->region_cap, B.send + off, cnt * 8, cudaMemcpyDefault, c->stream));
+                for (int l = 0; l < LP; l++) cnt += B.h_tot[3 * MAX_BUCKETS + p * LP + l];
+                if (cnt) GB_CUDA(cudaMemcpyAsync(c->peer_inbox[b % NSETS][p] + (size_t)c->rank * c->region_cap, B.send + off, cnt * 8, cudaMemcpyDefault, c->xfer));
                 off += cnt;
             }
-            // the counts travel AFTER the keys on my stream: whoever has my counts has my keys
-            GB_TRY(all_to_all_rows(c, B.d_tot, B.d_tot + NB, (size_t)LP));
-            GB_CUDA(cudaMemcpyAsync(B.h_tot, B.d_tot, 2 * NB * 8, cudaMemcpyDeviceToHost, c->stream));
+            // the counts travel AFTER the keys on the transfer stream: whoever has my counts has my keys
+            GB_TRY(all_to_all_rows(c, B.d_tot, B.d_tot + NB, (size_t)LP, c->xfer));
+            GB_CUDA(cudaMemcpyAsync(B.h_tot, B.d_tot, 2 * NB * 8, cudaMemcpyDeviceToHost, c->xfer));
+            GB_CUDA(cudaEventRecord(B.exchanged, c->xfer));
         } else if (p2p) {
             PeerOut po;
             memset(&po, 0, sizeof po);
-            for (int p = 0; p < P; p++) po.base[p] = c->peer_inbox[b % 3][p] + (size_t)c->rank * c->region_cap;
+            for (int p = 0; p < P; p++) po.base[p] = c->peer_inbox[b % NSETS][p] + (size_t)c->rank * c->region_cap;
             GB_TRY(part_scatter_peers(rb, k, m->v210, pl, B.work, po, c->stream));
             // the counts travel AFTER the keys on my stream: whoever has my counts has my keys
             GB_TRY(all_to_all_rows(c, B.d_tot, B.d_tot + NB, (size_t)LP));
@@ -656,8 +674,15 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
             GB_TRY(part_scatter(rb, k, m->v210, pl, B.work, B.send, c->stream)); // runs while the host waits for the counts
         }
         mark(c->stream);
-        const double t_issue = now_ms();
-        GB_CUDA(cudaStreamSynchronize(c->stream));
+        t_issue = now_ms();
+        return GB_OK;
+    };
+    // ---- stage B of batch b: with everybody's counts on the host, the chunk table of the received keys (slice-major) and their
+    // upsert on the map's stream
+    auto stage_b = [&](int64_t b) -> int {
+        BatchBufs &B = bufs[b % NSETS];
+        if (p2p && dma) GB_CUDA(cudaEventSynchronize(B.exchanged));
+        else GB_CUDA(cudaStreamSynchronize(c->stream));
         const double t_counts = now_ms();
         unsigned long long scnt[MAX_RANKS], soff[MAX_RANKS], rcnt[MAX_RANKS], roff[MAX_RANKS];
         unsigned long long st = 0, rt = 0;
@@ -670,7 +695,7 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
         windows += (int64_t)st;
         const unsigned long long *recv_keys = nullptr;
         if (p2p) {
-            recv_keys = c->inbox[b % 3];
+            recv_keys = c->inbox[b % NSETS];
         } else {
             GB_TRY(B.ensure(0, (size_t)rt));
             GB_TRY(all_to_all_v(c, B.send, soff, scnt, B.recv, roff, rcnt, ncclUint64));
@@ -696,8 +721,10 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
                 }
             vstart[NB] = v;
         }
-        GB_CUDA(cudaMemcpyAsync(B.d_tot + 2 * NB, vstart, (2 * NB + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-        GB_CUDA(cudaEventRecord(B.exchanged, c->stream));
+        // the transfer stream orders the table behind the keys it describes (dma) / the communicator's stream does
+        cudaStream_t ts = p2p && dma ? c->xfer : c->stream;
+        GB_CUDA(cudaMemcpyAsync(B.d_tot + 2 * NB, vstart, (2 * NB + 1) * 8, cudaMemcpyHostToDevice, ts));
+        GB_CUDA(cudaEventRecord(B.exchanged, ts));
 
         // room for the received keys (every one may be new); grow only with the pipeline drained
         int64_t cap = (int64_t)m->cap;
@@ -734,13 +761,28 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
         pending_upper += (int64_t)rt;
         if (trace) fprintf(stderr, "[pmap] batch %lld: issued %.3f  bucketed+counts %.3f  enqueued %.3f ms (send %llu recv %llu)\n", (long long)b,
                            t_issue - t_begin, t_counts - t_begin, now_ms() - t_begin, st, rt);
+        return GB_OK;
+    };
+    if (p2p && dma) {
+        // software pipeline: the bucket pass of batch b + 1 is queued before the host waits for the transfer of batch b
+        if (batches) GB_TRY(stage_a(0));
+        for (int64_t b = 0; b < batches; b++) {
+            if (b + 1 < batches) GB_TRY(stage_a(b + 1));
+            GB_TRY(stage_b(b));
+        }
+    } else {
+        for (int64_t b = 0; b < batches; b++) {
+            GB_TRY(stage_a(b));
+            GB_TRY(stage_b(b));
+        }
     }
     GB_CUDA(cudaEventRecord(m->ev1, m->stream));
     GB_TRY(drain(m, bufs));
     GB_CUDA(cudaStreamSynchronize(c->stream));
+    GB_CUDA(cudaStreamSynchronize(c->xfer));
     if (trace) {
         fprintf(stderr, "[pmap] drained %.3f ms\n", now_ms() - t_begin);
-        for (size_t b = 0; b + 7 <= tev.size(); b += 7) {
+        for (size_t b = 0; !(p2p && dma) && b + 7 <= tev.size(); b += 7) { // (the pipelined stages interleave their marks)
             float t[7];
             for (int i = 0; i < 7; i++) cudaEventElapsedTime(&t[i], tev[0], tev[b + i]);
             fprintf(stderr, "[pmap] gpu batch %zu: count %.3f-%.3f  counts-exchange -%.3f  scatter -%.3f  all-to-all -%.3f | upsert %.3f-%.3f\n",
@@ -810,6 +852,13 @@ int gb_comm_create(const uint8_t id[GB_UNIQUE_ID_BYTES], int rank, int n_ranks, 
         set_error("stream creation failed");
         return GB_E_CUDA;
     }
+    if (cudaStreamCreateWithFlags(&c->xfer, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaStreamDestroy(c->stream);
+        ncclCommDestroy(c->nccl);
+        delete c;
+        set_error("stream creation failed");
+        return GB_E_CUDA;
+    }
     *out = reinterpret_cast<gb_comm *>(c);
     return GB_OK;
 }
@@ -822,9 +871,8 @@ int gb_comm_destroy(gb_comm *h)
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     close_inboxes(c);
     close_windows(c);
-    c->bufs[0].release();
-    c->bufs[1].release();
-    c->bufs[2].release();
+    for (int i = 0; i < NSETS; i++) c->bufs[i].release();
+    if (c->xfer) { cudaStreamSynchronize(c->xfer); cudaStreamDestroy(c->xfer); }
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     if (c->nccl) ncclCommDestroy(c->nccl);

@@ -150,7 +150,18 @@ SG_HD int khash(const Ctx &c, u64 v) { return c.v210 ? scala_hash<true>(v) : sca
 // min H(1 .. w-2), H(w-1): the successors of x keep positions 1 .. w-1 and add one m-mer at the end, the predecessors keep
 // 0 .. w-2 and add one at the front, so the 8 neighbour owners cost one m-mer hash each.
 constexpr u32 H_NONE = 0xFFFFFFFFu;
-SG_HD u32 mmer_hash(u64 fwd, u64 rc) { return (u32)(mix64(fwd < rc ? fwd : rc) >> 32); }
+// 32-bit finalizer (murmur3 fmix32): the m-mer hashes are the inner loop of the owner function (21 per k-mer, 8 more for its
+// neighbours), and an m-mer has at most 22 bits -- 64-bit multiplies here made MasksOp three times as long as the single-GPU kernel
+SG_HD u32 fmix32(u32 h)
+{
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return h;
+}
+SG_HD u32 mmer_hash(u64 fwd, u64 rc) { return fmix32((u32)(fwd < rc ? fwd : rc) + 0x9E3779B9u); }
 SG_HD int minimizer_len(int k)
 {
     int m = (k + 1) / 2;
@@ -177,7 +188,7 @@ SG_HD MinParts min_parts(u64 x, u64 rcx, int k, int m)
 }
 SG_HD u32 min3(u32 a, u32 b, u32 c) { a = a < b ? a : b; return a < c ? a : c; }
 // the minimum of w hashes crowds towards 0: it is hashed once more before it picks the rank
-SG_HD u32 owner_from_hash(u32 h, int P) { return (u32)(((mix64((u64)h + 1) >> 32) * (u64)P) >> 32); }
+SG_HD u32 owner_from_hash(u32 h, int P) { return (u32)(((u64)fmix32(h ^ 0x7F4A7C15u) * (u64)P) >> 32); }
 SG_HD u32 owner_of_kmer(u64 x, int k, int m, int P)
 {
     const MinParts mp = min_parts(x, revcomp(x, k), k, m);

@@ -23,13 +23,14 @@ PY
 {
   if [ "$1" = "tests" ]; then
     echo "== sharded parity tests at $NGPU GPUs"
-    timeout 1200 python -m pytest tests/test_parity_multigpu.py -q -m gpu -x 2>&1 | tail -8
+    timeout 1200 python -m pytest tests/test_parity_multigpu.py -q -m gpu -x ${TESTSEL:+-k "$TESTSEL"} 2>&1 | tail -8
   fi
-  TAILN=14 run dma_trace "trace=1,a2a=2" --no-graph
+  TAILN=6 run dma_trace "trace=1,a2a=2" --no-graph
   TAILN=12 run sgraph_trace "trace=1,pgraph_sharded=1"
   run default ""
   run dma "a2a=2" --no-graph
+  run dma_b3 "a2a=2,batches=3" --no-graph
   run dma_b4 "a2a=2,batches=4" --no-graph
-  run dma_b3_s16 "a2a=2,batches=3,slice_bits=4" --no-graph
+  run dma_b4_s16 "a2a=2,batches=4,slice_bits=4" --no-graph
 } > $LOG 2>&1
 cat $LOG
