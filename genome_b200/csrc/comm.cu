@@ -575,7 +575,7 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     // fewest passes, but #buckets = P x slices must stay small for NVLink (long store runs), so slices grow with the
     // shard.  TWO: the wire buckets are owners only (longest runs) and the receiver re-buckets each batch by fine slice
     // (one more local pass over 8 B keys) -- keeps the upsert L2-resident for multi-GB shards.
-    int64_t two_level = (int64_t)(sizeof(Slot) * m->cap > (4ull << 30));
+    int64_t two_level = (int64_t)(SLOT_BYTES * m->cap > (4ull << 30));
     if (g_tune.route) two_level = g_tune.route == 2;
     GB_TRY(all_reduce_i64(c, &two_level, ncclMax));
     if (two_level) lp = 0;

@@ -54,15 +54,36 @@ struct Tuning {
 };
 extern Tuning g_tune;
 
+#define GB_HD __host__ __device__ __forceinline__
 // ---------------------------------------------------------------- table layout
-// One 16-byte slot per key: a 32-byte DRAM sector holds two slots, so the key compare, the count
-// update and the graph-phase vertex id of one k-mer touch exactly one sector.
-struct __align__(16) Slot {
-    unsigned long long key; // EMPTY_KEY when free; k <= 31 keys use at most 62 bits
-    int count;              // DNAMap[Int] value
-    unsigned int vid;       // dense vertex id, assigned by gb_graph_build
+// Structure of arrays over ONE allocation of 16 bytes per slot: keys[cap] (u64) | counts[cap] (i32) | vids[cap] (u32).
+// Why not one 16-byte record per slot (rounds 1 and 2a): on B200 a 128-byte L2 line that is both READ (key compare) and WRITTEN
+// (count red) costs twice the L2 time of the same requests on separate lines -- measured with the access pattern alone,
+// profiles/r2c_l2_request_modes*.jsonl: load + red on one slot 4.2 cycles per update per SM, on separate arrays 2.1; different
+// sectors of one line do not help (4.25).  With the arrays apart the key lines are read-mostly (written once per distinct key by
+// the claiming CAS), the count lines are written only, and the vertex ids are not touched before Graph.buildGraph.
+struct Table {
+    unsigned long long *key = nullptr; // EMPTY_KEY when free; k <= 31 keys use at most 62 bits
+    int *count = nullptr;              // DNAMap[Int] value
+    unsigned int *vid = nullptr;       // dense vertex id, assigned by gb_graph_build / deleteAll
+    unsigned long long cap = 0;
 };
-static_assert(sizeof(Slot) == 16, "slot must be 16 bytes");
+constexpr size_t SLOT_BYTES = 16;
+GB_HD Table table_view(void *base, unsigned long long cap)
+{
+    Table t;
+    t.key = static_cast<unsigned long long *>(base);
+    t.count = reinterpret_cast<int *>(t.key + cap);
+    t.vid = reinterpret_cast<unsigned int *>(t.count + cap);
+    t.cap = cap;
+    return t;
+}
+// one slot's contents in registers
+struct Slot {
+    unsigned long long key;
+    int count;
+    unsigned int vid;
+};
 
 constexpr unsigned long long EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
 constexpr unsigned int NONE32 = 0xFFFFFFFFu;
@@ -70,7 +91,6 @@ constexpr unsigned int NONE32 = 0xFFFFFFFFu;
 constexpr int SM_COUNT = 148; // B200
 
 // ---------------------------------------------------------------- k-mer arithmetic (device + host)
-#define GB_HD __host__ __device__ __forceinline__
 
 // Long1DNASeq.hashCode = long.## (S/dna/DNASeq.scala:103), scala-library 2.9.1: iv = (int)v;
 // if (iv == v) iv else (int)(v ^ (v >>> 32)).  For 0 <= v < 2^62 both branches equal (int)(v ^ (v >>> 32)).
@@ -149,15 +169,31 @@ GB_HD unsigned int fp_tag(unsigned long long h) { return (unsigned int)((h >> 20
 
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device memory access helpers
-// table slots are read with L1 bypass (random access, no reuse inside an SM; L1 is not coherent)
-__device__ __forceinline__ Slot load_slot(const Slot *p)
+// table arrays are read with L1 bypass (random access, no reuse inside an SM; L1 is not coherent)
+__device__ __forceinline__ unsigned long long load_key(const Table &t, unsigned long long i)
+{
+    unsigned long long k;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(k) : "l"(t.key + i));
+    return k;
+}
+__device__ __forceinline__ int load_count(const Table &t, unsigned long long i)
+{
+    int c;
+    asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(c) : "l"(t.count + i));
+    return c;
+}
+__device__ __forceinline__ unsigned int load_vid(const Table &t, unsigned long long i)
+{
+    unsigned int v;
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(t.vid + i));
+    return v;
+}
+__device__ __forceinline__ Slot load_slot(const Table &t, unsigned long long i)
 {
     Slot s;
-    unsigned int lo, hi, c, v;
-    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(c), "=r"(v) : "l"(p));
-    s.key = ((unsigned long long)hi << 32) | lo;
-    s.count = (int)c;
-    s.vid = v;
+    s.key = load_key(t, i);
+    s.count = load_count(t, i);
+    s.vid = load_vid(t, i);
     return s;
 }
 
@@ -167,30 +203,26 @@ __device__ __forceinline__ void red_add_s32(int *p, int v)
 }
 
 
-// probe for `key`; returns slot index or -1.  With `fp` (one byte per slot, 0 = empty, else fp_tag of the resident key;
-// 1/16 of the table, L2-resident) the probe walks the fingerprints and touches the table only on a tag match: a
-// negative probe -- 3 of 4 in Graph.buildGraph -- costs no DRAM access.
-__device__ __forceinline__ long long probe_find(const Slot *table, unsigned long long cap, unsigned long long key, Slot *out,
-                                                const uint8_t *fp = nullptr)
+// probe for `key`; returns slot index or -1 (the caller loads the count or the vertex id it needs: they live in other arrays).
+// With `fp` (one byte per slot, 0 = empty, else fp_tag of the resident key; 1/16 of the table, L2-resident) the probe walks the
+// fingerprints and touches the table only on a tag match: a negative probe -- 3 of 4 in Graph.buildGraph -- costs no DRAM access.
+__device__ __forceinline__ long long probe_find(const Table &table, unsigned long long key, const uint8_t *fp = nullptr)
 {
-    const unsigned long long h = mix64(key);
+    const unsigned long long h = mix64(key), cap = table.cap;
     unsigned long long i = slot_of(h, cap);
     if (fp) {
         const unsigned int tag = fp_tag(h);
         for (;;) {
             const unsigned int t = fp[i];
             if (t == 0) return -1;
-            if (t == tag) {
-                Slot s = load_slot(table + i);
-                if (s.key == key) { *out = s; return (long long)i; }
-            }
+            if (t == tag && load_key(table, i) == key) return (long long)i;
             i = next_slot(i, cap);
         }
     }
     for (;;) { // the table is never full (map_budget), so an EMPTY slot always ends the probe
-        Slot s = load_slot(table + i);
-        if (s.key == key) { *out = s; return (long long)i; }
-        if (s.key == EMPTY_KEY) return -1;
+        const unsigned long long cur = load_key(table, i);
+        if (cur == key) return (long long)i;
+        if (cur == EMPTY_KEY) return -1;
         i = next_slot(i, cap);
     }
 }
@@ -200,39 +232,39 @@ __device__ __forceinline__ long long probe_find(const Slot *table, unsigned long
 // decides; both orientations are probed only when the two hashes tie (FreqFilter's rule then stores
 // either orientation) or when keys were inserted as-is through update (dual).  If both
 // orientations are stored, the numerically smaller key is the PRIMARY one: it alone carries a vertex id.
-// On success *slot is the primary stored slot and *strand = 1 when that stored key is rc(q) != q.
+// On success *slot is the index of the primary stored slot and *strand = 1 when that stored key is rc(q) != q.
 template <bool V210>
-__device__ __forceinline__ bool find_oriented(const Slot *table, unsigned long long cap, int k, bool dual,
-                                              unsigned long long q, Slot *slot, unsigned int *strand, const uint8_t *fp = nullptr)
+__device__ __forceinline__ bool find_oriented(const Table &table, int k, bool dual, unsigned long long q, unsigned long long *slot,
+                                              unsigned int *strand, const uint8_t *fp = nullptr)
 {
     unsigned long long r = revcomp(q, k);
     int hq = scala_hash<V210>(q), hr = scala_hash<V210>(r);
     if (!dual && hq != hr) {
         unsigned long long c = hq < hr ? q : r;
-        if (probe_find(table, cap, c, slot, fp) < 0) return false;
+        const long long i = probe_find(table, c, fp);
+        if (i < 0) return false;
+        *slot = (unsigned long long)i;
         *strand = c != q;
         return true;
     }
-    Slot sq, sr;
-    bool fq = probe_find(table, cap, q, &sq, fp) >= 0;
-    bool fr = r != q && probe_find(table, cap, r, &sr, fp) >= 0;
-    if (!fq && !fr) return false;
-    bool use_r = fr && (!fq || r < q);
-    *slot = use_r ? sr : sq;
+    const long long iq = probe_find(table, q, fp);
+    const long long ir = r != q ? probe_find(table, r, fp) : -1;
+    if (iq < 0 && ir < 0) return false;
+    bool use_r = ir >= 0 && (iq < 0 || r < q);
+    *slot = (unsigned long long)(use_r ? ir : iq);
     *strand = use_r;
     return true;
 }
 
 // a stored key is SECONDARY (no vertex of its own) when rc(key) is stored too and is numerically smaller
 template <bool V210>
-__device__ __forceinline__ bool is_secondary(const Slot *table, unsigned long long cap, int k, bool dual, unsigned long long key,
+__device__ __forceinline__ bool is_secondary(const Table &table, int k, bool dual, unsigned long long key,
                                              const uint8_t *fp = nullptr)
 {
     unsigned long long r = revcomp(key, k);
     if (r >= key) return false;
     if (!dual && scala_hash<V210>(key) != scala_hash<V210>(r)) return false;
-    Slot s;
-    return probe_find(table, cap, r, &s, fp) >= 0;
+    return probe_find(table, r, fp) >= 0;
 }
 #endif
 
@@ -366,9 +398,10 @@ struct Map {
     bool v210 = false;
     bool noncanonical = false; // keys were inserted through update/update_counts as-is
     unsigned long long cap = 0; // capacity in slots (any multiple of 1024)
-    Slot *table = nullptr;
+    void *table = nullptr;     // keys | counts | vids of `cap` slots, packed at the front of the allocation (table_view)
     unsigned long long alloc_cap = 0; // the allocation behind `table` holds this many slots (>= cap)
-    Slot *spare = nullptr;     // the other table allocation of the clear / filter cycle, kept for reuse
+    void *spare = nullptr;     // the other table allocation of the clear / filter cycle, kept for reuse
+    Table view() const { return table_view(table, cap); }
     unsigned long long spare_cap = 0;
     unsigned long long *stage = nullptr; // key staging of the partitioned insert and of the filter (grow-only)
     size_t stage_cap = 0;
@@ -424,8 +457,8 @@ inline unsigned int grid_for(unsigned long long n, int threads, int per_sm = 16)
     if (g > cap) g = cap;
     return (unsigned int)(g ? g : 1);
 }
-int map_swap_table(Map *m, unsigned long long new_cap, Slot **old_table, unsigned long long *old_alloc_cap);
-void map_retire_table(Map *m, Slot *t, unsigned long long alloc_cap);
+int map_swap_table(Map *m, unsigned long long new_cap, void **old_table, unsigned long long *old_alloc_cap);
+void map_retire_table(Map *m, void *t, unsigned long long alloc_cap);
 int map_stage(Map *m, size_t n_u64);
 int pool_setup(int device);
 inline unsigned long long cap_for(int64_t keys)

@@ -131,33 +131,25 @@ __device__ __forceinline__ int item_keys(const ReadTile &tile, unsigned int item
     return cnt;
 }
 
-__device__ __forceinline__ unsigned long long load_key(const Slot *p)
-{
-    unsigned long long k;
-    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(k) : "l"(&p->key));
-    return k;
-}
-
 // update(key, 1, _ + 1) (S/ds/ArrayDNAMap.scala:129-150) starting at slot idx whose key was already loaded
 // into `cur`.  The caller guarantees the table never fills (map_budget), so the probe always terminates.
 // Returns 1 when the key was new.
-__device__ __forceinline__ int upsert_add(Slot *table, unsigned long long cap, unsigned long long idx,
-                                          unsigned long long cur, unsigned long long key, int add)
+__device__ __forceinline__ int upsert_add(const Table &table, unsigned long long idx, unsigned long long cur, unsigned long long key, int add)
 {
     for (;;) {
         if (cur == key) {
-            red_add_s32(&table[idx].count, add);
+            red_add_s32(table.count + idx, add);
             return 0;
         }
         if (cur == EMPTY_KEY) {
-            unsigned long long old = atomicCAS(&table[idx].key, EMPTY_KEY, key);
+            unsigned long long old = atomicCAS(table.key + idx, EMPTY_KEY, key);
             if (old == EMPTY_KEY || old == key) {
-                red_add_s32(&table[idx].count, add);
+                red_add_s32(table.count + idx, add);
                 return old == EMPTY_KEY;
             }
         }
-        idx = next_slot(idx, cap);
-        cur = load_key(table + idx);
+        idx = next_slot(idx, table.cap);
+        cur = load_key(table, idx);
     }
 }
 #endif

@@ -68,21 +68,21 @@ __device__ __forceinline__ unsigned long long oriented_kmer(unsigned long long k
 constexpr int TILE = 1024; // slots per CTA tile in the compaction passes (256 threads x 4)
 
 template <bool V210>
-__device__ __forceinline__ bool slot_is_vertex(const Slot *table, unsigned long long cap, int k, bool dual, const Slot &s)
+__device__ __forceinline__ bool slot_is_vertex(const Table &table, int k, bool dual, unsigned long long key)
 {
-    return s.key != EMPTY_KEY && !is_secondary<V210>(table, cap, k, dual, s.key);
+    return key != EMPTY_KEY && !is_secondary<V210>(table, k, dual, key);
 }
 
 template <bool V210>
 __global__ void __launch_bounds__(256)
-count_vertices_kernel(const Slot *table, unsigned long long cap, int k, bool dual, unsigned long long *tile_count)
+count_vertices_kernel(Table table, int k, bool dual, unsigned long long *tile_count)
 {
-    const unsigned long long n = cap;
+    const unsigned long long n = table.cap;
     unsigned int c = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         unsigned long long i = (unsigned long long)blockIdx.x * TILE + j * 256 + threadIdx.x;
-        if (i < n) c += slot_is_vertex<V210>(table, cap, k, dual, load_slot(table + i));
+        if (i < n) c += slot_is_vertex<V210>(table, k, dual, load_key(table, i));
     }
     unsigned long long base = block_alloc(c, nullptr); // exclusive prefix inside the CTA, no counter
     __shared__ unsigned int s_total;
@@ -94,21 +94,20 @@ count_vertices_kernel(const Slot *table, unsigned long long cap, int k, bool dua
 // assigns vid in slot order (deterministic), writes keys[vid] and the slot's vid field
 template <bool V210>
 __global__ void __launch_bounds__(256)
-assign_vertices_kernel(Slot *table, unsigned long long cap, int k, bool dual, const unsigned long long *tile_base,
-                       unsigned long long *keys)
+assign_vertices_kernel(Table table, int k, bool dual, const unsigned long long *tile_base, unsigned long long *keys)
 {
-    const unsigned long long n = cap;
+    const unsigned long long n = table.cap;
     // thread t owns 4 CONSECUTIVE slots so that vids follow slot order
     unsigned long long i0 = (unsigned long long)blockIdx.x * TILE + threadIdx.x * 4;
-    Slot s[4];
+    unsigned long long s[4];
     bool live[4];
     unsigned int c = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         live[j] = false;
         if (i0 + j < n) {
-            s[j] = load_slot(table + i0 + j);
-            live[j] = slot_is_vertex<V210>(table, cap, k, dual, s[j]);
+            s[j] = load_key(table, i0 + j);
+            live[j] = slot_is_vertex<V210>(table, k, dual, s[j]);
         }
         c += live[j];
     }
@@ -116,8 +115,8 @@ assign_vertices_kernel(Slot *table, unsigned long long cap, int k, bool dual, co
 #pragma unroll
     for (int j = 0; j < 4; j++)
         if (live[j]) {
-            keys[v] = s[j].key;
-            table[i0 + j].vid = (unsigned int)v;
+            keys[v] = s[j];
+            table.vid[i0 + j] = (unsigned int)v;
             v++;
         }
 }
@@ -128,14 +127,15 @@ assign_vertices_kernel(Slot *table, unsigned long long cap, int k, bool dual, co
 // orientation of a k-mer stored twice (hash tie / as-is inserts): it is no vertex (mask 0 = isolated, never referenced).
 template <bool V210>
 __global__ void __launch_bounds__(256)
-masks_kernel(const Slot *table, unsigned long long cap, int k, bool dual, const unsigned long long *keys, unsigned long long lo,
+masks_kernel(Table table, int k, bool dual, const unsigned long long *keys, unsigned long long lo,
              unsigned long long n, bool check_secondary, const uint8_t *fp, uint8_t *mask8, unsigned int *nbr_out, unsigned int *nbr_in)
 {
+    const unsigned long long cap = table.cap;
     unsigned long long v = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= lo + n) return;
     const unsigned long long x = keys[v];
     unsigned int out = 0, in = 0, so = NONE32, si = NONE32;
-    if (check_secondary && is_secondary<V210>(table, cap, k, dual, x, fp)) {
+    if (check_secondary && is_secondary<V210>(table, k, dual, x, fp)) {
         mask8[v] = 0;
         nbr_out[v] = NONE32;
         nbr_in[v] = NONE32;
@@ -163,27 +163,25 @@ masks_kernel(const Slot *table, unsigned long long cap, int k, bool dual, const 
         for (int j = 0; j < 8; j++) t0[j] = fp[hm[j]];
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            Slot s;
+            unsigned long long at = 0;
             unsigned int strand = st[j];
             bool found = false;
             if (!simple[j]) {
                 const unsigned long long q = j < 4 ? kmer_append(x, k, j) : kmer_prepend(x, k, j - 4);
-                found = find_oriented<V210>(table, cap, k, dual, q, &s, &strand, fp);
+                found = find_oriented<V210>(table, k, dual, q, &at, &strand, fp);
             } else {
                 unsigned long long i = hm[j];
                 unsigned int t = t0[j];
                 while (t != 0) {
-                    if (t == tg[j]) {
-                        s = load_slot(table + i);
-                        if (s.key == cq[j]) { found = true; break; }
-                    }
+                    if (t == tg[j] && load_key(table, i) == cq[j]) { found = true; at = i; break; }
                     i = next_slot(i, cap);
                     t = fp[i];
                 }
             }
             if (found) {
-                if (j < 4) { out |= 1u << j; so = 2 * s.vid + strand; }
-                else { in |= 1u << (j - 4); si = 2 * s.vid + strand; }
+                const unsigned int w = 2 * load_vid(table, at) + strand;
+                if (j < 4) { out |= 1u << j; so = w; }
+                else { in |= 1u << (j - 4); si = w; }
             }
         }
         mask8[v] = (uint8_t)(out | (in << 4));
@@ -193,15 +191,15 @@ masks_kernel(const Slot *table, unsigned long long cap, int k, bool dual, const 
     }
 #pragma unroll
     for (unsigned int b = 0; b < 4; b++) {
-        Slot s;
+        unsigned long long at;
         unsigned int strand;
-        if (find_oriented<V210>(table, cap, k, dual, kmer_append(x, k, b), &s, &strand)) {
+        if (find_oriented<V210>(table, k, dual, kmer_append(x, k, b), &at, &strand)) {
             out |= 1u << b;
-            so = 2 * s.vid + strand;
+            so = 2 * load_vid(table, at) + strand;
         }
-        if (find_oriented<V210>(table, cap, k, dual, kmer_prepend(x, k, b), &s, &strand)) {
+        if (find_oriented<V210>(table, k, dual, kmer_prepend(x, k, b), &at, &strand)) {
             in |= 1u << b;
-            si = 2 * s.vid + strand;
+            si = 2 * load_vid(table, at) + strand;
         }
     }
     mask8[v] = (uint8_t)(out | (in << 4));
@@ -211,8 +209,7 @@ masks_kernel(const Slot *table, unsigned long long cap, int k, bool dual, const 
 
 // gb_map_neighbour_masks: the same probes for arbitrary query k-mers
 template <bool V210>
-__global__ void query_masks_kernel(const Slot *table, unsigned long long cap, int k, bool dual, const unsigned long long *q,
-                                   long long n, uint8_t *masks)
+__global__ void query_masks_kernel(Table table, int k, bool dual, const unsigned long long *q, long long n, uint8_t *masks)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -220,10 +217,10 @@ __global__ void query_masks_kernel(const Slot *table, unsigned long long cap, in
     unsigned int out = 0, in = 0;
 #pragma unroll
     for (unsigned int b = 0; b < 4; b++) {
-        Slot s;
+        unsigned long long at;
         unsigned int strand;
-        if (find_oriented<V210>(table, cap, k, dual, kmer_append(x, k, b), &s, &strand)) out |= 1u << b;
-        if (find_oriented<V210>(table, cap, k, dual, kmer_prepend(x, k, b), &s, &strand)) in |= 1u << b;
+        if (find_oriented<V210>(table, k, dual, kmer_append(x, k, b), &at, &strand)) out |= 1u << b;
+        if (find_oriented<V210>(table, k, dual, kmer_prepend(x, k, b), &at, &strand)) in |= 1u << b;
     }
     masks[i] = (uint8_t)(out | (in << 4));
 }
@@ -298,7 +295,7 @@ __global__ void init_vertices_kernel(BuildArrays B, const unsigned long long *no
 // buildEdges (Graph.scala:349-365), first step of every edge: one thread per oriented vertex that is a node.
 // Edge ids follow (node index, base) order; out-bases are visited in Base.fromInt order (351).
 template <bool V210>
-__global__ void start_edges_kernel(BuildArrays B, const Slot *table, unsigned long long cap, bool dual,
+__global__ void start_edges_kernel(BuildArrays B, Table table, bool dual,
                                    const unsigned long long *node_idx, const unsigned long long *edge_idx,
                                    unsigned long long *A, unsigned int *edge_start, unsigned int *edge_end,
                                    unsigned long long *edge_len)
@@ -312,10 +309,10 @@ __global__ void start_edges_kernel(BuildArrays B, const Slot *table, unsigned lo
     const unsigned int me = (unsigned int)node_idx[u];
     for (unsigned int b = 0; b < 4; b++) {
         if (!(out & (1u << b))) continue;
-        Slot s;
+        unsigned long long at = 0;
         unsigned int strand = 0;
-        find_oriented<V210>(table, cap, B.k, dual, kmer_append(x, B.k, b), &s, &strand); // present by construction
-        unsigned int w = normalise(B, 2 * s.vid + strand), wo, wi;
+        find_oriented<V210>(table, B.k, dual, kmer_append(x, B.k, b), &at, &strand); // present by construction
+        unsigned int w = normalise(B, 2 * load_vid(table, at) + strand), wo, wi;
         edge_start[e] = me;
         if (vertex_type(B, w, &wo, &wi) == TAG_TERM) {
             edge_end[e] = (unsigned int)node_idx[w];
@@ -820,14 +817,14 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
         const unsigned long long tiles = (slots + TILE - 1) / TILE;
         Tmp<unsigned long long> tile_cnt;
         GB_TRY(tile_cnt.alloc(tiles, st));
-        count_vertices_kernel<V210><<<(unsigned int)tiles, 256, 0, st>>>(m->table, bits, k, dual, tile_cnt.p);
+        count_vertices_kernel<V210><<<(unsigned int)tiles, 256, 0, st>>>(m->view(), k, dual, tile_cnt.p);
         GB_LAUNCHED();
         GB_TRY(exclusive_scan_u64(tile_cnt.p, tiles, total.p, st));
         GB_TRY(read_u64(total.p, &n, 1, st));
         if (n >= (1ull << 30)) { set_error("%llu stored k-mers on one GPU: the graph build addresses at most 2^30", n); return GB_E_CAPACITY; }
         tick("counted vertices");
         GB_TRY(keys_tmp.alloc(n, st));
-        assign_vertices_kernel<V210><<<(unsigned int)tiles, 256, 0, st>>>(m->table, bits, k, dual, tile_cnt.p, keys_tmp.p);
+        assign_vertices_kernel<V210><<<(unsigned int)tiles, 256, 0, st>>>(m->view(), k, dual, tile_cnt.p, keys_tmp.p);
         GB_LAUNCHED();
         keys_p = keys_tmp.p;
     }
@@ -847,7 +844,7 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
         const unsigned long long lo = sp ? sp->lo : 0, cnt = sp ? sp->hi - sp->lo : n;
         // the fingerprint array is built together with the vertex array (deleteAll / replica insert)
         const uint8_t *fp = given ? m->fp : nullptr;
-        LAUNCH(masks_kernel<V210>, cnt, m->table, bits, k, dual, keys.p, lo, cnt, given, fp, mask8.p, nbr_out.p, nbr_in.p);
+        LAUNCH(masks_kernel<V210>, cnt, m->view(), k, dual, keys.p, lo, cnt, given, fp, mask8.p, nbr_out.p, nbr_in.p);
         GB_CUDA(cudaEventRecord(m->fev[1], st));
         if (sp) {
             GB_CUDA(cudaStreamSynchronize(st));
@@ -886,7 +883,7 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
     Tmp<unsigned long long> A;
     GB_TRY(A.alloc(n2, st));
     LAUNCH(init_vertices_kernel, n2, B, node_idx.p, A.p, g->node_kmer);
-    LAUNCH(start_edges_kernel<V210>, n2, B, m->table, bits, dual, node_idx.p, edge_idx.p, A.p, g->edge_start, g->edge_end,
+    LAUNCH(start_edges_kernel<V210>, n2, B, m->view(), dual, node_idx.p, edge_idx.p, A.p, g->edge_start, g->edge_end,
            g->edge_off);
     node_idx.release();
 
@@ -1091,8 +1088,8 @@ int gb_map_neighbour_masks(gb_map *h, const uint64_t *keys, int64_t n, uint8_t *
     GB_TRY(dk.alloc((size_t)n * 8));
     GB_TRY(dm.alloc((size_t)n));
     GB_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-    if (m->v210) LAUNCH(query_masks_kernel<true>, n, m->table, m->cap, m->k, m->noncanonical, (const unsigned long long *)dk.p, n, (uint8_t *)dm.p);
-    else LAUNCH(query_masks_kernel<false>, n, m->table, m->cap, m->k, m->noncanonical, (const unsigned long long *)dk.p, n, (uint8_t *)dm.p);
+    if (m->v210) LAUNCH(query_masks_kernel<true>, n, m->view(), m->k, m->noncanonical, (const unsigned long long *)dk.p, n, (uint8_t *)dm.p);
+    else LAUNCH(query_masks_kernel<false>, n, m->view(), m->k, m->noncanonical, (const unsigned long long *)dk.p, n, (uint8_t *)dm.p);
     GB_CUDA(cudaMemcpyAsync(masks, dm.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     GB_CUDA(cudaStreamSynchronize(st));
     return GB_OK;

@@ -93,12 +93,18 @@ int pool_setup(int)
 
 // ================================================================ kernels
 
-__global__ void init_table_kernel(Slot *t, unsigned long long n)
+// EMPTY table: keys = all ones, counts = 0; with_vid: vertex ids = NONE too.  n is a multiple of 1024 (cap_for), so every array
+// is a whole number of 16-byte vectors.  The vertex ids of a counting table are never read before they are assigned
+// (assign_vertices_kernel / place_distinct_kernel write them for every vertex), so the clear of a FreqFilter pass moves 12 bytes
+// per slot, not 16.
+__global__ void init_table_kernel(Table t, bool with_vid)
 {
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    uint4 e = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, NONE32);
-    for (; i < n; i += stride) reinterpret_cast<uint4 *>(t)[i] = e;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), zero = make_uint4(0u, 0u, 0u, 0u);
+    for (unsigned long long i = i0; i < t.cap / 2; i += stride) reinterpret_cast<uint4 *>(t.key)[i] = ones;
+    for (unsigned long long i = i0; i < t.cap / 4; i += stride) reinterpret_cast<uint4 *>(t.count)[i] = zero;
+    if (with_vid)
+        for (unsigned long long i = i0; i < t.cap / 4; i += stride) reinterpret_cast<uint4 *>(t.vid)[i] = ones;
 }
 
 // ---------------------------------------------------------------- bulk FreqFilter.add
@@ -108,8 +114,7 @@ template <bool FIXED, bool V210>
 __global__ void __launch_bounds__(INSERT_THREADS)
 insert_reads_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes,
                     const unsigned long long *__restrict__ offsets, unsigned int rec_bytes,
-                    long long read0, long long n_reads, int k, Slot *table, unsigned long long cap,
-                    unsigned long long *counters)
+                    long long read0, long long n_reads, int k, Table table, unsigned long long *counters)
 {
     __shared__ ReadTile tile;
     __shared__ unsigned int s_newkeys;
@@ -125,13 +130,13 @@ insert_reads_kernel(const uint8_t *__restrict__ bin, unsigned long long n_bytes,
         unsigned long long key[SEG], idx[SEG], cur[SEG];
         const int cnt = item_keys<V210>(tile, item, k, key);
 #pragma unroll
-        for (int j = 0; j < SEG; j++) idx[j] = slot_of(mix64(key[j]), cap);
+        for (int j = 0; j < SEG; j++) idx[j] = slot_of(mix64(key[j]), table.cap);
 #pragma unroll
         for (int j = 0; j < SEG; j++)
-            if (j < cnt) cur[j] = load_key(table + idx[j]);
+            if (j < cnt) cur[j] = load_key(table, idx[j]);
 #pragma unroll
         for (int j = 0; j < SEG; j++)
-            if (j < cnt) newkeys += upsert_add(table, cap, idx[j], cur[j], key[j], 1);
+            if (j < cnt) newkeys += upsert_add(table, idx[j], cur[j], key[j], 1);
     }
 
     // one global atomic per CTA for the size counter
@@ -191,7 +196,7 @@ __global__ void verify_records_kernel(const uint8_t *__restrict__ bin, unsigned 
 // SET: update(key, v); set_vid: additionally slot.vid = the key's index in `keys` (keys must be distinct then)
 template <bool SET>
 __global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ vals,
-                                   long long n, Slot *table, unsigned long long cap, unsigned long long *counters, bool set_vid = false,
+                                   long long n, Table table, unsigned long long *counters, bool set_vid = false,
                                    uint8_t *fp = nullptr)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -199,19 +204,20 @@ __global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, 
     if (i < n) {
         unsigned long long key = keys[i];
         const unsigned long long h = mix64(key);
+        const unsigned long long cap = table.cap;
         unsigned long long idx = slot_of(h, cap);
         if (!SET) {
-            nk = upsert_add(table, cap, idx, load_key(table + idx), key, 1);
+            nk = upsert_add(table, idx, load_key(table, idx), key, 1);
         } else {
             for (;;) {
-                unsigned long long cur = load_key(table + idx);
+                unsigned long long cur = load_key(table, idx);
                 if (cur == EMPTY_KEY) {
-                    cur = atomicCAS(&table[idx].key, EMPTY_KEY, key);
+                    cur = atomicCAS(table.key + idx, EMPTY_KEY, key);
                     if (cur == EMPTY_KEY) { nk = 1; cur = key; }
                 }
                 if (cur == key) {
-                    atomicExch(&table[idx].count, vals[i]);
-                    if (set_vid) table[idx].vid = (unsigned int)i;
+                    atomicExch(table.count + idx, vals[i]);
+                    if (set_vid) table.vid[idx] = (unsigned int)i;
                     if (fp) fp[idx] = (uint8_t)fp_tag(h);
                     break;
                 }
@@ -228,9 +234,10 @@ __global__ void update_keys_kernel(const unsigned long long *__restrict__ keys, 
 // store; two keys per thread in flight.  Replaces update_keys_kernel<true> here: 5 L2 requests per key (load, CAS, exchange,
 // two stores) became 3 (measured on C2's 4.6 M survivors: 0.51 ms before).
 __global__ void __launch_bounds__(256)
-place_distinct_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ vals, long long n, Slot *table, unsigned long long cap,
+place_distinct_kernel(const unsigned long long *__restrict__ keys, const int *__restrict__ vals, long long n, Table table,
                       uint8_t *fp, unsigned long long *counters)
 {
+    const unsigned long long cap = table.cap;
     const long long i0 = ((long long)blockIdx.x * 256 + threadIdx.x);
     const long long stride = (long long)gridDim.x * 256;
     unsigned long long key[2], h[2], idx[2], old[2];
@@ -247,7 +254,7 @@ place_distinct_kernel(const unsigned long long *__restrict__ keys, const int *__
     }
 #pragma unroll
     for (int j = 0; j < 2; j++)
-        if (ok[j]) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
+        if (ok[j]) old[j] = atomicCAS(table.key + idx[j], EMPTY_KEY, key[j]);
     int nk = 0;
 #pragma unroll
     for (int j = 0; j < 2; j++) {
@@ -255,11 +262,11 @@ place_distinct_kernel(const unsigned long long *__restrict__ keys, const int *__
         const long long i = i0 + j * stride;
         while (old[j] != EMPTY_KEY) { // someone else's slot: linear probing (keys are distinct: old is never this key)
             idx[j] = next_slot(idx[j], cap);
-            old[j] = load_key(table + idx[j]);
-            if (old[j] == EMPTY_KEY) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
+            old[j] = load_key(table, idx[j]);
+            if (old[j] == EMPTY_KEY) old[j] = atomicCAS(table.key + idx[j], EMPTY_KEY, key[j]);
         }
-        const unsigned long long cv = ((unsigned long long)(unsigned int)i << 32) | (unsigned int)vals[i];
-        *reinterpret_cast<unsigned long long *>(&table[idx[j]].count) = cv; // count | vid: the slot is ours alone
+        table.count[idx[j]] = vals[i]; // the slot is ours alone
+        table.vid[idx[j]] = (unsigned int)i;
         fp[idx[j]] = (uint8_t)fp_tag(h[j]);
         nk++;
     }
@@ -267,14 +274,13 @@ place_distinct_kernel(const unsigned long long *__restrict__ keys, const int *__
     if ((threadIdx.x & 31) == 0 && nk) atomicAdd(&counters[0], (unsigned long long)nk);
 }
 
-__global__ void lookup_kernel(const unsigned long long *__restrict__ keys, long long n, const Slot *table, unsigned long long cap,
-                              int *counts, uint8_t *found)
+__global__ void lookup_kernel(const unsigned long long *__restrict__ keys, long long n, Table table, int *counts, uint8_t *found)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Slot s;
-    bool f = probe_find(table, cap, keys[i], &s) >= 0;
-    if (counts) counts[i] = f ? s.count : 0;
+    const long long at = probe_find(table, keys[i]);
+    const bool f = at >= 0;
+    if (counts) counts[i] = f ? load_count(table, (unsigned long long)at) : 0;
     if (found) found[i] = f;
 }
 
@@ -282,9 +288,9 @@ __global__ void lookup_kernel(const unsigned long long *__restrict__ keys, long 
 // survivors into (key, count) arrays (warp-aggregated cursor), then they are re-inserted into a table sized for
 // them (the reference tombstones and rescales when the load drops below 0.3, ArrayDNAMap.scala:217-230).
 __global__ void __launch_bounds__(256)
-compact_survivors_kernel(const Slot *table, unsigned long long n, int min_count, unsigned long long *out_keys, int *out_vals,
-                         unsigned long long *counters)
+compact_survivors_kernel(Table table, int min_count, unsigned long long *out_keys, int *out_vals, unsigned long long *counters)
 {
+    const unsigned long long n = table.cap;
     // a CTA iteration covers 1024 consecutive slots (4 per thread) and takes ONE ticket from the global cursor
     const unsigned long long tiles = (n + 1023) / 1024;
     for (unsigned long long t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -295,7 +301,7 @@ compact_survivors_kernel(const Slot *table, unsigned long long n, int min_count,
             const unsigned long long i = t * 1024 + (unsigned long long)j * 256 + threadIdx.x;
             s[j].key = EMPTY_KEY;
             s[j].count = 0;
-            if (i < n) s[j] = load_slot(table + i);
+            if (i < n) { s[j].key = __ldcs(table.key + i); s[j].count = __ldcs(table.count + i); }
             c += s[j].key != EMPTY_KEY && s[j].count >= min_count;
         }
         unsigned long long pos = block_alloc(c, &counters[1]);
@@ -309,19 +315,22 @@ compact_survivors_kernel(const Slot *table, unsigned long long n, int min_count,
     }
 }
 
-__global__ void rehash_kernel(const Slot *old_table, unsigned long long n, int min_count, bool filter,
-                              Slot *new_table, unsigned long long new_cap)
+__global__ void rehash_kernel(Table old_table, int min_count, bool filter, Table new_table)
 {
+    const unsigned long long n = old_table.cap, new_cap = new_table.cap;
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        Slot s = load_slot(old_table + i);
-        if (s.key == EMPTY_KEY || (filter && s.count < min_count)) continue;
+        Slot s;
+        s.key = __ldcs(old_table.key + i);
+        if (s.key == EMPTY_KEY) continue;
+        s.count = __ldcs(old_table.count + i);
+        if (filter && s.count < min_count) continue;
         unsigned long long idx = slot_of(mix64(s.key), new_cap);
         for (;;) {
-            unsigned long long cur = load_key(new_table + idx);
-            if (cur == EMPTY_KEY && atomicCAS(&new_table[idx].key, EMPTY_KEY, s.key) == EMPTY_KEY) {
-                new_table[idx].count = s.count;
+            unsigned long long cur = load_key(new_table, idx);
+            if (cur == EMPTY_KEY && atomicCAS(new_table.key + idx, EMPTY_KEY, s.key) == EMPTY_KEY) {
+                new_table.count[idx] = s.count;
                 break;
             }
             idx = next_slot(idx, new_cap);
@@ -330,9 +339,9 @@ __global__ void rehash_kernel(const Slot *old_table, unsigned long long n, int m
 }
 
 // mapReduce/foreach export: compaction with one global atomic per CTA
-__global__ void export_kernel(const Slot *table, unsigned long long n, unsigned long long *keys, int *vals,
-                              unsigned long long cap, unsigned long long *counters)
+__global__ void export_kernel(Table table, unsigned long long *keys, int *vals, unsigned long long cap, unsigned long long *counters)
 {
+    const unsigned long long n = table.cap;
     __shared__ unsigned int s_n;
     __shared__ unsigned long long s_base;
     unsigned long long tiles = (n + blockDim.x - 1) / blockDim.x;
@@ -342,7 +351,8 @@ __global__ void export_kernel(const Slot *table, unsigned long long n, unsigned 
         __syncthreads();
         Slot s;
         s.key = EMPTY_KEY;
-        if (i < n) s = load_slot(table + i);
+        s.count = 0;
+        if (i < n) { s.key = __ldcs(table.key + i); s.count = __ldcs(table.count + i); }
         bool live = s.key != EMPTY_KEY;
         unsigned int ballot = __ballot_sync(0xFFFFFFFFu, live);
         unsigned int lane = threadIdx.x & 31, wbase = 0;
@@ -373,14 +383,14 @@ namespace gb {
 // Table memory.  A FreqFilter pass cycles between a large table (counting) and a small one (after deleteAll), and
 // the next pass starts again with a large one: the map keeps both allocations (`table` and `spare`) and swaps them,
 // so that the steady state allocates nothing.  Everything happens in stream order on m->stream.
-static int init_table(Slot *t, unsigned long long n, cudaStream_t s)
+static int init_table(void *t, unsigned long long n, cudaStream_t s, bool with_vid)
 {
-    init_table_kernel<<<grid_for(n, 256, 32), 256, 0, s>>>(t, n);
+    init_table_kernel<<<grid_for(n / 2, 256, 32), 256, 0, s>>>(table_view(t, n), with_vid);
     GB_LAUNCHED();
     return GB_OK;
 }
 
-void map_retire_table(Map *m, Slot *t, unsigned long long alloc_cap)
+void map_retire_table(Map *m, void *t, unsigned long long alloc_cap)
 {
     if (!t) return;
     if (!m->spare) { m->spare = t; m->spare_cap = alloc_cap; return; }
@@ -391,18 +401,18 @@ void map_retire_table(Map *m, Slot *t, unsigned long long alloc_cap)
 
 // make an EMPTY table of new_cap slots current; the previous one is handed back (still valid on the stream:
 // the caller rehashes out of it and then retires it)
-int map_swap_table(Map *m, unsigned long long new_cap, Slot **old_table, unsigned long long *old_alloc_cap)
+int map_swap_table(Map *m, unsigned long long new_cap, void **old_table, unsigned long long *old_alloc_cap)
 {
-    Slot *nt = nullptr;
+    void *nt = nullptr;
     unsigned long long na = new_cap;
     if (m->spare && m->spare_cap >= new_cap) {
         nt = m->spare;
         na = m->spare_cap;
         m->spare = nullptr;
     } else {
-        GB_CUDA(cudaMalloc((void **)&nt, sizeof(Slot) * new_cap));
+        GB_CUDA(cudaMalloc(&nt, SLOT_BYTES * new_cap));
     }
-    GB_TRY(init_table(nt, new_cap, m->stream));
+    GB_TRY(init_table(nt, new_cap, m->stream, false));
     m->kept_valid = false;
     *old_table = m->table;
     *old_alloc_cap = m->alloc_cap;
@@ -430,11 +440,11 @@ int map_stage(Map *m, size_t n_u64)
 // rehash into a table of new_cap slots (optionally dropping counts below min_count)
 int map_rebuild(Map *m, unsigned long long new_cap, bool filter, int min_count)
 {
-    Slot *old = nullptr;
+    void *old = nullptr;
     unsigned long long old_alloc = 0;
     const unsigned long long n = m->cap;
     GB_TRY(map_swap_table(m, new_cap, &old, &old_alloc));
-    rehash_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(old, n, min_count, filter, m->table, new_cap);
+    rehash_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(table_view(old, n), min_count, filter, m->view());
     GB_LAUNCHED();
     map_retire_table(m, old, old_alloc);
     m->grows++;
@@ -463,7 +473,7 @@ int map_budget(Map *m, int64_t incoming, int64_t *budget)
 int map_launch_update_counts(Map *m, const unsigned long long *d_keys, int64_t n, cudaStream_t st)
 {
     if (n <= 0) return GB_OK;
-    update_keys_kernel<false><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, nullptr, n, m->table, m->cap, m->d_counters);
+    update_keys_kernel<false><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, nullptr, n, m->view(), m->d_counters);
     GB_LAUNCHED();
     return GB_OK;
 }
@@ -484,9 +494,9 @@ int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d
         fp = m->fp;
     }
     if (n <= 0) return GB_OK;
-    if (set_vid && (g_tune.exp & 1)) update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, m->d_counters, true, fp);
-    else if (set_vid) place_distinct_kernel<<<(unsigned int)((n + 511) / 512), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, fp, m->d_counters);
-    else update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->table, m->cap, m->d_counters, false, nullptr);
+    if (set_vid && (g_tune.exp & 1)) update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->view(), m->d_counters, true, fp);
+    else if (set_vid) place_distinct_kernel<<<(unsigned int)((n + 511) / 512), 256, 0, st>>>(d_keys, d_vals, n, m->view(), fp, m->d_counters);
+    else update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->view(), m->d_counters, false, nullptr);
     GB_LAUNCHED();
     return GB_OK;
 }
@@ -512,10 +522,10 @@ static int launch_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
     unsigned int grid = (unsigned int)((n_reads + TILE_READS - 1) / TILE_READS);
     if (m->v210)
         insert_reads_kernel<FIXED, true><<<grid, INSERT_THREADS, 0, m->stream>>>(
-            d_bin, n_bytes, d_off, rec, read0, n_reads, m->k, m->table, m->cap, m->d_counters);
+            d_bin, n_bytes, d_off, rec, read0, n_reads, m->k, m->view(), m->d_counters);
     else
         insert_reads_kernel<FIXED, false><<<grid, INSERT_THREADS, 0, m->stream>>>(
-            d_bin, n_bytes, d_off, rec, read0, n_reads, m->k, m->table, m->cap, m->d_counters);
+            d_bin, n_bytes, d_off, rec, read0, n_reads, m->k, m->view(), m->d_counters);
     GB_LAUNCHED();
     return GB_OK;
 }
@@ -684,7 +694,7 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
         const int64_t take_windows = fixed ? take * win_per_read_max
                                            : (h_win_prefix ? h_win_prefix[done + take] - h_win_prefix[done] : take * win_per_read_max);
         const int mode = insert_mode();
-        const bool partitioned = mode == 2 || (mode == 0 && ((size_t)sizeof(Slot) * m->cap) > (96u << 20) && take_windows >= (1 << 20));
+        const bool partitioned = mode == 2 || (mode == 0 && (SLOT_BYTES * m->cap) > (96u << 20) && take_windows >= (1 << 20));
         GB_CUDA(cudaEventRecord(m->ev0, m->stream));
         if (partitioned) {
             // bounded key staging: at most 2^28 k-mers (2 GiB) per call, pipelined inside
@@ -737,7 +747,7 @@ static int insert_host_pipelined(Map *m, const uint8_t *bin, int64_t n_reads, un
     GB_TRY(map_budget(m, want, &budget));
     if (want > budget) return GB_OK;
     const int mode = insert_mode();
-    if (!(mode == 2 || (mode == 0 && ((size_t)sizeof(Slot) * m->cap) > (96u << 20)))) return GB_OK;
+    if (!(mode == 2 || (mode == 0 && (SLOT_BYTES * m->cap) > (96u << 20)))) return GB_OK;
     if (!m->part) m->part = new PartWork();
     PartWork &w = *m->part;
     GB_TRY(w.ensure(m->stream));
@@ -878,7 +888,7 @@ int map_export_device(Map *m, unsigned long long *d_keys, int *d_vals)
     if (m->size == 0) return GB_OK;
     unsigned long long n = m->cap;
     GB_TRY(map_zero_counters(m));
-    export_kernel<<<grid_for(n, 256, 16), 256, 0, m->stream>>>(m->table, n, d_keys, d_vals, (unsigned long long)m->size, m->d_counters);
+    export_kernel<<<grid_for(n, 256, 16), 256, 0, m->stream>>>(m->view(), d_keys, d_vals, (unsigned long long)m->size, m->d_counters);
     GB_LAUNCHED();
     unsigned long long c[4];
     GB_TRY(map_read_counters(m, c));
@@ -947,7 +957,7 @@ int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_ma
         if (r) break;
         if ((r = cudaMalloc((void **)&m->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess ? GB_OK : GB_E_OOM)) break;
         {
-            Slot *none = nullptr;
+            void *none = nullptr;
             unsigned long long none_cap = 0;
             if ((r = map_swap_table(m, cap0, &none, &none_cap))) break;
         }
@@ -1170,8 +1180,7 @@ int gb_map_lookup(gb_map *h, const uint64_t *keys, int64_t n, int32_t *counts, u
     GB_TRY(dc.alloc((size_t)n * 4, m->stream));
     GB_TRY(df.alloc((size_t)n, m->stream));
     GB_CUDA(cudaMemcpyAsync(dk.p, keys, (size_t)n * 8, cudaMemcpyHostToDevice, m->stream));
-    lookup_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, m->stream>>>((const unsigned long long *)dk.p, n, m->table, m->cap,
-                                                                          (int *)dc.p, (uint8_t *)df.p);
+    lookup_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, m->stream>>>((const unsigned long long *)dk.p, n, m->view(), (int *)dc.p, (uint8_t *)df.p);
     GB_LAUNCHED();
     if (counts) GB_CUDA(cudaMemcpyAsync(counts, dc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, m->stream));
     if (found) GB_CUDA(cudaMemcpyAsync(found, df.p, (size_t)n, cudaMemcpyDeviceToHost, m->stream));
@@ -1192,7 +1201,7 @@ int gb_map_delete_below(gb_map *h, int32_t min_count)
     unsigned long long *sk = m->stage;
     int *sv = reinterpret_cast<int *>(m->stage + m->size);
     GB_CUDA(cudaEventRecord(m->fev[0], m->stream));
-    compact_survivors_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(m->table, n, min_count, sk, sv, m->d_counters);
+    compact_survivors_kernel<<<grid_for(n, 256, 32), 256, 0, m->stream>>>(m->view(), min_count, sk, sv, m->d_counters);
     GB_LAUNCHED();
     GB_CUDA(cudaEventRecord(m->fev[1], m->stream));
     unsigned long long c[4];
@@ -1207,7 +1216,7 @@ int gb_map_delete_below(gb_map *h, int32_t min_count)
     int64_t keep = (int64_t)c[1];
     if (keep == m->size) return GB_OK;
     // a fresh table sized for the survivors
-    Slot *old = nullptr;
+    void *old = nullptr;
     unsigned long long old_alloc = 0;
     GB_TRY(map_swap_table(m, cap_for(keep), &old, &old_alloc));
     map_retire_table(m, old, old_alloc);
@@ -1240,7 +1249,7 @@ int gb_map_export(gb_map *h, uint64_t *keys, int32_t *vals, int64_t cap, int64_t
     GB_TRY(dv.alloc((size_t)m->size * 4, m->stream));
     unsigned long long n = m->cap;
     GB_TRY(map_zero_counters(m));
-    export_kernel<<<grid_for(n, 256, 16), 256, 0, m->stream>>>(m->table, n, (unsigned long long *)dk.p, (int *)dv.p,
+    export_kernel<<<grid_for(n, 256, 16), 256, 0, m->stream>>>(m->view(), (unsigned long long *)dk.p, (int *)dv.p,
                                                              (unsigned long long)m->size, m->d_counters);
     GB_LAUNCHED();
     if (keys) GB_CUDA(cudaMemcpyAsync(keys, dk.p, (size_t)m->size * 8, cudaMemcpyDeviceToHost, m->stream));
@@ -1258,12 +1267,12 @@ int gb_map_clear(gb_map *h, int64_t min_capacity)
     if (min_capacity < 0) { set_error("negative capacity"); return GB_E_ARG; }
     unsigned long long nb = cap_for(min_capacity);
     if (nb != m->cap) {
-        Slot *old = nullptr;
+        void *old = nullptr;
         unsigned long long old_alloc = 0;
         GB_TRY(map_swap_table(m, nb, &old, &old_alloc));
         map_retire_table(m, old, old_alloc);
     } else {
-        GB_TRY(init_table(m->table, m->cap, m->stream));
+        GB_TRY(init_table(m->table, m->cap, m->stream, false));
     }
     m->size = 0;
     m->kept_valid = false;
@@ -1394,7 +1403,7 @@ int gb_map_stats(gb_map *h, int64_t stats[8])
     if (!stats) { set_error("null argument"); return GB_E_ARG; }
     memset(stats, 0, 8 * sizeof(int64_t));
     stats[0] = (int64_t)m->cap;
-    stats[1] = stats[0] * (int64_t)sizeof(Slot);
+    stats[1] = stats[0] * (int64_t)SLOT_BYTES;
     stats[2] = m->grows;
     stats[3] = m->windows;
     stats[4] = m->last_insert_ns;

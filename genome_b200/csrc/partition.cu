@@ -10,6 +10,8 @@
 // The same buckets, with an owner-shard prefix, are what the sharded map sends over NVLink (comm.cu).
 #include <math.h>
 
+#include <algorithm>
+
 #include "partition.cuh"
 
 #include "extract.cuh"
@@ -144,8 +146,7 @@ part_bases_kernel(const unsigned long long *bucket_total, unsigned int nb, unsig
 struct SlabOut {
     unsigned int slab = 0;              // keys per (bucket, CTA) slab
     unsigned int *count = nullptr;      // [nb][grid]
-    Slot *table = nullptr;              // overflow path
-    unsigned long long cap = 0;
+    Table table;                        // overflow path
     unsigned long long *spread = nullptr;   // new-key tallies (fold_new_keys_kernel)
     unsigned long long *overflowed = nullptr; // keys that took the overflow path (they count as k-windows too)
     // LIST mode (ovf != nullptr; the chunked host insert): the bucket pass must not touch the table (the stream is not verified
@@ -270,8 +271,8 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
                     const unsigned long long at = atomicAdd(so.overflowed, 1ull);
                     if (at < so.ovf_cap) so.ovf[at] = key1; else *so.failed = 1u;
                 } else {
-                    const unsigned long long i = slot_of(mix64(key1), so.cap);
-                    if (upsert_add(so.table, so.cap, i, load_key(so.table + i), key1, 1)) atomicAdd(&so.spread[blockIdx.x & (SPREAD - 1)], 1ull);
+                    const unsigned long long i = slot_of(mix64(key1), so.table.cap);
+                    if (upsert_add(so.table, i, load_key(so.table, i), key1, 1)) atomicAdd(&so.spread[blockIdx.x & (SPREAD - 1)], 1ull);
                     atomicAdd(so.overflowed, 1ull);
                 }
                 continue;
@@ -327,9 +328,9 @@ constexpr int IK_PER_THREAD = 4; // measured 2 / 4 / 8 / 16 keys per thread: 1.7
 template <bool DEV_TOTAL>
 __global__ void __launch_bounds__(IK_THREADS)
 insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vstart,
-                   const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Slot *table, unsigned long long cap,
-                   unsigned long long *spread)
+                   const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Table table, unsigned long long *spread)
 {
+    const unsigned long long cap = table.cap;
     constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
     const unsigned long long v0 = (unsigned long long)blockIdx.x * IK_PER_CTA;
     if (DEV_TOTAL) {
@@ -361,24 +362,24 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
     unsigned long long old[IK_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < IK_PER_THREAD; j++)
-        if (ok[j]) cur[j] = load_key(table + idx[j]);
+        if (ok[j]) cur[j] = load_key(table, idx[j]);
     // the CAS round trips of a thread's keys overlap: all of them are issued before the first result is used
 #pragma unroll
     for (int j = 0; j < IK_PER_THREAD; j++) {
         old[j] = cur[j];
-        if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
+        if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(table.key + idx[j], EMPTY_KEY, key[j]);
     }
 #pragma unroll
     for (int j = 0; j < IK_PER_THREAD; j++) {
         if (!ok[j]) continue;
         const bool claimed = cur[j] == EMPTY_KEY && old[j] == EMPTY_KEY;
         if (claimed || old[j] == key[j]) {
-            red_add_s32(&table[idx[j]].count, 1);
+            red_add_s32(table.count + idx[j], 1);
             nk += claimed;
         } else {
             // the slot belongs to another key: linear probing from the next slot (rare at load <= 0.5)
             unsigned long long nx = next_slot(idx[j], cap);
-            nk += upsert_add(table, cap, nx, load_key(table + nx), key[j], 1);
+            nk += upsert_add(table, nx, load_key(table, nx), key[j], 1);
         }
     }
     nk = __reduce_add_sync(0xFFFFFFFFu, nk);
@@ -398,48 +399,87 @@ fold_new_keys_kernel(unsigned long long *spread, unsigned long long *counters)
 }
 
 // The same upsert over the SLABS of the single-pass bucket pass: slab number s = (bucket, CTA of the bucket pass) holds count[s]
-// keys at keys[s * slab], and CTA (s, part) takes keys [part * 1024, ...) of it.  The launch is sized for full slabs; a CTA
-// whose part lies beyond count[s] leaves at once.  No chunk table, no search: measured on C2 the search over the 19 k-entry
+// keys at keys[s * slab], and work item (s, part) takes keys [part * 1024, ...) of it.  The launch is sized for full slabs; an
+// item whose part lies beyond count[s] does nothing.  No chunk table, no search: measured on C2 the search over the 19 k-entry
 // chunk table cost the generic kernel 0.2 ms (2.15 against 1.95 ms).  Slabs are bucket-major, so slice order is kept.
-__global__ void __launch_bounds__(IK_THREADS)
+// The kernel is latency bound (ncu r2c: 29 long-scoreboard stall cycles per issue, half occupancy): three dependent round trips
+// per key -- staged key, table key, compare-and-swap.  Variants under measurement (gb_tune exp): MINB = CTAs per SM the register
+// allocation must allow; CAS_FIRST = the compare-and-swap IS the probe (no preceding load: one round trip less for a new key, and
+// key lines see atomics only); PERSIST = one CTA per SM slot walks the items and fetches the next item's keys before it works on
+// the current ones.  Slot indices are 32-bit (IdxT) whenever the table has fewer than 2^32 slots.
+template <int MINB, bool CAS_FIRST, bool PERSIST, typename IdxT>
+__global__ void __launch_bounds__(IK_THREADS, MINB)
 insert_slabs_kernel(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ count, unsigned int slab,
-                    unsigned int ctas_per_slab, Slot *table, unsigned long long cap, unsigned long long *spread)
+                    unsigned int ctas_per_slab, unsigned int n_work, Table table, unsigned long long *spread)
 {
     constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
-    const unsigned int s = blockIdx.x / ctas_per_slab, part = blockIdx.x - s * ctas_per_slab;
-    const unsigned int n = min(count[s], slab), v0 = part * IK_PER_CTA;
-    if (v0 >= n) return;
-    const unsigned long long *src = keys + (size_t)s * slab + v0;
-    unsigned long long key[IK_PER_THREAD], idx[IK_PER_THREAD], cur[IK_PER_THREAD], old[IK_PER_THREAD];
-    bool ok[IK_PER_THREAD];
-#pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++) {
-        const unsigned int i = (unsigned int)j * IK_THREADS + threadIdx.x;
-        ok[j] = v0 + i < n;
-        if (ok[j]) {
-            key[j] = __ldcs(src + i);
-            idx[j] = slot_of(mix64(key[j]), cap);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++)
-        if (ok[j]) cur[j] = load_key(table + idx[j]);
-#pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++) {
-        old[j] = cur[j];
-        if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(&table[idx[j]].key, EMPTY_KEY, key[j]);
-    }
+    const unsigned long long cap = table.cap;
     int nk = 0;
+    auto fetch = [&](unsigned int w, unsigned long long (&key)[IK_PER_THREAD], bool (&ok)[IK_PER_THREAD]) {
+        const unsigned int s = w / ctas_per_slab, part = w - s * ctas_per_slab;
+        const unsigned int n = min(count[s], slab), v0 = part * IK_PER_CTA;
+        const unsigned long long *src = keys + (size_t)s * slab + v0;
 #pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++) {
-        if (!ok[j]) continue;
-        const bool claimed = cur[j] == EMPTY_KEY && old[j] == EMPTY_KEY;
-        if (claimed || old[j] == key[j]) {
-            red_add_s32(&table[idx[j]].count, 1);
-            nk += claimed;
+        for (int j = 0; j < IK_PER_THREAD; j++) {
+            const unsigned int i = (unsigned int)j * IK_THREADS + threadIdx.x;
+            ok[j] = v0 + i < n;
+            if (ok[j]) key[j] = __ldcs(src + i);
+        }
+    };
+    auto process = [&](const unsigned long long (&key)[IK_PER_THREAD], const bool (&ok)[IK_PER_THREAD]) {
+        IdxT idx[IK_PER_THREAD];
+        unsigned long long cur[IK_PER_THREAD], old[IK_PER_THREAD];
+#pragma unroll
+        for (int j = 0; j < IK_PER_THREAD; j++)
+            if (ok[j]) idx[j] = (IdxT)slot_of(mix64(key[j]), cap);
+        if (CAS_FIRST) {
+#pragma unroll
+            for (int j = 0; j < IK_PER_THREAD; j++) {
+                cur[j] = EMPTY_KEY;
+                if (ok[j]) old[j] = atomicCAS(table.key + idx[j], EMPTY_KEY, key[j]);
+            }
         } else {
-            unsigned long long nx = next_slot(idx[j], cap);
-            nk += upsert_add(table, cap, nx, load_key(table + nx), key[j], 1);
+#pragma unroll
+            for (int j = 0; j < IK_PER_THREAD; j++)
+                if (ok[j]) cur[j] = load_key(table, idx[j]);
+#pragma unroll
+            for (int j = 0; j < IK_PER_THREAD; j++) {
+                old[j] = cur[j];
+                if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(table.key + idx[j], EMPTY_KEY, key[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < IK_PER_THREAD; j++) {
+            if (!ok[j]) continue;
+            const bool claimed = cur[j] == EMPTY_KEY && old[j] == EMPTY_KEY;
+            if (claimed || old[j] == key[j]) {
+                red_add_s32(table.count + idx[j], 1);
+                nk += claimed;
+            } else {
+                unsigned long long nx = next_slot(idx[j], cap);
+                nk += upsert_add(table, nx, load_key(table, nx), key[j], 1);
+            }
+        }
+    };
+    unsigned long long key[IK_PER_THREAD];
+    bool ok[IK_PER_THREAD];
+    if (!PERSIST) {
+        fetch(blockIdx.x, key, ok);
+        process(key, ok);
+    } else {
+        unsigned int w = blockIdx.x;
+        if (w < n_work) fetch(w, key, ok);
+        while (w < n_work) {
+            const unsigned int wn = w + gridDim.x;
+            unsigned long long key2[IK_PER_THREAD];
+            bool ok2[IK_PER_THREAD];
+#pragma unroll
+            for (int j = 0; j < IK_PER_THREAD; j++) ok2[j] = false;
+            if (wn < n_work) fetch(wn, key2, ok2);
+            process(key, ok);
+#pragma unroll
+            for (int j = 0; j < IK_PER_THREAD; j++) { key[j] = key2[j]; ok[j] = ok2[j]; }
+            w = wn;
         }
     }
     nk = __reduce_add_sync(0xFFFFFFFFu, nk);
@@ -612,8 +652,7 @@ int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &
     SlabOut so;
     so.slab = slab;
     so.count = w.cta_hist; // [nb][grid] here (the counted passes use it as [grid][nb])
-    so.table = m->table;
-    so.cap = m->cap;
+    so.table = m->view();
     so.spread = m->d_spread;
     so.overflowed = w.bucket_total; // one word is enough; the counted passes are not running
     GB_CUDA(cudaMemsetAsync(so.overflowed, 0, 8, st));
@@ -694,9 +733,22 @@ int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d
         GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));
     }
     const unsigned int per = (slab + IK_THREADS * IK_PER_THREAD - 1) / (IK_THREADS * IK_PER_THREAD);
-    const unsigned long long grid = (unsigned long long)n_slabs * per;
-    if (grid >= 0x7FFFFFFFull) { set_error("internal: %llu slab CTAs", grid); return GB_E_ARG; }
-    insert_slabs_kernel<<<(unsigned int)grid, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, m->table, m->cap, m->d_spread);
+    const unsigned long long work = (unsigned long long)n_slabs * per;
+    if (work >= 0x7FFFFFFFull) { set_error("internal: %llu slab CTAs", work); return GB_E_ARG; }
+    const Table t = m->view();
+    const long long e = g_tune.exp;
+    const bool cas_first = e & 2, persist = e & 4;
+    const int minb = (e & 16) ? 8 : (e & 8) ? 6 : 4;
+    const unsigned int grid = persist ? (unsigned int)std::min<unsigned long long>(work, (unsigned long long)SM_COUNT * minb) : (unsigned int)work;
+#define GB_IS(M, C, P, I) insert_slabs_kernel<M, C, P, I><<<grid, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, (unsigned int)work, t, m->d_spread)
+#define GB_IS3(M, I) do { if (cas_first) { if (persist) GB_IS(M, true, true, I); else GB_IS(M, true, false, I); } \
+                          else { if (persist) GB_IS(M, false, true, I); else GB_IS(M, false, false, I); } } while (0)
+    if (t.cap >= (1ull << 32)) GB_IS3(4, unsigned long long);
+    else if (minb == 8) GB_IS3(8, unsigned int);
+    else if (minb == 6) GB_IS3(6, unsigned int);
+    else GB_IS3(4, unsigned int);
+#undef GB_IS3
+#undef GB_IS
     GB_LAUNCHED();
     fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
     GB_LAUNCHED();
@@ -714,9 +766,9 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
     }
     const unsigned int grid = (unsigned int)((n_total + IK_THREADS * IK_PER_THREAD - 1) / (IK_THREADS * IK_PER_THREAD));
     if (total_is_upper_bound)
-        insert_keys_kernel<true><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread);
+        insert_keys_kernel<true><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->view(), m->d_spread);
     else
-        insert_keys_kernel<false><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->table, m->cap, m->d_spread);
+        insert_keys_kernel<false><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->view(), m->d_spread);
     GB_LAUNCHED();
     fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
     GB_LAUNCHED();

@@ -51,8 +51,13 @@ int gb_bench_random_atomics(int device, size_t table_bytes, int64_t n_updates, i
 int gb_bench_smem_upsert(int device, int slots_log2, int64_t keys_per_bucket, int64_t n_buckets, int ctas_per_sm, int iters,
                          int64_t *ns_per_iter, int64_t *distinct_keys);
 /* diagnostics: the request rate of the upsert's access pattern with hashing and probing stripped away: n_updates random 16-byte
- * slots of a region of region_bytes (choose it to fit L2 or not); mode 1 = 8-byte load, 2 = 4-byte red.add, 3 = load then red
- * (an existing key), 4 = load, 64-bit CAS, red (a new key); 4 updates per thread in flight.  ns per pass. */
+ * slots of a region of region_bytes (choose it to fit L2 or not); mode = base + 100 * log2(updates in flight per thread; 0 = 4)
+ * + 1000 * P (P > 0: persistent grid of P CTAs per SM, software-pipelined); base 1 = 8-byte load, 2 = 4-byte red.add, 3 = load
+ * then a dependent red (an existing key), 4 = load, 64-bit CAS, red (a new key), 5 = load and an independent red, 6 = load then a
+ * dependent red on another slot, 7 = atom.add with a return value, 8 = 16-byte load then red, 9 = load then a plain store,
+ * 10 = load from one half / red into the other, 11 / 12 = loads and reds issued by different SMs / warps, 13 = separate key and
+ * count arrays, 14 = keys and counts in different sectors of one 128-byte line, 15 / 16 = 13 / 14 with a CAS on the key.
+ * ns per pass. */
 int gb_bench_l2_requests(int device, size_t region_bytes, int64_t n_updates, int mode, int iters, int64_t *ns_per_iter);
 /* tuning and test hooks (process-wide; not part of the reference surface).  The library reads no environment variable on
  * its data path: every default is a measured choice, and the parity tests use these keys to force a path that
