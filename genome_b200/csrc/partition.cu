@@ -138,11 +138,13 @@ part_bases_kernel(const unsigned long long *bucket_total, unsigned int nb, unsig
 // scattered 8-byte stores per warp instruction.  That is what fills NVLink write packets when PEER.
 // PEER: the position of a key is (owner, index inside the owner's segment) packed in 32 bits and the store goes to
 // the owner's inbox through its peer mapping -- the all-to-all happens inside this kernel, store by store.
-// SLABS (GENOME_B200_COUNTLESS=1, single-GPU path only): there is NO count pass.  CTA c owns, for every bucket b, the slab
-// [(b * grid + c) * slab, + slab) of `out`, sized for its expected share plus 8 sigma; what it wrote goes to so.count[b * grid +
-// c], and make_slab_chunks_kernel turns the counts into the chunk table of the upsert (bucket-major, so slice order is kept).
-// A key that does not fit its slab is upserted right here, with the random access of the direct path: always correct, and only
-// pathological inputs (one bucket far above its share within one CTA's tiles) ever take it.
+// (The single-GPU insert does not use this kernel: bucket_slabs_kernel below needs no count pass.)
+
+// Destination of the single-pass bucket pass (bucket_slabs_kernel; single-GPU path only).  CTA c owns, for every bucket b, the slab
+// [(b * grid + c) * slab, + slab) of `out`, sized for its expected share plus 8 sigma; what it wrote goes to count[b * grid + c],
+// and the upsert walks the slabs in that (bucket-major = slice) order.  A key that does not fit its slab is upserted by the bucket
+// pass itself, with the random access of the direct path: always correct, and only pathological inputs (one bucket far above its
+// share within one CTA's tiles) ever take it.
 struct SlabOut {
     unsigned int slab = 0;              // keys per (bucket, CTA) slab
     unsigned int *count = nullptr;      // [nb][grid]
@@ -158,10 +160,10 @@ struct SlabOut {
     unsigned int *failed = nullptr;
 };
 
-template <bool FIXED, bool V210, bool SRC_KEYS, bool PEER, bool SLABS>
+template <bool FIXED, bool V210, bool SRC_KEYS, bool PEER>
 __global__ void __launch_bounds__(INSERT_THREADS, 4)
 part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int lp_bits, unsigned int nb, const unsigned int *cta_off,
-                    const unsigned long long *bucket_base, unsigned long long *out, PeerOut peers, SlabOut so)
+                    const unsigned long long *bucket_base, unsigned long long *out, PeerOut peers)
 {
     __shared__ ReadTile tile;
     extern __shared__ unsigned int s_dyn[];
@@ -175,10 +177,6 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
     unsigned long long *skey = reinterpret_cast<unsigned long long *>(sdst + ROUND_KEYS); // offset 10 nb + 2 + ROUND_KEYS words: even
     // position of the CTA's next key of bucket b, relative to out[0] (a batch holds < 2^32 keys)
     for (unsigned int b = tid; b < nb; b += INSERT_THREADS) {
-        if (SLABS) {
-            bcur[b] = (b * gridDim.x + blockIdx.x) * so.slab + so.count[(size_t)b * gridDim.x + blockIdx.x]; // < 2^32: checked by the host
-            continue;
-        }
         unsigned int pos = (unsigned int)bucket_base[b] + cta_off[(size_t)blockIdx.x * nb + b];
         if (PEER) { // relative to the owner's segment, owner in the top bits
             const unsigned int o = b >> lp_bits;
@@ -260,30 +258,11 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
                 const unsigned int idx = bstart[bk[j]] + in_bucket;
                 skey[idx] = key[j];
                 unsigned int pos = bcur[bk[j]] + in_bucket;
-                if (SLABS && pos >= (bk[j] * gridDim.x + blockIdx.x + 1) * so.slab) pos = 0xFFFFFFFFu; // beyond the slab
                 sdst[idx] = pos;
             }
         __syncthreads();
-        for (unsigned int idx = tid; idx < round_total; idx += INSERT_THREADS) {
-            if (SLABS && sdst[idx] == 0xFFFFFFFFu) {
-                const unsigned long long key1 = skey[idx];
-                if (so.ovf) {
-                    const unsigned long long at = atomicAdd(so.overflowed, 1ull);
-                    if (at < so.ovf_cap) so.ovf[at] = key1; else *so.failed = 1u;
-                } else {
-                    const unsigned long long i = slot_of(mix64(key1), so.table.cap);
-                    if (upsert_add(so.table, i, load_key(so.table, i), key1, 1)) atomicAdd(&so.spread[blockIdx.x & (SPREAD - 1)], 1ull);
-                    atomicAdd(so.overflowed, 1ull);
-                }
-                continue;
-            }
-            store(sdst[idx], skey[idx]);
-        }
-        if (SLABS) { // a full slab stays full: no 32-bit wrap
-            if (tid < (int)nb) bcur[tid] = min(bcur[tid] + (bstart[tid + 1] - bstart[tid]), (tid * gridDim.x + blockIdx.x + 1) * so.slab);
-        } else {
-            if (tid < (int)nb) bcur[tid] += bstart[tid + 1] - bstart[tid];
-        }
+        for (unsigned int idx = tid; idx < round_total; idx += INSERT_THREADS) store(sdst[idx], skey[idx]);
+        if (tid < (int)nb) bcur[tid] += bstart[tid + 1] - bstart[tid];
         __syncthreads();
     };
     if (SRC_KEYS) {
@@ -307,13 +286,165 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
             }
         }
     }
-    if (SLABS) { // do_round ends with a barrier: bcur is final
-        for (unsigned int b = tid; b < nb; b += INSERT_THREADS) {
-            const unsigned int used = bcur[b] - (b * gridDim.x + blockIdx.x) * so.slab;
-            so.count[(size_t)b * gridDim.x + blockIdx.x] = min(used, so.slab);
+}
+
+// ---------------------------------------------------------------- the single-pass bucket pass (single GPU)
+// One pass over the reads, no count pass: CTA c owns, for every bucket b, the slab [(b * grid + c) * slab, + slab) of `out`
+// (SlabOut above).  Same CTA-level multisplit as part_scatter_kernel, rebuilt around what ncu showed there (profiles/
+// insert_r2c_*: 157 instructions per k-mer, the ADU pipe -- match.any and barriers -- 69 % busy):
+//   * the lanes of a warp that share a bucket are found with one ballot per bucket BIT (vote + one 3-input logic op) instead of
+//     match.any;
+//   * three CTA barriers per round instead of six: warp 0 alone turns the per-warp counts into positions (prefix over the warps,
+//     scan over the buckets, slab cursors) between two of them;
+//   * no per-key destination array: the round is flushed run by run (a warp copies a bucket's run to the slab cursor), so the
+//     slab bound is checked once per run and a key costs one shared load and one global store.
+// LPB = log2(buckets) at compile time (the ballots and the shared-memory indexing unroll), -1 = run time (any nb <= 128).
+template <bool FIXED, bool V210, int LPB>
+__global__ void __launch_bounds__(INSERT_THREADS, 4)
+bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, unsigned long long *out, SlabOut so)
+{
+    __shared__ ReadTile tile;
+    extern __shared__ unsigned int s_dyn[];
+    // layout: rcnt [WARPS][nb] | bstart [nb + 1] | dbase [nb] | bcur [nb] | (pad) | skey [ROUND_KEYS] u64
+    const int lp_bits = LPB >= 0 ? LPB : lp_bits_rt;
+    const unsigned int nb = LPB >= 0 ? (1u << (LPB >= 0 ? LPB : 0)) : nb_rt;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned int *rcnt_all = s_dyn;
+    unsigned int *rcnt = rcnt_all + (size_t)warp * nb;
+    unsigned int *bstart = s_dyn + (size_t)WARPS * nb;
+    unsigned int *dbase = bstart + nb + 1;
+    unsigned int *bcur = dbase + nb;
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(s_dyn + (((size_t)(WARPS + 3) * nb + 1 + 1) & ~(size_t)1));
+    const unsigned int slab = so.slab, grid = gridDim.x, cta = blockIdx.x;
+    for (unsigned int b = tid; b < nb; b += INSERT_THREADS) bcur[b] = (b * grid + cta) * slab + so.count[(size_t)b * grid + cta]; // < 2^32: checked by the host
+    const unsigned int lt = (1u << lane) - 1;
+    __syncthreads();
+    const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
+    for (long long t = cta; t < n_tiles; t += grid) {
+        stage_tile<FIXED>(tile, rb.bin, rb.n_bytes, rb.offsets, rb.rec_bytes, rb.read0, rb.n_reads, k, t);
+        const unsigned int total_items = tile.prefix[TILE_READS];
+        for (unsigned int item0 = 0; item0 < total_items; item0 += INSERT_THREADS) { // uniform over the CTA
+            const unsigned int item = item0 + tid;
+            unsigned long long key[SEG];
+            int cnt = 0;
+            if (item < total_items) cnt = item_keys<V210>(tile, item, k, key);
+            for (unsigned int b = lane; b < nb; b += 32) rcnt[b] = 0;
+            unsigned int bk[SEG], pm[SEG];
+#pragma unroll
+            for (int j = 0; j < SEG; j++) {
+                const bool valid = j < cnt;
+                const unsigned int b = lp_bits ? (unsigned int)(mix64(key[j]) >> (64 - lp_bits)) : 0u;
+                unsigned int peers = __ballot_sync(0xFFFFFFFFu, valid);
+                if (LPB >= 0) {
+#pragma unroll
+                    for (int bit = 0; bit < (LPB >= 0 ? LPB : 0); bit++) {
+                        const bool one = (b >> bit) & 1u;
+                        const unsigned int bal = __ballot_sync(0xFFFFFFFFu, one);
+                        peers &= one ? bal : ~bal;
+                    }
+                } else {
+                    for (int bit = 0; bit < lp_bits; bit++) { // uniform trip count
+                        const bool one = (b >> bit) & 1u;
+                        const unsigned int bal = __ballot_sync(0xFFFFFFFFu, one);
+                        peers &= one ? bal : ~bal;
+                    }
+                }
+                bk[j] = b;
+                pm[j] = valid ? peers : 0u;
+            }
+            __syncwarp();
+            unsigned int rk[SEG];
+#pragma unroll
+            for (int j = 0; j < SEG; j++) {
+                const bool valid = pm[j] != 0;
+                const unsigned int rank = __popc(pm[j] & lt);
+                const unsigned int base = valid ? rcnt[bk[j]] : 0;
+                __syncwarp();
+                if (valid && rank == 0) rcnt[bk[j]] = base + __popc(pm[j]);
+                __syncwarp();
+                rk[j] = base + rank; // rank among this warp's keys of the bucket in this round
+            }
+            __syncthreads(); // (A) every warp's counts are final; the previous round's flush is over
+            if (warp == 0) {
+                unsigned int carry = 0;
+                for (unsigned int b0 = 0; b0 < nb; b0 += 32) {
+                    const unsigned int b = b0 + lane;
+                    unsigned int tot = 0, pre[WARPS];
+                    if (b < nb) {
+#pragma unroll
+                        for (int w = 0; w < WARPS; w++) {
+                            pre[w] = tot; // exclusive prefix over the warps
+                            tot += rcnt_all[(size_t)w * nb + b];
+                        }
+                    }
+                    unsigned int incl = tot;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const unsigned int x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= d) incl += x;
+                    }
+                    if (b < nb) {
+                        const unsigned int st = carry + incl - tot;
+                        bstart[b] = st;
+#pragma unroll
+                        for (int w = 0; w < WARPS; w++) rcnt_all[(size_t)w * nb + b] = st + pre[w]; // where warp w's keys of b start in the staging area
+                        const unsigned int cur = bcur[b], hi = (b * grid + cta + 1) * slab;
+                        dbase[b] = cur;
+                        bcur[b] = min(cur + tot, hi); // a full slab stays full: no 32-bit wrap
+                    }
+                    carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                }
+                if (lane == 0) bstart[nb] = carry;
+            }
+            __syncthreads(); // (B)
+#pragma unroll
+            for (int j = 0; j < SEG; j++)
+                if (j < cnt) skey[rcnt[bk[j]] + rk[j]] = key[j];
+            __syncthreads(); // (C) the round is staged, sorted by bucket
+            for (unsigned int b = warp; b < nb; b += WARPS) {
+                const unsigned int s0 = bstart[b], n = bstart[b + 1] - s0, pos = dbase[b];
+                const unsigned int room = (b * grid + cta + 1) * slab - pos;
+                for (unsigned int i = lane; i < n; i += 32) {
+                    const unsigned long long key1 = skey[s0 + i];
+                    if (i < room) { out[pos + i] = key1; continue; }
+                    if (so.ovf) { // beyond the slab, LIST mode
+                        const unsigned long long at = atomicAdd(so.overflowed, 1ull);
+                        if (at < so.ovf_cap) so.ovf[at] = key1; else *so.failed = 1u;
+                    } else { // beyond the slab: upserted right here, random access
+                        const unsigned long long i1 = slot_of(mix64(key1), so.table.cap);
+                        if (upsert_add(so.table, i1, load_key(so.table, i1), key1, 1)) atomicAdd(&so.spread[cta & (SPREAD - 1)], 1ull);
+                        atomicAdd(so.overflowed, 1ull);
+                    }
+                }
+            }
+            // no barrier here: the next round touches only warp-private counters before its barrier (A)
+        }
+        __syncthreads(); // the tile is overwritten by the next stage_tile; skey / bstart by the next round
+    }
+    __syncthreads();
+    for (unsigned int b = tid; b < nb; b += INSERT_THREADS) so.count[(size_t)b * grid + cta] = min(bcur[b] - (b * grid + cta) * slab, slab);
+}
+
+template <bool FIXED, bool V210>
+static void launch_bucket_slabs(int grid, size_t smem, cudaStream_t st, const ReadBatch &rb, int k, int lp_bits, unsigned int nb, unsigned long long *out,
+                                const SlabOut &so)
+{
+#define GB_BS(L) bucket_slabs_kernel<FIXED, V210, L><<<grid, INSERT_THREADS, smem, st>>>(rb, k, lp_bits, nb, out, so)
+    if (FIXED && !V210) { // the common stream shape gets the unrolled forms
+        switch (nb == (1u << lp_bits) ? lp_bits : -1) {
+        case 3: GB_BS(3); return;
+        case 4: GB_BS(4); return;
+        case 5: GB_BS(5); return;
+        case 6: GB_BS(6); return;
+        case 7: GB_BS(7); return;
+        default: break;
         }
     }
+    GB_BS(-1);
+#undef GB_BS
 }
+
+static size_t slabs_smem(unsigned int nb) { return ((((size_t)(WARPS + 3) * nb + 2) & ~(size_t)1) + 2) * 4 + (size_t)ROUND_KEYS * 8; }
 
 // ---------------------------------------------------------------- bulk upsert from key ranges
 constexpr int IK_THREADS = 256;
@@ -557,7 +688,7 @@ static int launch_scatter(const ReadBatch &rb, int k, bool v210, const PartLayou
     memset(&po, 0, sizeof po);
     if (peers) po = *peers;
     KeySource none;
-#define GB_PS(F, V, P) part_scatter_kernel<F, V, false, P, false><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist, w.bucket_base, out, po, SlabOut())
+#define GB_PS(F, V, P) part_scatter_kernel<F, V, false, P><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, (unsigned int)pl.owners, pl.lp_bits, nb, w.cta_hist, w.bucket_base, out, po)
 #define GB_PS2(F, V) do { if (peers) GB_PS(F, V, true); else GB_PS(F, V, false); } while (0)
     if (fixed) { if (v210) GB_PS2(true, true); else GB_PS2(true, false); }
     else { if (v210) GB_PS2(false, true); else GB_PS2(false, false); }
@@ -584,8 +715,8 @@ int part_scatter_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, un
     ReadBatch none;
     PeerOut po;
     memset(&po, 0, sizeof po);
-    part_scatter_kernel<true, false, true, false, false><<<w.grid, INSERT_THREADS, scatter_smem(nb), st>>>(none, ks, 0, (unsigned int)pl.owners, pl.lp_bits, nb,
-                                                                                                    w.cta_hist, w.bucket_base, out, po, SlabOut());
+    part_scatter_kernel<true, false, true, false><<<w.grid, INSERT_THREADS, scatter_smem(nb), st>>>(none, ks, 0, (unsigned int)pl.owners, pl.lp_bits, nb,
+                                                                                             w.cta_hist, w.bucket_base, out, po);
     GB_LAUNCHED();
     return GB_OK;
 }
@@ -647,7 +778,7 @@ int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &
         GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));
     }
     const bool fixed = rb.offsets == nullptr;
-    const size_t smem = scatter_smem(nb);
+    const size_t smem = slabs_smem(nb);
     const unsigned int n_chunks = nb * (unsigned int)w.grid;
     SlabOut so;
     so.slab = slab;
@@ -657,10 +788,7 @@ int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &
     so.overflowed = w.bucket_total; // one word is enough; the counted passes are not running
     GB_CUDA(cudaMemsetAsync(so.overflowed, 0, 8, st));
     GB_CUDA(cudaMemsetAsync(so.count, 0, (size_t)n_chunks * 4, st)); // the kernel resumes from these cursors
-    PeerOut po;
-    memset(&po, 0, sizeof po);
-    KeySource none;
-#define GB_PSS(F, V) part_scatter_kernel<F, V, false, false, true><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, 1u, pl.lp_bits, nb, nullptr, nullptr, out, po, so)
+#define GB_PSS(F, V) launch_bucket_slabs<F, V>(w.grid, smem, st, rb, k, pl.lp_bits, nb, out, so)
     if (fixed) { if (v210) GB_PSS(true, true); else GB_PSS(true, false); }
     else { if (v210) GB_PSS(false, true); else GB_PSS(false, false); }
 #undef GB_PSS
@@ -692,12 +820,9 @@ int slab_list_range(const ReadBatch &rb, int k, bool v210, const PartLayout &pl,
     so.ovf = out + (size_t)slab * nb * (size_t)w.grid;
     so.ovf_cap = ovf_cap;
     so.failed = reinterpret_cast<unsigned int *>(w.bucket_total + 1);
-    PeerOut po;
-    memset(&po, 0, sizeof po);
-    KeySource none;
-    const size_t smem = scatter_smem(nb);
-    if (v210) part_scatter_kernel<true, true, false, false, true><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, 1u, pl.lp_bits, nb, nullptr, nullptr, out, po, so);
-    else part_scatter_kernel<true, false, false, false, true><<<w.grid, INSERT_THREADS, smem, st>>>(rb, none, k, 1u, pl.lp_bits, nb, nullptr, nullptr, out, po, so);
+    const size_t smem = slabs_smem(nb);
+    if (v210) launch_bucket_slabs<true, true>(w.grid, smem, st, rb, k, pl.lp_bits, nb, out, so);
+    else launch_bucket_slabs<true, false>(w.grid, smem, st, rb, k, pl.lp_bits, nb, out, so);
     GB_LAUNCHED();
     return GB_OK;
 }
