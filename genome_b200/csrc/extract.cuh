@@ -23,6 +23,7 @@ struct __align__(16) ReadTile {
     unsigned int start[TILE_READS];   // bit position of base 0 of the read inside `bytes`
     unsigned int prefix[TILE_READS + 1]; // exclusive prefix of work items per read
     unsigned short nwin[TILE_READS];
+    unsigned int ipr_inv; // every read of the tile has the same number (>= 2) of work items: floor(2^32 / items) + 1, else 0
 };
 
 #ifdef __CUDACC__
@@ -99,6 +100,10 @@ __device__ __forceinline__ int stage_tile(ReadTile &tile, const uint8_t *__restr
             run += c[j];
         }
         if (tid == 31) tile.prefix[TILE_READS] = run;
+        // equal-length reads (the usual stream): item -> read by one multiply instead of a search (item_keys)
+        const unsigned int c0 = __shfl_sync(0xFFFFFFFFu, c[0], 0);
+        const bool same = __all_sync(0xFFFFFFFFu, c[0] == c0 && c[1] == c0 && c[2] == c0 && c[3] == c0);
+        if (tid == 0) tile.ipr_inv = same && c0 >= 2 ? (unsigned int)((1ull << 32) / c0) + 1u : 0u;
     }
     __syncthreads();
     return nr;
@@ -108,10 +113,15 @@ __device__ __forceinline__ int stage_tile(ReadTile &tile, const uint8_t *__restr
 template <bool V210>
 __device__ __forceinline__ int item_keys(const ReadTile &tile, unsigned int item, int k, unsigned long long key[SEG])
 {
-    int lo = 0, hi = TILE_READS;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (tile.prefix[mid] <= item) lo = mid; else hi = mid;
+    int lo = 0;
+    if (tile.ipr_inv) {
+        lo = (int)__umulhi(item, tile.ipr_inv); // exact for item < 2^32 / items per read
+    } else {
+        int hi = TILE_READS;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (tile.prefix[mid] <= item) lo = mid; else hi = mid;
+        }
     }
     const unsigned long long kmask = (1ull << (2 * k)) - 1;
     const unsigned int p = (item - tile.prefix[lo]) * SEG;

@@ -329,7 +329,8 @@ bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, uns
             int cnt = 0;
             if (item < total_items) cnt = item_keys<V210>(tile, item, k, key);
             for (unsigned int b = lane; b < nb; b += 32) rcnt[b] = 0;
-            unsigned int bk[SEG], pm[SEG];
+            unsigned int bk[SEG], pm[SEG], rk[SEG];
+            if (__any_sync(0xFFFFFFFFu, cnt > 0)) { // a warp without items (the tail round of a tile) only keeps the barriers
 #pragma unroll
             for (int j = 0; j < SEG; j++) {
                 const bool valid = j < cnt;
@@ -353,7 +354,6 @@ bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, uns
                 pm[j] = valid ? peers : 0u;
             }
             __syncwarp();
-            unsigned int rk[SEG];
 #pragma unroll
             for (int j = 0; j < SEG; j++) {
                 const bool valid = pm[j] != 0;
@@ -363,6 +363,7 @@ bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, uns
                 if (valid && rank == 0) rcnt[bk[j]] = base + __popc(pm[j]);
                 __syncwarp();
                 rk[j] = base + rank; // rank among this warp's keys of the bucket in this round
+            }
             }
             __syncthreads(); // (A) every warp's counts are final; the previous round's flush is over
             if (warp == 0) {
@@ -403,14 +404,16 @@ bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, uns
             __syncthreads(); // (C) the round is staged, sorted by bucket
             for (unsigned int b = warp; b < nb; b += WARPS) {
                 const unsigned int s0 = bstart[b], n = bstart[b + 1] - s0, pos = dbase[b];
-                const unsigned int room = (b * grid + cta + 1) * slab - pos;
-                for (unsigned int i = lane; i < n; i += 32) {
+                const unsigned int room = (b * grid + cta + 1) * slab - pos, fit = min(n, room);
+                const unsigned long long *sp = skey + s0 + lane;
+                unsigned long long *gp = out + pos + lane;
+                for (unsigned int i = lane; i < fit; i += 32, sp += 32, gp += 32) *gp = *sp;
+                for (unsigned int i = fit + lane; i < n; i += 32) { // beyond the slab (pathological inputs only)
                     const unsigned long long key1 = skey[s0 + i];
-                    if (i < room) { out[pos + i] = key1; continue; }
-                    if (so.ovf) { // beyond the slab, LIST mode
+                    if (so.ovf) { // LIST mode
                         const unsigned long long at = atomicAdd(so.overflowed, 1ull);
                         if (at < so.ovf_cap) so.ovf[at] = key1; else *so.failed = 1u;
-                    } else { // beyond the slab: upserted right here, random access
+                    } else { // upserted right here, random access
                         const unsigned long long i1 = slot_of(mix64(key1), so.table.cap);
                         if (upsert_add(so.table, i1, load_key(so.table, i1), key1, 1)) atomicAdd(&so.spread[cta & (SPREAD - 1)], 1ull);
                         atomicAdd(so.overflowed, 1ull);
@@ -533,89 +536,125 @@ fold_new_keys_kernel(unsigned long long *spread, unsigned long long *counters)
 // keys at keys[s * slab], and work item (s, part) takes keys [part * 1024, ...) of it.  The launch is sized for full slabs; an
 // item whose part lies beyond count[s] does nothing.  No chunk table, no search: measured on C2 the search over the 19 k-entry
 // chunk table cost the generic kernel 0.2 ms (2.15 against 1.95 ms).  Slabs are bucket-major, so slice order is kept.
-// The kernel is latency bound (ncu r2c: 29 long-scoreboard stall cycles per issue, half occupancy): three dependent round trips
-// per key -- staged key, table key, compare-and-swap.  Variants under measurement (gb_tune exp): MINB = CTAs per SM the register
-// allocation must allow; CAS_FIRST = the compare-and-swap IS the probe (no preceding load: one round trip less for a new key, and
-// key lines see atomics only); PERSIST = one CTA per SM slot walks the items and fetches the next item's keys before it works on
-// the current ones.  Slot indices are 32-bit (IdxT) whenever the table has fewer than 2^32 slots.
-template <int MINB, bool CAS_FIRST, bool PERSIST, typename IdxT>
-__global__ void __launch_bounds__(IK_THREADS, MINB)
+// The kernel is latency bound (ncu r2c: 29 long-scoreboard stall cycles per issue): three dependent round trips per key -- staged
+// key, table key, compare-and-swap -- so the register allocation is held to 6 CTAs per SM (measured r2d: 1.76 -> 1.62 ms on C2;
+// 8 CTAs per SM spill and give 1.65).  Measured and dropped (profiles/r2d_upsert_variants.jsonl): the compare-and-swap as the
+// probe (no preceding load): 1.73 ms; a persistent grid fetching the next item's keys early: 9 ms -- the CTAs drift apart and
+// the slice being filled no longer stays in L2.  Slot indices are 32-bit (IdxT) whenever the table has fewer than 2^32 slots.
+// BOUNDED (the clear fused into the insert, insert_slabs below): only slots below `limit` are initialised; a probe that reaches
+// `limit` gives up and appends the key to the overflow list, which is upserted when the whole table is valid.
+struct OvfList {
+    unsigned long long *keys = nullptr, *cursor = nullptr; // cursor counts every append, also those beyond cap
+    unsigned long long cap = 0;
+    unsigned int *failed = nullptr; // set when an append did not fit
+};
+__device__ __forceinline__ void ovf_append(const OvfList &l, unsigned long long key)
+{
+    const unsigned long long at = atomicAdd(l.cursor, 1ull);
+    if (at < l.cap) l.keys[at] = key; else *l.failed = 1u;
+}
+
+template <bool BOUNDED, typename IdxT>
+__global__ void __launch_bounds__(IK_THREADS, 6)
 insert_slabs_kernel(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ count, unsigned int slab,
-                    unsigned int ctas_per_slab, unsigned int n_work, Table table, unsigned long long *spread)
+                    unsigned int ctas_per_slab, unsigned int w0, Table table, unsigned long long *spread, unsigned long long limit, OvfList ovf,
+                    int abl = 0)
 {
     constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
     const unsigned long long cap = table.cap;
-    int nk = 0;
-    auto fetch = [&](unsigned int w, unsigned long long (&key)[IK_PER_THREAD], bool (&ok)[IK_PER_THREAD]) {
-        const unsigned int s = w / ctas_per_slab, part = w - s * ctas_per_slab;
-        const unsigned int n = min(count[s], slab), v0 = part * IK_PER_CTA;
-        const unsigned long long *src = keys + (size_t)s * slab + v0;
+    const unsigned int w = w0 + blockIdx.x;
+    const unsigned int s = w / ctas_per_slab, part = w - s * ctas_per_slab;
+    const unsigned int n = min(count[s], slab), v0 = part * IK_PER_CTA;
+    if (v0 >= n) return;
+    const unsigned long long *src = keys + (size_t)s * slab + v0;
+    unsigned long long key[IK_PER_THREAD], cur[IK_PER_THREAD], old[IK_PER_THREAD];
+    IdxT idx[IK_PER_THREAD];
+    bool ok[IK_PER_THREAD];
 #pragma unroll
-        for (int j = 0; j < IK_PER_THREAD; j++) {
-            const unsigned int i = (unsigned int)j * IK_THREADS + threadIdx.x;
-            ok[j] = v0 + i < n;
-            if (ok[j]) key[j] = __ldcs(src + i);
+    for (int j = 0; j < IK_PER_THREAD; j++) {
+        const unsigned int i = (unsigned int)j * IK_THREADS + threadIdx.x;
+        ok[j] = v0 + i < n;
+        if (ok[j]) {
+            key[j] = __ldcs(src + i);
+            idx[j] = (IdxT)slot_of(mix64(key[j]), cap);
         }
-    };
-    auto process = [&](const unsigned long long (&key)[IK_PER_THREAD], const bool (&ok)[IK_PER_THREAD]) {
-        IdxT idx[IK_PER_THREAD];
-        unsigned long long cur[IK_PER_THREAD], old[IK_PER_THREAD];
+    }
+    if (abl == 2) { // ABLATION (timing only): staged keys + hashing, no table access
+        unsigned long long a = 0;
 #pragma unroll
         for (int j = 0; j < IK_PER_THREAD; j++)
-            if (ok[j]) idx[j] = (IdxT)slot_of(mix64(key[j]), cap);
-        if (CAS_FIRST) {
+            if (ok[j]) a += idx[j];
+        if (a == 0x123456789ull) spread[0] = a;
+        return;
+    }
 #pragma unroll
-            for (int j = 0; j < IK_PER_THREAD; j++) {
-                cur[j] = EMPTY_KEY;
-                if (ok[j]) old[j] = atomicCAS(table.key + idx[j], EMPTY_KEY, key[j]);
+    for (int j = 0; j < IK_PER_THREAD; j++)
+        if (ok[j]) cur[j] = load_key(table, idx[j]);
+    if (abl == 1 || abl == 3) { // ABLATION (timing only): 1 = table loads only; 3 = loads, then a red for every key, no CAS
+        unsigned long long a = 0;
+#pragma unroll
+        for (int j = 0; j < IK_PER_THREAD; j++)
+            if (ok[j]) {
+                a += cur[j];
+                if (abl == 3) red_add_s32(table.count + idx[j], cur[j] == key[j] ? 1 : 2);
             }
+        if (a == 0x123456789ull) spread[0] = a;
+        return;
+    }
+    // the CAS round trips of a thread's keys overlap: all of them are issued before the first result is used
+#pragma unroll
+    for (int j = 0; j < IK_PER_THREAD; j++) {
+        old[j] = cur[j];
+        if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(table.key + idx[j], EMPTY_KEY, key[j]);
+    }
+    int nk = 0;
+#pragma unroll
+    for (int j = 0; j < IK_PER_THREAD; j++) {
+        if (!ok[j]) continue;
+        const bool claimed = cur[j] == EMPTY_KEY && old[j] == EMPTY_KEY;
+        if (claimed || old[j] == key[j]) {
+            red_add_s32(table.count + idx[j], 1);
+            nk += claimed;
+        } else if (!BOUNDED) {
+            // the slot belongs to another key: linear probing from the next slot (rare at load <= 0.5)
+            const unsigned long long nx = next_slot(idx[j], cap);
+            nk += upsert_add(table, nx, load_key(table, nx), key[j], 1);
         } else {
-#pragma unroll
-            for (int j = 0; j < IK_PER_THREAD; j++)
-                if (ok[j]) cur[j] = load_key(table, idx[j]);
-#pragma unroll
-            for (int j = 0; j < IK_PER_THREAD; j++) {
-                old[j] = cur[j];
-                if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(table.key + idx[j], EMPTY_KEY, key[j]);
+            unsigned long long at = (unsigned long long)idx[j] + 1; // no wrap: slots beyond `limit` (or before the slice) may be uninitialised
+            for (;;) {
+                if (at >= limit) { ovf_append(ovf, key[j]); break; }
+                unsigned long long c = load_key(table, at);
+                if (c == EMPTY_KEY) {
+                    c = atomicCAS(table.key + at, EMPTY_KEY, key[j]);
+                    if (c == EMPTY_KEY) { nk++; c = key[j]; }
+                }
+                if (c == key[j]) { red_add_s32(table.count + at, 1); break; }
+                at++;
             }
-        }
-#pragma unroll
-        for (int j = 0; j < IK_PER_THREAD; j++) {
-            if (!ok[j]) continue;
-            const bool claimed = cur[j] == EMPTY_KEY && old[j] == EMPTY_KEY;
-            if (claimed || old[j] == key[j]) {
-                red_add_s32(table.count + idx[j], 1);
-                nk += claimed;
-            } else {
-                unsigned long long nx = next_slot(idx[j], cap);
-                nk += upsert_add(table, nx, load_key(table, nx), key[j], 1);
-            }
-        }
-    };
-    unsigned long long key[IK_PER_THREAD];
-    bool ok[IK_PER_THREAD];
-    if (!PERSIST) {
-        fetch(blockIdx.x, key, ok);
-        process(key, ok);
-    } else {
-        unsigned int w = blockIdx.x;
-        if (w < n_work) fetch(w, key, ok);
-        while (w < n_work) {
-            const unsigned int wn = w + gridDim.x;
-            unsigned long long key2[IK_PER_THREAD];
-            bool ok2[IK_PER_THREAD];
-#pragma unroll
-            for (int j = 0; j < IK_PER_THREAD; j++) ok2[j] = false;
-            if (wn < n_work) fetch(wn, key2, ok2);
-            process(key, ok);
-#pragma unroll
-            for (int j = 0; j < IK_PER_THREAD; j++) { key[j] = key2[j]; ok[j] = ok2[j]; }
-            w = wn;
         }
     }
     nk = __reduce_add_sync(0xFFFFFFFFu, nk);
     if ((threadIdx.x & 31) == 0 && nk)
         atomicAdd(&spread[(blockIdx.x * (IK_THREADS / 32) + (threadIdx.x >> 5)) & (SPREAD - 1)], (unsigned long long)nk);
+}
+
+// slots [lo, hi) of an uninitialised table become EMPTY (keys all ones, counts 0); the vertex ids stay undefined (common.cuh)
+__global__ void __launch_bounds__(256)
+init_slots_kernel(Table t, unsigned long long lo, unsigned long long hi)
+{
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
+    for (unsigned long long i = lo + (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < hi; i += stride) {
+        t.key[i] = EMPTY_KEY;
+        t.count[i] = 0;
+    }
+}
+
+// the overflow list's 3-word chunk table { vstart[0], vstart[1], off[0] } once nothing appends to it any more
+__global__ void ovf_desc_kernel(const unsigned long long *cursor, unsigned long long cap, unsigned long long *desc)
+{
+    desc[0] = 0;
+    desc[1] = min(*cursor, cap);
+    desc[2] = 0;
 }
 
 // ---------------------------------------------------------------- host side
@@ -849,7 +888,16 @@ int make_single_chunk(const unsigned long long *d_total, unsigned long long *d_d
     return GB_OK;
 }
 
-int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d_count, unsigned int slab, unsigned int n_slabs, cudaStream_t st)
+// sc == nullptr: the table is valid, one launch over all slabs.
+// sc != nullptr: THE CLEAR IS FUSED INTO THE INSERT.  The table is logically empty but physically uninitialised (Map::lazy_clear);
+// bucket b's keys have their home slots in [start_b, start_{b+1}] (start_b = slot of the smallest hash of the bucket), so the
+// slices are initialised one at a time, each right before its keys are upserted: init [start_b + A, start_{b+1} + A), upsert
+// bucket b with probing bounded by start_{b+1} + A (A slots of room for linear probing past the slice's end; a probe that needs
+// more, or would wrap at the end of the table, spills to the overflow list).  The slice is written by the init, updated by the
+// upsert and leaves L2 once: the separate clear (a DRAM write of the whole table) and the upsert's DRAM reads of empty lines
+// both disappear.  Afterwards the overflow list (bucket-pass overflows + spilled probes) is upserted into the now valid table.
+int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d_count, unsigned int slab, unsigned int n_slabs, cudaStream_t st,
+                 const SliceClear *sc)
 {
     if (!n_slabs || !slab) return GB_OK;
     m->kept_valid = false;
@@ -861,22 +909,40 @@ int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d
     const unsigned long long work = (unsigned long long)n_slabs * per;
     if (work >= 0x7FFFFFFFull) { set_error("internal: %llu slab CTAs", work); return GB_E_ARG; }
     const Table t = m->view();
-    const long long e = g_tune.exp;
-    const bool cas_first = e & 2, persist = e & 4;
-    const int minb = (e & 16) ? 8 : (e & 8) ? 6 : 4;
-    const unsigned int grid = persist ? (unsigned int)std::min<unsigned long long>(work, (unsigned long long)SM_COUNT * minb) : (unsigned int)work;
-#define GB_IS(M, C, P, I) insert_slabs_kernel<M, C, P, I><<<grid, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, (unsigned int)work, t, m->d_spread)
-#define GB_IS3(M, I) do { if (cas_first) { if (persist) GB_IS(M, true, true, I); else GB_IS(M, true, false, I); } \
-                          else { if (persist) GB_IS(M, false, true, I); else GB_IS(M, false, false, I); } } while (0)
-    if (t.cap >= (1ull << 32)) GB_IS3(4, unsigned long long);
-    else if (minb == 8) GB_IS3(8, unsigned int);
-    else if (minb == 6) GB_IS3(6, unsigned int);
-    else GB_IS3(4, unsigned int);
-#undef GB_IS3
-#undef GB_IS
-    GB_LAUNCHED();
+    const bool idx32 = t.cap < (1ull << 32);
+    if (!sc) {
+        if (idx32) insert_slabs_kernel<false, unsigned int><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, 0u, t, m->d_spread, 0ull, OvfList(), (int)((g_tune.exp >> 6) & 3));
+        else insert_slabs_kernel<false, unsigned long long><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, 0u, t, m->d_spread, 0ull, OvfList());
+        GB_LAUNCHED();
+    } else {
+        constexpr unsigned long long AHEAD = 8192;
+        const unsigned int nb = (unsigned int)sc->nb, per_bucket = (unsigned int)sc->grid * per;
+        if ((unsigned long long)nb * sc->grid != n_slabs) { set_error("internal: %u buckets x %d CTAs != %u slabs", nb, sc->grid, n_slabs); return GB_E_ARG; }
+        auto start_of = [&](unsigned int b) -> unsigned long long { // slot of the smallest hash of bucket b
+            if (b == 0 || sc->lp_bits == 0) return b == 0 ? 0 : t.cap;
+            if (b >= nb) return t.cap;
+            return slot_of((unsigned long long)b << (64 - sc->lp_bits), t.cap);
+        };
+        OvfList ovf;
+        ovf.keys = sc->ovf; ovf.cursor = sc->cursor; ovf.cap = sc->ovf_cap; ovf.failed = sc->failed;
+        for (unsigned int b = 0; b < nb; b++) {
+            const unsigned long long lo = b == 0 ? 0 : std::min(t.cap, start_of(b) + AHEAD);
+            const unsigned long long hi = b + 1 == nb ? t.cap : std::min(t.cap, start_of(b + 1) + AHEAD);
+            if (hi > lo) {
+                init_slots_kernel<<<grid_for(hi - lo, 256, 32), 256, 0, st>>>(t, lo, hi);
+                GB_LAUNCHED();
+            }
+            if (idx32) insert_slabs_kernel<true, unsigned int><<<per_bucket, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, b * per_bucket, t, m->d_spread, hi, ovf);
+            else insert_slabs_kernel<true, unsigned long long><<<per_bucket, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, b * per_bucket, t, m->d_spread, hi, ovf);
+            GB_LAUNCHED();
+        }
+        m->lazy_clear = false; // every slot has been initialised
+        ovf_desc_kernel<<<1, 1, 0, st>>>(sc->cursor, sc->ovf_cap, sc->d_desc);
+        GB_LAUNCHED();
+    }
     fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
     GB_LAUNCHED();
+    if (sc) GB_TRY(insert_key_chunks(m, sc->ovf, sc->d_desc, sc->d_desc + 2, 1, sc->ovf_cap, st, true));
     return GB_OK;
 }
 
