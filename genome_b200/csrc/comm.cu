@@ -910,7 +910,6 @@ int gb_pmap_create(gb_comm *ch, int k, int64_t min_capacity_per_shard, uint32_t 
     Comm *c = reinterpret_cast<Comm *>(ch);
     GB_TRY(gb_map_create(k, min_capacity_per_shard, c->device, flags, out));
     reinterpret_cast<Map *>(*out)->comm = c;
-    GB_TRY(map_materialize(reinterpret_cast<Map *>(*out))); // shards are filled by internal calls: no deferred clear
     // every rank must be tuned alike: the ownership rule is a property of the whole sharded map
     if (g_tune.wire_superkmer) reinterpret_cast<Map *>(*out)->owner_mode = 1;
     return GB_OK;
@@ -1152,9 +1151,8 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
     if (!rh) {
         GB_TRY(gb_map_create(m->k, (int64_t)t, m->device, m->v210 ? GB_FLAG_HASH_SCALA_210 : 0, &rh));
         m->replica = reinterpret_cast<Map *>(rh);
-        GB_TRY(map_materialize(m->replica));
     } else {
-        GB_TRY(map_clear(reinterpret_cast<Map *>(rh), (int64_t)t, false)); // filled by internal calls right below: no deferred clear
+        GB_TRY(gb_map_clear(rh, (int64_t)t));
     }
     Map *r = reinterpret_cast<Map *>(rh);
     r->noncanonical = dual != 0;

@@ -49,8 +49,6 @@ struct Tuning {
                                         // ncclSend/ncclRecv, 2 = local bucket pass + copy-engine pushes into the inboxes
     long long wire_superkmer = 0;       // sharded maps created from now on: minimizer owners, 16-byte super-k-mer records on the wire
     long long pgraph_sharded = 0;       // Graph.buildGraph over shards without a replica (sgraph.cuh)
-    long long lazy_clear = 1;           // gb_map_clear of an unsharded map only marks the table; the next single-pass insert initialises
-                                        // it slice by slice on the way (the clear fused into the insert), anything else first clears it
     long long trace = 0;                // phase timings on stderr
     long long exp = 0;                  // A/B bits of the experiment in progress (0 in production; see scripts/r2_insert_sweep.py)
 };
@@ -66,7 +64,7 @@ extern Tuning g_tune;
 // the claiming CAS), the count lines are written only, and the vertex ids are not touched before Graph.buildGraph.
 struct Table {
     unsigned long long *key = nullptr; // EMPTY_KEY when free; k <= 31 keys use at most 62 bits
-    int *count = nullptr;              // DNAMap[Int] value
+    int *count = nullptr;              // DNAMap[Int] value; the word of a FREE slot holds 1, the count its claimer starts with
     unsigned int *vid = nullptr;       // dense vertex id, assigned by gb_graph_build / deleteAll
     unsigned long long cap = 0;
 };
@@ -404,7 +402,6 @@ struct Map {
     unsigned long long alloc_cap = 0; // the allocation behind `table` holds this many slots (>= cap)
     void *spare = nullptr;     // the other table allocation of the clear / filter cycle, kept for reuse
     Table view() const { return table_view(table, cap); }
-    bool lazy_clear = false;   // the table is logically EMPTY but its memory is uninitialised (gb_map_clear deferred: map_materialize)
     unsigned long long spare_cap = 0;
     unsigned long long *stage = nullptr; // key staging of the partitioned insert and of the filter (grow-only)
     size_t stage_cap = 0;
@@ -449,10 +446,7 @@ struct ShardPlan {
     void *ctx = nullptr;
 };
 int graph_build_sharded(gb_map *h, gb_graph **out, const ShardPlan *sp);
-// every entry point starts here; keep_lazy: the caller can work on a deferred clear itself (the insert entry points)
-int check_map(gb_map *h, Map **m, bool keep_lazy = false);
-int map_materialize(Map *m);                                  // a deferred clear is carried out now
-int map_clear(Map *m, int64_t min_capacity, bool may_defer);  // gb_map_clear
+int check_map(gb_map *h, Map **m);
 // assert(key.length == k) of apply / contains (S/ds/ArrayDNAMap.scala:182-206): a query with bits above 2k is an error
 int check_keys(const Map *m, const uint64_t *keys, int64_t n);
 
@@ -463,7 +457,7 @@ inline unsigned int grid_for(unsigned long long n, int threads, int per_sm = 16)
     if (g > cap) g = cap;
     return (unsigned int)(g ? g : 1);
 }
-int map_swap_table(Map *m, unsigned long long new_cap, void **old_table, unsigned long long *old_alloc_cap, bool defer_init = false);
+int map_swap_table(Map *m, unsigned long long new_cap, void **old_table, unsigned long long *old_alloc_cap);
 void map_retire_table(Map *m, void *t, unsigned long long alloc_cap);
 int map_stage(Map *m, size_t n_u64);
 int pool_setup(int device);

@@ -141,7 +141,7 @@ __device__ __forceinline__ int item_keys(const ReadTile &tile, unsigned int item
     return cnt;
 }
 
-// update(key, 1, _ + 1) (S/ds/ArrayDNAMap.scala:129-150) starting at slot idx whose key was already loaded
+// update(key, add, _ + add) (S/ds/ArrayDNAMap.scala:129-150) starting at slot idx whose key was already loaded
 // into `cur`.  The caller guarantees the table never fills (map_budget), so the probe always terminates.
 // Returns 1 when the key was new.
 __device__ __forceinline__ int upsert_add(const Table &table, unsigned long long idx, unsigned long long cur, unsigned long long key, int add)
@@ -153,9 +153,13 @@ __device__ __forceinline__ int upsert_add(const Table &table, unsigned long long
         }
         if (cur == EMPTY_KEY) {
             unsigned long long old = atomicCAS(table.key + idx, EMPTY_KEY, key);
-            if (old == EMPTY_KEY || old == key) {
+            if (old == EMPTY_KEY) { // claimed: the count word of a free slot already holds 1 (init_table_kernel)
+                if (add != 1) red_add_s32(table.count + idx, add - 1);
+                return 1;
+            }
+            if (old == key) {
                 red_add_s32(table.count + idx, add);
-                return old == EMPTY_KEY;
+                return 0;
             }
         }
         idx = next_slot(idx, table.cap);

@@ -93,16 +93,18 @@ int pool_setup(int)
 
 // ================================================================ kernels
 
-// EMPTY table: keys = all ones, counts = 0; with_vid: vertex ids = NONE too.  n is a multiple of 1024 (cap_for), so every array
+// EMPTY table: keys = all ones, counts = 1 (!); with_vid: vertex ids = NONE too.  The count word of a free slot already holds the
+// 1 of the key that will claim it, so update(key, 1, _ + 1) of a NEW key is the claiming compare-and-swap alone, without a red
+// behind it -- 31 % of C2's k-mer instances are new keys (upsert_add, extract.cuh; every other writer stores the count outright).  n is a multiple of 1024 (cap_for), so every array
 // is a whole number of 16-byte vectors.  The vertex ids of a counting table are never read before they are assigned
 // (assign_vertices_kernel / place_distinct_kernel write them for every vertex), so the clear of a FreqFilter pass moves 12 bytes
 // per slot, not 16.
 __global__ void init_table_kernel(Table t, bool with_vid)
 {
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x, i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 ones = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu), first = make_uint4(1u, 1u, 1u, 1u);
     for (unsigned long long i = i0; i < t.cap / 2; i += stride) reinterpret_cast<uint4 *>(t.key)[i] = ones;
-    for (unsigned long long i = i0; i < t.cap / 4; i += stride) reinterpret_cast<uint4 *>(t.count)[i] = zero;
+    for (unsigned long long i = i0; i < t.cap / 4; i += stride) reinterpret_cast<uint4 *>(t.count)[i] = first;
     if (with_vid)
         for (unsigned long long i = i0; i < t.cap / 4; i += stride) reinterpret_cast<uint4 *>(t.vid)[i] = ones;
 }
@@ -401,7 +403,7 @@ void map_retire_table(Map *m, void *t, unsigned long long alloc_cap)
 
 // make an EMPTY table of new_cap slots current; the previous one is handed back (still valid on the stream:
 // the caller rehashes out of it and then retires it)
-int map_swap_table(Map *m, unsigned long long new_cap, void **old_table, unsigned long long *old_alloc_cap, bool defer_init)
+int map_swap_table(Map *m, unsigned long long new_cap, void **old_table, unsigned long long *old_alloc_cap)
 {
     void *nt = nullptr;
     unsigned long long na = new_cap;
@@ -412,8 +414,7 @@ int map_swap_table(Map *m, unsigned long long new_cap, void **old_table, unsigne
     } else {
         GB_CUDA(cudaMalloc(&nt, SLOT_BYTES * new_cap));
     }
-    if (!defer_init) GB_TRY(init_table(nt, new_cap, m->stream, false));
-    m->lazy_clear = defer_init;
+    GB_TRY(init_table(nt, new_cap, m->stream, false));
     m->kept_valid = false;
     *old_table = m->table;
     *old_alloc_cap = m->alloc_cap;
@@ -441,7 +442,6 @@ int map_stage(Map *m, size_t n_u64)
 // rehash into a table of new_cap slots (optionally dropping counts below min_count)
 int map_rebuild(Map *m, unsigned long long new_cap, bool filter, int min_count)
 {
-    GB_TRY(map_materialize(m));
     void *old = nullptr;
     unsigned long long old_alloc = 0;
     const unsigned long long n = m->cap;
@@ -594,11 +594,7 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
     const unsigned int slab = g_tune.single_pass && n_sub == 1 && pl.owners == 1 && nbk <= 128 && half >= countless_min()
                                   ? slab_keys_for(slab_cta_keys(n_reads, (unsigned long long)half, (int)grid), nbk, (int)grid) : 0;
     const size_t slab_keys = (size_t)slab * nbk * (size_t)grid, n_slab_chunks = (size_t)nbk * (size_t)grid;
-    // a deferred clear is fused into the single-pass form only (LIST-mode bucket pass: it may not touch the uninitialised table)
-    const bool fused = m->lazy_clear && slab != 0 && d_off == nullptr;
-    if (!fused) GB_TRY(map_materialize(m));
-    const unsigned long long ovf_cap = fused ? (unsigned long long)half / 16 + 65536 : 0;
-    GB_TRY(map_stage(m, slab ? slab_keys + (size_t)ovf_cap + 16 : (size_t)((n_sub > 1 ? 2 : 1) * (half + 8))));
+    GB_TRY(map_stage(m, slab ? slab_keys + 8 : (size_t)((n_sub > 1 ? 2 : 1) * (half + 8))));
     if (n_sub == 1) bk = up; // nothing to overlap: one stream, no cross-stream events
     // the bucket stream starts after everything already queued on the map's stream (clear, earlier inserts)
     GB_CUDA(cudaEventRecord(m->pe[2], up));
@@ -613,11 +609,7 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
         ReadBatch rb;
         rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = d_off; rb.rec_bytes = rec; rb.read0 = r0; rb.n_reads = nr;
         if (s >= 2) GB_CUDA(cudaStreamWaitEvent(bk, m->pfree[h], 0)); // the upsert of sub-batch s - 2 has consumed this half
-        if (fused) {
-            GB_TRY(slab_list_begin(pl, *work[h], bk));
-            GB_TRY(slab_list_range(rb, m->k, m->v210, pl, *work[h], keys, slab, ovf_cap, bk));
-            GB_TRY(slab_list_end(pl, *work[h], slab, ovf_cap, keys + slab_keys + ovf_cap, m, bk));
-        } else if (slab) {
+        if (slab) {
             GB_TRY(part_scatter_slabs(rb, m->k, m->v210, pl, *work[h], keys, slab, m, bk));
         } else {
             GB_TRY(part_count(rb, m->k, m->v210, pl, *work[h], bk));
@@ -635,14 +627,7 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
         }
         // the buckets are contiguous and already in slice order: one chunk; the launch is sized from the upper bound
         unsigned long long total = (unsigned long long)wu;
-        if (fused) {
-            SliceClear sc;
-            sc.nb = (int)nbk; sc.grid = (int)grid; sc.lp_bits = pl.lp_bits;
-            sc.ovf = keys + slab_keys; sc.ovf_cap = ovf_cap;
-            sc.cursor = work[h]->bucket_total; sc.failed = reinterpret_cast<unsigned int *>(work[h]->bucket_total + 1);
-            sc.d_desc = keys + slab_keys + ovf_cap;
-            GB_TRY(insert_slabs(m, keys, work[h]->cta_hist, slab, (unsigned int)n_slab_chunks, up, &sc));
-        } else if (slab) {
+        if (slab) {
             // the fill counts are on the device (keys in slabs; overflowed keys were upserted by the bucket pass)
             (void)total;
             GB_TRY(insert_slabs(m, keys, work[h]->cta_hist, slab, (unsigned int)n_slab_chunks, up));
@@ -660,21 +645,8 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
         GB_CUDA(cudaEventRecord(m->pfree[h], up));
     }
     if (bk != up) GB_CUDA(cudaEventRecord(m->pe[1], bk));
-    unsigned long long ovf_flags[2] = { 0, 0 };
-    if (fused) GB_CUDA(cudaMemcpyAsync(ovf_flags, work[0]->bucket_total, 16, cudaMemcpyDeviceToHost, up));
     GB_CUDA(cudaStreamSynchronize(bk));
     GB_CUDA(cudaStreamSynchronize(up));
-    if (fused && (unsigned int)ovf_flags[1]) {
-        // the overflow list did not hold everything (a pathological stream: one bucket far above its share): keys are missing
-        // from the table.  Start over on a cleared table with the counted passes, which need no list.
-        GB_TRY(init_table(m->table, m->cap, m->stream, false));
-        GB_TRY(map_zero_counters(m));
-        const long long sp = g_tune.single_pass;
-        g_tune.single_pass = 0;
-        const int rc = insert_partitioned(m, d_bin, n_bytes, d_off, rec, read0, n_reads, win_upper, bound_is_exact);
-        g_tune.single_pass = sp;
-        return rc;
-    }
     float ms = 0;
     // span of the bucket stream (one stream: up to the start of the upsert)
     GB_CUDA(cudaEventElapsedTime(&ms, m->pe[0], bk != up ? m->pe[1] : m->pup[0]));
@@ -740,10 +712,8 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
                                           (fixed && !lengths_vary) || h_win_prefix != nullptr));
             }
         } else if (fixed) {
-            GB_TRY(map_materialize(m));
             GB_TRY(launch_insert<true>(m, d_bin, n_bytes, nullptr, rec, done, take));
         } else {
-            GB_TRY(map_materialize(m));
             GB_TRY(launch_insert<false>(m, d_bin, n_bytes, d_off, 0, done, take));
         }
         GB_CUDA(cudaEventRecord(m->ev1, m->stream));
@@ -852,26 +822,11 @@ static int insert_host_pipelined(Map *m, const uint8_t *bin, int64_t n_reads, un
         GB_TRY(map_zero_counters(m)); // counters[3] was advanced by slab_list_end
         return GB_OK;
     }
-    if (m->lazy_clear) { // the clear is still pending: fuse it into the upsert, slice by slice (partition.cu)
-        SliceClear sc;
-        sc.nb = (int)nb; sc.grid = w.grid; sc.lp_bits = pl.lp_bits;
-        sc.ovf = keys + slab_keys; sc.ovf_cap = ovf_cap;
-        sc.cursor = w.bucket_total; sc.failed = reinterpret_cast<unsigned int *>(w.bucket_total + 1);
-        sc.d_desc = d_desc;
-        GB_TRY(insert_slabs(m, keys, w.cta_hist, slab, (unsigned int)n_chunks, m->stream, &sc));
-        GB_CUDA(cudaMemcpyAsync(flags, w.bucket_total, 16, cudaMemcpyDeviceToHost, m->stream));
-    } else {
-        GB_TRY(insert_slabs(m, keys, w.cta_hist, slab, (unsigned int)n_chunks, m->stream));
-        // the overflow list (its keys hit any slice: random access for those few); d_desc = its 3-word chunk table
-        GB_TRY(insert_key_chunks(m, keys + slab_keys, d_desc, d_desc + 2, 1, ovf_cap, m->stream, true));
-    }
+    GB_TRY(insert_slabs(m, keys, w.cta_hist, slab, (unsigned int)n_chunks, m->stream));
+    // the overflow list (its keys hit any slice: random access for those few); d_desc = its 3-word chunk table
+    GB_TRY(insert_key_chunks(m, keys + slab_keys, d_desc, d_desc + 2, 1, ovf_cap, m->stream, true));
     GB_CUDA(cudaEventRecord(m->ev1, m->stream));
     GB_TRY(map_read_counters(m, c));
-    if ((unsigned int)flags[1]) { // probes that left their slice overran the list: keys are missing; clear, and take the ordinary path
-        GB_TRY(init_table(m->table, m->cap, m->stream, false));
-        GB_TRY(map_zero_counters(m));
-        return GB_OK;
-    }
     float ms = 0;
     GB_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->pe[0]));
     m->phase_ns[0] = (int64_t)(ms * 1e6); // copy + bucket pass, overlapped
@@ -918,41 +873,12 @@ int check_keys(const Map *m, const uint64_t *keys, int64_t n)
     return GB_OK;
 }
 
-int check_map(gb_map *h, Map **m, bool keep_lazy)
+int check_map(gb_map *h, Map **m)
 {
     if (!h) { set_error("null map handle"); return GB_E_ARG; }
     *m = reinterpret_cast<Map *>(h);
     GB_CUDA(cudaSetDevice((*m)->device));
-    if (!keep_lazy) GB_TRY(map_materialize(*m));
     return GB_OK;
-}
-
-int map_clear(Map *m, int64_t min_capacity, bool may_defer)
-{
-    unsigned long long nb = cap_for(min_capacity);
-    if (nb != m->cap) {
-        void *old = nullptr;
-        unsigned long long old_alloc = 0;
-        GB_TRY(map_swap_table(m, nb, &old, &old_alloc, may_defer));
-        map_retire_table(m, old, old_alloc);
-    } else if (may_defer) {
-        m->lazy_clear = true;
-    } else {
-        m->lazy_clear = false;
-        GB_TRY(init_table(m->table, m->cap, m->stream, false));
-    }
-    m->size = 0;
-    m->kept_valid = false;
-    m->noncanonical = false;
-    m->windows = 0;
-    return GB_OK;
-}
-
-int map_materialize(Map *m)
-{
-    if (!m->lazy_clear) return GB_OK;
-    m->lazy_clear = false;
-    return init_table(m->table, m->cap, m->stream, false);
 }
 
 } // namespace gb
@@ -1035,7 +961,7 @@ int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_ma
         {
             void *none = nullptr;
             unsigned long long none_cap = 0;
-            if ((r = map_swap_table(m, cap0, &none, &none_cap, g_tune.lazy_clear != 0))) break; // a new map is a cleared map: deferred too
+            if ((r = map_swap_table(m, cap0, &none, &none_cap))) break;
         }
         if ((r = cudaStreamSynchronize(m->stream) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
     } while (0);
@@ -1090,7 +1016,7 @@ int gb_map_insert_reads_device(gb_map *h, const uint8_t *d_bin, size_t n_bytes, 
                                int64_t n_reads, int64_t *n_windows)
 {
     Map *m;
-    GB_TRY(check_map(h, &m, true)); // a deferred clear may be fused into this insert (insert_device)
+    GB_TRY(check_map(h, &m));
     ArenaScope scope(&m->arena);
     if (n_windows) *n_windows = 0;
     if (n_reads < 0 || (!d_bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
@@ -1116,7 +1042,7 @@ int gb_map_insert_reads_device(gb_map *h, const uint8_t *d_bin, size_t n_bytes, 
 int gb_map_insert_reads(gb_map *h, const uint8_t *bin, size_t n_bytes, int64_t n_reads, int64_t *n_windows)
 {
     Map *m;
-    GB_TRY(check_map(h, &m, true)); // a deferred clear may be fused into this insert (insert_device)
+    GB_TRY(check_map(h, &m));
     ArenaScope scope(&m->arena);
     if (n_windows) *n_windows = 0;
     if (n_reads < 0 || (!bin && n_reads > 0)) { set_error("bad arguments"); return GB_E_ARG; }
@@ -1169,7 +1095,7 @@ int gb_map_insert_records_device(gb_map *h, const uint8_t *d_bin, size_t n_bytes
                                  int64_t *n_windows)
 {
     Map *m;
-    GB_TRY(check_map(h, &m, true)); // a deferred clear may be fused into this insert (insert_device)
+    GB_TRY(check_map(h, &m));
     ArenaScope scope(&m->arena);
     if (n_windows) *n_windows = 0;
     if (n_records < 0 || (!d_bin && n_records > 0) || rec_bytes < 1 || rec_bytes > (uint32_t)MAX_REC_BYTES || max_len > 255) { set_error("bad arguments"); return GB_E_ARG; }
@@ -1339,9 +1265,22 @@ int gb_map_export(gb_map *h, uint64_t *keys, int32_t *vals, int64_t cap, int64_t
 int gb_map_clear(gb_map *h, int64_t min_capacity)
 {
     Map *m;
-    GB_TRY(check_map(h, &m, true)); // a clear that is still deferred is simply superseded
+    GB_TRY(check_map(h, &m));
     if (min_capacity < 0) { set_error("negative capacity"); return GB_E_ARG; }
-    return map_clear(m, min_capacity, g_tune.lazy_clear != 0 && !m->comm);
+    unsigned long long nb = cap_for(min_capacity);
+    if (nb != m->cap) {
+        void *old = nullptr;
+        unsigned long long old_alloc = 0;
+        GB_TRY(map_swap_table(m, nb, &old, &old_alloc));
+        map_retire_table(m, old, old_alloc);
+    } else {
+        GB_TRY(init_table(m->table, m->cap, m->stream, false));
+    }
+    m->size = 0;
+    m->kept_valid = false;
+    m->noncanonical = false;
+    m->windows = 0;
+    return GB_OK;
 }
 
 long long gb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -1349,7 +1288,7 @@ long long gb_launch_count(void) { return g_launches.load(std::memory_order_relax
 static long long *tune_field(const char *name)
 {
     static const struct { const char *name; long long Tuning::*field; } table[] = {
-        { "lazy_clear", &Tuning::lazy_clear }, { "insert_path", &Tuning::insert_path }, { "single_pass", &Tuning::single_pass }, { "single_pass_min", &Tuning::single_pass_min },
+        { "insert_path", &Tuning::insert_path }, { "single_pass", &Tuning::single_pass }, { "single_pass_min", &Tuning::single_pass_min },
         { "slice_bits", &Tuning::slice_bits }, { "batches", &Tuning::batches }, { "h2d_chunks", &Tuning::h2d_chunks },
         { "route", &Tuning::route }, { "a2a", &Tuning::a2a },
         { "wire_superkmer", &Tuning::wire_superkmer }, { "pgraph_sharded", &Tuning::pgraph_sharded }, { "trace", &Tuning::trace }, { "exp", &Tuning::exp },

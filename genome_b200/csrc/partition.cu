@@ -507,9 +507,10 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
     for (int j = 0; j < IK_PER_THREAD; j++) {
         if (!ok[j]) continue;
         const bool claimed = cur[j] == EMPTY_KEY && old[j] == EMPTY_KEY;
-        if (claimed || old[j] == key[j]) {
+        if (claimed) {
+            nk++; // the count word of a free slot already holds this key's 1 (init_table_kernel)
+        } else if (old[j] == key[j]) {
             red_add_s32(table.count + idx[j], 1);
-            nk += claimed;
         } else {
             // the slot belongs to another key: linear probing from the next slot (rare at load <= 0.5)
             unsigned long long nx = next_slot(idx[j], cap);
@@ -533,37 +534,26 @@ fold_new_keys_kernel(unsigned long long *spread, unsigned long long *counters)
 }
 
 // The same upsert over the SLABS of the single-pass bucket pass: slab number s = (bucket, CTA of the bucket pass) holds count[s]
-// keys at keys[s * slab], and work item (s, part) takes keys [part * 1024, ...) of it.  The launch is sized for full slabs; an
-// item whose part lies beyond count[s] does nothing.  No chunk table, no search: measured on C2 the search over the 19 k-entry
+// keys at keys[s * slab], and CTA (s, part) takes keys [part * 1024, ...) of it.  The launch is sized for full slabs; a CTA
+// whose part lies beyond count[s] leaves at once.  No chunk table, no search: measured on C2 the search over the 19 k-entry
 // chunk table cost the generic kernel 0.2 ms (2.15 against 1.95 ms).  Slabs are bucket-major, so slice order is kept.
 // The kernel is latency bound (ncu r2c: 29 long-scoreboard stall cycles per issue): three dependent round trips per key -- staged
 // key, table key, compare-and-swap -- so the register allocation is held to 6 CTAs per SM (measured r2d: 1.76 -> 1.62 ms on C2;
-// 8 CTAs per SM spill and give 1.65).  Measured and dropped (profiles/r2d_upsert_variants.jsonl): the compare-and-swap as the
-// probe (no preceding load): 1.73 ms; a persistent grid fetching the next item's keys early: 9 ms -- the CTAs drift apart and
-// the slice being filled no longer stays in L2.  Slot indices are 32-bit (IdxT) whenever the table has fewer than 2^32 slots.
-// BOUNDED (the clear fused into the insert, insert_slabs below): only slots below `limit` are initialised; a probe that reaches
-// `limit` gives up and appends the key to the overflow list, which is upserted when the whole table is valid.
-struct OvfList {
-    unsigned long long *keys = nullptr, *cursor = nullptr; // cursor counts every append, also those beyond cap
-    unsigned long long cap = 0;
-    unsigned int *failed = nullptr; // set when an append did not fit
-};
-__device__ __forceinline__ void ovf_append(const OvfList &l, unsigned long long key)
-{
-    const unsigned long long at = atomicAdd(l.cursor, 1ull);
-    if (at < l.cap) l.keys[at] = key; else *l.failed = 1u;
-}
-
-template <bool BOUNDED, typename IdxT>
+// 8 CTAs per SM spill and give 1.65).  Measured and dropped (profiles/r2d_upsert_variants.jsonl, r2g_upsert_ablation.jsonl): the
+// compare-and-swap as the probe (no preceding load): 1.73 ms; a persistent grid fetching the next item's keys early: 9 ms -- the
+// CTAs drift apart and the slice being filled no longer stays in L2; the clear fused into the insert (slice-wise initialisation
+// right before a slice is filled, bounded probing, overflow list): 2.39 ms against 0.23 + 1.52 -- lines that are already in L2 do
+// not make the upsert faster, its bound is the L2's handling of the requests, not DRAM.  What the parts cost on C2: staged keys +
+// hashing 0.20 ms, + table key loads 0.47, + one red per key 0.87, + compare-and-swap of the 31 % new keys 1.52.
+// Slot indices are 32-bit (IdxT) whenever the table has fewer than 2^32 slots.
+template <typename IdxT>
 __global__ void __launch_bounds__(IK_THREADS, 6)
 insert_slabs_kernel(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ count, unsigned int slab,
-                    unsigned int ctas_per_slab, unsigned int w0, Table table, unsigned long long *spread, unsigned long long limit, OvfList ovf,
-                    int abl = 0)
+                    unsigned int ctas_per_slab, Table table, unsigned long long *spread)
 {
     constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
     const unsigned long long cap = table.cap;
-    const unsigned int w = w0 + blockIdx.x;
-    const unsigned int s = w / ctas_per_slab, part = w - s * ctas_per_slab;
+    const unsigned int s = blockIdx.x / ctas_per_slab, part = blockIdx.x - s * ctas_per_slab;
     const unsigned int n = min(count[s], slab), v0 = part * IK_PER_CTA;
     if (v0 >= n) return;
     const unsigned long long *src = keys + (size_t)s * slab + v0;
@@ -579,28 +569,9 @@ insert_slabs_kernel(const unsigned long long *__restrict__ keys, const unsigned 
             idx[j] = (IdxT)slot_of(mix64(key[j]), cap);
         }
     }
-    if (abl == 2) { // ABLATION (timing only): staged keys + hashing, no table access
-        unsigned long long a = 0;
-#pragma unroll
-        for (int j = 0; j < IK_PER_THREAD; j++)
-            if (ok[j]) a += idx[j];
-        if (a == 0x123456789ull) spread[0] = a;
-        return;
-    }
 #pragma unroll
     for (int j = 0; j < IK_PER_THREAD; j++)
         if (ok[j]) cur[j] = load_key(table, idx[j]);
-    if (abl == 1 || abl == 3) { // ABLATION (timing only): 1 = table loads only; 3 = loads, then a red for every key, no CAS
-        unsigned long long a = 0;
-#pragma unroll
-        for (int j = 0; j < IK_PER_THREAD; j++)
-            if (ok[j]) {
-                a += cur[j];
-                if (abl == 3) red_add_s32(table.count + idx[j], cur[j] == key[j] ? 1 : 2);
-            }
-        if (a == 0x123456789ull) spread[0] = a;
-        return;
-    }
     // the CAS round trips of a thread's keys overlap: all of them are issued before the first result is used
 #pragma unroll
     for (int j = 0; j < IK_PER_THREAD; j++) {
@@ -612,49 +583,19 @@ insert_slabs_kernel(const unsigned long long *__restrict__ keys, const unsigned 
     for (int j = 0; j < IK_PER_THREAD; j++) {
         if (!ok[j]) continue;
         const bool claimed = cur[j] == EMPTY_KEY && old[j] == EMPTY_KEY;
-        if (claimed || old[j] == key[j]) {
+        if (claimed) {
+            nk++; // the count word of a free slot already holds this key's 1 (init_table_kernel)
+        } else if (old[j] == key[j]) {
             red_add_s32(table.count + idx[j], 1);
-            nk += claimed;
-        } else if (!BOUNDED) {
+        } else {
             // the slot belongs to another key: linear probing from the next slot (rare at load <= 0.5)
             const unsigned long long nx = next_slot(idx[j], cap);
             nk += upsert_add(table, nx, load_key(table, nx), key[j], 1);
-        } else {
-            unsigned long long at = (unsigned long long)idx[j] + 1; // no wrap: slots beyond `limit` (or before the slice) may be uninitialised
-            for (;;) {
-                if (at >= limit) { ovf_append(ovf, key[j]); break; }
-                unsigned long long c = load_key(table, at);
-                if (c == EMPTY_KEY) {
-                    c = atomicCAS(table.key + at, EMPTY_KEY, key[j]);
-                    if (c == EMPTY_KEY) { nk++; c = key[j]; }
-                }
-                if (c == key[j]) { red_add_s32(table.count + at, 1); break; }
-                at++;
-            }
         }
     }
     nk = __reduce_add_sync(0xFFFFFFFFu, nk);
     if ((threadIdx.x & 31) == 0 && nk)
         atomicAdd(&spread[(blockIdx.x * (IK_THREADS / 32) + (threadIdx.x >> 5)) & (SPREAD - 1)], (unsigned long long)nk);
-}
-
-// slots [lo, hi) of an uninitialised table become EMPTY (keys all ones, counts 0); the vertex ids stay undefined (common.cuh)
-__global__ void __launch_bounds__(256)
-init_slots_kernel(Table t, unsigned long long lo, unsigned long long hi)
-{
-    const unsigned long long stride = (unsigned long long)gridDim.x * 256;
-    for (unsigned long long i = lo + (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < hi; i += stride) {
-        t.key[i] = EMPTY_KEY;
-        t.count[i] = 0;
-    }
-}
-
-// the overflow list's 3-word chunk table { vstart[0], vstart[1], off[0] } once nothing appends to it any more
-__global__ void ovf_desc_kernel(const unsigned long long *cursor, unsigned long long cap, unsigned long long *desc)
-{
-    desc[0] = 0;
-    desc[1] = min(*cursor, cap);
-    desc[2] = 0;
 }
 
 // ---------------------------------------------------------------- host side
@@ -888,16 +829,7 @@ int make_single_chunk(const unsigned long long *d_total, unsigned long long *d_d
     return GB_OK;
 }
 
-// sc == nullptr: the table is valid, one launch over all slabs.
-// sc != nullptr: THE CLEAR IS FUSED INTO THE INSERT.  The table is logically empty but physically uninitialised (Map::lazy_clear);
-// bucket b's keys have their home slots in [start_b, start_{b+1}] (start_b = slot of the smallest hash of the bucket), so the
-// slices are initialised one at a time, each right before its keys are upserted: init [start_b + A, start_{b+1} + A), upsert
-// bucket b with probing bounded by start_{b+1} + A (A slots of room for linear probing past the slice's end; a probe that needs
-// more, or would wrap at the end of the table, spills to the overflow list).  The slice is written by the init, updated by the
-// upsert and leaves L2 once: the separate clear (a DRAM write of the whole table) and the upsert's DRAM reads of empty lines
-// both disappear.  Afterwards the overflow list (bucket-pass overflows + spilled probes) is upserted into the now valid table.
-int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d_count, unsigned int slab, unsigned int n_slabs, cudaStream_t st,
-                 const SliceClear *sc)
+int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d_count, unsigned int slab, unsigned int n_slabs, cudaStream_t st)
 {
     if (!n_slabs || !slab) return GB_OK;
     m->kept_valid = false;
@@ -909,40 +841,11 @@ int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d
     const unsigned long long work = (unsigned long long)n_slabs * per;
     if (work >= 0x7FFFFFFFull) { set_error("internal: %llu slab CTAs", work); return GB_E_ARG; }
     const Table t = m->view();
-    const bool idx32 = t.cap < (1ull << 32);
-    if (!sc) {
-        if (idx32) insert_slabs_kernel<false, unsigned int><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, 0u, t, m->d_spread, 0ull, OvfList(), (int)((g_tune.exp >> 6) & 3));
-        else insert_slabs_kernel<false, unsigned long long><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, 0u, t, m->d_spread, 0ull, OvfList());
-        GB_LAUNCHED();
-    } else {
-        constexpr unsigned long long AHEAD = 8192;
-        const unsigned int nb = (unsigned int)sc->nb, per_bucket = (unsigned int)sc->grid * per;
-        if ((unsigned long long)nb * sc->grid != n_slabs) { set_error("internal: %u buckets x %d CTAs != %u slabs", nb, sc->grid, n_slabs); return GB_E_ARG; }
-        auto start_of = [&](unsigned int b) -> unsigned long long { // slot of the smallest hash of bucket b
-            if (b == 0 || sc->lp_bits == 0) return b == 0 ? 0 : t.cap;
-            if (b >= nb) return t.cap;
-            return slot_of((unsigned long long)b << (64 - sc->lp_bits), t.cap);
-        };
-        OvfList ovf;
-        ovf.keys = sc->ovf; ovf.cursor = sc->cursor; ovf.cap = sc->ovf_cap; ovf.failed = sc->failed;
-        for (unsigned int b = 0; b < nb; b++) {
-            const unsigned long long lo = b == 0 ? 0 : std::min(t.cap, start_of(b) + AHEAD);
-            const unsigned long long hi = b + 1 == nb ? t.cap : std::min(t.cap, start_of(b + 1) + AHEAD);
-            if (hi > lo) {
-                init_slots_kernel<<<grid_for(hi - lo, 256, 32), 256, 0, st>>>(t, lo, hi);
-                GB_LAUNCHED();
-            }
-            if (idx32) insert_slabs_kernel<true, unsigned int><<<per_bucket, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, b * per_bucket, t, m->d_spread, hi, ovf);
-            else insert_slabs_kernel<true, unsigned long long><<<per_bucket, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, b * per_bucket, t, m->d_spread, hi, ovf);
-            GB_LAUNCHED();
-        }
-        m->lazy_clear = false; // every slot has been initialised
-        ovf_desc_kernel<<<1, 1, 0, st>>>(sc->cursor, sc->ovf_cap, sc->d_desc);
-        GB_LAUNCHED();
-    }
+    if (t.cap < (1ull << 32)) insert_slabs_kernel<unsigned int><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, t, m->d_spread);
+    else insert_slabs_kernel<unsigned long long><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, t, m->d_spread);
+    GB_LAUNCHED();
     fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
     GB_LAUNCHED();
-    if (sc) GB_TRY(insert_key_chunks(m, sc->ovf, sc->d_desc, sc->d_desc + 2, 1, sc->ovf_cap, st, true));
     return GB_OK;
 }
 

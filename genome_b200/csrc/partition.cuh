@@ -86,18 +86,8 @@ int slab_list_range(const ReadBatch &rb, int k, bool v210, const PartLayout &pl,
 int slab_list_end(const PartLayout &pl, PartWork &w, unsigned int slab, unsigned long long ovf_cap, unsigned long long *d_desc, Map *m, cudaStream_t st);
 int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned long long *out, unsigned int slab,
                        Map *m, cudaStream_t st);
-// the upsert over those slabs (slab s holds min(d_count[s], slab) keys at d_keys + s * slab), in slab order = slice order.
-// With a SliceClear the table is initialised slice by slice on the way (the clear fused into the insert; partition.cu) and the
-// overflow list of the LIST-mode bucket pass -- which also takes the probes that leave their slice -- is upserted at the end.
-struct SliceClear {
-    int nb = 0, grid = 0, lp_bits = 0;            // slabs are [bucket][CTA of the bucket pass]; bucket = top lp_bits of the hash
-    unsigned long long *ovf = nullptr, ovf_cap = 0; // the overflow list of the bucket pass ...
-    unsigned long long *cursor = nullptr;          // ... its append cursor
-    unsigned int *failed = nullptr;                // ... and its "did not fit" flag
-    unsigned long long *d_desc = nullptr;          // 3 words: receives the list's chunk table
-};
-int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d_count, unsigned int slab, unsigned int n_slabs, cudaStream_t st,
-                 const SliceClear *sc = nullptr);
+// the upsert over those slabs (slab s holds min(d_count[s], slab) keys at d_keys + s * slab), in slab order = slice order
+int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d_count, unsigned int slab, unsigned int n_slabs, cudaStream_t st);
 
 // desc = { 0, *d_total, 0 } (the chunk table of ONE contiguous range) and counters[3] += *d_total, all on the stream
 int make_single_chunk(const unsigned long long *d_total, unsigned long long *d_desc, unsigned long long *d_counters, cudaStream_t st);

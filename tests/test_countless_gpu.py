@@ -1,5 +1,5 @@
 """The single-pass bucket pass (per-(bucket, CTA) slabs instead of a count pass, csrc/partition.cu
-bucket_slabs_kernel; the default for large batches, with the clear of a new table fused into the insert) against the oracle, forced onto small inputs, and its
+part_scatter_kernel<..., SLABS>; the default for large batches) against the oracle, forced onto small inputs, and its
 corner cases: slab overflow, the overflow list of the chunked host insert, ragged streams, super-k-mer records."""
 import os
 
@@ -129,8 +129,7 @@ def test_superkmer_records_insert_like_the_reads(gpu, k, P):
     ok, ov = om.export_sorted()
     d = torch.zeros(recs.size + 16, dtype=torch.uint8, device="cuda")
     d[:recs.size].copy_(torch.from_numpy(np.ascontiguousarray(recs).reshape(-1)))
-    for env in (dict(insert_path=1), dict(insert_path=2, single_pass=0), dict(insert_path=2, single_pass=1, single_pass_min=1),
-                dict(insert_path=2, single_pass=1, single_pass_min=1, lazy_clear=0)):
+    for env in (dict(insert_path=1), dict(insert_path=2, single_pass=0), dict(insert_path=2, single_pass=1, single_pass_min=1)):
         with capi.tuned(**env):
             gm = ArrayDNAMap(k, 1 << 22)
             assert gm.insert_records_device(d.data_ptr(), recs.size, 16, recs.shape[0], 52) == w

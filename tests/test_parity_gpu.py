@@ -12,16 +12,14 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["direct", "partitioned", "single-pass", "single-pass-cleared-first"])
+@pytest.fixture(params=["direct", "partitioned", "single-pass"])
 def insert_path(request):
     """Every insert path against the oracle.  Small tables take the direct kernel by default; the L2-blocked path (the one
     bench.py times and every BASELINE config takes) is forced here, once with the counted bucket pass (part_count +
-    part_scatter: also what the sharded map runs) and with the single-pass one (bucket_slabs_kernel, the default for large
-    batches) -- there once with the clear of the new table fused into the insert (slice-wise initialisation, bounded probing,
-    overflow list: the default) and once on a table cleared beforehand."""
+    part_scatter: also what the sharded map runs) and once with the single-pass one (part_scatter<SLABS>, the default for
+    large batches), both followed by insert_keys_kernel."""
     kw = {"direct": dict(insert_path=1), "partitioned": dict(insert_path=2, single_pass=0),
-          "single-pass": dict(insert_path=2, single_pass=1, single_pass_min=1),
-          "single-pass-cleared-first": dict(insert_path=2, single_pass=1, single_pass_min=1, lazy_clear=0)}[request.param]
+          "single-pass": dict(insert_path=2, single_pass=1, single_pass_min=1)}[request.param]
     with capi.tuned(**kw):
         yield request.param
 
