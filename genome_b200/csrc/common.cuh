@@ -49,6 +49,8 @@ struct Tuning {
                                         // ncclSend/ncclRecv, 2 = local bucket pass + copy-engine pushes into the inboxes
     long long wire_superkmer = 0;       // sharded maps created from now on: minimizer owners, 16-byte super-k-mer records on the wire
     long long pgraph_sharded = 0;       // Graph.buildGraph over shards without a replica (sgraph.cuh)
+    long long count_cap_x10 = 30;       // slots per expected key (x 10) of a counting table (gb_map_create / gb_map_clear); the table
+                                        // deleteAll leaves behind always gets 3 (Graph.buildGraph's membership probes want load <= 1/3)
     long long trace = 0;                // phase timings on stderr
     long long exp = 0;                  // A/B bits of the experiment in progress (0 in production; see scripts/r2_insert_sweep.py)
 };
@@ -461,11 +463,11 @@ int map_swap_table(Map *m, unsigned long long new_cap, void **old_table, unsigne
 void map_retire_table(Map *m, void *t, unsigned long long alloc_cap);
 int map_stage(Map *m, size_t n_u64);
 int pool_setup(int device);
-inline unsigned long long cap_for(int64_t keys)
+inline unsigned long long cap_for(int64_t keys, long long slots_per_key_x10 = 30)
 {
-    // load <= 1/3 at `keys`, a multiple of 1024 slots, at least 1024
+    // load <= 1/3 at `keys` by default, a multiple of 1024 slots, at least 1024
     // measured on C2: load 0.22 -> 0.37 costs 10% in the upsert and 60% in the graph build's membership probes
-    unsigned long long c = ((unsigned long long)(keys > 0 ? keys : 0) * 3 + 1023) / 1024 * 1024;
+    unsigned long long c = (((unsigned long long)(keys > 0 ? keys : 0) * (unsigned long long)slots_per_key_x10 + 9) / 10 + 1023) / 1024 * 1024;
     return c < 1024 ? 1024 : c;
 }
 

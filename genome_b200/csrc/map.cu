@@ -669,6 +669,7 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
     m->kept_valid = false;
     int64_t done = 0;
     int64_t total_ns = 0;
+    unsigned long long before[4] = { 0, 0, 0, 0 };
     m->phase_ns[0] = m->phase_ns[1] = m->phase_ns[2] = 0;
     while (done < n_reads) {
         // how many reads fit the budget (whole tiles)
@@ -691,8 +692,9 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
             take = std::max<int64_t>(TILE_READS, take / TILE_READS * TILE_READS);
             take = std::min(take, left);
         }
-        unsigned long long before[4], after[4];
-        GB_TRY(map_read_counters(m, before));
+        // the counters were zeroed above and only this call advances them: what they held before this batch is known on the host,
+        // and the batch's work is queued behind whatever the stream is still doing (the clear) without a synchronisation
+        unsigned long long after[4];
         const int64_t take_windows = fixed ? take * win_per_read_max
                                            : (h_win_prefix ? h_win_prefix[done + take] - h_win_prefix[done] : take * win_per_read_max);
         const int mode = insert_mode();
@@ -722,6 +724,7 @@ static int insert_device(Map *m, const uint8_t *d_bin, size_t n_bytes, const uns
         GB_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
         total_ns += (int64_t)(ms * 1e6);
         m->size += (int64_t)(after[0] - before[0]);
+        before[0] = after[0];
         done += take;
     }
     unsigned long long c[4];
@@ -942,7 +945,7 @@ int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_ma
     m->k = k;
     m->device = device;
     m->v210 = (flags & GB_FLAG_HASH_SCALA_210) != 0;
-    const unsigned long long cap0 = cap_for(min_capacity);
+    const unsigned long long cap0 = cap_for(min_capacity, g_tune.count_cap_x10);
     int r = GB_OK;
     do {
         if ((r = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
@@ -1267,7 +1270,7 @@ int gb_map_clear(gb_map *h, int64_t min_capacity)
     Map *m;
     GB_TRY(check_map(h, &m));
     if (min_capacity < 0) { set_error("negative capacity"); return GB_E_ARG; }
-    unsigned long long nb = cap_for(min_capacity);
+    unsigned long long nb = cap_for(min_capacity, g_tune.count_cap_x10);
     if (nb != m->cap) {
         void *old = nullptr;
         unsigned long long old_alloc = 0;
@@ -1288,7 +1291,7 @@ long long gb_launch_count(void) { return g_launches.load(std::memory_order_relax
 static long long *tune_field(const char *name)
 {
     static const struct { const char *name; long long Tuning::*field; } table[] = {
-        { "insert_path", &Tuning::insert_path }, { "single_pass", &Tuning::single_pass }, { "single_pass_min", &Tuning::single_pass_min },
+        { "count_cap_x10", &Tuning::count_cap_x10 }, { "insert_path", &Tuning::insert_path }, { "single_pass", &Tuning::single_pass }, { "single_pass_min", &Tuning::single_pass_min },
         { "slice_bits", &Tuning::slice_bits }, { "batches", &Tuning::batches }, { "h2d_chunks", &Tuning::h2d_chunks },
         { "route", &Tuning::route }, { "a2a", &Tuning::a2a },
         { "wire_superkmer", &Tuning::wire_superkmer }, { "pgraph_sharded", &Tuning::pgraph_sharded }, { "trace", &Tuning::trace }, { "exp", &Tuning::exp },

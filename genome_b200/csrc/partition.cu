@@ -296,27 +296,33 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
 //     match.any;
 //   * three CTA barriers per round instead of six: warp 0 alone turns the per-warp counts into positions (prefix over the warps,
 //     scan over the buckets, slab cursors) between two of them;
-//   * no per-key destination array: the round is flushed run by run (a warp copies a bucket's run to the slab cursor), so the
-//     slab bound is checked once per run and a key costs one shared load and one global store.
+//   * the staging position of a key and its destination differ by a per-bucket constant that warp 0 leaves in shared memory, so
+//     the flush is a flat loop -- consecutive threads store consecutive staged keys -- with no per-bucket bookkeeping (a run-wise
+//     flush, one warp per bucket run, cost 39 instructions per key at 64 keys per run: profiles/r2j).
 // LPB = log2(buckets) at compile time (the ballots and the shared-memory indexing unroll), -1 = run time (any nb <= 128).
 template <bool FIXED, bool V210, int LPB>
-__global__ void __launch_bounds__(INSERT_THREADS, 4)
+__global__ void __launch_bounds__(INSERT_THREADS, 4) // measured r2j: 5 / 6 CTAs per SM (51 / 42 registers, spills): 0.618 / 0.641 against 0.594 ms
 bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, unsigned long long *out, SlabOut so)
 {
     __shared__ ReadTile tile;
     extern __shared__ unsigned int s_dyn[];
-    // layout: rcnt [WARPS][nb] | bstart [nb + 1] | dbase [nb] | bcur [nb] | (pad) | skey [ROUND_KEYS] u64
+    // layout: rcnt [WARPS][nb] | delta [nb] | lim [nb] | bcur [nb] | total [1] | sdst [ROUND_KEYS] | (pad) | skey [ROUND_KEYS] u64
     const int lp_bits = LPB >= 0 ? LPB : lp_bits_rt;
     const unsigned int nb = LPB >= 0 ? (1u << (LPB >= 0 ? LPB : 0)) : nb_rt;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned int *rcnt_all = s_dyn;
     unsigned int *rcnt = rcnt_all + (size_t)warp * nb;
-    unsigned int *bstart = s_dyn + (size_t)WARPS * nb;
-    unsigned int *dbase = bstart + nb + 1;
-    unsigned int *bcur = dbase + nb;
-    unsigned long long *skey = reinterpret_cast<unsigned long long *>(s_dyn + (((size_t)(WARPS + 3) * nb + 1 + 1) & ~(size_t)1));
+    unsigned int *delta = s_dyn + (size_t)WARPS * nb; // destination - staging position, per bucket and round
+    unsigned int *lim = delta + nb;                   // end of this CTA's slab of the bucket
+    unsigned int *bcur = lim + nb;
+    unsigned int *total = bcur + nb;
+    unsigned int *sdst = total + 1;
+    unsigned long long *skey = reinterpret_cast<unsigned long long *>(s_dyn + (((size_t)(WARPS + 3) * nb + 1 + ROUND_KEYS + 1) & ~(size_t)1));
     const unsigned int slab = so.slab, grid = gridDim.x, cta = blockIdx.x;
-    for (unsigned int b = tid; b < nb; b += INSERT_THREADS) bcur[b] = (b * grid + cta) * slab + so.count[(size_t)b * grid + cta]; // < 2^32: checked by the host
+    for (unsigned int b = tid; b < nb; b += INSERT_THREADS) {
+        bcur[b] = (b * grid + cta) * slab + so.count[(size_t)b * grid + cta]; // < 2^32: checked by the host
+        lim[b] = (b * grid + cta + 1) * slab;
+    }
     const unsigned int lt = (1u << lane) - 1;
     __syncthreads();
     const long long n_tiles = (rb.n_reads + TILE_READS - 1) / TILE_READS;
@@ -386,38 +392,40 @@ bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, uns
                     }
                     if (b < nb) {
                         const unsigned int st = carry + incl - tot;
-                        bstart[b] = st;
 #pragma unroll
                         for (int w = 0; w < WARPS; w++) rcnt_all[(size_t)w * nb + b] = st + pre[w]; // where warp w's keys of b start in the staging area
-                        const unsigned int cur = bcur[b], hi = (b * grid + cta + 1) * slab;
-                        dbase[b] = cur;
-                        bcur[b] = min(cur + tot, hi); // a full slab stays full: no 32-bit wrap
+                        const unsigned int cur = bcur[b];
+                        delta[b] = cur - st;
+                        bcur[b] = min(cur + tot, lim[b]); // a full slab stays full: no 32-bit wrap
                     }
                     carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
                 }
-                if (lane == 0) bstart[nb] = carry;
+                if (lane == 0) *total = carry;
             }
             __syncthreads(); // (B)
 #pragma unroll
             for (int j = 0; j < SEG; j++)
-                if (j < cnt) skey[rcnt[bk[j]] + rk[j]] = key[j];
+                if (j < cnt) {
+                    const unsigned int at = rcnt[bk[j]] + rk[j], dst = at + delta[bk[j]];
+                    skey[at] = key[j];
+                    sdst[at] = dst < lim[bk[j]] ? dst : 0xFFFFFFFFu; // beyond the slab
+                }
             __syncthreads(); // (C) the round is staged, sorted by bucket
-            for (unsigned int b = warp; b < nb; b += WARPS) {
-                const unsigned int s0 = bstart[b], n = bstart[b + 1] - s0, pos = dbase[b];
-                const unsigned int room = (b * grid + cta + 1) * slab - pos, fit = min(n, room);
-                const unsigned long long *sp = skey + s0 + lane;
-                unsigned long long *gp = out + pos + lane;
-                for (unsigned int i = lane; i < fit; i += 32, sp += 32, gp += 32) *gp = *sp;
-                for (unsigned int i = fit + lane; i < n; i += 32) { // beyond the slab (pathological inputs only)
-                    const unsigned long long key1 = skey[s0 + i];
-                    if (so.ovf) { // LIST mode
-                        const unsigned long long at = atomicAdd(so.overflowed, 1ull);
-                        if (at < so.ovf_cap) so.ovf[at] = key1; else *so.failed = 1u;
-                    } else { // upserted right here, random access
-                        const unsigned long long i1 = slot_of(mix64(key1), so.table.cap);
-                        if (upsert_add(so.table, i1, load_key(so.table, i1), key1, 1)) atomicAdd(&so.spread[cta & (SPREAD - 1)], 1ull);
-                        atomicAdd(so.overflowed, 1ull);
-                    }
+            const unsigned int round_total = *total;
+#pragma unroll
+            for (int i = 0; i < SEG; i++) {
+                const unsigned int at = (unsigned int)i * INSERT_THREADS + tid;
+                if (at >= round_total) break;
+                const unsigned int dst = sdst[at];
+                const unsigned long long key1 = skey[at];
+                if (dst != 0xFFFFFFFFu) { out[dst] = key1; continue; }
+                if (so.ovf) { // beyond the slab (pathological inputs only), LIST mode
+                    const unsigned long long pos = atomicAdd(so.overflowed, 1ull);
+                    if (pos < so.ovf_cap) so.ovf[pos] = key1; else *so.failed = 1u;
+                } else { // upserted right here, random access
+                    const unsigned long long i1 = slot_of(mix64(key1), so.table.cap);
+                    if (upsert_add(so.table, i1, load_key(so.table, i1), key1, 1)) atomicAdd(&so.spread[cta & (SPREAD - 1)], 1ull);
+                    atomicAdd(so.overflowed, 1ull);
                 }
             }
             // no barrier here: the next round touches only warp-private counters before its barrier (A)
@@ -447,11 +455,11 @@ static void launch_bucket_slabs(int grid, size_t smem, cudaStream_t st, const Re
 #undef GB_BS
 }
 
-static size_t slabs_smem(unsigned int nb) { return ((((size_t)(WARPS + 3) * nb + 2) & ~(size_t)1) + 2) * 4 + (size_t)ROUND_KEYS * 8; }
+static size_t slabs_smem(unsigned int nb) { return ((((size_t)(WARPS + 3) * nb + 1 + ROUND_KEYS + 1) & ~(size_t)1) + 2) * 4 + (size_t)ROUND_KEYS * 8; }
 
 // ---------------------------------------------------------------- bulk upsert from key ranges
 constexpr int IK_THREADS = 256;
-constexpr int IK_PER_THREAD = 4; // measured 2 / 4 / 8 / 16 keys per thread: 1.78 / 1.80 / 2.07 / 3.70 ms on C2
+constexpr int IK_PER_THREAD = 3; // 3 keys per thread in 32 registers = 8 CTAs per SM: the measurements are at insert_slabs_kernel below
 
 // No CTA barrier anywhere: every thread finds its own chunk, every warp adds its new-key count to one of SPREAD
 // global counters (fold_new_keys_kernel sums them into counters[0] afterwards).
@@ -459,8 +467,9 @@ constexpr int IK_PER_THREAD = 4; // measured 2 / 4 / 8 / 16 keys per thread: 1.7
 // by one 128-bit compare-and-swap (1.865 ms against 1.834 ms), CAS-first probing, 2 / 8 / 16 keys per thread, prefetching the
 // next table slice into L2 while the current one is filled (2.22 against 2.15 ms).
 // DEV_TOTAL: n_total is only an upper bound (it sized the grid); the exact number of keys is vstart[n_chunks].
-template <bool DEV_TOTAL>
-__global__ void __launch_bounds__(IK_THREADS)
+// Slot indices are 32-bit (IdxT) whenever the table has fewer than 2^32 slots.
+template <bool DEV_TOTAL, typename IdxT>
+__global__ void __launch_bounds__(IK_THREADS, 8)
 insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ vstart,
                    const unsigned long long *__restrict__ off, int n_chunks, unsigned long long n_total, Table table, unsigned long long *spread)
 {
@@ -480,7 +489,8 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
         }
         c = lo;
     }
-    unsigned long long key[IK_PER_THREAD], idx[IK_PER_THREAD], cur[IK_PER_THREAD];
+    unsigned long long key[IK_PER_THREAD], cur[IK_PER_THREAD];
+    IdxT idx[IK_PER_THREAD];
     bool ok[IK_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < IK_PER_THREAD; j++) {
@@ -489,7 +499,7 @@ insert_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned l
         if (ok[j]) {
             while (v >= vstart[c + 1]) c++; // chunks ascend with v; empty chunks are skipped
             key[j] = __ldcs(keys + off[c] + (v - vstart[c]));
-            idx[j] = slot_of(mix64(key[j]), cap);
+            idx[j] = (IdxT)slot_of(mix64(key[j]), cap);
         }
     }
     int nk = 0;
@@ -534,34 +544,35 @@ fold_new_keys_kernel(unsigned long long *spread, unsigned long long *counters)
 }
 
 // The same upsert over the SLABS of the single-pass bucket pass: slab number s = (bucket, CTA of the bucket pass) holds count[s]
-// keys at keys[s * slab], and CTA (s, part) takes keys [part * 1024, ...) of it.  The launch is sized for full slabs; a CTA
+// keys at keys[s * slab], and CTA (s, part) takes keys [part * 768, ...) of it.  The launch is sized for full slabs; a CTA
 // whose part lies beyond count[s] leaves at once.  No chunk table, no search: measured on C2 the search over the 19 k-entry
 // chunk table cost the generic kernel 0.2 ms (2.15 against 1.95 ms).  Slabs are bucket-major, so slice order is kept.
 // The kernel is latency bound (ncu r2c: 29 long-scoreboard stall cycles per issue): three dependent round trips per key -- staged
-// key, table key, compare-and-swap -- so the register allocation is held to 6 CTAs per SM (measured r2d: 1.76 -> 1.62 ms on C2;
-// 8 CTAs per SM spill and give 1.65).  Measured and dropped (profiles/r2d_upsert_variants.jsonl, r2g_upsert_ablation.jsonl): the
+// key, table key, compare-and-swap -- so it runs at full occupancy: 3 keys per thread in 32 registers, 8 CTAs per SM (measured
+// r2i, keys per thread x CTAs per SM on C2: 4 x 6 1.326 ms, 3 x 8 1.303, 2 x 8 1.356, 4 x 8 (spills) 1.458, 6 x 5 1.531).  Measured and dropped (profiles/r2d_upsert_variants.jsonl, r2g_upsert_ablation.jsonl): the
 // compare-and-swap as the probe (no preceding load): 1.73 ms; a persistent grid fetching the next item's keys early: 9 ms -- the
 // CTAs drift apart and the slice being filled no longer stays in L2; the clear fused into the insert (slice-wise initialisation
 // right before a slice is filled, bounded probing, overflow list): 2.39 ms against 0.23 + 1.52 -- lines that are already in L2 do
 // not make the upsert faster, its bound is the L2's handling of the requests, not DRAM.  What the parts cost on C2: staged keys +
 // hashing 0.20 ms, + table key loads 0.47, + one red per key 0.87, + compare-and-swap of the 31 % new keys 1.52.
 // Slot indices are 32-bit (IdxT) whenever the table has fewer than 2^32 slots.
+constexpr int IS_PER_THREAD = 3;
 template <typename IdxT>
-__global__ void __launch_bounds__(IK_THREADS, 6)
+__global__ void __launch_bounds__(IK_THREADS, 8)
 insert_slabs_kernel(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ count, unsigned int slab,
                     unsigned int ctas_per_slab, Table table, unsigned long long *spread)
 {
-    constexpr int IK_PER_CTA = IK_THREADS * IK_PER_THREAD;
+    constexpr int IK_PER_CTA = IK_THREADS * IS_PER_THREAD;
     const unsigned long long cap = table.cap;
     const unsigned int s = blockIdx.x / ctas_per_slab, part = blockIdx.x - s * ctas_per_slab;
     const unsigned int n = min(count[s], slab), v0 = part * IK_PER_CTA;
     if (v0 >= n) return;
     const unsigned long long *src = keys + (size_t)s * slab + v0;
-    unsigned long long key[IK_PER_THREAD], cur[IK_PER_THREAD], old[IK_PER_THREAD];
-    IdxT idx[IK_PER_THREAD];
-    bool ok[IK_PER_THREAD];
+    unsigned long long key[IS_PER_THREAD], cur[IS_PER_THREAD], old[IS_PER_THREAD];
+    IdxT idx[IS_PER_THREAD];
+    bool ok[IS_PER_THREAD];
 #pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++) {
+    for (int j = 0; j < IS_PER_THREAD; j++) {
         const unsigned int i = (unsigned int)j * IK_THREADS + threadIdx.x;
         ok[j] = v0 + i < n;
         if (ok[j]) {
@@ -570,17 +581,17 @@ insert_slabs_kernel(const unsigned long long *__restrict__ keys, const unsigned 
         }
     }
 #pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++)
+    for (int j = 0; j < IS_PER_THREAD; j++)
         if (ok[j]) cur[j] = load_key(table, idx[j]);
     // the CAS round trips of a thread's keys overlap: all of them are issued before the first result is used
 #pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++) {
+    for (int j = 0; j < IS_PER_THREAD; j++) {
         old[j] = cur[j];
         if (ok[j] && cur[j] == EMPTY_KEY) old[j] = atomicCAS(table.key + idx[j], EMPTY_KEY, key[j]);
     }
     int nk = 0;
 #pragma unroll
-    for (int j = 0; j < IK_PER_THREAD; j++) {
+    for (int j = 0; j < IS_PER_THREAD; j++) {
         if (!ok[j]) continue;
         const bool claimed = cur[j] == EMPTY_KEY && old[j] == EMPTY_KEY;
         if (claimed) {
@@ -837,7 +848,7 @@ int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d
         GB_CUDA(cudaMalloc((void **)&m->d_spread, SPREAD * 8));
         GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));
     }
-    const unsigned int per = (slab + IK_THREADS * IK_PER_THREAD - 1) / (IK_THREADS * IK_PER_THREAD);
+    const unsigned int per = (slab + IK_THREADS * IS_PER_THREAD - 1) / (IK_THREADS * IS_PER_THREAD);
     const unsigned long long work = (unsigned long long)n_slabs * per;
     if (work >= 0x7FFFFFFFull) { set_error("internal: %llu slab CTAs", work); return GB_E_ARG; }
     const Table t = m->view();
@@ -859,10 +870,11 @@ int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned l
         GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));
     }
     const unsigned int grid = (unsigned int)((n_total + IK_THREADS * IK_PER_THREAD - 1) / (IK_THREADS * IK_PER_THREAD));
-    if (total_is_upper_bound)
-        insert_keys_kernel<true><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->view(), m->d_spread);
-    else
-        insert_keys_kernel<false><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, m->view(), m->d_spread);
+    const Table t = m->view();
+#define GB_IK(D, I) insert_keys_kernel<D, I><<<grid, IK_THREADS, 0, st>>>(d_keys, d_vstart, d_off, n_chunks, n_total, t, m->d_spread)
+    if (t.cap < (1ull << 32)) { if (total_is_upper_bound) GB_IK(true, unsigned int); else GB_IK(false, unsigned int); }
+    else { if (total_is_upper_bound) GB_IK(true, unsigned long long); else GB_IK(false, unsigned long long); }
+#undef GB_IK
     GB_LAUNCHED();
     fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
     GB_LAUNCHED();
