@@ -545,6 +545,156 @@ static int drain(Map *m, BatchBufs *bufs)
     return GB_OK;
 }
 
+// The keys of an overflow list (rare: a bucket far above its share inside one CTA's tiles) get to their owners by the staged route:
+// owner-major split of the list, counts and keys through NCCL, plain chunk upsert.  Collective: every rank calls it for the batch
+// (with an empty list if it has none).
+static int route_key_list(Map *m, Comm *c, BatchBufs &B, const unsigned long long *d_list, unsigned long long n_local, int64_t *received)
+{
+    const int P = c->n_ranks;
+    PartLayout po;
+    po.owners = P;
+    po.lp_bits = 0;
+    unsigned long long *d_desc = B.d_tot + 3 * MAX_BUCKETS; // { vstart[0], vstart[1], off[0] } of my list | the same for what I receive
+    unsigned long long h_desc[3] = { 0, n_local, 0 };
+    GB_CUDA(cudaMemcpyAsync(d_desc, h_desc, 24, cudaMemcpyHostToDevice, c->stream));
+    GB_TRY(B.ensure(0, (size_t)n_local));
+    KeySource ks;
+    ks.keys = d_list; ks.vstart = d_desc; ks.off = d_desc + 2; ks.n_chunks = 1; ks.n_total = n_local;
+    GB_TRY(part_count_keys(ks, po, B.work2, c->stream));
+    GB_TRY(part_scatter_keys(ks, po, B.work2, B.recv, c->stream));
+    unsigned long long scnt[MAX_RANKS], rcnt[MAX_RANKS], soff[MAX_RANKS], roff[MAX_RANKS];
+    GB_TRY(comm_scratch(c));
+    GB_TRY(exchange_counts(c, B.work2.bucket_total, c->d_scratch + 1536, scnt, rcnt)); // synchronises the communicator's stream
+    unsigned long long st = 0, rt = 0;
+    for (int p = 0; p < P; p++) { soff[p] = st; st += scnt[p]; roff[p] = rt; rt += rcnt[p]; }
+    DeviceBuf d_in;
+    GB_TRY(d_in.alloc((size_t)(rt + 1) * 8));
+    GB_TRY(all_to_all_v(c, B.recv, soff, scnt, (unsigned long long *)d_in.p, roff, rcnt, ncclUint64));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    if (rt) {
+        int64_t budget = 0;
+        GB_CUDA(cudaStreamSynchronize(m->stream));
+        unsigned long long cn[4];
+        GB_TRY(map_read_counters(m, cn));
+        m->size += (int64_t)cn[0];
+        GB_TRY(map_zero_counters(m));
+        GB_TRY(map_budget(m, (int64_t)rt, &budget));
+        while (budget < (int64_t)rt) {
+            GB_TRY(map_rebuild(m, m->cap * 2, false, 0));
+            budget = (int64_t)(m->cap * 0.9) - m->size;
+        }
+        unsigned long long h_desc2[3] = { 0, rt, 0 };
+        GB_CUDA(cudaMemcpyAsync(d_desc + 4, h_desc2, 24, cudaMemcpyHostToDevice, m->stream));
+        GB_TRY(insert_key_chunks(m, (const unsigned long long *)d_in.p, d_desc + 4, d_desc + 6, 1, rt, m->stream));
+        GB_CUDA(cudaStreamSynchronize(m->stream)); // d_in goes away
+    }
+    *received = (int64_t)rt;
+    return GB_OK;
+}
+
+// Sharded FreqFilter.add, single-pass form (fixed-stride streams, one routing level, peer-mapped inboxes): NO count pass and no
+// per-bucket counts on the host.  Per batch, on the communicator's stream: bucket_slabs_kernel<PEER> stores every canonical k-mer
+// into a slab of its owner's inbox (slab = (source rank, table slice, CTA), sized for the CTA's share + 8 sigma) and leaves the
+// slabs' fill counts beside them; one 8-byte-per-pair all-to-all follows the keys on the stream ("whoever has my total has my
+// keys") and tells the owner how many keys arrived, which is all the host needs (room in the table).  On the map's stream the
+// owner upserts the slabs slice-major.  The next batch's bucket pass is queued before the host waits for this batch's totals.
+static int pmap_insert_slabs(Map *m, const uint8_t *d_bin, size_t n_bytes, unsigned int rec, int64_t win_max, int64_t n_reads, int64_t batch_reads,
+                             int64_t batches, const PartLayout &pl, unsigned int slab, int64_t *n_windows)
+{
+    Comm *c = m->comm;
+    const int P = c->n_ranks, k = m->k, LP = 1 << pl.lp_bits;
+    BatchBufs *bufs = c->bufs;
+    for (int i = 0; i < NSETS; i++) GB_TRY(bufs[i].work.ensure(c->stream));
+    const unsigned int G = (unsigned int)bufs[0].work.grid;
+    const unsigned long long cnt_off = (unsigned long long)LP * G * slab;
+    const bool trace = g_tune.trace && c->rank == 0;
+    auto now_ms = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    const double t_begin = now_ms();
+    if (trace) fprintf(stderr, "[pmap] single-pass: %lld reads, %lld batches of %lld, %d slices, slab %u keys, region %llu keys\n", (long long)n_reads,
+                       (long long)batches, (long long)batch_reads, LP, slab, (unsigned long long)c->region_cap);
+    GB_TRY(map_zero_counters(m));
+    GB_CUDA(cudaStreamSynchronize(m->stream));
+    GB_CUDA(cudaEventRecord(m->ev0, m->stream));
+    int64_t windows = 0, pending_upper = 0;
+    // d_tot / h_tot: [0, P) keys I put into owner o's slabs | [P, 2P) keys source s put into mine | [2P] overflow cursor | [2P + 1] its
+    // "did not fit" flag | [2P + 2] overflow keys on all ranks
+    auto stage_a = [&](int64_t b) -> int {
+        BatchBufs &B = bufs[b % NSETS];
+        if (b >= 2 && bufs[(b - 2) % NSETS].in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, bufs[(b - 2) % NSETS].inserted, 0));
+        if (B.in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, B.inserted, 0));
+        const int64_t r0 = std::min(n_reads, b * batch_reads), r1 = std::min(n_reads, r0 + batch_reads), nr = r1 - r0;
+        GB_TRY(B.ensure((size_t)(nr * win_max) + 8, 0)); // the overflow list can take the whole batch
+        GB_CUDA(cudaMemsetAsync(B.d_tot, 0, (size_t)(2 * P + 4) * 8, c->stream));
+        PeerSlabs ps;
+        memset(&ps, 0, sizeof ps);
+        for (int o = 0; o < P; o++) {
+            ps.keys[o] = c->peer_inbox[b % NSETS][o] + (size_t)c->rank * c->region_cap;
+            ps.cnt[o] = reinterpret_cast<unsigned int *>(ps.keys[o] + cnt_off);
+        }
+        ps.owner_total = B.d_tot;
+        ps.owners = (unsigned int)P;
+        ReadBatch rb;
+        rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = nullptr; rb.rec_bytes = rec; rb.read0 = r0; rb.n_reads = nr;
+        GB_TRY(bucket_slabs_peers(rb, k, m->v210, pl, B.work, slab, ps, B.send, B.send_cap, B.d_tot + 2 * P, reinterpret_cast<unsigned int *>(B.d_tot + 2 * P + 1),
+                                  c->stream));
+        GB_TRY(all_to_all_rows(c, B.d_tot, B.d_tot + P, 1)); // the totals travel AFTER the keys on my stream
+        GB_NCCL(ncclAllReduce(B.d_tot + 2 * P, B.d_tot + 2 * P + 2, 1, ncclUint64, ncclSum, c->nccl, c->stream));
+        GB_CUDA(cudaMemcpyAsync(B.h_tot, B.d_tot, (size_t)(2 * P + 4) * 8, cudaMemcpyDeviceToHost, c->stream));
+        GB_CUDA(cudaEventRecord(B.exchanged, c->stream));
+        return GB_OK;
+    };
+    auto stage_b = [&](int64_t b) -> int {
+        BatchBufs &B = bufs[b % NSETS];
+        GB_CUDA(cudaEventSynchronize(B.exchanged));
+        unsigned long long sent = 0, rt = 0;
+        for (int p = 0; p < P; p++) { sent += B.h_tot[p]; rt += B.h_tot[P + p]; }
+        const unsigned long long ovf_mine = B.h_tot[2 * P], ovf_all = B.h_tot[2 * P + 2];
+        if ((unsigned int)B.h_tot[2 * P + 1]) { set_error("internal: the overflow list of a sharded batch did not hold its keys"); return GB_E_INVARIANT; }
+        windows += (int64_t)(sent + ovf_mine);
+        // room for the received keys (every one may be new); grow only with the pipeline drained
+        int64_t cap = (int64_t)m->cap;
+        if ((int64_t)(cap * 0.9) - m->size - pending_upper < (int64_t)rt || (m->size + pending_upper) * 10 > cap * 7) {
+            GB_TRY(drain(m, bufs));
+            pending_upper = 0;
+            int64_t budget = 0;
+            GB_TRY(map_budget(m, (int64_t)rt, &budget));
+            while (budget < (int64_t)rt) {
+                GB_TRY(map_rebuild(m, m->cap * 2, false, 0));
+                budget = (int64_t)(m->cap * 0.9) - m->size;
+            }
+        }
+        GB_CUDA(cudaStreamWaitEvent(m->stream, B.exchanged, 0));
+        InboxSlabs in;
+        in.sources = (unsigned int)P; in.slices = (unsigned int)LP; in.grid = G; in.region_cap = c->region_cap; in.cnt_off = cnt_off;
+        GB_TRY(insert_inbox_slabs(m, c->inbox[b % NSETS], in, slab, m->stream));
+        GB_CUDA(cudaEventRecord(B.inserted, m->stream));
+        B.in_flight = true;
+        pending_upper += (int64_t)rt;
+        if (ovf_all) { // some rank's slabs overflowed in this batch: all ranks route their lists (drains the pipeline; pathological inputs only)
+            int64_t got = 0;
+            GB_TRY(route_key_list(m, c, B, B.send, ovf_mine, &got));
+            pending_upper += got;
+        }
+        if (trace) fprintf(stderr, "[pmap] batch %lld: sent %llu (+ %llu overflowed), received %llu, enqueued at %.3f ms\n", (long long)b, sent, ovf_mine, rt, now_ms() - t_begin);
+        return GB_OK;
+    };
+    if (batches) GB_TRY(stage_a(0));
+    for (int64_t b = 0; b < batches; b++) {
+        if (b + 1 < batches) GB_TRY(stage_a(b + 1));
+        GB_TRY(stage_b(b));
+    }
+    GB_CUDA(cudaEventRecord(m->ev1, m->stream));
+    GB_TRY(drain(m, bufs));
+    GB_CUDA(cudaStreamSynchronize(c->stream));
+    if (trace) fprintf(stderr, "[pmap] drained %.3f ms\n", now_ms() - t_begin);
+    float ms = 0;
+    GB_CUDA(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+    m->last_insert_ns = (int64_t)(ms * 1e6);
+    m->windows += windows;
+    if (n_windows) *n_windows = windows;
+    return GB_OK;
+}
+
 // Sharded FreqFilter.add.  Per batch of reads, on the communicator's stream: bucket the canonical k-mers by
 // (owner shard, table slice) [partition.cu]; exchange the per-bucket counts; all-to-all the owner segments over
 // NVLink.  On the map's stream: upsert the received keys slice by slice (every source's sub-bucket of slice 0, then
@@ -602,8 +752,37 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
         tev.push_back(e);
     };
     BatchBufs *bufs = c->bufs;
+    // the single-pass form (pmap_insert_slabs) when every rank can take it: fixed-stride stream, one routing level, peer stores,
+    // batches large enough for slabs; its inbox regions hold slabs + their counts
+    const int64_t batch_windows = std::min<int64_t>(batch_reads, std::max<int64_t>(n_reads, 1)) * std::max<int64_t>(win_max, 1);
+    int64_t slab_keys_cta = 0, can_slabs = fixed && !two_level && g_tune.a2a == 0 && g_tune.single_pass && (int64_t)len0 >= k;
+    // its wire buckets may be as many as the staged pass handles (128): the runs it stores are 2048 / buckets keys, and the
+    // owner's upsert stays L2-blocked up to 8 GPUs (P = 8: 16 slices per shard; the 32-bucket limit of the counted pass below
+    // leaves 4 -- 480 MB slices on C2 -- which is why that one loses the L2 blocking as P grows)
+    PartLayout pls;
+    pls.owners = P;
+    {
+        int64_t lps = slice_bits_for(m->cap, P);
+        if (g_tune.slice_bits >= 0) lps = std::min<int64_t>(lps, g_tune.slice_bits);
+        GB_TRY(all_reduce_i64(c, &lps, ncclMin));
+        pls.lp_bits = (int)lps;
+    }
+    const int LPS = 1 << pls.lp_bits, NBS = pls.nb();
+    {
+        GB_TRY(bufs[0].work.ensure(c->stream));
+        slab_keys_cta = (int64_t)slab_cta_keys(std::min<int64_t>(batch_reads, n_reads), (unsigned long long)batch_windows, bufs[0].work.grid);
+        int64_t big_enough = batch_windows >= std::max<int64_t>(1, g_tune.single_pass_min) ? 1 : 0;
+        GB_TRY(all_reduce_i64(c, &big_enough, ncclMax)); // a rank with few (or no) reads follows the others
+        GB_TRY(all_reduce_i64(c, &can_slabs, ncclMin));
+        GB_TRY(all_reduce_i64(c, &slab_keys_cta, ncclMax));
+        can_slabs = can_slabs && big_enough;
+    }
+    unsigned int slab = can_slabs && NBS <= 128 ? slab_keys_for((unsigned long long)slab_keys_cta, (unsigned int)NBS, bufs[0].work.grid) : 0;
+    if (slab && (unsigned long long)LPS * bufs[0].work.grid * slab + (unsigned long long)LPS * bufs[0].work.grid / 2 + 8 >= (1ull << P2P_REL_BITS)) slab = 0;
+    const size_t region_need = slab ? (size_t)LPS * bufs[0].work.grid * slab + (size_t)LPS * bufs[0].work.grid / 2 + 8 : (size_t)batch_windows;
     // fused routing: every rank's bucket pass stores straight into the owners' inboxes over NVLink
-    GB_TRY(ensure_inboxes(c, (size_t)std::min<int64_t>(batch_reads, std::max<int64_t>(n_reads, 1)) * (size_t)std::max<int64_t>(win_max, 1)));
+    GB_TRY(ensure_inboxes(c, region_need));
+    if (slab && c->p2p == 1) return pmap_insert_slabs(m, d_bin, n_bytes, rec, win_max, n_reads, batch_reads, batches, pls, slab, n_windows);
     const bool p2p = c->p2p == 1;
     const bool dma = g_tune.a2a == 2; // local bucket pass + copy-engine pushes (0: the bucket pass stores into the peers' inboxes itself)
     if (trace) fprintf(stderr, "[pmap] routing: %s, %s (%d wire buckets, %d slices)\n", p2p ? (dma ? "local bucket pass + copy-engine pushes into NVLink inboxes" : "peer stores into NVLink inboxes") : "NCCL send/recv",

@@ -48,7 +48,7 @@ struct Tuning {
     long long a2a = 0;                  // sharded insert: 0 = the bucket pass stores into the peers' inboxes (NVLink stores), 1 = staged
                                         // ncclSend/ncclRecv, 2 = local bucket pass + copy-engine pushes into the inboxes
     long long wire_superkmer = 0;       // sharded maps created from now on: minimizer owners, 16-byte super-k-mer records on the wire
-    long long pgraph_sharded = 0;       // Graph.buildGraph over shards without a replica (sgraph.cuh)
+    long long pgraph_sharded = 1;       // Graph.buildGraph over shards without a replica (sgraph.cuh); 0 = all-gather the shards, build replicated
     long long count_cap_x10 = 30;       // slots per expected key (x 10) of a counting table (gb_map_create / gb_map_clear); the table
                                         // deleteAll leaves behind always gets 3 (Graph.buildGraph's membership probes want load <= 1/3)
     long long trace = 0;                // phase timings on stderr

@@ -160,6 +160,7 @@ struct SlabOut {
     unsigned int *failed = nullptr;
 };
 
+
 template <bool FIXED, bool V210, bool SRC_KEYS, bool PEER>
 __global__ void __launch_bounds__(INSERT_THREADS, 4)
 part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int lp_bits, unsigned int nb, const unsigned int *cta_off,
@@ -300,15 +301,18 @@ part_scatter_kernel(ReadBatch rb, KeySource ks, int k, unsigned int owners, int 
 //     the flush is a flat loop -- consecutive threads store consecutive staged keys -- with no per-bucket bookkeeping (a run-wise
 //     flush, one warp per bucket run, cost 39 instructions per key at 64 keys per run: profiles/r2j).
 // LPB = log2(buckets) at compile time (the ballots and the shared-memory indexing unroll), -1 = run time (any nb <= 128).
-template <bool FIXED, bool V210, int LPB>
+// PEER: sharded form (PeerSlabs); LPB then counts the bits of the whole bucket id (owner | slice), lp_bits_rt the slice bits.
+template <bool FIXED, bool V210, int LPB, bool PEER>
 __global__ void __launch_bounds__(INSERT_THREADS, 4) // measured r2j: 5 / 6 CTAs per SM (51 / 42 registers, spills): 0.618 / 0.641 against 0.594 ms
-bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, unsigned long long *out, SlabOut so)
+bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, unsigned long long *out, SlabOut so, PeerSlabs ps)
 {
     __shared__ ReadTile tile;
     extern __shared__ unsigned int s_dyn[];
     // layout: rcnt [WARPS][nb] | delta [nb] | lim [nb] | bcur [nb] | total [1] | sdst [ROUND_KEYS] | (pad) | skey [ROUND_KEYS] u64
-    const int lp_bits = LPB >= 0 ? LPB : lp_bits_rt;
-    const unsigned int nb = LPB >= 0 ? (1u << (LPB >= 0 ? LPB : 0)) : nb_rt;
+    const int lp_bits = LPB >= 0 && !PEER ? LPB : lp_bits_rt; // slice bits
+    const unsigned int nb = LPB >= 0 && !PEER ? (1u << (LPB >= 0 ? LPB : 0)) : nb_rt;
+    int id_bits = LPB >= 0 ? LPB : lp_bits; // bits of a bucket id: one ballot each
+    if (LPB < 0 && PEER) { id_bits = 0; while ((1u << id_bits) < nb) id_bits++; }
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned int *rcnt_all = s_dyn;
     unsigned int *rcnt = rcnt_all + (size_t)warp * nb;
@@ -320,8 +324,13 @@ bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, uns
     unsigned long long *skey = reinterpret_cast<unsigned long long *>(s_dyn + (((size_t)(WARPS + 3) * nb + 1 + ROUND_KEYS + 1) & ~(size_t)1));
     const unsigned int slab = so.slab, grid = gridDim.x, cta = blockIdx.x;
     for (unsigned int b = tid; b < nb; b += INSERT_THREADS) {
-        bcur[b] = (b * grid + cta) * slab + so.count[(size_t)b * grid + cta]; // < 2^32: checked by the host
-        lim[b] = (b * grid + cta + 1) * slab;
+        if (PEER) { // position = owner | index inside my region of the owner's inbox (slice-major slabs); a launch starts empty slabs
+            const unsigned int o = b >> lp_bits, l = b & ((1u << lp_bits) - 1);
+            bcur[b] = (o << P2P_REL_BITS) | ((l * grid + cta) * slab); // region < 2^P2P_REL_BITS keys: checked by the host
+        } else {
+            bcur[b] = (b * grid + cta) * slab + so.count[(size_t)b * grid + cta]; // < 2^32: checked by the host
+        }
+        lim[b] = (PEER ? bcur[b] : (b * grid + cta) * slab) + slab;
     }
     const unsigned int lt = (1u << lane) - 1;
     __syncthreads();
@@ -340,7 +349,13 @@ bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, uns
 #pragma unroll
             for (int j = 0; j < SEG; j++) {
                 const bool valid = j < cnt;
-                const unsigned int b = lp_bits ? (unsigned int)(mix64(key[j]) >> (64 - lp_bits)) : 0u;
+                unsigned int b;
+                if (PEER) {
+                    const unsigned long long h = mix64(key[j]);
+                    b = (owner_of(h, ps.owners) << lp_bits) | (lp_bits ? (unsigned int)(h >> (64 - lp_bits)) : 0u);
+                } else {
+                    b = lp_bits ? (unsigned int)(mix64(key[j]) >> (64 - lp_bits)) : 0u;
+                }
                 unsigned int peers = __ballot_sync(0xFFFFFFFFu, valid);
                 if (LPB >= 0) {
 #pragma unroll
@@ -350,7 +365,7 @@ bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, uns
                         peers &= one ? bal : ~bal;
                     }
                 } else {
-                    for (int bit = 0; bit < lp_bits; bit++) { // uniform trip count
+                    for (int bit = 0; bit < id_bits; bit++) { // uniform trip count
                         const bool one = (b >> bit) & 1u;
                         const unsigned int bal = __ballot_sync(0xFFFFFFFFu, one);
                         peers &= one ? bal : ~bal;
@@ -418,7 +433,11 @@ bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, uns
                 if (at >= round_total) break;
                 const unsigned int dst = sdst[at];
                 const unsigned long long key1 = skey[at];
-                if (dst != 0xFFFFFFFFu) { out[dst] = key1; continue; }
+                if (dst != 0xFFFFFFFFu) {
+                    if (PEER) ps.keys[dst >> P2P_REL_BITS][dst & ((1u << P2P_REL_BITS) - 1)] = key1;
+                    else out[dst] = key1;
+                    continue;
+                }
                 if (so.ovf) { // beyond the slab (pathological inputs only), LIST mode
                     const unsigned long long pos = atomicAdd(so.overflowed, 1ull);
                     if (pos < so.ovf_cap) so.ovf[pos] = key1; else *so.failed = 1u;
@@ -433,14 +452,24 @@ bucket_slabs_kernel(ReadBatch rb, int k, int lp_bits_rt, unsigned int nb_rt, uns
         __syncthreads(); // the tile is overwritten by the next stage_tile; skey / bstart by the next round
     }
     __syncthreads();
-    for (unsigned int b = tid; b < nb; b += INSERT_THREADS) so.count[(size_t)b * grid + cta] = min(bcur[b] - (b * grid + cta) * slab, slab);
+    for (unsigned int b = tid; b < nb; b += INSERT_THREADS) {
+        if (PEER) {
+            const unsigned int o = b >> lp_bits, l = b & ((1u << lp_bits) - 1), used = bcur[b] - (lim[b] - slab);
+            ps.cnt[o][l * grid + cta] = used;
+            if (used) atomicAdd(&ps.owner_total[o], (unsigned long long)used);
+        } else {
+            so.count[(size_t)b * grid + cta] = min(bcur[b] - (b * grid + cta) * slab, slab);
+        }
+    }
 }
 
 template <bool FIXED, bool V210>
 static void launch_bucket_slabs(int grid, size_t smem, cudaStream_t st, const ReadBatch &rb, int k, int lp_bits, unsigned int nb, unsigned long long *out,
                                 const SlabOut &so)
 {
-#define GB_BS(L) bucket_slabs_kernel<FIXED, V210, L><<<grid, INSERT_THREADS, smem, st>>>(rb, k, lp_bits, nb, out, so)
+    PeerSlabs none;
+    memset(&none, 0, sizeof none);
+#define GB_BS(L) bucket_slabs_kernel<FIXED, V210, L, false><<<grid, INSERT_THREADS, smem, st>>>(rb, k, lp_bits, nb, out, so, none)
     if (FIXED && !V210) { // the common stream shape gets the unrolled forms
         switch (nb == (1u << lp_bits) ? lp_bits : -1) {
         case 3: GB_BS(3); return;
@@ -557,17 +586,30 @@ fold_new_keys_kernel(unsigned long long *spread, unsigned long long *counters)
 // hashing 0.20 ms, + table key loads 0.47, + one red per key 0.87, + compare-and-swap of the 31 % new keys 1.52.
 // Slot indices are 32-bit (IdxT) whenever the table has fewer than 2^32 slots.
 constexpr int IS_PER_THREAD = 3;
-template <typename IdxT>
+// INBOX (sharded map): the slabs are the ones P source ranks stored into this rank's inbox (PeerSlabs); they are walked slice-major --
+// slab number s = ((slice * P + source) * grid + CTA) -- so that the resident CTAs still share one table slice.
+template <typename IdxT, bool INBOX>
 __global__ void __launch_bounds__(IK_THREADS, 8)
 insert_slabs_kernel(const unsigned long long *__restrict__ keys, const unsigned int *__restrict__ count, unsigned int slab,
-                    unsigned int ctas_per_slab, Table table, unsigned long long *spread)
+                    unsigned int ctas_per_slab, Table table, unsigned long long *spread, InboxSlabs in)
 {
     constexpr int IK_PER_CTA = IK_THREADS * IS_PER_THREAD;
     const unsigned long long cap = table.cap;
     const unsigned int s = blockIdx.x / ctas_per_slab, part = blockIdx.x - s * ctas_per_slab;
-    const unsigned int n = min(count[s], slab), v0 = part * IK_PER_CTA;
+    const unsigned long long *slab_keys;
+    unsigned int filled;
+    if (INBOX) {
+        const unsigned int cta = s % in.grid, ls = s / in.grid, src_rank = ls % in.sources, l = ls / in.sources;
+        const unsigned long long *region = keys + (size_t)src_rank * in.region_cap;
+        slab_keys = region + (size_t)(l * in.grid + cta) * slab;
+        filled = reinterpret_cast<const unsigned int *>(region + in.cnt_off)[l * in.grid + cta];
+    } else {
+        slab_keys = keys + (size_t)s * slab;
+        filled = count[s];
+    }
+    const unsigned int n = min(filled, slab), v0 = part * IK_PER_CTA;
     if (v0 >= n) return;
-    const unsigned long long *src = keys + (size_t)s * slab + v0;
+    const unsigned long long *src = slab_keys + v0;
     unsigned long long key[IS_PER_THREAD], cur[IS_PER_THREAD], old[IS_PER_THREAD];
     IdxT idx[IS_PER_THREAD];
     bool ok[IS_PER_THREAD];
@@ -852,10 +894,67 @@ int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d
     const unsigned long long work = (unsigned long long)n_slabs * per;
     if (work >= 0x7FFFFFFFull) { set_error("internal: %llu slab CTAs", work); return GB_E_ARG; }
     const Table t = m->view();
-    if (t.cap < (1ull << 32)) insert_slabs_kernel<unsigned int><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, t, m->d_spread);
-    else insert_slabs_kernel<unsigned long long><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, t, m->d_spread);
+    InboxSlabs none;
+    if (t.cap < (1ull << 32)) insert_slabs_kernel<unsigned int, false><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, t, m->d_spread, none);
+    else insert_slabs_kernel<unsigned long long, false><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_keys, d_count, slab, per, t, m->d_spread, none);
     GB_LAUNCHED();
     fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
+    GB_LAUNCHED();
+    return GB_OK;
+}
+
+// upsert of the slabs P source ranks stored into this rank's inbox (one buffer set), slice-major
+int insert_inbox_slabs(Map *m, const unsigned long long *d_inbox, const InboxSlabs &in, unsigned int slab, cudaStream_t st)
+{
+    if (!slab || !in.sources || !in.slices) return GB_OK;
+    m->kept_valid = false;
+    if (!m->d_spread) {
+        GB_CUDA(cudaMalloc((void **)&m->d_spread, SPREAD * 8));
+        GB_CUDA(cudaMemsetAsync(m->d_spread, 0, SPREAD * 8, st));
+    }
+    const unsigned int per = (slab + IK_THREADS * IS_PER_THREAD - 1) / (IK_THREADS * IS_PER_THREAD);
+    const unsigned long long work = (unsigned long long)in.slices * in.sources * in.grid * per;
+    if (work >= 0x7FFFFFFFull) { set_error("internal: %llu slab CTAs", work); return GB_E_ARG; }
+    const Table t = m->view();
+    if (t.cap < (1ull << 32)) insert_slabs_kernel<unsigned int, true><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_inbox, nullptr, slab, per, t, m->d_spread, in);
+    else insert_slabs_kernel<unsigned long long, true><<<(unsigned int)work, IK_THREADS, 0, st>>>(d_inbox, nullptr, slab, per, t, m->d_spread, in);
+    GB_LAUNCHED();
+    fold_new_keys_kernel<<<1, SPREAD, 0, st>>>(m->d_spread, m->d_counters);
+    GB_LAUNCHED();
+    return GB_OK;
+}
+
+// the single-pass bucket pass of a sharded map: reads [read0, +n_reads) of a fixed-stride stream into the owners' inbox slabs (ps);
+// keys beyond a slab are appended to the LOCAL list ovf[0 .. ovf_cap) (cursor *d_cursor, zeroed here; *d_failed set if it overflows)
+int bucket_slabs_peers(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned int slab, const PeerSlabs &ps,
+                       unsigned long long *ovf, unsigned long long ovf_cap, unsigned long long *d_cursor, unsigned int *d_failed, cudaStream_t st)
+{
+    GB_TRY(w.ensure(st));
+    const unsigned int nb = (unsigned int)pl.nb();
+    if (nb > STAGE_MAX_BUCKETS || rb.offsets) { set_error("internal: sharded slab bucket pass with %u buckets / a ragged stream", nb); return GB_E_ARG; }
+    if ((unsigned long long)(1u << pl.lp_bits) * (unsigned long long)w.grid * slab >= (1ull << P2P_REL_BITS)) { set_error("internal: inbox region beyond 2^%d keys", P2P_REL_BITS); return GB_E_ARG; }
+    SlabOut so;
+    so.slab = slab;
+    so.overflowed = d_cursor;
+    so.ovf = ovf;
+    so.ovf_cap = ovf_cap;
+    so.failed = d_failed;
+    GB_CUDA(cudaMemsetAsync(d_cursor, 0, 8, st));
+    GB_CUDA(cudaMemsetAsync(d_failed, 0, 4, st));
+    const size_t smem = slabs_smem(nb);
+    int bits = 0;
+    while ((1u << bits) < nb) bits++;
+#define GB_BP(V, L) bucket_slabs_kernel<true, V, L, true><<<w.grid, INSERT_THREADS, smem, st>>>(rb, k, pl.lp_bits, nb, nullptr, so, ps)
+    if (v210) GB_BP(true, -1);
+    else switch (bits) {
+        case 3: GB_BP(false, 3); break;
+        case 4: GB_BP(false, 4); break;
+        case 5: GB_BP(false, 5); break;
+        case 6: GB_BP(false, 6); break;
+        case 7: GB_BP(false, 7); break;
+        default: GB_BP(false, -1); break;
+    }
+#undef GB_BP
     GB_LAUNCHED();
     return GB_OK;
 }

@@ -89,6 +89,26 @@ int part_scatter_slabs(const ReadBatch &rb, int k, bool v210, const PartLayout &
 // the upsert over those slabs (slab s holds min(d_count[s], slab) keys at d_keys + s * slab), in slab order = slice order
 int insert_slabs(Map *m, const unsigned long long *d_keys, const unsigned int *d_count, unsigned int slab, unsigned int n_slabs, cudaStream_t st);
 
+// The same pass on a sharded map (comm.cu): bucket = (owner shard, table slice), and the slabs of owner o live in o's NVLink inbox --
+// the all-to-all happens inside the kernel, store by store, in the staged runs.  keys[o] / cnt[o] = this rank's region of owner o's
+// inbox through its peer mapping: slice-major slabs [slice][CTA], then their fill counts.  No count pass, no counts on the host: the
+// owner upserts straight from the slabs (insert_slabs_kernel, InboxSlabs).  owner_total[o] += keys put into owner o's slabs.
+struct PeerSlabs {
+    unsigned long long *keys[MAX_RANKS];
+    unsigned int *cnt[MAX_RANKS];
+    unsigned long long *owner_total = nullptr;
+    unsigned int owners = 0;
+};
+// what the owner sees of them: its inbox holds `sources` regions of region_cap keys; a region = slice-major slabs [slices][grid],
+// then (at key offset cnt_off) their fill counts as u32
+struct InboxSlabs {
+    unsigned int sources = 0, slices = 0, grid = 0;
+    unsigned long long region_cap = 0, cnt_off = 0;
+};
+int bucket_slabs_peers(const ReadBatch &rb, int k, bool v210, const PartLayout &pl, PartWork &w, unsigned int slab, const PeerSlabs &ps,
+                       unsigned long long *ovf, unsigned long long ovf_cap, unsigned long long *d_cursor, unsigned int *d_failed, cudaStream_t st);
+int insert_inbox_slabs(Map *m, const unsigned long long *d_inbox, const InboxSlabs &in, unsigned int slab, cudaStream_t st);
+
 // desc = { 0, *d_total, 0 } (the chunk table of ONE contiguous range) and counters[3] += *d_total, all on the stream
 int make_single_chunk(const unsigned long long *d_total, unsigned long long *d_desc, unsigned long long *d_counters, cudaStream_t st);
 

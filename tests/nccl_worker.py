@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from genome_b200.dnamap import Communicator, PairedEndData, PartitionedDNAMap, FreqFilter, owner_of, torch_broadcast  # noqa: E402
 from genome_b200.graph import Graph  # noqa: E402
+from genome_b200 import synth  # noqa: E402
 from oracle import pyoracle  # noqa: E402
 from tests import helpers as H  # noqa: E402
 
@@ -59,6 +60,26 @@ def main():
         H.assert_graph_equal(g, og)
         g.close()
         m.close()
+    # every read the same sequence: a handful of keys, so whole buckets go to ONE owner and, in the single-pass form, overflow their
+    # slabs -- the overflow lists take the staged route.  Counts must still be exact.
+    k = 21
+    one = synth.sample_reads(synth.random_genome(100, 5), 100, 1, 0.0, 6)
+    reads = np.repeat(one, 6000, axis=0)
+    b = synth.pack_fixed(reads)
+    n = reads.shape[0]
+    mine = PairedEndData(b, n // 2).shard(rank, world)
+    m = PartitionedDNAMap(k, comm, 1 << 16)
+    w = m.insert_reads(mine)
+    om, ow = H.oracle_counts(b, n, k)
+    tw = torch.tensor([w], device="cuda")
+    dist.all_reduce(tw)
+    assert int(tw.item()) == ow, (int(tw.item()), ow)
+    assert m.size == om.size()
+    ok, ov = om.export_sorted()
+    sel = m.owner(ok) == rank
+    gk, gv = m.export_sorted()
+    assert np.array_equal(gk, ok[sel]) and np.array_equal(gv, ov[sel])
+    m.close()
     # fewer pairs than ranks: some ranks hold no reads at all but still take part in every collective
     k = 15
     b, n, _ = H.small_reads(400, 60, 1, 0.0, seed=77)

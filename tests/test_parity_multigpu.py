@@ -24,14 +24,18 @@ def test_pmap_matches_oracle(gpu, world):
     if gpu < world:
         pytest.skip("needs %d GPUs, box has %d" % (world, gpu))
     run_world(world)
+    run_world(world, {"GENOME_B200_TUNE": "single_pass_min=1"})
 
 
 @pytest.mark.parametrize("env", [{"GENOME_B200_TUNE": "route=2"}, {"GENOME_B200_TUNE": "a2a=1"}, {"GENOME_B200_TUNE": "batches=5,slice_bits=1"},
-                                 {"GENOME_B200_TUNE": "a2a=2"}, {"GENOME_B200_TUNE": "a2a=2,batches=5,route=2"}],
-                         ids=["two-level", "nccl-staged", "many-batches", "dma-push", "dma-push-many-batches-two-level"])
+                                 {"GENOME_B200_TUNE": "a2a=2"}, {"GENOME_B200_TUNE": "a2a=2,batches=5,route=2"},
+                                 {"GENOME_B200_TUNE": "single_pass_min=1"}, {"GENOME_B200_TUNE": "single_pass_min=1,batches=5,slice_bits=2"}],
+                         ids=["two-level", "nccl-staged", "many-batches", "dma-push", "dma-push-many-batches-two-level", "single-pass",
+                              "single-pass-many-batches"])
 def test_pmap_routing_variants(gpu, env):
     """The same sharded run through the other routing paths: receiver-side re-bucketing, NCCL send/recv staging instead of
-    peer stores, more batches than buffer sets."""
+    peer stores, more batches than buffer sets; and the single-pass form (slabs in the owners' inboxes, no count pass: what large
+    batches take by default) forced onto these small inputs, incl. the overflow lists of the all-reads-alike case."""
     if gpu < 2:
         pytest.skip("needs 2 GPUs, box has %d" % gpu)
     run_world(2, env)
@@ -45,6 +49,8 @@ def test_pmap_sharded_graph_build(gpu, world):
     if gpu < world:
         pytest.skip("needs %d GPUs, box has %d" % (world, gpu))
     run_world(world, {"GENOME_B200_TUNE": "pgraph_sharded=1"})
+    if world > 1:
+        run_world(world, {"GENOME_B200_TUNE": "pgraph_sharded=0"})  # the replicated build (all-gather of the shards) beside it
 
 
 @pytest.mark.parametrize("world", [1, 2, 8])
