@@ -503,8 +503,8 @@ def main():
         partitioned = st["upsert_ns"] > 0
         single_pass = bool(capi.get_tune("single_pass")) and windows >= capi.get_tune("single_pass_min")
         if partitioned:
-            dom, dom_s = "insert_keys_kernel", st["upsert_ns"] * 1e-9
-            path = ("L2-blocked, single pass: part_scatter_kernel<SLABS> + insert_keys_kernel" if single_pass
+            dom, dom_s = ("insert_slabs_kernel" if single_pass else "insert_keys_kernel"), st["upsert_ns"] * 1e-9
+            path = ("L2-blocked, single pass: bucket_slabs_kernel + insert_slabs_kernel" if single_pass
                     else "L2-blocked: part_count_kernel + part_scatter_kernel + insert_keys_kernel")
         else:
             dom, dom_s, path = "insert_reads_kernel", ins_s, "direct: insert_reads_kernel"
@@ -546,7 +546,8 @@ def main():
                         "achieved": nbytes / sec / 1e9 if sec > 0 else None, "peak": peak, "unit": "GB/s",
                         "frac": nbytes / sec / 1e9 / peak if sec > 0 else None, "note": note}
             roofline_graph = [
-                entry("compact_survivors_kernel (deleteAll sweep)", 16.0 * ph["slots_swept"], ph["filter_sweep_ns"], "SURVEY 8(d): 12 B read + <= 4 B write per slot"),
+                entry("compact_survivors_kernel (deleteAll sweep)", 12.0 * ph["slots_swept"] + 12.0 * kept, ph["filter_sweep_ns"],
+                      "12 B read per slot (key and count arrays; the vertex ids are not touched) + 12 B written per survivor"),
                 entry("masks_kernel (Graph.buildGraph membership probes)", 73.0 * kept, gph["graph_masks_ns"], "SURVEY 8(d): 8 probes x 8 B + 8 B own key + 1 B mask per kept k-mer"),
                 entry("jump_kernel x %d (list ranking)" % gph["graph_jump_launches"], 16.0 * 2 * kept * gph["graph_jump_launches"], gph["graph_rank_ns"],
                       "SURVEY 8(d): 16 B per oriented vertex and jump round"),
@@ -556,19 +557,19 @@ def main():
         # slowest rank's event time; the first-touch term needs the distinct count before the filter, which the timed loop does not keep
         ins_s = max_over_ranks(float(np.mean(insert_ns)) * 1e-9)
         algo_bytes = 16.0 * windows + float(b.size)
-        superkmer = bool(capi.get_tune("wire_superkmer"))
+        single_pass = bool(capi.get_tune("single_pass")) and windows // 2 >= capi.get_tune("single_pass_min")
         if rank == 0:
             roofline = {"bound": "hbm",
-                        "kernel": ("sharded insert, super-k-mer wire: split (count + emit) + NCCL exchange + local L2-blocked insert" if superkmer else
+                        "kernel": ("sharded insert, single pass: bucket_slabs_kernel<PEER> (NVLink stores into slabs of the owners' inboxes) + insert_slabs_kernel<INBOX>"
+                                   if single_pass else
                                    "sharded insert: part_count + part_scatter<PEER> (NVLink stores into the owners' inboxes) + insert_keys_kernel"),
                         "achieved": algo_bytes / ins_s / 1e9, "peak": peak, "unit": "GB/s", "frac": algo_bytes / ins_s / 1e9 / peak,
                         "traffic": None, "peak_source": peak_src, "insert_ms": ins_s * 1e3,
                         "insert_kmers_per_s_per_gpu": windows / ins_s,
                         "insert_vs_64B_sector_roofline": (windows / ins_s) * 64.0 / (peak * 1e9)}
-            if not superkmer:
-                roofline["nvlink_bytes_out_per_gpu"] = 8.0 * windows * (world - 1) / world
-                roofline["nvlink_gbs_out_per_gpu"] = 8.0 * windows * (world - 1) / world / ins_s / 1e9
-                roofline["nvlink_frac_of_measured_770"] = roofline["nvlink_gbs_out_per_gpu"] / 770.0
+            roofline["nvlink_bytes_out_per_gpu"] = 8.0 * windows * (world - 1) / world
+            roofline["nvlink_gbs_out_per_gpu"] = 8.0 * windows * (world - 1) / world / ins_s / 1e9
+            roofline["nvlink_frac_of_900_per_direction"] = roofline["nvlink_gbs_out_per_gpu"] / 900.0
     graph = R.get("graph")
     launches, clocks = R["launches"], R["clocks"]
     step_s, wall_step_s, G = R["step_s"], R["wall_step_s"], R["G"]
@@ -593,8 +594,7 @@ def main():
             "config": {"workload": "%s: %s" % (args.workload, desc), "k": K, "rounds": ROUNDS, "reads_per_gpu": n_reads,
                        "kmer_instances_per_gpu": windows, "genome_bp": G, "scale": args.scale,
                        "sharding": ("one table" if world == 1 else
-                                    "minimizer-owner shard per GPU, 16-byte super-k-mer records over NCCL" if capi.get_tune("wire_superkmer")
-                                    else "hash-prefix shard per GPU, keys stored into the owners' NVLink inboxes by the bucket pass"),
+                                    "hash-prefix shard per GPU, keys stored into the owners' NVLink inboxes by the bucket pass"),
                        "tuning": tuning or "defaults",
                        "l2": "table (%.2f GB) is re-initialised and randomly written every step: far larger than the 126 MB L2" % (table_bytes / 1e9)},
             "parity_checked": bool(parity and parity["ok"]), "parity": parity, "identities": R.get("identities"),

@@ -22,16 +22,15 @@
 #include "common.cuh"
 #include "extract.cuh"
 #include "partition.cuh"
+#include "sgraph.cuh"
 #include "sgraph_fabric.cuh"
-#include "superkmer.cuh"
 
 namespace gb {
 
 
-// one of the two staging sets of the sharded insert; lives as long as the communicator
-// buffer sets of the sharded insert (staging, inbox, events), used round-robin by the batches of one call.  Peer stores need 3 (a rank
-// that has my counts of batch j knows my upsert of j - 2 is over); the copy-engine pipeline issues the transfer of batch j + 1 before
-// it has the counts of batch j, hence 4 (see pmap_insert).
+// buffer sets of the sharded insert (staging, inbox, events), used round-robin by the batches of one call; they live as long as the
+// communicator.  A rank that has my totals of batch j knows my upsert of j - 2 is over, so 3 sets would do for the form that waits
+// for the totals before it queues the next batch; the single-pass form queues the bucket pass of batch j + 1 first: one more.
 constexpr int NSETS = 4;
 
 struct BatchBufs {
@@ -40,7 +39,7 @@ struct BatchBufs {
     unsigned long long *d_tot = nullptr, *h_tot = nullptr; // bucket totals (mine, received) and the upsert's chunk table
     PartWork work;  // bucket pass of the outgoing keys (communicator stream)
     PartWork work2; // re-bucketing of the received keys by fine table slice (map stream; two-level routing)
-    cudaEvent_t exchanged = nullptr, inserted = nullptr, scattered = nullptr;
+    cudaEvent_t exchanged = nullptr, inserted = nullptr;
     bool in_flight = false;
     int ensure(size_t ns, size_t nr);
     void release();
@@ -51,7 +50,6 @@ struct Comm {
     ncclComm_t nccl = nullptr;
     cudaStream_t stream = nullptr; // bucketing + collectives
     BatchBufs bufs[NSETS];
-    cudaStream_t xfer = nullptr;   // copy-engine pushes + the count exchange that follows them
     unsigned long long *d_scratch = nullptr, *h_scratch = nullptr;
     // NVLink inboxes (fused routing): inbox[i] holds n_ranks regions of region_cap keys, region s is written by rank s
     // through its peer mapping peer_inbox[i][me] obtained with CUDA IPC
@@ -213,7 +211,6 @@ int BatchBufs::ensure(size_t ns, size_t nr)
         GB_CUDA(cudaHostAlloc((void **)&h_tot, (4 * MAX_BUCKETS + 8) * 8, cudaHostAllocDefault));
         GB_CUDA(cudaEventCreateWithFlags(&exchanged, cudaEventDisableTiming));
         GB_CUDA(cudaEventCreateWithFlags(&inserted, cudaEventDisableTiming));
-        GB_CUDA(cudaEventCreateWithFlags(&scattered, cudaEventDisableTiming));
     }
     return GB_OK;
 }
@@ -226,11 +223,10 @@ void BatchBufs::release()
     if (h_tot) cudaFreeHost(h_tot);
     if (exchanged) cudaEventDestroy(exchanged);
     if (inserted) cudaEventDestroy(inserted);
-    if (scattered) cudaEventDestroy(scattered);
     work.release();
     work2.release();
     send = recv = d_tot = h_tot = nullptr;
-    exchanged = inserted = scattered = nullptr;
+    exchanged = inserted = nullptr;
 }
 
 static void close_inboxes(Comm *c)
@@ -413,123 +409,10 @@ struct NcclFabric : sg::Fabric {
     }
 };
 
-// ---------------------------------------------------------------- super-k-mer wire format (GENOME_B200_WIRE=superkmer)
-// One thread per read around the CPU-checked functors of superkmer.cuh.  Their per-record atomics go to SHARED memory here
-// (millions of records on P counters would serialise in L2): a CTA counts into shared counters and adds them to the global
-// ones once; the emit kernel counts first, reserves one block per owner for the whole CTA, then emits through shared cursors.
-constexpr int SK_THREADS = 128;
-static_assert(SK_THREADS >= MAX_RANKS, "one thread per owner in the CTA epilogues");
-__global__ void __launch_bounds__(SK_THREADS) sk_count_kernel(unsigned long long n, sg::SkCountOp op)
+// owner of a key: a prefix of its slot hash (orientation-blind only through FreqFilter's canonical rule: keys arrive canonical)
+static inline int32_t pmap_owner_of(const Map *, unsigned long long key, int P)
 {
-    __shared__ unsigned long long s_cnt[MAX_RANKS + 1]; // [owner] records, [MAX_RANKS] k-windows
-    for (int i = threadIdx.x; i <= MAX_RANKS; i += SK_THREADS) s_cnt[i] = 0;
-    __syncthreads();
-    const unsigned long long r = (unsigned long long)blockIdx.x * SK_THREADS + threadIdx.x;
-    sg::SkCountOp local = op;
-    local.per_owner = s_cnt;
-    local.windows = s_cnt + MAX_RANKS;
-    if (r < n) local(r);
-    __syncthreads();
-    if ((int)threadIdx.x < op.P && s_cnt[threadIdx.x]) atomicAdd(op.per_owner + threadIdx.x, s_cnt[threadIdx.x]);
-    if (threadIdx.x == 0 && s_cnt[MAX_RANKS]) atomicAdd(op.windows, s_cnt[MAX_RANKS]);
-}
-__global__ void __launch_bounds__(SK_THREADS) sk_emit_kernel(unsigned long long n, sg::SkEmitOp op)
-{
-    __shared__ unsigned long long s_cnt[MAX_RANKS + 1], s_cur[MAX_RANKS];
-    __shared__ unsigned long long *s_out[MAX_RANKS];
-    for (int i = threadIdx.x; i <= MAX_RANKS; i += SK_THREADS) s_cnt[i] = 0;
-    __syncthreads();
-    const unsigned long long r = (unsigned long long)blockIdx.x * SK_THREADS + threadIdx.x;
-    if (r < n) sg::SkCountOp{ op.bin, op.offsets, op.rec_bytes, op.k, op.m, op.P, s_cnt, s_cnt + MAX_RANKS }(r);
-    __syncthreads();
-    if ((int)threadIdx.x < op.P) {
-        const unsigned long long mine = s_cnt[threadIdx.x];
-        const unsigned long long base = mine ? atomicAdd(op.cursor + threadIdx.x, mine) : 0; // this CTA's block of owner's records
-        s_out[threadIdx.x] = op.out[threadIdx.x] + 2 * base;
-        s_cur[threadIdx.x] = 0;
-    }
-    __syncthreads();
-    sg::SkEmitOp local = op;
-    local.cursor = s_cur;
-    local.out = s_out;
-    if (r < n) local(r);
-}
-
-// owner of a key under the map's ownership rule (both rules are orientation-blind: x and rc(x) share the owner)
-static inline int32_t pmap_owner_of(const Map *m, unsigned long long key, int P)
-{
-    if (m->owner_mode == 1) return (int32_t)sg::owner_of_kmer(key, m->k, sg::minimizer_len(m->k), P);
     return (int32_t)owner_of(mix64(key), (unsigned int)P);
-}
-
-// Sharded FreqFilter.add with super-k-mers on the wire (csrc/superkmer.cuh): every read is cut into runs
-// of k-windows with one minimizer owner, each run is one 16-byte record; the records are grouped by owner in a local buffer
-// (count pass + emit pass, one thread per read), exchanged with grouped ncclSend / ncclRecv (~1.5 B per k-window instead of
-// 8), and every rank inserts what it received through the single-GPU path (map_insert_records: the L2-blocked insert with
-// the records as its reads).  One batch per call, no overlap of exchange and insert yet.  Collective.
-// Written after this round's GPU budget was spent: opt-in, tests/test_parity_multigpu.py (GENOME_B200_UNVALIDATED=1).
-static int pmap_insert_superkmers(Map *m, const uint8_t *d_bin, const unsigned long long *d_off, unsigned int rec, int64_t n_reads,
-                                  int64_t *n_windows)
-{
-    Comm *c = m->comm;
-    ArenaScope scope(&m->arena); // count / send / receive buffers: from the map's arena (no cudaMalloc per call in the steady state)
-    const int P = c->n_ranks, k = m->k, mlen = sg::minimizer_len(k);
-    if (sg::sk_max_windows(k) < 1) { set_error("super-k-mer records hold 52 bases: k = %d does not fit", k); return GB_E_K_RANGE; }
-    cudaStream_t st = c->stream;
-    GB_CUDA(cudaStreamSynchronize(m->stream)); // d_bin may have been produced on the map's stream
-    cudaEvent_t e0 = nullptr, e1 = nullptr; // the whole call on the device clock: split + exchange + insert
-    GB_CUDA(cudaEventCreate(&e0));
-    GB_CUDA(cudaEventCreate(&e1));
-    struct EvGuard { cudaEvent_t a, b; ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } ev_guard{ e0, e1 };
-    GB_CUDA(cudaEventRecord(e0, st));
-    DeviceBuf d_cnt, d_cursor, d_out;
-    GB_TRY(d_cnt.alloc((2 * MAX_RANKS + 2) * 8));
-    GB_TRY(d_cursor.alloc(MAX_RANKS * 8));
-    GB_TRY(d_out.alloc(MAX_RANKS * 8));
-    unsigned long long *cnt = (unsigned long long *)d_cnt.p, *win = cnt + 2 * MAX_RANKS;
-    GB_CUDA(cudaMemsetAsync(cnt, 0, (2 * MAX_RANKS + 2) * 8, st));
-    GB_CUDA(cudaMemsetAsync(d_cursor.p, 0, MAX_RANKS * 8, st));
-    const unsigned int grid = (unsigned int)((n_reads + SK_THREADS - 1) / SK_THREADS);
-    if (n_reads > 0) {
-        sk_count_kernel<<<grid, SK_THREADS, 0, st>>>((unsigned long long)n_reads, sg::SkCountOp{ d_bin, d_off, rec, k, mlen, P, cnt, win });
-        GB_LAUNCHED();
-    }
-    // counts to their owners; offsets on both sides
-    std::vector<unsigned long long> scnt(P), rcnt(P), soff(P), roff(P);
-    GB_TRY(exchange_counts(c, cnt, cnt + MAX_RANKS, scnt.data(), rcnt.data()));
-    unsigned long long my_windows = 0;
-    GB_CUDA(cudaMemcpy(&my_windows, win, 8, cudaMemcpyDeviceToHost));
-    unsigned long long ns = 0, nr = 0;
-    for (int p = 0; p < P; p++) { soff[p] = 2 * ns; ns += scnt[p]; roff[p] = 2 * nr; nr += rcnt[p]; }
-    DeviceBuf d_send, d_recv;
-    GB_TRY(d_send.alloc((size_t)ns * 16 + 16));
-    GB_TRY(d_recv.alloc((size_t)nr * 16 + 32));
-    std::vector<unsigned long long *> out(P);
-    for (int p = 0; p < P; p++) out[p] = (unsigned long long *)d_send.p + soff[p];
-    GB_CUDA(cudaMemcpyAsync(d_out.p, out.data(), (size_t)P * 8, cudaMemcpyHostToDevice, st));
-    if (n_reads > 0) {
-        sk_emit_kernel<<<grid, SK_THREADS, 0, st>>>((unsigned long long)n_reads, sg::SkEmitOp{ d_bin, d_off, rec, k, mlen, P, (unsigned long long *)d_cursor.p,
-                                                                                               (unsigned long long *const *)d_out.p });
-        GB_LAUNCHED();
-    }
-    // 2 u64 per record
-    std::vector<unsigned long long> scnt2(P), rcnt2(P);
-    for (int p = 0; p < P; p++) { scnt2[p] = 2 * scnt[p]; rcnt2[p] = 2 * rcnt[p]; }
-    GB_TRY(all_to_all_v(c, (const unsigned long long *)d_send.p, soff.data(), scnt2.data(), (unsigned long long *)d_recv.p, roff.data(), rcnt2.data(),
-                        ncclUint64));
-    GB_CUDA(cudaStreamSynchronize(st)); // `out` (host) and the send buffer are free again; the records are here
-    int64_t w_local = 0;
-    GB_TRY(map_insert_records(m, (const uint8_t *)d_recv.p, (size_t)nr * 16, 16, (int64_t)nr, (unsigned int)sg::SK_MAX_BASES, &w_local));
-    GB_CUDA(cudaStreamSynchronize(m->stream));
-    GB_CUDA(cudaEventRecord(e1, st));
-    GB_CUDA(cudaEventSynchronize(e1));
-    float ms = 0;
-    GB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    m->phase_ns[0] = (int64_t)(ms * 1e6) - m->last_insert_ns; // split + exchange (everything but the local insert)
-    m->last_insert_ns = (int64_t)(ms * 1e6);
-    m->fixed_stride = d_off ? 0 : 1;
-    if (n_windows) *n_windows = (int64_t)my_windows; // updates issued for THIS rank's reads, like the k-mer wire path
-    return GB_OK;
 }
 
 // wait for every in-flight insert, fold the new-key counter into m->size
@@ -703,7 +586,6 @@ static int pmap_insert_slabs(Map *m, const uint8_t *d_bin, size_t n_bytes, unsig
 static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsigned long long *d_off, unsigned int rec,
                        unsigned int len0, int64_t n_reads, const int64_t *h_win_prefix, int64_t *n_windows)
 {
-    if (m->owner_mode == 1) return pmap_insert_superkmers(m, d_bin, d_off, rec, n_reads, n_windows);
     Comm *c = m->comm;
     const int P = c->n_ranks;
     const int k = m->k;
@@ -784,8 +666,7 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     GB_TRY(ensure_inboxes(c, region_need));
     if (slab && c->p2p == 1) return pmap_insert_slabs(m, d_bin, n_bytes, rec, win_max, n_reads, batch_reads, batches, pls, slab, n_windows);
     const bool p2p = c->p2p == 1;
-    const bool dma = g_tune.a2a == 2; // local bucket pass + copy-engine pushes (0: the bucket pass stores into the peers' inboxes itself)
-    if (trace) fprintf(stderr, "[pmap] routing: %s, %s (%d wire buckets, %d slices)\n", p2p ? (dma ? "local bucket pass + copy-engine pushes into NVLink inboxes" : "peer stores into NVLink inboxes") : "NCCL send/recv",
+    if (trace) fprintf(stderr, "[pmap] routing: %s, %s (%d wire buckets, %d slices)\n", p2p ? "peer stores into NVLink inboxes" : "NCCL send/recv",
                        two_level ? "two-level" : "one-level", NB, two_level ? 1 << fine.lp_bits : LP);
     GB_TRY(map_zero_counters(m));
     GB_CUDA(cudaStreamSynchronize(m->stream));
@@ -805,7 +686,7 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
         const int64_t r0 = std::min(n_reads, b * batch_reads), r1 = std::min(n_reads, r0 + batch_reads), nr = r1 - r0;
         const int64_t w_upper = fixed ? nr * win_max : (h_win_prefix ? h_win_prefix[r1] - h_win_prefix[r0] : nr * win_max);
         if (B.in_flight) GB_CUDA(cudaStreamWaitEvent(c->stream, B.inserted, 0)); // its buffers are still being read
-        GB_TRY(B.ensure(p2p && !dma ? 0 : (size_t)w_upper, 0));
+        GB_TRY(B.ensure(p2p ? 0 : (size_t)w_upper, 0));
         ReadBatch rb;
         rb.bin = d_bin; rb.n_bytes = n_bytes; rb.offsets = d_off; rb.rec_bytes = rec; rb.read0 = r0; rb.n_reads = nr;
         // d_tot: [0, NB) my bucket totals (row o = what I send to owner o), [NB, 2NB) row s = what source s sends me
@@ -818,30 +699,7 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
             GB_CUDA(cudaMemcpyAsync(B.h_tot, B.d_tot, 2 * NB * 8, cudaMemcpyDeviceToHost, c->stream));
         }
         mark(c->stream);
-        if (p2p && dma) {
-            // The bucket pass writes LOCAL staging memory (as fast as on one GPU); the owner segments -- contiguous: buckets are
-            // owner-major -- are then pushed into the owners' inboxes by the COPY ENGINES on a second stream, at NVLink speed and
-            // beside the kernels (the next batch's bucket pass, the previous batch's upsert), instead of stalling the bucket pass on
-            // remote stores (measured at P = 4: 0.67 ms per 48 M keys with remote stores, 0.35 ms local).  The sizes come from the
-            // count pass: one host read of NB totals, taken while the scatter behind it runs.
-            GB_CUDA(cudaMemcpyAsync(B.h_tot + 3 * MAX_BUCKETS, B.d_tot, NB * 8, cudaMemcpyDeviceToHost, c->stream));
-            GB_CUDA(cudaEventRecord(B.exchanged, c->stream));
-            GB_TRY(part_scatter(rb, k, m->v210, pl, B.work, B.send, c->stream));
-            GB_CUDA(cudaEventRecord(B.scattered, c->stream));
-            GB_CUDA(cudaEventSynchronize(B.exchanged)); // the totals are on the host; the scatter queued behind them is running
-            GB_CUDA(cudaStreamWaitEvent(c->xfer, B.scattered, 0));
-            unsigned long long off = 0;
-            for (int p = 0; p < P; p++) {
-                unsigned long long cnt = 0;
-                for (int l = 0; l < LP; l++) cnt += B.h_tot[3 * MAX_BUCKETS + p * LP + l];
-                if (cnt) GB_CUDA(cudaMemcpyAsync(c->peer_inbox[b % NSETS][p] + (size_t)c->rank * c->region_cap, B.send + off, cnt * 8, cudaMemcpyDefault, c->xfer));
-                off += cnt;
-            }
-            // the counts travel AFTER the keys on the transfer stream: whoever has my counts has my keys
-            GB_TRY(all_to_all_rows(c, B.d_tot, B.d_tot + NB, (size_t)LP, c->xfer));
-            GB_CUDA(cudaMemcpyAsync(B.h_tot, B.d_tot, 2 * NB * 8, cudaMemcpyDeviceToHost, c->xfer));
-            GB_CUDA(cudaEventRecord(B.exchanged, c->xfer));
-        } else if (p2p) {
+        if (p2p) {
             PeerOut po;
             memset(&po, 0, sizeof po);
             for (int p = 0; p < P; p++) po.base[p] = c->peer_inbox[b % NSETS][p] + (size_t)c->rank * c->region_cap;
@@ -860,8 +718,7 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     // upsert on the map's stream
     auto stage_b = [&](int64_t b) -> int {
         BatchBufs &B = bufs[b % NSETS];
-        if (p2p && dma) GB_CUDA(cudaEventSynchronize(B.exchanged));
-        else GB_CUDA(cudaStreamSynchronize(c->stream));
+        GB_CUDA(cudaStreamSynchronize(c->stream));
         const double t_counts = now_ms();
         unsigned long long scnt[MAX_RANKS], soff[MAX_RANKS], rcnt[MAX_RANKS], roff[MAX_RANKS];
         unsigned long long st = 0, rt = 0;
@@ -900,10 +757,8 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
                 }
             vstart[NB] = v;
         }
-        // the transfer stream orders the table behind the keys it describes (dma) / the communicator's stream does
-        cudaStream_t ts = p2p && dma ? c->xfer : c->stream;
-        GB_CUDA(cudaMemcpyAsync(B.d_tot + 2 * NB, vstart, (2 * NB + 1) * 8, cudaMemcpyHostToDevice, ts));
-        GB_CUDA(cudaEventRecord(B.exchanged, ts));
+        GB_CUDA(cudaMemcpyAsync(B.d_tot + 2 * NB, vstart, (2 * NB + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        GB_CUDA(cudaEventRecord(B.exchanged, c->stream));
 
         // room for the received keys (every one may be new); grow only with the pipeline drained
         int64_t cap = (int64_t)m->cap;
@@ -942,26 +797,16 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
                            t_issue - t_begin, t_counts - t_begin, now_ms() - t_begin, st, rt);
         return GB_OK;
     };
-    if (p2p && dma) {
-        // software pipeline: the bucket pass of batch b + 1 is queued before the host waits for the transfer of batch b
-        if (batches) GB_TRY(stage_a(0));
-        for (int64_t b = 0; b < batches; b++) {
-            if (b + 1 < batches) GB_TRY(stage_a(b + 1));
-            GB_TRY(stage_b(b));
-        }
-    } else {
-        for (int64_t b = 0; b < batches; b++) {
-            GB_TRY(stage_a(b));
-            GB_TRY(stage_b(b));
-        }
+    for (int64_t b = 0; b < batches; b++) {
+        GB_TRY(stage_a(b));
+        GB_TRY(stage_b(b));
     }
     GB_CUDA(cudaEventRecord(m->ev1, m->stream));
     GB_TRY(drain(m, bufs));
     GB_CUDA(cudaStreamSynchronize(c->stream));
-    GB_CUDA(cudaStreamSynchronize(c->xfer));
     if (trace) {
         fprintf(stderr, "[pmap] drained %.3f ms\n", now_ms() - t_begin);
-        for (size_t b = 0; !(p2p && dma) && b + 7 <= tev.size(); b += 7) { // (the pipelined stages interleave their marks)
+        for (size_t b = 0; b + 7 <= tev.size(); b += 7) {
             float t[7];
             for (int i = 0; i < 7; i++) cudaEventElapsedTime(&t[i], tev[0], tev[b + i]);
             fprintf(stderr, "[pmap] gpu batch %zu: count %.3f-%.3f  counts-exchange -%.3f  scatter -%.3f  all-to-all -%.3f | upsert %.3f-%.3f\n",
@@ -1031,13 +876,6 @@ int gb_comm_create(const uint8_t id[GB_UNIQUE_ID_BYTES], int rank, int n_ranks, 
         set_error("stream creation failed");
         return GB_E_CUDA;
     }
-    if (cudaStreamCreateWithFlags(&c->xfer, cudaStreamNonBlocking) != cudaSuccess) {
-        cudaStreamDestroy(c->stream);
-        ncclCommDestroy(c->nccl);
-        delete c;
-        set_error("stream creation failed");
-        return GB_E_CUDA;
-    }
     *out = reinterpret_cast<gb_comm *>(c);
     return GB_OK;
 }
@@ -1051,7 +889,6 @@ int gb_comm_destroy(gb_comm *h)
     close_inboxes(c);
     close_windows(c);
     for (int i = 0; i < NSETS; i++) c->bufs[i].release();
-    if (c->xfer) { cudaStreamSynchronize(c->xfer); cudaStreamDestroy(c->xfer); }
     if (c->d_scratch) cudaFree(c->d_scratch);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     if (c->nccl) ncclCommDestroy(c->nccl);
@@ -1089,8 +926,6 @@ int gb_pmap_create(gb_comm *ch, int k, int64_t min_capacity_per_shard, uint32_t 
     Comm *c = reinterpret_cast<Comm *>(ch);
     GB_TRY(gb_map_create(k, min_capacity_per_shard, c->device, flags, out));
     reinterpret_cast<Map *>(*out)->comm = c;
-    // every rank must be tuned alike: the ownership rule is a property of the whole sharded map
-    if (g_tune.wire_superkmer) reinterpret_cast<Map *>(*out)->owner_mode = 1;
     return GB_OK;
 }
 
@@ -1177,11 +1012,6 @@ int gb_pmap_owner(gb_map *h, const uint64_t *keys, int64_t n, int32_t *owner)
     Map *m;
     GB_TRY(check_pmap(h, &m));
     if (n < 0 || (n > 0 && (!keys || !owner))) { set_error("bad arguments"); return GB_E_ARG; }
-    if (m->owner_mode == 1) {
-        if (n < 0 || (n > 0 && (!keys || !owner))) { set_error("bad arguments"); return GB_E_ARG; }
-        for (int64_t i = 0; i < n; i++) owner[i] = pmap_owner_of(m, keys[i], m->comm->n_ranks);
-        return GB_OK;
-    }
     return gb_owner_of(keys, n, m->comm->n_ranks, owner);
 }
 
@@ -1193,7 +1023,7 @@ int gb_owner_of(const uint64_t *keys, int64_t n, int n_parts, int32_t *owner)
     return GB_OK;
 }
 
-// the ownership rule of a GENOME_B200_WIRE=superkmer map (and of the sharded graph build): minimizer owner; host arithmetic
+// the ownership rule of the sharded graph build (sgraph.cuh): minimizer owner; host arithmetic
 int gb_owner_of_minimizer(const uint64_t *keys, int64_t n, int k, int n_parts, int32_t *owner)
 {
     if (n < 0 || n_parts < 1 || (n > 0 && (!keys || !owner))) { set_error("bad arguments"); return GB_E_ARG; }

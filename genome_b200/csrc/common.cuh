@@ -46,13 +46,9 @@ struct Tuning {
     long long h2d_chunks = 4;           // host insert: chunks of the host-to-device copy overlapped with the bucket pass
     long long route = 0;                // sharded insert: 0 = by shard size, 1 = one level (owner, slice) on the wire, 2 = two levels
     long long a2a = 0;                  // sharded insert: 0 = the bucket pass stores into the peers' inboxes (NVLink stores), 1 = staged
-                                        // ncclSend/ncclRecv, 2 = local bucket pass + copy-engine pushes into the inboxes
-    long long wire_superkmer = 0;       // sharded maps created from now on: minimizer owners, 16-byte super-k-mer records on the wire
+                                        // ncclSend/ncclRecv (what a box without peer access takes by itself)
     long long pgraph_sharded = 1;       // Graph.buildGraph over shards without a replica (sgraph.cuh); 0 = all-gather the shards, build replicated
-    long long count_cap_x10 = 30;       // slots per expected key (x 10) of a counting table (gb_map_create / gb_map_clear); the table
-                                        // deleteAll leaves behind always gets 3 (Graph.buildGraph's membership probes want load <= 1/3)
     long long trace = 0;                // phase timings on stderr
-    long long exp = 0;                  // A/B bits of the experiment in progress (0 in production; see scripts/r2_insert_sweep.py)
 };
 extern Tuning g_tune;
 
@@ -427,7 +423,6 @@ struct Map {
     unsigned long long *d_counters = nullptr; // [0] new keys [1] survivors / exported [2] stream flags [3] k-windows
     unsigned long long *d_spread = nullptr;   // spread new-key tallies of insert_keys_kernel (partition.cu)
     Comm *comm = nullptr;
-    int owner_mode = 0; // sharded maps: 0 = owner by hash prefix, 1 = owner by minimizer (super-k-mer wire format, comm.cu)
     // after deleteAll (or in a replica): the stored keys as one device array whose index IS the vertex id written in
     // the slots, so Graph.buildGraph needs no numbering pass.  Any mutation invalidates it.
     const unsigned long long *kept_keys = nullptr;
@@ -463,11 +458,12 @@ int map_swap_table(Map *m, unsigned long long new_cap, void **old_table, unsigne
 void map_retire_table(Map *m, void *t, unsigned long long alloc_cap);
 int map_stage(Map *m, size_t n_u64);
 int pool_setup(int device);
-inline unsigned long long cap_for(int64_t keys, long long slots_per_key_x10 = 30)
+inline unsigned long long cap_for(int64_t keys)
 {
-    // load <= 1/3 at `keys` by default, a multiple of 1024 slots, at least 1024
-    // measured on C2: load 0.22 -> 0.37 costs 10% in the upsert and 60% in the graph build's membership probes
-    unsigned long long c = (((unsigned long long)(keys > 0 ? keys : 0) * (unsigned long long)slots_per_key_x10 + 9) / 10 + 1023) / 1024 * 1024;
+    // load <= 1/3 at `keys`, a multiple of 1024 slots, at least 1024.  Measured on C2 (profiles/r2i_*: counting table at 3 / 2.5 / 2 /
+    // 1.5 slots per expected key): insert 1.95 / 2.16 / 2.25 / 2.63 ms -- the probing a fuller table needs costs more than its
+    // smaller clear and filter sweep give back (0.34 -> 0.16 ms); Graph.buildGraph's membership probes want the low load anyway
+    unsigned long long c = ((unsigned long long)(keys > 0 ? keys : 0) * 3 + 1023) / 1024 * 1024;
     return c < 1024 ? 1024 : c;
 }
 

@@ -496,8 +496,7 @@ int map_launch_update_set(Map *m, const unsigned long long *d_keys, const int *d
         fp = m->fp;
     }
     if (n <= 0) return GB_OK;
-    if (set_vid && (g_tune.exp & 1)) update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->view(), m->d_counters, true, fp);
-    else if (set_vid) place_distinct_kernel<<<(unsigned int)((n + 511) / 512), 256, 0, st>>>(d_keys, d_vals, n, m->view(), fp, m->d_counters);
+    if (set_vid) place_distinct_kernel<<<(unsigned int)((n + 511) / 512), 256, 0, st>>>(d_keys, d_vals, n, m->view(), fp, m->d_counters);
     else update_keys_kernel<true><<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(d_keys, d_vals, n, m->view(), m->d_counters, false, nullptr);
     GB_LAUNCHED();
     return GB_OK;
@@ -945,7 +944,7 @@ int gb_map_create(int k, int64_t min_capacity, int device, uint32_t flags, gb_ma
     m->k = k;
     m->device = device;
     m->v210 = (flags & GB_FLAG_HASH_SCALA_210) != 0;
-    const unsigned long long cap0 = cap_for(min_capacity, g_tune.count_cap_x10);
+    const unsigned long long cap0 = cap_for(min_capacity);
     int r = GB_OK;
     do {
         if ((r = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) == cudaSuccess ? GB_OK : GB_E_CUDA)) break;
@@ -1270,7 +1269,7 @@ int gb_map_clear(gb_map *h, int64_t min_capacity)
     Map *m;
     GB_TRY(check_map(h, &m));
     if (min_capacity < 0) { set_error("negative capacity"); return GB_E_ARG; }
-    unsigned long long nb = cap_for(min_capacity, g_tune.count_cap_x10);
+    unsigned long long nb = cap_for(min_capacity);
     if (nb != m->cap) {
         void *old = nullptr;
         unsigned long long old_alloc = 0;
@@ -1291,10 +1290,10 @@ long long gb_launch_count(void) { return g_launches.load(std::memory_order_relax
 static long long *tune_field(const char *name)
 {
     static const struct { const char *name; long long Tuning::*field; } table[] = {
-        { "count_cap_x10", &Tuning::count_cap_x10 }, { "insert_path", &Tuning::insert_path }, { "single_pass", &Tuning::single_pass }, { "single_pass_min", &Tuning::single_pass_min },
+        { "insert_path", &Tuning::insert_path }, { "single_pass", &Tuning::single_pass }, { "single_pass_min", &Tuning::single_pass_min },
         { "slice_bits", &Tuning::slice_bits }, { "batches", &Tuning::batches }, { "h2d_chunks", &Tuning::h2d_chunks },
         { "route", &Tuning::route }, { "a2a", &Tuning::a2a },
-        { "wire_superkmer", &Tuning::wire_superkmer }, { "pgraph_sharded", &Tuning::pgraph_sharded }, { "trace", &Tuning::trace }, { "exp", &Tuning::exp },
+        { "pgraph_sharded", &Tuning::pgraph_sharded }, { "trace", &Tuning::trace },
     };
     if (name)
         for (const auto &e : table)

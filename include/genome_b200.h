@@ -62,8 +62,9 @@ int gb_bench_l2_requests(int device, size_t region_bytes, int64_t n_updates, int
 /* tuning and test hooks (process-wide; not part of the reference surface).  The library reads no environment variable on
  * its data path: every default is a measured choice, and the parity tests use these keys to force a path that
  * small inputs would not take by themselves.  Keys: insert_path (0 auto, 1 direct, 2 L2-blocked), single_pass,
- * single_pass_min, slice_bits, batches, h2d_chunks, route (0 auto, 1 one level, 2 two levels), a2a (0 peer stores, 1 NCCL staged, 2 copy-engine pushes),
- * wire_superkmer, pgraph_sharded, trace, exp (A/B bits of an experiment in progress; 0 in production).  *previous (optional) receives the old value. */
+ * single_pass_min, slice_bits, batches, h2d_chunks, route (0 auto, 1 one level, 2 two levels), a2a (0 peer stores, 1 NCCL staged),
+ * pgraph_sharded (1 = Graph.buildGraph over shards without a replica, the default; 0 = replicated after an all-gather), trace.
+ * *previous (optional) receives the old value. */
 int gb_tune(const char *name, int64_t value, int64_t *previous);
 int gb_tune_get(const char *name, int64_t *value);
 int gb_version(void);
@@ -94,9 +95,8 @@ int gb_map_insert_reads_device(gb_map *m, const uint8_t *d_bin, size_t n_bytes, 
                                int64_t n_reads, int64_t *n_windows);
 
 /* same for n_records records laid out at a FIXED STRIDE of rec_bytes, each with its own length byte (<= max_len, and
- * 1 + ceil(len / 4) <= rec_bytes; the rest of a record is padding): ragged reads without an offset array, and the receiving
- * end of the super-k-mer wire format (csrc/superkmer.cuh: 16-byte records, max_len 52).  Records shorter than k contribute
- * nothing (FreqFilter.scala:29).  (Written after this round's GPU budget was spent: device test opt-in.) */
+ * 1 + ceil(len / 4) <= rec_bytes; the rest of a record is padding): ragged reads -- or pieces of reads, e.g. 16-byte super-k-mer
+ * records -- without an offset array.  Records shorter than k contribute nothing (FreqFilter.scala:29). */
 int gb_map_insert_records_device(gb_map *m, const uint8_t *d_bin, size_t n_bytes, uint32_t rec_bytes, int64_t n_records, uint32_t max_len,
                                  int64_t *n_windows);
 
@@ -262,7 +262,7 @@ int gb_pmap_graph_build(gb_map *m, gb_graph **out);
 int gb_pmap_owner(gb_map *m, const uint64_t *keys, int64_t n, int32_t *owner);
 /* the same partition(key) (PartitionedDNAMap.scala:60-63) for n_parts shards: host arithmetic, needs no GPU */
 int gb_owner_of(const uint64_t *keys, int64_t n, int n_parts, int32_t *owner);
-/* the other ownership rule, used by maps created under GENOME_B200_WIRE=superkmer and by the sharded graph build: the hash of the
+/* the ownership rule of the sharded graph build (gb_pmap_graph_build re-routes the kept k-mers by it): the hash of the
  * k-mer's minimizer (smallest hashed canonical m-mer), shared by a k-mer, its reverse complement and ~90 % of its (k-1)-overlap
  * neighbours; host arithmetic, needs no GPU */
 int gb_owner_of_minimizer(const uint64_t *keys, int64_t n, int k, int n_parts, int32_t *owner);

@@ -12,7 +12,7 @@
 #include <vector>
 
 #include "../../genome_b200/csrc/sgraph.cuh"
-#include "../../genome_b200/csrc/superkmer.cuh"
+#include "superkmer.cuh"
 
 namespace gb {
 void set_error(const char *, ...) {}

@@ -1,17 +1,14 @@
-// superkmer.cuh -- the wire format planned for the sharded insert: instead of one 8-byte canonical k-mer
-// per k-window, a read is cut into RUNS of consecutive windows that share their minimizer owner (sgraph.cuh), at most
-// SK_MAX_WINDOWS windows per run, and each run travels as one 16-byte record in the reference's `.bin` record layout
-// (S/data/PairedEndData.scala:24-32: 1 length byte, then 4 bases per byte, first base in the low bits) at a fixed stride.
-// On random sequence a run holds ~(k - m + 2) / 2 windows, so the wire carries ~1.5 bytes per k-window instead of 8, and the
-// receiver inserts the records as if they were (short) reads.
-//
-// STATUS: the splitting logic only, as backend-agnostic per-item code (one read per call), checked on the CPU through
-// tests/emul/sgraph_emul.cpp (tests/test_superkmer_emul_cpu.py): the records reproduce the reads' k-window multiset exactly and
-// every window of a record has the record's owner.  Not wired into comm.cu yet (the NVLink measurements that motivate it are
-// in DESIGN.md).  Receiver side: extract.cuh's stage_tile<FIXED> already reads every record's own length byte, so a record
-// stream is insertable as it is; the host-side fixed-stride verification and exact window bounds are what must be relaxed.
+// superkmer.cuh -- TEST INFRASTRUCTURE: cuts reads into 16-byte super-k-mer records, the generator behind the device test of
+// gb_map_insert_records_device (tests/test_countless_gpu.py) and tests/test_superkmer_emul_cpu.py.  A read is cut into RUNS of
+// consecutive k-windows that share their minimizer owner (csrc/sgraph.cuh), at most SK_MAX_WINDOWS windows per run; each run is one
+// record in the reference's `.bin` record layout (S/data/PairedEndData.scala:24-32: 1 length byte, then 4 bases per byte, first
+// base in the low bits) at a fixed stride.  The records reproduce the reads' canonical k-window multiset exactly.
+// History: round 2 ran this as the WIRE FORMAT of the sharded insert (1.5 bytes per k-window instead of 8: minimizer owners, count +
+// emit pass, NCCL exchange, insert of the records).  Measured on 2 B200s (profiles/r2l_multi_2gpu_variants.log): 8.3 ms per 96.6 M
+// k-windows per GPU against 2.8 ms for 8-byte keys stored into NVLink inboxes (2.4 ms single pass) -- the minimizer arithmetic and
+// the second extraction cost far more than the wire saves.  Removed from the library; the splitter stays here as a record generator.
 #pragma once
-#include "sgraph.cuh"
+#include "../../genome_b200/csrc/sgraph.cuh"
 
 namespace gb {
 namespace sg {

@@ -37,7 +37,7 @@ def main():
         assert m.size == om.size()
         # this shard holds exactly the oracle's keys that it owns
         ok, ov = om.export_sorted()
-        sel = m.owner(ok) == rank   # the map's own ownership rule (hash prefix, or minimizer with wire_superkmer)
+        sel = m.owner(ok) == rank   # the map's own ownership rule
         gk, gv = m.export_sorted()
         assert np.array_equal(gk, ok[sel]) and np.array_equal(gv, ov[sel])
         assert m.local_size == int(sel.sum())
@@ -108,7 +108,7 @@ def main():
     om, ow = H.oracle_counts(b, n, k)
     assert m.size == om.size()
     ok, ov = om.export_sorted()
-    sel = m.owner(ok) == rank   # the map's own ownership rule (hash prefix, or minimizer with wire_superkmer)
+    sel = m.owner(ok) == rank   # the map's own ownership rule
     gk, gv = m.export_sorted()
     assert np.array_equal(gk, ok[sel]) and np.array_equal(gv, ov[sel])
     m.close()

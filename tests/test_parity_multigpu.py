@@ -28,10 +28,8 @@ def test_pmap_matches_oracle(gpu, world):
 
 
 @pytest.mark.parametrize("env", [{"GENOME_B200_TUNE": "route=2"}, {"GENOME_B200_TUNE": "a2a=1"}, {"GENOME_B200_TUNE": "batches=5,slice_bits=1"},
-                                 {"GENOME_B200_TUNE": "a2a=2"}, {"GENOME_B200_TUNE": "a2a=2,batches=5,route=2"},
                                  {"GENOME_B200_TUNE": "single_pass_min=1"}, {"GENOME_B200_TUNE": "single_pass_min=1,batches=5,slice_bits=2"}],
-                         ids=["two-level", "nccl-staged", "many-batches", "dma-push", "dma-push-many-batches-two-level", "single-pass",
-                              "single-pass-many-batches"])
+                         ids=["two-level", "nccl-staged", "many-batches", "single-pass", "single-pass-many-batches"])
 def test_pmap_routing_variants(gpu, env):
     """The same sharded run through the other routing paths: receiver-side re-bucketing, NCCL send/recv staging instead of
     peer stores, more batches than buffer sets; and the single-pass form (slabs in the owners' inboxes, no count pass: what large
@@ -51,15 +49,3 @@ def test_pmap_sharded_graph_build(gpu, world):
     run_world(world, {"GENOME_B200_TUNE": "pgraph_sharded=1"})
     if world > 1:
         run_world(world, {"GENOME_B200_TUNE": "pgraph_sharded=0"})  # the replicated build (all-gather of the shards) beside it
-
-
-@pytest.mark.parametrize("world", [1, 2, 8])
-def test_pmap_superkmer_wire(gpu, world):
-    """The sharded insert with super-k-mers on the wire (gb_tune wire_superkmer = 1: minimizer owners, 16-byte records,
-    csrc/superkmer.cuh + comm.cu pmap_insert_superkmers): same worker, same oracle comparisons (shard contents are checked
-    through the map's own owner function); together with the sharded graph build, whose re-routing then finds every key at
-    home."""
-    if gpu < world:
-        pytest.skip("needs %d GPUs, box has %d" % (world, gpu))
-    run_world(world, {"GENOME_B200_TUNE": "wire_superkmer=1"})
-    run_world(world, {"GENOME_B200_TUNE": "wire_superkmer=1,pgraph_sharded=1"})

@@ -23,7 +23,7 @@ def load_emul():
     src = os.path.join(HERE, "emul", "sgraph_emul.cpp")
     out = os.path.join(HERE, "_build", "libsgraph_emul.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    deps = [src] + [os.path.join(ROOT, "genome_b200", "csrc", f) for f in ("sgraph.cuh", "sgraph_fabric.cuh", "superkmer.cuh", "common.cuh")]
+    deps = [src, os.path.join(HERE, "emul", "superkmer.cuh")] + [os.path.join(ROOT, "genome_b200", "csrc", f) for f in ("sgraph.cuh", "sgraph_fabric.cuh", "common.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",

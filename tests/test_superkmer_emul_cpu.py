@@ -1,7 +1,6 @@
-"""The super-k-mer wire format planned for the sharded insert (genome_b200/csrc/superkmer.cuh), run on the
-CPU through the g++ backend: reads are cut into runs of k-windows that share their minimizer owner and packed as 16-byte
-`.bin`-layout records.  The records must carry exactly the reads' k-windows (checked through the oracle's own extraction) and
-every window of a record must belong to the record's owner."""
+"""The super-k-mer splitter (tests/emul/superkmer.cuh, test infrastructure: the record generator of the device test of
+gb_map_insert_records_device) against the oracle's own extraction: the records carry exactly the reads' canonical k-window multiset and
+every window of a record has the record's minimizer owner (csrc/sgraph.cuh: the ownership rule of the sharded graph build)."""
 import ctypes as C
 import os
 
@@ -95,7 +94,7 @@ def test_short_and_boundary_reads(emul):
 
 def test_library_minimizer_owner_matches_the_emulation(emul):
     """gb_owner_of_minimizer (host arithmetic inside libgenome_b200.so, what gb_pmap_lookup routes by under
-    GENOME_B200_WIRE=superkmer) against the g++ build of the same header; and the reverse complement shares the owner."""
+    the sharded graph build) against the g++ build of the same header; and the reverse complement shares the owner."""
     from genome_b200 import capi
     rng = np.random.default_rng(11)
     full, incr = np.zeros(9, np.uint32), np.zeros(8, np.uint32)
@@ -111,18 +110,3 @@ def test_library_minimizer_owner_matches_the_emulation(emul):
             for x, o in zip(keys[:80].tolist(), own[:80].tolist()):
                 emul.emul_owners(k, P, C.c_uint64(x), ptr(full), ptr(incr))
                 assert int(full[0]) == o
-
-
-@pytest.mark.parametrize("world", [2, 3])
-def test_superkmer_routing_gloo(emul, world):
-    """world_size 2 and 3 over gloo (tests/gloo_superkmer_worker.py): split -> route records to minimizer owners -> insert what
-    arrived; the shards are exactly the owner's keys with the single-map counts."""
-    import subprocess
-    import sys
-    here = os.path.dirname(os.path.abspath(__file__))
-    port = str(29760 + world)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-                        "--master-port", port, os.path.join(here, "gloo_superkmer_worker.py")], capture_output=True, text=True, env=env, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-5000:]
-    assert "SUPERKMER ROUTING OK world %d" % world in r.stdout
