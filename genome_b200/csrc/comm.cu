@@ -638,13 +638,13 @@ static int pmap_insert(Map *m, const uint8_t *d_bin, size_t n_bytes, const unsig
     // batches large enough for slabs; its inbox regions hold slabs + their counts
     const int64_t batch_windows = std::min<int64_t>(batch_reads, std::max<int64_t>(n_reads, 1)) * std::max<int64_t>(win_max, 1);
     int64_t slab_keys_cta = 0, can_slabs = fixed && !two_level && g_tune.a2a == 0 && g_tune.single_pass && (int64_t)len0 >= k;
-    // its wire buckets may be as many as the staged pass handles (128): the runs it stores are 2048 / buckets keys, and the
-    // owner's upsert stays L2-blocked up to 8 GPUs (P = 8: 16 slices per shard; the 32-bucket limit of the counted pass below
-    // leaves 4 -- 480 MB slices on C2 -- which is why that one loses the L2 blocking as P grows)
+    // its wire buckets may be as many as the staged pass handles (128): the runs it stores are 2048 / buckets keys, and with 16
+    // slices per shard the owner's upsert stays L2-blocked up to 8 GPUs (the 32-bucket limit of the counted pass below leaves 4
+    // slices at P = 8 -- 480 MB each on C2 -- which is why that one loses the L2 blocking as P grows)
     PartLayout pls;
     pls.owners = P;
     {
-        int64_t lps = slice_bits_for(m->cap, P);
+        int64_t lps = std::min<int64_t>(4, slice_bits_for(m->cap, P)); // measured at P = 2 on C2: 16 slices 2.41 ms, 32 slices 2.50 (shorter store runs)
         if (g_tune.slice_bits >= 0) lps = std::min<int64_t>(lps, g_tune.slice_bits);
         GB_TRY(all_reduce_i64(c, &lps, ncclMin));
         pls.lp_bits = (int)lps;
