@@ -96,6 +96,14 @@ class MapGraph:
                                             capi.ptr(es), capi.ptr(ee), capi.ptr(off), capi.ptr(codes), rm.size, capi.ptr(rm)))
         return list(range(nn, nn + nk.size)), list(range(ne, ne + es.size))
 
+    def write(self, path):
+        """MapGraph.write(file) (Graph.scala:232-248): the Kryo `graph` file (formats.write_kryo_graph; ids = index + 1)."""
+        from . import formats
+        node_kmer, es, ee, off, bases = self.export()
+        seqs = [bases[int(off[i]):int(off[i + 1])] for i in range(es.size)]
+        with open(path, "wb") as f:
+            f.write(formats.write_kryo_graph(self.k, node_kmer, es, ee, seqs))
+
     def simplifyGraph(self):
         capi.check(capi.lib().gb_graph_simplify(self.h))
 
@@ -230,6 +238,25 @@ class Graph:
         fn = capi.lib().gb_pmap_graph_build if isinstance(kmersFreq, PartitionedDNAMap) else capi.lib().gb_graph_build
         capi.check(fn(kmersFreq.h, C.byref(h)))
         return MapGraph(h, k)
+
+    @staticmethod
+    def apply(path, device=0):
+        """Graph(file) (Graph.scala:384-390): reads a Kryo `graph` file into device memory -- an empty graph (buildGraph of an
+        empty map) filled by the bulk addNode / addEdge of gb_graph_edit."""
+        from . import formats
+        from .dnamap import ArrayDNAMap
+        with open(path, "rb") as f:
+            nodes, edges = formats.read_kryo_graph(f.read())
+        k, node_kmer, es, ee, seqs = formats.kryo_graph_arrays(nodes, edges)
+        if k == 0:
+            raise ValueError("a graph file without nodes does not say its k")
+        empty = ArrayDNAMap(k, device=device)
+        try:
+            g = Graph.buildGraph(k, empty)
+        finally:
+            empty.close()
+        g.edit(add_nodes=node_kmer.tolist(), add_edges=[(int(es[i]), int(ee[i]), seqs[i]) for i in range(es.size)])
+        return g
 
     @staticmethod
     def buildGraphVirtualShards(k, kmersFreq, n_shards):

@@ -65,3 +65,31 @@ def small_reads(genome_len, read_len, coverage, err, seed, ragged=False):
     lens = rng.integers(0, read_len + 1, size=n_reads)
     lst = [reads[i, :lens[i]] for i in range(n_reads)]
     return synth.pack_ragged(lst), n_reads, genome
+
+
+def hash_ties(variant=291):
+    """[(k, [k-mers x with hash(x) == hash(rc x), x != rc x])] from tests/golden/hash_ties.json (found by brute force,
+    tests/golden/find_hash_ties.c); every test that uses them re-checks the property with the oracle's own arithmetic."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hash_ties.json")) as f:
+        return [(e["k"], e["kmers"]) for e in json.load(f) if e["variant"] == variant]
+
+
+def tie_reads(k, kmers, seed, strands="both", copies=3, flank=40):
+    """Reads over a genome that embeds the hash-tie k-mers `kmers` between random flanks: every window of k + 12 bases of the
+    forward strand (`strands` = "forward"), of the reverse strand ("reverse") or of both, `copies` times each.  A read of x stores
+    rc(x) and a read of rc(x) stores x (FreqFilter.scala:32, tie => rcx), so "both" leaves BOTH orientations of a tie k-mer in
+    the table and "forward" leaves only rc(x).  Returns (.bin bytes, number of reads)."""
+    rng = np.random.default_rng(seed)
+    parts = [rng.integers(0, 4, flank).astype(np.uint8)]
+    for x in kmers:
+        parts.append(np.array([(int(x) >> (2 * i)) & 3 for i in range(k)], np.uint8))
+        parts.append(rng.integers(0, 4, flank).astype(np.uint8))
+    genome = np.concatenate(parts)
+    rl = k + 12
+    strands_ = {"forward": [genome], "reverse": [revcomp_codes(genome)], "both": [genome, revcomp_codes(genome)]}[strands]
+    reads = [s[i:i + rl] for s in strands_ for i in range(s.size - rl + 1) for _ in range(copies)]
+    if len(reads) % 2:
+        reads.append(reads[-1])
+    return synth.pack_fixed(np.stack(reads)), len(reads)

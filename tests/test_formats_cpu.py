@@ -224,3 +224,111 @@ def test_convert2bin_cuts_reads_to_their_quality_segment():
     reads = formats.read_bin(b, 2)
     assert pairs == 1 and [len(r) for r in reads] == [8, 4]
     assert kmers == (8 - k + 1) + (4 - k + 1) and short == 0
+
+
+# ---- the Kryo `graph` file (Graph.scala:232-261, Node.scala:14-37): formats.write_kryo_graph / read_kryo_graph
+def _zz(v):
+    """Kryo's writeLong(v, false) for small non-negative v: zig-zag then one varint byte"""
+    assert 0 <= v < 64
+    return bytes([2 * v])
+
+
+def test_kryo_graph_bytes_of_a_two_node_graph():
+    """The stream spelled out by hand from the reference's call sites and Kryo 2.x's wire rules (formats.py header): a graph
+    GT -> TA with one edge `A` (k = 2).  Marker 1 before every object, the class name once, name id afterwards."""
+    k = 2
+    gt = 1 | 3 << 2      # G = 1 at bits 0-1, T = 3 at bits 2-3
+    ta = 3 | 0 << 2
+    got = F.write_kryo_graph(k, [gt, ta], [0], [1], [np.array([0], np.uint8)])
+    name = bytearray(b"ru.ifmo.genome.dna.Long1DNASeq")
+    name[-1] |= 0x80
+    want = b"\x01"                                           # writeObject(out, this): new object
+    want += b"\x00\x00\x00\x02"                              # out.writeInt(nodes.size)
+    want += b"\x01" + (1).to_bytes(8, "big")                 # node 1: marker, out.writeLong(id)
+    want += b"\x01\x00" + bytes(name)                        # writeClass: NAME + 2, name id 0, the name
+    want += b"\x01" + bytes([k]) + bytes([2 * gt])           # marker, len: Byte, long: zig-zag varlong
+    want += b"\x00\x00\x00\x00"                              # no in-edges
+    want += b"\x00\x00\x00\x01" + b"\x00" + (1).to_bytes(8, "big")   # one out-edge: base A -> edge 1
+    want += b"\x01" + (2).to_bytes(8, "big")                 # node 2
+    want += b"\x01\x00"                                      # the class again: name id only
+    want += b"\x01" + bytes([k]) + bytes([2 * ta])
+    want += b"\x00\x00\x00\x01" + (1).to_bytes(8, "big")     # in-edge 1
+    want += b"\x00\x00\x00\x00"
+    want += b"\x00\x00\x00\x01"                              # out.writeInt(edges.size)
+    want += b"\x01" + _zz(2) + _zz(1)                        # edge: marker, endId, id (FieldSerializer: fields by name)
+    want += b"\x01\x00" + b"\x01" + bytes([1]) + _zz(0)      # seq: class by id, marker, len 1, long 0
+    want += _zz(1)                                           # startId
+    assert got == want
+    nodes, edges = F.read_kryo_graph(got)
+    assert [(n[0], n[1].tolist(), n[2], n[3]) for n in nodes] == [(1, [1, 3], [], [(0, 1)]), (2, [3, 0], [1], [])]
+    assert [(e[0], e[1], e[2], e[3].tolist()) for e in edges] == [(1, 1, 2, [0])]
+
+
+def test_kryo_varints():
+    assert F._kvar(0, 32) == b"\x00" and F._kvar(127, 32) == b"\x7f" and F._kvar(128, 32) == b"\x80\x01"
+    assert F._kvar(0xFFFFFFFF, 32) == b"\xff\xff\xff\xff\x0f"
+    assert F._kzig(-1 & 0xFFFFFFFF, 32) == b"\x01" and F._kzig(1, 32) == b"\x02"
+    assert len(F._kvar((1 << 64) - 1, 64)) == 9 and F._kvar((1 << 64) - 1, 64)[-1] == 0xFF
+    assert F._kzig(1 << 63, 64) == b"\xff" * 9            # Long.MinValue -> all ones
+    rng = np.random.default_rng(5)
+    for bits in (32, 64):
+        vals = [0, 1, (1 << bits) - 1, 1 << (bits - 1), (1 << (bits - 1)) - 1] + [int(x) >> s for x in rng.integers(0, 1 << 63, 200) for s in (0, 20, 45)]
+        for v in vals:
+            v &= (1 << bits) - 1
+            for enc, dec in ((F._kvar, "var"), (F._kzig, "zig")):
+                r = F._KryoReader(enc(v, bits))
+                assert getattr(r, dec)(bits) == v and r.pos == len(r.b)
+
+
+@pytest.mark.parametrize("k", [1, 5, 16, 31])
+def test_kryo_graph_round_trip(k):
+    """Every sequence class of DNASeq.newBuilder.result (<= 32 bases, <= 64, longer) and lengths around the word borders."""
+    rng = np.random.default_rng(k)
+    n_nodes = 7
+    node_kmer = rng.integers(0, 1 << (2 * k), n_nodes, dtype=np.uint64)
+    lens = [1, 31, 32, 33, 63, 64, 65, 66, 67, 68, 200, 4097]
+    es = rng.integers(0, n_nodes, len(lens)).astype(np.uint32)
+    ee = rng.integers(0, n_nodes, len(lens)).astype(np.uint32)
+    seqs = [rng.integers(0, 4, ln).astype(np.uint8) for ln in lens]
+    used = {}
+    for e in range(len(lens)):       # a Map[Base, Long] per node: distinct first bases among a node's out-edges
+        taken = used.setdefault(int(es[e]), set())
+        free = [b for b in range(4) if b not in taken]
+        if not free:
+            es[e] = next(n for n in range(n_nodes) if len(used.setdefault(n, set())) < 4)
+            taken = used[int(es[e])]
+            free = [b for b in range(4) if b not in taken]
+        seqs[e][0] = free[0]
+        taken.add(free[0])
+    data = F.write_kryo_graph(k, node_kmer, es, ee, seqs)
+    nodes, edges = F.read_kryo_graph(data)
+    k2, nk2, es2, ee2, seqs2 = F.kryo_graph_arrays(nodes, edges)
+    assert k2 == k and np.array_equal(nk2, node_kmer) and np.array_equal(es2, es) and np.array_equal(ee2, ee)
+    assert all(np.array_equal(a, b) for a, b in zip(seqs, seqs2))
+    # the node records agree with the edge list (what Graph.addEdge maintains)
+    for i, (nid, _, ins, outs) in enumerate(nodes):
+        assert nid == i + 1
+        assert sorted(ins) == sorted(e + 1 for e in range(len(lens)) if ee[e] == i)
+        assert sorted(outs) == sorted((int(seqs[e][0]), e + 1) for e in range(len(lens)) if es[e] == i)
+    # all three class names appear exactly once in the stream
+    for cls in ("Long1DNASeq", "Long2DNASeq", "ArrayDNASeq"):
+        assert data.count(cls.encode()[:-1]) == 1
+
+
+def test_kryo_graph_rejects_what_the_reference_cannot_have_written():
+    good = F.write_kryo_graph(3, [5, 9], [0], [1], [np.array([2, 1], np.uint8)])
+    F.read_kryo_graph(good)
+    with pytest.raises(ValueError, match="truncated"):
+        F.read_kryo_graph(good[:-1])
+    with pytest.raises(ValueError, match="after the graph"):
+        F.read_kryo_graph(good + b"\x00")
+    with pytest.raises(ValueError, match="reference marker"):
+        F.read_kryo_graph(b"\x00" + good[1:])            # a null MapGraph
+    with pytest.raises(ValueError, match="same first base"):
+        F.write_kryo_graph(3, [5, 9], [0, 0], [1, 1], [np.array([2], np.uint8), np.array([2, 3], np.uint8)])
+    with pytest.raises(ValueError, match="does not fit"):
+        F.write_kryo_graph(3, [5, 9], [0], [2], [np.array([2], np.uint8)])
+    nodes, edges = F.read_kryo_graph(good)
+    with pytest.raises(ValueError, match="does not hold"):
+        F.kryo_graph_arrays(nodes, [(1, 1, 7, edges[0][3])])
+    assert F.kryo_graph_arrays([], [])[0] == 0

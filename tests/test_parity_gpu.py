@@ -175,8 +175,16 @@ GRAPH_CASES = [
 ]
 
 
+@pytest.fixture(params=["per-kmer", "per-probe"])
+def masks_variant(request):
+    """Both forms of the membership probes of Graph.buildGraph: masks_kernel (one thread per stored k-mer, 8 probes each) and
+    masks_flat_kernel (one lane per probe, masks from the warp ballot)."""
+    with capi.tuned(masks_flat=int(request.param == "per-probe")):
+        yield request.param
+
+
 @pytest.mark.parametrize("k,glen,rl,cov,err,rounds", GRAPH_CASES)
-def test_build_graph_matches_oracle(gpu, k, glen, rl, cov, err, rounds):
+def test_build_graph_matches_oracle(gpu, masks_variant, k, glen, rl, cov, err, rounds):
     b, n, _ = H.small_reads(glen, rl, cov, err, seed=2000 + k)
     data = PairedEndData(b, n // 2)
     gm = FreqFilter.extractFilteredKmers(data, k, rounds)
@@ -263,7 +271,7 @@ def test_remove_edges_then_simplify(gpu):
     g.check()
 
 
-def test_noncanonical_keys_both_orientations(gpu):
+def test_noncanonical_keys_both_orientations(gpu, masks_variant):
     """Keys pushed through update as they are: both orientations of a k-mer can be stored (like a hash tie,
     SURVEY Q3); contains() probes both, nodes are a SET of oriented k-mers."""
     k = 9
@@ -286,12 +294,44 @@ def test_noncanonical_keys_both_orientations(gpu):
     H.assert_graph_equal(g, og)
 
 
-def test_hash_tie_canonical_rule(gpu):
-    """x with hash(x) == hash(rc x), x != rc x: the reference stores rc(x) for a read of x and x for a read of rc(x)
-    (FreqFilter.scala:32: tie => rcx).  Built by search over random 31-mers is infeasible (2^-32); k = 16 makes
-    Long.## = low ^ high over 32 significant bits where ties are constructible: low 32 bits only => hash = value."""
-    k = 16  # 32-bit keys: hash(x) = (int)x, so a tie needs x == rc(x): palindromes only; use the kernel check instead
-    # direct check of the canonical choice on all orientations of random k-mers for several k
+@pytest.mark.parametrize("strands", ["both", "forward"])
+def test_hash_tie_kmers_in_real_reads(gpu, insert_path, masks_variant, strands):
+    """x with hash(x) == hash(rc x), x != rc x (even k >= 18 only, tests/golden/hash_ties.json): a read of x stores rc(x) and a
+    read of rc(x) stores x (FreqFilter.scala:32: tie => rcx).  Reads of both strands leave BOTH orientations in the table of a map
+    that is not `dual`: the insert's tie rule, contains() probing both orientations and the primary / secondary orientation of
+    Graph.buildGraph (single GPU and sharded) are exercised with real reads; reads of one strand store only the orientation
+    the reads do not spell."""
+    for k, kmers in H.hash_ties():
+        b, n = H.tie_reads(k, kmers, seed=k, strands=strands)
+        om, ow = H.oracle_counts(b, n, k)
+        gm, gw = gpu_map_from(b, n, k)
+        assert gw == ow
+        gk, gv = gm.export_sorted()
+        ok, ov = om.export_sorted()
+        assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
+        stored = set(int(x) for x in gk)
+        for x in kmers:
+            assert pyoracle.revcomp(x, k) in stored and (x in stored) == (strands == "both")
+        _, found = gm.lookup(np.array(kmers, np.uint64))     # apply(x): exact orientation, no canonicalisation
+        assert found.all() if strands == "both" else not found.any()
+        gm.delete_below(3)
+        om.delete_below(3)
+        gk, gv = gm.export_sorted()
+        ok, ov = om.export_sorted()
+        assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
+        og = pyoracle.OracleGraph(om)
+        g = Graph.buildGraph(k, gm)
+        assert og.counts()[1] > 0
+        H.assert_graph_equal(g, og)
+        g.check()
+        for P in (2, 3):
+            H.assert_graph_equal(Graph.buildGraphVirtualShards(k, gm, P), og)
+        g.simplifyGraph(); og.simplify()
+        H.assert_graph_equal(g, og)
+
+
+def test_canonical_rule_on_random_kmers(gpu):
+    """The canonical choice (FreqFilter.scala:31-32) on all orientations of random k-mers for several k."""
     for kk in (16, 17, 21, 31):
         rng = np.random.default_rng(kk)
         xs = rng.integers(0, 1 << (2 * kk), size=4000, dtype=np.uint64)

@@ -98,3 +98,26 @@ def test_graph_edit_mutators(gpu):
     assert g.counts() == (nn, ne, nb)
     assert H.canon_gpu_graph(g) == before
     g.check()
+
+
+@pytest.mark.parametrize("k,glen,rl,cov,err", [(31, 20000, 100, 30, 0.01), (9, 4000, 40, 15, 0.03)])
+def test_graph_file_round_trip(gpu, tmp_path, k, glen, rl, cov, err):
+    """graph.write(file) then Graph(file) (Graph.scala:232-261,384-390; GraphBuilder.scala:56 -> GraphSimplifier.scala:34): the Kryo
+    file carries the graph from the builder script to the simplifier script.  The graph read back equals the one written and
+    behaves the same under simplifyGraph."""
+    from genome_b200 import formats
+    from genome_b200.dnamap import FreqFilter
+    from genome_b200.graph import Graph
+    b, n, _ = H.small_reads(glen, rl, cov, err, seed=2000 + k)
+    g = Graph.buildGraph(k, FreqFilter.extractFilteredKmers(PairedEndData(b, n // 2), k, 2))
+    path = str(tmp_path / "graph")
+    g.write(path)
+    nodes, edges = formats.read_kryo_graph(open(path, "rb").read())
+    assert (len(nodes), len(edges), sum(e[3].size for e in edges)) == g.counts()
+    g2 = Graph.apply(path)
+    assert g2.counts() == g.counts()
+    assert H.canon_gpu_graph(g2) == H.canon_gpu_graph(g)
+    g2.check()
+    g.simplifyGraph()
+    g2.simplifyGraph()
+    assert H.canon_gpu_graph(g2) == H.canon_gpu_graph(g)

@@ -333,3 +333,24 @@ def test_golden_fixture(emul):
         for threads in (False, True):
             got, counts, _ = sharded_build(emul, k, keys, P, threads=threads)
             assert got == want
+
+
+@pytest.mark.parametrize("strands", ["both", "forward"])
+def test_sharded_build_with_hash_tie_kmers(emul, strands):
+    """Even-k k-mers whose two orientations hash alike (tests/golden/hash_ties.json): reads of both strands store BOTH orientations
+    (FreqFilter.scala:32, tie => rcx) without the map being `dual`, so the probes cannot pick a canonical orientation, the
+    numerically smaller stored orientation is the vertex and the other one is secondary; reads of one strand store only the
+    orientation the reads do NOT spell.  The sharded build must give the oracle's graph either way."""
+    for k, kmers in H.hash_ties():
+        b, n = H.tie_reads(k, kmers, seed=k, strands=strands)
+        om, og = oracle_graph(b, n, k, 3)
+        keys, _ = om.export()
+        stored = set(int(x) for x in keys)
+        for x in kmers:
+            assert pyoracle.revcomp(x, k) in stored and (x in stored) == (strands == "both")
+        want = H.canon_oracle_graph(og)
+        assert og.counts()[1] > 0
+        for P, split in [(1, "even"), (2, "even"), (3, "skewed"), (8, "even")]:
+            got, counts, st = sharded_build(emul, k, keys, P, split=split, seed=P)
+            assert counts == og.counts(), (k, P, split)
+            assert got == want, (k, P, split)
