@@ -210,8 +210,12 @@ masks_kernel(Table table, int k, bool dual, const unsigned long long *keys, unsi
 // The same probes with ONE LANE PER (stored k-mer, neighbour query): 8 consecutive lanes share a key (lane j < 4: successor by base
 // j, j >= 4: predecessor by base j - 4), so the warp's ballot of `found` holds the mask bytes of its 4 keys, and the unique
 // neighbour of a side comes from the lane that found it by one shuffle.  No 8-fold unrolled probe code (masks_kernel: 4 500 SASS
-// instructions, 64 registers), 8 x the independent probes in flight per resident thread.  rc of a neighbour is one shift of rc(x):
-// rc(x.drop(1) :+ b) = comp(b) +: rc(x).take(k-1), rc(b +: x.take(k-1)) = rc(x).drop(1) :+ comp(b).
+// instructions, 64 registers, 40 % of the warps resident; here 26 registers, 85 %), 8 x the independent probes in flight per
+// resident thread: 1.36 -> 0.77 ms on C2 (profiles/r2r_masks_timing.json).  rc of a neighbour is one shift of rc(x):
+// rc(x.drop(1) :+ b) = comp(b) +: rc(x).take(k-1), rc(b +: x.take(k-1)) = rc(x).drop(1) :+ comp(b) -- so successor and
+// predecessor lanes run the SAME instructions on swapped operands (A = (s.drop(1) :+ c), B = (comp(c) +: t.take(k-1)) with
+// (s, t, c) = (x, rc x, b) or (rc x, x, comp b): {A, B} = {q, rc q} either way), and the warp stays converged up to the probe
+// loop: the first form of this kernel branched on `rc(x) < x` and on `j < 4` and ran its body twice per warp (ncu source page).
 template <bool V210>
 __global__ void __launch_bounds__(256)
 masks_flat_kernel(Table table, int k, bool dual, const unsigned long long *keys, unsigned long long lo,
@@ -219,35 +223,32 @@ masks_flat_kernel(Table table, int k, bool dual, const unsigned long long *keys,
 {
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int lane = threadIdx.x & 31, j = lane & 7, group = lane & 24;
-    const unsigned long long v = lo + (t >> 3);
-    const bool live = (t >> 3) < n; // no early exit: every lane of the warp takes part in the ballot and the shuffles
+    const bool live = (t >> 3) < n; // no early exit: every lane of the warp takes part in the ballot and the shuffles;
+    const unsigned long long v = lo + (live ? (t >> 3) : 0); // the lanes behind the last key redo key `lo` and drop the result
+    const unsigned long long x = keys[v];
+    const unsigned long long rcx = revcomp(x, k);
+    // a SECONDARY orientation (rc stored too and numerically smaller) is no vertex: mask 0, never referenced.  Only hash ties
+    // (even k) and as-is inserts can store both orientations
+    bool skip = !live;
+    const bool suspect = check_secondary & (rcx < x) & (dual | (scala_hash<V210>(x) == scala_hash<V210>(rcx)));
+    if (suspect) skip |= probe_find(table, rcx, fp) >= 0;
+    __syncwarp();
+    const bool succ = j < 4;
+    const unsigned int c = succ ? (j & 3u) : ((j & 3u) ^ 3u);
+    const unsigned long long A = kmer_append(succ ? x : rcx, k, c), B = kmer_prepend(succ ? rcx : x, k, c ^ 3u);
+    const int hA = scala_hash<V210>(A), hB = scala_hash<V210>(B);
     bool found = false;
     unsigned int w = NONE32;
-    if (live) {
-        const unsigned long long x = keys[v];
-        const unsigned long long rcx = revcomp(x, k);
-        // a SECONDARY orientation (rc stored too and numerically smaller) is no vertex: mask 0, never referenced
-        bool secondary = false;
-        if (check_secondary && rcx < x && (dual || scala_hash<V210>(x) == scala_hash<V210>(rcx)))
-            secondary = probe_find(table, rcx, fp) >= 0;
-        if (!secondary) {
-            const unsigned int b = j & 3;
-            const unsigned long long q = j < 4 ? kmer_append(x, k, b) : kmer_prepend(x, k, b);
-            const unsigned long long r = j < 4 ? kmer_prepend(rcx, k, b ^ 3u) : kmer_append(rcx, k, b ^ 3u);
-            const int hq = scala_hash<V210>(q), hr = scala_hash<V210>(r);
-            unsigned long long at = 0;
-            unsigned int strand = 0;
-            if (!dual && hq != hr) { // one stored orientation possible: the canonical one
-                const unsigned long long c = hq < hr ? q : r;
-                const long long i = probe_find(table, c, fp);
-                found = i >= 0;
-                at = (unsigned long long)i;
-                strand = c != q;
-            } else {
-                found = find_oriented<V210>(table, k, dual, q, &at, &strand, fp);
-            }
-            if (found) w = 2 * load_vid(table, at) + strand;
-        }
+    if (!dual && hA != hB) { // one stored orientation possible: the canonical one (always, for odd k)
+        const bool pickA = hA < hB;
+        const long long i = skip ? -1 : probe_find(table, pickA ? A : B, fp);
+        found = i >= 0;
+        if (found) w = 2 * load_vid(table, (unsigned long long)i) + (unsigned int)(pickA != succ); // strand: the stored key is rc(q)
+    } else if (!skip) {
+        unsigned long long at = 0;
+        unsigned int strand = 0;
+        found = find_oriented<V210>(table, k, dual, succ ? A : B, &at, &strand, fp);
+        if (found) w = 2 * load_vid(table, at) + strand;
     }
     const unsigned int byte = (__ballot_sync(0xFFFFFFFFu, found) >> group) & 0xFFu;
     const unsigned int out = byte & 0xFu, in = byte >> 4;

@@ -409,6 +409,56 @@ struct MasksOp { // incoming / outcoming (Graph.scala:272-282) of every stored k
         nbr_in[v] = si;
     }
 };
+// The same probes with ONE ITEM PER (stored key, neighbour query) -- the default: MasksOp keeps 8 queries in the registers of one
+// thread (76 registers, a third of the warps resident, profiles/masks_r2r_*), which hides little of the latency of a probe that
+// goes to a peer's index over NVLink.  Here a key's minimizer parts are computed once (PartsOp), every query is an item of its
+// own (ProbeOp: 8 consecutive items = 8 consecutive lanes share a key) and a third sweep folds the 8 answers of a key into its mask
+// byte and unique neighbours (CombineOp: one 32-byte read per key).
+struct PartsOp { // per stored key: is it a vertex at all (a secondary orientation is not), and the parts of its minimizer
+    Ctx c; u32 *parts; u8 *skip;
+    SG_HD void operator()(u64 v) const
+    {
+        const Peer &me = c.peer[c.me];
+        const u64 x = me.keys[v];
+        skip[v] = is_secondary(c, me, x) ? 1 : 0;
+        const MinParts mp = min_parts(x, revcomp(x, c.k), c.k, c.m);
+        parts[3 * v] = mp.first;
+        parts[3 * v + 1] = mp.mid;
+        parts[3 * v + 2] = mp.last;
+    }
+};
+struct ProbeOp { // item i = 8 v + j: the successor of key v by base j / 2 (j even) or its predecessor (j odd), NONE32 = absent
+    Ctx c; const u32 *parts; const u8 *skip; u32 *found;
+    SG_HD void operator()(u64 i) const
+    {
+        const u64 v = i >> 3;
+        const u32 j = (u32)i & 7u;
+        u32 g = NONE32;
+        if (!skip[v]) {
+            const u64 x = c.peer[c.me].keys[v], rcx = revcomp(x, c.k);
+            const MinParts mp{ parts[3 * v], parts[3 * v + 1], parts[3 * v + 2] };
+            const Neighbour nb = neighbour_of(mp, x, rcx, c.k, c.m, c.P, (j & 1) == 0, j >> 1);
+            u32 f = 0;
+            if (find_g(c, nb.owner, nb.q, nb.rq, &f)) g = f;
+        }
+        found[i] = g;
+    }
+};
+struct CombineOp { // the 8 answers of a key -> incoming / outcoming masks and the unique neighbour of either side
+    const u32 *found; u8 *mask8; u32 *nbr_out, *nbr_in;
+    SG_HD void operator()(u64 v) const
+    {
+        u32 out = 0, in = 0, so = NONE32, si = NONE32;
+        for (u32 j = 0; j < 8; j++) {
+            const u32 g = found[8 * v + j];
+            if (g == NONE32) continue;
+            if ((j & 1) == 0) { out |= 1u << (j >> 1); so = g; } else { in |= 1u << (j >> 1); si = g; }
+        }
+        mask8[v] = (u8)(out | (in << 4));
+        nbr_out[v] = so;
+        nbr_in[v] = si;
+    }
+};
 struct ClassifyOp { // per oriented vertex: is it a node, how many edges start there, does it head a segment
     Ctx c; Local L;
     SG_HD void operator()(u64 uu) const
@@ -633,7 +683,7 @@ inline size_t base_words(u64 n_bases) { return (size_t)((n_bases + 15) / 16) + 2
 
 // One sharded build.  in[l] belongs to rank fab.mine[l]; the resulting graph (identical on every process) is allocated
 // through in[0].ex.  Collective: every process of the fabric calls it with the same k / dual / v210.
-inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual, bool v210, Result *res)
+inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual, bool v210, Result *res, bool per_probe = true)
 {
     const int P = fab.P, nl = (int)fab.mine.size();
     if (P < 1 || P > MAXR || nl < 1 || (int)in.size() != nl) { set_error("sharded build: bad rank set"); return GB_E_ARG; }
@@ -734,7 +784,19 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
         const u64 n = ctx[l].peer[ctx[l].me].n;
         GB_TRY(sg_new(ex, &nbr_out[l], (size_t)n));
         GB_TRY(sg_new(ex, &nbr_in[l], (size_t)n));
-        GB_TRY(sg_launch(ex, n, MasksOp{ ctx[l], (u8 *)ctx[l].peer[ctx[l].me].mask8, nbr_out[l], nbr_in[l] }));
+        u8 *mask8 = (u8 *)ctx[l].peer[ctx[l].me].mask8;
+        if (per_probe) {
+            u32 *parts = nullptr, *found = nullptr;
+            u8 *skip = nullptr;
+            GB_TRY(sg_new(ex, &parts, 3 * (size_t)n));
+            GB_TRY(sg_new(ex, &skip, (size_t)n));
+            GB_TRY(sg_new(ex, &found, 8 * (size_t)n));
+            GB_TRY(sg_launch(ex, n, PartsOp{ ctx[l], parts, skip }));
+            GB_TRY(sg_launch(ex, 8 * n, ProbeOp{ ctx[l], parts, skip, found }));
+            GB_TRY(sg_launch(ex, n, CombineOp{ found, mask8, nbr_out[l], nbr_in[l] }));
+        } else {
+            GB_TRY(sg_launch(ex, n, MasksOp{ ctx[l], mask8, nbr_out[l], nbr_in[l] }));
+        }
         loc[l] = Local{ nbr_out[l], nbr_in[l], nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0 };
     }
     GB_TRY(fab.barrier());

@@ -64,7 +64,7 @@ int gb_bench_l2_requests(int device, size_t region_bytes, int64_t n_updates, int
  * small inputs would not take by themselves.  Keys: insert_path (0 auto, 1 direct, 2 L2-blocked), single_pass,
  * single_pass_min, slice_bits, batches, h2d_chunks, route (0 auto, 1 one level, 2 two levels), a2a (0 peer stores, 1 NCCL staged),
  * pgraph_sharded (1 = Graph.buildGraph over shards without a replica, the default; 0 = replicated after an all-gather),
- * masks_flat (membership probes of Graph.buildGraph: 1 = one lane per (k-mer, neighbour), 0 = one thread per k-mer), trace.
+ * masks_flat (membership probes of Graph.buildGraph: 1 = one lane per (k-mer, neighbour), the default; 0 = one thread per k-mer), trace.
  * *previous (optional) receives the old value. */
 int gb_tune(const char *name, int64_t value, int64_t *previous);
 int gb_tune_get(const char *name, int64_t *value);

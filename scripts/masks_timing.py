@@ -40,11 +40,17 @@ for flat in (0, 1):
                                 "probes_ms_min": min(probes[tail]), "probes_ms_all": probes, "build_ms_min": min(builds[tail]),
                                 "ranking_ms_min": min(ranking[tail]), "counts": counts, "same_graph_as_first": same})
 P = int(os.environ.get("SG_P", "8"))
-builds = []
-for rep in range(reps):
-    g = Graph.buildGraphVirtualShards(K, m, P)
-    builds.append(g.stats()["build_ns"] * 1e-6)
-    same = ref[0] == g.counts()
-    g.close()
-out["virtual_shards"] = {"P": P, "build_ms_min": min(builds[min(2, reps - 1):]), "build_ms_all": builds, "same_counts": same}
+out["virtual_shards"] = []
+for flat in (0, 1):
+    if reps == 1 and flat == 0:
+        continue                     # the ncu pass profiles the default form only
+    with capi.tuned(masks_flat=flat):
+        builds = []
+        for rep in range(reps):
+            g = Graph.buildGraphVirtualShards(K, m, P)
+            builds.append(g.stats()["build_ns"] * 1e-6)
+            same = ref[0] == g.counts()
+            g.close()
+    out["virtual_shards"].append({"P": P, "masks_flat": flat, "probes": "PartsOp + ProbeOp + CombineOp" if flat else "MasksOp",
+                                  "build_ms_min": min(builds[min(2, reps - 1):]), "build_ms_all": builds, "same_counts": same})
 print(json.dumps(out))
