@@ -391,15 +391,46 @@ __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long
 // in-place pointer jumping: A[u] = (ancestor, distance) is an invariant under any interleaving because every
 // 64-bit entry is read and written whole.  Each thread jumps up to JUMPS times per launch.
 constexpr int JUMPS = 4;
-__global__ void jump_kernel(unsigned long long *A, unsigned long long n2, unsigned long long *unresolved)
+// SUBLIST RANKING (Helman-JaJa; gb_tune rank_sublists): plain pointer jumping moves O(n log n) entries -- on C2 chains are ~3 000
+// vertices long, 4 launches over all 9.2 M oriented vertices, each at ~70 % of the L2's random-request rate (ncu, profiles/masks_r2r_*:
+// jump_kernel 0.22 + 0.22 + 0.13 + 0.04 ms).  Instead: (1) every head and every SPLITTER (1 interior vertex in 4, picked by a hash of
+// its index) walks forward along succ to the next splitter or the end of its chain and leaves (walker, steps) in every vertex it
+// passes -- one visit per vertex; (2) pointer jumping over the splitters alone, whose entries now form a list 4 x shorter with the
+// true distances (non-splitters leave at once: the predicate is arithmetic); (3) one more hop for everybody else.
+__device__ __forceinline__ bool is_splitter(unsigned int u) { return ((u * 0x9E3779B1u) >> 30) == 0; }
+
+__global__ void walk_sublists_kernel(BuildArrays B, unsigned long long *A)
+{
+    const unsigned long long uu = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (uu >= 2 * B.n) return;
+    const unsigned int u = (unsigned int)uu;
+    const unsigned int tag = a_tag(ld_cg_u64(A + u));
+    // heads were written by start_edges_kernel (RES, rank 0); an interior vertex is UNRES whoever wrote it last
+    if (!(tag == TAG_RES || (tag == TAG_UNRES && is_splitter(u)))) return;
+    unsigned int cur = u, d = 0;
+    for (;;) {
+        const unsigned int w = succ_of(B, cur);
+        // the successor of an interior vertex is the next interior vertex of its chain (in = out = 1, so cur is its only
+        // predecessor and this walker its only visitor) or the node that ends the chain
+        if (a_tag(ld_cg_u64(A + w)) != TAG_UNRES) break;
+        d++;
+        A[w] = a_make(TAG_UNRES, u, d); // a perfect cycle with one splitter closes on the walker itself: never resolves, like before
+        if (is_splitter(w)) break;
+        cur = w;
+    }
+}
+
+// which = 0: every vertex, 1: splitters only
+__global__ void jump_kernel(unsigned long long *A, unsigned long long n2, unsigned long long *unresolved, int which)
 {
     unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int pending = 0;
-    if (u < n2) {
+    if (u < n2 && (which == 0 || is_splitter((unsigned int)u))) {
         unsigned long long a = ld_cg_u64(A + u);
         if (a_tag(a) == TAG_UNRES) {
+            const int jumps = which ? 2 * JUMPS : JUMPS; // few threads are at work in a splitter round: more jumps, fewer launches
 #pragma unroll 1
-            for (int j = 0; j < JUMPS; j++) {
+            for (int j = 0; j < jumps; j++) {
                 unsigned long long ap = ld_cg_u64(A + a_ptr(a));
                 a = a_make(a_tag(ap), a_ptr(ap), (unsigned long long)a_dist(a) + a_dist(ap));
                 if (a_tag(a) != TAG_UNRES) break;
@@ -951,10 +982,16 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
     while ((1ull << (bound - 2)) < n2 + 1) bound++; // ceil(log2) + slack; each launch makes >= 1 jump
     GB_CUDA(cudaEventRecord(m->fev[2], st));
     unsigned long long pending = 1;
+    const bool sublists = g_tune.rank_sublists != 0;
+    if (sublists) LAUNCH(walk_sublists_kernel, n2, B, A.p);
     while (pending && rounds < bound) {
         GB_CUDA(cudaMemsetAsync(total.p + 2, 0, 8, st));
-        LAUNCH(jump_kernel, n2, A.p, n2, total.p + 2);
+        LAUNCH(jump_kernel, n2, A.p, n2, total.p + 2, sublists ? 1 : 0);
         GB_TRY(read_u64(total.p + 2, &pending, 1, st));
+        rounds++;
+    }
+    if (sublists) { // everybody else is one hop from a resolved walker (vertices of perfect cycles stay unresolved)
+        LAUNCH(jump_kernel, n2, A.p, n2, total.p + 2, 0);
         rounds++;
     }
     g->stats[1] = rounds;

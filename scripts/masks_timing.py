@@ -21,8 +21,9 @@ m.insert_reads(b, n)
 m.delete_below(3)
 out = {"workload": cfg, "scale": scale, "kept_kmers": m.size, "variants": []}
 ref = None
-for flat in (0, 1):
-    with capi.tuned(masks_flat=flat):
+VARIANTS = ((1, 1),) if os.environ.get("MT_ONLY") == "sublists" else ((0, 0), (1, 0), (1, 1))
+for flat, sub in VARIANTS:
+    with capi.tuned(masks_flat=flat, rank_sublists=sub):
         probes, builds, ranking = [], [], []
         for rep in range(reps):
             g = Graph.buildGraph(K, m)
@@ -30,20 +31,22 @@ for flat in (0, 1):
             probes.append(ph["graph_masks_ns"] * 1e-6)
             ranking.append(ph["graph_rank_ns"] * 1e-6)
             builds.append(g.stats()["build_ns"] * 1e-6)
+            g_launches = g.stats()["jump_launches"]
             counts = g.counts()
             if ref is None:
                 ref = (counts, sorted(int(x) for x in g.export()[0]))
             same = ref == (counts, sorted(int(x) for x in g.export()[0]))
             g.close()
         tail = slice(min(2, reps - 1), None)   # the first passes settle the arenas
-        out["variants"].append({"masks_flat": flat, "kernel": "masks_flat_kernel" if flat else "masks_kernel",
+        out["variants"].append({"masks_flat": flat, "rank_sublists": sub, "kernel": "masks_flat_kernel" if flat else "masks_kernel",
+                                "jump_launches": g_launches,
                                 "probes_ms_min": min(probes[tail]), "probes_ms_all": probes, "build_ms_min": min(builds[tail]),
                                 "ranking_ms_min": min(ranking[tail]), "counts": counts, "same_graph_as_first": same})
 P = int(os.environ.get("SG_P", "8"))
 out["virtual_shards"] = []
 for flat in (0, 1):
-    if reps == 1 and flat == 0:
-        continue                     # the ncu pass profiles the default form only
+    if (reps == 1 and flat == 0) or os.environ.get("MT_ONLY") == "sublists":
+        continue                     # the ncu passes profile one form only
     with capi.tuned(masks_flat=flat):
         builds = []
         for rep in range(reps):

@@ -175,11 +175,12 @@ GRAPH_CASES = [
 ]
 
 
-@pytest.fixture(params=["per-kmer", "per-probe"])
+@pytest.fixture(params=["per-kmer", "per-probe", "per-probe+sublists"])
 def masks_variant(request):
-    """Both forms of the membership probes of Graph.buildGraph: masks_kernel (one thread per stored k-mer, 8 probes each) and
-    masks_flat_kernel (one lane per probe, masks from the warp ballot)."""
-    with capi.tuned(masks_flat=int(request.param == "per-probe")):
+    """The forms of Graph.buildGraph's two heavy phases: membership probes by masks_kernel (one thread per stored k-mer, 8 probes
+    each) or masks_flat_kernel (one lane per probe, masks from the warp ballot); list ranking by plain pointer jumping or by
+    sublist walks + pointer jumping over the splitters."""
+    with capi.tuned(masks_flat=int(request.param != "per-kmer"), rank_sublists=int(request.param.endswith("sublists"))):
         yield request.param
 
 
@@ -209,7 +210,7 @@ def test_build_graph_matches_oracle(gpu, masks_variant, k, glen, rl, cov, err, r
 
 
 @pytest.mark.parametrize("k,glen,rl,cov,err,rounds", GRAPH_CASES)
-def test_graph_operators_match_oracle(gpu, k, glen, rl, cov, err, rounds):
+def test_graph_operators_match_oracle(gpu, masks_variant, k, glen, rl, cov, err, rounds):
     b, n, _ = H.small_reads(glen, rl, cov, err, seed=3000 + k)
 
     def fresh():
@@ -348,7 +349,7 @@ def test_canonical_rule_on_random_kmers(gpu):
         assert [int(v) for v in gv] == [exp[x] for x in sorted(exp)]
 
 
-def test_perfect_cycle_is_dropped(gpu):
+def test_perfect_cycle_is_dropped(gpu, masks_variant):
     """A circular sequence with no branch has no terminal k-mer: buildGraph yields nothing (Graph.scala:375)."""
     k = 11
     genome = synth.random_genome(500, 8)  # a seed without a repeated 10-mer on either strand
@@ -366,7 +367,7 @@ def test_perfect_cycle_is_dropped(gpu):
     assert g.stats()["cycle_vertices"] == 2 * genome.size
 
 
-def test_error_free_linear_genome_is_two_edges(gpu):
+def test_error_free_linear_genome_is_two_edges(gpu, masks_variant):
     """an error-free random linear genome gives exactly 4 nodes / 2 edges, and the two edges spell the
     genome and its reverse complement."""
     k = 31
