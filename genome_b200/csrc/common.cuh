@@ -48,9 +48,6 @@ struct Tuning {
     long long a2a = 0;                  // sharded insert: 0 = the bucket pass stores into the peers' inboxes (NVLink stores), 1 = staged
                                         // ncclSend/ncclRecv (what a box without peer access takes by itself)
     long long pgraph_sharded = 1;       // Graph.buildGraph over shards without a replica (sgraph.cuh); 0 = all-gather the shards, build replicated
-    long long masks_flat = 1;           // Graph.buildGraph membership probes: 1 = one lane / item per (k-mer, neighbour) (masks_flat_kernel; over
-                                        // shards PartsOp + ProbeOp + CombineOp), 0 = one thread per k-mer (masks_kernel, MasksOp)
-    long long rank_sublists = 0;        // Graph.buildGraph list ranking on one GPU: 1 = sublist walks + pointer jumping over splitters, 0 = plain pointer jumping
     long long trace = 0;                // phase timings on stderr
 };
 extern Tuning g_tune;

@@ -122,103 +122,24 @@ assign_vertices_kernel(Table table, int k, bool dual, const unsigned long long *
 }
 
 // incoming / outcoming (Graph.scala:272-282) of every stored key: 8 membership probes, either orientation.
+// incoming / outcoming (Graph.scala:272-282) of every stored k-mer: 8 membership probes (contains, Graph.scala:270).
 // mask8 = out | in << 4; nbr_out / nbr_in = the oriented neighbour when there is exactly one.
 // `check_secondary`: keys[] came from a compacted array, not from the numbering pass, so an entry may be the SECONDARY
 // orientation of a k-mer stored twice (hash tie / as-is inserts): it is no vertex (mask 0 = isolated, never referenced).
-template <bool V210>
-__global__ void __launch_bounds__(256)
-masks_kernel(Table table, int k, bool dual, const unsigned long long *keys, unsigned long long lo,
-             unsigned long long n, bool check_secondary, const uint8_t *fp, uint8_t *mask8, unsigned int *nbr_out, unsigned int *nbr_in)
-{
-    const unsigned long long cap = table.cap;
-    unsigned long long v = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= lo + n) return;
-    const unsigned long long x = keys[v];
-    unsigned int out = 0, in = 0, so = NONE32, si = NONE32;
-    if (check_secondary && is_secondary<V210>(table, k, dual, x, fp)) {
-        mask8[v] = 0;
-        nbr_out[v] = NONE32;
-        nbr_in[v] = NONE32;
-        return;
-    }
-    if (fp) {
-        // all 8 home fingerprints are fetched before the first one is looked at (they are L2 hits; 2 of 3 homes are
-        // empty at load 1/3, which settles most negative probes at once); only tag matches go to the table
-        unsigned long long cq[8], hm[8];
-        unsigned int tg[8], st[8], t0[8];
-        bool simple[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const unsigned long long q = j < 4 ? kmer_append(x, k, j) : kmer_prepend(x, k, j - 4);
-            const unsigned long long r = revcomp(q, k);
-            const int hq = scala_hash<V210>(q), hr = scala_hash<V210>(r);
-            simple[j] = !dual && hq != hr; // one stored orientation possible: the canonical one
-            cq[j] = hq < hr ? q : r;
-            st[j] = cq[j] != q;
-            const unsigned long long h = mix64(cq[j]);
-            hm[j] = slot_of(h, cap);
-            tg[j] = fp_tag(h);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++) t0[j] = fp[hm[j]];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            unsigned long long at = 0;
-            unsigned int strand = st[j];
-            bool found = false;
-            if (!simple[j]) {
-                const unsigned long long q = j < 4 ? kmer_append(x, k, j) : kmer_prepend(x, k, j - 4);
-                found = find_oriented<V210>(table, k, dual, q, &at, &strand, fp);
-            } else {
-                unsigned long long i = hm[j];
-                unsigned int t = t0[j];
-                while (t != 0) {
-                    if (t == tg[j] && load_key(table, i) == cq[j]) { found = true; at = i; break; }
-                    i = next_slot(i, cap);
-                    t = fp[i];
-                }
-            }
-            if (found) {
-                const unsigned int w = 2 * load_vid(table, at) + strand;
-                if (j < 4) { out |= 1u << j; so = w; }
-                else { in |= 1u << (j - 4); si = w; }
-            }
-        }
-        mask8[v] = (uint8_t)(out | (in << 4));
-        nbr_out[v] = so;
-        nbr_in[v] = si;
-        return;
-    }
-#pragma unroll
-    for (unsigned int b = 0; b < 4; b++) {
-        unsigned long long at;
-        unsigned int strand;
-        if (find_oriented<V210>(table, k, dual, kmer_append(x, k, b), &at, &strand)) {
-            out |= 1u << b;
-            so = 2 * load_vid(table, at) + strand;
-        }
-        if (find_oriented<V210>(table, k, dual, kmer_prepend(x, k, b), &at, &strand)) {
-            in |= 1u << b;
-            si = 2 * load_vid(table, at) + strand;
-        }
-    }
-    mask8[v] = (uint8_t)(out | (in << 4));
-    nbr_out[v] = so;
-    nbr_in[v] = si;
-}
-
-// The same probes with ONE LANE PER (stored k-mer, neighbour query): 8 consecutive lanes share a key (lane j < 4: successor by base
-// j, j >= 4: predecessor by base j - 4), so the warp's ballot of `found` holds the mask bytes of its 4 keys, and the unique
-// neighbour of a side comes from the lane that found it by one shuffle.  No 8-fold unrolled probe code (masks_kernel: 4 500 SASS
-// instructions, 64 registers, 40 % of the warps resident; here 26 registers, 85 %), 8 x the independent probes in flight per
-// resident thread: 1.36 -> 0.77 ms on C2 (profiles/r2r_masks_timing.json).  rc of a neighbour is one shift of rc(x):
+// ONE LANE PER (stored k-mer, neighbour query): 8 consecutive lanes share a key (lane j < 4: successor by base j, j >= 4:
+// predecessor by base j - 4), so the warp's ballot of `found` holds the mask bytes of its 4 keys, and the unique neighbour of a
+// side comes from the lane that found it by one shuffle.  Rounds 1-2 ran one THREAD per k-mer with its 8 probes unrolled (4 500
+// SASS instructions, 64 registers, 40 % of the warps resident, 1.36 ms on C2); this form: 26 registers, 83 % resident, 8 x the
+// independent probes in flight per resident thread, 0.60 ms (profiles/r2s_masks_timing.json, masks_r2r / masks_r2s ncu
+// summaries).  With the fingerprint array (`fp`, one byte per slot, L2-resident) a negative probe -- 3 of 4 -- ends on one byte.
+// rc of a neighbour is one shift of rc(x):
 // rc(x.drop(1) :+ b) = comp(b) +: rc(x).take(k-1), rc(b +: x.take(k-1)) = rc(x).drop(1) :+ comp(b) -- so successor and
 // predecessor lanes run the SAME instructions on swapped operands (A = (s.drop(1) :+ c), B = (comp(c) +: t.take(k-1)) with
 // (s, t, c) = (x, rc x, b) or (rc x, x, comp b): {A, B} = {q, rc q} either way), and the warp stays converged up to the probe
-// loop: the first form of this kernel branched on `rc(x) < x` and on `j < 4` and ran its body twice per warp (ncu source page).
+// loop: the first per-lane form branched on `rc(x) < x` and on `j < 4` and ran its body twice per warp (ncu source page; 0.77 ms).
 template <bool V210>
 __global__ void __launch_bounds__(256)
-masks_flat_kernel(Table table, int k, bool dual, const unsigned long long *keys, unsigned long long lo,
+masks_kernel(Table table, int k, bool dual, const unsigned long long *keys, unsigned long long lo,
                   unsigned long long n, bool check_secondary, const uint8_t *fp, uint8_t *mask8, unsigned int *nbr_out, unsigned int *nbr_in)
 {
     const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -252,7 +173,7 @@ masks_flat_kernel(Table table, int k, bool dual, const unsigned long long *keys,
     }
     const unsigned int byte = (__ballot_sync(0xFFFFFFFFu, found) >> group) & 0xFFu;
     const unsigned int out = byte & 0xFu, in = byte >> 4;
-    // the neighbour reference matters only when its side has exactly one bit; take the highest finder like masks_kernel does
+    // the neighbour reference matters only when its side has exactly one bit; any finder will do: take the highest
     const unsigned int so = __shfl_sync(0xFFFFFFFFu, w, out ? group + (31 - __clz(out)) : lane);
     const unsigned int si = __shfl_sync(0xFFFFFFFFu, w, in ? group + 4 + (31 - __clz(in)) : lane);
     if (live && j == 0) {
@@ -391,46 +312,15 @@ __device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long
 // in-place pointer jumping: A[u] = (ancestor, distance) is an invariant under any interleaving because every
 // 64-bit entry is read and written whole.  Each thread jumps up to JUMPS times per launch.
 constexpr int JUMPS = 4;
-// SUBLIST RANKING (Helman-JaJa; gb_tune rank_sublists): plain pointer jumping moves O(n log n) entries -- on C2 chains are ~3 000
-// vertices long, 4 launches over all 9.2 M oriented vertices, each at ~70 % of the L2's random-request rate (ncu, profiles/masks_r2r_*:
-// jump_kernel 0.22 + 0.22 + 0.13 + 0.04 ms).  Instead: (1) every head and every SPLITTER (1 interior vertex in 4, picked by a hash of
-// its index) walks forward along succ to the next splitter or the end of its chain and leaves (walker, steps) in every vertex it
-// passes -- one visit per vertex; (2) pointer jumping over the splitters alone, whose entries now form a list 4 x shorter with the
-// true distances (non-splitters leave at once: the predicate is arithmetic); (3) one more hop for everybody else.
-__device__ __forceinline__ bool is_splitter(unsigned int u) { return ((u * 0x9E3779B1u) >> 30) == 0; }
-
-__global__ void walk_sublists_kernel(BuildArrays B, unsigned long long *A)
-{
-    const unsigned long long uu = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (uu >= 2 * B.n) return;
-    const unsigned int u = (unsigned int)uu;
-    const unsigned int tag = a_tag(ld_cg_u64(A + u));
-    // heads were written by start_edges_kernel (RES, rank 0); an interior vertex is UNRES whoever wrote it last
-    if (!(tag == TAG_RES || (tag == TAG_UNRES && is_splitter(u)))) return;
-    unsigned int cur = u, d = 0;
-    for (;;) {
-        const unsigned int w = succ_of(B, cur);
-        // the successor of an interior vertex is the next interior vertex of its chain (in = out = 1, so cur is its only
-        // predecessor and this walker its only visitor) or the node that ends the chain
-        if (a_tag(ld_cg_u64(A + w)) != TAG_UNRES) break;
-        d++;
-        A[w] = a_make(TAG_UNRES, u, d); // a perfect cycle with one splitter closes on the walker itself: never resolves, like before
-        if (is_splitter(w)) break;
-        cur = w;
-    }
-}
-
-// which = 0: every vertex, 1: splitters only
-__global__ void jump_kernel(unsigned long long *A, unsigned long long n2, unsigned long long *unresolved, int which)
+__global__ void jump_kernel(unsigned long long *A, unsigned long long n2, unsigned long long *unresolved)
 {
     unsigned long long u = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int pending = 0;
-    if (u < n2 && (which == 0 || is_splitter((unsigned int)u))) {
+    if (u < n2) {
         unsigned long long a = ld_cg_u64(A + u);
         if (a_tag(a) == TAG_UNRES) {
-            const int jumps = which ? 2 * JUMPS : JUMPS; // few threads are at work in a splitter round: more jumps, fewer launches
 #pragma unroll 1
-            for (int j = 0; j < jumps; j++) {
+            for (int j = 0; j < JUMPS; j++) {
                 unsigned long long ap = ld_cg_u64(A + a_ptr(a));
                 a = a_make(a_tag(ap), a_ptr(ap), (unsigned long long)a_dist(a) + a_dist(ap));
                 if (a_tag(a) != TAG_UNRES) break;
@@ -930,10 +820,7 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
         const unsigned long long lo = sp ? sp->lo : 0, cnt = sp ? sp->hi - sp->lo : n;
         // the fingerprint array is built together with the vertex array (deleteAll / replica insert)
         const uint8_t *fp = given ? m->fp : nullptr;
-        if (g_tune.masks_flat)
-            LAUNCH(masks_flat_kernel<V210>, 8 * cnt, m->view(), k, dual, keys.p, lo, cnt, given, fp, mask8.p, nbr_out.p, nbr_in.p);
-        else
-            LAUNCH(masks_kernel<V210>, cnt, m->view(), k, dual, keys.p, lo, cnt, given, fp, mask8.p, nbr_out.p, nbr_in.p);
+        LAUNCH(masks_kernel<V210>, 8 * cnt, m->view(), k, dual, keys.p, lo, cnt, given, fp, mask8.p, nbr_out.p, nbr_in.p); // a lane per probe
         GB_CUDA(cudaEventRecord(m->fev[1], st));
         if (sp) {
             GB_CUDA(cudaStreamSynchronize(st));
@@ -982,16 +869,10 @@ static int build_graph(Map *m, Graph *g, const ShardPlan *sp)
     while ((1ull << (bound - 2)) < n2 + 1) bound++; // ceil(log2) + slack; each launch makes >= 1 jump
     GB_CUDA(cudaEventRecord(m->fev[2], st));
     unsigned long long pending = 1;
-    const bool sublists = g_tune.rank_sublists != 0;
-    if (sublists) LAUNCH(walk_sublists_kernel, n2, B, A.p);
     while (pending && rounds < bound) {
         GB_CUDA(cudaMemsetAsync(total.p + 2, 0, 8, st));
-        LAUNCH(jump_kernel, n2, A.p, n2, total.p + 2, sublists ? 1 : 0);
+        LAUNCH(jump_kernel, n2, A.p, n2, total.p + 2);
         GB_TRY(read_u64(total.p + 2, &pending, 1, st));
-        rounds++;
-    }
-    if (sublists) { // everybody else is one hop from a resolved walker (vertices of perfect cycles stay unresolved)
-        LAUNCH(jump_kernel, n2, A.p, n2, total.p + 2, 0);
         rounds++;
     }
     g->stats[1] = rounds;

@@ -1293,7 +1293,7 @@ static long long *tune_field(const char *name)
         { "insert_path", &Tuning::insert_path }, { "single_pass", &Tuning::single_pass }, { "single_pass_min", &Tuning::single_pass_min },
         { "slice_bits", &Tuning::slice_bits }, { "batches", &Tuning::batches }, { "h2d_chunks", &Tuning::h2d_chunks },
         { "route", &Tuning::route }, { "a2a", &Tuning::a2a },
-        { "pgraph_sharded", &Tuning::pgraph_sharded }, { "masks_flat", &Tuning::masks_flat }, { "rank_sublists", &Tuning::rank_sublists }, { "trace", &Tuning::trace },
+        { "pgraph_sharded", &Tuning::pgraph_sharded }, { "trace", &Tuning::trace },
     };
     if (name)
         for (const auto &e : table)

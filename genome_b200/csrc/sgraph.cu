@@ -156,7 +156,7 @@ static int build_with(sg::Fabric &fab, Map *const *maps, const std::vector<std::
         }
     }
     sg::Result res;
-    const int rc = sg::build(fab, in, k, dual, v210, &res, g_tune.masks_flat != 0);
+    const int rc = sg::build(fab, in, k, dual, v210, &res);
     if (rc != GB_OK) return fail(rc);
     if (cudaEventRecord(ev1, stream) != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) { set_error("sharded build failed on the device"); return fail(GB_E_CUDA); }
     float ms = 0;

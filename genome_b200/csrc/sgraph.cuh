@@ -151,7 +151,7 @@ SG_HD int khash(const Ctx &c, u64 v) { return c.v210 ? scala_hash<true>(v) : sca
 // 0 .. w-2 and add one at the front, so the 8 neighbour owners cost one m-mer hash each.
 constexpr u32 H_NONE = 0xFFFFFFFFu;
 // 32-bit finalizer (murmur3 fmix32): the m-mer hashes are the inner loop of the owner function (21 per k-mer, 8 more for its
-// neighbours), and an m-mer has at most 22 bits -- 64-bit multiplies here made MasksOp three times as long as the single-GPU kernel
+// neighbours), and an m-mer has at most 22 bits -- 64-bit multiplies here made the probes three times as long as the single-GPU kernel
 SG_HD u32 fmix32(u32 h)
 {
     h ^= h >> 16;
@@ -226,7 +226,7 @@ SG_HD u32 neighbour_owner(const MinParts &mp, u64 x, u64 rcx, int k, int m, int 
 }
 
 // ---- membership in one rank's index
-// the probe from slot i on, with the tag of slot i already loaded (t8): MasksOp fetches the 8 home tags of a key together
+// the probe from slot i on, with the tag of slot i already loaded (t8)
 SG_HD bool probe_from(const Peer &t, u64 key, u32 tg, u64 i, u32 t8, u32 *vid)
 {
     for (;;) {
@@ -354,66 +354,12 @@ struct IndexInsertOp { // putNew of entry i: first free slot from the key's home
         tag[s] = (u8)fp_tag(h);
     }
 };
-struct MasksOp { // incoming / outcoming (Graph.scala:272-282) of every stored key
-    Ctx c; u8 *mask8; u32 *nbr_out, *nbr_in;
-    SG_HD void operator()(u64 v) const
-    {
-        const Peer &me = c.peer[c.me];
-        const u64 x = me.keys[v];
-        u32 out = 0, in = 0, so = NONE32, si = NONE32;
-        if (!is_secondary(c, me, x)) { // a secondary orientation is no vertex: mask 0 = isolated, never referenced
-            const u64 rcx = revcomp(x, c.k);
-            const MinParts mp = min_parts(x, rcx, c.k, c.m);
-            // the 8 queries first (j = 2b: successor by base b, 2b + 1: predecessor), then their 8 home tags in flight
-            // together -- the owner's index may sit behind an NVLink load -- then the (few) probes that go on
-            u64 cq[8];                 // the orientation to look up (canonical unless the hashes tie or keys are dual)
-            u32 home[8], meta[8], t8[8]; // meta: owner | tag << 8 | strand << 16 | generic << 17
-#pragma unroll
-            for (u32 j = 0; j < 8; j++) {
-                const Neighbour nb = neighbour_of(mp, x, rcx, c.k, c.m, c.P, (j & 1) == 0, j >> 1);
-                const int hq = khash(c, nb.q), hr = khash(c, nb.rq);
-                if (!c.dual && hq != hr) {
-                    cq[j] = hq < hr ? nb.q : nb.rq;
-                    const u64 h = mix64(cq[j]);
-                    home[j] = (u32)slot_of(h, c.peer[nb.owner].cap); // cap < 2^32: a rank holds fewer than 2^30 keys
-                    meta[j] = nb.owner | (fp_tag(h) << 8) | ((u32)(cq[j] != nb.q) << 16);
-                } else {
-                    cq[j] = nb.q;
-                    home[j] = 0;
-                    meta[j] = nb.owner | (1u << 17);
-                }
-            }
-#pragma unroll
-            for (u32 j = 0; j < 8; j++) {
-                const Peer &t = c.peer[meta[j] & 0xFF];
-                t8[j] = (meta[j] >> 17) || t.n == 0 ? 0u : (u32)t.tag[home[j]];
-            }
-#pragma unroll
-            for (u32 j = 0; j < 8; j++) {
-                const u32 owner = meta[j] & 0xFF;
-                u32 g = 0;
-                bool found;
-                if (meta[j] >> 17) {
-                    found = find_g(c, owner, cq[j], revcomp(cq[j], c.k), &g);
-                } else {
-                    u32 vid = 0;
-                    found = probe_from(c.peer[owner], cq[j], (meta[j] >> 8) & 0xFF, home[j], t8[j], &vid);
-                    g = g_make(c, owner, 2 * vid + ((meta[j] >> 16) & 1));
-                }
-                if (!found) continue;
-                if ((j & 1) == 0) { out |= 1u << (j >> 1); so = g; } else { in |= 1u << (j >> 1); si = g; }
-            }
-        }
-        mask8[v] = (u8)(out | (in << 4));
-        nbr_out[v] = so;
-        nbr_in[v] = si;
-    }
-};
-// The same probes with ONE ITEM PER (stored key, neighbour query) -- the default: MasksOp keeps 8 queries in the registers of one
-// thread (76 registers, a third of the warps resident, profiles/masks_r2r_*), which hides little of the latency of a probe that
-// goes to a peer's index over NVLink.  Here a key's minimizer parts are computed once (PartsOp), every query is an item of its
-// own (ProbeOp: 8 consecutive items = 8 consecutive lanes share a key) and a third sweep folds the 8 answers of a key into its mask
-// byte and unique neighbours (CombineOp: one 32-byte read per key).
+// incoming / outcoming (Graph.scala:272-282) of every stored key with ONE ITEM PER (stored key, neighbour query).  The first form
+// (MasksOp, rounds 2a-2q) kept the 8 queries of a key in the registers of one thread: 76 registers, a third of the warps resident
+// (profiles/masks_r2r_ncu_full_summary.csv), which hides little of the latency of a probe that goes to a peer's index over
+// NVLink.  Here a key's minimizer parts are computed once (PartsOp), every query is an item of its own (ProbeOp: 8 consecutive
+// items = 8 consecutive lanes share a key, 26 registers) and a third sweep folds the 8 answers of a key into its mask byte and
+// unique neighbours (CombineOp: one 32-byte read per key).  Per rank of 8 virtual ranks on C2: 0.229 -> 0.018 + 0.094 + 0.009 ms.
 struct PartsOp { // per stored key: is it a vertex at all (a secondary orientation is not), and the parts of its minimizer
     Ctx c; u32 *parts; u8 *skip;
     SG_HD void operator()(u64 v) const
@@ -683,7 +629,7 @@ inline size_t base_words(u64 n_bases) { return (size_t)((n_bases + 15) / 16) + 2
 
 // One sharded build.  in[l] belongs to rank fab.mine[l]; the resulting graph (identical on every process) is allocated
 // through in[0].ex.  Collective: every process of the fabric calls it with the same k / dual / v210.
-inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual, bool v210, Result *res, bool per_probe = true)
+inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual, bool v210, Result *res)
 {
     const int P = fab.P, nl = (int)fab.mine.size();
     if (P < 1 || P > MAXR || nl < 1 || (int)in.size() != nl) { set_error("sharded build: bad rank set"); return GB_E_ARG; }
@@ -785,18 +731,14 @@ inline int build(Fabric &fab, const std::vector<RankInput> &in, int k, bool dual
         GB_TRY(sg_new(ex, &nbr_out[l], (size_t)n));
         GB_TRY(sg_new(ex, &nbr_in[l], (size_t)n));
         u8 *mask8 = (u8 *)ctx[l].peer[ctx[l].me].mask8;
-        if (per_probe) {
-            u32 *parts = nullptr, *found = nullptr;
-            u8 *skip = nullptr;
-            GB_TRY(sg_new(ex, &parts, 3 * (size_t)n));
-            GB_TRY(sg_new(ex, &skip, (size_t)n));
-            GB_TRY(sg_new(ex, &found, 8 * (size_t)n));
-            GB_TRY(sg_launch(ex, n, PartsOp{ ctx[l], parts, skip }));
-            GB_TRY(sg_launch(ex, 8 * n, ProbeOp{ ctx[l], parts, skip, found }));
-            GB_TRY(sg_launch(ex, n, CombineOp{ found, mask8, nbr_out[l], nbr_in[l] }));
-        } else {
-            GB_TRY(sg_launch(ex, n, MasksOp{ ctx[l], mask8, nbr_out[l], nbr_in[l] }));
-        }
+        u32 *parts = nullptr, *found = nullptr;
+        u8 *skip = nullptr;
+        GB_TRY(sg_new(ex, &parts, 3 * (size_t)n));
+        GB_TRY(sg_new(ex, &skip, (size_t)n));
+        GB_TRY(sg_new(ex, &found, 8 * (size_t)n));
+        GB_TRY(sg_launch(ex, n, PartsOp{ ctx[l], parts, skip }));
+        GB_TRY(sg_launch(ex, 8 * n, ProbeOp{ ctx[l], parts, skip, found }));
+        GB_TRY(sg_launch(ex, n, CombineOp{ found, mask8, nbr_out[l], nbr_in[l] }));
         loc[l] = Local{ nbr_out[l], nbr_in[l], nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0 };
     }
     GB_TRY(fab.barrier());

@@ -63,8 +63,7 @@ int gb_bench_l2_requests(int device, size_t region_bytes, int64_t n_updates, int
  * its data path: every default is a measured choice, and the parity tests use these keys to force a path that
  * small inputs would not take by themselves.  Keys: insert_path (0 auto, 1 direct, 2 L2-blocked), single_pass,
  * single_pass_min, slice_bits, batches, h2d_chunks, route (0 auto, 1 one level, 2 two levels), a2a (0 peer stores, 1 NCCL staged),
- * pgraph_sharded (1 = Graph.buildGraph over shards without a replica, the default; 0 = replicated after an all-gather),
- * masks_flat (membership probes of Graph.buildGraph: 1 = one lane per (k-mer, neighbour), the default; 0 = one thread per k-mer), trace.
+ * pgraph_sharded (1 = Graph.buildGraph over shards without a replica, the default; 0 = replicated after an all-gather), trace.
  * *previous (optional) receives the old value. */
 int gb_tune(const char *name, int64_t value, int64_t *previous);
 int gb_tune_get(const char *name, int64_t *value);
@@ -184,7 +183,7 @@ int gb_graph_remove_edges(gb_graph *g, const uint32_t *edge_idx, int64_t n);
  *                                        replacements and new edges may name the new nodes;
  *   removeNode (185-187): the listed nodes are dropped; like the reference's it does not touch edges, so a node that an edge
  *                                        still starts or ends at is refused (GB_E_INVARIANT; the earlier steps stay applied).
- * Every array is a host array; any count may be 0.  (Written after this round's GPU budget was spent: device test opt-in.) */
+ * Every array is a host array; any count may be 0. */
 int gb_graph_edit(gb_graph *g, int64_t n_replace, const uint32_t *edge_idx, const uint32_t *new_start, const uint32_t *new_end,
                   int64_t n_add_nodes, const uint64_t *add_node_kmers, int64_t n_add_edges, const uint32_t *add_start,
                   const uint32_t *add_end, const uint64_t *add_off, const uint8_t *add_bases, int64_t n_remove_nodes,

@@ -198,8 +198,6 @@ struct CallbackFabric : Fabric {
 
 extern "C" {
 
-// `v210` below carries two flags: bit 0 = scala >= 2.10 hash, bit 1 = membership probes in the one-thread-per-k-mer form (MasksOp)
-// instead of the default one-item-per-probe form (PartsOp + ProbeOp + CombineOp)
 // this process's rank of a build whose fabric is `cb`; two-call pattern like emul_sharded_build (sizes first)
 int emul_sharded_build_rank(int k, int dual, int v210, int P, int rank, const uint64_t *keys, uint64_t n, const EmulFabricCallbacks *cb,
                             uint64_t *out, uint64_t *node_kmer, uint32_t *edge_start, uint32_t *edge_end, uint64_t *edge_off, uint32_t *bases)
@@ -208,7 +206,7 @@ int emul_sharded_build_rank(int k, int dual, int v210, int P, int rank, const ui
     CallbackFabric fab(*cb, P, rank);
     std::vector<RankInput> in{ RankInput{ &ex, (const u64 *)keys, n } };
     Result res;
-    const int rc = build(fab, in, k, dual != 0, (v210 & 1) != 0, &res, (v210 & 2) == 0);
+    const int rc = build(fab, in, k, dual != 0, v210 != 0, &res);
     if (rc != GB_OK) return rc;
     out[0] = res.n_nodes; out[1] = res.n_edges; out[2] = res.n_bases;
     out[3] = res.kept; out[4] = res.segments; out[5] = res.cycle_vertices; out[6] = (uint64_t)res.jump_rounds; out[7] = (uint64_t)res.seg_rounds;
@@ -236,7 +234,7 @@ int emul_sharded_build_threads(int k, int dual, int v210, int P, const uint64_t 
         th.emplace_back([&, r] {
             ThreadFabric fab(hub, ex[(size_t)r], r);
             std::vector<RankInput> in{ RankInput{ &ex[(size_t)r], (const u64 *)keys + off[r], off[r + 1] - off[r] } };
-            rcs[(size_t)r] = build(fab, in, k, dual != 0, (v210 & 1) != 0, &res[(size_t)r], (v210 & 2) == 0);
+            rcs[(size_t)r] = build(fab, in, k, dual != 0, v210 != 0, &res[(size_t)r]);
         });
     for (auto &t : th) t.join();
     for (int r = 0; r < P; r++)
@@ -277,7 +275,7 @@ int emul_sharded_build(int k, int dual, int v210, int P, const uint64_t *keys, c
     }
     LocalFabric fab(P, pex);
     Result res;
-    const int rc = build(fab, in, k, dual != 0, (v210 & 1) != 0, &res, (v210 & 2) == 0);
+    const int rc = build(fab, in, k, dual != 0, v210 != 0, &res);
     if (rc != GB_OK) return rc;
     out[0] = res.n_nodes; out[1] = res.n_edges; out[2] = res.n_bases;
     out[3] = res.kept; out[4] = res.segments; out[5] = res.cycle_vertices; out[6] = (uint64_t)res.jump_rounds; out[7] = (uint64_t)res.seg_rounds;

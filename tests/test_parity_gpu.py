@@ -175,17 +175,8 @@ GRAPH_CASES = [
 ]
 
 
-@pytest.fixture(params=["per-kmer", "per-probe", "per-probe+sublists"])
-def masks_variant(request):
-    """The forms of Graph.buildGraph's two heavy phases: membership probes by masks_kernel (one thread per stored k-mer, 8 probes
-    each) or masks_flat_kernel (one lane per probe, masks from the warp ballot); list ranking by plain pointer jumping or by
-    sublist walks + pointer jumping over the splitters."""
-    with capi.tuned(masks_flat=int(request.param != "per-kmer"), rank_sublists=int(request.param.endswith("sublists"))):
-        yield request.param
-
-
 @pytest.mark.parametrize("k,glen,rl,cov,err,rounds", GRAPH_CASES)
-def test_build_graph_matches_oracle(gpu, masks_variant, k, glen, rl, cov, err, rounds):
+def test_build_graph_matches_oracle(gpu, k, glen, rl, cov, err, rounds):
     b, n, _ = H.small_reads(glen, rl, cov, err, seed=2000 + k)
     data = PairedEndData(b, n // 2)
     gm = FreqFilter.extractFilteredKmers(data, k, rounds)
@@ -210,7 +201,7 @@ def test_build_graph_matches_oracle(gpu, masks_variant, k, glen, rl, cov, err, r
 
 
 @pytest.mark.parametrize("k,glen,rl,cov,err,rounds", GRAPH_CASES)
-def test_graph_operators_match_oracle(gpu, masks_variant, k, glen, rl, cov, err, rounds):
+def test_graph_operators_match_oracle(gpu, k, glen, rl, cov, err, rounds):
     b, n, _ = H.small_reads(glen, rl, cov, err, seed=3000 + k)
 
     def fresh():
@@ -272,7 +263,7 @@ def test_remove_edges_then_simplify(gpu):
     g.check()
 
 
-def test_noncanonical_keys_both_orientations(gpu, masks_variant):
+def test_noncanonical_keys_both_orientations(gpu):
     """Keys pushed through update as they are: both orientations of a k-mer can be stored (like a hash tie,
     SURVEY Q3); contains() probes both, nodes are a SET of oriented k-mers."""
     k = 9
@@ -296,7 +287,7 @@ def test_noncanonical_keys_both_orientations(gpu, masks_variant):
 
 
 @pytest.mark.parametrize("strands", ["both", "forward"])
-def test_hash_tie_kmers_in_real_reads(gpu, insert_path, masks_variant, strands):
+def test_hash_tie_kmers_in_real_reads(gpu, insert_path, strands):
     """x with hash(x) == hash(rc x), x != rc x (even k >= 18 only, tests/golden/hash_ties.json): a read of x stores rc(x) and a
     read of rc(x) stores x (FreqFilter.scala:32: tie => rcx).  Reads of both strands leave BOTH orientations in the table of a map
     that is not `dual`: the insert's tie rule, contains() probing both orientations and the primary / secondary orientation of
@@ -349,7 +340,7 @@ def test_canonical_rule_on_random_kmers(gpu):
         assert [int(v) for v in gv] == [exp[x] for x in sorted(exp)]
 
 
-def test_perfect_cycle_is_dropped(gpu, masks_variant):
+def test_perfect_cycle_is_dropped(gpu):
     """A circular sequence with no branch has no terminal k-mer: buildGraph yields nothing (Graph.scala:375)."""
     k = 11
     genome = synth.random_genome(500, 8)  # a seed without a repeated 10-mer on either strand
@@ -367,7 +358,7 @@ def test_perfect_cycle_is_dropped(gpu, masks_variant):
     assert g.stats()["cycle_vertices"] == 2 * genome.size
 
 
-def test_error_free_linear_genome_is_two_edges(gpu, masks_variant):
+def test_error_free_linear_genome_is_two_edges(gpu):
     """an error-free random linear genome gives exactly 4 nodes / 2 edges, and the two edges spell the
     genome and its reverse complement."""
     k = 31

@@ -41,7 +41,7 @@ def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def sharded_build(emul, k, keys, P, dual=False, split="even", seed=0, threads=False, per_key_probes=False):
+def sharded_build(emul, k, keys, P, dual=False, split="even", seed=0, threads=False):
     """Runs the emulated build with the kept keys dealt to P ranks (`split`: even / skewed / all on the last rank) and
     returns (canonical graph as in tests/helpers.py, stats dict)."""
     keys = np.ascontiguousarray(keys, np.uint64)
@@ -57,8 +57,7 @@ def sharded_build(emul, k, keys, P, dual=False, split="even", seed=0, threads=Fa
     off = np.array(cuts, np.uint64)
     out = np.zeros(8, np.uint64)
     fn = emul.emul_sharded_build_threads if threads else emul.emul_sharded_build
-    flags = 2 if per_key_probes else 0   # bit 1: MasksOp (one thread per k-mer) instead of the per-probe ops
-    rc = fn(k, int(dual), flags, P, ptr(keys), ptr(off), ptr(out), None, None, None, None, None)
+    rc = fn(k, int(dual), 0, P, ptr(keys), ptr(off), ptr(out), None, None, None, None, None)
     assert rc == 0, rc
     N, E, B = int(out[0]), int(out[1]), int(out[2])
     node_kmer = np.zeros(max(N, 1), np.uint64)
@@ -66,7 +65,7 @@ def sharded_build(emul, k, keys, P, dual=False, split="even", seed=0, threads=Fa
     ee = np.zeros(max(E, 1), np.uint32)
     eo = np.zeros(E + 1, np.uint64)
     words = np.zeros((B + 15) // 16 + 1, np.uint32)
-    rc = fn(k, int(dual), flags, P, ptr(keys), ptr(off), ptr(out), ptr(node_kmer), ptr(es), ptr(ee), ptr(eo), ptr(words))
+    rc = fn(k, int(dual), 0, P, ptr(keys), ptr(off), ptr(out), ptr(node_kmer), ptr(es), ptr(ee), ptr(eo), ptr(words))
     assert rc == 0
     bases = np.zeros(words.size * 16, np.uint8)
     for j in range(16):
@@ -134,9 +133,6 @@ def test_sharded_build_matches_oracle(emul, k, glen, rl, cov, err, rounds):
         assert st["kept"] == keys.size
         if P == 1:
             assert st["segments"] == 0
-    for P in (1, 3, 8):   # the one-thread-per-k-mer form of the membership probes (MasksOp)
-        got, counts, st = sharded_build(emul, k, keys, P, split="skewed", seed=P, per_key_probes=True)
-        assert counts == og.counts() and got == want, ("per-key probes", P)
 
 
 def test_segments_are_a_small_fraction(emul):
@@ -355,7 +351,6 @@ def test_sharded_build_with_hash_tie_kmers(emul, strands):
         want = H.canon_oracle_graph(og)
         assert og.counts()[1] > 0
         for P, split in [(1, "even"), (2, "even"), (3, "skewed"), (8, "even")]:
-            for per_key in (False, True):
-                got, counts, st = sharded_build(emul, k, keys, P, split=split, seed=P, per_key_probes=per_key)
-                assert counts == og.counts(), (k, P, split, per_key)
-                assert got == want, (k, P, split, per_key)
+            got, counts, st = sharded_build(emul, k, keys, P, split=split, seed=P)
+            assert counts == og.counts(), (k, P, split)
+            assert got == want, (k, P, split)

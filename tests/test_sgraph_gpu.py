@@ -17,16 +17,6 @@ from tests.test_sgraph_emul_cpu import GRAPH_CASES
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["per-probe", "per-kmer", "per-probe+sublists"], autouse=True)
-def probes_variant(request):
-    """Both forms of the membership probes: one item per (k-mer, neighbour) -- PartsOp + ProbeOp + CombineOp over shards,
-    masks_flat_kernel on one GPU (the default) -- and one thread per k-mer (MasksOp / masks_kernel); and, for the single-GPU
-    builds these tests compare with, both forms of the list ranking (plain pointer jumping / sublist walks)."""
-    from genome_b200 import capi
-    with capi.tuned(masks_flat=int(request.param != "per-kmer"), rank_sublists=int(request.param.endswith("sublists"))):
-        yield request.param
-
-
 @pytest.mark.parametrize("k,glen,rl,cov,err,rounds", GRAPH_CASES)
 def test_virtual_shards_match_oracle(gpu, k, glen, rl, cov, err, rounds):
     b, n, _ = H.small_reads(glen, rl, cov, err, seed=2000 + k)
