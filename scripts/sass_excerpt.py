@@ -12,7 +12,7 @@ LIB = os.path.join(ROOT, "genome_b200", "libgenome_b200.so")
 WANT = sys.argv[1:] or ["bucket_slabs_kernelILb1ELb0ELi5ELb0E", "bucket_slabs_kernelILb1ELb0ELi7ELb1E", "insert_slabs_kernelIjLb0E", "insert_slabs_kernelIjLb1E",
                         "part_scatter_kernelILb1ELb0ELb0ELb1E", "part_count_kernelILb1ELb0ELb0E", "insert_keys_kernelILb0EjE",
                         "insert_reads_kernelILb1ELb0E", "place_distinct_kernel", "compact_survivors_kernel", "init_table_kernel", "masks_kernelILb0E",
-                        "jump_kernel"]
+                        "jump_kernel", "items_kernelINS0_7ProbeOpE", "items_kernelINS0_7PartsOpE", "items_kernelINS0_9CombineOpE"]
 MEM = re.compile(r"\b(LDG|STG|LDS|STS|LDSM|ATOM|ATOMG|ATOMS|RED|REDG|REDUX|MATCH|VOTE|BAR|LDC|LDGSTS|UBLKCP|UTMALDG|CCTL|MEMBAR|SHFL|WARPSYNC)\b")
 
 
