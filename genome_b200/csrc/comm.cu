@@ -11,7 +11,7 @@
 //     [two-level routing only: re-bucket the received keys by fine table slice]
 //     insert_keys_kernel        : update(key, 1, _ + 1) for the received keys, slice by slice (L2-blocked)
 // Three inbox/buffer sets; batch b + 1 is bucketed and exchanged while batch b is upserted.
-// GENOME_B200_A2A=nccl replaces the peer stores by staged ncclSend/ncclRecv segments (the baseline).
+// gb_tune a2a = 1 replaces the peer stores by staged ncclSend/ncclRecv segments (what a box without peer access takes).
 #include <dlfcn.h>
 #include <time.h>
 #include <nccl.h> // types only: the library is bound at run time (see NcclApi)
@@ -1112,8 +1112,8 @@ int gb_pmap_graph_build(gb_map *h, gb_graph **out)
     int64_t total = m->size, dual = m->noncanonical;
     GB_TRY(all_reduce_i64(c, &total, ncclSum));
     GB_TRY(all_reduce_i64(c, &dual, ncclMax));
-    // GENOME_B200_PGRAPH=sharded: no replica -- minimizer re-routing, rank-local list ranking, segment list (sgraph.cuh).
-    // Needs peer access between all ranks; every rank reads the same environment, so the choice is collective.
+    // gb_tune pgraph_sharded (the default): no replica -- minimizer re-routing, rank-local list ranking, segment list (sgraph.cuh).
+    // Needs peer access between all ranks; the tuning key is process-wide and set alike on every rank, so the choice is collective.
     if (g_tune.pgraph_sharded && P <= sg::MAXR) {
         GB_TRY(ensure_inboxes(c, 0)); // settles c->p2p (collective)
         if (c->p2p == 1) {

@@ -579,7 +579,7 @@ static int insert_partitioned(Map *m, const uint8_t *d_bin, size_t n_bytes, cons
     // sub-batches of whole persistent-grid waves of tiles, about four of them
     const int64_t tiles = (n_reads + TILE_READS - 1) / TILE_READS, grid = work[0]->grid;
     // measured on C2 (one B200): 1 / 2 / 4 / 8 sub-batches = 2.95 / 3.13 / 3.20 / 3.93 ms -- on ONE GPU the two passes
-    // fight for the same SM slots and L2, so the default is no overlap; GENOME_B200_BATCHES turns the pipeline on
+    // fight for the same SM slots and L2, so the default is no overlap; gb_tune batches turns the pipeline on
     const int want = (int)std::max<long long>(1, g_tune.batches);
     int64_t per_tiles = std::max<int64_t>(1, (tiles / want + grid / 2) / grid) * grid;
     if (tiles < 2 * grid || want == 1) per_tiles = tiles;
@@ -1056,7 +1056,7 @@ int gb_map_insert_reads(gb_map *h, const uint8_t *bin, size_t n_bytes, int64_t n
     // i*rec imply the record chain is i*rec).  Otherwise scan the chain on the host.
     unsigned int len0 = bin[0], rec = 1 + (len0 + 3) / 4;
     bool try_fixed = (unsigned long long)n_reads * rec <= n_bytes;
-    if (try_fixed) { // opt-in: chunked copy overlapped with the single-pass bucket pass
+    if (try_fixed) { // chunked copy overlapped with the single-pass bucket pass (when the batch qualifies: *handled)
         bool handled = false;
         GB_TRY(insert_host_pipelined(m, bin, n_reads, rec, len0, n_windows, &handled));
         if (handled) return GB_OK;

@@ -754,7 +754,7 @@ int part_scatter_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, un
     return GB_OK;
 }
 
-// ---- the single-pass variant (GENOME_B200_COUNTLESS=1)
+// ---- the single-pass variant (gb_tune single_pass, the default for large batches)
 // keys per (bucket, CTA) slab.  A CTA takes every grid-th tile, so what it can see is bounded by its number of tiles, not by
 // total / grid (a batch with fewer tiles than CTAs leaves most CTAs idle and the busy ones with a whole tile each):
 // cta_keys = tiles per CTA x reads per tile x windows per read; the slab is that share of one bucket plus 8 standard

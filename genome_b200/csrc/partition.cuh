@@ -76,7 +76,7 @@ int part_scatter_keys(const KeySource &ks, const PartLayout &pl, PartWork &w, un
 int insert_key_chunks(Map *m, const unsigned long long *d_keys, const unsigned long long *d_vstart, const unsigned long long *d_off,
                       int n_chunks, unsigned long long n_total, cudaStream_t st, bool total_is_upper_bound = false);
 
-// the single-pass bucket pass (no count pass; GENOME_B200_COUNTLESS=1, single-GPU insert): see part_scatter_kernel<..., SLABS>
+// the single-pass bucket pass (no count pass; gb_tune single_pass): see bucket_slabs_kernel
 unsigned int slab_keys_for(unsigned long long cta_keys, unsigned int nb, int grid);
 unsigned long long slab_cta_keys(long long n_reads, unsigned long long windows, int grid);
 // the same in LIST mode for the chunked host insert: begin / one launch per read range / end (see partition.cu)

@@ -5,10 +5,10 @@
 //   gb_graph_build_virtual_shards    the same build over P VIRTUAL ranks on one device (LocalFabric): the kept k-mers of a
 //                                    single-GPU map are dealt to P ranks that live in one address space.  This is how the
 //                                    device code of the sharded build is validated (and profiled) on a single GPU.
-// Status: written after this round's GPU budget was spent.  The algorithm (functors + orchestration, the code compiled here)
-// is checked against the oracle by tests/test_sgraph_emul_cpu.py through a g++ backend; the device tests are opt-in
-// (tests/test_sgraph_gpu.py, GENOME_B200_UNVALIDATED=1) and gb_pmap_graph_build keeps the replicated build unless
-// GENOME_B200_PGRAPH=sharded.
+// The algorithm (functors + orchestration, the code compiled here) is also checked against the oracle on the CPU by
+// tests/test_sgraph_emul_cpu.py through a g++ backend; on the device by tests/test_sgraph_gpu.py (virtual ranks) and
+// tests/test_parity_multigpu.py (1, 2 and 8 ranks).  gb_pmap_graph_build runs this build by default (gb_tune pgraph_sharded;
+// 0 = the replicated build).
 #include <vector>
 
 #include "common.cuh"

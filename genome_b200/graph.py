@@ -265,7 +265,7 @@ class Graph:
         if k != kmersFreq.k:
             raise ValueError("k differs from the map's k")
         if isinstance(kmersFreq, PartitionedDNAMap):
-            raise ValueError("virtual shards run on a single-GPU map; a PartitionedDNAMap shards over its GPUs (GENOME_B200_PGRAPH=sharded)")
+            raise ValueError("virtual shards run on a single-GPU map; a PartitionedDNAMap shards over its own GPUs (Graph.buildGraph)")
         h = C.c_void_p()
         capi.check(capi.lib().gb_graph_build_virtual_shards(kmersFreq.h, int(n_shards), C.byref(h)))
         return MapGraph(h, k)

@@ -149,9 +149,9 @@ int gb_map_phase_ns(gb_map *m, int64_t ns[8]);
 /* Graph.buildGraph(k, kmersFreq) (Graph.scala:269-382) on the map's current contents */
 int gb_graph_build(gb_map *m, gb_graph **out);
 /* The SHARDED form of Graph.buildGraph (csrc/sgraph.cuh: the build gb_pmap_graph_build runs over the GPUs of a box when
- * GENOME_B200_PGRAPH=sharded) over n_shards VIRTUAL ranks on this map's one device: same result as gb_graph_build up to
- * node / edge numbering.  A diagnostic entry point: it exists so that the multi-GPU algorithm can be checked and profiled
- * on a single GPU.  1 <= n_shards <= 16.  EXPERIMENTAL this round (device test opt-in, tests/test_sgraph_gpu.py). */
+ * gb_tune pgraph_sharded = 1, the default) over n_shards VIRTUAL ranks on this map's one device: same result as gb_graph_build up
+ * to node / edge numbering.  A diagnostic entry point: it exists so that the multi-GPU algorithm can be checked and profiled
+ * on a single GPU (tests/test_sgraph_gpu.py).  1 <= n_shards <= 16. */
 int gb_graph_build_virtual_shards(gb_map *m, int n_shards, gb_graph **out);
 int gb_graph_destroy(gb_graph *g);
 /* getNodes.size, getEdges.size, getEdges.map(_.seq.length).sum (GraphBuilder.scala:39) */
@@ -166,7 +166,7 @@ int gb_graph_components(gb_graph *g, uint32_t *node_label, int64_t *n_components
  * ties (the norm: strand twins) go to the component holding the smallest node k-mer */
 int gb_graph_retain_largest(gb_graph *g);
 /* MapGraph.retain(nodesSet) (Graph.scala:161-165) for any node set: node_keep[n_nodes] (host), non-zero = keep; edges stay
- * when both ends stay.  (Written after this round's GPU budget was spent: device test opt-in.) */
+ * when both ends stay. */
 int gb_graph_retain(gb_graph *g, const uint8_t *node_keep);
 /* MapGraph.simplifyGraph (Graph.scala:211-230) */
 int gb_graph_simplify(gb_graph *g);

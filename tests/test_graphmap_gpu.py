@@ -47,8 +47,7 @@ def test_graph_positions_match_oracle(gpu, k, glen, rl, cov, err, rounds):
     assert mine == theirs
 
 
-# gb_graph_map_* was written after this round's GPU budget was spent: its logic is covered by the g++ emulation
-# (tests/test_walk_emul_cpu.py::test_graph_map_get_all_matches_oracle)
+# the logic of gb_graph_map_* is also covered on the CPU by the g++ emulation (tests/test_walk_emul_cpu.py::test_graph_map_get_all_matches_oracle)
 @pytest.mark.parametrize("k,glen,rl,cov,err,rounds", [(31, 20000, 100, 30, 0.01, 3), (15, 5000, 60, 30, 0.01, 2), (4, 120, 20, 6, 0.0, 1)])
 def test_graph_map_handle(gpu, k, glen, rl, cov, err, rounds):
     """GraphPositionMap.size / getAll / contains against the exported entry list: every entry is found under its k-mer, absent

@@ -1,6 +1,5 @@
 """The reference's driver scripts mirrored over the C ABI, end to end on the device: GraphBuilder.startup
-(S/scripts/GraphBuilder.scala:18-59) against the oracle.  Compositions of entry points that have their own parity tests; written
-after round 1's GPU budget was spent; first run on a B200 in round 2 (profiles/r2a_validate_1gpu.log)."""
+(S/scripts/GraphBuilder.scala:18-59) against the oracle.  Compositions of entry points that have their own parity tests."""
 import os
 
 import numpy as np

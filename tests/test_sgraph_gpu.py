@@ -1,7 +1,6 @@
 """The sharded Graph.buildGraph (csrc/sgraph.cuh) on the device: P virtual ranks on one GPU against the oracle and against
 the single-GPU build.  The same functors and orchestration pass tests/test_sgraph_emul_cpu.py through a g++ backend; these
-tests cover the CUDA backend (launches, atomics, scans, arena memory).  Written after this round's GPU budget was spent:
-first run on a B200 in round 2 (profiles/r2a_validate_1gpu.log)."""
+tests cover the CUDA backend (launches, atomics, scans, arena memory)."""
 import os
 
 import numpy as np
