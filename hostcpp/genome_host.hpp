@@ -5,15 +5,19 @@
 //   object FreqFilter      S/data/FreqFilter.scala:25-58     -> genome::FreqFilter::extractFilteredKmers
 //   object Graph / MapGraph S/data/graph/Graph.scala         -> genome::Graph::buildGraph, genome::MapGraph
 //   GraphSimplifier's pair loop and node sweep S/scripts/GraphSimplifier.scala:188-317 -> MapGraph::pairSupport / splitNodes
+//   MapGraph.write(file) / Graph(file)  Graph.scala:232-261,384-390 -> MapGraph::write / Graph::apply (kryo_graph.hpp)
 // Errors surface as genome::Error (the reference asserts / fails its Futures).  No CPU fallback exists.
 #pragma once
 #include <cstdint>
+#include <fstream>
+#include <iterator>
 #include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
 
 #include "../include/genome_b200.h"
+#include "kryo_graph.hpp"
 
 namespace genome {
 
@@ -33,11 +37,12 @@ struct Edge {
 
 class MapGraph {
   public:
-    explicit MapGraph(gb_graph *g) : g_(g) {}
+    explicit MapGraph(gb_graph *g, int k = 0) : g_(g), k_(k) {}
     MapGraph(const MapGraph &) = delete;
     MapGraph &operator=(const MapGraph &) = delete;
-    MapGraph(MapGraph &&o) noexcept : g_(o.g_) { o.g_ = nullptr; }
+    MapGraph(MapGraph &&o) noexcept : g_(o.g_), k_(o.k_) { o.g_ = nullptr; }
     ~MapGraph() { gb_graph_destroy(g_); }
+    int k() const { return k_; }
 
     std::vector<uint64_t> getNodes() const
     {
@@ -135,10 +140,27 @@ class MapGraph {
     void simplifyGraph() { check(gb_graph_simplify(g_)); }          // Graph.scala:211-230
     void removeBubbles() { check(gb_graph_remove_bubbles(g_)); }    // Graph.scala:125-149
     void removeEdges(const std::vector<uint32_t> &idx) { check(gb_graph_remove_edges(g_, idx.data(), (int64_t)idx.size())); }
+    // MapGraph.write(file) (Graph.scala:232-248): the Kryo `graph` file that GraphBuilder hands to GraphSimplifier
+    void write(const std::string &path) const
+    {
+        kryo::GraphArrays a;
+        a.k = k_;
+        a.nodeKmer = getNodes();
+        for (auto &e : getEdges()) {
+            a.edgeStart.push_back(e.start);
+            a.edgeEnd.push_back(e.end);
+            a.edgeSeq.push_back(std::move(e.seq));
+        }
+        const std::vector<uint8_t> bytes = kryo::write(a);
+        std::ofstream f(path, std::ios::binary);
+        f.write((const char *)bytes.data(), (std::streamsize)bytes.size());
+        if (!f) throw Error(GB_E_ARG, "cannot write " + path);
+    }
     gb_graph *handle() const { return g_; }
 
   private:
     gb_graph *g_;
+    int k_;
 };
 
 class DNAMap {
@@ -205,7 +227,33 @@ struct Graph {
         if (k != kmersFreq.k()) throw Error(GB_E_ARG, "k differs from the map's k");
         gb_graph *g = nullptr;
         check(gb_graph_build(kmersFreq.handle(), &g));
-        return MapGraph(g);
+        return MapGraph(g, k);
+    }
+    // Graph(file) (Graph.scala:384-390): the Kryo `graph` file into device memory -- the graph of an empty map, filled by the
+    // bulk addNode / addEdge of gb_graph_edit
+    static MapGraph apply(const std::string &path, int device = 0)
+    {
+        std::ifstream f(path, std::ios::binary);
+        if (!f) throw Error(GB_E_ARG, "cannot read " + path);
+        const std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        kryo::GraphArrays a;
+        try {
+            a = kryo::read(bytes);
+        } catch (const std::runtime_error &e) {
+            throw Error(GB_E_ARG, path + ": " + e.what());
+        }
+        if (a.nodeKmer.empty()) throw Error(GB_E_ARG, path + ": a graph file without nodes does not say its k");
+        std::vector<uint64_t> off(a.edgeSeq.size() + 1, 0);
+        std::vector<uint8_t> codes;
+        for (size_t e = 0; e < a.edgeSeq.size(); e++) {
+            codes.insert(codes.end(), a.edgeSeq[e].begin(), a.edgeSeq[e].end());
+            off[e + 1] = codes.size();
+        }
+        DNAMap empty(a.k, 0, device);
+        MapGraph g = buildGraph(a.k, empty);
+        check(gb_graph_edit(g.handle(), 0, nullptr, nullptr, nullptr, (int64_t)a.nodeKmer.size(), a.nodeKmer.data(), (int64_t)a.edgeStart.size(),
+                            a.edgeStart.data(), a.edgeEnd.data(), off.data(), codes.data(), 0, nullptr));
+        return g;
     }
     // the sharded form of buildGraph (csrc/sgraph.cuh) over nShards virtual ranks on the map's one device: the multi-GPU
     // algorithm on a single GPU, same graph up to node / edge numbering
@@ -214,7 +262,7 @@ struct Graph {
         if (k != kmersFreq.k()) throw Error(GB_E_ARG, "k differs from the map's k");
         gb_graph *g = nullptr;
         check(gb_graph_build_virtual_shards(kmersFreq.handle(), nShards, &g));
-        return MapGraph(g);
+        return MapGraph(g, k);
     }
 };
 

@@ -1,6 +1,7 @@
 // graph_builder.cpp -- GraphBuilder.startup (S/scripts/GraphBuilder.scala:18-59, relative to /root/reference) written
 // against the C++ host mirror: reads a `.bin` stream, counts, filters, builds, keeps the largest component, prints the
-// log lines the Scala driver prints.  Usage: graph_builder <reads.bin> <n_pairs> <k> [min_capacity]
+// log lines the Scala driver prints, writes the Kryo `graph` file when asked (GraphBuilder.scala:56).
+// Usage: graph_builder <reads.bin> <n_pairs> <k> [min_capacity [graph_out]]
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -11,7 +12,7 @@
 
 int main(int argc, char **argv)
 {
-    if (argc < 4) { std::fprintf(stderr, "usage: %s <reads.bin> <n_pairs> <k> [min_capacity]\n", argv[0]); return 2; }
+    if (argc < 4) { std::fprintf(stderr, "usage: %s <reads.bin> <n_pairs> <k> [min_capacity [graph_out]]\n", argv[0]); return 2; }
     try {
         std::ifstream f(argv[1], std::ios::binary);
         std::vector<uint8_t> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
@@ -36,6 +37,7 @@ int main(int argc, char **argv)
         for (auto &p : hist) std::printf(" (%lld,%lld)", (long long)p.first, (long long)p.second);
         std::printf("\nMax component size: %lld (of %lld components)\n", (long long)best, (long long)nc);
         graph.retainLargest();
+        if (argc > 5) graph.write(argv[5]);                        // graph.asInstanceOf[MapGraph].write(outfile), GraphBuilder.scala:56
         graph.simplifyGraph();
         std::printf("Graph nodes: %zu\n", graph.getNodes().size());
         std::printf("Node map: %zu\n", graph.getGraphMap().size()); // Graph.scala:117: nodeMap.size

@@ -1,8 +1,9 @@
 // graph_simplifier.cpp -- GraphBuilder.startup followed by GraphSimplifier.startup (S/scripts/GraphSimplifier.scala:138-357,
 // relative to /root/reference) against the C++ host mirror.  The reference passes the graph between the two scripts as a
-// Kryo file; that format is not reproduced, so this driver runs both stages in one process.
-// Usage: graph_simplifier <reads.bin> <n_pairs> <k> <cutoff> [range_first range_last [contigs_file]]
-// Compiled and link-checked in the CPU tests; not yet run on a GPU (its calls are the ones tests/test_walk_gpu.py makes).
+// Kryo file (Graph(infile), GraphSimplifier.scala:34): with `--graph <file>` as the first two arguments this driver reads the
+// file graph_builder wrote (then <k> is taken from the file and the argument is ignored); without, it runs both stages in
+// one process.
+// Usage: graph_simplifier [--graph <graph file>] <reads.bin> <n_pairs> <k> <cutoff> [range_first range_last [contigs_file]]
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -13,19 +14,30 @@
 
 int main(int argc, char **argv)
 {
-    if (argc < 5) { std::fprintf(stderr, "usage: %s <reads.bin> <n_pairs> <k> <cutoff> [range_first range_last [contigs]]\n", argv[0]); return 2; }
+    const char *graphFile = nullptr;
+    if (argc > 2 && std::string(argv[1]) == "--graph") {
+        graphFile = argv[2];
+        argv += 2;
+        argc -= 2;
+    }
+    if (argc < 5) { std::fprintf(stderr, "usage: %s [--graph <graph file>] <reads.bin> <n_pairs> <k> <cutoff> [range_first range_last [contigs]]\n", argv[0]); return 2; }
     try {
         std::ifstream f(argv[1], std::ios::binary);
         std::vector<uint8_t> bin((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
         const int64_t pairs = std::atoll(argv[2]);
-        const int k = std::atoi(argv[3]);
+        int k = std::atoi(argv[3]);
         const int cutoff = std::atoi(argv[4]);                    // genome.cutoff (application.conf:71)
         const int first = argc > 6 ? std::atoi(argv[5]) : 180;    // implicit val range = 180 to 250 (GraphSimplifier.scala:153)
         const int last = argc > 6 ? std::atoi(argv[6]) : 250;
-        genome::DNAMap kmersFreq(k);
-        genome::FreqFilter::extractFilteredKmers(kmersFreq, bin.data(), bin.size(), pairs, 3);
-        genome::MapGraph graph = genome::Graph::buildGraph(k, kmersFreq);
-        graph.retainLargest();                                     // GraphBuilder.scala:52-54
+        auto builderStage = [&]() {
+            genome::DNAMap kmersFreq(k);
+            genome::FreqFilter::extractFilteredKmers(kmersFreq, bin.data(), bin.size(), pairs, 3);
+            genome::MapGraph g = genome::Graph::buildGraph(k, kmersFreq);
+            g.retainLargest();                                     // GraphBuilder.scala:52-54
+            return g;
+        };
+        genome::MapGraph graph = graphFile ? genome::Graph::apply(graphFile) : builderStage();
+        if (graphFile) k = graph.k();                              // val k = graph.getNodes.head.seq.length (GraphSimplifier.scala:36)
         std::printf("K = %d\n", k);
         auto ps = graph.pairSupport(bin.data(), bin.size(), pairs, first, last);
         std::printf("Bad pairs: %lld\n", (long long)ps.badPairs);

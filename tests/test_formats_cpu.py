@@ -332,3 +332,45 @@ def test_kryo_graph_rejects_what_the_reference_cannot_have_written():
     with pytest.raises(ValueError, match="does not hold"):
         F.kryo_graph_arrays(nodes, [(1, 1, 7, edges[0][3])])
     assert F.kryo_graph_arrays([], [])[0] == 0
+
+
+def test_cpp_kryo_codec_reproduces_the_python_bytes(tmp_path):
+    """hostcpp/kryo_graph.hpp (MapGraph::write / Graph::apply of the C++ host mirror): decode + encode of the files formats.py
+    writes gives the same bytes, for every sequence class; malformed files are refused."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "kryo_codec")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-O1", "-fsanitize=address,undefined", "-o", exe,
+                        os.path.join(root, "tests", "emul", "kryo_codec_main.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rng = np.random.default_rng(77)
+    for k in (1, 5, 16, 31):
+        n_nodes = 6
+        node_kmer = rng.integers(0, 1 << (2 * k), n_nodes, dtype=np.uint64)
+        lens = [1, 2, 31, 32, 33, 63, 64, 65, 67, 68, 129, 1000]
+        es = np.array([i % n_nodes for i in range(len(lens))], np.uint32)      # <= 2 out-edges per node: give them distinct first bases
+        ee = rng.integers(0, n_nodes, len(lens)).astype(np.uint32)
+        seqs = [rng.integers(0, 4, ln).astype(np.uint8) for ln in lens]
+        for e in range(len(lens)):
+            seqs[e][0] = e // n_nodes
+        data = F.write_kryo_graph(k, node_kmer, es, ee, seqs)
+        src, dst = tmp_path / ("g%d.kryo" % k), tmp_path / ("g%d.out" % k)
+        src.write_bytes(data)
+        r = subprocess.run([exe, str(src), str(dst)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.strip() == "k=%d nodes=%d edges=%d" % (k, n_nodes, len(lens))
+        assert dst.read_bytes() == data
+        bad = tmp_path / "bad.kryo"
+        bad.write_bytes(data[:-3])
+        r = subprocess.run([exe, str(bad), str(dst)], capture_output=True, text=True)
+        assert r.returncode == 1 and "truncated" in r.stderr
+        bad.write_bytes(data + b"\x01")
+        r = subprocess.run([exe, str(bad), str(dst)], capture_output=True, text=True)
+        assert r.returncode == 1 and "after the graph" in r.stderr
+    # the hand-spelled stream of test_kryo_graph_bytes_of_a_two_node_graph
+    two = F.write_kryo_graph(2, [1 | 3 << 2, 3], [0], [1], [np.array([0], np.uint8)])
+    src = tmp_path / "two.kryo"
+    src.write_bytes(two)
+    r = subprocess.run([exe, str(src), str(tmp_path / "two.out")], capture_output=True, text=True)
+    assert r.returncode == 0 and (tmp_path / "two.out").read_bytes() == two
