@@ -331,3 +331,190 @@ def graph_positions(graph):
             seq = seq.drop(1).append(base)
             dist += 1
     return out
+
+
+# ---------------------------------------------------------------------------------------------- MapGraph.replaceStart / replaceEnd (197-209)
+def replace_start(graph, edge_id, new_start):
+    edge = graph.edges[edge_id]
+    graph.edges[edge.id] = Edge(edge.id, new_start.id, edge.end_id, edge.seq)
+    graph.nodes[edge.start_id].out_edge_ids.pop(edge.seq[0], None)
+    new_start.out_edge_ids[edge.seq[0]] = edge.id
+
+
+def replace_end(graph, edge_id, new_end):
+    edge = graph.edges[edge_id]
+    graph.edges[edge.id] = Edge(edge.id, edge.start_id, new_end.id, edge.seq)
+    old = graph.nodes[edge.end_id]
+    if edge.id in old.in_edge_ids:
+        old.in_edge_ids.remove(edge.id)
+    if edge.id not in new_end.in_edge_ids:
+        new_end.in_edge_ids.append(edge.id)
+
+
+# ---------------------------------------------------------------------------------------------- WalkingActor (S/scripts/GraphSimplifier.scala:33-127)
+class WalkingActor:
+    """Positions are ('node', id) or ('edge', id, dist) like NodeGraphPosition / EdgeGraphPosition."""
+
+    def __init__(self, graph, range_first, range_last):
+        self.graph, self.first, self.last = graph, range_first, range_last
+        self.cache = {}
+
+    def in_range(self, v):
+        return self.first <= v <= self.last
+
+    def reachable(self, node_id):                          # 42-72: Dijkstra backwards over in-edges, distances <= range.last
+        if node_id in self.cache:
+            return self.cache[node_id]
+        import heapq
+        g = self.graph
+        queue, seen = [(0, node_id)], {}
+        while queue:
+            dist, u = heapq.heappop(queue)                 # the ordering y._1 - x._1 makes the smallest distance the head
+            if u not in seen:
+                seen[u] = dist
+                for edge in g.in_edges(g.nodes[u]):
+                    d2 = dist + len(edge.seq)
+                    if d2 <= self.last:
+                        heapq.heappush(queue, (d2, edge.start_id))
+        if len(self.cache) < 50000:
+            self.cache[node_id] = seen
+        return seen
+
+    def receive(self, pos1, pos2):                         # 77-126: (good, pathEdges)
+        g = self.graph
+        path_edges = set()
+        if pos2[0] == "node":
+            node2, dist2 = pos2[1], 0
+        else:
+            node2, dist2 = g.edges[pos2[1]].start_id, pos2[2]
+        start_edge = g.edges[pos1[1]] if pos1[0] == "edge" else None
+        end_edge = g.edges[pos2[1]] if pos2[0] == "edge" else None
+        reach = self.reachable(node2)
+        memo = {}
+
+        def dfs(node1, dist1, prev_edge):
+            key = (prev_edge.id if prev_edge is not None else None, dist1)
+            if key in memo:
+                return memo[key]
+            if dist1 + dist2 + reach.get(node1, self.last + 1) > self.last:
+                return False
+            if node1 == node2 and self.in_range(dist1 + dist2):
+                if prev_edge is not None and end_edge is not None:
+                    path_edges.add((prev_edge.id, end_edge.id))
+                cur = True
+            else:
+                cur = False
+            for e in g.out_edges(g.nodes[node1]):
+                res = dfs(e.end_id, dist1 + len(e.seq), e)
+                if res and prev_edge is not None:
+                    path_edges.add((prev_edge.id, e.id))
+                cur |= res
+            memo[key] = cur
+            return cur
+
+        if pos1[0] == "node":
+            node0, dist0 = pos1[1], 0
+        else:
+            node0, dist0 = g.edges[pos1[1]].end_id, len(g.edges[pos1[1]].seq) - pos1[2]
+        import sys
+        old = sys.getrecursionlimit()
+        sys.setrecursionlimit(20000)
+        try:
+            good = dfs(node0, dist0, start_edge)
+        finally:
+            sys.setrecursionlimit(old)
+        return good, path_edges
+
+
+# ---------------------------------------------------------------------------------------------- GraphSimplifier.startup (138-357)
+def pair_support(graph, bin_bytes, count, k, range_first, range_last, take_first=None):
+    """The pair loop (188-263): returns (pathsMap {(e1 id, e2 id): count}, badPairs, walked orientation cases)."""
+    gmap = {}
+    for kmer, pos in graph_positions(graph):               # graphMap = graph.getGraphMap: putNew keeps every position of a k-mer
+        gmap.setdefault(kmer, []).append(pos)
+    actor = WalkingActor(graph, range_first, range_last)
+
+    def annotate(positions1, positions2):                  # 192-206
+        for p in positions1:
+            if p[0] == "edge":
+                for q in positions2:
+                    if q[0] == "edge" and p[1] == q[1] and range_first <= (q[2] - p[2]) + k <= range_last:
+                        return None
+        return positions1, positions2
+
+    paths, bad, walked = {}, 0, 0
+    pairs = read_pairs(bin_bytes, count)
+    if take_first is not None:
+        pairs = pairs[:take_first]
+    for p1, p2 in pairs:
+        if len(p1) < k or len(p2) < k:
+            continue
+        a, b = seq_from_codes(p1[:k]), seq_from_codes(p2[:k])
+        f1, f2 = gmap.get(a.long, []), gmap.get(b.rev_complement().long, [])
+        f3, f4 = gmap.get(b.long, []), gmap.get(a.rev_complement().long, [])
+        for l1, l2 in ((f1, f2), (f3, f4)):
+            if annotate(l1, l2) is None:
+                continue
+            todo = [(x, y) for x in l1 for y in l2]
+            if not todo:
+                continue                                   # `for (list <- Future.sequence(futures) if !list.isEmpty)`
+            walked += 1
+            results = [actor.receive(x, y) for x, y in todo]
+            good = any(r[0] for r in results)
+            path_edges = set().union(*[r[1] for r in results])
+            for es in path_edges:
+                paths[es] = paths.get(es, 0) + 1
+            if not good:
+                bad += 1
+    return paths, bad, walked
+
+
+def split_nodes(graph, paths, cutoff):
+    """The node sweep (266-317) without the simplifyGraph that follows: returns (edges removed, nodes added)."""
+    to_remove, added = set(), 0
+    for node in list(graph.nodes.values()):
+        in_, out = list(node.in_edge_ids), list(node.out_edge_ids.values())
+        if not in_ or not out:
+            continue
+        matrix = [[paths.get((i, j), 0) for j in out] for i in in_]
+        col_left, col_right = [False] * len(in_), [False] * len(out)
+
+        def dfs_left(i):
+            assert not col_left[i]
+            col_left[i] = True
+            l, r = {i}, set()
+            for j in range(len(out)):
+                if not col_right[j] and matrix[i][j] >= cutoff:
+                    l1, r1 = dfs_right(j)
+                    l |= l1
+                    r |= r1
+            return l, r
+
+        def dfs_right(j):
+            assert not col_right[j]
+            col_right[j] = True
+            l, r = set(), {j}
+            for i in range(len(in_)):
+                if not col_left[i] and matrix[i][j] >= cutoff:
+                    l1, r1 = dfs_left(i)
+                    l |= l1
+                    r |= r1
+            return l, r
+
+        for i in range(len(in_)):
+            if col_left[i]:
+                continue
+            l, r = dfs_left(i)
+            if not r:
+                to_remove.add(in_[i])
+            else:
+                new_node = graph.add_node(node.seq)
+                added += 1
+                for x in l:
+                    replace_end(graph, in_[x], new_node)
+                for x in r:
+                    replace_start(graph, out[x], new_node)
+        to_remove |= {out[j] for j in range(len(out)) if not col_right[j]}
+    for eid in to_remove:                                  # 320: toRemove.foreach(id => graph.removeEdge(graph.getEdge(id)))
+        graph.remove_edge(graph.edges[eid])
+    return len(to_remove), added

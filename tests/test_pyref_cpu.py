@@ -233,3 +233,81 @@ def test_remove_bubbles_on_fresh_graphs():
         pg.simplify_graph()
         assert list(pg.canonical()) == list(H.canon_oracle_graph(og)), (k, "bubbles + simplify")
     assert popped >= 4       # both strands of at least two of the bubbles
+
+
+# ---- GraphSimplifier (S/scripts/GraphSimplifier.scala): WalkingActor, the pair loop, the node sweep
+def _edge_forms(pg):
+    return {e.id: (pg.nodes[e.start_id].seq.long, pg.nodes[e.end_id].seq.long, bytes(e.seq)) for e in pg.edges.values()}
+
+
+def _oracle_edge_forms(og):
+    node_kmer, node_id, es, ee, off, bases = og.export()
+    by_id = {int(i): int(x) for i, x in zip(node_id, node_kmer)}
+    return {int(eid): (by_id[int(es[i])], by_id[int(ee[i])], bases[int(off[i]):int(off[i + 1])].tobytes()) for i, eid in enumerate(og.edge_ids())}
+
+
+@pytest.mark.parametrize("k,n,seed", [(5, 300, 1), (6, 600, 2), (4, 120, 4)])
+def test_walking_actor(k, n, seed):
+    """WalkingActor.receive of both restatements for random position pairs on a small-k tangle (ids differ: positions and
+    edge pairs are translated through the canonical form of their node / edge, which is unique in these graphs)."""
+    from tests.test_walk_cpu import kmers_of, rand_seq
+    om = kmers_of([rand_seq(n, seed)], k)
+    og = pyoracle.OracleGraph(om)
+    keys, vals = om.export()
+    pg = pyref.build_graph(k, {(int(x), k): int(v) for x, v in zip(keys, vals)})
+    oforms, pforms = _oracle_edge_forms(og), _edge_forms(pg)
+    assert len(set(oforms.values())) == len(oforms) and sorted(oforms.values()) == sorted(pforms.values())
+    p_edge = {form: eid for eid, form in pforms.items()}
+    p_node = {nd.seq.long: nid for nid, nd in pg.nodes.items()}
+    o_node = {int(i): int(x) for x, i in zip(og.export()[0], og.export()[1])}
+    kmer, ident, dist = og.graph_map()
+
+    def to_py(i):
+        return ("node", p_node[o_node[int(ident[i])]]) if dist[i] == 0 else ("edge", p_edge[oforms[int(ident[i])]], int(dist[i]))
+
+    actor = pyref.WalkingActor(pg, 6, 11)
+    rng = np.random.default_rng(seed)
+    n_good = 0
+    for _ in range(150):
+        i, j = rng.integers(0, kmer.size, 2)
+        good, pairs = og.walk((int(ident[i]), int(dist[i])), (int(ident[j]), int(dist[j])), 6, 11)
+        pgood, ppairs = actor.receive(to_py(i), to_py(j))
+        assert pgood == good
+        assert sorted((pforms[a], pforms[b]) for a, b in ppairs) == sorted((oforms[a], oforms[b]) for a, b in pairs)
+        n_good += good
+    assert n_good > 0
+
+
+@pytest.mark.parametrize("cutoff", [5, 10 ** 6])
+def test_pair_loop_and_node_sweep(cutoff):
+    """Two sequences sharing one k-mer (tests/test_walk_cpu.py): pathsMap, badPairs, the walked cases, the graph after the node
+    sweep and after simplifyGraph -- both restatements."""
+    from genome_b200 import synth
+    from tests.test_walk_cpu import reads_of, two_chromosomes
+    k, L = 15, 50
+    g1, g2 = two_chromosomes(k, 11)
+    reads = reads_of([g1, g2], L, 400, (60, 100), 21)
+    b = synth.pack_fixed(reads)
+    n = reads.shape[0]
+    om = pyoracle.OracleMap(k)
+    om.insert_reads(b, n)
+    om.delete_below(2)
+    og = pyoracle.OracleGraph(om)
+    kept = pyref.extract_filtered_kmers(b, n // 2, k, 2)
+    pg = pyref.build_graph(k, kept)
+    oforms, pforms = _oracle_edge_forms(og), _edge_forms(pg)
+    assert len(set(oforms.values())) == len(oforms) and sorted(oforms.values()) == sorted(pforms.values())
+    lo, hi = 90, 155
+    e1, e2, cnt, bad, walked = og.pair_support(b, n // 2, lo, hi)
+    paths, pbad, pwalked = pyref.pair_support(pg, b, n // 2, k, lo, hi)
+    assert (pbad, pwalked) == (bad, walked) and walked > 0
+    want = sorted((oforms[int(a)], oforms[int(c)], int(v)) for a, c, v in zip(e1, e2, cnt))
+    got = sorted((pforms[a], pforms[c], v) for (a, c), v in paths.items())
+    assert got == want and len(got) >= 4
+    removed, added = og.split(e1, e2, cnt, cutoff)
+    premoved, padded = pyref.split_nodes(pg, paths, cutoff)
+    assert (premoved, padded) == (removed, added)
+    assert list(pg.canonical()) == list(H.canon_oracle_graph(og))
+    og.simplify()
+    pg.simplify_graph()
+    assert list(pg.canonical()) == list(H.canon_oracle_graph(og))
