@@ -126,6 +126,20 @@ class ClockSampler:
                 "window": window}
 
 
+def graph_traffic(workload, scale, k, root=ROOT):
+    """DRAM bytes per build of the graph kernels from the committed ncu capture (profiles/graph_kernels_traffic.json), used only
+    when it was taken on this workload: {kernel: (bytes, launches, source)}.  Never fails the bench: anything odd -> {}."""
+    try:
+        with open(os.path.join(root, "profiles", "graph_kernels_traffic.json")) as f:
+            t = json.load(f)
+        if t.get("workload") != workload or t.get("scale") != scale or t.get("k") != k:
+            return {}
+        return {name: (float(v["dram_bytes_read"]) + float(v["dram_bytes_write"]), int(v.get("launches", 1)), v.get("source"))
+                for name, v in t.get("kernels", {}).items()}
+    except Exception:
+        return {}
+
+
 def canon_graph(node_kmer, es, ee, off, bases, node_id=None):
     """Sorted node k-mers and sorted edge multiset keyed by node k-mers (ids are not reproducible)."""
     if node_id is None:
@@ -540,11 +554,17 @@ def main():
                 roofline["traffic_over_algorithmic"] = roofline["traffic"] / algo_bytes
         if R.get("graph"):
             ph, gph, kept = R["phase"], R["graph_phase"], R["kept_total"]
+            gtraffic = graph_traffic(args.workload, args.scale, K)
             def entry(kernel, nbytes, ns_, note):
                 sec = ns_ * 1e-9
-                return {"kernel": kernel, "bound": "hbm", "algorithmic_bytes": nbytes, "ms": ns_ * 1e-6,
-                        "achieved": nbytes / sec / 1e9 if sec > 0 else None, "peak": peak, "unit": "GB/s",
-                        "frac": nbytes / sec / 1e9 / peak if sec > 0 else None, "note": note}
+                e = {"kernel": kernel, "bound": "hbm", "algorithmic_bytes": nbytes, "ms": ns_ * 1e-6,
+                     "achieved": nbytes / sec / 1e9 if sec > 0 else None, "peak": peak, "unit": "GB/s",
+                     "frac": nbytes / sec / 1e9 / peak if sec > 0 else None, "traffic": None, "note": note}
+                t = gtraffic.get(kernel.split(" ")[0])
+                if t and nbytes > 0:   # ncu: dram__bytes_read.sum + dram__bytes_write.sum of the kernel's launches in one build
+                    e["traffic"], e["traffic_launches"], e["traffic_source"] = t
+                    e["traffic_over_algorithmic"] = t[0] / nbytes
+                return e
             roofline_graph = [
                 entry("compact_survivors_kernel (deleteAll sweep)", 12.0 * ph["slots_swept"] + 12.0 * kept, ph["filter_sweep_ns"],
                       "12 B read per slot (key and count arrays; the vertex ids are not touched) + 12 B written per survivor"),

@@ -167,3 +167,20 @@ def test_ctypes_signatures_have_the_headers_arity():
         n = 0 if args.strip() in ("", "void") else len(args.split(","))
         if name in capi.SIGNATURES:
             assert len(capi.SIGNATURES[name][1]) == n, name
+
+
+def test_bench_reads_graph_kernel_traffic_only_for_its_workload():
+    """bench.py's roofline_graph entries take their DRAM traffic from the committed ncu capture, and only on the workload it
+    was taken on; a missing or odd file must not fail the bench."""
+    import importlib
+    old = sys.argv
+    sys.argv = ["bench.py"]
+    try:
+        bench = importlib.import_module("bench")
+    finally:
+        sys.argv = old
+    t = bench.graph_traffic("C2", 1.0, 31)
+    assert set(t) == {"masks_kernel", "jump_kernel"} and t["jump_kernel"][1] == 4
+    assert 1.0e9 < t["masks_kernel"][0] < 2.0e9
+    assert bench.graph_traffic("C2", 0.5, 31) == {} and bench.graph_traffic("C1", 1.0, 31) == {}
+    assert bench.graph_traffic("C2", 1.0, 31, root="/nonexistent") == {}
